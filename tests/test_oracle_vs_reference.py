@@ -1,0 +1,115 @@
+"""Pin of the CPU restatement (oracle/lbm_oracle.cpp) against the reference's own per-cell code.
+
+The reference build (oracle/_ref/libref_*.so) exists wherever oracle/Makefile could see /root/reference
+(this container; the built .so travels to the GPU box).  Strict IEEE builds on both sides, so the
+comparison is bit for bit: distributions, macroscopic fields, for every operator / equilibrium /
+precision / streaming pattern, over random maps that exercise every cell type (d3q27/bc.h:51-241,
+d2q9/bc.h:89-196).
+"""
+import numpy as np
+import pytest
+
+import lbm_cases as lc
+from oracle import oracle as O
+
+pytestmark = pytest.mark.skipif(
+    not (O.available("reference", O.AB) and O.available("reference", O.AA) and O.available("port")),
+    reason="oracle/_ref (reference build) or the port library is not built",
+)
+
+COMBOS_3D = [(O.CUM, O.EQ_INV_CUM), (O.CUM, O.EQ_STD), (O.SRT, O.EQ_STD), (O.SRT, O.EQ_INV_CUM), (O.BGK, O.EQ_STD), (O.MRT_LES, O.EQ_STD), (O.MRT_LES, O.EQ_INV_CUM)]
+
+
+def run_pair(d: O.Desc, m: np.ndarray, p: O.Params, nsteps: int, seed=11, noise=0.05):
+    out = []
+    for kind in ("reference", "port"):
+        orc = O.Oracle(d, kind)
+        a = lc.noisy_df(d, orc, seed=seed, noise=noise)
+        b = a.copy()
+        mac = d.new_macro()
+        p.stat_counter = 0
+        if d.macro != O.MACRO_VOID:
+            orc.initial_macro(p, a, mac)
+        for it in range(nsteps):
+            p.stat_counter = it
+            orc.step(p, a, b, mac, m, it, 1, 1)
+        out.append((a, b, mac))
+    return out
+
+
+def assert_same(ref, port, what):
+    for name, r, q in zip(("df_a", "df_b", "macro"), ref, port):
+        assert np.isfinite(r).all(), f"{what}: reference {name} not finite"
+        if not np.array_equal(r, q):
+            diff = np.abs(r.astype(np.float64) - q.astype(np.float64))
+            i = np.unravel_index(np.argmax(diff), diff.shape)
+            raise AssertionError(f"{what}: {name} differs, max |d|={diff.max():.3e} at {i}: ref={r[i]!r} port={q[i]!r}")
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+@pytest.mark.parametrize("coll,eq", COMBOS_3D)
+def test_d3q27_random_zoo(coll, eq, streaming, prec):
+    d = O.Desc(lattice=O.D3Q27, coll=coll, eq=eq, streaming=streaming, precision=prec, X=9, Y=8, Z=7)
+    m = lc.map_random_ab(d) if streaming == O.AB else lc.map_random_aa(d)
+    p = O.Params(lbmViscosity=0.013, fx=3e-5, fy=-2e-5, fz=1e-5, inflow_vx=0.04, inflow_vy=0.01, inflow_vz=-0.02)
+    ref, port = run_pair(d, m, p, nsteps=4)
+    assert_same(ref, port, f"coll={coll} eq={eq} st={streaming} prec={prec}")
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+@pytest.mark.parametrize("coll", [O.SRT, O.CLBM])
+def test_d2q9_random_zoo(coll, streaming, prec):
+    d = O.Desc(lattice=O.D2Q9, coll=coll, eq=O.EQ_STD, streaming=streaming, precision=prec, X=13, Y=11, Z=1)
+    m = lc.map_random_ab(d) if streaming == O.AB else lc.map_random_aa(d)
+    p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.05, inflow_vy=-0.01)
+    ref, port = run_pair(d, m, p, nsteps=4)
+    assert_same(ref, port, f"2d coll={coll} st={streaming} prec={prec}")
+
+
+@pytest.mark.parametrize("macro,inflow", [(O.MACRO_VOID, O.INFLOW_CONST), (O.MACRO_MEAN, O.INFLOW_CONST), (O.MACRO_DEFAULT, O.INFLOW_PROFILE_YZ), (O.MACRO_DEFAULT, O.INFLOW_NONE)])
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+def test_d3q27_cum_macro_and_inflow_flavours(macro, inflow, prec):
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, macro=macro, inflow=inflow, precision=prec, X=8, Y=7, Z=6)
+    m = lc.map_random_ab(d, seed=3)
+    rs = np.random.RandomState(5)
+    prof = (0.05 * rs.random_sample((d.Z, d.Y))).astype(d.dtype)
+    p = O.Params(lbmViscosity=0.004, fx=1e-5, inflow_vx=0.03, vx_profile=prof if inflow == O.INFLOW_PROFILE_YZ else None)
+    ref, port = run_pair(d, m, p, nsteps=5)
+    assert_same(ref, port, f"macro={macro} inflow={inflow} prec={prec}")
+
+
+@pytest.mark.parametrize("macro", [O.MACRO_VOID, O.MACRO_MEAN])
+def test_d2q9_macro_flavours(macro):
+    d = O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, macro=macro, X=10, Y=9, Z=1)
+    m = lc.map_random_ab(d, seed=4)
+    p = O.Params(lbmViscosity=0.01, fx=1e-5, inflow_vx=0.03)
+    ref, port = run_pair(d, m, p, nsteps=5)
+    assert_same(ref, port, f"2d macro={macro}")
+
+
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+def test_ghost_plane_rule(streaming):
+    """nproc>1 index rule with one ghost x-plane per side (kernels.h:21-29,39-48): no wrapping in x."""
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, X=6, Y=8, Z=8, ox=1, nproc=2)
+    m = lc.map_duct_periodic_x(d)
+    m[0], m[-1] = m[-2], m[1]  # ghost map planes = periodic neighbours
+    p = O.Params(lbmViscosity=0.01, fx=1e-5)
+    ref, port = run_pair(d, m, p, nsteps=2)
+    assert_same(ref, port, f"ghost st={streaming}")
+
+
+def test_long_run_smooth_box_stays_identical():
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AA, X=12, Y=12, Z=12)
+    m = lc.map_periodic(d)
+    p = O.Params(lbmViscosity=1e-3, fx=1e-6)
+    out = []
+    for kind in ("reference", "port"):
+        orc = O.Oracle(d, kind)
+        a = d.new_df()
+        orc.set_equilibrium_field(a, *lc.smooth_fields(d))
+        mac = d.new_macro()
+        orc.step(p, a, a, mac, m, 0, 200, 2)
+        out.append((a, a, mac))
+    assert_same(out[0], out[1], "200 steps A-A")
