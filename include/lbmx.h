@@ -1,0 +1,209 @@
+/* lbmx.h -- C ABI of the B200-native lattice-Boltzmann time-stepping engine (liblbmx.so).
+ *
+ * This is the drop-in boundary for the one hot path of TNL-LBM (buresjan/tnl-lbm): the fused
+ * collide-and-stream update over a uniform structure-of-arrays lattice.  The reference has no FFI of
+ * its own; its seam is the trivially-copyable `block.data` POD handed by value to cudaLBMKernel
+ * (include/lbm3d/lbm_data.h:7-131, launch site include/lbm3d/state.hpp:1034-1040) plus the
+ * LBM_BLOCK / LBM methods that prepare it.  Every entry point below names the reference interface
+ * it replaces (paths relative to the reference's include/lbm3d/ unless stated).
+ *
+ * Conventions: C linkage, opaque handle, plain pointers and sizes, `int` status (0 = LBMX_OK),
+ * lbmx_last_error() for the message of the last failure on the calling thread.  A handle is not
+ * thread-safe: one driver thread per engine (the reference drives one rank from one thread too).
+ * There is no CPU fallback: every call that needs the GPU fails with LBMX_ERR_CUDA without one.
+ *
+ * Host array layout at this boundary is the reference's (lbm_data.h:49-57, defs.h:85-86):
+ *     cell(x,y,z)   = (x*Z + z)*Y + y                     y fastest, then z, then x
+ *     df(q,x,y,z)   = q*XYZ + cell(x,y,z)                 structure of arrays over q
+ * for the LOCAL slab of this rank.  With `with_ghosts` = 1 the x extent is X_local + 2*ghost_x and
+ * plane 0 is the left ghost plane (the reference's storage including overlaps, as its checkpoints
+ * save it: checkpoint.h:58-101).
+ */
+#ifndef LBMX_H
+#define LBMX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBMX_VERSION 100
+
+enum lbmx_status { LBMX_OK = 0, LBMX_ERR_ARG = 1, LBMX_ERR_UNSUPPORTED = 2, LBMX_ERR_CUDA = 3, LBMX_ERR_NCCL = 4, LBMX_ERR_STATE = 5 };
+
+/* lattice / trait selectors: the template arguments of LBM_CONFIG (defs.h:169-250) as enums */
+enum lbmx_lattice { LBMX_D3Q27 = 0, LBMX_D2Q9 = 1, LBMX_D3Q19 = 2 /* no reference implementation: parity unpinned */ };
+enum lbmx_coll {
+	LBMX_COLL_CUM = 0,	   /* D3Q27_CUM      d3q27/col_cum.h:14-485 */
+	LBMX_COLL_SRT = 1,	   /* D3Q27_SRT      d3q27/col_srt.h:16-108   | D2Q9_SRT  d2q9/col_srt.h:16-44 */
+	LBMX_COLL_BGK = 2,	   /* D3Q27_BGK      d3q27/col_bgk.h:16-145 */
+	LBMX_COLL_MRT_LES = 3, /* D3Q27_MRT      d3q27/col_mrt.h:13-141 */
+	LBMX_COLL_CLBM = 4	   /* D2Q9_CLBM      d2q9/col_clbm.h:13-89 */
+};
+enum lbmx_eq { LBMX_EQ_STD = 0 /* D3Q27_EQ eq.h:8-130, D2Q9_EQ */, LBMX_EQ_INV_CUM = 1 /* D3Q27_EQ_INV_CUM eq_inv_cum.h:13-137 */ };
+enum lbmx_streaming { LBMX_STREAM_AB = 0 /* streaming_AB.h */, LBMX_STREAM_AA = 1 /* streaming_AA.h */ };
+enum lbmx_macro { LBMX_MACRO_VOID = 0, LBMX_MACRO_DEFAULT = 1, LBMX_MACRO_MEAN = 2 }; /* d3q27/macro.h:50-188, d2q9/macro.h */
+enum lbmx_inflow {
+	LBMX_INFLOW_NONE = 0,	  /* NSE_Data_NoInflow      lbm_data.h:117-131 */
+	LBMX_INFLOW_CONST = 1,	  /* NSE_Data_ConstInflow   lbm_data.h:98-115, NSE2D_Data_ConstInflow sim_2D/sim2d_1.cu:20-35 */
+	LBMX_INFLOW_PROFILE_YZ = 2 /* NSE_Data_XProfileInflow sim_NSE/sim_2.cu:16-33 */
+};
+enum lbmx_precision { LBMX_F32 = 0 /* TraitsSP */, LBMX_F64 = 1 /* TraitsDP */ }; /* defs.h:118-119 */
+
+/* when the per-cell macroscopic fields are written */
+enum lbmx_macro_policy {
+	LBMX_MACRO_EVERY_STEP = 0, /* as the reference: every step (d3q27/macro.h:64-71) */
+	LBMX_MACRO_LAST_STEP = 1,  /* only by the last step of each lbmx_step() batch: same values at every point where the
+								  host can observe them (the reference copies them out on output cadence only, state.hpp:1134-1142) */
+	LBMX_MACRO_NEVER = 2
+};
+
+typedef struct lbmx_desc
+{
+	int32_t lattice, coll, eq, streaming, macro, inflow, precision;
+	int32_t macro_policy;
+	int64_t X, Y, Z;  /* GLOBAL lattice size (D2Q9: Z = 1) */
+	int32_t rank;	  /* this process' x-slab ...                                       (lattice_decomposition.h:16-55) */
+	int32_t nranks;	  /* ... out of nranks contiguous x-slabs, one GPU each */
+	int32_t device;	  /* CUDA device ordinal, -1 = current */
+	int32_t ghost_x;  /* 1: one ghost x-plane per side and the reference's nproc>1 index rule (kernels.h:21-29,39-48);
+						 forced to 1 when nranks > 1; with nranks == 1 the exchange is a periodic self-exchange */
+	int32_t periodic_x; /* slab 0 and slab nranks-1 are neighbours (State ctor `periodic_lattice`, lattice_decomposition.h:148-162) */
+	int32_t reserved[3];
+} lbmx_desc;
+
+/* per-step scalars: the non-pointer members of block.data (lbm_data.h:12-30,87-115), set by
+ * State::updateKernelData (state.hpp:1314-1321) and the solver's updateKernelVelocities() */
+typedef struct lbmx_params
+{
+	double lbmViscosity;
+	double fx, fy, fz;
+	double inflow_vx, inflow_vy, inflow_vz;
+	int32_t stat_counter; /* MACRO_Mean sample index; lbmx_step(n>1) increments it per step */
+	int32_t reserved;
+} lbmx_params;
+
+typedef struct lbmx_layout
+{
+	int64_t X_local, Y, Z; /* slab size without ghost planes */
+	int64_t x_offset;	   /* global x of local plane 0 */
+	int64_t ghost_x;	   /* ghost planes per side */
+	int64_t XYZ;		   /* storage cells per component = (X_local + 2*ghost_x)*Y*Z */
+	int32_t Q, n_macro, sizeof_real, dfmax; /* dfmax: 2 for A-B, 1 for A-A (defs.h:40-63) */
+} lbmx_layout;
+
+/* raw device pointers mirroring block.data for code that wants them (checkpoint / writers): lbm_data.h:24-30 */
+typedef struct lbmx_ptrs
+{
+	void* dfs[2]; /* dfs[0] = df_cur, dfs[1] = df_out of the NEXT step (A-A: dfs[1] = NULL) */
+	void* dmacro;
+	int16_t* dmap;
+	int32_t even_iter;
+	int32_t reserved;
+} lbmx_ptrs;
+
+typedef struct lbmx_engine lbmx_engine;
+
+const char* lbmx_last_error(void);
+int lbmx_version(void);
+
+/* Host-only helpers (no GPU needed) -------------------------------------------------------------------------------------- */
+
+/* 1-D slab decomposition along x; replaces decomposeLattice_D1Q3 (lattice_decomposition.h:16-55) */
+int lbmx_decompose_x(int64_t X, int32_t nranks, int32_t rank, int64_t* x_offset, int64_t* x_local);
+
+/* Populations that cross an x-face: the +x movers go right, the -x movers go left (df_sync_directions, defs.h:309-340).
+ * Writes up to 9 direction indices into each list, returns the count. */
+int lbmx_halo_directions(int32_t lattice, int32_t* to_right, int32_t* to_left);
+
+/* One halo transfer of the exchange that follows the step at `iteration` (replaces LBM_BLOCK::startDrealArraySynchronization,
+ * lbm_block.hpp:410-451, and LBM::synchronizeDFsAndMacroDevice, lbm.hpp:196-280).  Planes are storage x indices of the local
+ * slab including ghosts (0 = left ghost, ghost_x .. ghost_x+X_local-1 = interior). */
+typedef struct lbmx_halo_msg
+{
+	int32_t to_right;	/* 1: goes to the right neighbour, 0: to the left neighbour */
+	int32_t n_dirs;		/* number of populations in dirs[] */
+	int32_t dirs[9];	/* population (q) indices, the same slot on both sides */
+	int64_t src_plane;	/* storage x-plane read on the sender */
+	int64_t dst_plane;	/* storage x-plane written on the receiver */
+} lbmx_halo_msg;
+int lbmx_halo_plan(int32_t lattice, int32_t streaming, int64_t iteration, int64_t X_local, lbmx_halo_msg msgs[2]);
+
+/* Engine life cycle ------------------------------------------------------------------------------------------------------ */
+
+/* replaces LBM ctor + LBM_BLOCK::allocateDeviceData (lbm.hpp:6-22, lbm_block.hpp:525-595) */
+int lbmx_create(const lbmx_desc* desc, lbmx_engine** out);
+int lbmx_destroy(lbmx_engine* e);
+int lbmx_get_layout(const lbmx_engine* e, lbmx_layout* out);
+
+/* Multi-GPU: rank 0 makes an id (128 bytes), the host distributes it (any broadcast the launcher offers), every rank joins.
+ * Replaces the MPI communicator of DistributedNDArraySynchronizer.  NCCL is bound at run time (dlopen "libnccl.so.2"). */
+int lbmx_comm_unique_id(void* id128);
+int lbmx_comm_init(lbmx_engine* e, const void* id128);
+
+/* State upload / download ------------------------------------------------------------------------------------------------- */
+
+/* LBM_BLOCK::copyMapToDevice (+ LBM::synchronizeMapDevice for the ghost planes): lbm_block.hpp:344-350,462-473.
+ * Also classifies the cells for the launch plan (bulk kernel vs. boundary list). */
+int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts);
+int lbmx_map_download(lbmx_engine* e, int16_t* host_map, int with_ghosts);
+
+/* LBM_BLOCK::setEquilibrium: every site incl. ghost planes, every DF copy (lbm_block.hpp:219-250) */
+int lbmx_df_set_equilibrium(lbmx_engine* e, double rho, double vx, double vy, double vz);
+/* per-cell variant (forLocalLatticeSites + setEquilibriumLat, common.h:126-158): double[X_local*Z*Y] fields, vz may be NULL */
+int lbmx_df_set_equilibrium_field(lbmx_engine* e, const double* rho, const double* vx, const double* vy, const double* vz);
+/* LBM_BLOCK::copyDFsToDevice / copyDFsToHost (lbm_block.hpp:352-376); host type = the engine's precision.
+ * which = 0: the array the next step reads (df_cur), 1: the other A-B copy. */
+int lbmx_df_upload(lbmx_engine* e, int which, const void* host_df, int with_ghosts);
+int lbmx_df_download(lbmx_engine* e, int which, void* host_df, int with_ghosts);
+/* fill the ghost planes of df_cur from the neighbours' boundary planes, all Q populations (SimInit's first
+ * synchronizeDFsAndMacroDevice(df_cur), state.hpp:966-972) */
+int lbmx_df_sync_ghosts(lbmx_engine* e);
+
+/* LBM_BLOCK::computeInitialMacro (lbm_block.hpp:252-277) */
+int lbmx_macro_init(lbmx_engine* e);
+/* LBM_BLOCK::copyMacroToHost / copyMacroToDevice (lbm_block.hpp:378-392): [n_macro][X_local*Z*Y] */
+int lbmx_macro_download(lbmx_engine* e, void* host_macro, int with_ghosts);
+int lbmx_macro_upload(lbmx_engine* e, const void* host_macro, int with_ghosts);
+
+int lbmx_set_params(lbmx_engine* e, const lbmx_params* p);
+/* NSE_Data_XProfileInflow::vx_profile (sim_NSE/sim_2.cu:16-33): real[size_y*size_z] in the engine's precision */
+int lbmx_set_inflow_profile(lbmx_engine* e, const void* host_profile, int64_t size_y, int64_t size_z);
+
+/* Time stepping ------------------------------------------------------------------------------------------------------------ */
+
+/* State::SimUpdate + LBM::updateKernelData (state.hpp:980-1145, lbm.hpp:314-330): advances `nsteps` iterations.
+ * Handles even/odd parity, the A-B pointer rotation, boundary-planes-first ordering and the halo exchange overlapped
+ * with the interior update.  Asynchronous: returns after enqueueing; lbmx_sync() waits. */
+int lbmx_step(lbmx_engine* e, int64_t nsteps);
+int lbmx_sync(lbmx_engine* e);
+/* same, bracketed by CUDA events on the engine's own compute stream; synchronises; elapsed device time in ms */
+int lbmx_step_timed(lbmx_engine* e, int64_t nsteps, float* elapsed_ms);
+
+int lbmx_get_iterations(const lbmx_engine* e, int64_t* it);
+int lbmx_set_iterations(lbmx_engine* e, int64_t it); /* checkpoint restore: parity travels with the raw arrays */
+
+/* the NaN scan of State::AfterSimUpdate (state.hpp:1166-1188): OR over rho != rho of the macro array */
+int lbmx_has_nan(lbmx_engine* e, int32_t* flag);
+
+/* escape hatch mirroring block.data (lbm_block.hpp:583-593) */
+int lbmx_get_device_ptrs(lbmx_engine* e, lbmx_ptrs* out);
+
+/* Introspection for the measurement harness -------------------------------------------------------------------------------- */
+typedef struct lbmx_stats
+{
+	int64_t kernel_launches;   /* kernels of this library launched since creation */
+	int64_t halo_bytes_sent;   /* bytes handed to NCCL / copied for the self-exchange */
+	int64_t boundary_cells;	   /* cells handled by the boundary-list kernel */
+	int64_t bulk_cells;		   /* cells handled by the bulk kernel */
+	int32_t bulk_regs, boundary_regs; /* registers per thread of the two step kernels (cudaFuncGetAttributes) */
+	int32_t bulk_block, reserved;
+} lbmx_stats;
+int lbmx_get_stats(lbmx_engine* e, lbmx_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBMX_H */

@@ -1,0 +1,147 @@
+"""Parity of the CUDA engine (called through the C ABI of include/lbmx.h) with the CPU oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): max relative error 1e-12 in fp64 and 1e-5 in fp32 on distributions and macroscopic
+fields; cell-type maps bit-exact.  Distributions are compared element-wise (they are strictly positive in every case here);
+velocities, which cross zero, relative to the field maximum.  The engine reorganises the arithmetic (one reciprocal instead
+of 32 divisions, pruned transforms, FMA), so equality to the last bit is not expected -- the oracle itself is bit-exact
+against the reference (tests/test_oracle_vs_reference.py, tests/test_oracle_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import lbm_cases as lc
+from engine_runner import engine_for, run_case_engine, set_params
+from oracle import oracle as O
+from tnl_lbm_b200 import binding as B
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = {O.F64: 1e-12, O.F32: 1e-5}
+
+
+def compare(case, df, mac, df_ref, mac_ref, tol, what):
+    assert np.isfinite(df).all(), what
+    e_df = lc.rel_err_elementwise(df, df_ref)
+    assert e_df <= tol, f"{what}: distributions rel err {e_df:.3e} > {tol}"
+    if case.desc.macro != O.MACRO_VOID:
+        for k in range(mac_ref.shape[0]):
+            e_m = lc.rel_err(mac[k], mac_ref[k])
+            assert e_m <= tol, f"{what}: macro[{k}] rel err {e_m:.3e} > {tol}"
+    return e_df
+
+
+@pytest.mark.parametrize("name", [c.name for c in gc.CASES])
+def test_engine_matches_oracle_and_golden(name):
+    case = gc.BY_NAME[name]
+    tol = TOL[case.desc.precision]
+    df, mac, stats = run_case_engine(case)
+    assert stats.kernel_launches > 0
+    # (1) the CPU restatement on the same inputs, full arrays
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=4)
+    compare(case, df, mac, df_ref, mac_ref, tol, name + " vs port")
+    # (2) the committed golden sample produced by the reference's own code
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    s = int(z["stride"])
+    compare(case, gc.sample(df, s), gc.sample(mac, s), z["df_sample"], z["macro_sample"], tol, name + " vs golden")
+
+
+@pytest.mark.parametrize("name", ["cum_f64_ab_zoo", "cum_f64_aa_zoo", "d2q9_srt_f64_ab_cavity"])
+def test_step_batching_is_invisible(name):
+    """lbmx_step(n) == n x lbmx_step(1): parity, pointer rotation and the LAST_STEP macro policy are consistent."""
+    case = gc.BY_NAME[name]
+    a_df, a_mac, _ = run_case_engine(case)
+    b_df, b_mac, _ = run_case_engine(case, chunk=1)
+    assert np.array_equal(a_df, b_df) and np.array_equal(a_mac, b_mac)
+    c_df, c_mac, _ = run_case_engine(case, macro_policy=B.MACRO_EVERY_STEP)
+    assert np.array_equal(a_df, c_df) and np.array_equal(a_mac, c_mac)
+
+
+def test_map_round_trip_is_bit_exact():
+    case = gc.BY_NAME["cum_f64_ab_zoo"]
+    m = case.make_map(case.desc)
+    with engine_for(case) as e:
+        e.map_upload(m)
+        assert np.array_equal(e.map_download(), m)
+        st = e.stats()
+        assert st.boundary_cells == int(np.sum((m != 0) & (m != 7)))
+        assert st.bulk_cells + st.boundary_cells == m.size
+
+
+def test_set_equilibrium_and_initial_macro_match_oracle():
+    for prec in (O.F64, O.F32):
+        d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, precision=prec, X=10, Y=9, Z=8)
+        case = gc.Case("tmp", d, O.Params(lbmViscosity=0.01, fx=1e-5), lc.map_periodic, 0, "smooth")
+        port = O.Oracle(d, "port")
+        ref = d.new_df()
+        fields = lc.smooth_fields(d)
+        port.set_equilibrium_field(ref, *fields)
+        mac_ref = d.new_macro()
+        port.initial_macro(case.params, ref, mac_ref)
+        with engine_for(case) as e:
+            e.map_upload(lc.map_periodic(d))
+            set_params(e, case.params)
+            e.set_equilibrium_field(*fields)
+            got = e.df_download(0)
+            assert lc.rel_err_elementwise(got, ref) <= (1e-14 if prec == O.F64 else 1e-6)
+            assert np.array_equal(e.df_download(1), got)  # every DF copy is initialised (lbm_block.hpp:247-249)
+            e.macro_init()
+            mac = e.macro_download()
+            for k in range(4):
+                assert lc.rel_err(mac[k], mac_ref[k]) <= (1e-14 if prec == O.F64 else 1e-6)
+            e.set_equilibrium(1.0, 0.01, -0.02, 0.03)
+            uni = d.new_df()
+            port.set_equilibrium(uni, 1.0, 0.01, -0.02, 0.03)
+            assert lc.rel_err_elementwise(e.df_download(0), uni) <= (1e-14 if prec == O.F64 else 1e-6)
+
+
+def test_nan_scan():
+    case = gc.BY_NAME["cum_f64_ab_box"]
+    d = case.desc
+    with engine_for(case) as e:
+        e.map_upload(lc.map_periodic(d))
+        e.set_equilibrium(1.0, 0, 0, 0)
+        set_params(e, case.params)
+        e.macro_init()
+        assert not e.has_nan()
+        bad = np.ones(e.df_shape(), dtype=e.dtype)
+        bad[3, 2, 2, 2] = np.nan
+        e.df_upload(bad, 0)
+        e.df_upload(bad, 1)
+        e.step(2)
+        assert e.has_nan()
+
+
+@pytest.mark.parametrize("streaming", [O.AA, O.AB])
+def test_1000_steps_cumulant_fp64_box(streaming):
+    """SURVEY §8d cfg 3 on a 32^3 copy: D3Q27 cumulant fp64, periodic box, smooth field + body force, 1000 steps."""
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, X=32, Y=32, Z=32)
+    case = gc.Case("box1000", d, O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 1000, "smooth")
+    df, mac, _ = run_case_engine(case)
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=os.cpu_count() or 4)
+    e = compare(case, df, mac, df_ref, mac_ref, 1e-12, f"1000 steps st={streaming}")
+    print(f"1000-step rel err (distributions) = {e:.3e}")
+
+
+def test_1000_steps_duct_with_walls_fp64():
+    """Body-force duct (sim_NSE/sim_2.cu:115-139 geometry, A-A-safe variant) -- walls, NOTHING shell, periodic x; 1000 steps."""
+    case0 = gc.BY_NAME["cum_f64_aa_duct"]
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AA, X=16, Y=20, Z=20)
+    case = gc.Case("duct1000", d, O.Params(lbmViscosity=5e-3, fx=1e-5), case0.make_map, 1000, "uniform")
+    df, mac, _ = run_case_engine(case)
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=os.cpu_count() or 4)
+    compare(case, df, mac, df_ref, mac_ref, 1e-12, "duct 1000 steps")
+
+
+def test_1000_steps_fp32_srt_and_d2q9():
+    for d, p, mk in [
+        (O.Desc(coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, precision=O.F32, X=24, Y=24, Z=24), O.Params(lbmViscosity=0.02, fx=1e-6), lc.map_periodic),
+        (O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, precision=O.F64, X=48, Y=48, Z=1), O.Params(lbmViscosity=0.05, inflow_vx=0.1), lc.map_cavity_2d),
+    ]:
+        case = gc.Case("long", d, p, mk, 1000, "smooth" if mk is lc.map_periodic else "uniform")
+        df, mac, _ = run_case_engine(case)
+        df_ref, mac_ref = gc.run_case(case, "port", nthreads=os.cpu_count() or 4)
+        compare(case, df, mac, df_ref, mac_ref, TOL[d.precision], f"1000 steps {d}")

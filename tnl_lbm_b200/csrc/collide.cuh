@@ -1,0 +1,502 @@
+// collide.cuh -- per-cell arithmetic of the hot path, written for registers on sm_100a.
+//
+// Everything here works on one cell's populations held in registers (f[Q], fully unrolled, compile-time direction
+// tables).  The operators compute what the reference's trait classes compute (cited per function, paths relative to
+// the reference's include/lbm3d/), but are organised for the GPU: the moment transforms are pruned to the moments the
+// default cumulant build actually relaxes, all divisions by rho collapse into one reciprocal, products with the
+// compile-time zeros/ones of the reference are dropped, and FMA contraction is allowed.  Agreement with the reference
+// is therefore to rounding (<= 1e-12 relative in fp64 over 1000 steps, tests/test_gpu_parity.py), not bit-for-bit.
+#pragma once
+#include "lattice.cuh"
+
+namespace lbmx {
+
+template <typename R>
+struct Phys
+{
+	R nu;		  // lbmViscosity (KS.lbmViscosity)
+	R fx, fy, fz; // homogeneous body force (NSE_Data, lbm_data.h:87-96)
+};
+
+// --------------------------------------------------------------------------------------------------------------------
+// density / velocity: COMMON::computeDensityAndVelocity (d3q27/common.h:16-50, d2q9/common.h:16-36).
+// The sums are organised as the z-column sums the cumulant transform needs anyway (the compiler merges them); the
+// association differs from the reference's tree, i.e. agreement to a few ulp.
+// --------------------------------------------------------------------------------------------------------------------
+template <typename R>
+LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
+{
+	using L = D3Q27;
+	R k0[3][3], d[3][3];
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++) {
+			const R fm = f[L::find(a - 1, b - 1, -1)], f0 = f[L::find(a - 1, b - 1, 0)], fp = f[L::find(a - 1, b - 1, 1)];
+			k0[a][b] = (fp + fm) + f0;
+			d[a][b] = fp - fm;
+		}
+	R A[3], By[3], Dz[3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		A[a] = (k0[a][2] + k0[a][0]) + k0[a][1];
+		By[a] = k0[a][2] - k0[a][0];
+		Dz[a] = (d[a][2] + d[a][0]) + d[a][1];
+	}
+	rho = (A[2] + A[0]) + A[1];
+	const R jx = A[2] - A[0];
+	const R jy = (By[2] + By[0]) + By[1];
+	const R jz = (Dz[2] + Dz[0]) + Dz[1];
+	const R ir = R(1) / rho;
+	vx = (jx + R(0.5) * P.fx) * ir;
+	vy = (jy + R(0.5) * P.fy) * ir;
+	vz = (jz + R(0.5) * P.fz) * ir;
+}
+
+template <typename R>
+LBMX_D void density_velocity(const R (&f)[9], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
+{
+	using L = D2Q9;
+	R k0[3], dy[3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R fm = f[L::find(a - 1, -1)], f0 = f[L::find(a - 1, 0)], fp = f[L::find(a - 1, 1)];
+		k0[a] = (fp + fm) + f0;
+		dy[a] = fp - fm;
+	}
+	rho = (k0[2] + k0[0]) + k0[1];
+	const R ir = R(1) / rho;
+	vx = ((k0[2] - k0[0]) + R(0.5) * P.fx) * ir;
+	vy = (((dy[2] + dy[0]) + dy[1]) + R(0.5) * P.fy) * ir;
+	vz = R(0);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// equilibria: D3Q27_EQ (d3q27/eq.h:13-130), D3Q27_EQ_INV_CUM (d3q27/eq_inv_cum.h:24-136), D2Q9_EQ (d2q9/eq.h:13-61)
+// --------------------------------------------------------------------------------------------------------------------
+template <typename R>
+LBMX_HD constexpr R w27(int q)
+{
+	const int n = (D3Q27::cx(q) != 0) + (D3Q27::cy(q) != 0) + (D3Q27::cz(q) != 0);
+	return n == 0 ? R(8.0 / 27.0) : n == 1 ? R(2.0 / 27.0) : n == 2 ? R(1.0 / 54.0) : R(1.0 / 216.0);
+}
+template <typename R>
+LBMX_HD constexpr R w9(int q)
+{
+	const int n = (D2Q9::cx(q) != 0) + (D2Q9::cy(q) != 0);
+	return n == 0 ? R(4.0 / 9.0) : n == 1 ? R(1.0 / 9.0) : R(1.0 / 36.0);
+}
+
+// all Q equilibrium populations at once (the per-axis factors are shared between directions)
+template <typename R>
+LBMX_D void equilibrium(R (&feq)[27], int eqkind, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	if (eqkind == 1) {	// product form +-w' rho gx gy gz with g(0) = 3v^2-2, g(+-1) = 3v^2 +- 3v + 1
+		const R v[3] = {vx, vy, vz};
+		R g[3][3];
+#pragma unroll
+		for (int a = 0; a < 3; a++) {
+			const R t = R(3) * v[a] * v[a];
+			g[a][1] = t - R(2);
+			g[a][2] = (t + R(3) * v[a]) + R(1);
+			g[a][0] = (t - R(3) * v[a]) + R(1);
+		}
+		static_for<27>([&](auto qc) {
+			constexpr int q = qc;
+			constexpr int n = (L::cx(q) != 0) + (L::cy(q) != 0) + (L::cz(q) != 0);
+			constexpr R w = n == 0 ? -R(1.0 / 27.0) : n == 1 ? R(1.0 / 54.0) : n == 2 ? -R(1.0 / 108.0) : R(1.0 / 216.0);
+			feq[q] = (w * rho) * ((g[0][L::cx(q) + 1] * g[1][L::cy(q) + 1]) * g[2][L::cz(q) + 1]);
+		});
+	}
+	else {	// second-order polynomial w rho (1 - 3/2 u.u + 3 c.u + 9/2 (c.u)^2)
+		const R base = R(1) - R(1.5) * ((vx * vx + vy * vy) + vz * vz);
+		static_for<27>([&](auto qc) {
+			constexpr int q = qc;
+			const R cu = (R(L::cx(q)) * vx + R(L::cy(q)) * vy) + R(L::cz(q)) * vz;
+			feq[q] = (w27<R>(q) * rho) * ((base + R(3) * cu) + (R(4.5) * cu) * cu);
+		});
+	}
+}
+
+template <typename R>
+LBMX_D void equilibrium(R (&feq)[9], int, R rho, R vx, R vy, R)
+{
+	using L = D2Q9;
+	const R base = R(1) - R(1.5) * (vx * vx + vy * vy);
+	static_for<9>([&](auto qc) {
+		constexpr int q = qc;
+		const R cu = R(L::cx(q)) * vx + R(L::cy(q)) * vy;
+		feq[q] = (w9<R>(q) * rho) * ((base + R(3) * cu) + (R(4.5) * cu) * cu);
+	});
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// D3Q27 cumulant collision, default build of the reference (d3q27/col_cum.h:14-485 with omega2..omega10 = 1, A = B = 0,
+// no antialias terms, col_cum.h:208-247).
+//
+// With every rate but omega1 equal to one, all cumulants of order >= 3 relax to zero, so of the forward transform only
+// the ten moments of order <= 2 are needed (col_cum.h:52-148 pruned): 102 instead of 162 operations.  The backward
+// chain (col_cum.h:312-445) is kept complete, with the identically-zero inputs removed from the first (x) level.
+// `rho`, `v*` are the pre-collision density and (half-force shifted) velocity the caller computed or imposed.
+// --------------------------------------------------------------------------------------------------------------------
+template <bool Z0, bool Z1, bool Z2, typename R>
+LBMX_D void back3(R k0, R k1, R k2, const R (&c)[6], R& fm, R& f0, R& fp)
+{
+	// c = {1-v^2, -2v, (v^2-v)/2, v-1/2, (v^2+v)/2, v+1/2}; Eq G2015(88)-(96), zero inputs elided at compile time
+	R z = R(0), m = R(0), p = R(0);
+	if constexpr (! Z2) {
+		z = -k2;
+		m = R(0.5) * k2;
+		p = m;
+	}
+	if constexpr (! Z1) {
+		z = c[1] * k1 + z;
+		m = c[3] * k1 + m;
+		p = c[5] * k1 + p;
+	}
+	if constexpr (! Z0) {
+		z = c[0] * k0 + z;
+		m = c[2] * k0 + m;
+		p = c[4] * k0 + p;
+	}
+	f0 = z;
+	fm = m;
+	fp = p;
+}
+
+template <typename R>
+LBMX_D void back_coeffs(R v, R (&c)[6])
+{
+	const R v2 = v * v;
+	c[0] = R(1) - v2;
+	c[1] = R(-2) * v;
+	c[2] = R(0.5) * (v2 - v);
+	c[3] = v - R(0.5);
+	c[4] = R(0.5) * (v2 + v);
+	c[5] = v + R(0.5);
+}
+
+template <typename R>
+LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	// ---- forward, z: per (x,y) column, orders 0..2 (Eq 6-8)
+	R z0[3][3], z1[3][3], z2[3][3];
+	{
+		const R vv = vz * vz, m2v = R(-2) * vz;
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+#pragma unroll
+			for (int b = 0; b < 3; b++) {
+				const R fm = f[L::find(a - 1, b - 1, -1)], f0 = f[L::find(a - 1, b - 1, 0)], fp = f[L::find(a - 1, b - 1, 1)];
+				const R s = fp + fm, d = fp - fm;
+				const R k0 = s + f0;
+				z0[a][b] = k0;
+				z1[a][b] = d - vz * k0;
+				z2[a][b] = (s + m2v * d) + vv * k0;
+			}
+	}
+	// ---- forward, y: only beta + gamma <= 2 (Eq 9-11)
+	R y00[3], y10[3], y20[3], y01[3], y11[3], y02[3];
+	{
+		const R vv = vy * vy, m2v = R(-2) * vy;
+#pragma unroll
+		for (int a = 0; a < 3; a++) {
+			{
+				const R s = z0[a][2] + z0[a][0], d = z0[a][2] - z0[a][0];
+				const R k0 = s + z0[a][1];
+				y00[a] = k0;
+				y10[a] = d - vy * k0;
+				y20[a] = (s + m2v * d) + vv * k0;
+			}
+			{
+				const R s = z1[a][2] + z1[a][0], d = z1[a][2] - z1[a][0];
+				const R k0 = s + z1[a][1];
+				y01[a] = k0;
+				y11[a] = d - vy * k0;
+			}
+			y02[a] = (z2[a][2] + z2[a][0]) + z2[a][1];
+		}
+	}
+	// ---- forward, x: alpha + beta + gamma <= 2 (Eq 12-14)
+	R k000, k100, k200, k010, k110, k001, k101, k020, k002, k011;
+	{
+		const R vv = vx * vx, m2v = R(-2) * vx;
+		{
+			const R s = y00[2] + y00[0], d = y00[2] - y00[0];
+			k000 = s + y00[1];
+			k100 = d - vx * k000;
+			k200 = (s + m2v * d) + vv * k000;
+		}
+		{
+			const R s = y10[2] + y10[0], d = y10[2] - y10[0];
+			k010 = s + y10[1];
+			k110 = d - vx * k010;
+		}
+		{
+			const R s = y01[2] + y01[0], d = y01[2] - y01[0];
+			k001 = s + y01[1];
+			k101 = d - vx * k001;
+		}
+		k020 = (y20[2] + y20[0]) + y20[1];
+		k002 = (y02[2] + y02[0]) + y02[1];
+		k011 = (y11[2] + y11[0]) + y11[1];
+	}
+	// ---- relaxation (col_cum.h:175,223-256): second order with omega1, trace with omega2 = 1, first order sign flip
+	const R omega1 = R(1) / (R(3) * P.nu + R(0.5));
+	const R keep = R(1) - omega1;
+	const R s110 = keep * k110, s101 = keep * k101, s011 = keep * k011;
+	const R r33 = keep * (k200 - k020), r34 = keep * (k200 - k002), r35 = k000;
+	const R third = R(1.0 / 3.0);
+	const R s200 = third * ((r33 + r34) + r35);
+	const R s020 = third * ((r34 - R(2) * r33) + r35);
+	const R s002 = third * ((r33 - R(2) * r34) + r35);
+	const R s100 = -k100, s010 = -k010, s001 = -k001;  // col_cum.h:341-345
+	// ---- cumulants -> central moments, orders 4..6 (Eq G2015(81)-(84), col_cum.h:312-338); all third-order and
+	//      fifth-order post-collision cumulants vanish, which removes S_12x-type moments altogether
+	const R ir = R(1) / rho;
+	const R s211 = (s200 * s011 + R(2) * s101 * s110) * ir;
+	const R s121 = (s020 * s101 + R(2) * s110 * s011) * ir;
+	const R s112 = (s002 * s110 + R(2) * s011 * s101) * ir;
+	const R s220 = (s020 * s200 + R(2) * s110 * s110) * ir;
+	const R s022 = (s002 * s020 + R(2) * s011 * s011) * ir;
+	const R s202 = (s200 * s002 + R(2) * s101 * s101) * ir;
+	const R s222 = (((s200 * s022 + s020 * s202) + s002 * s220) + R(4) * ((s011 * s211 + s101 * s121) + s110 * s112)) * ir
+				 - ((R(16) * s110 * s101 * s011 + R(4) * ((s101 * s101 * s020 + s011 * s011 * s200) + s110 * s110 * s002)) + R(2) * s200 * s020 * s002)
+					   * (ir * ir);
+	// ---- backward, x (Eq 88-90): x[a][beta][gamma]
+	R cx_[6], cy_[6], cz_[6];
+	back_coeffs(vx, cx_);
+	back_coeffs(vy, cy_);
+	back_coeffs(vz, cz_);
+	R x[3][3][3];
+	back3<false, false, false>(k000, s100, s200, cx_, x[0][0][0], x[1][0][0], x[2][0][0]);
+	back3<false, false, true>(s001, s101, R(0), cx_, x[0][0][1], x[1][0][1], x[2][0][1]);
+	back3<false, true, false>(s002, R(0), s202, cx_, x[0][0][2], x[1][0][2], x[2][0][2]);
+	back3<false, false, true>(s010, s110, R(0), cx_, x[0][1][0], x[1][1][0], x[2][1][0]);
+	back3<false, true, false>(s011, R(0), s211, cx_, x[0][1][1], x[1][1][1], x[2][1][1]);
+	back3<true, false, true>(R(0), s112, R(0), cx_, x[0][1][2], x[1][1][2], x[2][1][2]);
+	back3<false, true, false>(s020, R(0), s220, cx_, x[0][2][0], x[1][2][0], x[2][2][0]);
+	back3<true, false, true>(R(0), s121, R(0), cx_, x[0][2][1], x[1][2][1], x[2][2][1]);
+	back3<false, true, false>(s022, R(0), s222, cx_, x[0][2][2], x[1][2][2], x[2][2][2]);
+	// ---- backward, y (Eq 91-93) then z (Eq 94-96)
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		R yb[3][3];	 // [b][gamma]
+#pragma unroll
+		for (int g = 0; g < 3; g++)
+			back3<false, false, false>(x[a][0][g], x[a][1][g], x[a][2][g], cy_, yb[0][g], yb[1][g], yb[2][g]);
+#pragma unroll
+		for (int b = 0; b < 3; b++) {
+			R fm, f0, fp;
+			back3<false, false, false>(yb[b][0], yb[b][1], yb[b][2], cz_, fm, f0, fp);
+			f[L::find(a - 1, b - 1, -1)] = fm;
+			f[L::find(a - 1, b - 1, 0)] = f0;
+			f[L::find(a - 1, b - 1, 1)] = fp;
+		}
+	}
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// D3Q27 SRT (col_srt.h:16-108), BGK (col_bgk.h:16-145, no Galilean correction), MRT_LES (col_mrt.h:13-141)
+// --------------------------------------------------------------------------------------------------------------------
+template <typename R>
+LBMX_D void collide_srt(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R tau = R(3) * P.nu + R(0.5);
+	const R itau = R(1) / tau;
+	const R iRho = R(1) / (rho == R(0) ? R(1) : rho);
+	const R pre = (R(1) - R(0.5) * itau) * (R(3) * iRho);
+	// (c - u).F per axis and sign
+	const R tx[3] = {(-vx - R(1)) * P.fx, -vx * P.fx, (-vx + R(1)) * P.fx};
+	const R ty[3] = {(-vy - R(1)) * P.fy, -vy * P.fy, (-vy + R(1)) * P.fy};
+	const R tz[3] = {(-vz - R(1)) * P.fz, -vz * P.fz, (-vz + R(1)) * P.fz};
+	R feq[27];
+	equilibrium(feq, eqkind, rho, vx, vy, vz);
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		const R S = (tx[L::cx(q) + 1] + ty[L::cy(q) + 1]) + tz[L::cz(q) + 1];
+		f[q] = f[q] + ((feq[q] - f[q]) * itau + (pre * S) * feq[q]);
+	});
+}
+
+template <typename R>
+LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R omega1 = R(1) / (R(3) * P.nu + R(0.5));
+	const R pre = (R(1) - R(0.5) * omega1) * (R(3) / rho);
+	const R v[3] = {vx, vy, vz};
+	R g[3][3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R z = (R(1.0 / 3.0) - R(1)) + v[a] * v[a];
+		const R p = R(-0.5) * ((z + R(1)) + v[a]);
+		g[a][1] = z;
+		g[a][2] = p;
+		g[a][0] = p + v[a];
+	}
+	const R tx[3] = {(-vx - R(1)) * P.fx, -vx * P.fx, (-vx + R(1)) * P.fx};
+	const R ty[3] = {(-vy - R(1)) * P.fy, -vy * P.fy, (-vy + R(1)) * P.fy};
+	const R tz[3] = {(-vz - R(1)) * P.fz, -vz * P.fz, (-vz + R(1)) * P.fz};
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		const R feq = ((-rho * g[0][L::cx(q) + 1]) * g[1][L::cy(q) + 1]) * g[2][L::cz(q) + 1];
+		const R S = (tx[L::cx(q) + 1] + ty[L::cy(q) + 1]) + tz[L::cz(q) + 1];
+		f[q] = f[q] + ((feq - f[q]) * omega1 + (pre * S) * feq);
+	});
+}
+
+template <typename R>
+LBMX_D void collide_mrt(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	// raw second moments from the z-column sums
+	R Pxx = 0, Pyy = 0, Pzz = 0, Pxy = 0, Pxz = 0, Pyz = 0;
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++) {
+			const R fm = f[L::find(a - 1, b - 1, -1)], f0 = f[L::find(a - 1, b - 1, 0)], fp = f[L::find(a - 1, b - 1, 1)];
+			const R s = fp + fm, d = fp - fm, k0 = s + f0;
+			Pzz += s;
+			if (a != 1)
+				Pxx += k0;
+			if (b != 1)
+				Pyy += k0;
+			if (a != 1 && b != 1)
+				Pxy += R((a - 1) * (b - 1)) * k0;
+			if (a != 1)
+				Pxz += R(a - 1) * d;
+			if (b != 1)
+				Pyz += R(b - 1) * d;
+		}
+	const R Nxx = Pxx - rho * (R(1.0 / 3.0) + vx * vx);
+	const R Nyy = Pyy - rho * (R(1.0 / 3.0) + vy * vy);
+	const R Nzz = Pzz - rho * (R(1.0 / 3.0) + vz * vz);
+	const R Nxy = Pxy - rho * vx * vy;
+	const R Nxz = Pxz - rho * vx * vz;
+	const R Nyz = Pyz - rho * vy * vz;
+	const R Qn = R(2) * (((Nxx * Nxx + Nyy * Nyy) + Nzz * Nzz) + R(2) * ((Nxy * Nxy + Nxz * Nxz) + Nyz * Nyz));
+	const R tau = R(3) * P.nu + R(0.5);
+	const R Csm = R(0.0342);
+	const R omega = R(2) / (sqrt(tau * tau + (R(2) * Csm * R(9)) * sqrt(Qn) / rho) + tau);	 // Smagorinsky rate
+	Pxx -= omega * Nxx;
+	Pyy -= omega * Nyy;
+	Pzz -= omega * Nzz;
+	Pxy -= omega * Nxy;
+	Pxz -= omega * Nxz;
+	Pyz -= omega * Nyz;
+	const R tr = R(1.5) * ((Pxx + Pyy) + Pzz);
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int a = L::cx(q), b = L::cy(q), c = L::cz(q);
+		constexpr int n = (a != 0) + (b != 0) + (c != 0);
+		const R lin = rho * ((R(2.5) - R(1.5) * R(n)) + R(3) * ((vx * R(a) + vy * R(b)) + vz * R(c)));
+		const R quad = ((Pxx * R(a * a) + Pyy * R(b * b)) + Pzz * R(c * c)) + R(2) * ((Pxy * R(a * b) + Pxz * R(a * c)) + Pyz * R(b * c));
+		f[q] = w27<R>(q) * ((lin + R(4.5) * quad) - tr);
+	});
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// D2Q9 SRT (d2q9/col_srt.h:16-44) and cascaded CLBM (d2q9/col_clbm.h:13-89)
+// --------------------------------------------------------------------------------------------------------------------
+template <typename R>
+LBMX_D void collide_srt(R (&f)[9], const Phys<R>& P, int, R rho, R vx, R vy, R)
+{
+	using L = D2Q9;
+	const R tau = R(3) * P.nu + R(0.5);
+	const R itau = R(1) / tau;
+	const R pre = R(1) - R(0.5) * itau;
+	const R fx = P.fx, fy = P.fy;
+	R F[9];
+	F[L::find(0, 0)] = pre * R(4) / R(9) * (R(3) * (-vx * fx - vy * fy));
+	F[L::find(1, 0)] = pre / R(9) * (R(3) * ((R(1) - vx) * fx - vy * fy) + R(9) * vx * fx);
+	F[L::find(-1, 0)] = pre / R(9) * (R(3) * ((R(-1) - vx) * fx - vy * fy) + R(9) * vx * fx);
+	F[L::find(0, 1)] = pre / R(9) * (R(3) * (-vx * fx + (R(1) - vy) * fy) + R(9) * vy * fy);
+	F[L::find(0, -1)] = pre / R(9) * (R(3) * (-vx * fx + (R(-1) - vy) * fy) + R(9) * vy * fy);
+	F[L::find(1, 1)] = pre / R(36) * (R(3) * ((R(1) - vx) * fx + (R(1) - vy) * fy) + R(9) * (vx + vy) * (fx + fy));
+	F[L::find(-1, -1)] = pre / R(36) * (R(3) * ((R(-1) - vx) * fx + (R(-1) - vy) * fy) + R(9) * (vx + vy) * (fx + fy));
+	F[L::find(1, -1)] = pre / R(36) * (R(3) * ((R(1) - vx) * fx + (R(-1) - vy) * fy) + R(9) * (vx - vy) * (fx - fy));
+	F[L::find(-1, 1)] = pre / R(36) * (R(3) * ((R(-1) - vx) * fx + (R(1) - vy) * fy) + R(9) * (vx - vy) * (fx - fy));
+	R feq[9];
+	equilibrium(feq, 0, rho, vx, vy, R(0));
+	static_for<9>([&](auto qc) {
+		constexpr int q = qc;
+		f[q] = f[q] + ((feq[q] - f[q]) * itau + F[q]);
+	});
+}
+
+template <typename R>
+LBMX_D void collide_clbm(R (&f)[9], const Phys<R>& P, R rho, R vx, R vy)
+{
+	using L = D2Q9;
+	const R tau = R(3) * P.nu + R(0.5);
+	const R fx = P.fx, fy = P.fy;
+	const R zz = f[L::find(0, 0)], pz = f[L::find(1, 0)], mz = f[L::find(-1, 0)], zp = f[L::find(0, 1)], zm = f[L::find(0, -1)];
+	const R pp = f[L::find(1, 1)], mm = f[L::find(-1, -1)], pm = f[L::find(1, -1)], mp = f[L::find(-1, 1)];
+	const R q4t = R(0.25) / tau;
+	const R diag = (pm + mm) + (pp + mp);
+	const R vx2 = vx * vx, vy2 = vy * vy;
+	// cascaded relaxation of the second moments (trace P, normal difference NE, shear V) and the higher central moments
+	const R Pm = R(1.0 / 12.0) * (rho * (vx2 + vy2) - pz - zp - zm - mz - R(2) * (diag - R(1.0 / 3.0) * rho) - (fx * vx + fy * vy));
+	const R NE = q4t * (zp + zm - pz - mz + rho * (vx2 - vy2) - (fx * vx - fy * vy));
+	const R V = q4t * ((pp + mm - mp - pm) - vx * vy * rho + R(0.5) * (fx * vy + fy * vx));
+	const R kxxyy = (pz + pp + mp + pm + mm + mz - vx2 * rho + R(2) * NE + R(6) * Pm) * (zp + pp + mp + zm + pm + mm - vy2 * rho - R(2) * NE + R(6) * Pm);
+	const R UP = -(R(0.25) * (pm + mm - pp - mp - R(2) * vx2 * vy * rho + vy * (rho - zp - zm - zz) + R(0.5) * vx2 * fy + fx * vx * vy)
+				   - vy * R(0.5) * (R(-3) * Pm - NE) + vx * ((pp - mp - pm + mm) * R(0.5) - R(2) * V));
+	const R RIGHT = -(R(0.25) * (mm + mp - pm - pp - R(2) * vy2 * vx * rho + vx * (rho - zz - mz - pz) + R(0.5) * vy2 * fx + fy * vy * vx)
+					  - vx * R(0.5) * (R(-3) * Pm + NE) + vy * ((pp + mm - pm - mp) * R(0.5) - R(2) * V));
+	const R NP = R(0.25)
+			   * (kxxyy - pp - mp - pm - mm - R(8) * Pm + R(2) * (vx * (pp - mp + pm - mm - R(4) * RIGHT) + vy * (pp + mp - pm - mm - R(4) * UP))
+				  + R(4) * vx * vy * (-pp + mp + pm - mm + R(4) * V) + vx2 * (-zp - pp - mp - zm - pm - mm + R(2) * NE - R(6) * Pm)
+				  + vy2 * ((-pz - pp - mp - pm - mm - mz - R(2) * NE - R(6) * Pm) + R(3) * vx2 * rho) - (fx * vx * vy2 + fy * vy * vx2));
+	// Premnath-Banerjee central-moment forcing
+	const R m1 = fx, m2 = fy;
+	const R m3 = R(6) * (fx * vx + fy * vy);
+	const R m4 = R(2) * (fx * vx - fy * vy);
+	const R m5 = fx * vy + fy * vx;
+	const R m6 = (R(2) - R(3) * vx2) * fy - R(6) * fx * vx * vy;
+	const R m7 = (R(2) - R(3) * vy2) * fx - R(6) * fy * vx * vy;
+	const R m8 = R(6) * ((R(3) * vy2 - R(2)) * fx * vx + (R(3) * vx2 - R(2)) * fy * vy);
+	const R i36 = R(1.0 / 36.0);
+	f[L::find(-1, 1)] = (mp + (R(2) * Pm + NP + V - UP + RIGHT)) + (R(-6) * m1 + R(6) * m2 + R(2) * m3 - R(9) * m5 - R(3) * m6 + R(3) * m7 + m8) * i36;
+	f[L::find(-1, 0)] = (mz + (-Pm - R(2) * NP + NE - R(2) * RIGHT)) + (R(-6) * m1 - m3 + R(9) * m4 - R(6) * m7 - R(2) * m8) * i36;
+	f[L::find(-1, -1)] = (mm + (R(2) * Pm + NP - V + UP + RIGHT)) + (R(-6) * m1 - R(6) * m2 + R(2) * m3 + R(9) * m5 + R(3) * m6 + R(3) * m7 + m8) * i36;
+	f[L::find(0, -1)] = (zm + (-Pm - R(2) * NP - NE - R(2) * UP)) + (R(-6) * m2 - m3 - R(9) * m4 - R(6) * m6 - R(2) * m8) * i36;
+	f[L::find(1, -1)] = (pm + (R(2) * Pm + NP + V + UP - RIGHT)) + (R(6) * m1 - R(6) * m2 + R(2) * m3 - R(9) * m5 + R(3) * m6 - R(3) * m7 + m8) * i36;
+	f[L::find(1, 0)] = (pz + (-Pm - R(2) * NP + NE + R(2) * RIGHT)) + (R(6) * m1 - m3 + R(9) * m4 + R(6) * m7 - R(2) * m8) * i36;
+	f[L::find(1, 1)] = (pp + (R(2) * Pm + NP - V - UP - RIGHT)) + (R(6) * m1 + R(6) * m2 + R(2) * m3 + R(9) * m5 - R(3) * m6 - R(3) * m7 + m8) * i36;
+	f[L::find(0, 1)] = (zp + (-Pm - R(2) * NP - NE + R(2) * UP)) + (R(6) * m2 - m3 - R(9) * m4 + R(6) * m6 - R(2) * m8) * i36;
+	f[L::find(0, 0)] = (zz + R(4) * (-Pm + NP)) + (-m3 + m8) * R(1.0 / 9.0);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// operator tags: what COLL means for a kernel instantiation
+// --------------------------------------------------------------------------------------------------------------------
+enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 };
+
+template <int KIND, typename R>
+LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
+{
+	if constexpr (KIND == K_CUM)
+		collide_cum(f, P, rho, vx, vy, vz);
+	else if constexpr (KIND == K_SRT)
+		collide_srt(f, P, eqkind, rho, vx, vy, vz);
+	else if constexpr (KIND == K_BGK)
+		collide_bgk(f, P, rho, vx, vy, vz);
+	else
+		collide_mrt(f, P, rho, vx, vy, vz);
+}
+template <int KIND, typename R>
+LBMX_D void collide(R (&f)[9], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
+{
+	if constexpr (KIND == K_SRT)
+		collide_srt(f, P, eqkind, rho, vx, vy, vz);
+	else
+		collide_clbm(f, P, rho, vx, vy);
+}
+
+}  // namespace lbmx

@@ -1,0 +1,999 @@
+// engine.cu -- host side of liblbmx.so: the engine object behind the C ABI of include/lbmx.h.
+//
+// Replaces, for the hot path only, what LBM / LBM_BLOCK / State::SimUpdate do in the reference (include/lbm3d/lbm.hpp,
+// lbm_block.hpp, state.hpp:980-1145): owns the device arrays of one x-slab, builds the launch plan from the cell-type
+// map, advances time steps (even/odd parity, A-B rotation), and exchanges ghost planes with the neighbouring slabs
+// (boundary planes first on a high-priority stream, NCCL send/recv on a communication stream, interior concurrently).
+// No CPU fallback anywhere: without a CUDA device every call fails with LBMX_ERR_CUDA.
+#include "../../include/lbmx.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lbmx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+	g_err = msg;
+	return code;
+}
+
+#define CU(call)                                                                                                                   \
+	do {                                                                                                                           \
+		cudaError_t err__ = (call);                                                                                                \
+		if (err__ != cudaSuccess)                                                                                                  \
+			return fail(LBMX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+	} while (0)
+
+// ---- NCCL bound at run time so that the library loads (and the host-only helpers work) on machines without it, and so
+//      that a process that already carries a libnccl.so.2 (e.g. torch's) shares that one copy --------------------------------
+struct NcclApi
+{
+	void* handle = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+	bool load(std::string& why)
+	{
+		if (handle)
+			return true;
+		const char* names[] = {"libnccl.so.2", "libnccl.so"};
+		for (const char* n : names) {
+			handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+			if (handle)
+				break;
+		}
+		if (! handle) {
+			why = std::string("dlopen(libnccl.so.2): ") + dlerror();
+			return false;
+		}
+#define SYM(field, name)                                   \
+	field = (decltype(field)) dlsym(handle, name);         \
+	if (! field) {                                         \
+		why = std::string("dlsym ") + name + " failed";    \
+		return false;                                      \
+	}
+		SYM(GetUniqueId, "ncclGetUniqueId")
+		SYM(CommInitRank, "ncclCommInitRank")
+		SYM(CommDestroy, "ncclCommDestroy")
+		SYM(Send, "ncclSend")
+		SYM(Recv, "ncclRecv")
+		SYM(GroupStart, "ncclGroupStart")
+		SYM(GroupEnd, "ncclGroupEnd")
+		SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+		return true;
+	}
+};
+NcclApi g_nccl;
+
+#define NC(call)                                                                                           \
+	do {                                                                                                   \
+		ncclResult_t r__ = (call);                                                                         \
+		if (r__ != ncclSuccess)                                                                            \
+			return fail(LBMX_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r__));            \
+	} while (0)
+
+int q_of(int lattice)
+{
+	return lattice == LBMX_D2Q9 ? 9 : 27;
+}
+int n_macro_of(int lattice, int macro)
+{
+	if (macro == LBMX_MACRO_VOID)
+		return 0;
+	if (lattice == LBMX_D2Q9)
+		return macro == LBMX_MACRO_DEFAULT ? 3 : 8;
+	return macro == LBMX_MACRO_DEFAULT ? 4 : 13;
+}
+
+template <typename L>
+int halo_dirs(int32_t* to_right, int32_t* to_left)
+{
+	int nr = 0, nl = 0;
+	for (int q = 0; q < L::Q; q++) {
+		if (L::cx(q) > 0)
+			to_right[nr++] = q;
+		if (L::cx(q) < 0)
+			to_left[nl++] = q;
+	}
+	return nr;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// engine
+// =====================================================================================================================
+struct lbmx_engine
+{
+	lbmx_desc d{};
+	lbmx_params prm{};
+	int dev = 0;
+	int Q = 27, NM = 4;
+	size_t rs = 8;	// sizeof(real)
+	int64_t X = 0, Y = 0, Z = 0, x0 = 0, ox = 0, YZ = 0, XYZ = 0;
+	int left = -1, right = -1;	// neighbour ranks (-1: none)
+	bool self_exchange = false;
+
+	void* df[2] = {nullptr, nullptr};
+	void* macro = nullptr;
+	int16_t* map = nullptr;
+	uint32_t* blist = nullptr;
+	void* profile = nullptr;
+	int64_t profile_sy = 0;
+	int* d_flag = nullptr;
+	int* d_dirs = nullptr;	// [2][9]: to_right, to_left
+	int n_hdirs = 0;
+	int32_t h_dirs[2][9];
+	void* sendbuf[2] = {nullptr, nullptr};	// packed halo planes (to right, to left)
+	void* recvbuf[2] = {nullptr, nullptr};	// (from left, from right)
+
+	std::vector<int64_t> plane_start;  // boundary-list offsets per local x plane, size X+1
+	int64_t nb = 0, n_bulk = 0;
+	bool map_ready = false;
+
+	int64_t iter = 0;
+	cudaStream_t s_main = nullptr, s_edge = nullptr, s_comm = nullptr;
+	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_main = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+	ncclComm_t comm = nullptr;
+
+	StepKernels<float> kf{};
+	StepKernels<double> kd{};
+	lbmx_stats stats{};
+
+	bool f64() const { return d.precision == LBMX_F64; }
+	bool aa() const { return d.streaming == LBMX_STREAM_AA; }
+	void* cur() const { return aa() ? df[0] : df[iter % 2]; }
+	void* other() const { return aa() ? nullptr : df[(iter + 1) % 2]; }
+};
+
+namespace {
+
+template <typename R>
+KParams<R> make_params(const lbmx_engine* e)
+{
+	KParams<R> p{};
+	p.cur = (R*) e->cur();
+	p.out = (R*) e->other();
+	p.macro = (R*) e->macro;
+	p.map = e->map;
+	p.profile = (const R*) e->profile;
+	p.blist = e->blist;
+	p.XYZ = e->XYZ;
+	p.X = (int) e->X;
+	p.Y = (int) e->Y;
+	p.Z = (int) e->Z;
+	p.ox = (int) e->ox;
+	p.YZ = (int) e->YZ;
+	p.x_begin = 0;
+	p.x_end = (int) e->X;
+	p.nb_begin = 0;
+	p.nb_end = (int) e->nb;
+	p.wrap = e->ox == 0 ? 1 : 0;
+	p.profile_sy = (int) e->profile_sy;
+	p.eq = e->d.eq;
+	p.inflow = e->d.inflow;
+	p.stream = e->aa() ? (e->iter % 2 == 0 ? S_AA_EVEN : S_AA_ODD) : S_AB;
+	p.out_mode = OUT_NONE;
+	p.stat_counter = e->prm.stat_counter;
+	const bool vm = e->d.macro == LBMX_MACRO_VOID;
+	p.void_macro = vm;
+	// MACRO_Void::copyQuantities is empty (d3q27/macro.h:174-188): the KernelStruct keeps lbmViscosity = 1, zero force
+	p.phys.nu = vm ? R(1) : (R) e->prm.lbmViscosity;
+	p.phys.fx = vm ? R(0) : (R) e->prm.fx;
+	p.phys.fy = vm ? R(0) : (R) e->prm.fy;
+	p.phys.fz = (vm || e->d.lattice == LBMX_D2Q9) ? R(0) : (R) e->prm.fz;
+	p.in_vx = (R) e->prm.inflow_vx;
+	p.in_vy = (R) e->prm.inflow_vy;
+	p.in_vz = (R) e->prm.inflow_vz;
+	return p;
+}
+
+constexpr int BLOCK = 128;
+
+// launch the two step kernels over local planes [xb, xe) on `st`
+template <typename R>
+int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, int xe, cudaStream_t st)
+{
+	if (xe <= xb)
+		return LBMX_OK;
+	p.x_begin = xb;
+	p.x_end = xe;
+	p.nb_begin = (int) e->plane_start[xb];
+	p.nb_end = (int) e->plane_start[xe];
+	dim3 grid((unsigned) ((e->YZ + BLOCK - 1) / BLOCK), (unsigned) (xe - xb));
+	K.bulk[p.stream]<<<grid, BLOCK, 0, st>>>(p);
+	e->stats.kernel_launches++;
+	const int nbl = p.nb_end - p.nb_begin;
+	if (nbl > 0) {
+		K.boundary<<<(nbl + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(p);
+		e->stats.kernel_launches++;
+	}
+	CU(cudaGetLastError());
+	return LBMX_OK;
+}
+
+size_t plane_bytes(const lbmx_engine* e)
+{
+	return (size_t) e->YZ * e->rs;
+}
+
+// enqueue the halo exchange that follows the step at e->iter on s_comm (replaces synchronizeDFsAndMacroDevice, lbm.hpp:196-280)
+template <typename R>
+int exchange(lbmx_engine* e, void* arr)
+{
+	lbmx_halo_msg msgs[2];
+	lbmx_halo_plan(e->d.lattice, e->d.streaming, e->iter, e->X, msgs);
+	R* a = (R*) arr;
+	const int nd = e->n_hdirs;
+	dim3 grid((unsigned) ((e->YZ + 255) / 256), (unsigned) nd);
+	if (e->self_exchange) {
+		// single slab with ghost planes and periodic x: the neighbour on both sides is this slab
+		for (int k = 0; k < 2; k++) {
+			const lbmx_halo_msg& m = msgs[k];
+			k_copy_planes<R><<<grid, 256, 0, e->s_comm>>>(a, a, e->XYZ, (int) e->YZ, nd, e->d_dirs + (m.to_right ? 0 : 9), m.src_plane, m.dst_plane);
+			e->stats.kernel_launches++;
+			e->stats.halo_bytes_sent += (int64_t) nd * plane_bytes(e);
+		}
+		CU(cudaGetLastError());
+		return LBMX_OK;
+	}
+	if (e->d.nranks == 1)
+		return LBMX_OK;	 // ghost planes without a periodic partner: nothing to exchange
+	if (! e->comm)
+		return fail(LBMX_ERR_STATE, "lbmx_step: nranks > 1 but lbmx_comm_init was not called");
+	// the 9 crossing populations of a plane are 9 separate contiguous runs of Y*Z reals (x is the slowest storage
+	// dimension): they go out as 9 sends per direction inside one NCCL group -- no pack/unpack kernels at all
+	NC(g_nccl.GroupStart());
+	for (int k = 0; k < 2; k++) {
+		const lbmx_halo_msg& m = msgs[k];
+		const int peer_send = m.to_right ? e->right : e->left;
+		const int peer_recv = m.to_right ? e->left : e->right;	// what arrives from the opposite side carries the same populations
+		for (int i = 0; i < nd; i++) {
+			const int q = m.dirs[i];
+			if (peer_send >= 0) {
+				NC(g_nccl.Send(a + q * e->XYZ + m.src_plane * e->YZ, plane_bytes(e), ncclInt8, peer_send, e->comm, e->s_comm));
+				e->stats.halo_bytes_sent += plane_bytes(e);
+			}
+			if (peer_recv >= 0)
+				NC(g_nccl.Recv(a + q * e->XYZ + m.dst_plane * e->YZ, plane_bytes(e), ncclInt8, peer_recv, e->comm, e->s_comm));
+		}
+	}
+	NC(g_nccl.GroupEnd());
+	e->stats.kernel_launches++;
+	return LBMX_OK;
+}
+
+template <typename R>
+int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
+{
+	const bool ghosts = e->ox > 0;
+	for (int64_t s = 0; s < nsteps; s++) {
+		KParams<R> p = make_params<R>(e);
+		const bool last = s == nsteps - 1;
+		if (e->d.macro == LBMX_MACRO_MEAN)
+			p.out_mode = OUT_MEAN;
+		else if (e->d.macro == LBMX_MACRO_DEFAULT && (e->d.macro_policy == LBMX_MACRO_EVERY_STEP || (e->d.macro_policy == LBMX_MACRO_LAST_STEP && last)))
+			p.out_mode = OUT_DEFAULT;
+		p.stat_counter = e->prm.stat_counter + (int) s;
+		int rc;
+		if (! ghosts) {
+			if ((rc = launch_range(e, K, p, 0, (int) e->X, e->s_main)))
+				return rc;
+		}
+		else {
+			// boundary planes first on the high-priority stream, then the exchange, interior concurrently (state.hpp:1060-1108)
+			CU(cudaStreamWaitEvent(e->s_edge, e->ev_main, 0));	// previous step's interior (reads/writes next to the edge planes)
+			CU(cudaStreamWaitEvent(e->s_edge, e->ev_comm, 0));	// previous exchange filled the ghost planes this step reads
+			if ((rc = launch_range(e, K, p, 0, 1, e->s_edge)))
+				return rc;
+			if (e->X > 1 && (rc = launch_range(e, K, p, (int) e->X - 1, (int) e->X, e->s_edge)))
+				return rc;
+			CU(cudaEventRecord(e->ev_edge, e->s_edge));
+			CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
+			if ((rc = launch_range(e, K, p, 1, (int) e->X - 1, e->s_main)))
+				return rc;
+			CU(cudaEventRecord(e->ev_main, e->s_main));
+			CU(cudaStreamWaitEvent(e->s_comm, e->ev_edge, 0));
+			// A-A odd steps also write the ghost planes from the planes next to the edge: those are edge-plane cells only
+			void* arr = e->aa() ? e->df[0] : e->other();
+			if ((rc = exchange<R>(e, arr)))
+				return rc;
+			CU(cudaEventRecord(e->ev_comm, e->s_comm));
+		}
+		e->iter++;
+	}
+	e->prm.stat_counter += (int) nsteps;
+	if (ghosts) {
+		// leave the engine in a state where s_main alone orders everything that was enqueued
+		CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
+		CU(cudaStreamWaitEvent(e->s_main, e->ev_edge, 0));
+	}
+	return LBMX_OK;
+}
+
+int step_dispatch(lbmx_engine* e, int64_t nsteps)
+{
+	if (! e->map_ready)
+		return fail(LBMX_ERR_STATE, "lbmx_step: upload a map first (lbmx_map_upload)");
+	CU(cudaSetDevice(e->dev));
+	return e->f64() ? step_impl<double>(e, e->kd, nsteps) : step_impl<float>(e, e->kf, nsteps);
+}
+
+bool pick_kernels(lbmx_engine* e)
+{
+	const lbmx_desc& d = e->d;
+	if (d.lattice == LBMX_D3Q27) {
+		switch (d.coll) {
+			case LBMX_COLL_CUM: return e->f64() ? get_kernels_d3q27_cum(e->kd) : get_kernels_d3q27_cum(e->kf);
+			case LBMX_COLL_SRT: return e->f64() ? get_kernels_d3q27_srt(e->kd) : get_kernels_d3q27_srt(e->kf);
+			case LBMX_COLL_BGK: return e->f64() ? get_kernels_d3q27_bgk(e->kd) : get_kernels_d3q27_bgk(e->kf);
+			case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt(e->kd) : get_kernels_d3q27_mrt(e->kf);
+		}
+	}
+	else if (d.lattice == LBMX_D2Q9) {
+		if (d.coll == LBMX_COLL_SRT)
+			return e->f64() ? get_kernels_d2q9_srt(e->kd) : get_kernels_d2q9_srt(e->kf);
+		if (d.coll == LBMX_COLL_CLBM)
+			return e->f64() ? get_kernels_d2q9_clbm(e->kd) : get_kernels_d2q9_clbm(e->kf);
+	}
+	return false;
+}
+
+// host <-> device copies of [ncomp][X(+2ox)][Z][Y] arrays with or without the ghost planes
+int copy_components(lbmx_engine* e, void* dev, void* host, int ncomp, size_t elem, bool with_ghosts, bool to_device)
+{
+	CU(cudaSetDevice(e->dev));
+	CU(cudaStreamSynchronize(e->s_main));
+	const size_t comp_dev = (size_t) e->XYZ * elem;
+	if (with_ghosts || e->ox == 0) {
+		const size_t bytes = comp_dev * ncomp;
+		CU(to_device ? cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice) : cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
+		return LBMX_OK;
+	}
+	const size_t comp_host = (size_t) e->X * e->YZ * elem;
+	const size_t skip = (size_t) e->ox * e->YZ * elem;
+	for (int c = 0; c < ncomp; c++) {  // the interior planes of one component are contiguous on both sides
+		char* dp = (char*) dev + (size_t) c * comp_dev + skip;
+		char* hp = (char*) host + (size_t) c * comp_host;
+		CU(to_device ? cudaMemcpy(dp, hp, comp_host, cudaMemcpyHostToDevice) : cudaMemcpy(hp, dp, comp_host, cudaMemcpyDeviceToHost));
+	}
+	return LBMX_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+const char* lbmx_last_error(void)
+{
+	return g_err.c_str();
+}
+
+int lbmx_version(void)
+{
+	return LBMX_VERSION;
+}
+
+int lbmx_decompose_x(int64_t X, int32_t nranks, int32_t rank, int64_t* x_offset, int64_t* x_local)
+{
+	if (X < 1 || nranks < 1 || rank < 0 || rank >= nranks || nranks > X)
+		return fail(LBMX_ERR_ARG, "lbmx_decompose_x: need 0 <= rank < nranks <= X");
+	// contiguous x-planes, remainder spread over the first ranks (decomposeLattice_D1Q3 splits the same way)
+	const int64_t base = X / nranks, rem = X % nranks;
+	const int64_t off = rank * base + std::min<int64_t>(rank, rem);
+	if (x_offset)
+		*x_offset = off;
+	if (x_local)
+		*x_local = base + (rank < rem ? 1 : 0);
+	return LBMX_OK;
+}
+
+int lbmx_halo_directions(int32_t lattice, int32_t* to_right, int32_t* to_left)
+{
+	int32_t r[9], l[9];
+	int n;
+	if (lattice == LBMX_D3Q27)
+		n = halo_dirs<D3Q27>(r, l);
+	else if (lattice == LBMX_D2Q9)
+		n = halo_dirs<D2Q9>(r, l);
+	else
+		return 0;
+	if (to_right)
+		std::memcpy(to_right, r, n * sizeof(int32_t));
+	if (to_left)
+		std::memcpy(to_left, l, n * sizeof(int32_t));
+	return n;
+}
+
+int lbmx_halo_plan(int32_t lattice, int32_t streaming, int64_t iteration, int64_t X_local, lbmx_halo_msg msgs[2])
+{
+	int32_t r[9], l[9];
+	const int n = lbmx_halo_directions(lattice, r, l);
+	if (n == 0)
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_halo_plan: unknown lattice");
+	// storage planes with one ghost plane per side: 0 = left ghost, 1 = first interior, X_local = last interior, X_local+1 = right ghost
+	const int64_t gL = 0, first = 1, last = X_local, gR = X_local + 1;
+	lbmx_halo_msg& toR = msgs[0];
+	lbmx_halo_msg& toL = msgs[1];
+	toR.to_right = 1;
+	toL.to_right = 0;
+	toR.n_dirs = toL.n_dirs = n;
+	const bool aa = streaming == LBMX_STREAM_AA;
+	const bool even = (iteration % 2) == 0;
+	if (! aa) {
+		// A-B: df_out holds post-collision values at their source cell; the +x movers of my last plane are what the right
+		// neighbour pulls from its left ghost plane (lbm_block.hpp:423-450 with df_sync_directions, defs.h:309-340)
+		std::memcpy(toR.dirs, r, sizeof(r));
+		std::memcpy(toL.dirs, l, sizeof(l));
+		toR.src_plane = last;
+		toR.dst_plane = gL;
+		toL.src_plane = first;
+		toL.dst_plane = gR;
+	}
+	else if (even) {
+		// A-A even step: post-collision f_q sits in slot opp(q) of its own cell, so what must travel right (the +x movers)
+		// is found in the -x slots of my last plane, and lands in the same slots of the neighbour's left ghost plane
+		// (lbm_block.hpp:428-436: "opposite direction on even steps")
+		std::memcpy(toR.dirs, l, sizeof(l));
+		std::memcpy(toL.dirs, r, sizeof(r));
+		toR.src_plane = last;
+		toR.dst_plane = gL;
+		toL.src_plane = first;
+		toL.dst_plane = gR;
+	}
+	else {
+		// A-A odd step: the +x movers of my last plane were written into MY right ghost plane (slot q at x + c_q); they
+		// belong to the first interior plane of the right neighbour (lbm_block.hpp:437-442: buffer offset 1)
+		std::memcpy(toR.dirs, r, sizeof(r));
+		std::memcpy(toL.dirs, l, sizeof(l));
+		toR.src_plane = gR;
+		toR.dst_plane = first;
+		toL.src_plane = gL;
+		toL.dst_plane = last;
+	}
+	return LBMX_OK;
+}
+
+int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
+{
+	if (! desc || ! out)
+		return fail(LBMX_ERR_ARG, "lbmx_create: null argument");
+	*out = nullptr;
+	const lbmx_desc& d = *desc;
+	if (d.X < 1 || d.Y < 1 || d.Z < 1)
+		return fail(LBMX_ERR_ARG, "lbmx_create: lattice sizes must be positive");
+	if (d.lattice == LBMX_D3Q19)
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: D3Q19 has no implementation in the reference and none here yet");
+	if (d.lattice == LBMX_D2Q9 && d.Z != 1)
+		return fail(LBMX_ERR_ARG, "lbmx_create: D2Q9 needs Z == 1 (the reference's X x Y x 1 lattice, sim_2D/sim2d_1.cu:134)");
+	if (d.precision != LBMX_F32 && d.precision != LBMX_F64)
+		return fail(LBMX_ERR_ARG, "lbmx_create: precision");
+	if (d.streaming != LBMX_STREAM_AB && d.streaming != LBMX_STREAM_AA)
+		return fail(LBMX_ERR_ARG, "lbmx_create: streaming");
+	if (d.macro < LBMX_MACRO_VOID || d.macro > LBMX_MACRO_MEAN || d.inflow < LBMX_INFLOW_NONE || d.inflow > LBMX_INFLOW_PROFILE_YZ)
+		return fail(LBMX_ERR_ARG, "lbmx_create: macro / inflow selector");
+	if (d.eq != LBMX_EQ_STD && d.eq != LBMX_EQ_INV_CUM)
+		return fail(LBMX_ERR_ARG, "lbmx_create: eq selector");
+	if (d.lattice == LBMX_D2Q9 && d.eq != LBMX_EQ_STD)
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: D2Q9 has only the polynomial equilibrium (d2q9/eq.h)");
+	if (d.nranks < 1 || d.rank < 0 || d.rank >= d.nranks)
+		return fail(LBMX_ERR_ARG, "lbmx_create: rank / nranks");
+
+	lbmx_engine* e = new lbmx_engine();
+	e->d = d;
+	if (e->d.nranks > 1)
+		e->d.ghost_x = 1;
+	int rc = lbmx_decompose_x(d.X, d.nranks, d.rank, &e->x0, &e->X);
+	if (rc) {
+		delete e;
+		return rc;
+	}
+	e->Y = d.Y;
+	e->Z = d.Z;
+	e->ox = e->d.ghost_x ? 1 : 0;
+	e->YZ = e->Y * e->Z;
+	e->XYZ = (e->X + 2 * e->ox) * e->YZ;
+	e->Q = q_of(d.lattice);
+	e->NM = n_macro_of(d.lattice, d.macro);
+	e->rs = d.precision == LBMX_F64 ? 8 : 4;
+	if (e->XYZ >= (int64_t) 1 << 31) {
+		delete e;
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: more than 2^31 storage cells per slab (cell indices are 32-bit); use more slabs");
+	}
+	if (! pick_kernels(e)) {
+		delete e;
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: no kernel family for this lattice / collision combination");
+	}
+	if (e->d.nranks > 1) {
+		e->left = e->d.rank > 0 ? e->d.rank - 1 : (e->d.periodic_x ? e->d.nranks - 1 : -1);
+		e->right = e->d.rank < e->d.nranks - 1 ? e->d.rank + 1 : (e->d.periodic_x ? 0 : -1);
+	}
+	else if (e->ox) {
+		e->self_exchange = e->d.periodic_x != 0;
+	}
+	e->n_hdirs = lbmx_halo_directions(d.lattice, e->h_dirs[0], e->h_dirs[1]);
+
+#define CUX(call)                                                                                             \
+	do {                                                                                                      \
+		cudaError_t err__ = (call);                                                                           \
+		if (err__ != cudaSuccess) {                                                                           \
+			fail(LBMX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));                       \
+			lbmx_destroy(e);                                                                                  \
+			return LBMX_ERR_CUDA;                                                                             \
+		}                                                                                                     \
+	} while (0)
+	if (d.device >= 0)
+		CUX(cudaSetDevice(d.device));
+	CUX(cudaGetDevice(&e->dev));
+	int lo = 0, hi = 0;
+	CUX(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+	CUX(cudaStreamCreateWithPriority(&e->s_main, cudaStreamNonBlocking, lo));
+	CUX(cudaStreamCreateWithPriority(&e->s_edge, cudaStreamNonBlocking, hi));
+	CUX(cudaStreamCreateWithPriority(&e->s_comm, cudaStreamNonBlocking, hi));
+	CUX(cudaEventCreateWithFlags(&e->ev_edge, cudaEventDisableTiming));
+	CUX(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
+	CUX(cudaEventCreateWithFlags(&e->ev_main, cudaEventDisableTiming));
+	CUX(cudaEventCreate(&e->ev_t0));
+	CUX(cudaEventCreate(&e->ev_t1));
+	const size_t df_bytes = (size_t) e->Q * e->XYZ * e->rs;
+	const int ncopies = e->aa() ? 1 : 2;
+	for (int i = 0; i < ncopies; i++) {
+		CUX(cudaMalloc(&e->df[i], df_bytes));
+		CUX(cudaMemsetAsync(e->df[i], 0, df_bytes, e->s_main));
+	}
+	if (e->NM > 0) {
+		CUX(cudaMalloc(&e->macro, (size_t) e->NM * e->XYZ * e->rs));
+		CUX(cudaMemsetAsync(e->macro, 0, (size_t) e->NM * e->XYZ * e->rs, e->s_main));
+	}
+	CUX(cudaMalloc(&e->map, (size_t) e->XYZ * sizeof(int16_t)));
+	CUX(cudaMemsetAsync(e->map, 0, (size_t) e->XYZ * sizeof(int16_t), e->s_main));
+	CUX(cudaMalloc(&e->d_flag, sizeof(int)));
+	CUX(cudaMalloc(&e->d_dirs, sizeof(int) * 18));
+	CUX(cudaMemcpyAsync(e->d_dirs, e->h_dirs, sizeof(int) * 18, cudaMemcpyHostToDevice, e->s_main));
+	CUX(cudaStreamSynchronize(e->s_main));
+	// registers of the step kernels, for the measurement harness
+	cudaFuncAttributes fa{};
+	const int mode = e->aa() ? S_AA_EVEN : S_AB;
+	const void* kb = e->f64() ? (const void*) e->kd.bulk[mode] : (const void*) e->kf.bulk[mode];
+	const void* kq = e->f64() ? (const void*) e->kd.boundary : (const void*) e->kf.boundary;
+	if (cudaFuncGetAttributes(&fa, kb) == cudaSuccess)
+		e->stats.bulk_regs = fa.numRegs;
+	if (cudaFuncGetAttributes(&fa, kq) == cudaSuccess)
+		e->stats.boundary_regs = fa.numRegs;
+	e->stats.bulk_block = BLOCK;
+#undef CUX
+	e->prm.lbmViscosity = 0.01;
+	*out = e;
+	return LBMX_OK;
+}
+
+int lbmx_destroy(lbmx_engine* e)
+{
+	if (! e)
+		return LBMX_OK;
+	cudaSetDevice(e->dev);
+	cudaDeviceSynchronize();
+	if (e->comm && g_nccl.CommDestroy)
+		g_nccl.CommDestroy(e->comm);
+	for (void* p : {e->df[0], e->df[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, (void*) e->d_flag, (void*) e->d_dirs, e->sendbuf[0], e->sendbuf[1], e->recvbuf[0], e->recvbuf[1]})
+		if (p)
+			cudaFree(p);
+	for (cudaEvent_t ev : {e->ev_edge, e->ev_comm, e->ev_main, e->ev_t0, e->ev_t1})
+		if (ev)
+			cudaEventDestroy(ev);
+	for (cudaStream_t s : {e->s_main, e->s_edge, e->s_comm})
+		if (s)
+			cudaStreamDestroy(s);
+	delete e;
+	return LBMX_OK;
+}
+
+int lbmx_get_layout(const lbmx_engine* e, lbmx_layout* out)
+{
+	if (! e || ! out)
+		return fail(LBMX_ERR_ARG, "lbmx_get_layout: null argument");
+	out->X_local = e->X;
+	out->Y = e->Y;
+	out->Z = e->Z;
+	out->x_offset = e->x0;
+	out->ghost_x = e->ox;
+	out->XYZ = e->XYZ;
+	out->Q = e->Q;
+	out->n_macro = e->NM;
+	out->sizeof_real = (int32_t) e->rs;
+	out->dfmax = e->aa() ? 1 : 2;
+	return LBMX_OK;
+}
+
+int lbmx_comm_unique_id(void* id128)
+{
+	std::string why;
+	if (! g_nccl.load(why))
+		return fail(LBMX_ERR_NCCL, why);
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	ncclUniqueId id;
+	NC(g_nccl.GetUniqueId(&id));
+	std::memcpy(id128, &id, 128);
+	return LBMX_OK;
+}
+
+int lbmx_comm_init(lbmx_engine* e, const void* id128)
+{
+	if (! e || ! id128)
+		return fail(LBMX_ERR_ARG, "lbmx_comm_init: null argument");
+	if (e->d.nranks < 2)
+		return LBMX_OK;
+	std::string why;
+	if (! g_nccl.load(why))
+		return fail(LBMX_ERR_NCCL, why);
+	CU(cudaSetDevice(e->dev));
+	ncclUniqueId id;
+	std::memcpy(&id, id128, 128);
+	NC(g_nccl.CommInitRank(&e->comm, e->d.nranks, id, e->d.rank));
+	return LBMX_OK;
+}
+
+static int exchange_full_planes(lbmx_engine* e, void* arr, int ncomp, size_t elem)
+{
+	// every component: my first / last interior plane -> the neighbours' ghost planes (map and initial-state synchronisation)
+	if (e->ox == 0)
+		return LBMX_OK;
+	CU(cudaSetDevice(e->dev));
+	const size_t pb = (size_t) e->YZ * elem;
+	char* a = (char*) arr;
+	auto plane = [&](int comp, int64_t xs) { return a + ((size_t) comp * e->XYZ + (size_t) xs * e->YZ) * elem; };
+	if (e->d.nranks == 1) {
+		if (! e->self_exchange)
+			return LBMX_OK;
+		for (int c = 0; c < ncomp; c++) {
+			CU(cudaMemcpyAsync(plane(c, 0), plane(c, e->X), pb, cudaMemcpyDeviceToDevice, e->s_main));
+			CU(cudaMemcpyAsync(plane(c, e->X + 1), plane(c, 1), pb, cudaMemcpyDeviceToDevice, e->s_main));
+		}
+		return LBMX_OK;
+	}
+	if (! e->comm)
+		return fail(LBMX_ERR_STATE, "ghost-plane synchronisation needs lbmx_comm_init first");
+	NC(g_nccl.GroupStart());
+	for (int c = 0; c < ncomp; c++) {
+		if (e->right >= 0) {
+			NC(g_nccl.Send(plane(c, e->X), pb, ncclInt8, e->right, e->comm, e->s_main));
+			NC(g_nccl.Recv(plane(c, e->X + 1), pb, ncclInt8, e->right, e->comm, e->s_main));
+		}
+		if (e->left >= 0) {
+			NC(g_nccl.Send(plane(c, 1), pb, ncclInt8, e->left, e->comm, e->s_main));
+			NC(g_nccl.Recv(plane(c, 0), pb, ncclInt8, e->left, e->comm, e->s_main));
+		}
+	}
+	NC(g_nccl.GroupEnd());
+	return LBMX_OK;
+}
+
+int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
+{
+	if (! e || ! host_map)
+		return fail(LBMX_ERR_ARG, "lbmx_map_upload: null argument");
+	int rc = copy_components(e, e->map, (void*) host_map, 1, sizeof(int16_t), with_ghosts != 0, true);
+	if (rc)
+		return rc;
+	if (! with_ghosts && e->ox) {
+		// LBM::synchronizeMapDevice (lbm.hpp:283-289); ghost planes without a neighbour keep GEO_FLUID (0)
+		if ((rc = exchange_full_planes(e, e->map, 1, sizeof(int16_t))))
+			return rc;
+		CU(cudaStreamSynchronize(e->s_main));
+	}
+	// launch plan: cells that are neither GEO_FLUID nor GEO_PERIODIC go to the boundary list, ordered by storage index
+	// (so list ranges per x-plane are contiguous and neighbouring entries are neighbouring cells)
+	std::vector<int16_t> hm((size_t) e->XYZ);
+	CU(cudaMemcpy(hm.data(), e->map, hm.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
+	const int fluid = 0;
+	const int periodic = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::PERIODIC : (int) D3Q27::PERIODIC;
+	std::vector<uint32_t> list;
+	e->plane_start.assign((size_t) e->X + 1, 0);
+	for (int64_t x = 0; x < e->X; x++) {
+		e->plane_start[(size_t) x] = (int64_t) list.size();
+		const int64_t base = (x + e->ox) * e->YZ;
+		for (int64_t i = 0; i < e->YZ; i++) {
+			const int m = hm[(size_t) (base + i)];
+			if (m != fluid && m != periodic)
+				list.push_back((uint32_t) (base + i));
+		}
+	}
+	e->plane_start[(size_t) e->X] = (int64_t) list.size();
+	e->nb = (int64_t) list.size();
+	e->n_bulk = e->X * e->YZ - e->nb;
+	if (e->blist) {
+		CU(cudaFree(e->blist));
+		e->blist = nullptr;
+	}
+	if (e->nb > 0) {
+		CU(cudaMalloc(&e->blist, list.size() * sizeof(uint32_t)));
+		CU(cudaMemcpy(e->blist, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	}
+	e->stats.boundary_cells = e->nb;
+	e->stats.bulk_cells = e->n_bulk;
+	e->map_ready = true;
+	return LBMX_OK;
+}
+
+int lbmx_map_download(lbmx_engine* e, int16_t* host_map, int with_ghosts)
+{
+	if (! e || ! host_map)
+		return fail(LBMX_ERR_ARG, "lbmx_map_download: null argument");
+	return copy_components(e, e->map, host_map, 1, sizeof(int16_t), with_ghosts != 0, false);
+}
+
+static int set_eq_common(lbmx_engine* e, const double* rho, const double* vx, const double* vy, const double* vz, double crho, double cvx, double cvy, double cvz)
+{
+	CU(cudaSetDevice(e->dev));
+	const bool field = rho != nullptr;
+	const int64_t n = field ? e->X * e->YZ : e->XYZ;
+	const int64_t cell0 = field ? e->ox * e->YZ : 0;
+	double* dev_fields[4] = {nullptr, nullptr, nullptr, nullptr};
+	const double* src[4] = {rho, vx, vy, vz};
+	int rc = LBMX_OK;
+	if (field) {
+		for (int k = 0; k < 4 && rc == LBMX_OK; k++) {
+			if (! src[k])
+				continue;
+			if (cudaMalloc(&dev_fields[k], (size_t) n * sizeof(double)) != cudaSuccess
+				|| cudaMemcpyAsync(dev_fields[k], src[k], (size_t) n * sizeof(double), cudaMemcpyHostToDevice, e->s_main) != cudaSuccess)
+				rc = fail(LBMX_ERR_CUDA, std::string("lbmx_df_set_equilibrium_field: ") + cudaGetErrorString(cudaGetLastError()));
+		}
+	}
+	if (rc == LBMX_OK) {
+		const unsigned blocks = (unsigned) ((n + 127) / 128);
+		if (e->f64())
+			e->kd.set_equilibrium<<<blocks, 128, 0, e->s_main>>>((double*) e->df[0], e->XYZ, n, cell0, e->d.eq, dev_fields[0], dev_fields[1], dev_fields[2], dev_fields[3], crho, cvx, cvy, cvz);
+		else
+			e->kf.set_equilibrium<<<blocks, 128, 0, e->s_main>>>((float*) e->df[0], e->XYZ, n, cell0, e->d.eq, dev_fields[0], dev_fields[1], dev_fields[2], dev_fields[3], crho, cvx, cvy, cvz);
+		e->stats.kernel_launches++;
+		if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(e->s_main) != cudaSuccess)
+			rc = fail(LBMX_ERR_CUDA, "lbmx_df_set_equilibrium: kernel failed");
+	}
+	for (double* p : dev_fields)
+		if (p)
+			cudaFree(p);
+	if (rc)
+		return rc;
+	if (field && e->ox) {
+		if ((rc = exchange_full_planes(e, e->df[0], e->Q, e->rs)))
+			return rc;
+	}
+	// "copy the initialized DFs so that they are not overridden" (lbm_block.hpp:247-249)
+	if (! e->aa())
+		CU(cudaMemcpyAsync(e->df[1], e->df[0], (size_t) e->Q * e->XYZ * e->rs, cudaMemcpyDeviceToDevice, e->s_main));
+	CU(cudaStreamSynchronize(e->s_main));
+	return LBMX_OK;
+}
+
+int lbmx_df_set_equilibrium(lbmx_engine* e, double rho, double vx, double vy, double vz)
+{
+	if (! e)
+		return fail(LBMX_ERR_ARG, "lbmx_df_set_equilibrium: null engine");
+	return set_eq_common(e, nullptr, nullptr, nullptr, nullptr, rho, vx, vy, vz);
+}
+
+int lbmx_df_set_equilibrium_field(lbmx_engine* e, const double* rho, const double* vx, const double* vy, const double* vz)
+{
+	if (! e || ! rho || ! vx || ! vy)
+		return fail(LBMX_ERR_ARG, "lbmx_df_set_equilibrium_field: null argument");
+	return set_eq_common(e, rho, vx, vy, vz, 0, 0, 0, 0);
+}
+
+int lbmx_df_upload(lbmx_engine* e, int which, const void* host_df, int with_ghosts)
+{
+	if (! e || ! host_df || which < 0 || which > 1)
+		return fail(LBMX_ERR_ARG, "lbmx_df_upload: bad argument");
+	void* dst = which == 0 ? e->cur() : e->other();
+	if (! dst)
+		return fail(LBMX_ERR_ARG, "lbmx_df_upload: the A-A pattern has a single array");
+	return copy_components(e, dst, (void*) host_df, e->Q, e->rs, with_ghosts != 0, true);
+}
+
+int lbmx_df_download(lbmx_engine* e, int which, void* host_df, int with_ghosts)
+{
+	if (! e || ! host_df || which < 0 || which > 1)
+		return fail(LBMX_ERR_ARG, "lbmx_df_download: bad argument");
+	void* src = which == 0 ? e->cur() : e->other();
+	if (! src)
+		return fail(LBMX_ERR_ARG, "lbmx_df_download: the A-A pattern has a single array");
+	return copy_components(e, src, host_df, e->Q, e->rs, with_ghosts != 0, false);
+}
+
+int lbmx_df_sync_ghosts(lbmx_engine* e)
+{
+	if (! e)
+		return fail(LBMX_ERR_ARG, "lbmx_df_sync_ghosts: null engine");
+	int rc = exchange_full_planes(e, e->cur(), e->Q, e->rs);
+	if (rc)
+		return rc;
+	CU(cudaStreamSynchronize(e->s_main));
+	return LBMX_OK;
+}
+
+int lbmx_macro_init(lbmx_engine* e)
+{
+	if (! e)
+		return fail(LBMX_ERR_ARG, "lbmx_macro_init: null engine");
+	if (e->NM == 0)
+		return LBMX_OK;
+	CU(cudaSetDevice(e->dev));
+	const int64_t n = e->X * e->YZ;
+	const unsigned blocks = (unsigned) ((n + 127) / 128);
+	if (e->f64()) {
+		KParams<double> p = make_params<double>(e);
+		p.out_mode = e->d.macro == LBMX_MACRO_MEAN ? OUT_MEAN : OUT_DEFAULT;
+		e->kd.initial_macro<<<blocks, 128, 0, e->s_main>>>(p);
+	}
+	else {
+		KParams<float> p = make_params<float>(e);
+		p.out_mode = e->d.macro == LBMX_MACRO_MEAN ? OUT_MEAN : OUT_DEFAULT;
+		e->kf.initial_macro<<<blocks, 128, 0, e->s_main>>>(p);
+	}
+	e->stats.kernel_launches++;
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(e->s_main));
+	return LBMX_OK;
+}
+
+int lbmx_macro_download(lbmx_engine* e, void* host_macro, int with_ghosts)
+{
+	if (! e || ! host_macro)
+		return fail(LBMX_ERR_ARG, "lbmx_macro_download: null argument");
+	if (e->NM == 0)
+		return LBMX_OK;
+	return copy_components(e, e->macro, host_macro, e->NM, e->rs, with_ghosts != 0, false);
+}
+
+int lbmx_macro_upload(lbmx_engine* e, const void* host_macro, int with_ghosts)
+{
+	if (! e || ! host_macro)
+		return fail(LBMX_ERR_ARG, "lbmx_macro_upload: null argument");
+	if (e->NM == 0)
+		return LBMX_OK;
+	return copy_components(e, e->macro, (void*) host_macro, e->NM, e->rs, with_ghosts != 0, true);
+}
+
+int lbmx_set_params(lbmx_engine* e, const lbmx_params* p)
+{
+	if (! e || ! p)
+		return fail(LBMX_ERR_ARG, "lbmx_set_params: null argument");
+	if (p->lbmViscosity == 0.0)
+		return fail(LBMX_ERR_ARG, "lbmx_set_params: lbmViscosity must not be 0 (state.hpp:985-990 aborts on it)");
+	e->prm = *p;
+	return LBMX_OK;
+}
+
+int lbmx_set_inflow_profile(lbmx_engine* e, const void* host_profile, int64_t size_y, int64_t size_z)
+{
+	if (! e || ! host_profile || size_y < 1 || size_z < 1)
+		return fail(LBMX_ERR_ARG, "lbmx_set_inflow_profile: bad argument");
+	CU(cudaSetDevice(e->dev));
+	CU(cudaStreamSynchronize(e->s_main));
+	if (e->profile)
+		CU(cudaFree(e->profile));
+	e->profile = nullptr;
+	CU(cudaMalloc(&e->profile, (size_t) (size_y * size_z) * e->rs));
+	CU(cudaMemcpy(e->profile, host_profile, (size_t) (size_y * size_z) * e->rs, cudaMemcpyHostToDevice));
+	e->profile_sy = size_y;
+	return LBMX_OK;
+}
+
+int lbmx_step(lbmx_engine* e, int64_t nsteps)
+{
+	if (! e || nsteps < 0)
+		return fail(LBMX_ERR_ARG, "lbmx_step: bad argument");
+	if (e->d.inflow == LBMX_INFLOW_PROFILE_YZ && ! e->profile)
+		return fail(LBMX_ERR_STATE, "lbmx_step: inflow profile selected but lbmx_set_inflow_profile was not called");
+	return step_dispatch(e, nsteps);
+}
+
+int lbmx_sync(lbmx_engine* e)
+{
+	if (! e)
+		return fail(LBMX_ERR_ARG, "lbmx_sync: null engine");
+	CU(cudaSetDevice(e->dev));
+	CU(cudaStreamSynchronize(e->s_main));
+	CU(cudaStreamSynchronize(e->s_edge));
+	CU(cudaStreamSynchronize(e->s_comm));
+	return LBMX_OK;
+}
+
+int lbmx_step_timed(lbmx_engine* e, int64_t nsteps, float* elapsed_ms)
+{
+	if (! e || ! elapsed_ms)
+		return fail(LBMX_ERR_ARG, "lbmx_step_timed: null argument");
+	int rc = lbmx_sync(e);
+	if (rc)
+		return rc;
+	CU(cudaEventRecord(e->ev_t0, e->s_main));
+	if ((rc = lbmx_step(e, nsteps)))
+		return rc;
+	CU(cudaEventRecord(e->ev_t1, e->s_main));  // s_main has waited for the edge and communication streams
+	CU(cudaEventSynchronize(e->ev_t1));
+	CU(cudaEventElapsedTime(elapsed_ms, e->ev_t0, e->ev_t1));
+	return lbmx_sync(e);
+}
+
+int lbmx_get_iterations(const lbmx_engine* e, int64_t* it)
+{
+	if (! e || ! it)
+		return fail(LBMX_ERR_ARG, "lbmx_get_iterations: null argument");
+	*it = e->iter;
+	return LBMX_OK;
+}
+
+int lbmx_set_iterations(lbmx_engine* e, int64_t it)
+{
+	if (! e || it < 0)
+		return fail(LBMX_ERR_ARG, "lbmx_set_iterations: bad argument");
+	e->iter = it;
+	return LBMX_OK;
+}
+
+int lbmx_has_nan(lbmx_engine* e, int32_t* flag)
+{
+	if (! e || ! flag)
+		return fail(LBMX_ERR_ARG, "lbmx_has_nan: null argument");
+	*flag = 0;
+	if (e->NM == 0)
+		return LBMX_OK;
+	CU(cudaSetDevice(e->dev));
+	CU(cudaMemsetAsync(e->d_flag, 0, sizeof(int), e->s_main));
+	if (e->f64())
+		k_has_nan<double><<<592, 256, 0, e->s_main>>>((const double*) e->macro, e->XYZ, e->d_flag);
+	else
+		k_has_nan<float><<<592, 256, 0, e->s_main>>>((const float*) e->macro, e->XYZ, e->d_flag);
+	e->stats.kernel_launches++;
+	CU(cudaGetLastError());
+	int h = 0;
+	CU(cudaMemcpyAsync(&h, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->s_main));
+	CU(cudaStreamSynchronize(e->s_main));
+	*flag = h;
+	return LBMX_OK;
+}
+
+int lbmx_get_device_ptrs(lbmx_engine* e, lbmx_ptrs* out)
+{
+	if (! e || ! out)
+		return fail(LBMX_ERR_ARG, "lbmx_get_device_ptrs: null argument");
+	out->dfs[0] = e->cur();
+	out->dfs[1] = e->other();
+	out->dmacro = e->macro;
+	out->dmap = e->map;
+	out->even_iter = (e->iter % 2) == 0;
+	out->reserved = 0;
+	return LBMX_OK;
+}
+
+int lbmx_get_stats(lbmx_engine* e, lbmx_stats* out)
+{
+	if (! e || ! out)
+		return fail(LBMX_ERR_ARG, "lbmx_get_stats: null argument");
+	*out = e->stats;
+	return LBMX_OK;
+}
+
+}  // extern "C"

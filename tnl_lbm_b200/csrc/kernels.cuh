@@ -1,0 +1,483 @@
+// kernels.cuh -- the fused collide-and-stream kernels (replaces cudaLBMKernel<NSE>, include/lbm3d/kernels.h:60-100).
+//
+// Launch plan per time step and slab:
+//   k_bulk      one thread per lattice cell over an x-range of the slab; handles GEO_FLUID and GEO_PERIODIC cells
+//               (the overwhelming majority) with compile-time streaming pattern and operator, everything else returns;
+//   k_boundary  one thread per entry of the compact boundary list built at map upload; the full cell-type dispatch of
+//               D3Q27_BC_All / D2Q9_BC_All (d3q27/bc.h:51-258, d2q9/bc.h:89-213).
+// Under both streaming patterns every population slot is read and written by exactly one cell per step, so the two
+// kernels (and the slab's x-ranges) are independent of each other and may run in any order or concurrently.
+//
+// Data layout (HBM): structure of arrays, the reference's storage order kept so that raw pointers stay interchangeable
+// with block.data (lbm_data.h:49-67): element (q, x, z, y) at q*XYZ + ((x+ox)*Z + z)*Y + y, y fastest.  A warp therefore
+// touches 32 consecutive reals of one population: fully coalesced for the x/z-shifted and unshifted accesses, one extra
+// 32-byte sector for the +-1 shifts in y.  Cell indices are 32-bit; only the per-population base q*XYZ is 64-bit.
+#pragma once
+#include "collide.cuh"
+
+namespace lbmx {
+
+enum StreamMode : int { S_AB = 0, S_AA_EVEN = 1, S_AA_ODD = 2 };
+enum OutMode : int { OUT_NONE = 0, OUT_DEFAULT = 1, OUT_MEAN = 2 };
+
+template <typename R>
+struct KParams
+{
+	R* cur;			   // df_cur (A-A: the only array)
+	R* out;			   // df_out (A-B)
+	R* macro;		   // [n_macro][XYZ]
+	const int16_t* map; // [XYZ]
+	const R* profile;  // inflow vx profile [z*profile_sy + y] or nullptr
+	const uint32_t* blist;	// boundary list: storage cell indices
+	long long XYZ;	   // storage cells per component
+	int X, Y, Z, ox;   // local slab size (no ghosts), ghost planes per side
+	int YZ;
+	int x_begin, x_end; // planes handled by this launch, local coordinates in [0, X)
+	int nb_begin, nb_end; // boundary-list range handled by this launch
+	int wrap;		   // 1: the reference's nproc==1 rule (GEO_PERIODIC cells wrap), 0: ghost-plane rule
+	int profile_sy;
+	int eq, inflow, stream, out_mode, stat_counter, void_macro;
+	Phys<R> phys;
+	R in_vx, in_vy, in_vz;
+};
+
+// neighbour deltas in storage cells for one cell: kernelInitIndices (kernels.h:6-58)
+struct Deltas
+{
+	int xm, xp, ym, yp, zm, zp;
+};
+
+template <bool AA, typename R>
+LBMX_D Deltas neighbour_deltas(const KParams<R>& p, bool periodic_cell, int x, int y, int z)
+{
+	Deltas d;
+	const int YZ = p.YZ, Y = p.Y;
+	if (periodic_cell) {
+		// wrap only in the 1-process rule; with ghost planes x+-1 always exists, and y/z are never cut
+		d.xp = (p.wrap && x == p.X - 1) ? -(p.X - 1) * YZ : YZ;
+		d.xm = (p.wrap && x == 0) ? (p.X - 1) * YZ : -YZ;
+		// y and z are never cut by the slab decomposition: periodic cells always wrap there.  (With nproc > 1 the reference
+		// would step out of the array instead, kernels.h:24-28 "TODO: use nproc_y and nproc_z"; identical wherever the
+		// reference is well defined, i.e. for periodic cells away from the y/z faces.)
+		d.yp = (y == p.Y - 1) ? -(p.Y - 1) : 1;
+		d.ym = (y == 0) ? (p.Y - 1) : -1;
+		d.zp = (z == p.Z - 1) ? -(p.Z - 1) * Y : Y;
+		d.zm = (z == 0) ? (p.Z - 1) * Y : -Y;
+	}
+	else if (AA) {
+		d.xp = YZ;
+		d.xm = -YZ;
+		d.yp = 1;
+		d.ym = -1;
+		d.zp = Y;
+		d.zm = -Y;
+	}
+	else {
+		d.xp = (x == p.X - 1 + p.ox) ? 0 : YZ;
+		d.xm = (x == -p.ox) ? 0 : -YZ;
+		d.yp = (y == p.Y - 1) ? 0 : 1;
+		d.ym = (y == 0) ? 0 : -1;
+		d.zp = (z == p.Z - 1) ? 0 : Y;
+		d.zm = (z == 0) ? 0 : -Y;
+	}
+	return d;
+}
+
+template <typename L>
+LBMX_D int dir_offset(const Deltas& d, int q, int sign)
+{
+	// storage offset of the neighbour in direction sign*c_q
+	const int cx = sign * L::cx(q), cy = sign * L::cy(q), cz = sign * L::cz(q);
+	return (cx > 0 ? d.xp : cx < 0 ? d.xm : 0) + (cy > 0 ? d.yp : cy < 0 ? d.ym : 0) + (cz > 0 ? d.zp : cz < 0 ? d.zm : 0);
+}
+
+// ---- streaming (d3q27/streaming_AB.h:12-58, streaming_AA.h:12-116 and the D2Q9 twins) ----
+template <typename L, int MODE, typename R>
+LBMX_D void stream_in(const KParams<R>& p, R (&f)[L::Q], int c, const Deltas& d)
+{
+	static_for<L::Q>([&](auto qc) {
+		constexpr int q = qc;
+		if constexpr (MODE == S_AB)
+			f[q] = __ldg(p.cur + (q * p.XYZ + (c + dir_offset<L>(d, q, -1))));
+		else if constexpr (MODE == S_AA_EVEN)
+			f[q] = p.cur[q * p.XYZ + c];
+		else
+			f[L::opp(q)] = p.cur[q * p.XYZ + (c + dir_offset<L>(d, q, +1))];
+	});
+}
+
+template <typename L, int MODE, typename R>
+LBMX_D void stream_out(const KParams<R>& p, const R (&f)[L::Q], int c, const Deltas& d)
+{
+	static_for<L::Q>([&](auto qc) {
+		constexpr int q = qc;
+		if constexpr (MODE == S_AB)
+			p.out[q * p.XYZ + c] = f[q];
+		else if constexpr (MODE == S_AA_EVEN)
+			p.cur[L::opp(q) * p.XYZ + c] = f[q];
+		else
+			p.cur[q * p.XYZ + (c + dir_offset<L>(d, q, +1))] = f[q];
+	});
+}
+
+// ---- macroscopic output (d3q27/macro.h:50-171, d2q9/macro.h:49-140) ----
+template <typename L, typename R>
+LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
+{
+	if (p.out_mode == OUT_NONE)
+		return;
+	constexpr int nd = L::NDIM;
+	R* M = p.macro;
+	const long long S = p.XYZ;
+	const R v[3] = {vx, vy, vz};
+	M[c] = rho;
+#pragma unroll
+	for (int a = 0; a < nd; a++)
+		M[(1 + a) * S + c] = v[a];
+	if (p.out_mode != OUT_MEAN)
+		return;
+	// running mean + Welford co-moments, components: means then xx,yy,zz,xy,xz,yz (3-D) / xx,yy,xy (2-D)
+	const R denom = R(1) / R(p.stat_counter + 1);
+	R delta[3], delta_new[3];
+#pragma unroll
+	for (int a = 0; a < nd; a++) {
+		const R old = M[(1 + nd + a) * S + c];
+		delta[a] = v[a] - old;
+		const R now = old + delta[a] * denom;
+		delta_new[a] = v[a] - now;
+		M[(1 + nd + a) * S + c] = now;
+	}
+	constexpr int np = nd == 3 ? 6 : 3;
+	constexpr int pa[6] = {0, 1, nd == 3 ? 2 : 0, 0, 0, 1};
+	constexpr int pb[6] = {0, 1, nd == 3 ? 2 : 1, 1, 2, 2};
+#pragma unroll
+	for (int i = 0; i < np; i++) {
+		const long long o = (long long) (1 + 2 * nd + i) * S + c;
+		M[o] = M[o] + delta_new[pa[i]] * delta[pb[i]];
+	}
+}
+
+// =====================================================================================================================
+// bulk kernel: GEO_FLUID / GEO_PERIODIC cells
+// =====================================================================================================================
+template <typename L, int KIND, typename R, int MODE>
+__global__ void __launch_bounds__(128) k_bulk(const KParams<R> p)
+{
+	const int yz = blockIdx.x * blockDim.x + threadIdx.x;
+	if (yz >= p.YZ)
+		return;
+	const int x = p.x_begin + blockIdx.y;
+	const int z = yz / p.Y;
+	const int y = yz - z * p.Y;
+	const int c = (x + p.ox) * p.YZ + yz;
+	const int m = p.map[c];
+	if (! L::bulk(m))
+		return;
+	const Deltas d = neighbour_deltas<MODE != S_AB>(p, m == L::PERIODIC, x, y, z);
+	R f[L::Q];
+	stream_in<L, MODE>(p, f, c, d);
+	R rho, vx, vy, vz;
+	density_velocity(f, p.phys, rho, vx, vy, vz);
+	collide<KIND>(f, p.phys, p.eq, rho, vx, vy, vz);
+	stream_out<L, MODE>(p, f, c, d);
+	output_macro<L>(p, c, rho, vx, vy, vz);
+}
+
+// =====================================================================================================================
+// boundary kernel: every other cell type, run-time streaming mode (the slow, rare path)
+// =====================================================================================================================
+template <typename L, typename R>
+LBMX_D R load_df(const KParams<R>& p, int q, int c)
+{
+	return p.cur[q * p.XYZ + c];
+}
+
+// moment inflow condition on the left face (Eichler 2024), d3q27/bc.h:82-136: rebuilds the nine +x populations
+template <typename R>
+LBMX_D void inflow_left_moments(R (&f)[27], R& rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+#define FQ(a, b, c) f[L::find(a, b, c)]
+	const R ring0 = ((FQ(0, 1, 1) + FQ(0, -1, -1)) + (FQ(0, 1, -1) + FQ(0, -1, 1))) + ((FQ(0, 1, 0) + FQ(0, -1, 0)) + (FQ(0, 0, 1) + FQ(0, 0, -1)));
+	const R ringm = ((FQ(-1, 1, 1) + FQ(-1, -1, -1)) + (FQ(-1, 1, -1) + FQ(-1, -1, 1))) + ((FQ(-1, 1, 0) + FQ(-1, -1, 0)) + (FQ(-1, 0, 1) + FQ(-1, 0, -1)));
+	rho = R(1) / (R(1) - vx) * ((FQ(0, 0, 0) + ring0) + R(2) * (FQ(-1, 0, 0) + ringm));
+	const R third = R(1.0 / 3.0);
+	const R m100 = rho * vx, m010 = rho * vy, m001 = rho * vz;
+	const R m011 = rho * (vy * vz);
+	const R m020 = third * rho + rho * (vy * vy);
+	const R m002 = third * rho + rho * (vz * vz);
+	const R m021 = third * rho * vz + rho * ((vy * vy) * vz);
+	const R m012 = third * rho * vy + rho * (vy * (vz * vz));
+	const R m022 = R(1.0 / 9.0) * rho + third * rho * (vy * vy + vz * vz) + rho * (vy * vy) * (vz * vz);
+	FQ(1, 0, 0) = (((m100 + (m022 - (m020 + m002))) + FQ(-1, 0, 0)) + ring0) + R(2) * ringm;
+	FQ(1, 1, 0) = R(0.5) * ((m020 - m022) + (-m012 + m010)) - (FQ(-1, 1, 0) + FQ(0, 1, 0));
+	FQ(1, -1, 0) = R(0.5) * ((m020 - m022) + (m012 - m010)) - (FQ(-1, -1, 0) + FQ(0, -1, 0));
+	FQ(1, 0, 1) = R(0.5) * ((m002 - m022) + (-m021 + m001)) - (FQ(-1, 0, 1) + FQ(0, 0, 1));
+	FQ(1, 0, -1) = R(0.5) * ((m002 - m022) + (m021 - m001)) - (FQ(-1, 0, -1) + FQ(0, 0, -1));
+	FQ(1, 1, 1) = R(0.25) * ((m022 + m011) + (m021 + m012)) - (FQ(-1, 1, 1) + FQ(0, 1, 1));
+	FQ(1, 1, -1) = R(0.25) * ((m022 - m011) + (-m021 + m012)) - (FQ(-1, 1, -1) + FQ(0, 1, -1));
+	FQ(1, -1, 1) = R(0.25) * ((m022 - m011) + (m021 - m012)) - (FQ(-1, -1, 1) + FQ(0, -1, 1));
+	FQ(1, -1, -1) = R(0.25) * ((m022 + m011) + (-m021 - m012)) - (FQ(-1, -1, -1) + FQ(0, -1, -1));
+#undef FQ
+}
+template <typename R>
+LBMX_D void inflow_left_moments(R (&)[9], R&, R, R, R)
+{}
+
+// symmetry planes: populations pointing in direction DST along AXIS take the value of their mirror image
+// (d3q27/bc.h:172-237, d2q9/bc.h:168-191).  D2Q9 quirk: the straight +-y pair is addressed through shadowed names in the
+// reference and ends up a no-op (see the wall rule below), so it is skipped here as well.
+template <typename L, int AXIS, int DST, typename R>
+LBMX_D void mirror_pops(R (&f)[L::Q])
+{
+	static_for<L::Q>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int cc = AXIS == 0 ? L::cx(q) : AXIS == 1 ? L::cy(q) : L::cz(q);
+		if constexpr (cc == DST && ! (L::NDIM == 2 && AXIS == 1 && L::cx(q) == 0)) {
+			constexpr int from = AXIS == 0 ? L::find(-L::cx(q), L::cy(q), L::cz(q)) : AXIS == 1 ? L::find(L::cx(q), -L::cy(q), L::cz(q)) : L::find(L::cx(q), L::cy(q), -L::cz(q));
+			f[q] = f[from];
+		}
+	});
+}
+
+template <typename L, int KIND, typename R>
+__global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
+{
+	const int i = p.nb_begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= p.nb_end)
+		return;
+	const int c = (int) p.blist[i];
+	const int m = p.map[c];
+	// recover (x,y,z) from the storage index
+	const int xs = c / p.YZ;
+	const int yz = c - xs * p.YZ;
+	const int x = xs - p.ox;
+	const int z = yz / p.Y;
+	const int y = yz - z * p.Y;
+	const bool aa = p.stream != S_AB;
+
+	R rho = R(1), vx = R(0), vy = R(0), vz = R(0);
+	if (m == L::NOTHING) {	// neither reads nor writes distributions (bc.h:53-60,252-253); reported rho=1, u=0
+		output_macro<L>(p, c, rho, vx, vy, vz);
+		return;
+	}
+	Deltas d = aa ? neighbour_deltas<true>(p, false, x, y, z) : neighbour_deltas<false>(p, false, x, y, z);
+	const Deltas d_store = d;
+	int c_load = c;
+	if (m == L::OUTFLOW_RIGHT) {  // pull as if standing on the cell to the left: xp = x = xm (bc.h:63-65)
+		c_load = c + d.xm;
+		d.xp = 0;
+		d.xm = 0;
+	}
+	R f[L::Q];
+	if (m != L::OUTFLOW_RIGHT_INTERP) {
+		if (p.stream == S_AB)
+			stream_in<L, S_AB>(p, f, c_load, d);
+		else if (p.stream == S_AA_EVEN)
+			stream_in<L, S_AA_EVEN>(p, f, c_load, d);
+		else
+			stream_in<L, S_AA_ODD>(p, f, c_load, d);
+	}
+	else {
+		// c_s-weighted interpolation of the populations entering through the right face (streaming_AB.h:209-242); A-B only
+		constexpr R cs = R(0.5773502691896257);
+		static_for<L::Q>([&](auto qc) {
+			constexpr int q = qc;
+			const int oyz = (L::cy(q) > 0 ? d.ym : L::cy(q) < 0 ? d.yp : 0) + (L::cz(q) > 0 ? d.zm : L::cz(q) < 0 ? d.zp : 0);
+			if constexpr (L::cx(q) < 0)
+				f[q] = cs * load_df<L>(p, q, c + d.xm + oyz) + (R(1) - cs) * load_df<L>(p, q, c + oyz);
+			else
+				f[q] = load_df<L>(p, q, c + (L::cx(q) > 0 ? d.xm : 0) + oyz);
+		});
+	}
+
+	auto inflow_velocity = [&]() {
+		if (p.inflow == 1) {
+			vx = p.in_vx;
+			vy = p.in_vy;
+			if (L::NDIM == 3)
+				vz = p.in_vz;
+		}
+		else if (p.inflow == 2) {
+			vx = p.profile[y + z * p.profile_sy];
+			vy = R(0);
+			vz = R(0);
+		}
+		else {
+			rho = R(1);
+			vx = vy = vz = R(0);
+		}
+	};
+	auto set_equilibrium = [&]() {
+		R feq[L::Q];
+		equilibrium(feq, p.eq, rho, vx, vy, vz);
+		static_for<L::Q>([&](auto qc) { f[qc] = feq[qc]; });
+	};
+	if (m == L::INFLOW) {
+		inflow_velocity();
+		rho = R(1);
+		set_equilibrium();
+	}
+	else if (m == L::INFLOW_LEFT) {
+		inflow_velocity();
+		inflow_left_moments(f, rho, vx, vy, vz);
+	}
+	else if (m == L::OUTFLOW_EQ) {
+		density_velocity(f, p.phys, rho, vx, vy, vz);
+		rho = R(1);
+		set_equilibrium();
+	}
+	else if (m == L::OUTFLOW_RIGHT) {
+		density_velocity(f, p.phys, rho, vx, vy, vz);
+		rho = R(1);
+	}
+	else if (m == L::OUTFLOW_RIGHT_INTERP) {
+		density_velocity(f, p.phys, rho, vx, vy, vz);
+		R e1[L::Q], e0[L::Q];
+		equilibrium(e1, p.eq, R(1), vx, vy, vz);
+		equilibrium(e0, p.eq, rho, vx, vy, vz);
+		static_for<L::Q>([&](auto qc) { f[qc] += e1[qc] - e0[qc]; });  // setEquilibriumDecomposition (common.h:94-124)
+		rho = R(1);
+	}
+	else if (m == L::WALL) {
+		// full-way bounce-back: swap opposite populations, no collision (bc.h:147-165).
+		// REFERENCE QUIRK kept for parity: in D2Q9_BC_All::preCollision the coordinate parameters zm/zp shadow the
+		// direction enumerators (d2q9/bc.h:90 vs defs.h:262-263), so its swap(f[zm], f[zp]) degenerates to a no-op on
+		// the X x Y x 1 lattice: the straight +-y populations are NOT bounced (nor mirrored by SYM_TOP/SYM_BOTTOM).
+		static_for<L::Q>([&](auto qc) {
+			constexpr int q = qc;
+			constexpr int o = L::opp(q);
+			if constexpr (o > q && ! (L::NDIM == 2 && L::cx(q) == 0)) {
+				const R t = f[q];
+				f[q] = f[o];
+				f[o] = t;
+			}
+		});
+	}
+	else {
+		if (m == L::SYM_TOP)
+			mirror_pops<L, L::NDIM - 1, -1>(f);
+		else if (m == L::SYM_BOTTOM)
+			mirror_pops<L, L::NDIM - 1, +1>(f);
+		else if (m == L::SYM_LEFT)
+			mirror_pops<L, 0, +1>(f);
+		else if (m == L::SYM_RIGHT)
+			mirror_pops<L, 0, -1>(f);
+		else if (m == L::SYM_BACK)
+			mirror_pops<L, 1, +1>(f);
+		else if (m == L::SYM_FRONT)
+			mirror_pops<L, 1, -1>(f);
+		density_velocity(f, p.phys, rho, vx, vy, vz);
+	}
+
+	if (L::collides(m))
+		collide<KIND>(f, p.phys, p.eq, rho, vx, vy, vz);
+
+	// stored at the true (x,y,z) also for OUTFLOW_RIGHT (kernels.h:97 passes the unmodified indices)
+	if (p.stream == S_AB)
+		stream_out<L, S_AB>(p, f, c, d_store);
+	else if (p.stream == S_AA_EVEN)
+		stream_out<L, S_AA_EVEN>(p, f, c, d_store);
+	else
+		stream_out<L, S_AA_ODD>(p, f, c, d_store);
+	output_macro<L>(p, c, rho, vx, vy, vz);
+}
+
+// =====================================================================================================================
+// initialisation / service kernels
+// =====================================================================================================================
+// LBM_BLOCK::setEquilibrium (lbm_block.hpp:219-250): every storage cell including ghosts; uniform state or per-cell fields
+template <typename L, typename R>
+__global__ void k_set_equilibrium(R* df, long long XYZ, long long n_cells, long long cell0, int eq, const double* rho, const double* vx, const double* vy,
+								  const double* vz, double crho, double cvx, double cvy, double cvz)
+{
+	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_cells)
+		return;
+	// the reference narrows the `real` (double) arguments to dreal at the call of EQ::eq_* (common.h:126-158)
+	const R r = (R) (rho ? rho[i] : crho), ux = (R) (rho ? vx[i] : cvx), uy = (R) (rho ? vy[i] : cvy), uz = (R) (rho ? (vz ? vz[i] : 0.0) : cvz);
+	R feq[L::Q];
+	equilibrium(feq, eq, r, ux, uy, uz);
+	static_for<L::Q>([&](auto qc) { df[qc * XYZ + cell0 + i] = feq[qc]; });
+}
+
+// LBM_BLOCK::computeInitialMacro (lbm_block.hpp:252-277): local read, force zeroed
+template <typename L, typename R>
+__global__ void k_initial_macro(const KParams<R> p)
+{
+	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const long long n = (long long) p.X * p.YZ;
+	if (i >= n)
+		return;
+	const int c = (int) (i + (long long) p.ox * p.YZ);
+	R f[L::Q];
+	static_for<L::Q>([&](auto qc) { f[qc] = p.cur[qc * p.XYZ + c]; });
+	Phys<R> ph = p.phys;
+	ph.fx = ph.fy = ph.fz = R(0);
+	R rho, vx, vy, vz;
+	density_velocity(f, ph, rho, vx, vy, vz);
+	output_macro<L>(p, c, rho, vx, vy, vz);
+}
+
+// NaN scan of the density field (state.hpp:1170-1175)
+template <typename R>
+__global__ void k_has_nan(const R* rho, long long n, int* flag)
+{
+	bool bad = false;
+	for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+		const R v = rho[i];
+		bad |= (v != v);
+	}
+	if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+		atomicOr(flag, 1);
+}
+
+// copy `n_dirs` population planes (Y*Z reals each) between storage planes of one or two arrays: self halo exchange and packing
+template <typename R>
+__global__ void k_copy_planes(R* dst, const R* src, long long XYZ, int YZ, int n_dirs, const int* dirs, long long src_plane, long long dst_plane)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= YZ)
+		return;
+	const int q = dirs[blockIdx.y];
+	dst[q * XYZ + dst_plane * YZ + i] = src[q * XYZ + src_plane * YZ + i];
+}
+
+// launcher table filled by the per-family translation units ---------------------------------------------------------
+template <typename R>
+struct StepKernels
+{
+	void (*bulk[3])(const KParams<R>);	// by StreamMode
+	void (*boundary)(const KParams<R>);
+	void (*initial_macro)(const KParams<R>);
+	void (*set_equilibrium)(R*, long long, long long, long long, int, const double*, const double*, const double*, const double*, double, double, double, double);
+};
+
+template <typename L, int KIND, typename R>
+StepKernels<R> make_step_kernels()
+{
+	StepKernels<R> k;
+	k.bulk[S_AB] = k_bulk<L, KIND, R, S_AB>;
+	k.bulk[S_AA_EVEN] = k_bulk<L, KIND, R, S_AA_EVEN>;
+	k.bulk[S_AA_ODD] = k_bulk<L, KIND, R, S_AA_ODD>;
+	k.boundary = k_boundary<L, KIND, R>;
+	k.initial_macro = k_initial_macro<L, R>;
+	k.set_equilibrium = k_set_equilibrium<L, R>;
+	return k;
+}
+
+// one getter per (lattice, operator) family, defined in inst_*.cu; returns false if the precision is not R
+bool get_kernels_d3q27_cum(StepKernels<float>&);
+bool get_kernels_d3q27_cum(StepKernels<double>&);
+bool get_kernels_d3q27_srt(StepKernels<float>&);
+bool get_kernels_d3q27_srt(StepKernels<double>&);
+bool get_kernels_d3q27_bgk(StepKernels<float>&);
+bool get_kernels_d3q27_bgk(StepKernels<double>&);
+bool get_kernels_d3q27_mrt(StepKernels<float>&);
+bool get_kernels_d3q27_mrt(StepKernels<double>&);
+bool get_kernels_d2q9_srt(StepKernels<float>&);
+bool get_kernels_d2q9_srt(StepKernels<double>&);
+bool get_kernels_d2q9_clbm(StepKernels<float>&);
+bool get_kernels_d2q9_clbm(StepKernels<double>&);
+
+}  // namespace lbmx
