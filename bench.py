@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the fused collide-and-stream path (D3Q27 cumulant, fp64, A-A streaming) on 1..8 B200.
+
+    python bench.py --gpus 1 --steps 200 --warmup 5                      # this engine, through the C ABI (liblbmx.so)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference --gpus 1 --steps K --warmup W        # the reference's CPU implementation (oracle/_ref)
+
+Workload (BASELINE.json configs[2], SURVEY.md §8d cfg 3): periodic box of GEO_PERIODIC cells, 512^3 cells per GPU,
+D3Q27_CUM + EQ_INV_CUM, fp64, A-A streaming, nu_lbm = 1e-3, body force fx = 1e-6, smooth sinusoidal initial field.
+At N > 1 the box is N*512 x 512 x 512, split into x-slabs of 512 planes (weak scaling): one process per GPU, ghost planes
+exchanged every step with NCCL send/recv (9 populations per direction) overlapped with the interior update.
+
+One JSON line on stdout (rank 0).  `value` = whole-job MLUPS with the state resident in HBM (device time, CUDA events on the
+engine's stream, max over ranks); `e2e` = the same job through the public C ABI with HOST buffers: upload of the cell map and
+of the initial macroscopic fields from pinned host memory, all time steps, download of the macroscopic result.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+Q, SIZEOF, B_PER_UPDATE = 27, 8, 27 * 2 * 8  # algorithmic bytes per lattice update: 432 B
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------ inputs
+def initial_fields(X_global, x0, xl, Y, Z):
+    """SURVEY §8d cfg 3: rho = 1 + 0.01 sin(2 pi x/X), vx = 0.05 sin(2 pi y/Y), vy = 0.02 cos(2 pi z/Z), vz = 0.01 as
+    float64 [x][z][y] arrays of the local slab (closed form: no RNG, identical on every platform)."""
+    x = np.arange(x0, x0 + xl, dtype=np.float64)[:, None, None]
+    z = np.arange(Z, dtype=np.float64)[None, :, None]
+    y = np.arange(Y, dtype=np.float64)[None, None, :]
+    shape = (xl, Z, Y)
+    rho = np.broadcast_to(1.0 + 0.01 * np.sin(2 * np.pi * x / X_global), shape)
+    vx = np.broadcast_to(0.05 * np.sin(2 * np.pi * y / Y), shape)
+    vy = np.broadcast_to(0.02 * np.cos(2 * np.pi * z / Z), shape)
+    return rho, vx, vy, 0.01
+
+
+def pinned(shape, dtype):
+    """Page-locked host buffer as a numpy array (torch is only the allocator here)."""
+    import torch
+
+    t = torch.empty(tuple(shape), dtype={np.float64: torch.float64, np.int16: torch.int16, np.float32: torch.float32}[dtype], pin_memory=True)
+    return t, t.numpy()
+
+
+# ------------------------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if not (t0 <= t <= t1 + 0.15):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except Exception:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(size: int, steps: int, warmup: int, threads: int, streaming_aa: bool = True):
+    """The reference's own per-cell code on the host cores (oracle/_ref, `fast` build), else the C++ restatement.
+    Returns (mlups, kind, ms_per_step)."""
+    from oracle import oracle as O
+
+    st = O.AA if streaming_aa else O.AB
+    kind = "reference" if O.available("reference", st, fast=True) else "port"
+    if kind == "port" and not O.available("port", fast=True):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, stdout=subprocess.DEVNULL)
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=st, precision=O.F64, X=size, Y=size, Z=size)
+    orc = O.Oracle(d, kind, fast=True)
+    df = d.new_df()
+    rho, vx, vy, vz = initial_fields(size, 0, size, size, size)
+    orc.set_equilibrium_field(df, np.ascontiguousarray(rho), np.ascontiguousarray(vx), np.ascontiguousarray(vy), np.full(rho.shape, vz))
+    other = df if streaming_aa else df.copy()
+    mac = d.new_macro()
+    m = d.new_map(7)  # GEO_PERIODIC
+    p = O.Params(lbmViscosity=1e-3, fx=1e-6)
+    if warmup:
+        orc.step(p, df, other, mac, m, 0, warmup, threads)
+    t0 = time.perf_counter()
+    orc.step(p, df, other, mac, m, warmup, steps, threads)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(mac).all()
+    return size ** 3 * steps / dt / 1e6, kind, dt / steps * 1e3
+
+
+# ------------------------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="lbmx", choices=["lbmx", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="cells per GPU along each axis (default: the 512^3 configuration)")
+    ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the periodic sub-box the CPU arm times")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streaming", default="AA", choices=["AA", "AB"])
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N = a.gpus
+    host_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workload = f"D3Q27 cumulant (EQ_INV_CUM) fp64 A-{'A' if a.streaming == 'AA' else 'B'} periodic box, {a.size}^3 cells per GPU, nu=1e-3, fx=1e-6"
+    config = {"workload": workload, "global_lattice": [a.size * N, a.size, a.size], "decomposition": f"x-slabs x{N}", "l2_policy": "working set (29 GB/GPU) larger than L2; no flush needed",
+              "macro_policy": "written by the last step of the batch (values identical at every host-observable point)"}
+
+    # ---------------------------------------------------------------- reference arm: the CPU implementation, rank 0 only
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        mlups, kind, ms = cpu_reference_run(a.cpu_sample, a.steps, a.warmup, host_threads, a.streaming == "AA")
+        sample = f"{a.cpu_sample}^3 periodic sub-box of the same field and operator, {a.steps} steps after {a.warmup} warm-up, OpenMP collapse(2) over (x,z) as state.hpp:1116"
+        line = {"impl": "reference", "metric": "MLUPS", "value": mlups, "unit": "MLUPS", "n_gpus": N, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": host_threads, "kind": kind, "sample": sample},
+                "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------- this engine
+    import torch  # plumbing only: pinned host memory, process group
+
+    from tnl_lbm_b200 import binding as B
+
+    assert world == N, f"--gpus {N} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {N}"
+    torch.cuda.set_device(local_rank)
+    if N > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v: float) -> float:
+        if N == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S = a.size
+    Xg = S * N
+    streaming = B.AA if a.streaming == "AA" else B.AB
+    eng = B.Engine(lattice=B.D3Q27, coll=B.CUM, eq=B.EQ_INV_CUM, streaming=streaming, macro=B.MACRO_DEFAULT, inflow=B.INFLOW_NONE, precision=B.F64,
+                   X=Xg, Y=S, Z=S, rank=rank, nranks=N, device=local_rank, ghost_x=1 if N > 1 else 0, periodic_x=1, macro_policy=B.MACRO_LAST_STEP)
+    if N > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idbuf.copy_(torch.frombuffer(bytearray(B.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        eng.comm_init(bytes(idbuf.cpu().numpy().tobytes()))
+    lay = eng.layout
+    xl, x0 = lay.X_local, lay.x_offset
+    cells_local = xl * S * S
+    cells_global = Xg * S * S
+
+    # host-side inputs in pinned memory (created on the host, as a solver's setupBoundaries()/initial condition would)
+    t_in = time.perf_counter()
+    keep = []
+    tm, h_map = pinned((xl, S, S), np.int16)
+    h_map[...] = 7  # GEO_PERIODIC (d3q27/bc.h:25)
+    keep.append(tm)
+    fields = []
+    rho, vx, vy, vz = initial_fields(Xg, x0, xl, S, S)
+    for src in (rho, vx, vy, vz):
+        t, arr = pinned((xl, S, S), np.float64)
+        arr[...] = src
+        keep.append(t)
+        fields.append(arr)
+    tmac, h_mac = pinned(eng.macro_shape(), np.float64)
+    keep.append(tmac)
+    log(f"[rank {rank}] host inputs ready in {time.perf_counter() - t_in:.1f}s; slab x0={x0} xl={xl}")
+
+    def upload_state():
+        eng.map_upload(h_map)
+        eng.set_equilibrium_field(*fields)
+        eng.iterations = 0
+
+    eng.set_params(lbmViscosity=1e-3, fx=1e-6, fy=0.0, fz=0.0)
+
+    # ---- device-resident measurement: W warm-up steps, then exactly K timed steps
+    upload_state()
+    eng.step(a.warmup)
+    eng.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    s0 = eng.stats()
+    l0, hb0 = s0.kernel_launches, s0.halo_bytes_sent
+    barrier()
+    t0 = time.perf_counter()
+    ms = eng.step_timed(a.steps)  # CUDA events on the engine's compute stream, which joins the edge and comm streams
+    barrier()
+    t1 = time.perf_counter()
+    s1 = eng.stats()
+    launches, halo_bytes = s1.kernel_launches - l0, s1.halo_bytes_sent - hb0
+    clocks = sampler.stop(t0, t1)
+    ms_max = allmax(ms)
+    value = cells_global * a.steps / (ms_max * 1e-3) / 1e6
+    assert not eng.has_nan(), "NaN in the density field after the timed steps"
+
+    # ---- end-to-end through the C ABI with host buffers: upload map + initial fields, K steps, download macros
+    barrier()
+    te0 = time.perf_counter()
+    upload_state()
+    eng.step(a.steps)
+    eng.macro_download(out=h_mac)
+    eng.sync()
+    torch.cuda.synchronize()
+    te = allmax(time.perf_counter() - te0)
+    e2e_value = cells_global * a.steps / te / 1e6
+    h2d = (h_map.nbytes + sum(f.nbytes for f in fields)) * N
+    d2h = h_mac.nbytes * N
+    rho_mean = float(h_mac[0].mean())
+    assert abs(rho_mean - 1.0) < 1e-6, rho_mean
+
+    st = eng.stats()
+    line = None
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        # the bulk kernel is the only kernel of a step at N=1 (at N>1: + 2 edge launches and the exchange), so its average
+        # duration is the event time per step; per launch it processes cells_local updates of 432 algorithmic bytes each
+        achieved = cells_local * B_PER_UPDATE / (ms_max * 1e-3 / a.steps) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if tj.get("size") == S and tj.get("streaming") == a.streaming:
+                    traffic = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        line = {"metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": N, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
+                        "what": "lbmx_map_upload + lbmx_df_set_equilibrium_field from pinned host buffers, lbmx_step(K), lbmx_macro_download"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_update": B_PER_UPDATE,
+                             "kernel": f"k_bulk<D3Q27,CUM,double,{'A-A even/odd' if a.streaming == 'AA' else 'A-B'}>", "registers": st.bulk_regs, "block": st.bulk_block},
+                "halo_bytes_per_step_per_gpu": halo_bytes / a.steps}
+    eng.close()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's CPU code on a bounded sample of the same workload
+    if rank == 0 and N == 1 and not a.no_cpu_baseline:
+        try:
+            probe, kind, _ = cpu_reference_run(a.cpu_sample, 2, 1, host_threads, a.streaming == "AA")
+            nsteps = int(min(max(15.0 * probe * 1e6 / a.cpu_sample ** 3, 4), 400))  # about 15 s of CPU work
+            mlups, kind, _ = cpu_reference_run(a.cpu_sample, nsteps, 1, host_threads, a.streaming == "AA")
+            line["cpu_baseline"] = {"value": mlups, "unit": "MLUPS", "cores": host_threads, "kind": kind,
+                                    "sample": f"{a.cpu_sample}^3 periodic sub-box of the same field and operator, {nsteps} steps, OpenMP over (x,z)"}
+        except Exception as ex:  # the checker being unavailable must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": host_threads, "kind": "unavailable", "sample": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if N > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -170,3 +170,13 @@ def rel_err_elementwise(a: np.ndarray, b: np.ndarray, floor: float = 1e-300) -> 
     """max_i |a_i-b_i| / |b_i| -- used for distributions (strictly positive in all test cases)."""
     a64, b64 = a.astype(np.float64), b.astype(np.float64)
     return float(np.max(np.abs(a64 - b64) / np.maximum(np.abs(b64), floor)))
+
+
+def macro_groups(d: O.Desc):
+    """Component groups that share a physical scale: density | velocity vector | running means | co-moments.  A velocity
+    component that is identically zero by symmetry (e.g. v_y in a duct) is compared relative to |u|_max, not to itself."""
+    nd = 2 if d.lattice == O.D2Q9 else 3
+    groups = [(0, 1, "rho"), (1, 1 + nd, "velocity")]
+    if d.macro == O.MACRO_MEAN:
+        groups += [(1 + nd, 1 + 2 * nd, "mean velocity"), (1 + 2 * nd, d.n_macro, "co-moments")]
+    return groups

@@ -28,9 +28,9 @@ def compare(case, df, mac, df_ref, mac_ref, tol, what):
     e_df = lc.rel_err_elementwise(df, df_ref)
     assert e_df <= tol, f"{what}: distributions rel err {e_df:.3e} > {tol}"
     if case.desc.macro != O.MACRO_VOID:
-        for k in range(mac_ref.shape[0]):
-            e_m = lc.rel_err(mac[k], mac_ref[k])
-            assert e_m <= tol, f"{what}: macro[{k}] rel err {e_m:.3e} > {tol}"
+        for lo, hi, label in lc.macro_groups(case.desc):
+            e_m = lc.rel_err(mac[lo:hi], mac_ref[lo:hi])
+            assert e_m <= tol, f"{what}: macro {label} rel err {e_m:.3e} > {tol}"
     return e_df
 
 
@@ -90,8 +90,8 @@ def test_set_equilibrium_and_initial_macro_match_oracle():
             assert np.array_equal(e.df_download(1), got)  # every DF copy is initialised (lbm_block.hpp:247-249)
             e.macro_init()
             mac = e.macro_download()
-            for k in range(4):
-                assert lc.rel_err(mac[k], mac_ref[k]) <= (1e-14 if prec == O.F64 else 1e-6)
+            for lo, hi, _ in lc.macro_groups(d):
+                assert lc.rel_err(mac[lo:hi], mac_ref[lo:hi]) <= (1e-14 if prec == O.F64 else 1e-6)
             e.set_equilibrium(1.0, 0.01, -0.02, 0.03)
             uni = d.new_df()
             port.set_equilibrium(uni, 1.0, 0.01, -0.02, 0.03)
