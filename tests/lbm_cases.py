@@ -180,3 +180,19 @@ def macro_groups(d: O.Desc):
     if d.macro == O.MACRO_MEAN:
         groups += [(1 + nd, 1 + 2 * nd, "mean velocity"), (1 + 2 * nd, d.n_macro, "co-moments")]
     return groups
+
+
+def df_floor(d: O.Desc) -> np.ndarray:
+    """Per-population floor for the element-wise relative error: half the lattice weight w_q (the population's own scale at
+    rho = 1).  Boundary rules (moment inflow, equilibrium decomposition) can drive single populations through zero; their
+    error is then measured against w_q / 2 instead of against a value that happens to be ~0."""
+    c = C9 if d.lattice == O.D2Q9 else C27
+    n = np.abs(c).sum(axis=1)
+    w = np.array([4 / 9, 1 / 9, 1 / 36])[n] if d.lattice == O.D2Q9 else np.array([8 / 27, 2 / 27, 1 / 54, 1 / 216])[n]
+    return 0.5 * w
+
+
+def rel_err_df(a: np.ndarray, b: np.ndarray, d: O.Desc) -> float:
+    fl = df_floor(d).reshape((-1,) + (1,) * (a.ndim - 1))
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    return float(np.max(np.abs(a64 - b64) / np.maximum(np.abs(b64), fl)))

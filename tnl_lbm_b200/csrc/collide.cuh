@@ -15,6 +15,7 @@ template <typename R>
 struct Phys
 {
 	R nu;		  // lbmViscosity (KS.lbmViscosity)
+	R omega1;	  // 1 / (3 nu + 1/2), evaluated once on the host in precision R (col_cum.h:175, col_srt.h:19, col_bgk.h:19)
 	R fx, fy, fz; // homogeneous body force (NSE_Data, lbm_data.h:87-96)
 };
 
@@ -244,7 +245,7 @@ LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 		k011 = (y11[2] + y11[0]) + y11[1];
 	}
 	// ---- relaxation (col_cum.h:175,223-256): second order with omega1, trace with omega2 = 1, first order sign flip
-	const R omega1 = R(1) / (R(3) * P.nu + R(0.5));
+	const R omega1 = P.omega1;
 	const R keep = R(1) - omega1;
 	const R s110 = keep * k110, s101 = keep * k101, s011 = keep * k011;
 	const R r33 = keep * (k200 - k020), r34 = keep * (k200 - k002), r35 = k000;
@@ -305,8 +306,7 @@ template <typename R>
 LBMX_D void collide_srt(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
-	const R tau = R(3) * P.nu + R(0.5);
-	const R itau = R(1) / tau;
+	const R itau = P.omega1;
 	const R iRho = R(1) / (rho == R(0) ? R(1) : rho);
 	const R pre = (R(1) - R(0.5) * itau) * (R(3) * iRho);
 	// (c - u).F per axis and sign
@@ -326,7 +326,7 @@ template <typename R>
 LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
-	const R omega1 = R(1) / (R(3) * P.nu + R(0.5));
+	const R omega1 = P.omega1;
 	const R pre = (R(1) - R(0.5) * omega1) * (R(3) / rho);
 	const R v[3] = {vx, vy, vz};
 	R g[3][3];
@@ -407,8 +407,7 @@ template <typename R>
 LBMX_D void collide_srt(R (&f)[9], const Phys<R>& P, int, R rho, R vx, R vy, R)
 {
 	using L = D2Q9;
-	const R tau = R(3) * P.nu + R(0.5);
-	const R itau = R(1) / tau;
+	const R itau = P.omega1;
 	const R pre = R(1) - R(0.5) * itau;
 	const R fx = P.fx, fy = P.fy;
 	R F[9];

@@ -150,6 +150,7 @@ struct lbmx_engine
 	int64_t nb = 0, n_bulk = 0;
 	bool map_ready = false;
 
+	unsigned ydiv_mul = 0, ydiv_shift = 0;
 	int64_t iter = 0;
 	cudaStream_t s_main = nullptr, s_edge = nullptr, s_comm = nullptr;
 	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_main = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -183,6 +184,12 @@ KParams<R> make_params(const lbmx_engine* e)
 	p.Z = (int) e->Z;
 	p.ox = (int) e->ox;
 	p.YZ = (int) e->YZ;
+	for (int q = 0; q < e->Q; q++) {
+		p.rd[q] = p.cur + (size_t) q * e->XYZ;
+		p.wr[q] = (e->aa() ? p.cur : p.out) + (size_t) q * e->XYZ;
+	}
+	p.ydiv_mul = e->ydiv_mul;
+	p.ydiv_shift = e->ydiv_shift;
 	p.x_begin = 0;
 	p.x_end = (int) e->X;
 	p.nb_begin = 0;
@@ -198,6 +205,7 @@ KParams<R> make_params(const lbmx_engine* e)
 	p.void_macro = vm;
 	// MACRO_Void::copyQuantities is empty (d3q27/macro.h:174-188): the KernelStruct keeps lbmViscosity = 1, zero force
 	p.phys.nu = vm ? R(1) : (R) e->prm.lbmViscosity;
+	p.phys.omega1 = R(1) / (R(3) * p.phys.nu + R(0.5));	 // IEEE division in precision R: the same bits the kernels used to compute per cell
 	p.phys.fx = vm ? R(0) : (R) e->prm.fx;
 	p.phys.fy = vm ? R(0) : (R) e->prm.fy;
 	p.phys.fz = (vm || e->d.lattice == LBMX_D2Q9) ? R(0) : (R) e->prm.fz;
@@ -207,7 +215,7 @@ KParams<R> make_params(const lbmx_engine* e)
 	return p;
 }
 
-constexpr int BLOCK = 128;
+constexpr int BLOCK = LBMX_BULK_BLOCK;
 
 // launch the two step kernels over local planes [xb, xe) on `st`
 template <typename R>
@@ -534,6 +542,15 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 		e->self_exchange = e->d.periodic_x != 0;
 	}
 	e->n_hdirs = lbmx_halo_directions(d.lattice, e->h_dirs[0], e->h_dirs[1]);
+	if (e->Y > 1) {
+		// division by an invariant (Granlund-Montgomery, N = 31): L = ceil(log2 Y), mul = ceil(2^(31+L) / Y) < 2^32, exact for n < 2^31
+		unsigned L = 0;
+		while (((int64_t) 1 << L) < e->Y)
+			L++;
+		const unsigned __int128 one = 1;
+		e->ydiv_mul = (unsigned) (((one << (31 + L)) + (unsigned __int128) e->Y - 1) / (unsigned __int128) e->Y);
+		e->ydiv_shift = L - 1;
+	}
 
 #define CUX(call)                                                                                             \
 	do {                                                                                                      \

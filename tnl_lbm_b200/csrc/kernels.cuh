@@ -15,6 +15,25 @@
 #pragma once
 #include "collide.cuh"
 
+// ---- tuning knobs of the bulk kernel (defaults = the shipped configuration; tools/kbench.cu sweeps them) ----
+// Measured on B200, D3Q27 cumulant fp64, 512^3 (profiles/kbench_r1.txt): every population is touched exactly once per step,
+// so L1 allocation (plain ld) and normal-priority L2 lines (plain st) only cost: ld.cg + st.cs is worth +9 % over plain.
+#ifndef LBMX_BULK_BLOCK
+	#define LBMX_BULK_BLOCK 128	 // threads per CTA, along the (y,z) plane
+#endif
+#ifndef LBMX_BULK_MINBLOCKS
+	#define LBMX_BULK_MINBLOCKS 4  // __launch_bounds__ second argument (register cap = 65536 / (BLOCK * MINBLOCKS) = 128: 16 warps per SM)
+#endif
+#ifndef LBMX_BULK_MINBLOCKS_AB
+	#define LBMX_BULK_MINBLOCKS_AB 5  // the A-B kernel fits 96 registers without spilling and likes the extra occupancy (kbench: 6.68 vs 6.33 TB/s)
+#endif
+#ifndef LBMX_LD_HINT
+	#define LBMX_LD_HINT 2	// 0 plain, 1 ld.global.cs (evict-first), 2 ld.global.cg (L2 only), 3 ld.global.lu
+#endif
+#ifndef LBMX_ST_HINT
+	#define LBMX_ST_HINT 1	// 0 plain, 1 st.global.cs, 2 st.global.cg, 3 st.global.wt
+#endif
+
 namespace lbmx {
 
 enum StreamMode : int { S_AB = 0, S_AA_EVEN = 1, S_AA_ODD = 2 };
@@ -25,6 +44,8 @@ struct KParams
 {
 	R* cur;			   // df_cur (A-A: the only array)
 	R* out;			   // df_out (A-B)
+	R* rd[27];		   // per-population read bases  cur + q*XYZ (kernel-parameter constants: one IMAD.WIDE per access)
+	R* wr[27];		   // per-population write bases (A-B: out + q*XYZ, A-A: cur + q*XYZ)
 	R* macro;		   // [n_macro][XYZ]
 	const int16_t* map; // [XYZ]
 	const R* profile;  // inflow vx profile [z*profile_sy + y] or nullptr
@@ -32,6 +53,7 @@ struct KParams
 	long long XYZ;	   // storage cells per component
 	int X, Y, Z, ox;   // local slab size (no ghosts), ghost planes per side
 	int YZ;
+	unsigned ydiv_mul, ydiv_shift;	// floor(n / Y) = umulhi(n, ydiv_mul) >> ydiv_shift for 0 <= n < 2^31 (ydiv_mul == 0: plain division)
 	int x_begin, x_end; // planes handled by this launch, local coordinates in [0, X)
 	int nb_begin, nb_end; // boundary-list range handled by this launch
 	int wrap;		   // 1: the reference's nproc==1 rule (GEO_PERIODIC cells wrap), 0: ghost-plane rule
@@ -40,6 +62,12 @@ struct KParams
 	Phys<R> phys;
 	R in_vx, in_vy, in_vz;
 };
+
+template <typename R>
+LBMX_D int div_by_Y(const KParams<R>& p, int n)
+{
+	return p.ydiv_mul ? (int) (__umulhi((unsigned) n, p.ydiv_mul) >> p.ydiv_shift) : n / p.Y;
+}
 
 // neighbour deltas in storage cells for one cell: kernelInitIndices (kernels.h:6-58)
 struct Deltas
@@ -87,8 +115,40 @@ template <typename L>
 LBMX_D int dir_offset(const Deltas& d, int q, int sign)
 {
 	// storage offset of the neighbour in direction sign*c_q
-	const int cx = sign * L::cx(q), cy = sign * L::cy(q), cz = sign * L::cz(q);
+	const int cx = sign * L::cx(q), cz = sign * L::cz(q);
+#ifdef LBMX_EXP_NOYSHIFT  // development experiment only (tools/kbench.cu): wrong physics, isolates the cost of the +-1 shifts in y
+	const int cy = 0;
+#else
+	const int cy = sign * L::cy(q);
+#endif
 	return (cx > 0 ? d.xp : cx < 0 ? d.xm : 0) + (cy > 0 ? d.yp : cy < 0 ? d.ym : 0) + (cz > 0 ? d.zp : cz < 0 ? d.zm : 0);
+}
+
+template <typename R>
+LBMX_D R ld_df(const R* ptr)
+{
+#if LBMX_LD_HINT == 1
+	return __ldcs(ptr);
+#elif LBMX_LD_HINT == 2
+	return __ldcg(ptr);
+#elif LBMX_LD_HINT == 3
+	return __ldlu(ptr);
+#else
+	return *ptr;
+#endif
+}
+template <typename R>
+LBMX_D void st_df(R* ptr, R v)
+{
+#if LBMX_ST_HINT == 1
+	__stcs(ptr, v);
+#elif LBMX_ST_HINT == 2
+	__stcg(ptr, v);
+#elif LBMX_ST_HINT == 3
+	__stwt(ptr, v);
+#else
+	*ptr = v;
+#endif
 }
 
 // ---- streaming (d3q27/streaming_AB.h:12-58, streaming_AA.h:12-116 and the D2Q9 twins) ----
@@ -98,11 +158,11 @@ LBMX_D void stream_in(const KParams<R>& p, R (&f)[L::Q], int c, const Deltas& d)
 	static_for<L::Q>([&](auto qc) {
 		constexpr int q = qc;
 		if constexpr (MODE == S_AB)
-			f[q] = __ldg(p.cur + (q * p.XYZ + (c + dir_offset<L>(d, q, -1))));
+			f[q] = __ldg(p.rd[q] + (c + dir_offset<L>(d, q, -1)));
 		else if constexpr (MODE == S_AA_EVEN)
-			f[q] = p.cur[q * p.XYZ + c];
+			f[q] = ld_df(p.rd[q] + c);
 		else
-			f[L::opp(q)] = p.cur[q * p.XYZ + (c + dir_offset<L>(d, q, +1))];
+			f[L::opp(q)] = ld_df(p.rd[q] + (c + dir_offset<L>(d, q, +1)));
 	});
 }
 
@@ -112,11 +172,11 @@ LBMX_D void stream_out(const KParams<R>& p, const R (&f)[L::Q], int c, const Del
 	static_for<L::Q>([&](auto qc) {
 		constexpr int q = qc;
 		if constexpr (MODE == S_AB)
-			p.out[q * p.XYZ + c] = f[q];
+			st_df(p.wr[q] + c, f[q]);
 		else if constexpr (MODE == S_AA_EVEN)
-			p.cur[L::opp(q) * p.XYZ + c] = f[q];
+			st_df(p.wr[L::opp(q)] + c, f[q]);
 		else
-			p.cur[q * p.XYZ + (c + dir_offset<L>(d, q, +1))] = f[q];
+			st_df(p.wr[q] + (c + dir_offset<L>(d, q, +1)), f[q]);
 	});
 }
 
@@ -160,25 +220,53 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 // =====================================================================================================================
 // bulk kernel: GEO_FLUID / GEO_PERIODIC cells
 // =====================================================================================================================
+// resident CTAs per SM the register allocation is sized for: the cumulant / MRT_LES kernels fit 128 (A-A) and 96 (A-B)
+// registers without spilling; fp64 SRT and BGK keep f[27], feq[27] and the source terms live and get 170
+template <int KIND, typename R, int MODE>
+constexpr int bulk_minblocks()
+{
+	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK))
+		return LBMX_BULK_MINBLOCKS < 3 ? LBMX_BULK_MINBLOCKS : 3;
+	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;
+}
+
 template <typename L, int KIND, typename R, int MODE>
-__global__ void __launch_bounds__(128) k_bulk(const KParams<R> p)
+__global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>()) k_bulk(const KParams<R> p)
 {
 	const int yz = blockIdx.x * blockDim.x + threadIdx.x;
 	if (yz >= p.YZ)
 		return;
 	const int x = p.x_begin + blockIdx.y;
-	const int z = yz / p.Y;
+	const int z = div_by_Y(p, yz);
 	const int y = yz - z * p.Y;
 	const int c = (x + p.ox) * p.YZ + yz;
 	const int m = p.map[c];
-	if (! L::bulk(m))
-		return;
-	const Deltas d = neighbour_deltas<MODE != S_AB>(p, m == L::PERIODIC, x, y, z);
 	R f[L::Q];
-	stream_in<L, MODE>(p, f, c, d);
+	Deltas d;
+	if constexpr (MODE == S_AB) {
+		if (! L::bulk(m))
+			return;
+		d = neighbour_deltas<false>(p, m == L::PERIODIC, x, y, z);
+		stream_in<L, MODE>(p, f, c, d);
+	}
+	else {
+		// A-A: the neighbour offsets do not depend on the cell type, so the 27 population loads are issued before the
+		// cell-type load has returned (one memory latency off the critical path of a latency-bound kernel).  GEO_FLUID
+		// cells on an unghosted domain face therefore wrap like GEO_PERIODIC ones; the reference leaves that case
+		// undefined (it steps out of the array: kernels.h:31-38), everywhere else the rule is the same.
+		d = neighbour_deltas<true>(p, true, x, y, z);
+		stream_in<L, MODE>(p, f, c, d);
+		if (! L::bulk(m))
+			return;
+	}
 	R rho, vx, vy, vz;
+#ifdef LBMX_EXP_NOCOLLIDE  // development experiment only: streaming without arithmetic = the memory-system ceiling of this access pattern
+	rho = f[0];
+	vx = vy = vz = R(0);
+#else
 	density_velocity(f, p.phys, rho, vx, vy, vz);
 	collide<KIND>(f, p.phys, p.eq, rho, vx, vy, vz);
+#endif
 	stream_out<L, MODE>(p, f, c, d);
 	output_macro<L>(p, c, rho, vx, vy, vz);
 }
