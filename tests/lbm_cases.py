@@ -196,3 +196,23 @@ def rel_err_df(a: np.ndarray, b: np.ndarray, d: O.Desc) -> float:
     fl = df_floor(d).reshape((-1,) + (1,) * (a.ndim - 1))
     a64, b64 = a.astype(np.float64), b.astype(np.float64)
     return float(np.max(np.abs(a64 - b64) / np.maximum(np.abs(b64), fl)))
+
+
+def map_duct_slab_safe(d: O.Desc) -> np.ndarray:
+    """Duct with periodic x whose only non-inert cells on the x faces are GEO_PERIODIC (the rest of the wall ring / shell is
+    GEO_NOTHING there), and whose periodic cells never touch a y/z face.  On such a map the reference's 1-process wrap rule
+    and its ghost-plane rule (kernels.h:21-57) address exactly the same neighbours, under A-B and A-A alike -- so an
+    undivided run and an N-slab run must agree bit for bit."""
+    g = geo(d)
+    if d.lattice == O.D2Q9:
+        m = d.new_map(g["FLUID"])
+        m[0, :, :] = g["PERIODIC"]
+        m[d.X - 1, :, :] = g["PERIODIC"]
+        m[:, :, 0] = g["WALL"]
+        m[:, :, d.Y - 1] = g["WALL"]
+    else:
+        m = map_duct_periodic_x(d)
+    for xf in (0, d.X - 1):
+        plane = m[xf]
+        plane[plane != g["PERIODIC"]] = g["NOTHING"]
+    return m

@@ -1,0 +1,82 @@
+"""Slab decomposition on the GPU: ghost planes, boundary-planes-first ordering and the halo exchange of the engine.
+
+* 1 GPU: a single slab with ghost planes and a periodic self-exchange must reproduce the run without ghost planes.
+* >= 2 GPUs (gpurun --gpus 2): one process per GPU, the engine's own NCCL send/recv; the assembled result must equal the
+  undivided oracle run within the fp64 tolerance, and be identical to the 1-slab self-exchange run of the engine."""
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import lbm_cases as lc
+from engine_runner import run_case_engine
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def run_ghost_single(case):
+    """Engine, one slab, ghost planes + periodic self-exchange."""
+    from engine_runner import engine_for, set_params
+
+    d = case.desc
+    port = O.Oracle(d, "port")
+    df0 = gc.initial_df(case, port)
+    with engine_for(case, ghost_x=1, periodic_x=1) as e:
+        e.map_upload(case.make_map(d))
+        e.df_upload(df0, 0)
+        e.df_sync_ghosts()
+        if d.streaming == O.AB:
+            e.df_upload(df0, 1)
+        set_params(e, case.params)
+        e.macro_init()
+        e.step(case.nsteps)
+        e.sync()
+        st = e.stats()
+        assert st.halo_bytes_sent > 0
+        return e.df_download(0), e.macro_download()
+
+
+@pytest.mark.parametrize("case_name", ["duct_ab", "duct_aa", "box_ab", "box_aa"])
+def test_ghost_planes_with_self_exchange_equal_plain_run(case_name):
+    import dist_workers as W
+
+    case = W.DIST_CASES[case_name]()
+    plain_df, plain_mac, _ = run_case_engine(case)
+    df, mac = run_ghost_single(case)
+    assert np.array_equal(df, plain_df), f"max diff {np.abs(df - plain_df).max():.3e}"
+    assert np.array_equal(mac, plain_mac)
+    ref_df, ref_mac = gc.run_case(case, "port", nthreads=4)
+    assert lc.rel_err_df(df, ref_df, case.desc) <= 1e-12
+
+
+@pytest.mark.parametrize("case_name", ["duct_ab", "duct_aa", "box_ab", "box_aa"])
+def test_two_gpus_nccl_halo_exchange(case_name):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    import dist_workers as W
+
+    world = 2
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(W.nccl_engine_worker, args=(world, free_port(), case_name, tmp), nprocs=world, join=True)
+        df, mac = W.gather(tmp, world)
+        halo = np.load(f"{tmp}/halo_0.npy")
+    case = W.DIST_CASES[case_name]()
+    assert halo[0] == case.nsteps * 2 * 9 * case.desc.Y * case.desc.Z * 8, "9 populations per direction per step"
+    one_df, one_mac = run_ghost_single(case)
+    assert np.array_equal(df, one_df), "2 slabs over NCCL must be identical to 1 slab with self-exchange"
+    assert np.array_equal(mac, one_mac)
+    ref_df, ref_mac = gc.run_case(case, "port", nthreads=4)
+    assert lc.rel_err_df(df, ref_df, case.desc) <= 1e-12
