@@ -257,7 +257,9 @@ int exchange(lbmx_engine* e, void* arr)
 		// single slab with ghost planes and periodic x: the neighbour on both sides is this slab
 		for (int k = 0; k < 2; k++) {
 			const lbmx_halo_msg& m = msgs[k];
-			k_copy_planes<R><<<grid, 256, 0, e->s_comm>>>(a, a, e->XYZ, (int) e->YZ, nd, e->d_dirs + (m.to_right ? 0 : 9), m.src_plane, m.dst_plane);
+			// which population slots travel depends on the streaming parity (A-A even steps carry the opposite slots), not on the direction
+			const int* dirs = e->d_dirs + (m.dirs[0] == e->h_dirs[0][0] ? 0 : 9);
+			k_copy_planes<R><<<grid, 256, 0, e->s_comm>>>(a, a, e->XYZ, (int) e->YZ, nd, dirs, m.src_plane, m.dst_plane);
 			e->stats.kernel_launches++;
 			e->stats.halo_bytes_sent += (int64_t) nd * plane_bytes(e);
 		}
@@ -693,15 +695,17 @@ static int exchange_full_planes(lbmx_engine* e, void* arr, int ncomp, size_t ele
 	if (! e->comm)
 		return fail(LBMX_ERR_STATE, "ghost-plane synchronisation needs lbmx_comm_init first");
 	NC(g_nccl.GroupStart());
+	// Posting order matters when both neighbours are the same rank (2 slabs, periodic): NCCL pairs the sends and receives of
+	// a rank pair in posting order, so "what goes right" must be posted together with "what comes from the left".
 	for (int c = 0; c < ncomp; c++) {
-		if (e->right >= 0) {
+		if (e->right >= 0)
 			NC(g_nccl.Send(plane(c, e->X), pb, ncclInt8, e->right, e->comm, e->s_main));
-			NC(g_nccl.Recv(plane(c, e->X + 1), pb, ncclInt8, e->right, e->comm, e->s_main));
-		}
-		if (e->left >= 0) {
-			NC(g_nccl.Send(plane(c, 1), pb, ncclInt8, e->left, e->comm, e->s_main));
+		if (e->left >= 0)
 			NC(g_nccl.Recv(plane(c, 0), pb, ncclInt8, e->left, e->comm, e->s_main));
-		}
+		if (e->left >= 0)
+			NC(g_nccl.Send(plane(c, 1), pb, ncclInt8, e->left, e->comm, e->s_main));
+		if (e->right >= 0)
+			NC(g_nccl.Recv(plane(c, e->X + 1), pb, ncclInt8, e->right, e->comm, e->s_main));
 	}
 	NC(g_nccl.GroupEnd());
 	return LBMX_OK;
