@@ -1,0 +1,117 @@
+// channel3d.cpp -- a solver written against the host mirror of TNL-LBM's interface (tnl_lbm_b200/host/lbm3d/core.h), in the
+// style of the reference's sim_NSE/sim_1.cu: compose LBM_CONFIG, derive StateLocal from State<NSE>, paint the map, execute().
+// Orifice channel: moment inflow on the left (GEO_INFLOW_LEFT), GEO_OUTFLOW_RIGHT, walls behind a GEO_NOTHING shell.
+//
+//   g++ -std=c++17 -Itnl_lbm_b200/host -Iinclude examples/channel3d.cpp -Ltnl_lbm_b200 -llbmx -o channel3d
+//   ./channel3d X Y Z steps out_prefix [AA]     -> out_prefix.map (int16) and out_prefix.macro (dreal), reference layout
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+
+#include "lbm3d/core.h"
+
+template <typename NSE>
+struct StateLocal : State<NSE>
+{
+	using TRAITS = typename NSE::TRAITS;
+	using BC = typename NSE::BC;
+	using MACRO = typename NSE::MACRO;
+	using State<NSE>::nse;
+	using real = typename TRAITS::real;
+	using idx = typename TRAITS::idx;
+	using lat_t = Lattice<3, real, idx>;
+
+	real lbm_inflow_vx = 0;
+	double probed_mass = 0;
+
+	void setupBoundaries() override
+	{
+		const idx X = nse.lat.global.x(), Y = nse.lat.global.y(), Z = nse.lat.global.z();
+		nse.setBoundaryX(0, BC::GEO_INFLOW_LEFT);
+		nse.setBoundaryX(X - 1, BC::GEO_OUTFLOW_RIGHT);
+		nse.setBoundaryZ(1, BC::GEO_WALL);
+		nse.setBoundaryZ(Z - 2, BC::GEO_WALL);
+		nse.setBoundaryY(1, BC::GEO_WALL);
+		nse.setBoundaryY(Y - 2, BC::GEO_WALL);
+		nse.setBoundaryZ(0, BC::GEO_NOTHING);
+		nse.setBoundaryZ(Z - 1, BC::GEO_NOTHING);
+		nse.setBoundaryY(0, BC::GEO_NOTHING);
+		nse.setBoundaryY(Y - 1, BC::GEO_NOTHING);
+		const idx cx = X / 5, width = Z / 10;
+		for (idx px = cx; px <= cx + width; px++)
+			for (idx pz = 1; pz <= Z - 2; pz++)
+				for (idx py = 1; py <= Y - 2; py++)
+					if (! (pz >= Z * 4 / 10 && pz <= Z * 6 / 10 && py >= Y * 4 / 10 && py <= Y * 6 / 10))
+						nse.setMap(px, py, pz, BC::GEO_WALL);
+	}
+	void updateKernelVelocities() override
+	{
+		for (auto& block : nse.blocks) {
+			block.data.inflow_vx = lbm_inflow_vx;
+			block.data.inflow_vy = 0;
+			block.data.inflow_vz = 0;
+		}
+	}
+	void probe1() override
+	{
+		// total mass from the host copy of the density field (copied on this cadence by SimUpdate)
+		probed_mass = 0;
+		nse.forLocalLatticeSites([&](auto& block, idx x, idx y, idx z) { probed_mass += block.hmacro(MACRO::e_rho, x, y, z); });
+	}
+	StateLocal(const std::string& id, const TNL::MPI::Comm& communicator, lat_t lat) : State<NSE>(id, communicator, std::move(lat)) {}
+};
+
+template <typename TRAITS>
+int run(int X, int Y, int Z, int steps, const char* prefix)
+{
+	using COLL = D3Q27_CUM<TRAITS, D3Q27_EQ_INV_CUM<TRAITS>>;
+	using NSE = LBM_CONFIG<TRAITS, D3Q27_KernelStruct, NSE_Data_ConstInflow<TRAITS>, COLL, typename COLL::EQ, D3Q27_STREAMING<TRAITS>, D3Q27_BC_All,
+						   D3Q27_MACRO_Default<TRAITS>>;
+	using real = typename TRAITS::real;
+	using lat_t = Lattice<3, real, typename TRAITS::idx>;
+
+	const real LBM_VISCOSITY = 1e-3, PHYS_VISCOSITY = 1.5e-5, PHYS_DL = 0.41 / ((real) Y - 2);
+	lat_t lat;
+	lat.global = typename lat_t::CoordinatesType(X, Y, Z);
+	lat.physDl = PHYS_DL;
+	lat.physDt = LBM_VISCOSITY / PHYS_VISCOSITY * PHYS_DL * PHYS_DL;
+	lat.physViscosity = PHYS_VISCOSITY;
+
+	StateLocal<NSE> state("channel3d", MPI_COMM_WORLD, lat);
+	if (! state.canCompute())
+		return 0;
+	state.lbm_inflow_vx = 0.04;
+	state.nse.physFinalTime = (steps - 0.5) * lat.physDt;
+	state.cnt[PRINT].period = 10 * lat.physDt;
+	state.cnt[PROBE1].period = 5 * lat.physDt;
+	execute(state);
+
+	auto& block = state.nse.blocks.front();
+	state.nse.copyMacroToHost();
+	state.nse.copyMapToHost();
+	std::ofstream(std::string(prefix) + ".map", std::ios::binary).write((const char*) block.hmap.v.data(), block.hmap.v.size() * sizeof(short));
+	std::ofstream(std::string(prefix) + ".macro", std::ios::binary)
+		.write((const char*) block.hmacro.v.data(), block.hmacro.v.size() * sizeof(typename TRAITS::dreal));
+	std::printf("iterations=%d mass=%.12f lbmViscosity=%.17g inflow_vx=%.17g\n", state.nse.iterations, state.probed_mass, (double) block.data.lbmViscosity,
+				(double) block.data.inflow_vx);
+	return 0;
+}
+
+int main(int argc, char** argv)
+{
+	TNLMPI_INIT mpi(argc, argv);
+	if (argc < 6) {
+		std::fprintf(stderr, "usage: %s X Y Z steps out_prefix [f32]\n", argv[0]);
+		return 1;
+	}
+	const bool f32 = argc > 6 && std::strcmp(argv[6], "f32") == 0;
+	try {
+		return f32 ? run<TraitsSP>(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5])
+				   : run<TraitsDP>(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
+	}
+	catch (const std::exception& e) {
+		std::fprintf(stderr, "error: %s\n", e.what());
+		return 2;
+	}
+}
