@@ -227,7 +227,8 @@ int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, 
 	p.x_end = xe;
 	p.nb_begin = (int) e->plane_start[xb];
 	p.nb_end = (int) e->plane_start[xe];
-	dim3 grid((unsigned) ((e->YZ + BLOCK - 1) / BLOCK), (unsigned) (xe - xb));
+	const int per_cta = BLOCK * K.cpt[p.stream];
+	dim3 grid((unsigned) ((e->YZ + per_cta - 1) / per_cta), (unsigned) (xe - xb));
 	K.bulk[p.stream]<<<grid, BLOCK, 0, st>>>(p);
 	e->stats.kernel_launches++;
 	const int nbl = p.nb_end - p.nb_begin;

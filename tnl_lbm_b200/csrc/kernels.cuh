@@ -111,13 +111,18 @@ LBMX_D Deltas neighbour_deltas(const KParams<R>& p, bool periodic_cell, int x, i
 	return d;
 }
 
-template <typename L>
+template <typename L, int WHICH = 0>
 LBMX_D int dir_offset(const Deltas& d, int q, int sign)
 {
 	// storage offset of the neighbour in direction sign*c_q
 	const int cx = sign * L::cx(q), cz = sign * L::cz(q);
-#ifdef LBMX_EXP_NOYSHIFT  // development experiment only (tools/kbench.cu): wrong physics, isolates the cost of the +-1 shifts in y
+	// development experiments only (tools/kbench.cu): wrong physics, isolate the cost of the +-1 shifts in y (WHICH: 1 = load, 2 = store)
+#if defined(LBMX_EXP_NOYSHIFT)
 	const int cy = 0;
+#elif defined(LBMX_EXP_NOYSHIFT_LD)
+	const int cy = WHICH == 1 ? 0 : sign * L::cy(q);
+#elif defined(LBMX_EXP_NOYSHIFT_ST)
+	const int cy = WHICH == 2 ? 0 : sign * L::cy(q);
 #else
 	const int cy = sign * L::cy(q);
 #endif
@@ -152,31 +157,44 @@ LBMX_D void st_df(R* ptr, R v)
 }
 
 // ---- streaming (d3q27/streaming_AB.h:12-58, streaming_AA.h:12-116 and the D2Q9 twins) ----
-template <typename L, int MODE, typename R>
+// NONNEG: the caller guarantees cell + offset >= 0 (bulk kernel: offsets wrap), so the index is zero-extended for free.
+// The boundary kernel keeps signed indices: under A-A a non-periodic cell on an unghosted face addresses x-1 / x+1 outside
+// its slice exactly as the reference does (kernels.h:31-38) -- that lands in the neighbouring population's slice, never outside
+// the allocation (slot 0 has no shift, the last slot only shifts towards lower x), so it is memory-safe though ill-defined.
+template <bool NONNEG>
+LBMX_D long long cell_index(int i)
+{
+	if constexpr (NONNEG)
+		return (long long) (unsigned) i;
+	else
+		return (long long) i;
+}
+
+template <typename L, int MODE, bool NONNEG = false, typename R>
 LBMX_D void stream_in(const KParams<R>& p, R (&f)[L::Q], int c, const Deltas& d)
 {
 	static_for<L::Q>([&](auto qc) {
 		constexpr int q = qc;
 		if constexpr (MODE == S_AB)
-			f[q] = __ldg(p.rd[q] + (c + dir_offset<L>(d, q, -1)));
+			f[q] = __ldg(p.rd[q] + cell_index<NONNEG>(c + dir_offset<L, 1>(d, q, -1)));
 		else if constexpr (MODE == S_AA_EVEN)
-			f[q] = ld_df(p.rd[q] + c);
+			f[q] = ld_df(p.rd[q] + cell_index<NONNEG>(c));
 		else
-			f[L::opp(q)] = ld_df(p.rd[q] + (c + dir_offset<L>(d, q, +1)));
+			f[L::opp(q)] = ld_df(p.rd[q] + cell_index<NONNEG>(c + dir_offset<L, 1>(d, q, +1)));
 	});
 }
 
-template <typename L, int MODE, typename R>
+template <typename L, int MODE, bool NONNEG = false, typename R>
 LBMX_D void stream_out(const KParams<R>& p, const R (&f)[L::Q], int c, const Deltas& d)
 {
 	static_for<L::Q>([&](auto qc) {
 		constexpr int q = qc;
 		if constexpr (MODE == S_AB)
-			st_df(p.wr[q] + c, f[q]);
+			st_df(p.wr[q] + cell_index<NONNEG>(c), f[q]);
 		else if constexpr (MODE == S_AA_EVEN)
-			st_df(p.wr[L::opp(q)] + c, f[q]);
+			st_df(p.wr[L::opp(q)] + cell_index<NONNEG>(c), f[q]);
 		else
-			st_df(p.wr[q] + (c + dir_offset<L>(d, q, +1)), f[q]);
+			st_df(p.wr[q] + cell_index<NONNEG>(c + dir_offset<L, 2>(d, q, +1)), f[q]);
 	});
 }
 
@@ -230,45 +248,74 @@ constexpr int bulk_minblocks()
 	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;
 }
 
+// cells per thread: a thread of the bulk kernel handles CPT cells, BLOCK cells apart (so every warp access still covers 32
+// consecutive cells).  All CPT x Q loads are issued before the first collision starts: more bytes in flight per SM at the same
+// occupancy, which is what the narrow cases need (fp32: 128 B per warp access; D2Q9: 9 loads per cell).
+// Chosen per lattice / precision / streaming mode from the tools/kbench sweep (profiles/kbench_r1_cpt.txt).
+template <typename L, typename R, int MODE>
+constexpr int bulk_cpt()
+{
+#ifdef LBMX_BULK_CPT
+	return LBMX_BULK_CPT;
+#else
+	if (L::Q == 27)
+		return sizeof(R) == 8 ? 1 : (MODE == S_AA_ODD ? 1 : 2);
+	return sizeof(R) == 8 ? (MODE == S_AB ? 1 : 2) : 2;
+#endif
+}
+
 template <typename L, int KIND, typename R, int MODE>
 __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>()) k_bulk(const KParams<R> p)
 {
-	const int yz = blockIdx.x * blockDim.x + threadIdx.x;
-	if (yz >= p.YZ)
-		return;
+	constexpr int CPT = bulk_cpt<L, R, MODE>();
 	const int x = p.x_begin + blockIdx.y;
-	const int z = div_by_Y(p, yz);
-	const int y = yz - z * p.Y;
-	const int c = (x + p.ox) * p.YZ + yz;
-	const int m = p.map[c];
-	R f[L::Q];
-	Deltas d;
-	if constexpr (MODE == S_AB) {
-		if (! L::bulk(m))
-			return;
-		d = neighbour_deltas<false>(p, m == L::PERIODIC, x, y, z);
-		stream_in<L, MODE>(p, f, c, d);
+	const int yz0 = blockIdx.x * (LBMX_BULK_BLOCK * CPT) + threadIdx.x;
+	R f[CPT][L::Q];
+	Deltas d[CPT];
+	int c[CPT], m[CPT];
+	bool face[CPT];
+	// ---- phase 1: every load of every cell of this thread
+#pragma unroll
+	for (int k = 0; k < CPT; k++) {
+		const int yz = yz0 + k * LBMX_BULK_BLOCK;
+		m[k] = -1;
+		if (yz < p.YZ) {
+			const int z = div_by_Y(p, yz);
+			const int y = yz - z * p.Y;
+			c[k] = (x + p.ox) * p.YZ + yz;
+			m[k] = p.map[c[k]];
+			// The neighbour offsets are formed with the periodic (wrapping) rule, which does not depend on the cell type and is
+			// always in bounds: the Q population loads are in flight before the cell-type load has returned (one memory latency
+			// off the critical path of a latency-bound kernel).  A-A: GEO_FLUID cells on an unghosted domain face thereby wrap
+			// like GEO_PERIODIC ones; the reference leaves that case undefined (it steps out of the array: kernels.h:31-38,
+			// SURVEY.md App. A).  A-B: such cells clamp in the reference (kernels.h:49-56) -- they are re-loaded below.
+			d[k] = neighbour_deltas<true>(p, true, x, y, z);
+			face[k] = (p.ox == 0 && (x == 0 || x == p.X - 1)) || y == 0 || y == p.Y - 1 || z == 0 || z == p.Z - 1;
+			stream_in<L, MODE, true>(p, f[k], c[k], d[k]);
+			if constexpr (MODE == S_AB) {
+				if (face[k] && m[k] == L::FLUID) {
+					d[k] = neighbour_deltas<false>(p, false, x, y, z);
+					stream_in<L, MODE, true>(p, f[k], c[k], d[k]);
+				}
+			}
+		}
 	}
-	else {
-		// A-A: the neighbour offsets do not depend on the cell type, so the 27 population loads are issued before the
-		// cell-type load has returned (one memory latency off the critical path of a latency-bound kernel).  GEO_FLUID
-		// cells on an unghosted domain face therefore wrap like GEO_PERIODIC ones; the reference leaves that case
-		// undefined (it steps out of the array: kernels.h:31-38), everywhere else the rule is the same.
-		d = neighbour_deltas<true>(p, true, x, y, z);
-		stream_in<L, MODE>(p, f, c, d);
-		if (! L::bulk(m))
-			return;
-	}
-	R rho, vx, vy, vz;
+	// ---- phase 2: collide and store, cell by cell
+#pragma unroll
+	for (int k = 0; k < CPT; k++) {
+		if (m[k] < 0 || ! L::bulk(m[k]))
+			continue;
+		R rho, vx, vy, vz;
 #ifdef LBMX_EXP_NOCOLLIDE  // development experiment only: streaming without arithmetic = the memory-system ceiling of this access pattern
-	rho = f[0];
-	vx = vy = vz = R(0);
+		rho = f[k][0];
+		vx = vy = vz = R(0);
 #else
-	density_velocity(f, p.phys, rho, vx, vy, vz);
-	collide<KIND>(f, p.phys, p.eq, rho, vx, vy, vz);
+		density_velocity(f[k], p.phys, rho, vx, vy, vz);
+		collide<KIND>(f[k], p.phys, p.eq, rho, vx, vy, vz);
 #endif
-	stream_out<L, MODE>(p, f, c, d);
-	output_macro<L>(p, c, rho, vx, vy, vz);
+		stream_out<L, MODE, true>(p, f[k], c[k], d[k]);
+		output_macro<L>(p, c[k], rho, vx, vy, vz);
+	}
 }
 
 // =====================================================================================================================
@@ -536,6 +583,7 @@ template <typename R>
 struct StepKernels
 {
 	void (*bulk[3])(const KParams<R>);	// by StreamMode
+	int cpt[3];						// cells per thread of the bulk kernels, by StreamMode
 	void (*boundary)(const KParams<R>);
 	void (*initial_macro)(const KParams<R>);
 	void (*set_equilibrium)(R*, long long, long long, long long, int, const double*, const double*, const double*, const double*, double, double, double, double);
@@ -548,6 +596,9 @@ StepKernels<R> make_step_kernels()
 	k.bulk[S_AB] = k_bulk<L, KIND, R, S_AB>;
 	k.bulk[S_AA_EVEN] = k_bulk<L, KIND, R, S_AA_EVEN>;
 	k.bulk[S_AA_ODD] = k_bulk<L, KIND, R, S_AA_ODD>;
+	k.cpt[S_AB] = bulk_cpt<L, R, S_AB>();
+	k.cpt[S_AA_EVEN] = bulk_cpt<L, R, S_AA_EVEN>();
+	k.cpt[S_AA_ODD] = bulk_cpt<L, R, S_AA_ODD>();
 	k.boundary = k_boundary<L, KIND, R>;
 	k.initial_macro = k_initial_macro<L, R>;
 	k.set_equilibrium = k_set_equilibrium<L, R>;
