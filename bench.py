@@ -137,6 +137,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the periodic sub-box the CPU arm times")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streaming", default="AA", choices=["AA", "AB"])
+    ap.add_argument("--workload", default="box", choices=["box", "channel"],
+                    help="box: periodic 512^3 per GPU, weak scaling (the headline metric); channel: BASELINE.json configs[3], the 2048x512x512 "
+                         "body-force duct of sim_NSE/sim_2.cu split into N x-slabs, strong scaling (N >= 2)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -145,8 +148,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     N = a.gpus
     host_threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    workload = f"D3Q27 cumulant (EQ_INV_CUM) fp64 A-{'A' if a.streaming == 'AA' else 'B'} periodic box, {a.size}^3 cells per GPU, nu=1e-3, fx=1e-6"
-    config = {"workload": workload, "global_lattice": [a.size * N, a.size, a.size], "decomposition": f"x-slabs x{N}", "l2_policy": "working set (29 GB/GPU) larger than L2; no flush needed",
+    channel = a.workload == "channel"
+    Xg = 4 * a.size if channel else a.size * N
+    if channel:
+        workload = (f"D3Q27 cumulant (EQ_INV_CUM) fp64 A-{'A' if a.streaming == 'AA' else 'B'} channel {Xg}x{a.size}x{a.size} (sim_2 duct: periodic x, "
+                    f"GEO_WALL ring behind a GEO_NOTHING shell), nu=1e-3, fx=1e-7, split into {N} x-slabs")
+    else:
+        workload = f"D3Q27 cumulant (EQ_INV_CUM) fp64 A-{'A' if a.streaming == 'AA' else 'B'} periodic box, {a.size}^3 cells per GPU, nu=1e-3, fx=1e-6"
+    config = {"workload": workload, "global_lattice": [Xg, a.size, a.size], "decomposition": f"x-slabs x{N}", "l2_policy": "working set (29 GB/GPU) larger than L2; no flush needed",
               "macro_policy": "written by the last step of the batch (values identical at every host-observable point)"}
 
     # ---------------------------------------------------------------- reference arm: the CPU implementation, rank 0 only
@@ -187,10 +196,10 @@ def main():
         return float(t.item())
 
     S = a.size
-    Xg = S * N
+    assert not (channel and N < 2), "--workload channel needs at least 2 GPUs (134 GB of distributions)"
     streaming = B.AA if a.streaming == "AA" else B.AB
     eng = B.Engine(lattice=B.D3Q27, coll=B.CUM, eq=B.EQ_INV_CUM, streaming=streaming, macro=B.MACRO_DEFAULT, inflow=B.INFLOW_NONE, precision=B.F64,
-                   X=Xg, Y=S, Z=S, rank=rank, nranks=N, device=local_rank, ghost_x=1 if N > 1 else 0, periodic_x=1, macro_policy=B.MACRO_LAST_STEP)
+                   X=Xg, Y=S, Z=S, rank=rank, nranks=N, device=local_rank, ghost_x=1 if (N > 1 or channel) else 0, periodic_x=1, macro_policy=B.MACRO_LAST_STEP)
     if N > 1:
         idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -206,25 +215,44 @@ def main():
     t_in = time.perf_counter()
     keep = []
     tm, h_map = pinned((xl, S, S), np.int16)
-    h_map[...] = 7  # GEO_PERIODIC (d3q27/bc.h:25)
     keep.append(tm)
     fields = []
-    rho, vx, vy, vz = initial_fields(Xg, x0, xl, S, S)
-    for src in (rho, vx, vy, vz):
-        t, arr = pinned((xl, S, S), np.float64)
-        arr[...] = src
-        keep.append(t)
-        fields.append(arr)
+    if channel:
+        # sim_NSE/sim_2.cu:125-138, painted in that order (global x planes 0 and X-1 periodic, walls at y,z = 1 / N-2, NOTHING outside)
+        h_map[...] = 0
+        if x0 == 0:
+            h_map[0] = 7
+        if x0 + xl == Xg:
+            h_map[xl - 1] = 7
+        h_map[:, 1, :] = 1
+        h_map[:, S - 2, :] = 1
+        h_map[:, :, 1] = 1
+        h_map[:, :, S - 2] = 1
+        h_map[:, 0, :] = 8
+        h_map[:, S - 1, :] = 8
+        h_map[:, :, 0] = 8
+        h_map[:, :, S - 1] = 8
+    else:
+        h_map[...] = 7  # GEO_PERIODIC (d3q27/bc.h:25)
+        rho, vx, vy, vz = initial_fields(Xg, x0, xl, S, S)
+        for src in (rho, vx, vy, vz):
+            t, arr = pinned((xl, S, S), np.float64)
+            arr[...] = src
+            keep.append(t)
+            fields.append(arr)
     tmac, h_mac = pinned(eng.macro_shape(), np.float64)
     keep.append(tmac)
     log(f"[rank {rank}] host inputs ready in {time.perf_counter() - t_in:.1f}s; slab x0={x0} xl={xl}")
 
     def upload_state():
         eng.map_upload(h_map)
-        eng.set_equilibrium_field(*fields)
+        if channel:
+            eng.set_equilibrium(1.0, 0.0, 0.0, 0.0)  # State::resetDFs (state.hpp:880-896)
+        else:
+            eng.set_equilibrium_field(*fields)
         eng.iterations = 0
 
-    eng.set_params(lbmViscosity=1e-3, fx=1e-6, fy=0.0, fz=0.0)
+    eng.set_params(lbmViscosity=1e-3, fx=1e-7 if channel else 1e-6, fy=0.0, fz=0.0)
 
     # ---- device-resident measurement: W warm-up steps, then exactly K timed steps
     upload_state()
@@ -265,7 +293,7 @@ def main():
         t = torch.tensor([rho_sum], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         rho_sum = float(t.item())
-    assert abs(rho_sum / cells_global - 1.0) < 1e-6, rho_sum / cells_global  # mass is conserved in the periodic box
+    assert abs(rho_sum / cells_global - 1.0) < 1e-6, rho_sum / cells_global  # mass is conserved (wall / NOTHING cells report rho = 1)
 
     st = eng.stats()
     line = None
@@ -288,7 +316,7 @@ def main():
             except Exception:
                 pass
         line = {"metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": N, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "higher_is_better": True, "scaling": "strong" if channel else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
                         "what": "lbmx_map_upload + lbmx_df_set_equilibrium_field from pinned host buffers, lbmx_step(K), lbmx_macro_download"},
                 "gpu_launches": int(launches),
