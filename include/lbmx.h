@@ -34,7 +34,12 @@ extern "C" {
 enum lbmx_status { LBMX_OK = 0, LBMX_ERR_ARG = 1, LBMX_ERR_UNSUPPORTED = 2, LBMX_ERR_CUDA = 3, LBMX_ERR_NCCL = 4, LBMX_ERR_STATE = 5 };
 
 /* lattice / trait selectors: the template arguments of LBM_CONFIG (defs.h:169-250) as enums */
-enum lbmx_lattice { LBMX_D3Q27 = 0, LBMX_D2Q9 = 1, LBMX_D3Q19 = 2 /* no reference implementation: parity unpinned */ };
+enum lbmx_lattice {
+	LBMX_D3Q27 = 0,
+	LBMX_D2Q9 = 1,
+	LBMX_D3Q19 = 2 /* directions 0..18 of the D3Q27 numbering (defs.h:273-295), SRT and MRT_LES only; the reference has no such
+					  lattice (BASELINE.json names it): parity unpinned by construction */
+};
 enum lbmx_coll {
 	LBMX_COLL_CUM = 0,	   /* D3Q27_CUM      d3q27/col_cum.h:14-485 */
 	LBMX_COLL_SRT = 1,	   /* D3Q27_SRT      d3q27/col_srt.h:16-108   | D2Q9_SRT  d2q9/col_srt.h:16-44 */

@@ -168,6 +168,20 @@ struct L27
 	static bool collides(int m) { return m == FLUID || m == PERIODIC || m == OUTFLOW_RIGHT || m == OUTFLOW_RIGHT_INTERP || m == INFLOW_LEFT; }	// d3q27/bc.h:243-248
 };
 
+// D3Q19 = the first 19 directions of the D3Q27 numbering.  PARITY UNPINNED: the reference has no such lattice,
+// so this part of the file is a restatement of nothing -- it applies the reference's SRT (col_srt.h) and MRT_LES (col_mrt.h)
+// formulas with the standard D3Q19 weights and exists only so that the engine's D3Q19 kernels have an independent CPU check.
+struct L19
+{
+	static constexpr int Q = 19;
+	static constexpr int NDIM = 3;
+	static int c(int q, int a) { return C27[q][a]; }
+	static int opp(int q) { return opp27(q); }
+	static int find(int cx, int cy, int cz) { return find27(cx, cy, cz); }
+	enum { FLUID, WALL, INFLOW, INFLOW_LEFT, OUTFLOW_EQ, OUTFLOW_RIGHT, OUTFLOW_RIGHT_INTERP, PERIODIC, NOTHING, SYM_TOP, SYM_BOTTOM, SYM_LEFT, SYM_RIGHT, SYM_BACK, SYM_FRONT };
+	static bool collides(int m) { return L27::collides(m); }
+};
+
 struct L9
 {
 	static constexpr int Q = 9;
@@ -207,6 +221,22 @@ void density_velocity(Cell<R, 27>& K)
 	const R cy = (d(D(1, 1, 1)) + d(D(1, 1, -1))) + (d(D(-1, 1, 1)) + d(D(-1, 1, -1)));
 	const R ey = (d(D(1, 1, 0)) + d(D(-1, 1, 0))) + (d(D(0, 1, 1)) + d(D(0, 1, -1)));
 	K.vy = (((cy + ey) + d(D(0, 1, 0))) + K.fy * half) / K.rho;
+}
+
+// D3Q19 (unpinned): plain pairwise sums over the 9 opposite pairs
+template <typename R>
+void density_velocity(Cell<R, 19>& K)
+{
+	R rho = K.f[0], j[3] = {0, 0, 0};
+	for (int q = 1; q < 19; q += 2) {
+		rho += K.f[q] + K.f[q + 1];
+		for (int a = 0; a < 3; a++)
+			j[a] += (R) C27[q][a] * (K.f[q] - K.f[q + 1]);
+	}
+	K.rho = rho;
+	K.vx = (j[0] + (R) 0.5 * K.fx) / rho;
+	K.vy = (j[1] + (R) 0.5 * K.fy) / rho;
+	K.vz = (j[2] + (R) 0.5 * K.fz) / rho;
 }
 
 // d2q9/common.h:16-36
@@ -268,6 +298,15 @@ template <typename R>
 R equilibrium(const Cell<R, 27>&, int eqkind, int q, R rho, R vx, R vy, R vz)
 {
 	return eqkind == ORC_EQ_INV_CUM ? eq27_inv_cum(q, rho, vx, vy, vz) : eq27_std(q, rho, vx, vy, vz);
+}
+template <typename R>
+R equilibrium(const Cell<R, 19>&, int, int q, R rho, R vx, R vy, R vz)  // D3Q19 (unpinned): eq.h polynomial, weights 1/3, 1/18, 1/36
+{
+	const R qx = (R) C27[q][0], qy = (R) C27[q][1], qz = (R) C27[q][2];
+	const int n = (C27[q][0] != 0) + (C27[q][1] != 0) + (C27[q][2] != 0);
+	const R w = n == 0 ? (R) (1.0 / 3.0) : n == 1 ? (R) (1.0 / 18.0) : (R) (1.0 / 36.0);
+	const R cu = qx * vx + qy * vy + qz * vz;
+	return w * rho * ((R) 1.0 - (R) 1.5 * (vx * vx + vy * vy + vz * vz) + (R) 3.0 * cu + (R) 4.5 * cu * cu);
 }
 template <typename R>
 R equilibrium(const Cell<R, 9>&, int, int q, R rho, R vx, R vy, R)
@@ -630,6 +669,48 @@ void collide(Cell<R, 27>& K, const oracle_desc& d)
 		case ORC_COLL_MRT_LES: collide_mrt27(K); break;
 	}
 }
+// D3Q19 (unpinned): SRT and MRT_LES with the formulas of col_srt.h / col_mrt.h over 19 velocities
+template <typename R>
+void collide(Cell<R, 19>& K, const oracle_desc& d)
+{
+	const R one = 1, half = (R) 0.5, two = 2, three = 3, third = (R) (1.0 / 3.0);
+	if (d.coll == ORC_COLL_SRT) {
+		const R tau = three * K.nu + half;
+		const R iRho = one / (K.rho == 0 ? one : K.rho);
+		R S[19], feq[19];
+		for (int q = 0; q < 19; q++) {
+			S[q] = force_projection(q, K.vx, K.vy, K.vz, K.fx, K.fy, K.fz) * iRho;
+			feq[q] = equilibrium(K, 0, q, K.rho, K.vx, K.vy, K.vz);
+		}
+		for (int q = 0; q < 19; q++)
+			K.f[q] += (feq[q] - K.f[q]) / tau + (one - half / tau) * S[q] * feq[q];
+		return;
+	}
+	R P[6] = {0, 0, 0, 0, 0, 0};
+	for (int q = 0; q < 19; q++) {
+		const int a = C27[q][0], b = C27[q][1], c = C27[q][2];
+		const int w[6] = {a * a, b * b, c * c, a * b, a * c, b * c};
+		for (int i = 0; i < 6; i++)
+			P[i] += (R) w[i] * K.f[q];
+	}
+	const R N[6] = {P[0] - K.rho * (third + K.vx * K.vx), P[1] - K.rho * (third + K.vy * K.vy), P[2] - K.rho * (third + K.vz * K.vz),
+					P[3] - K.rho * K.vx * K.vy, P[4] - K.rho * K.vx * K.vz, P[5] - K.rho * K.vy * K.vz};
+	const R Qn = two * (N[0] * N[0] + N[1] * N[1] + N[2] * N[2] + two * (N[3] * N[3] + N[4] * N[4] + N[5] * N[5]));
+	const R tau = three * K.nu + half;
+	const R omega = two / (std::sqrt(tau * tau + two * (R) 0.0342 * three * three * std::sqrt(Qn) / K.rho) + tau);
+	for (int i = 0; i < 6; i++)
+		P[i] -= omega * N[i];
+	for (int q = 0; q < 19; q++) {
+		const int a = C27[q][0], b = C27[q][1], c = C27[q][2];
+		const int n = (a != 0) + (b != 0) + (c != 0);
+		const R w = n == 0 ? third : n == 1 ? (R) (1.0 / 18.0) : (R) (1.0 / 36.0);
+		K.f[q] = w
+			   * (K.rho * ((R) 2.5 - (R) 1.5 * (R) n + three * (K.vx * (R) a + K.vy * (R) b + K.vz * (R) c))
+				  + (R) 4.5 * (P[0] * (R) (a * a) + P[1] * (R) (b * b) + P[2] * (R) (c * c) + two * (P[3] * (R) (a * b) + P[4] * (R) (a * c) + P[5] * (R) (b * c)))
+				  - (R) 1.5 * (P[0] + P[1] + P[2]));
+	}
+}
+
 template <typename R>
 void collide(Cell<R, 9>& K, const oracle_desc& d)
 {
@@ -699,7 +780,7 @@ void inflow(const Block<R>& B, Cell<R, Q>& K, idx, idx y, idx z)
 		case ORC_INFLOW_CONST:
 			K.vx = B.in_vx;
 			K.vy = B.in_vy;
-			if (Q == 27)
+			if (Q != 9)
 				K.vz = B.in_vz;
 			break;
 		case ORC_INFLOW_PROFILE_YZ:
@@ -754,6 +835,13 @@ void inflow_left_moments(Cell<R, 27>& K)
 template <typename R>
 void inflow_left_moments(Cell<R, 9>&)
 {}
+template <typename R>
+void inflow_left_moments(Cell<R, 19>& K)  // D3Q19 (unpinned): no moment condition exists for 19 velocities; impose the equilibrium of (1, u_in)
+{
+	K.rho = 1;
+	for (int q = 0; q < 19; q++)
+		K.f[q] = equilibrium(K, 0, q, K.rho, K.vx, K.vy, K.vz);
+}
 
 // REFERENCE QUIRK, reproduced on purpose (D2Q9 only).  D2Q9_BC_All::preCollision takes coordinate parameters named
 // `zm` and `zp` (d2q9/bc.h:90) which shadow the direction enumerators zp=3 / zm=4 (defs.h:262-263).  Inside that function
@@ -883,7 +971,7 @@ void output_macro(const Block<R>& B, const Cell<R, Q>& K, const oracle_desc& d, 
 		return;
 	const idx c = B.cell(x, y, z);
 	R* M = B.macro;
-	const int nd = Q == 27 ? 3 : 2;
+	const int nd = Q == 9 ? 2 : 3;
 	const R v[3] = {K.vx, K.vy, K.vz};
 	M[0 * B.XYZ + c] = K.rho;
 	for (int a = 0; a < nd; a++)
@@ -927,7 +1015,7 @@ void cell_update(const Block<R>& B, const oracle_desc& d, idx x, idx y, idx z)
 		K.nu = B.nu;
 		K.fx = B.fx;
 		K.fy = B.fy;
-		K.fz = Q == 27 ? B.fz : 0;
+		K.fz = Q != 9 ? B.fz : 0;
 	}
 	const bool active = pre_collision<L>(B, K, d, m, n, aa);
 	if (L::collides(m))
@@ -1041,7 +1129,9 @@ bool supported(const oracle_desc* d)
 		return d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_MRT_LES && (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM);
 	if (d->lattice == ORC_D2Q9)
 		return (d->coll == ORC_COLL_SRT || d->coll == ORC_COLL_CLBM) && d->eq == ORC_EQ_STD && d->Z == 1;
-	return false;  // D3Q19: the reference has no such lattice -- nothing to restate
+	if (d->lattice == ORC_D3Q19)  // no reference implementation: PARITY UNPINNED (see L19)
+		return (d->coll == ORC_COLL_SRT || d->coll == ORC_COLL_MRT_LES) && d->eq == ORC_EQ_STD;
+	return false;
 }
 
 }  // namespace
@@ -1051,6 +1141,8 @@ bool supported(const oracle_desc* d)
 		return -1;                                                                        \
 	if (d->lattice == ORC_D3Q27)                                                          \
 		return d->precision == ORC_F64 ? fn<L27, double>(__VA_ARGS__) : fn<L27, float>(__VA_ARGS__); \
+	if (d->lattice == ORC_D3Q19)                                                          \
+		return d->precision == ORC_F64 ? fn<L19, double>(__VA_ARGS__) : fn<L19, float>(__VA_ARGS__); \
 	return d->precision == ORC_F64 ? fn<L9, double>(__VA_ARGS__) : fn<L9, float>(__VA_ARGS__);
 
 extern "C" {

@@ -186,10 +186,10 @@ def df_floor(d: O.Desc) -> np.ndarray:
     """Per-population floor for the element-wise relative error: half the lattice weight w_q (the population's own scale at
     rho = 1).  Boundary rules (moment inflow, equilibrium decomposition) can drive single populations through zero; their
     error is then measured against w_q / 2 instead of against a value that happens to be ~0."""
-    c = C9 if d.lattice == O.D2Q9 else C27
+    c = C9 if d.lattice == O.D2Q9 else C27[: d.Q]
     n = np.abs(c).sum(axis=1)
-    w = np.array([4 / 9, 1 / 9, 1 / 36])[n] if d.lattice == O.D2Q9 else np.array([8 / 27, 2 / 27, 1 / 54, 1 / 216])[n]
-    return 0.5 * w
+    table = {O.D2Q9: [4 / 9, 1 / 9, 1 / 36], O.D3Q27: [8 / 27, 2 / 27, 1 / 54, 1 / 216], O.D3Q19: [1 / 3, 1 / 18, 1 / 36]}[d.lattice]
+    return 0.5 * np.array(table)[n]
 
 
 def rel_err_df(a: np.ndarray, b: np.ndarray, d: O.Desc) -> float:

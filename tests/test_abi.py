@@ -63,6 +63,8 @@ def test_halo_directions_are_the_x_movers():
     assert l == [q for q in range(27) if lc.C27[q][0] < 0] and len(l) == 9
     r2, l2 = B.halo_directions(B.D2Q9)
     assert r2 == [1, 5, 7] and l2 == [2, 6, 8]
+    r3, l3 = B.halo_directions(B.D3Q19)
+    assert r3 == [1, 7, 9, 11, 13] and l3 == [2, 8, 10, 12, 14]
 
 
 def test_halo_plan_planes_and_slots():
@@ -81,7 +83,9 @@ def test_halo_plan_planes_and_slots():
 
 def test_create_rejects_unsupported_combinations():
     with pytest.raises(B.LbmxError, match="D3Q19"):
-        B.Engine(lattice=B.D3Q19)
+        B.Engine(lattice=B.D3Q19, coll=B.SRT, eq=B.EQ_INV_CUM)  # the product-form equilibrium needs 27 velocities
+    with pytest.raises(B.LbmxError, match="no kernel family"):
+        B.Engine(lattice=B.D3Q19, coll=B.CUM, eq=B.EQ_STD)
     with pytest.raises(B.LbmxError, match="Z == 1"):
         B.Engine(lattice=B.D2Q9, coll=B.SRT, eq=B.EQ_STD, Z=4)
     with pytest.raises(B.LbmxError):

@@ -473,6 +473,119 @@ LBMX_D void collide_clbm(R (&f)[9], const Phys<R>& P, R rho, R vx, R vy)
 }
 
 // --------------------------------------------------------------------------------------------------------------------
+// D3Q19 (no reference implementation -- parity unpinned): the D3Q27 operators restricted to the 19-velocity set with the
+// standard weights 1/3, 1/18, 1/36.  SRT with the reference's source-term form (col_srt.h) and the polynomial equilibrium
+// (eq.h); "MRT_LES" = the regularised second-moment operator with Smagorinsky rate of col_mrt.h, which is lattice-agnostic.
+// --------------------------------------------------------------------------------------------------------------------
+template <typename R>
+LBMX_HD constexpr R w19(int q)
+{
+	const int n = (D3Q19::cx(q) != 0) + (D3Q19::cy(q) != 0) + (D3Q19::cz(q) != 0);
+	return n == 0 ? R(1.0 / 3.0) : n == 1 ? R(1.0 / 18.0) : R(1.0 / 36.0);
+}
+
+template <typename R>
+LBMX_D void density_velocity(const R (&f)[19], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
+{
+	using L = D3Q19;
+	R r = f[0], jx = R(0), jy = R(0), jz = R(0);
+	static_for<9>([&](auto ic) {  // opposite pairs are adjacent: (1,2), (3,4), ...
+		constexpr int q = 1 + 2 * ic;
+		const R s = f[q] + f[q + 1], d = f[q] - f[q + 1];
+		r += s;
+		if constexpr (L::cx(q) != 0)
+			jx += R(L::cx(q)) * d;
+		if constexpr (L::cy(q) != 0)
+			jy += R(L::cy(q)) * d;
+		if constexpr (L::cz(q) != 0)
+			jz += R(L::cz(q)) * d;
+	});
+	rho = r;
+	const R ir = R(1) / rho;
+	vx = (jx + R(0.5) * P.fx) * ir;
+	vy = (jy + R(0.5) * P.fy) * ir;
+	vz = (jz + R(0.5) * P.fz) * ir;
+}
+
+template <typename R>
+LBMX_D void equilibrium(R (&feq)[19], int, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q19;
+	const R base = R(1) - R(1.5) * ((vx * vx + vy * vy) + vz * vz);
+	static_for<19>([&](auto qc) {
+		constexpr int q = qc;
+		const R cu = (R(L::cx(q)) * vx + R(L::cy(q)) * vy) + R(L::cz(q)) * vz;
+		feq[q] = (w19<R>(q) * rho) * ((base + R(3) * cu) + (R(4.5) * cu) * cu);
+	});
+}
+
+template <typename R>
+LBMX_D void collide_srt(R (&f)[19], const Phys<R>& P, int, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q19;
+	const R itau = P.omega1;
+	const R iRho = R(1) / (rho == R(0) ? R(1) : rho);
+	const R pre = (R(1) - R(0.5) * itau) * (R(3) * iRho);
+	const R tx[3] = {(-vx - R(1)) * P.fx, -vx * P.fx, (-vx + R(1)) * P.fx};
+	const R ty[3] = {(-vy - R(1)) * P.fy, -vy * P.fy, (-vy + R(1)) * P.fy};
+	const R tz[3] = {(-vz - R(1)) * P.fz, -vz * P.fz, (-vz + R(1)) * P.fz};
+	R feq[19];
+	equilibrium(feq, 0, rho, vx, vy, vz);
+	static_for<19>([&](auto qc) {
+		constexpr int q = qc;
+		const R S = (tx[L::cx(q) + 1] + ty[L::cy(q) + 1]) + tz[L::cz(q) + 1];
+		f[q] = f[q] + ((feq[q] - f[q]) * itau + (pre * S) * feq[q]);
+	});
+}
+
+template <typename R>
+LBMX_D void collide_mrt(R (&f)[19], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q19;
+	R Pxx = 0, Pyy = 0, Pzz = 0, Pxy = 0, Pxz = 0, Pyz = 0;
+	static_for<19>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int a = L::cx(q), b = L::cy(q), c = L::cz(q);
+		if constexpr (a != 0)
+			Pxx += f[q];
+		if constexpr (b != 0)
+			Pyy += f[q];
+		if constexpr (c != 0)
+			Pzz += f[q];
+		if constexpr (a * b != 0)
+			Pxy += R(a * b) * f[q];
+		if constexpr (a * c != 0)
+			Pxz += R(a * c) * f[q];
+		if constexpr (b * c != 0)
+			Pyz += R(b * c) * f[q];
+	});
+	const R Nxx = Pxx - rho * (R(1.0 / 3.0) + vx * vx);
+	const R Nyy = Pyy - rho * (R(1.0 / 3.0) + vy * vy);
+	const R Nzz = Pzz - rho * (R(1.0 / 3.0) + vz * vz);
+	const R Nxy = Pxy - rho * vx * vy;
+	const R Nxz = Pxz - rho * vx * vz;
+	const R Nyz = Pyz - rho * vy * vz;
+	const R Qn = R(2) * (((Nxx * Nxx + Nyy * Nyy) + Nzz * Nzz) + R(2) * ((Nxy * Nxy + Nxz * Nxz) + Nyz * Nyz));
+	const R tau = R(3) * P.nu + R(0.5);
+	const R omega = R(2) / (sqrt(tau * tau + (R(2) * R(0.0342) * R(9)) * sqrt(Qn) / rho) + tau);
+	Pxx -= omega * Nxx;
+	Pyy -= omega * Nyy;
+	Pzz -= omega * Nzz;
+	Pxy -= omega * Nxy;
+	Pxz -= omega * Nxz;
+	Pyz -= omega * Nyz;
+	const R tr = R(1.5) * ((Pxx + Pyy) + Pzz);
+	static_for<19>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int a = L::cx(q), b = L::cy(q), c = L::cz(q);
+		constexpr int n = (a != 0) + (b != 0) + (c != 0);
+		const R lin = rho * ((R(2.5) - R(1.5) * R(n)) + R(3) * ((vx * R(a) + vy * R(b)) + vz * R(c)));
+		const R quad = ((Pxx * R(a * a) + Pyy * R(b * b)) + Pzz * R(c * c)) + R(2) * ((Pxy * R(a * b) + Pxz * R(a * c)) + Pyz * R(b * c));
+		f[q] = w19<R>(q) * ((lin + R(4.5) * quad) - tr);
+	});
+}
+
+// --------------------------------------------------------------------------------------------------------------------
 // operator tags: what COLL means for a kernel instantiation
 // --------------------------------------------------------------------------------------------------------------------
 enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 };
@@ -486,6 +599,14 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 		collide_srt(f, P, eqkind, rho, vx, vy, vz);
 	else if constexpr (KIND == K_BGK)
 		collide_bgk(f, P, rho, vx, vy, vz);
+	else
+		collide_mrt(f, P, rho, vx, vy, vz);
+}
+template <int KIND, typename R>
+LBMX_D void collide(R (&f)[19], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
+{
+	if constexpr (KIND == K_SRT)
+		collide_srt(f, P, eqkind, rho, vx, vy, vz);
 	else
 		collide_mrt(f, P, rho, vx, vy, vz);
 }

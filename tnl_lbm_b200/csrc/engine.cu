@@ -93,7 +93,7 @@ NcclApi g_nccl;
 
 int q_of(int lattice)
 {
-	return lattice == LBMX_D2Q9 ? 9 : 27;
+	return lattice == LBMX_D2Q9 ? 9 : (lattice == LBMX_D3Q19 ? 19 : 27);
 }
 int n_macro_of(int lattice, int macro)
 {
@@ -360,6 +360,12 @@ bool pick_kernels(lbmx_engine* e)
 			case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt(e->kd) : get_kernels_d3q27_mrt(e->kf);
 		}
 	}
+	else if (d.lattice == LBMX_D3Q19) {
+		if (d.coll == LBMX_COLL_SRT)
+			return e->f64() ? get_kernels_d3q19_srt(e->kd) : get_kernels_d3q19_srt(e->kf);
+		if (d.coll == LBMX_COLL_MRT_LES)
+			return e->f64() ? get_kernels_d3q19_mrt(e->kd) : get_kernels_d3q19_mrt(e->kf);
+	}
 	else if (d.lattice == LBMX_D2Q9) {
 		if (d.coll == LBMX_COLL_SRT)
 			return e->f64() ? get_kernels_d2q9_srt(e->kd) : get_kernels_d2q9_srt(e->kf);
@@ -427,6 +433,8 @@ int lbmx_halo_directions(int32_t lattice, int32_t* to_right, int32_t* to_left)
 	int n;
 	if (lattice == LBMX_D3Q27)
 		n = halo_dirs<D3Q27>(r, l);
+	else if (lattice == LBMX_D3Q19)
+		n = halo_dirs<D3Q19>(r, l);
 	else if (lattice == LBMX_D2Q9)
 		n = halo_dirs<D2Q9>(r, l);
 	else
@@ -495,8 +503,10 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 	const lbmx_desc& d = *desc;
 	if (d.X < 1 || d.Y < 1 || d.Z < 1)
 		return fail(LBMX_ERR_ARG, "lbmx_create: lattice sizes must be positive");
-	if (d.lattice == LBMX_D3Q19)
-		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: D3Q19 has no implementation in the reference and none here yet");
+	if (d.lattice != LBMX_D3Q27 && d.lattice != LBMX_D3Q19 && d.lattice != LBMX_D2Q9)
+		return fail(LBMX_ERR_ARG, "lbmx_create: lattice selector");
+	if (d.lattice == LBMX_D3Q19 && d.eq != LBMX_EQ_STD)
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: D3Q19 has only the polynomial equilibrium (the product form needs 27 velocities)");
 	if (d.lattice == LBMX_D2Q9 && d.Z != 1)
 		return fail(LBMX_ERR_ARG, "lbmx_create: D2Q9 needs Z == 1 (the reference's X x Y x 1 lattice, sim_2D/sim2d_1.cu:134)");
 	if (d.precision != LBMX_F32 && d.precision != LBMX_F64)
@@ -730,7 +740,7 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	std::vector<int16_t> hm((size_t) e->XYZ);
 	CU(cudaMemcpy(hm.data(), e->map, hm.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
 	const int fluid = 0;
-	const int periodic = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::PERIODIC : (int) D3Q27::PERIODIC;
+	const int periodic = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::PERIODIC : (int) D3Q27::PERIODIC;	// D3Q19 shares the D3Q27 cell types
 	std::vector<uint32_t> list;
 	e->plane_start.assign((size_t) e->X + 1, 0);
 	for (int64_t x = 0; x < e->X; x++) {

@@ -258,7 +258,7 @@ constexpr int bulk_cpt()
 #ifdef LBMX_BULK_CPT
 	return LBMX_BULK_CPT;
 #else
-	if (L::Q == 27)
+	if (L::Q >= 19)
 		return sizeof(R) == 8 ? 1 : (MODE == S_AA_ODD ? 1 : 2);
 	return sizeof(R) == 8 ? (MODE == S_AB ? 1 : 2) : 2;
 #endif
@@ -358,6 +358,16 @@ LBMX_D void inflow_left_moments(R (&f)[27], R& rho, R vx, R vy, R vz)
 template <typename R>
 LBMX_D void inflow_left_moments(R (&)[9], R&, R, R, R)
 {}
+template <typename R>
+LBMX_D void inflow_left_moments(R (&f)[19], R& rho, R vx, R vy, R vz)
+{
+	// the moment condition of d3q27/bc.h:82-136 is specific to 27 velocities; on D3Q19 GEO_INFLOW_LEFT imposes the equilibrium
+	// of (rho = 1, inflow velocity), i.e. it behaves like GEO_INFLOW followed by a collision
+	rho = R(1);
+	R feq[19];
+	equilibrium(feq, 0, rho, vx, vy, vz);
+	static_for<19>([&](auto qc) { f[qc] = feq[qc]; });
+}
 
 // symmetry planes: populations pointing in direction DST along AXIS take the value of their mirror image
 // (d3q27/bc.h:172-237, d2q9/bc.h:168-191).  D2Q9 quirk: the straight +-y pair is addressed through shadowed names in the
@@ -614,6 +624,10 @@ bool get_kernels_d3q27_bgk(StepKernels<float>&);
 bool get_kernels_d3q27_bgk(StepKernels<double>&);
 bool get_kernels_d3q27_mrt(StepKernels<float>&);
 bool get_kernels_d3q27_mrt(StepKernels<double>&);
+bool get_kernels_d3q19_srt(StepKernels<float>&);
+bool get_kernels_d3q19_srt(StepKernels<double>&);
+bool get_kernels_d3q19_mrt(StepKernels<float>&);
+bool get_kernels_d3q19_mrt(StepKernels<double>&);
 bool get_kernels_d2q9_srt(StepKernels<float>&);
 bool get_kernels_d2q9_srt(StepKernels<double>&);
 bool get_kernels_d2q9_clbm(StepKernels<float>&);

@@ -55,6 +55,26 @@ struct D3Q27
 	LBMX_HD static constexpr bool bulk(int m) { return m == FLUID || m == PERIODIC; }
 };
 
+// D3Q19: the first 19 directions of the D3Q27 numbering (the "+Q19" block of defs.h:273-295).  The reference has no such
+// lattice: BASELINE.json names it, so it exists here, with PARITY UNPINNED by construction.
+struct D3Q19
+{
+	static constexpr int Q = 19;
+	static constexpr int NDIM = 3;
+	LBMX_HD static constexpr int cx(int q) { return D3Q27::cx(q); }
+	LBMX_HD static constexpr int cy(int q) { return D3Q27::cy(q); }
+	LBMX_HD static constexpr int cz(int q) { return D3Q27::cz(q); }
+	LBMX_HD static constexpr int find(int x, int y, int z)
+	{
+		const int q = D3Q27::find(x, y, z);
+		return q < 19 ? q : -1;
+	}
+	LBMX_HD static constexpr int opp(int q) { return find(-cx(q), -cy(q), -cz(q)); }
+	enum : int { FLUID = 0, WALL, INFLOW, INFLOW_LEFT, OUTFLOW_EQ, OUTFLOW_RIGHT, OUTFLOW_RIGHT_INTERP, PERIODIC, NOTHING, SYM_TOP, SYM_BOTTOM, SYM_LEFT, SYM_RIGHT, SYM_BACK, SYM_FRONT };
+	LBMX_HD static constexpr bool collides(int m) { return D3Q27::collides(m); }
+	LBMX_HD static constexpr bool bulk(int m) { return m == FLUID || m == PERIODIC; }
+};
+
 struct D2Q9
 {
 	static constexpr int Q = 9;

@@ -40,7 +40,7 @@ def run(lattice, coll, eq, prec, streaming, shape, steps, map_kind="periodic"):
     e.close()
     cells = X * Y * Z
     mlups = cells * steps / (ms * 1e-3) / 1e6
-    q = 9 if lattice == B.D2Q9 else 27
+    q = {B.D2Q9: 9, B.D3Q19: 19}.get(lattice, 27)
     bpu = q * 2 * (8 if prec == B.F64 else 4)
     return mlups, mlups * bpu / 1e3, st.bulk_regs, bpu
 
@@ -61,6 +61,10 @@ def main():
             for st in (B.AA, B.AB):
                 shape = (384, 384, 384) if (prec == B.F64 or st == B.AB) else (512, 512, 512)
                 cfgs.append(("D3Q27", B.D3Q27, coll, eq, prec, st, shape, "periodic"))
+    for coll in (B.MRT_LES, B.SRT):  # BASELINE.json configs[4]: "D3Q19 MRT fp32 ... (A-A vs A-B)"; no reference implementation (parity unpinned)
+        for prec in (B.F32, B.F64):
+            for st in (B.AA, B.AB):
+                cfgs.append(("D3Q19", B.D3Q19, coll, B.EQ_STD, prec, st, (512, 512, 512) if prec == B.F32 else (384, 384, 384), "periodic"))
     for coll in (B.SRT, B.CLBM):
         for prec in (B.F64, B.F32):
             for st in (B.AA, B.AB):
