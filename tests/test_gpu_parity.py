@@ -173,3 +173,52 @@ def run_port_fast(case):
     orc.initial_macro(p, a, mac)
     orc.step(p, a, b, mac, case.make_map(d), 0, case.nsteps, os.cpu_count() or 4)
     return (a if case.nsteps % 2 == 0 or d.streaming == O.AA else b), mac
+
+
+@pytest.mark.parametrize("name", ["cum_f64_aa_zoo", "cum_f64_ab_zoo"])
+def test_raw_state_dump_and_resume(name):
+    """Checkpoint semantics of the reference (checkpoint.h:58-101, state.hpp:678-737): the raw arrays as stored (ghost planes
+    included), the macro array and the iteration counter are enough to resume -- under A-A the parity travels with the
+    counter.  Interrupted-and-resumed must be bit-identical to uninterrupted."""
+    case = gc.BY_NAME[name]
+    d = case.desc
+    port = O.Oracle(d, "port")
+    df0 = gc.initial_df(case, port)
+    m = case.make_map(d)
+
+    def fresh():
+        e = engine_for(case, ghost_x=1, periodic_x=1)
+        e.map_upload(m)
+        set_params(e, case.params)
+        return e
+
+    with fresh() as e:
+        e.df_upload(df0, 0)
+        e.df_sync_ghosts()
+        if d.streaming == O.AB:
+            e.df_upload(df0, 1)
+        e.macro_init()
+        e.step(7)
+        full_df, full_mac = e.df_download(0, with_ghosts=True), e.macro_download()
+    with fresh() as e:
+        e.df_upload(df0, 0)
+        e.df_sync_ghosts()
+        if d.streaming == O.AB:
+            e.df_upload(df0, 1)
+        e.macro_init()
+        e.step(3)
+        saved = dict(it=e.iterations, cur=e.df_download(0, with_ghosts=True), mac=e.macro_download(with_ghosts=True), map=e.map_download(with_ghosts=True))
+        if d.streaming == O.AB:
+            saved["other"] = e.df_download(1, with_ghosts=True)
+    with engine_for(case, ghost_x=1, periodic_x=1) as e:
+        e.map_upload(saved["map"], with_ghosts=True)
+        set_params(e, case.params)
+        e.iterations = saved["it"]
+        e.df_upload(saved["cur"], 0, with_ghosts=True)
+        if d.streaming == O.AB:
+            e.df_upload(saved["other"], 1, with_ghosts=True)
+        e.macro_upload(saved["mac"], with_ghosts=True)
+        e.step(4)
+        assert e.iterations == 7
+        assert np.array_equal(e.df_download(0, with_ghosts=True), full_df)
+        assert np.array_equal(e.macro_download(), full_mac)
