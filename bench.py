@@ -306,13 +306,16 @@ def main():
         # the bulk kernel is the only kernel of a step at N=1 (at N>1: + 2 edge launches and the exchange), so its average
         # duration is the event time per step; per launch it processes cells_local updates of 432 algorithmic bytes each
         achieved = cells_local * B_PER_UPDATE / (ms_max * 1e-3 / a.steps) / 1e9
-        traffic = None
+        # DRAM bytes per launch from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of k_bulk), which was
+        # taken at 256^3; per lattice update it is size-independent, so it is scaled by this run's cells per launch
+        traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if tj.get("size") == S and tj.get("streaming") == a.streaming:
-                    traffic = tj.get("dram_bytes_per_launch")
+                if tj.get("streaming") == a.streaming and not channel:
+                    traffic = tj["dram_bytes_per_update"] * cells_local
+                    traffic_note = f"{tj['dram_bytes_per_update']:.1f} B per update ({tj['source']}) x {cells_local} updates per launch"
             except Exception:
                 pass
         line = {"metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": N, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps,
@@ -320,7 +323,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
                         "what": "lbmx_map_upload + lbmx_df_set_equilibrium_field from pinned host buffers, lbmx_step(K), lbmx_macro_download"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                              "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_update": B_PER_UPDATE,
                              "kernel": f"k_bulk<D3Q27,CUM,double,{'A-A even/odd' if a.streaming == 'AA' else 'A-B'}>", "registers": st.bulk_regs, "block": st.bulk_block},
                 "halo_bytes_per_step_per_gpu": halo_bytes / a.steps}
