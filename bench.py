@@ -339,6 +339,16 @@ def main():
                                     "sample": f"{a.cpu_sample}^3 periodic sub-box of the same field and operator, {nsteps} steps, OpenMP over (x,z)"}
         except Exception as ex:  # the checker being unavailable must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": host_threads, "kind": "unavailable", "sample": repr(ex)}
+    # ---- GPU baseline beside it (rank 0, N = 1): the reference's own cudaLBMKernel recompiled for sm_100a through the TNL
+    #      stand-in (oracle/ref_gpu_bench.cu -> oracle/_ref/, built where the reference tree exists), same box, same lattice
+    if rank == 0 and N == 1 and not a.no_cpu_baseline and not channel:
+        exe = os.path.join(ROOT, "oracle", "_ref", f"ref_gpu_bench_{'aa' if a.streaming == 'AA' else 'ab'}")
+        if os.path.exists(exe):
+            try:
+                r = subprocess.run([exe, str(S), "20"], capture_output=True, text=True, timeout=300)
+                line["reference_gpu_kernel"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as ex:
+                line["reference_gpu_kernel"] = {"error": repr(ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if N > 1:

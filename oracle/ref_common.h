@@ -127,6 +127,7 @@ inline typename NSE::DATA ref_make_data(const oracle_desc* d, const oracle_param
 	return SD;
 }
 
+#ifndef USE_CUDA  // with USE_CUDA kernels.h declares the __global__ cudaLBMKernel instead of the per-cell host function (kernels.h:60-66)
 // one or more full time steps: State::SimUpdate host branch (state.hpp:1114-1123) + LBM::updateKernelData (lbm.hpp:314-330)
 template <typename NSE>
 int ref_step(const oracle_desc* d, const oracle_params* p, void* df_a, void* df_b, void* macro, const int16_t* map, int64_t iteration, int nsteps,
@@ -155,6 +156,8 @@ int ref_step(const oracle_desc* d, const oracle_params* p, void* df_a, void* df_
 	}
 	return 0;
 }
+
+#endif
 
 template <typename dreal, typename idx>
 struct RefLatView
@@ -231,8 +234,10 @@ int ref_invoke(const RefCall& c)
 	switch (c.op) {
 		case 0:
 			return 0;
+#ifndef USE_CUDA
 		case 1:
 			return ref_step<NSE>(c.d, c.p, c.df_a, c.df_b, c.macro, c.map, c.iteration, c.nsteps, c.nthreads);
+#endif
 		case 2:
 			return ref_set_eq<NSE>(c.d, c.df_a, c.rho, c.vx, c.vy, c.vz, c.crho, c.cvx, c.cvy, c.cvz);
 		case 3:

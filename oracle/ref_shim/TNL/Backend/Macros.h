@@ -25,7 +25,11 @@ namespace Backend {
 template <typename T>
 __cuda_callable__ inline T ldg(const T& value)
 {
+#ifdef __CUDA_ARCH__
+	return __ldg(&value);  // what TNL::Backend::ldg does in device code
+#else
 	return value;
+#endif
 }
 }  // namespace Backend
 

@@ -91,6 +91,10 @@ LBMX_D Deltas neighbour_deltas(const KParams<R>& p, bool periodic_cell, int x, i
 		d.ym = (y == 0) ? (p.Y - 1) : -1;
 		d.zp = (z == p.Z - 1) ? -(p.Z - 1) * Y : Y;
 		d.zm = (z == 0) ? (p.Z - 1) * Y : -Y;
+#ifdef LBMX_EXP_YSHIFT4	 // development experiment only (wrong physics): y-neighbours 4 cells away = sector-aligned but line-misaligned accesses
+		d.yp = (y >= p.Y - 4) ? -(p.Y - 4) : 4;
+		d.ym = (y < 4) ? (p.Y - 4) : -4;
+#endif
 	}
 	else if (AA) {
 		d.xp = YZ;
