@@ -177,6 +177,11 @@ int lbmx_set_params(lbmx_engine* e, const lbmx_params* p);
 /* NSE_Data_XProfileInflow::vx_profile (sim_NSE/sim_2.cu:16-33): real[size_y*size_z] in the engine's precision */
 int lbmx_set_inflow_profile(lbmx_engine* e, const void* host_profile, int64_t size_y, int64_t size_z);
 
+/* D2Q9 GEO_FLUID_NEAR_WALL (Bouzidi interpolated bounce-back, d2q9/bc.h:61-87,140-167; A-B streaming only): the coefficient array
+ * of LBM_BLOCK::allocateBouzidiCoeffArrays / block.data.bouzidi_coeff_ptr (lbm_data.h:69-83): real[8][X_local*Z*Y], direction
+ * order E,N,W,S,NE,NW,SW,SE, negative = the link does not hit a wall.  Without it every coefficient reads -1. */
+int lbmx_bouzidi_upload(lbmx_engine* e, const void* host_coeff);
+
 /* Time stepping ------------------------------------------------------------------------------------------------------------ */
 
 /* State::SimUpdate + LBM::updateKernelData (state.hpp:980-1145, lbm.hpp:314-330): advances `nsteps` iterations.

@@ -94,6 +94,7 @@ struct Block
 	idx profile_sy;
 	int stat_counter;
 	int inflow_kind;
+	const R* bouzidi;  // [8][XYZ] or nullptr
 
 	idx cell(idx x, idx y, idx z) const	 // lbm_data.h:49-57 with permutation (x,z,y), overlap in x only
 	{
@@ -862,6 +863,37 @@ inline bool shadow_pair(int cx, int cy, const Nbr& n, int& a, int& b)
 	return true;
 }
 
+// D2Q9 GEO_FLUID_NEAR_WALL: Bouzidi interpolated bounce-back on the links that hit a wall (d2q9/bc.h:61-87,140-167), A-B only.
+// theta < 0: the link does not hit a wall, plain pull.  Called after the ordinary streaming has filled K.f.
+// Same shadowing quirk as the wall rule: the two statements for the straight +-y links are written `KS.f[zp] = ...` /
+// `KS.f[zm] = ...` with the shadowed names (bc.h:153,155), so they assign f[0] (overwritten by the rest-particle line right
+// after) and the +-y populations keep their plainly streamed values.
+template <typename R>
+void bouzidi_near_wall(const Block<R>& B, Cell<R, 9>& K, const Nbr& n)
+{
+	auto theta = [&](int dir) -> R { return B.bouzidi ? B.bouzidi[dir * B.XYZ + B.cell(n.x, n.y, n.z)] : (R) -1; };
+	auto fb = [&](R th, int k, int kbar, idx xB, idx yB, idx xS, idx yS) -> R {
+		if (th < (R) 0)
+			return B.cur[B.at(kbar, xS, yS, n.z)];
+		const R fA = B.cur[B.at(k, n.x, n.y, n.z)], fOppA = B.cur[B.at(kbar, n.x, n.y, n.z)], fB = B.cur[B.at(k, xB, yB, n.z)];
+		if (th <= (R) 0.5)
+			return (R) 2.0 * th * fA + ((R) 1.0 - (R) 2.0 * th) * fB;
+		const R w = (R) 0.5 / th;
+		return ((R) 1.0 - w) * fOppA + w * fA;
+	};
+	const R th_e = theta(0), th_w = theta(2), th_ne = theta(4), th_nw = theta(5), th_sw = theta(6), th_se = theta(7);
+	K.f[E(1, 0)] = fb(th_w, E(-1, 0), E(1, 0), n.xp, n.y, n.xm, n.y);
+	K.f[E(-1, 0)] = fb(th_e, E(1, 0), E(-1, 0), n.xm, n.y, n.xp, n.y);
+	K.f[E(1, 1)] = fb(th_sw, E(-1, -1), E(1, 1), n.xp, n.yp, n.xm, n.ym);
+	K.f[E(-1, 1)] = fb(th_se, E(1, -1), E(-1, 1), n.xm, n.yp, n.xp, n.ym);
+	K.f[E(-1, -1)] = fb(th_ne, E(1, 1), E(-1, -1), n.xm, n.ym, n.xp, n.yp);
+	K.f[E(1, -1)] = fb(th_nw, E(-1, 1), E(1, -1), n.xp, n.ym, n.xm, n.yp);
+	K.f[E(0, 0)] = B.cur[B.at(E(0, 0), n.x, n.y, n.z)];
+}
+template <typename R, int Q>
+void bouzidi_near_wall(const Block<R>&, Cell<R, Q>&, const Nbr&)
+{}
+
 // returns false for GEO_NOTHING (cell neither reads nor writes distributions)
 template <typename L, typename R, int Q>
 bool pre_collision(const Block<R>& B, Cell<R, Q>& K, const oracle_desc& d, int m, Nbr n, bool aa)
@@ -956,6 +988,8 @@ bool pre_collision(const Block<R>& B, Cell<R, Q>& K, const oracle_desc& d, int m
 		density_velocity(K);
 	}
 	else {
+		if (L::NDIM == 2 && m == 12 && ! aa)  // D2Q9 GEO_FLUID_NEAR_WALL (d2q9/bc.h:29); under A-A the reference's df_cur reads are meaningless
+			bouzidi_near_wall(B, K, n);
 		density_velocity(K);
 	}
 	return true;
@@ -1047,6 +1081,7 @@ Block<R> make_block(const oracle_desc* d, const oracle_params* p)
 		B.profile = (const R*) p->vx_profile;
 		B.profile_sy = p->profile_size_y;
 		B.stat_counter = p->stat_counter;
+		B.bouzidi = (const R*) p->bouzidi_coeff;
 	}
 	return B;
 }

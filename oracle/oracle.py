@@ -50,6 +50,7 @@ class _Params(C.Structure):
         ("profile_size_y", C.c_int64),
         ("stat_counter", C.c_int32),
         ("pad_", C.c_int32),
+        ("bouzidi_coeff", C.c_void_p),
     ]
 
 
@@ -109,6 +110,7 @@ class Params:
     inflow_vz: float = 0.0
     vx_profile: np.ndarray | None = None  # dreal[z, y]
     stat_counter: int = 0
+    bouzidi: np.ndarray | None = None  # dreal[8, x, z, y] (D2Q9 near-wall interpolation coefficients)
     _keep: list = field(default_factory=list, repr=False)
 
     def c(self) -> _Params:
@@ -117,7 +119,11 @@ class Params:
             assert self.vx_profile.flags["C_CONTIGUOUS"]
             ptr = self.vx_profile.ctypes.data
             sy = self.vx_profile.shape[-1]
-        return _Params(self.lbmViscosity, self.fx, self.fy, self.fz, self.inflow_vx, self.inflow_vy, self.inflow_vz, ptr, sy, self.stat_counter, 0)
+        bz = None
+        if self.bouzidi is not None:
+            assert self.bouzidi.flags["C_CONTIGUOUS"] and self.bouzidi.shape[0] == 8
+            bz = self.bouzidi.ctypes.data
+        return _Params(self.lbmViscosity, self.fx, self.fy, self.fz, self.inflow_vx, self.inflow_vy, self.inflow_vz, ptr, sy, self.stat_counter, 0, bz)
 
 
 def _path(kind: str, streaming: int, fast: bool) -> str:

@@ -47,6 +47,8 @@ typedef struct oracle_params
 	int64_t profile_size_y;
 	int32_t stat_counter; /* MACRO_Mean sample index (d3q27/macro.h:117) */
 	int32_t pad_;
+	const void* bouzidi_coeff; /* D2Q9 GEO_FLUID_NEAR_WALL: dreal[8][XYZ], direction order E,N,W,S,NE,NW,SW,SE, < 0 = link does not hit a wall
+								  (lbm_data.h:69-83); NULL = every coefficient reads -1 */
 } oracle_params;
 
 /* 0 = ok, nonzero = combination not available in this library */

@@ -122,6 +122,7 @@ inline typename NSE::DATA ref_make_data(const oracle_desc* d, const oracle_param
 		SD.fx = (dreal) p->fx;
 		SD.fy = (dreal) p->fy;
 		SD.fz = (dreal) p->fz;
+		SD.bouzidi_coeff_ptr = (dreal*) p->bouzidi_coeff;
 		ref_bind_inflow(SD, p);
 	}
 	return SD;

@@ -22,6 +22,8 @@ def set_params(e: B.Engine, p: O.Params):
                  stat_counter=0)
     if p.vx_profile is not None:
         e.set_inflow_profile(p.vx_profile)
+    if p.bouzidi is not None:
+        e.bouzidi_upload(p.bouzidi)
 
 
 def run_case_engine(case: gc.Case, chunk: int | None = None, **kw):

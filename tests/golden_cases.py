@@ -62,8 +62,21 @@ CASES = [
     Case("d2q9_clbm_f64_aa_zoo", O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AA, X=13, Y=11, Z=1), _p2(), zoo, 4),
     Case("d2q9_clbm_f32_ab_zoo", O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, precision=O.F32, X=13, Y=11, Z=1), _p2(), zoo, 4),
     Case("cum_f64_ab_mean", O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, macro=O.MACRO_MEAN, X=8, Y=7, Z=6), _p3(), lambda d: lc.map_random_ab(d, seed=3), 5),
+    Case("d2q9_srt_f64_ab_bouzidi", O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, X=13, Y=11, Z=1),
+         _p2(bouzidi=lc.map_and_coeffs_bouzidi(O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, X=13, Y=11, Z=1))[1]),
+         lambda d: lc.map_and_coeffs_bouzidi(d)[0], 4, seed=5),
+    Case("cum_f64_ab_profile", O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, inflow=O.INFLOW_PROFILE_YZ, X=10, Y=9, Z=8),
+         O.Params(lbmViscosity=0.004, fx=1e-5, vx_profile=(0.05 * np.random.RandomState(5).random_sample((8, 9)))), lambda d: _profile_map(d), 6),
     Case("cum_f64_ab_void", O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, macro=O.MACRO_VOID, X=8, Y=7, Z=6), _p3(), lambda d: lc.map_random_ab(d, seed=3), 3),
 ]
+
+
+def _profile_map(d):
+    m = d.new_map(lc.G3["FLUID"])
+    m[0] = lc.G3["INFLOW_LEFT"]
+    m[1, 2:5, 2:6] = lc.G3["INFLOW"]
+    m[d.X - 1] = lc.G3["OUTFLOW_RIGHT"]
+    return m
 
 
 def _duct_all_periodic_faces(d):

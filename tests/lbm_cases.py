@@ -216,3 +216,12 @@ def map_duct_slab_safe(d: O.Desc) -> np.ndarray:
         plane = m[xf]
         plane[plane != g["PERIODIC"]] = g["NOTHING"]
     return m
+
+
+def map_and_coeffs_bouzidi(d: O.Desc, seed: int = 9):
+    """Random D2Q9 map with ~30 % GEO_FLUID_NEAR_WALL (=12) cells and coefficients theta in [-0.8, 1.2] for all 8 links."""
+    rs = np.random.RandomState(seed)
+    m = map_random_ab(d, seed=seed)
+    m[rs.random_sample(m.shape) < 0.3] = 12
+    bz = (2.0 * rs.random_sample((8,) + m.shape) - 0.8).astype(d.dtype)
+    return m, bz

@@ -222,3 +222,42 @@ def test_raw_state_dump_and_resume(name):
         assert e.iterations == 7
         assert np.array_equal(e.df_download(0, with_ghosts=True), full_df)
         assert np.array_equal(e.macro_download(), full_mac)
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+def test_profile_inflow_matches_oracle(prec):
+    """NSE_Data_XProfileInflow (sim_NSE/sim_2.cu:16-33): the inflow velocity is read from a (y,z) profile array."""
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, inflow=O.INFLOW_PROFILE_YZ, precision=prec, X=10, Y=9, Z=8)
+    rs = np.random.RandomState(5)
+    prof = (0.05 * rs.random_sample((d.Z, d.Y))).astype(d.dtype)
+    m = d.new_map(lc.G3["FLUID"])
+    m[0] = lc.G3["INFLOW_LEFT"]
+    m[1, 2:5, 2:6] = lc.G3["INFLOW"]
+    m[d.X - 1] = lc.G3["OUTFLOW_RIGHT"]
+    case = gc.Case("profile", d, O.Params(lbmViscosity=0.004, fx=1e-5, vx_profile=prof), lambda dd: m, 6, "noisy")
+    df, mac, _ = run_case_engine(case)
+    df_ref, mac_ref = gc.run_case(case, "port")
+    compare(case, df, mac, df_ref, mac_ref, TOL[prec], "profile inflow")
+
+
+def test_mean_macro_across_step_batches():
+    """MACRO_Mean accumulators (d3q27/macro.h:84-171): lbmx_step(n) advances stat_counter per step, so batching is invisible."""
+    case = gc.BY_NAME["cum_f64_ab_mean"]
+    a_df, a_mac, _ = run_case_engine(case)          # one batch of 5
+    b_df, b_mac, _ = run_case_engine(case, chunk=2)  # 2 + 2 + 1
+    assert np.array_equal(a_mac, b_mac) and np.array_equal(a_df, b_df)
+    _, mac_ref = gc.run_case(case, "port")
+    for lo, hi, label in lc.macro_groups(case.desc):
+        assert lc.rel_err(a_mac[lo:hi], mac_ref[lo:hi]) <= 1e-12, label
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("coll", [O.SRT, O.CLBM])
+def test_d2q9_bouzidi_near_wall_matches_oracle(coll, prec):
+    d = O.Desc(lattice=O.D2Q9, coll=coll, eq=O.EQ_STD, streaming=O.AB, precision=prec, X=13, Y=11, Z=1)
+    m, bz = lc.map_and_coeffs_bouzidi(d)
+    p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.05, inflow_vy=-0.01, bouzidi=bz)
+    case = gc.Case("bouzidi", d, p, lambda dd: m, 4, "noisy", seed=5)
+    df, mac, _ = run_case_engine(case)
+    df_ref, mac_ref = gc.run_case(case, "port")
+    compare(case, df, mac, df_ref, mac_ref, TOL[prec], "bouzidi")

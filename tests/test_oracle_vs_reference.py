@@ -113,3 +113,14 @@ def test_long_run_smooth_box_stays_identical():
         orc.step(p, a, a, mac, m, 0, 200, 2)
         out.append((a, a, mac))
     assert_same(out[0], out[1], "200 steps A-A")
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("coll", [O.SRT, O.CLBM])
+def test_d2q9_bouzidi_near_wall(coll, prec):
+    """GEO_FLUID_NEAR_WALL with random interpolation coefficients in [-0.8, 1.2] (both Bouzidi branches and "no wall")."""
+    d = O.Desc(lattice=O.D2Q9, coll=coll, eq=O.EQ_STD, streaming=O.AB, precision=prec, X=13, Y=11, Z=1)
+    m, bz = lc.map_and_coeffs_bouzidi(d)
+    p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.05, inflow_vy=-0.01, bouzidi=bz)
+    ref, port = run_pair(d, m, p, nsteps=3, seed=5)
+    assert_same(ref, port, f"bouzidi coll={coll} prec={prec}")

@@ -62,7 +62,7 @@ SYMBOLS = [
     "lbmx_last_error", "lbmx_version", "lbmx_decompose_x", "lbmx_halo_directions", "lbmx_halo_plan", "lbmx_create", "lbmx_destroy", "lbmx_get_layout",
     "lbmx_comm_unique_id", "lbmx_comm_init", "lbmx_map_upload", "lbmx_map_download", "lbmx_df_set_equilibrium", "lbmx_df_set_equilibrium_field",
     "lbmx_df_upload", "lbmx_df_download", "lbmx_df_sync_ghosts", "lbmx_macro_init", "lbmx_macro_download", "lbmx_macro_upload", "lbmx_set_params",
-    "lbmx_set_inflow_profile", "lbmx_step", "lbmx_sync", "lbmx_step_timed", "lbmx_get_iterations", "lbmx_set_iterations", "lbmx_has_nan",
+    "lbmx_set_inflow_profile", "lbmx_bouzidi_upload", "lbmx_step", "lbmx_sync", "lbmx_step_timed", "lbmx_get_iterations", "lbmx_set_iterations", "lbmx_has_nan",
     "lbmx_get_device_ptrs", "lbmx_get_stats",
 ]
 
@@ -98,6 +98,7 @@ def lib():
         L.lbmx_macro_upload.argtypes = [vp, vp, C.c_int]
         L.lbmx_set_params.argtypes = [vp, C.POINTER(Params)]
         L.lbmx_set_inflow_profile.argtypes = [vp, vp, i64, i64]
+        L.lbmx_bouzidi_upload.argtypes = [vp, vp]
         L.lbmx_step.argtypes = [vp, i64]
         L.lbmx_sync.argtypes = [vp]
         L.lbmx_step_timed.argtypes = [vp, i64, C.POINTER(C.c_float)]
@@ -243,6 +244,10 @@ class Engine:
     def set_inflow_profile(self, prof):
         assert prof.ndim == 2
         _check(lib().lbmx_set_inflow_profile(self._h, self._ptr(prof, self.dtype), prof.shape[1], prof.shape[0]), "lbmx_set_inflow_profile")
+
+    def bouzidi_upload(self, coeff):
+        shp = (8,) + self.map_shape(False)
+        _check(lib().lbmx_bouzidi_upload(self._h, self._ptr(coeff, self.dtype, shp)), "lbmx_bouzidi_upload")
 
     # -- stepping
     def step(self, n=1):

@@ -138,6 +138,7 @@ struct lbmx_engine
 	int16_t* map = nullptr;
 	uint32_t* blist = nullptr;
 	void* profile = nullptr;
+	void* bouzidi = nullptr;
 	int64_t profile_sy = 0;
 	int* d_flag = nullptr;
 	int* d_dirs = nullptr;	// [2][9]: to_right, to_left
@@ -177,6 +178,7 @@ KParams<R> make_params(const lbmx_engine* e)
 	p.macro = (R*) e->macro;
 	p.map = e->map;
 	p.profile = (const R*) e->profile;
+	p.bouzidi = (const R*) e->bouzidi;
 	p.blist = e->blist;
 	p.XYZ = e->XYZ;
 	p.X = (int) e->X;
@@ -627,7 +629,7 @@ int lbmx_destroy(lbmx_engine* e)
 	cudaDeviceSynchronize();
 	if (e->comm && g_nccl.CommDestroy)
 		g_nccl.CommDestroy(e->comm);
-	for (void* p : {e->df[0], e->df[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, (void*) e->d_flag, (void*) e->d_dirs, e->sendbuf[0], e->sendbuf[1], e->recvbuf[0], e->recvbuf[1]})
+	for (void* p : {e->df[0], e->df[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs, e->sendbuf[0], e->sendbuf[1], e->recvbuf[0], e->recvbuf[1]})
 		if (p)
 			cudaFree(p);
 	for (cudaEvent_t ev : {e->ev_edge, e->ev_comm, e->ev_main, e->ev_t0, e->ev_t1})
@@ -931,6 +933,20 @@ int lbmx_set_inflow_profile(lbmx_engine* e, const void* host_profile, int64_t si
 	CU(cudaMemcpy(e->profile, host_profile, (size_t) (size_y * size_z) * e->rs, cudaMemcpyHostToDevice));
 	e->profile_sy = size_y;
 	return LBMX_OK;
+}
+
+int lbmx_bouzidi_upload(lbmx_engine* e, const void* host_coeff)
+{
+	if (! e || ! host_coeff)
+		return fail(LBMX_ERR_ARG, "lbmx_bouzidi_upload: null argument");
+	if (e->d.lattice != LBMX_D2Q9 || e->aa())
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_bouzidi_upload: the near-wall interpolation exists for D2Q9 with A-B streaming only (d2q9/bc.h:140-167)");
+	CU(cudaSetDevice(e->dev));
+	if (! e->bouzidi) {
+		CU(cudaMalloc(&e->bouzidi, (size_t) 8 * e->XYZ * e->rs));
+		CU(cudaMemset(e->bouzidi, 0xbf, (size_t) 8 * e->XYZ * e->rs));	// ghost planes: a negative value (0xbfbf... < 0 in both precisions)
+	}
+	return copy_components(e, e->bouzidi, (void*) host_coeff, 8, e->rs, false, true);
 }
 
 int lbmx_step(lbmx_engine* e, int64_t nsteps)

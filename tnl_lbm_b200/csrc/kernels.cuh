@@ -49,6 +49,7 @@ struct KParams
 	R* macro;		   // [n_macro][XYZ]
 	const int16_t* map; // [XYZ]
 	const R* profile;  // inflow vx profile [z*profile_sy + y] or nullptr
+	const R* bouzidi;  // D2Q9 near-wall interpolation coefficients [8][XYZ] or nullptr (lbm_data.h:69-83)
 	const uint32_t* blist;	// boundary list: storage cell indices
 	long long XYZ;	   // storage cells per component
 	int X, Y, Z, ox;   // local slab size (no ghosts), ghost planes per side
@@ -373,6 +374,37 @@ LBMX_D void inflow_left_moments(R (&f)[19], R& rho, R vx, R vy, R vz)
 	static_for<19>([&](auto qc) { f[qc] = feq[qc]; });
 }
 
+// D2Q9 GEO_FLUID_NEAR_WALL: Bouzidi interpolated bounce-back (d2q9/bc.h:61-87,140-167), A-B only.  theta < 0: link does not hit
+// a wall.  Runs after the ordinary pull has filled f.  REFERENCE QUIRK kept: the statements for the straight +-y links are
+// written with the shadowed names zp/zm (bc.h:153,155) and end up assigning f[0], which the rest-particle line overwrites --
+// so only the six links with an x component are interpolated.
+template <typename R>
+LBMX_D void bouzidi_near_wall(const KParams<R>& p, R (&f)[9], int c, const Deltas& d)
+{
+	using L = D2Q9;
+	auto theta = [&](int dir) -> R { return p.bouzidi ? p.bouzidi[dir * p.XYZ + c] : R(-1); };
+	auto fb = [&](R th, int k, int kbar, int offB, int offS) -> R {
+		if (th < R(0))
+			return p.cur[kbar * p.XYZ + (c + offS)];
+		const R fA = p.cur[k * p.XYZ + c], fOppA = p.cur[kbar * p.XYZ + c], fB = p.cur[k * p.XYZ + (c + offB)];
+		if (th <= R(0.5))
+			return R(2) * th * fA + (R(1) - R(2) * th) * fB;
+		const R w = R(0.5) / th;
+		return (R(1) - w) * fOppA + w * fA;
+	};
+	// coefficient order: 0 E, 1 N, 2 W, 3 S, 4 NE, 5 NW, 6 SW, 7 SE
+	f[L::find(1, 0)] = fb(theta(2), L::find(-1, 0), L::find(1, 0), d.xp, d.xm);
+	f[L::find(-1, 0)] = fb(theta(0), L::find(1, 0), L::find(-1, 0), d.xm, d.xp);
+	f[L::find(1, 1)] = fb(theta(6), L::find(-1, -1), L::find(1, 1), d.xp + d.yp, d.xm + d.ym);
+	f[L::find(-1, 1)] = fb(theta(7), L::find(1, -1), L::find(-1, 1), d.xm + d.yp, d.xp + d.ym);
+	f[L::find(-1, -1)] = fb(theta(4), L::find(1, 1), L::find(-1, -1), d.xm + d.ym, d.xp + d.yp);
+	f[L::find(1, -1)] = fb(theta(5), L::find(-1, 1), L::find(1, -1), d.xp + d.ym, d.xm + d.yp);
+	f[L::find(0, 0)] = p.cur[c];
+}
+template <typename R, int Q>
+LBMX_D void bouzidi_near_wall(const KParams<R>&, R (&)[Q], int, const Deltas&)
+{}
+
 // symmetry planes: populations pointing in direction DST along AXIS take the value of their mirror image
 // (d3q27/bc.h:172-237, d2q9/bc.h:168-191).  D2Q9 quirk: the straight +-y pair is addressed through shadowed names in the
 // reference and ends up a no-op (see the wall rule below), so it is skipped here as well.
@@ -516,6 +548,8 @@ __global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
 			mirror_pops<L, 1, +1>(f);
 		else if (m == L::SYM_FRONT)
 			mirror_pops<L, 1, -1>(f);
+		else if (L::NDIM == 2 && m == 12 && p.stream == S_AB)  // D2Q9 GEO_FLUID_NEAR_WALL (d2q9/bc.h:29); plain fluid under A-A
+			bouzidi_near_wall(p, f, c, d);
 		density_velocity(f, p.phys, rho, vx, vy, vz);
 	}
 
