@@ -337,6 +337,7 @@ struct LBM_Data
 	dreal* dfs[DFMAX] = {};
 	dreal* dmacro = nullptr;
 	map_t* dmap = nullptr;
+	dreal* bouzidi_coeff_ptr = nullptr;	 // informational on the host side: the engine owns the device copy (lbmx_bouzidi_upload)
 	idx X() const { return sizes[0]; }
 	idx Y() const { return sizes[1]; }
 	idx Z() const { return sizes[2]; }
@@ -459,6 +460,25 @@ struct LBM_BLOCK
 		{
 			return v[k * n + (size_t) (((x - off.x()) * loc.z() + (z - off.z())) * loc.y() + (y - off.y()))];
 		}
+		dreal* getData() { return v.empty() ? nullptr : v.data(); }
+		const dreal* getData() const { return v.empty() ? nullptr : v.data(); }
+		void setValue(dreal value) { std::fill(v.begin(), v.end(), value); }
+	};
+	// device-side Bouzidi array of the reference (`block.dBouzidi = block.hBouzidi;`, sim_2D/sim2d_2.cu:328): a proxy whose
+	// assignment uploads through the C ABI
+	struct DeviceBouzidi
+	{
+		LBM_BLOCK* owner = nullptr;
+		bool uploaded = false;
+		DeviceBouzidi& operator=(const HostField& h)
+		{
+			if (owner && owner->engine && ! h.v.empty()) {
+				lbmx_host::check(lbmx_bouzidi_upload(owner->engine, h.v.data()), "lbmx_bouzidi_upload");
+				uploaded = true;
+			}
+			return *this;
+		}
+		dreal* getData() const { return uploaded ? reinterpret_cast<dreal*>(owner) : nullptr; }	// non-null token: the pointer itself is not usable on the host
 	};
 
 	typename CONFIG::DATA data;
@@ -467,15 +487,19 @@ struct LBM_BLOCK
 	HostMap hmap;
 	HostField hmacro;
 	HostField hfs[DFMAX];  // host copies of the distributions, filled by copyDFsToHost only
+	HostField hBouzidi;	   // D2Q9 near-wall coefficients [8][local], allocated by allocateBouzidiCoeffArrays (lbm_block.hpp:740-770)
+	DeviceBouzidi dBouzidi;
 	lbmx_engine* engine = nullptr;
 
-	LBM_BLOCK(idx3d global_, idx3d local_, idx3d offset_) : global(global_), local(local_), offset(offset_) {}
+	LBM_BLOCK(idx3d global_, idx3d local_, idx3d offset_) : global(global_), local(local_), offset(offset_) { dBouzidi.owner = this; }
 	LBM_BLOCK(const LBM_BLOCK&) = delete;
 	LBM_BLOCK(LBM_BLOCK&& o) noexcept
 	: data(o.data), global(o.global), local(o.local), offset(o.offset), rank(o.rank), nproc(o.nproc), id(o.id), hmap(std::move(o.hmap)),
-	  hmacro(std::move(o.hmacro)), engine(o.engine)
+	  hmacro(std::move(o.hmacro)), hBouzidi(std::move(o.hBouzidi)), engine(o.engine)
 	{
 		o.engine = nullptr;
+		dBouzidi.owner = this;
+		dBouzidi.uploaded = o.dBouzidi.uploaded;
 	}
 	~LBM_BLOCK()
 	{
@@ -569,7 +593,21 @@ struct LBM_BLOCK
 		data.dmap = (map_t*) p.dmap;
 		data.even_iter = p.even_iter != 0;
 	}
-	void copyMapToDevice() { lbmx_host::check(lbmx_map_upload(engine, hmap.v.data(), 0), "lbmx_map_upload"); }
+	void allocateBouzidiCoeffArrays()
+	{
+		const size_t n = (size_t) local.x() * local.y() * local.z();
+		hBouzidi.v.assign(8 * n, (dreal) -1);
+		hBouzidi.off = offset;
+		hBouzidi.loc = local;
+		hBouzidi.n = n;
+	}
+	// also moves the Bouzidi coefficients when they are allocated, like the reference (lbm_block.hpp:355-364)
+	void copyMapToDevice()
+	{
+		lbmx_host::check(lbmx_map_upload(engine, hmap.v.data(), 0), "lbmx_map_upload");
+		if (hBouzidi.getData() != nullptr)
+			dBouzidi = hBouzidi;
+	}
 	void copyMapToHost() { lbmx_host::check(lbmx_map_download(engine, hmap.v.data(), 0), "lbmx_map_download"); }
 	void copyMacroToHost()
 	{
@@ -678,6 +716,7 @@ struct LBM
 	LBMX_FANOUT(copyMacroToDevice)
 	LBMX_FANOUT(allocateHostData)
 	LBMX_FANOUT(computeInitialMacro)
+	LBMX_FANOUT(allocateBouzidiCoeffArrays)
 #undef LBMX_FANOUT
 	void copyDFsToHost(uint8_t t)
 	{
