@@ -280,11 +280,16 @@ def main():
     barrier()
     te0 = time.perf_counter()
     upload_state()
+    te_up = time.perf_counter()
     eng.step(a.steps)
+    eng.sync()
+    te_st = time.perf_counter()
     eng.macro_download(out=h_mac)
     eng.sync()
     torch.cuda.synchronize()
-    te = allmax(time.perf_counter() - te0)
+    te1 = time.perf_counter()
+    log(f"[rank {rank}] e2e phases: upload {te_up - te0:.3f}s, {a.steps} steps {te_st - te_up:.3f}s, macro download {te1 - te_st:.3f}s")
+    te = allmax(te1 - te0)
     e2e_value = cells_global * a.steps / te / 1e6
     h2d = (h_map.nbytes + sum(f.nbytes for f in fields)) * N
     d2h = h_mac.nbytes * N

@@ -9,6 +9,8 @@
 #include "kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -118,6 +120,31 @@ int halo_dirs(int32_t* to_right, int32_t* to_left)
 }
 
 }  // namespace
+
+// ---- cell classification on the device (lbmx_map_upload): which cells go to the boundary list, how many per x-plane ----------
+struct IsBoundaryCell
+{
+	const int16_t* map;
+	int periodic;
+	__host__ __device__ bool operator()(uint32_t c) const
+	{
+		const int m = map[c];
+		return m != 0 && m != periodic;	 // neither GEO_FLUID nor GEO_PERIODIC
+	}
+};
+
+__global__ void k_count_boundary_cells(const int16_t* map, long long first_cell, int YZ, int periodic, unsigned* per_plane)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool b = false;
+	if (i < YZ) {
+		const int m = map[first_cell + (long long) blockIdx.y * YZ + i];
+		b = m != 0 && m != periodic;
+	}
+	const unsigned n = __popc(__ballot_sync(0xffffffffu, b));
+	if ((threadIdx.x & 31) == 0 && n)
+		atomicAdd(per_plane + blockIdx.y, n);
+}
 
 // =====================================================================================================================
 // engine
@@ -738,32 +765,47 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 		CU(cudaStreamSynchronize(e->s_main));
 	}
 	// launch plan: cells that are neither GEO_FLUID nor GEO_PERIODIC go to the boundary list, ordered by storage index
-	// (so list ranges per x-plane are contiguous and neighbouring entries are neighbouring cells)
-	std::vector<int16_t> hm((size_t) e->XYZ);
-	CU(cudaMemcpy(hm.data(), e->map, hm.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
-	const int fluid = 0;
+	// (so list ranges per x-plane are contiguous and neighbouring entries are neighbouring cells).  Counted and compacted on
+	// the device: the map never travels back to the host.
 	const int periodic = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::PERIODIC : (int) D3Q27::PERIODIC;	// D3Q19 shares the D3Q27 cell types
-	std::vector<uint32_t> list;
+	const long long first_cell = (long long) e->ox * e->YZ, n_cells = (long long) e->X * e->YZ;
+	unsigned* d_counts = nullptr;
+	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) e->X));
+	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) e->X, e->s_main));
+	k_count_boundary_cells<<<dim3((unsigned) ((e->YZ + 255) / 256), (unsigned) e->X), 256, 0, e->s_main>>>(e->map, first_cell, (int) e->YZ, periodic, d_counts);
+	e->stats.kernel_launches++;
+	std::vector<unsigned> counts((size_t) e->X);
+	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) e->X, cudaMemcpyDeviceToHost, e->s_main));
+	CU(cudaStreamSynchronize(e->s_main));
+	CU(cudaFree(d_counts));
 	e->plane_start.assign((size_t) e->X + 1, 0);
-	for (int64_t x = 0; x < e->X; x++) {
-		e->plane_start[(size_t) x] = (int64_t) list.size();
-		const int64_t base = (x + e->ox) * e->YZ;
-		for (int64_t i = 0; i < e->YZ; i++) {
-			const int m = hm[(size_t) (base + i)];
-			if (m != fluid && m != periodic)
-				list.push_back((uint32_t) (base + i));
-		}
-	}
-	e->plane_start[(size_t) e->X] = (int64_t) list.size();
-	e->nb = (int64_t) list.size();
-	e->n_bulk = e->X * e->YZ - e->nb;
+	for (int64_t x = 0; x < e->X; x++)
+		e->plane_start[(size_t) x + 1] = e->plane_start[(size_t) x] + counts[(size_t) x];
+	e->nb = e->plane_start[(size_t) e->X];
+	e->n_bulk = n_cells - e->nb;
 	if (e->blist) {
 		CU(cudaFree(e->blist));
 		e->blist = nullptr;
 	}
 	if (e->nb > 0) {
-		CU(cudaMalloc(&e->blist, list.size() * sizeof(uint32_t)));
-		CU(cudaMemcpy(e->blist, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		CU(cudaMalloc(&e->blist, (size_t) e->nb * sizeof(uint32_t)));
+		cub::CountingInputIterator<uint32_t> cells((uint32_t) first_cell);
+		IsBoundaryCell pred{e->map, periodic};
+		int* d_selected = nullptr;
+		void* d_temp = nullptr;
+		size_t temp_bytes = 0;
+		CU(cudaMalloc(&d_selected, sizeof(int)));
+		CU(cub::DeviceSelect::If(nullptr, temp_bytes, cells, e->blist, d_selected, (int) n_cells, pred, e->s_main));
+		CU(cudaMalloc(&d_temp, temp_bytes));
+		CU(cub::DeviceSelect::If(d_temp, temp_bytes, cells, e->blist, d_selected, (int) n_cells, pred, e->s_main));	 // stable: output is sorted
+		e->stats.kernel_launches++;
+		int selected = 0;
+		CU(cudaMemcpyAsync(&selected, d_selected, sizeof(int), cudaMemcpyDeviceToHost, e->s_main));
+		CU(cudaStreamSynchronize(e->s_main));
+		CU(cudaFree(d_temp));
+		CU(cudaFree(d_selected));
+		if (selected != e->nb)
+			return fail(LBMX_ERR_STATE, "lbmx_map_upload: boundary-list compaction disagrees with the per-plane counts");
 	}
 	e->stats.boundary_cells = e->nb;
 	e->stats.bulk_cells = e->n_bulk;
