@@ -76,8 +76,18 @@ typedef struct lbmx_desc
 	int32_t ghost_x;  /* 1: one ghost x-plane per side and the reference's nproc>1 index rule (kernels.h:21-29,39-48);
 						 forced to 1 when nranks > 1; with nranks == 1 the exchange is a periodic self-exchange */
 	int32_t periodic_x; /* slab 0 and slab nranks-1 are neighbours (State ctor `periodic_lattice`, lattice_decomposition.h:148-162) */
-	int32_t reserved[3];
+	int32_t flags;		/* LBMX_FLAG_* */
+	int32_t reserved[2];
 } lbmx_desc;
+
+/* "Parity arithmetic": kernels that evaluate every expression in the reference's floating-point association, with true divisions
+ * and without FMA contraction (tnl_lbm_b200/csrc/collide_strict.cuh, nvcc -fmad=false).  With this flag the engine reproduces the
+ * reference's strict-IEEE CPU build BIT FOR BIT in fp32 and fp64 (tests/test_gpu_parity.py: every golden case and 1000-step runs).
+ * Why it exists: in fp32 the reference is not reproducible to the 1e-5 tolerance against itself across compilers' contraction
+ * choices (2e-5 in velocity after 1000 steps between its strict and its FMA-contracted CPU build), so "within tolerance of the
+ * reference" needs a pinned arithmetic to be checkable.  The default kernels (one reciprocal, pruned transforms, FMA) stay within
+ * 1e-12 (fp64) of it and are faster.  D3Q27 and D2Q9 only: D3Q19 has no reference. */
+#define LBMX_FLAG_STRICT_ARITH 1
 
 /* per-step scalars: the non-pointer members of block.data (lbm_data.h:12-30,87-115), set by
  * State::updateKernelData (state.hpp:1314-1321) and the solver's updateKernelVelocities() */

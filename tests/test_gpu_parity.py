@@ -261,3 +261,43 @@ def test_d2q9_bouzidi_near_wall_matches_oracle(coll, prec):
     df, mac, _ = run_case_engine(case)
     df_ref, mac_ref = gc.run_case(case, "port")
     compare(case, df, mac, df_ref, mac_ref, TOL[prec], "bouzidi")
+
+
+def assert_bit_exact(a, ref, what):
+    """-0.0 == +0.0 counts as equal (np.array_equal); anything else must match to the last bit."""
+    assert a.shape == ref.shape and a.dtype == ref.dtype, what
+    if not np.array_equal(a, ref):
+        diff = np.abs(a.astype(np.float64) - ref.astype(np.float64))
+        i = np.unravel_index(np.argmax(diff), diff.shape)
+        raise AssertionError(f"{what}: {int((a != ref).sum())} of {a.size} values differ, max abs {diff.max():.3e} at {tuple(int(v) for v in i)} got={a[i]!r} ref={ref[i]!r}")
+
+
+@pytest.mark.parametrize("name", [c.name for c in gc.CASES])
+def test_parity_arithmetic_is_bit_exact(name):
+    """LBMX_FLAG_STRICT_ARITH: kernels that keep the reference's floating-point association, true divisions and no FMA contraction.
+    They reproduce the reference's strict CPU build BIT FOR BIT, fp32 and fp64, on every golden case -- full arrays against the
+    CPU restatement, and the committed samples that the reference's own code produced (tests/golden/make_golden.py)."""
+    case = gc.BY_NAME[name]
+    df, mac, _ = run_case_engine(case, flags=B.FLAG_STRICT_ARITH)
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=4)
+    assert_bit_exact(df, df_ref, name + " strict: distributions vs port")
+    if case.desc.macro != O.MACRO_VOID:
+        assert_bit_exact(mac, mac_ref, name + " strict: macro vs port")
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    s_ = int(z["stride"])
+    assert_bit_exact(gc.sample(df, s_), z["df_sample"], name + " strict: distributions vs golden sample")
+    if case.desc.macro != O.MACRO_VOID:
+        assert_bit_exact(gc.sample(mac, s_), z["macro_sample"], name + " strict: macro vs golden sample")
+
+
+@pytest.mark.parametrize("coll,eq,st,prec,nu", [(O.SRT, O.EQ_STD, O.AB, O.F32, 0.02), (O.CUM, O.EQ_INV_CUM, O.AA, O.F32, 1e-3), (O.MRT_LES, O.EQ_STD, O.AA, O.F32, 1e-3),
+                                                 (O.CUM, O.EQ_INV_CUM, O.AB, O.F64, 1e-3)])
+def test_1000_steps_parity_arithmetic_is_bit_exact(coll, eq, st, prec, nu):
+    """The fp32 case on which the reference differs from itself by 2e-5 (strict vs FMA build): in parity arithmetic the engine
+    stays identical to the strict reference over 1000 steps -- distributions, density and velocity."""
+    d = O.Desc(coll=coll, eq=eq, streaming=st, precision=prec, X=24, Y=24, Z=24)
+    case = gc.Case("long", d, O.Params(lbmViscosity=nu, fx=1e-6), lc.map_periodic, 1000, "smooth")
+    df, mac, _ = run_case_engine(case, flags=B.FLAG_STRICT_ARITH)
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=os.cpu_count() or 4)
+    assert_bit_exact(df, df_ref, "1000 steps, parity arithmetic: distributions")
+    assert_bit_exact(mac, mac_ref, "1000 steps, parity arithmetic: macro")

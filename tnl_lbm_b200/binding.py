@@ -22,6 +22,7 @@ MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN = 0, 1, 2
 INFLOW_NONE, INFLOW_CONST, INFLOW_PROFILE_YZ = 0, 1, 2
 F32, F64 = 0, 1
 MACRO_EVERY_STEP, MACRO_LAST_STEP, MACRO_NEVER = 0, 1, 2
+FLAG_STRICT_ARITH = 1
 
 
 class LbmxError(RuntimeError):
@@ -32,8 +33,8 @@ class Desc(C.Structure):
     _fields_ = (
         [(n, C.c_int32) for n in ("lattice", "coll", "eq", "streaming", "macro", "inflow", "precision", "macro_policy")]
         + [(n, C.c_int64) for n in ("X", "Y", "Z")]
-        + [(n, C.c_int32) for n in ("rank", "nranks", "device", "ghost_x", "periodic_x")]
-        + [("reserved", C.c_int32 * 3)]
+        + [(n, C.c_int32) for n in ("rank", "nranks", "device", "ghost_x", "periodic_x", "flags")]
+        + [("reserved", C.c_int32 * 2)]
     )
 
 
@@ -144,9 +145,9 @@ class Engine:
     """One x-slab of a lattice on one GPU.  Host arrays use the reference layout: [q | component][x][z][y], y fastest."""
 
     def __init__(self, lattice=D3Q27, coll=CUM, eq=EQ_INV_CUM, streaming=AB, macro=MACRO_DEFAULT, inflow=INFLOW_CONST, precision=F64,
-                 X=8, Y=8, Z=8, rank=0, nranks=1, device=-1, ghost_x=0, periodic_x=0, macro_policy=MACRO_LAST_STEP):
+                 X=8, Y=8, Z=8, rank=0, nranks=1, device=-1, ghost_x=0, periodic_x=0, macro_policy=MACRO_LAST_STEP, flags=0):
         self._h = C.c_void_p()
-        self.desc = Desc(lattice, coll, eq, streaming, macro, inflow, precision, macro_policy, X, Y, Z, rank, nranks, device, ghost_x, periodic_x)
+        self.desc = Desc(lattice, coll, eq, streaming, macro, inflow, precision, macro_policy, X, Y, Z, rank, nranks, device, ghost_x, periodic_x, flags)
         _check(lib().lbmx_create(C.byref(self.desc), C.byref(self._h)), "lbmx_create")
         self.layout = Layout()
         _check(lib().lbmx_get_layout(self._h, C.byref(self.layout)), "lbmx_get_layout")

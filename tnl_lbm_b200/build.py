@@ -73,6 +73,15 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
             cmd = [NVCC, *ARCH, *COMMON, "-Xptxas", "-v", f"-DLBMX_FAMILY={fam}", f"-DLBMX_LAT={lat}", f"-DLBMX_KIND={kind}", f"-DLBMX_REAL={real}",
                    "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]
             tasks.append((cmd, obj))
+    # every reference family once more in parity arithmetic: reference association (collide_strict.cuh) and no FMA contraction
+    for fam, lat, kind in FAMILIES:
+        if lat == "D3Q19":
+            continue
+        for real in ("float", "double"):
+            obj = os.path.join(OBJ, f"inst_{fam}_{real}_strict.o")
+            cmd = [NVCC, *ARCH, *COMMON, "-fmad=false", "-DLBMX_STRICT=1", "-Xptxas", "-v", f"-DLBMX_FAMILY={fam}_strict", f"-DLBMX_LAT={lat}",
+                   f"-DLBMX_KIND={kind}", f"-DLBMX_REAL={real}", "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]
+            tasks.append((cmd, obj))
     eng = os.path.join(OBJ, "engine.o")
     tasks.append(([NVCC, *ARCH, *COMMON, "-c", os.path.join(CSRC, "engine.cu"), "-o", eng], eng))
     jobs = jobs or min(len(tasks), os.cpu_count() or 4)

@@ -19,6 +19,17 @@ struct Phys
 	R fx, fy, fz; // homogeneous body force (NSE_Data, lbm_data.h:87-96)
 };
 
+}  // namespace lbmx
+
+// LBMX_STRICT=1 (with nvcc -fmad=false) selects the reference-association variants of collide_strict.cuh for this object file
+#ifndef LBMX_STRICT
+	#define LBMX_STRICT 0
+#endif
+#include "collide_strict.cuh"
+
+namespace lbmx {
+constexpr bool kStrict = LBMX_STRICT != 0;
+
 // --------------------------------------------------------------------------------------------------------------------
 // density / velocity: COMMON::computeDensityAndVelocity (d3q27/common.h:16-50, d2q9/common.h:16-36).
 // The sums are organised as the z-column sums the cumulant transform needs anyway (the compiler merges them); the
@@ -28,6 +39,10 @@ template <typename R>
 LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
 {
 	using L = D3Q27;
+	if constexpr (kStrict) {
+		strict::density_velocity(f, P, rho, vx, vy, vz);
+		return;
+	}
 	R k0[3][3], d[3][3];
 #pragma unroll
 	for (int a = 0; a < 3; a++)
@@ -58,6 +73,10 @@ template <typename R>
 LBMX_D void density_velocity(const R (&f)[9], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
 {
 	using L = D2Q9;
+	if constexpr (kStrict) {
+		strict::density_velocity(f, P, rho, vx, vy, vz);
+		return;
+	}
 	R k0[3], dy[3];
 #pragma unroll
 	for (int a = 0; a < 3; a++) {
@@ -593,7 +612,20 @@ enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 };
 template <int KIND, typename R>
 LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
-	if constexpr (KIND == K_CUM)
+	if constexpr (kStrict) {
+		if constexpr (KIND == K_CUM)
+			strict::collide_cum(f, P, rho, vx, vy, vz);
+		else if constexpr (KIND == K_SRT) {
+			R feq[27];
+			equilibrium(feq, eqkind, rho, vx, vy, vz);
+			strict::collide_srt(f, feq, P, rho, vx, vy, vz);
+		}
+		else if constexpr (KIND == K_BGK)
+			strict::collide_bgk(f, P, rho, vx, vy, vz);
+		else
+			strict::collide_mrt(f, P, rho, vx, vy, vz);
+	}
+	else if constexpr (KIND == K_CUM)
 		collide_cum(f, P, rho, vx, vy, vz);
 	else if constexpr (KIND == K_SRT)
 		collide_srt(f, P, eqkind, rho, vx, vy, vz);
@@ -613,7 +645,16 @@ LBMX_D void collide(R (&f)[19], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 template <int KIND, typename R>
 LBMX_D void collide(R (&f)[9], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
-	if constexpr (KIND == K_SRT)
+	if constexpr (kStrict) {
+		if constexpr (KIND == K_SRT) {
+			R feq[9];
+			equilibrium(feq, 0, rho, vx, vy, R(0));
+			strict::collide_srt(f, feq, P, vx, vy);
+		}
+		else
+			strict::collide_clbm(f, P, rho, vx, vy);
+	}
+	else if constexpr (KIND == K_SRT)
 		collide_srt(f, P, eqkind, rho, vx, vy, vz);
 	else
 		collide_clbm(f, P, rho, vx, vy);

@@ -1,0 +1,369 @@
+// collide_strict.cuh -- "parity arithmetic": the per-cell operators with the reference's floating-point association.
+//
+// Selected per object file with -DLBMX_STRICT=1 together with nvcc -fmad=false (tnl_lbm_b200/build.py builds the fp32 kernel
+// families this way; lbmx_desc.flags & LBMX_FLAG_STRICT_ARITH picks them).  Why it exists: in fp32 the reference is not
+// reproducible to the 1e-5 tolerance against ITSELF once the compiler may contract a*b+c into FMAs or the sums are re-associated
+// (its strict and its contracted CPU builds differ by 2e-5 in velocity after 1000 steps).  These variants evaluate every
+// expression in the order the reference writes it (cited per function, paths relative to the reference's include/lbm3d/), with
+// true divisions, so that the fp32 engine agrees with the reference's strict build to rounding of the few terms that differ:
+// the identically-zero products that are dropped, and the <= 1e-9-relative residues the reference carries in its third-order
+// cumulants (col_cum.h:278-285 with omega3 = omega4 = 1).  The fast variants in collide.cuh remain the default.
+#pragma once
+#include "lattice.cuh"
+
+namespace lbmx {
+
+template <typename R>
+struct Phys;
+
+namespace strict {
+
+// d3q27/common.h:16-50 -- s(q) = f[q] + f[opp q], d(q) = f[q] - f[opp q]
+template <typename R>
+LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
+{
+	using L = D3Q27;
+#define SQ(a, b, c) (f[L::find(a, b, c)] + f[L::find(-(a), -(b), -(c))])
+#define DQ(a, b, c) (f[L::find(a, b, c)] - f[L::find(-(a), -(b), -(c))])
+	const R corners = (SQ(1, 1, 1) + SQ(1, -1, 1)) + (SQ(1, 1, -1) + SQ(-1, 1, 1));
+	const R edges = ((SQ(0, 1, 1) + SQ(0, 1, -1)) + (SQ(1, 0, 1) + SQ(1, 0, -1))) + (SQ(1, 1, 0) + SQ(1, -1, 0));
+	const R axes = (SQ(1, 0, 0) + SQ(0, 1, 0)) + SQ(0, 0, 1);
+	rho = ((corners + edges) + axes) + f[L::find(0, 0, 0)];
+	const R half = R(0.5);
+	const R cz = (DQ(1, 1, 1) + DQ(-1, 1, 1)) + (DQ(1, -1, 1) + DQ(-1, -1, 1));
+	const R ez = (DQ(0, 1, 1) + DQ(0, -1, 1)) + (DQ(1, 0, 1) + DQ(-1, 0, 1));
+	vz = (((cz + ez) + DQ(0, 0, 1)) + P.fz * half) / rho;
+	const R cx = (DQ(1, 1, 1) + DQ(1, -1, 1)) + (DQ(1, 1, -1) + DQ(1, -1, -1));
+	const R ex = (DQ(1, 0, 1) + DQ(1, 0, -1)) + (DQ(1, 1, 0) + DQ(1, -1, 0));
+	vx = (((cx + ex) + DQ(1, 0, 0)) + P.fx * half) / rho;
+	const R cy = (DQ(1, 1, 1) + DQ(1, 1, -1)) + (DQ(-1, 1, 1) + DQ(-1, 1, -1));
+	const R ey = (DQ(1, 1, 0) + DQ(-1, 1, 0)) + (DQ(0, 1, 1) + DQ(0, 1, -1));
+	vy = (((cy + ey) + DQ(0, 1, 0)) + P.fy * half) / rho;
+#undef SQ
+#undef DQ
+}
+
+// d2q9/common.h:16-36
+template <typename R>
+LBMX_D void density_velocity(const R (&f)[9], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
+{
+	using L = D2Q9;
+#define F2(a, b) f[L::find(a, b)]
+	const R half = R(0.5);
+	rho = F2(0, 0) + (((F2(1, 0) + F2(-1, 0)) + (F2(0, -1) + F2(0, 1))) + ((F2(1, 1) + F2(-1, -1)) + (F2(-1, 1) + F2(1, -1))));
+	vx = (((F2(1, 0) - F2(-1, 0)) + ((F2(1, -1) - F2(-1, 1)) + (F2(1, 1) - F2(-1, -1)))) + half * P.fx) / rho;
+	vy = (((F2(0, 1) - F2(0, -1)) + ((F2(-1, 1) - F2(1, -1)) + (F2(1, 1) - F2(-1, -1)))) + half * P.fy) / rho;
+	vz = R(0);
+#undef F2
+}
+
+// Eq 6-8 / 9-11 / 12-14 (col_cum.h:52-148): (f-, f0, f+) -> (k0, k1, k2) along one axis
+template <typename R>
+LBMX_D void to_central(R& lo, R& mid, R& hi, R v)
+{
+	const R fm = lo, fz = mid, fp = hi;
+	const R k0 = (fp + fm) + fz;
+	lo = k0;
+	mid = (fp - fm) - v * k0;
+	hi = (fp + fm) - R(2) * v * (fp - fm) + v * v * k0;
+}
+
+// Eq G2015(88)-(96), col_cum.h:349-445: (k0, k1, k2) -> (f-, f0, f+) along one axis
+template <typename R>
+LBMX_D void from_central(R& lo, R& mid, R& hi, R v)
+{
+	const R k0 = lo, k1 = mid, k2 = hi;
+	const R one = R(1), two = R(2), half = R(0.5);
+	mid = k0 * (one - v * v) - two * v * k1 - k2;
+	lo = (k0 * (v * v - v) + k1 * (two * v - one) + k2) * half;
+	hi = (k0 * (v * v + v) + k1 * (two * v + one) + k2) * half;
+}
+
+// d3q27/col_cum.h:14-485, default build (omega2..omega10 = 1, A = B = 0, no velocity-derivative terms), evaluated the way the
+// reference evaluates it: all 27 central moments, and the third-order cumulants keep the rounding residue that
+// (-a-b)/2 + (a-b)/2 + b leaves behind (col_cum.h:278-285) -- dropping it changes single bits, and a single bit is enough for two
+// fp32 runs to drift apart like two different roundings.  Only terms that are exactly +-0 for finite inputs are left out:
+// (1 - omega_n) * C with omega_n = 1, and every product with A, B or a velocity derivative.
+template <typename R>
+LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R one = R(1), two = R(2), four = R(4), half = R(0.5), third = R(1.0 / 3.0);
+	R m[3][3][3];  // index 0,1,2 = velocity sign -,0,+ before an axis is transformed, moment order 0,1,2 after
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++)
+#pragma unroll
+			for (int c = 0; c < 3; c++)
+				m[a][b][c] = f[L::find(a - 1, b - 1, c - 1)];
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++)
+			to_central(m[a][b][0], m[a][b][1], m[a][b][2], vz);
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int c = 0; c < 3; c++)
+			to_central(m[a][0][c], m[a][1][c], m[a][2][c], vy);
+#pragma unroll
+	for (int b = 0; b < 3; b++)
+#pragma unroll
+		for (int c = 0; c < 3; c++)
+			to_central(m[0][b][c], m[1][b][c], m[2][b][c], vx);
+
+	const R omega1 = one / (R(3) * P.nu + half);
+	const R keep = one - omega1;
+	R S[3][3][3];
+	S[0][0][0] = m[0][0][0];
+	S[1][0][0] = -m[1][0][0];  // col_cum.h:341-345
+	S[0][1][0] = -m[0][1][0];
+	S[0][0][1] = -m[0][0][1];
+	S[1][1][0] = keep * m[1][1][0];
+	S[1][0][1] = keep * m[1][0][1];
+	S[0][1][1] = keep * m[0][1][1];
+	const R r33 = keep * (m[2][0][0] - m[0][2][0]), r34 = keep * (m[2][0][0] - m[0][0][2]), r35 = m[0][0][0];
+	S[2][0][0] = third * (r33 + r34 + r35);
+	S[0][2][0] = third * (-two * r33 + r34 + r35);
+	S[0][0][2] = third * (r33 - two * r34 + r35);
+	// Eq 36-41 with omega3 = omega4 = 1 (x * 1 is exact)
+	S[1][2][0] = (-m[1][0][2] - m[1][2][0]) * half + (m[1][0][2] - m[1][2][0]) * half + m[1][2][0];
+	S[1][0][2] = (-m[1][0][2] - m[1][2][0]) * half + (-m[1][0][2] + m[1][2][0]) * half + m[1][0][2];
+	S[2][1][0] = (-m[0][1][2] - m[2][1][0]) * half + (m[0][1][2] - m[2][1][0]) * half + m[2][1][0];
+	S[0][1][2] = (-m[0][1][2] - m[2][1][0]) * half + (-m[0][1][2] + m[2][1][0]) * half + m[0][1][2];
+	S[0][2][1] = (-m[0][2][1] - m[2][0][1]) * half + (-m[0][2][1] + m[2][0][1]) * half + m[0][2][1];
+	S[2][0][1] = (-m[0][2][1] - m[2][0][1]) * half + (m[0][2][1] - m[2][0][1]) * half + m[2][0][1];
+	// Eq G2015(81)-(84), col_cum.h:312-338; the post-collision cumulants of order >= 4 and Cs_111 are +-0
+#define s(a, b, c) S[a][b][c]
+	S[2][1][1] = (s(2, 0, 0) * s(0, 1, 1) + two * s(1, 0, 1) * s(1, 1, 0)) / rho;
+	S[1][2][1] = (s(0, 2, 0) * s(1, 0, 1) + two * s(1, 1, 0) * s(0, 1, 1)) / rho;
+	S[1][1][2] = (s(0, 0, 2) * s(1, 1, 0) + two * s(0, 1, 1) * s(1, 0, 1)) / rho;
+	S[2][2][0] = (s(0, 2, 0) * s(2, 0, 0) + two * s(1, 1, 0) * s(1, 1, 0)) / rho;
+	S[0][2][2] = (s(0, 0, 2) * s(0, 2, 0) + two * s(0, 1, 1) * s(0, 1, 1)) / rho;
+	S[2][0][2] = (s(2, 0, 0) * s(0, 0, 2) + two * s(1, 0, 1) * s(1, 0, 1)) / rho;
+	S[1][2][2] = (s(0, 2, 0) * s(1, 0, 2) + s(0, 0, 2) * s(1, 2, 0) + two * (s(1, 1, 0) * s(0, 1, 2) + s(1, 0, 1) * s(0, 2, 1))) / rho;
+	S[2][1][2] = (s(0, 0, 2) * s(2, 1, 0) + s(2, 0, 0) * s(0, 1, 2) + two * (s(0, 1, 1) * s(2, 0, 1) + s(1, 1, 0) * s(1, 0, 2))) / rho;
+	S[2][2][1] = (s(2, 0, 0) * s(0, 2, 1) + s(0, 2, 0) * s(2, 0, 1) + two * (s(1, 0, 1) * s(1, 2, 0) + s(0, 1, 1) * s(2, 1, 0))) / rho;
+	S[1][1][1] = R(0);
+	S[2][2][2] = (s(2, 0, 0) * s(0, 2, 2) + s(0, 2, 0) * s(2, 0, 2) + s(0, 0, 2) * s(2, 2, 0)
+				  + four * (s(0, 1, 1) * s(2, 1, 1) + s(1, 0, 1) * s(1, 2, 1) + s(1, 1, 0) * s(1, 1, 2))
+				  + two * (s(1, 2, 0) * s(1, 0, 2) + s(2, 1, 0) * s(0, 1, 2) + s(2, 0, 1) * s(0, 2, 1)))
+					 / rho
+			   - (R(16) * s(1, 1, 0) * s(1, 0, 1) * s(0, 1, 1)
+				  + four * (s(1, 0, 1) * s(1, 0, 1) * s(0, 2, 0) + s(0, 1, 1) * s(0, 1, 1) * s(2, 0, 0) + s(1, 1, 0) * s(1, 1, 0) * s(0, 0, 2))
+				  + two * s(2, 0, 0) * s(0, 2, 0) * s(0, 0, 2))
+					 / rho / rho;
+#undef s
+#pragma unroll
+	for (int b = 0; b < 3; b++)
+#pragma unroll
+		for (int c = 0; c < 3; c++)
+			from_central(S[0][b][c], S[1][b][c], S[2][b][c], vx);
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int c = 0; c < 3; c++)
+			from_central(S[a][0][c], S[a][1][c], S[a][2][c], vy);
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++)
+			from_central(S[a][b][0], S[a][b][1], S[a][b][2], vz);
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++)
+#pragma unroll
+			for (int c = 0; c < 3; c++)
+				f[L::find(a - 1, b - 1, c - 1)] = S[a][b][c];
+}
+
+// source factor 3 ((c-u).F), col_srt.h:25-51 / col_bgk.h:62-88
+template <typename R>
+LBMX_D R force_projection(int cx, int cy, int cz, R vx, R vy, R vz, const Phys<R>& P)
+{
+	const R one = R(1);
+	const R tx = cx < 0 ? (-vx - one) * P.fx : (cx > 0 ? (-vx + one) * P.fx : -vx * P.fx);
+	const R ty = cy < 0 ? (-vy - one) * P.fy : (cy > 0 ? (-vy + one) * P.fy : -vy * P.fy);
+	const R tz = cz < 0 ? (-vz - one) * P.fz : (cz > 0 ? (-vz + one) * P.fz : -vz * P.fz);
+	return R(3) * (tx + ty + tz);
+}
+
+// col_srt.h:16-108 -- feq[] supplied by the caller (equilibrium() in collide.cuh is already in the reference's association)
+template <typename R>
+LBMX_D void collide_srt(R (&f)[27], const R (&feq)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R one = R(1), half = R(0.5);
+	const R tau = R(3) * P.nu + half;
+	const R iRho = one / (rho == R(0) ? one : rho);
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		const R S = force_projection(L::cx(q), L::cy(q), L::cz(q), vx, vy, vz, P) * iRho;
+		f[q] += (feq[q] - f[q]) / tau + (one - half / tau) * S * feq[q];
+	});
+}
+
+// col_bgk.h:16-145 (no Galilean correction)
+template <typename R>
+LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R one = R(1), half = R(0.5), third = R(1.0 / 3.0);
+	const R omega1 = one / (R(3) * P.nu + half);
+	const R v[3] = {vx, vy, vz};
+	R g[3][3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R z = third - one + v[a] * v[a];
+		const R p = -half * (z + one + v[a]);
+		g[a][1] = z;
+		g[a][2] = p;
+		g[a][0] = p + v[a];
+	}
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		const R S = force_projection(L::cx(q), L::cy(q), L::cz(q), vx, vy, vz, P) / rho;
+		const R feq = -rho * g[0][L::cx(q) + 1] * g[1][L::cy(q) + 1] * g[2][L::cz(q) + 1];
+		f[q] += (feq - f[q]) * omega1 + (one - half * omega1) * S * feq;
+	});
+}
+
+// col_mrt.h:13-141 ("MRT_LES")
+template <typename R>
+LBMX_D void collide_mrt(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R two = R(2), three = R(3), third = R(1.0 / 3.0);
+	// running sums in lexicographic (x,y,z) order over the signs -,0,+ (col_mrt.h:18-31)
+	R Pxx = 0, Pyy = 0, Pzz = 0, Pxy = 0, Pxz = 0, Pyz = 0;
+	static_for<27>([&](auto ic) {
+		constexpr int i = ic;
+		constexpr int a = i / 9 - 1, b = (i / 3) % 3 - 1, c = i % 3 - 1;
+		const R v = f[L::find(a, b, c)];
+		if constexpr (a != 0)
+			Pxx = Pxx + v;
+		if constexpr (b != 0)
+			Pyy = Pyy + v;
+		if constexpr (c != 0)
+			Pzz = Pzz + v;
+		if constexpr (a * b > 0)
+			Pxy = Pxy + v;
+		if constexpr (a * b < 0)
+			Pxy = Pxy - v;
+		if constexpr (a * c > 0)
+			Pxz = Pxz + v;
+		if constexpr (a * c < 0)
+			Pxz = Pxz - v;
+		if constexpr (b * c > 0)
+			Pyz = Pyz + v;
+		if constexpr (b * c < 0)
+			Pyz = Pyz - v;
+	});
+	const R Nxx = Pxx - rho * (third + vx * vx);
+	const R Nyy = Pyy - rho * (third + vy * vy);
+	const R Nzz = Pzz - rho * (third + vz * vz);
+	const R Nxz = Pxz - rho * vx * vz;
+	const R Nxy = Pxy - rho * vx * vy;
+	const R Nyz = Pyz - rho * vy * vz;
+	const R Qn = two * (Nxx * Nxx + Nyy * Nyy + Nzz * Nzz + two * (Nxy * Nxy + Nxz * Nxz + Nyz * Nyz));
+	const R tau = three * P.nu + R(0.5);
+	const R Csm = R(0.0342);
+	// the reference's unqualified sqrt() is ::sqrt(double) in the host build this mode is pinned to, also for dreal = float:
+	// the rate is evaluated in double and rounded once (col_mrt.h:63-66)
+	const double inner = (double) (tau * tau) + (double) (two * Csm * three * three) * ::sqrt((double) Qn) / (double) rho;
+	const R omega = (R) ((double) two / (::sqrt(inner) + (double) tau));
+	Pxx -= omega * Nxx;
+	Pyy -= omega * Nyy;
+	Pzz -= omega * Nzz;
+	Pxy -= omega * Nxy;
+	Pxz -= omega * Nxz;
+	Pyz -= omega * Nyz;
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int a = L::cx(q), b = L::cy(q), c = L::cz(q);
+		constexpr int n = (a != 0) + (b != 0) + (c != 0);
+		constexpr R w = n == 0 ? R(8.0 / 27.0) : n == 1 ? R(2.0 / 27.0) : n == 2 ? R(1.0 / 54.0) : R(1.0 / 216.0);
+		f[q] = w
+			 * (rho * (R(2.5) - R(1.5) * R(n) + three * (vx * R(a) + vy * R(b) + vz * R(c)))
+				+ R(4.5) * (Pxx * R(a * a) + Pyy * R(b * b) + Pzz * R(c * c) + two * (Pxy * R(a * b) + Pxz * R(a * c) + Pyz * R(b * c))) - R(1.5) * (Pxx + Pyy + Pzz));
+	});
+}
+
+// d2q9/col_srt.h:16-44
+template <typename R>
+LBMX_D void collide_srt(R (&f)[9], const R (&feq)[9], const Phys<R>& P, R vx, R vy)
+{
+	using L = D2Q9;
+	const R one = R(1), half = R(0.5), three = R(3), four = R(4), nine = R(9), n36 = R(36);
+	const R tau = three * P.nu + half;
+	const R fx = P.fx, fy = P.fy;
+	const R pre = one - half / tau;
+	R F[9];
+	F[L::find(0, 0)] = pre * four / nine * (three * (-vx * fx - vy * fy));
+	F[L::find(1, 0)] = pre / nine * (three * ((one - vx) * fx - vy * fy) + nine * vx * fx);
+	F[L::find(-1, 0)] = pre / nine * (three * ((-one - vx) * fx - vy * fy) + nine * vx * fx);
+	F[L::find(0, 1)] = pre / nine * (three * (-vx * fx + (one - vy) * fy) + nine * vy * fy);
+	F[L::find(0, -1)] = pre / nine * (three * (-vx * fx + (-one - vy) * fy) + nine * vy * fy);
+	F[L::find(1, 1)] = pre / n36 * (three * ((one - vx) * fx + (one - vy) * fy) + nine * (vx + vy) * (fx + fy));
+	F[L::find(-1, -1)] = pre / n36 * (three * ((-one - vx) * fx + (-one - vy) * fy) + nine * (vx + vy) * (fx + fy));
+	F[L::find(1, -1)] = pre / n36 * (three * ((one - vx) * fx + (-one - vy) * fy) + nine * (vx - vy) * (fx - fy));
+	F[L::find(-1, 1)] = pre / n36 * (three * ((-one - vx) * fx + (one - vy) * fy) + nine * (vx - vy) * (fx - fy));
+	static_for<9>([&](auto qc) {
+		constexpr int q = qc;
+		f[q] += (feq[q] - f[q]) / tau + F[q];
+	});
+}
+
+// d2q9/col_clbm.h:13-89
+template <typename R>
+LBMX_D void collide_clbm(R (&f)[9], const Phys<R>& P, R rho, R vx, R vy)
+{
+	using L = D2Q9;
+	const R tau = R(3) * P.nu + R(0.5);
+	const R fx = P.fx, fy = P.fy;
+	const R zz = f[L::find(0, 0)], pz = f[L::find(1, 0)], mz = f[L::find(-1, 0)], zp = f[L::find(0, 1)], zm = f[L::find(0, -1)];
+	const R pp = f[L::find(1, 1)], mm = f[L::find(-1, -1)], pm = f[L::find(1, -1)], mp = f[L::find(-1, 1)];
+	const R c2 = 2, c3 = 3, c4 = 4, c6 = 6, c8 = 8, c9 = 9, c36 = 36, q25 = R(.25), h5 = R(.5);
+	const R Pm = R(1.) / R(12.) * (rho * (vx * vx + vy * vy) - pz - zp - zm - mz - c2 * (pm + mm + pp + mp - R(1.) / R(3.) * rho) - (fx * vx + fy * vy));
+	const R NE = q25 / tau * (zp + zm - pz - mz + rho * (vx * vx - vy * vy) - (fx * vx - fy * vy));
+	const R V = q25 / tau * ((pp + mm - mp - pm) - vx * vy * rho + h5 * (fx * vy + fy * vx));
+	const R kxxyy = (pz + pp + mp + pm + mm + mz - vx * vx * rho + c2 * NE + c6 * Pm) * (zp + pp + mp + zm + pm + mm - vy * vy * rho - c2 * NE + c6 * Pm);
+	const R UP = (-(q25 * (pm + mm - pp - mp - c2 * vx * vx * vy * rho + vy * (rho - zp - zm - zz) - h5 * (-vx * vx) * fy + fx * vx * vy)
+					- vy * h5 * (-c3 * Pm - NE) + vx * ((pp - mp - pm + mm) * h5 - c2 * V)));
+	const R RIGHT = (-(q25 * (mm + mp - pm - pp - c2 * vy * vy * vx * rho + vx * (rho - zz - mz - pz) - h5 * (-vy * vy) * fx + fy * vy * vx)
+					   - vx * h5 * (-c3 * Pm + NE) + vy * ((pp + mm - pm - mp) * h5 - c2 * V)));
+	const R NP = (q25
+				  * (kxxyy - pp - mp - pm - mm - c8 * Pm + c2 * (vx * (pp - mp + pm - mm - c4 * RIGHT) + vy * (pp + mp - pm - mm - c4 * UP))
+					 + c4 * vx * vy * (-pp + mp + pm - mm + c4 * V) + vx * vx * (-zp - pp - mp - zm - pm - mm + c2 * NE - c6 * Pm)
+					 + vy * vy * ((-pz - pp - mp - pm - mm - mz - c2 * NE - c6 * Pm) + c3 * vx * vx * rho) - (fx * vx * vy * vy + fy * vy * vx * vx)));
+	f[L::find(-1, 1)] += c2 * Pm + NP + V - UP + RIGHT;
+	f[L::find(-1, 0)] += -Pm - c2 * NP + NE - c2 * RIGHT;
+	f[L::find(-1, -1)] += c2 * Pm + NP - V + UP + RIGHT;
+	f[L::find(0, -1)] += -Pm - c2 * NP - NE - c2 * UP;
+	f[L::find(1, -1)] += c2 * Pm + NP + V + UP - RIGHT;
+	f[L::find(1, 0)] += -Pm - c2 * NP + NE + c2 * RIGHT;
+	f[L::find(1, 1)] += c2 * Pm + NP - V - UP - RIGHT;
+	f[L::find(0, 1)] += -Pm - c2 * NP - NE + c2 * UP;
+	f[L::find(0, 0)] += (c4 * (-Pm + NP));
+	const R m1 = fx, m2 = fy;
+	const R m3 = c6 * (fx * vx + fy * vy);
+	const R m4 = c2 * (fx * vx - fy * vy);
+	const R m5 = fx * vy + fy * vx;
+	const R m6 = (c2 - c3 * vx * vx) * fy - c6 * fx * vx * vy;
+	const R m7 = (c2 - c3 * vy * vy) * fx - c6 * fy * vx * vy;
+	const R m8 = c6 * ((c3 * vy * vy - c2) * fx * vx + (c3 * vx * vx - c2) * fy * vy);
+	f[L::find(0, 0)] += (-m3 + m8) / c9;
+	f[L::find(1, 0)] += (c6 * m1 - m3 + c9 * m4 + c6 * m7 - c2 * m8) / c36;
+	f[L::find(0, 1)] += (c6 * m2 - m3 - c9 * m4 + c6 * m6 - c2 * m8) / c36;
+	f[L::find(-1, 0)] += (-c6 * m1 - m3 + c9 * m4 - c6 * m7 - c2 * m8) / c36;
+	f[L::find(0, -1)] += (-c6 * m2 - m3 - c9 * m4 - c6 * m6 - c2 * m8) / c36;
+	f[L::find(1, 1)] += (c6 * m1 + c6 * m2 + c2 * m3 + c9 * m5 - c3 * m6 - c3 * m7 + m8) / c36;
+	f[L::find(-1, 1)] += (-c6 * m1 + c6 * m2 + c2 * m3 - c9 * m5 - c3 * m6 + c3 * m7 + m8) / c36;
+	f[L::find(-1, -1)] += (-c6 * m1 - c6 * m2 + c2 * m3 + c9 * m5 + c3 * m6 + c3 * m7 + m8) / c36;
+	f[L::find(1, -1)] += (c6 * m1 - c6 * m2 + c2 * m3 - c9 * m5 + c3 * m6 - c3 * m7 + m8) / c36;
+}
+
+}  // namespace strict
+}  // namespace lbmx

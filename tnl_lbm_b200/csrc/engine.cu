@@ -171,8 +171,6 @@ struct lbmx_engine
 	int* d_dirs = nullptr;	// [2][9]: to_right, to_left
 	int n_hdirs = 0;
 	int32_t h_dirs[2][9];
-	void* sendbuf[2] = {nullptr, nullptr};	// packed halo planes (to right, to left)
-	void* recvbuf[2] = {nullptr, nullptr};	// (from left, from right)
 
 	std::vector<int64_t> plane_start;  // boundary-list offsets per local x plane, size X+1
 	int64_t nb = 0, n_bulk = 0;
@@ -220,7 +218,6 @@ KParams<R> make_params(const lbmx_engine* e)
 	p.ydiv_mul = e->ydiv_mul;
 	p.ydiv_shift = e->ydiv_shift;
 	p.x_begin = 0;
-	p.x_end = (int) e->X;
 	p.nb_begin = 0;
 	p.nb_end = (int) e->nb;
 	p.wrap = e->ox == 0 ? 1 : 0;
@@ -231,7 +228,6 @@ KParams<R> make_params(const lbmx_engine* e)
 	p.out_mode = OUT_NONE;
 	p.stat_counter = e->prm.stat_counter;
 	const bool vm = e->d.macro == LBMX_MACRO_VOID;
-	p.void_macro = vm;
 	// MACRO_Void::copyQuantities is empty (d3q27/macro.h:174-188): the KernelStruct keeps lbmViscosity = 1, zero force
 	p.phys.nu = vm ? R(1) : (R) e->prm.lbmViscosity;
 	p.phys.omega1 = R(1) / (R(3) * p.phys.nu + R(0.5));	 // IEEE division in precision R: the same bits the kernels used to compute per cell
@@ -253,7 +249,6 @@ int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, 
 	if (xe <= xb)
 		return LBMX_OK;
 	p.x_begin = xb;
-	p.x_end = xe;
 	p.nb_begin = (int) e->plane_start[xb];
 	p.nb_end = (int) e->plane_start[xe];
 	const int per_cta = BLOCK * K.cpt[p.stream];
@@ -381,6 +376,23 @@ int step_dispatch(lbmx_engine* e, int64_t nsteps)
 bool pick_kernels(lbmx_engine* e)
 {
 	const lbmx_desc& d = e->d;
+	if (d.flags & LBMX_FLAG_STRICT_ARITH) {	 // parity arithmetic (lattices checked by the caller)
+		if (d.lattice == LBMX_D3Q27) {
+			switch (d.coll) {
+				case LBMX_COLL_CUM: return e->f64() ? get_kernels_d3q27_cum_strict(e->kd) : get_kernels_d3q27_cum_strict(e->kf);
+				case LBMX_COLL_SRT: return e->f64() ? get_kernels_d3q27_srt_strict(e->kd) : get_kernels_d3q27_srt_strict(e->kf);
+				case LBMX_COLL_BGK: return e->f64() ? get_kernels_d3q27_bgk_strict(e->kd) : get_kernels_d3q27_bgk_strict(e->kf);
+				case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt_strict(e->kd) : get_kernels_d3q27_mrt_strict(e->kf);
+			}
+		}
+		else if (d.lattice == LBMX_D2Q9) {
+			if (d.coll == LBMX_COLL_SRT)
+				return e->f64() ? get_kernels_d2q9_srt_strict(e->kd) : get_kernels_d2q9_srt_strict(e->kf);
+			if (d.coll == LBMX_COLL_CLBM)
+				return e->f64() ? get_kernels_d2q9_clbm_strict(e->kd) : get_kernels_d2q9_clbm_strict(e->kf);
+		}
+		return false;
+	}
 	if (d.lattice == LBMX_D3Q27) {
 		switch (d.coll) {
 			case LBMX_COLL_CUM: return e->f64() ? get_kernels_d3q27_cum(e->kd) : get_kernels_d3q27_cum(e->kf);
@@ -550,6 +562,8 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: D2Q9 has only the polynomial equilibrium (d2q9/eq.h)");
 	if (d.nranks < 1 || d.rank < 0 || d.rank >= d.nranks)
 		return fail(LBMX_ERR_ARG, "lbmx_create: rank / nranks");
+	if ((d.flags & LBMX_FLAG_STRICT_ARITH) && d.lattice == LBMX_D3Q19)
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: LBMX_FLAG_STRICT_ARITH follows the reference's arithmetic, and the reference has no D3Q19");
 
 	lbmx_engine* e = new lbmx_engine();
 	e->d = d;
@@ -656,7 +670,7 @@ int lbmx_destroy(lbmx_engine* e)
 	cudaDeviceSynchronize();
 	if (e->comm && g_nccl.CommDestroy)
 		g_nccl.CommDestroy(e->comm);
-	for (void* p : {e->df[0], e->df[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs, e->sendbuf[0], e->sendbuf[1], e->recvbuf[0], e->recvbuf[1]})
+	for (void* p : {e->df[0], e->df[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs})
 		if (p)
 			cudaFree(p);
 	for (cudaEvent_t ev : {e->ev_edge, e->ev_comm, e->ev_main, e->ev_t0, e->ev_t1})

@@ -55,11 +55,11 @@ struct KParams
 	int X, Y, Z, ox;   // local slab size (no ghosts), ghost planes per side
 	int YZ;
 	unsigned ydiv_mul, ydiv_shift;	// floor(n / Y) = umulhi(n, ydiv_mul) >> ydiv_shift for 0 <= n < 2^31 (ydiv_mul == 0: plain division)
-	int x_begin, x_end; // planes handled by this launch, local coordinates in [0, X)
+	int x_begin;	   // first plane handled by this launch (local coordinate in [0, X)); the grid's y extent is the plane count
 	int nb_begin, nb_end; // boundary-list range handled by this launch
 	int wrap;		   // 1: the reference's nproc==1 rule (GEO_PERIODIC cells wrap), 0: ghost-plane rule
 	int profile_sy;
-	int eq, inflow, stream, out_mode, stat_counter, void_macro;
+	int eq, inflow, stream, out_mode, stat_counter;
 	Phys<R> phys;
 	R in_vx, in_vy, in_vz;
 };
@@ -269,7 +269,8 @@ constexpr int bulk_cpt()
 #endif
 }
 
-template <typename L, int KIND, typename R, int MODE>
+// ARITH (= LBMX_STRICT of the object file) only makes the kernel symbols of the fast and the parity-arithmetic builds distinct
+template <typename L, int KIND, typename R, int MODE, int ARITH = LBMX_STRICT>
 __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>()) k_bulk(const KParams<R> p)
 {
 	constexpr int CPT = bulk_cpt<L, R, MODE>();
@@ -421,7 +422,7 @@ LBMX_D void mirror_pops(R (&f)[L::Q])
 	});
 }
 
-template <typename L, int KIND, typename R>
+template <typename L, int KIND, typename R, int ARITH = LBMX_STRICT>
 __global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
 {
 	const int i = p.nb_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
 // initialisation / service kernels
 // =====================================================================================================================
 // LBM_BLOCK::setEquilibrium (lbm_block.hpp:219-250): every storage cell including ghosts; uniform state or per-cell fields
-template <typename L, typename R>
+template <typename L, typename R, int ARITH = LBMX_STRICT>
 __global__ void k_set_equilibrium(R* df, long long XYZ, long long n_cells, long long cell0, int eq, const double* rho, const double* vx, const double* vy,
 								  const double* vz, double crho, double cvx, double cvy, double cvz)
 {
@@ -585,7 +586,7 @@ __global__ void k_set_equilibrium(R* df, long long XYZ, long long n_cells, long 
 }
 
 // LBM_BLOCK::computeInitialMacro (lbm_block.hpp:252-277): local read, force zeroed
-template <typename L, typename R>
+template <typename L, typename R, int ARITH = LBMX_STRICT>
 __global__ void k_initial_macro(const KParams<R> p)
 {
 	const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -662,6 +663,19 @@ bool get_kernels_d3q27_bgk(StepKernels<float>&);
 bool get_kernels_d3q27_bgk(StepKernels<double>&);
 bool get_kernels_d3q27_mrt(StepKernels<float>&);
 bool get_kernels_d3q27_mrt(StepKernels<double>&);
+// the same families in parity arithmetic (collide_strict.cuh, -fmad=false)
+bool get_kernels_d3q27_cum_strict(StepKernels<float>&);
+bool get_kernels_d3q27_cum_strict(StepKernels<double>&);
+bool get_kernels_d3q27_srt_strict(StepKernels<float>&);
+bool get_kernels_d3q27_srt_strict(StepKernels<double>&);
+bool get_kernels_d3q27_bgk_strict(StepKernels<float>&);
+bool get_kernels_d3q27_bgk_strict(StepKernels<double>&);
+bool get_kernels_d3q27_mrt_strict(StepKernels<float>&);
+bool get_kernels_d3q27_mrt_strict(StepKernels<double>&);
+bool get_kernels_d2q9_srt_strict(StepKernels<float>&);
+bool get_kernels_d2q9_srt_strict(StepKernels<double>&);
+bool get_kernels_d2q9_clbm_strict(StepKernels<float>&);
+bool get_kernels_d2q9_clbm_strict(StepKernels<double>&);
 bool get_kernels_d3q19_srt(StepKernels<float>&);
 bool get_kernels_d3q19_srt(StepKernels<double>&);
 bool get_kernels_d3q19_mrt(StepKernels<float>&);

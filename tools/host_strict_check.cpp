@@ -1,0 +1,60 @@
+// Host-side check of collide_strict.cuh against the CPU restatement (test tool; g++ -ffp-contract=off).
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+using std::sqrt;
+#define LBMX_STRICT 1
+#include "../tnl_lbm_b200/csrc/collide.cuh"
+#include "../oracle/oracle_api.h"
+using namespace lbmx;
+template <typename R, int KIND>
+int run(int coll, int eq, int prec)
+{
+	const int N = 6;
+	oracle_desc d{};
+	d.lattice = ORC_D3Q27; d.coll = coll; d.eq = eq; d.streaming = ORC_STREAM_AB; d.macro = ORC_MACRO_DEFAULT; d.inflow = ORC_INFLOW_CONST;
+	d.precision = prec; d.nproc = 1; d.X = d.Y = d.Z = N; d.ox = 0;
+	oracle_params p{};
+	p.lbmViscosity = 1e-3; p.fx = 1e-6; p.fy = -2e-6; p.fz = 3e-6;
+	const size_t XYZ = N * N * N;
+	std::vector<R> a(27 * XYZ), b(27 * XYZ), mac(4 * XYZ), mine(27 * XYZ);
+	std::vector<int16_t> map(XYZ, 7);  // GEO_PERIODIC
+	srand(5);
+	for (int q = 0; q < 27; q++) {
+		int n = (D3Q27::cx(q) != 0) + (D3Q27::cy(q) != 0) + (D3Q27::cz(q) != 0);
+		double w = n == 0 ? 8. / 27 : n == 1 ? 2. / 27 : n == 2 ? 1. / 54 : 1. / 216;
+		for (size_t i = 0; i < XYZ; i++) a[q * XYZ + i] = (R) (w * (1 + 0.05 * (rand() / (double) RAND_MAX - 0.5)));
+	}
+	Phys<R> P; P.nu = (R) p.lbmViscosity; P.omega1 = R(1) / (R(3) * P.nu + R(0.5)); P.fx = (R) p.fx; P.fy = (R) p.fy; P.fz = (R) p.fz;
+	for (int x = 0; x < N; x++) for (int z = 0; z < N; z++) for (int y = 0; y < N; y++) {
+		R f[27];
+		for (int q = 0; q < 27; q++) {
+			int xs = (x - D3Q27::cx(q) + N) % N, ys = (y - D3Q27::cy(q) + N) % N, zs = (z - D3Q27::cz(q) + N) % N;
+			f[q] = a[q * XYZ + ((size_t) xs * N + zs) * N + ys];
+		}
+		R rho, vx, vy, vz;
+		density_velocity(f, P, rho, vx, vy, vz);
+		collide<KIND>(f, P, eq, rho, vx, vy, vz);
+		for (int q = 0; q < 27; q++) mine[q * XYZ + ((size_t) x * N + z) * N + y] = f[q];
+	}
+	oracle_step(&d, &p, a.data(), b.data(), mac.data(), map.data(), 0, 1, 1);
+	size_t nd = 0; double mx = 0;
+	for (size_t i = 0; i < 27 * XYZ; i++) if (mine[i] != b[i]) { nd++; mx = std::fmax(mx, std::fabs((double) mine[i] - (double) b[i])); }
+	printf("coll %d eq %d prec %d: %zu of %zu differ, max abs %.3e\n", coll, eq, prec, nd, 27 * XYZ, mx);
+	return nd != 0;
+}
+int main()
+{
+	int r = 0;
+	r |= run<float, K_CUM>(ORC_COLL_CUM, ORC_EQ_INV_CUM, ORC_F32);
+	r |= run<double, K_CUM>(ORC_COLL_CUM, ORC_EQ_INV_CUM, ORC_F64);
+	r |= run<float, K_SRT>(ORC_COLL_SRT, ORC_EQ_STD, ORC_F32);
+	r |= run<float, K_BGK>(ORC_COLL_BGK, ORC_EQ_STD, ORC_F32);
+	r |= run<float, K_MRT>(ORC_COLL_MRT_LES, ORC_EQ_STD, ORC_F32);
+	return r;
+}

@@ -35,7 +35,7 @@ int main(int argc, char** argv)
 	k_set_equilibrium<KB_LAT, R><<<(unsigned) ((XYZ + 127) / 128), 128>>>(a, XYZ, XYZ, 0, 1, nullptr, nullptr, nullptr, nullptr, 1.0, 0.03, 0.01, -0.02);
 	CK(cudaMemcpy(b, a, sizeof(R) * KB_LAT::Q * XYZ, cudaMemcpyDeviceToDevice));
 	KParams<R> p{};
-	p.cur = a; p.out = b; p.macro = mac; p.map = map; p.XYZ = XYZ; p.X = p.Y = S; p.Z = SZ; p.ox = 0; p.YZ = S * SZ; p.x_begin = 0; p.x_end = S;
+	p.cur = a; p.out = b; p.macro = mac; p.map = map; p.XYZ = XYZ; p.X = p.Y = S; p.Z = SZ; p.ox = 0; p.YZ = S * SZ; p.x_begin = 0;
 	p.wrap = 1; p.eq = 1; p.out_mode = OUT_NONE; p.phys.nu = R(1e-3); p.phys.omega1 = R(1) / (R(3) * p.phys.nu + R(0.5));
 	{ unsigned L = 0; while ((1u << L) < (unsigned) S) L++; p.ydiv_mul = (unsigned) ((((unsigned long long) 1 << (31 + L)) + S - 1) / S); p.ydiv_shift = L - 1; }
 	auto set_bases = [&](bool aa) { for (int q = 0; q < KB_LAT::Q; q++) { p.rd[q] = p.cur + (size_t) q * XYZ; p.wr[q] = (aa ? p.cur : p.out) + (size_t) q * XYZ; } };
