@@ -3,7 +3,11 @@
 // Orifice channel: moment inflow on the left (GEO_INFLOW_LEFT), GEO_OUTFLOW_RIGHT, walls behind a GEO_NOTHING shell.
 //
 //   g++ -std=c++17 -Itnl_lbm_b200/host -Iinclude examples/channel3d.cpp -Ltnl_lbm_b200 -llbmx -o channel3d
-//   ./channel3d X Y Z steps out_prefix [AA]     -> out_prefix.map (int16) and out_prefix.macro (dreal), reference layout
+//   ./channel3d X Y Z steps out_prefix [f32] [halt=N] [dump]
+//        -> out_prefix.map (int16) and out_prefix.macro (dreal), reference layout
+//   halt=N : stop after N steps and save a checkpoint (results_channel3d/checkpoint.bp + flag.loadstate); the next invocation
+//            in the same directory resumes from it, exactly like a reference solver after a wall-time stop
+//   dump   : register cuts and write outputData() fields through the raw-dump writers (results_channel3d/output_*)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +28,13 @@ struct StateLocal : State<NSE>
 
 	real lbm_inflow_vx = 0;
 	double probed_mass = 0;
+	int halt_at = 0;  // stop the time loop after this many steps (stands in for the wall-time limit), 0 = never
+
+	void computeAfterLBMKernel() override
+	{
+		if (halt_at > 0 && nse.iterations + 1 >= halt_at)
+			nse.terminate = true;
+	}
 
 	void setupBoundaries() override
 	{
@@ -53,6 +64,18 @@ struct StateLocal : State<NSE>
 			block.data.inflow_vz = 0;
 		}
 	}
+	// the fields a writer asks for, by index (same protocol as the reference's solvers, e.g. sim_NSE/sim_1.cu:57-73)
+	bool outputData(const LBM_BLOCK<NSE>& block, int index, int dof, char* desc, idx x, idx y, idx z, real& value, int& dofs) override
+	{
+		int k = 0;
+		if (index == k++)
+			return this->vtk_helper("lbm_density", block.hmacro(MACRO::e_rho, x, y, z), 1, desc, value, dofs);
+		if (index == k++) {
+			const int c = dof == 0 ? MACRO::e_vx : (dof == 1 ? MACRO::e_vy : MACRO::e_vz);
+			return this->vtk_helper("velocity", block.hmacro(c, x, y, z), 3, desc, value, dofs);
+		}
+		return false;
+	}
 	void probe1() override
 	{
 		// total mass from the host copy of the density field (copied on this cadence by SimUpdate)
@@ -63,7 +86,7 @@ struct StateLocal : State<NSE>
 };
 
 template <typename TRAITS>
-int run(int X, int Y, int Z, int steps, const char* prefix)
+int run(int X, int Y, int Z, int steps, const char* prefix, int halt, bool dump)
 {
 	using COLL = D3Q27_CUM<TRAITS, D3Q27_EQ_INV_CUM<TRAITS>>;
 	using NSE = LBM_CONFIG<TRAITS, D3Q27_KernelStruct, NSE_Data_ConstInflow<TRAITS>, COLL, typename COLL::EQ, D3Q27_STREAMING<TRAITS>, D3Q27_BC_All,
@@ -82,10 +105,23 @@ int run(int X, int Y, int Z, int steps, const char* prefix)
 	if (! state.canCompute())
 		return 0;
 	state.lbm_inflow_vx = 0.04;
+	state.halt_at = halt;
 	state.nse.physFinalTime = (steps - 0.5) * lat.physDt;
 	state.cnt[PRINT].period = 10 * lat.physDt;
 	state.cnt[PROBE1].period = 5 * lat.physDt;
+	if (dump) {
+		state.cnt[VTK2D].period = 20 * lat.physDt;
+		state.cnt[VTK3D].period = 30 * lat.physDt;
+		state.cnt[VTK3DCUT].period = 30 * lat.physDt;
+		state.add2Dcut_X(X / 2, "cutsX/cut_X");
+		state.add2Dcut_Z(Z / 2, "cut_Z");
+		state.add3Dcut(X / 4, Y / 4, Z / 4, X / 2, Y / 2, Z / 2, 2, "box");
+	}
 	execute(state);
+	if (halt > 0) {	 // what core.h does when the wall time runs out (core.h:57-63)
+		state.copyAllToHost();
+		state.saveState();
+	}
 
 	auto& block = state.nse.blocks.front();
 	state.nse.copyMacroToHost();
@@ -102,13 +138,22 @@ int main(int argc, char** argv)
 {
 	TNLMPI_INIT mpi(argc, argv);
 	if (argc < 6) {
-		std::fprintf(stderr, "usage: %s X Y Z steps out_prefix [f32]\n", argv[0]);
+		std::fprintf(stderr, "usage: %s X Y Z steps out_prefix [f32] [halt=N] [dump]\n", argv[0]);
 		return 1;
 	}
-	const bool f32 = argc > 6 && std::strcmp(argv[6], "f32") == 0;
+	bool f32 = false, dump = false;
+	int halt = 0;
+	for (int i = 6; i < argc; i++) {
+		if (std::strcmp(argv[i], "f32") == 0)
+			f32 = true;
+		else if (std::strcmp(argv[i], "dump") == 0)
+			dump = true;
+		else if (std::strncmp(argv[i], "halt=", 5) == 0)
+			halt = atoi(argv[i] + 5);
+	}
 	try {
-		return f32 ? run<TraitsSP>(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5])
-				   : run<TraitsDP>(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
+		return f32 ? run<TraitsSP>(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], halt, dump)
+				   : run<TraitsDP>(atoi(argv[1]), atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5], halt, dump);
 	}
 	catch (const std::exception& e) {
 		std::fprintf(stderr, "error: %s\n", e.what());

@@ -3,7 +3,9 @@
 
 * examples/channel3d.cpp : this repository's solver in the reference's style; its result is compared with the CPU oracle.
 * sim_NSE/sim_1.cu, sim_2D/sim2d_1.cu : the reference's UNMODIFIED sources (compiled where /root/reference exists; the
-  binaries travel to the GPU box).  Their writers are out of scope, so the check is that they run to completion."""
+  binaries travel to the GPU box): they run to completion and their cuts land in the raw-dump writers.
+* checkpoint / restart through State::saveState / loadState (reference variable names, local-storage shapes) is bit-identical
+  to an uninterrupted run; the 3-D / cut writers keep the reference's (z, y, x) float ordering."""
 import os
 import re
 import subprocess
@@ -57,7 +59,7 @@ def test_channel3d_matches_oracle(prec):
     X, Y, Z, steps = 48, 20, 20, 60
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, "run")
-        r = subprocess.run([exe, str(X), str(Y), str(Z), str(steps), out] + (["f32"] if prec == "f32" else []), capture_output=True, text=True, timeout=300)
+        r = subprocess.run([exe, str(X), str(Y), str(Z), str(steps), out] + (["f32"] if prec == "f32" else []), capture_output=True, text=True, timeout=300, cwd=tmp)
         assert r.returncode == 0, r.stdout + r.stderr
         m = re.search(r"iterations=(\d+) mass=(\S+) lbmViscosity=(\S+) inflow_vx=(\S+)", r.stdout)
         assert m and int(m.group(1)) == steps, r.stdout
@@ -103,10 +105,144 @@ def test_unmodified_reference_solvers_run(exe_name, arg):
     exe = os.path.join(BIN, exe_name)
     if not os.path.exists(exe):
         pytest.skip(f"{exe_name} not built (needs /root/reference at build time)")
-    r = subprocess.run([exe, arg], capture_output=True, text=True, timeout=600)
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([exe, arg], capture_output=True, text=True, timeout=600, cwd=tmp)
+        dumps = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp) for f in fs if f.endswith(".txt")]
+        flags = [f for dp, _, fs in os.walk(tmp) for f in fs if f.startswith("flag.")]
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert len(dumps) > 10, "the solver's cuts did not reach the raw-dump writers"
+    assert "flag.finished" in flags or "flag.terminated" in flags
     assert "GLUPS=" in r.stdout
     assert "physFinalTime reached" in r.stdout or "terminate flag triggered" in r.stdout
     iters = [int(x) for x in re.findall(r"iter=(\d+)", r.stdout)]
     assert iters and iters[-1] > 1000
     print(exe_name, "last lines:", r.stdout.strip().splitlines()[-3:])
+
+
+def _read_dump(base):
+    """RawWriter output: <base>.txt = index (name dtype count dofs byte_offset), <base>.bin = payloads."""
+    raw = open(base + ".bin", "rb").read()
+    out, header = {}, None
+    for line in open(base + ".txt"):
+        t = line.split()
+        if line.startswith("#"):
+            header = {t[i]: [int(v) for v in t[i + 1:i + 4]] for i in (1, 5, 9)}
+        elif t[1] == "scalar":
+            out[t[0]] = float(t[2])
+        else:
+            out[t[0]] = np.frombuffer(raw, dtype=np.dtype(t[1]), count=int(t[2]), offset=int(t[4]))
+    return header, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe_name,halt", [("channel3d", 30), ("channel3d_aa", 31)])
+def test_checkpoint_restart_is_bit_identical(exe_name, halt):
+    """Stop after `halt` steps, saveState(), start again in the same results directory: loadState() restores map, DFs (ghost planes
+    and A-A parity included), macro, iteration and counters, and the run ends bit-identical to an uninterrupted one."""
+    exe = os.path.join(BIN, exe_name)
+    if not os.path.exists(exe):
+        pytest.skip(f"examples/bin/{exe_name} not built")
+    X, Y, Z, steps = 40, 16, 16, 60
+    args = [exe, str(X), str(Y), str(Z), str(steps)]
+    with tempfile.TemporaryDirectory() as t1, tempfile.TemporaryDirectory() as t2:
+        r = subprocess.run(args + [os.path.join(t1, "full")], capture_output=True, text=True, timeout=300, cwd=t1)
+        assert r.returncode == 0, r.stdout + r.stderr
+        full = np.fromfile(os.path.join(t1, "full.macro"), dtype=np.float64)
+        r = subprocess.run(args + [os.path.join(t2, "part"), f"halt={halt}"], capture_output=True, text=True, timeout=300, cwd=t2)
+        assert r.returncode == 0 and f"iterations={halt} " in r.stdout, r.stdout + r.stderr
+        ck = os.path.join(t2, "results_channel3d", "checkpoint.bp")
+        assert os.path.exists(os.path.join(t2, "results_channel3d", "flag.loadstate"))
+        attrs = dict(line.rstrip("\n").split("\t") for line in open(os.path.join(ck, "attributes.txt")))
+        assert int(attrs["LBM_iterations"]) == halt and int(attrs["LBM_total_blocks"]) == 1
+        variables = {t[0]: (t[1], int(t[2])) for t in (line.split() for line in open(os.path.join(ck, "variables.txt")))}
+        n = X * Y * Z
+        dfmax = 1 if exe_name.endswith("_aa") else 2
+        expect = {"LBM_map_block_0": ("int16", n), "LBM_macro_block_0": ("float64", 4 * n)}
+        expect.update({f"LBM_df_{k}_block_0": ("float64", 27 * n) for k in range(dfmax)})
+        assert variables == expect
+        assert os.path.getsize(os.path.join(ck, "LBM_df_0_block_0.bin")) == 27 * n * 8
+        r = subprocess.run(args + [os.path.join(t2, "resumed")], capture_output=True, text=True, timeout=300, cwd=t2)
+        assert r.returncode == 0 and "Loading data from checkpoint" in r.stdout and f"iterations={steps} " in r.stdout, r.stdout + r.stderr
+        resumed = np.fromfile(os.path.join(t2, "resumed.macro"), dtype=np.float64)
+        assert np.array_equal(np.fromfile(os.path.join(t2, "resumed.map"), dtype=np.int16), np.fromfile(os.path.join(t1, "full.map"), dtype=np.int16))
+    assert np.array_equal(full, resumed)
+
+
+@pytest.mark.gpu
+def test_raw_dump_writers_keep_reference_ordering():
+    """writeVTKs_3D / _3Dcut / _2D feed the solver's outputData() hook in the reference's (z, y, x) order with its variable names
+    (lbm_block.hpp:800-1110): "wall", scalar "<id>", vector "<id>X/Y/Z", "TIME"."""
+    exe = os.path.join(BIN, "channel3d")
+    if not os.path.exists(exe):
+        pytest.skip("examples/bin/channel3d not built")
+    X, Y, Z, steps = 40, 16, 16, 60
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([exe, str(X), str(Y), str(Z), str(steps), os.path.join(tmp, "run"), "dump"], capture_output=True, text=True, timeout=300, cwd=tmp)
+        assert r.returncode == 0, r.stdout + r.stderr
+        mac = np.fromfile(os.path.join(tmp, "run.macro"), dtype=np.float64).reshape(4, X, Z, Y)
+        cmap = np.fromfile(os.path.join(tmp, "run.map"), dtype=np.int16).reshape(X, Z, Y)
+        res = os.path.join(tmp, "results_channel3d")
+        h3, d3 = _read_dump(os.path.join(res, "output_3D.2"))  # cycles 0, 1, 2 at steps 0, 30, 60
+        hb, db = _read_dump(os.path.join(res, "output_3Dcut_box.2"))
+        hx, dx = _read_dump(os.path.join(res, "output_2D_cutsX", "cut_X.3"))  # steps 0, 20, 40, 60
+        hz, dz = _read_dump(os.path.join(res, "output_2D_cut_Z.3"))
+    zyx = lambda a: a.transpose(1, 2, 0)  # [x, z, y] -> [z, y, x]
+    assert h3["global"] == [X, Y, Z] and sorted(d3) == ["TIME", "lbm_density", "velocityX", "velocityY", "velocityZ", "wall"]
+    assert np.array_equal(d3["wall"].reshape(Z, Y, X), zyx(cmap).astype(np.int32))
+    assert np.array_equal(d3["lbm_density"].reshape(Z, Y, X), zyx(mac[0]).astype(np.float32))
+    for k, c in enumerate("XYZ"):
+        assert np.array_equal(d3["velocity" + c].reshape(Z, Y, X), zyx(mac[1 + k]).astype(np.float32))
+    assert d3["TIME"] > 0
+    # box [X/4, X/4 + X/2) x ... with stride 2
+    sl = lambda n: slice(n // 4, n // 4 + n // 2, 2)
+    assert hb["global"] == [X // 4, Y // 4, Z // 4]
+    assert np.array_equal(db["lbm_density"].reshape(Z // 4, Y // 4, X // 4), zyx(mac[0][sl(X), sl(Z), sl(Y)]).astype(np.float32))
+    assert hx["global"] == [1, Y, Z] and np.array_equal(dx["velocityX"].reshape(Z, Y), mac[1][X // 2].astype(np.float32))
+    assert hz["global"] == [X, Y, 1] and np.array_equal(dz["lbm_density"].reshape(Y, X), mac[0][:, Z // 2, :].T.astype(np.float32))
+
+
+def test_checkpoint_manager_round_trip_on_cpu():
+    """CheckpointManager alone (no GPU): attributes and raw variables written under the reference's naming scheme read back equal;
+    a wrong shape is refused."""
+    src = r'''
+#include "lbm3d/core.h"
+struct Blk { int id = 3; };
+int main(int, char** argv)
+{
+	const std::string dir = argv[1];
+	std::vector<double> a = {1.5, -2.25, 3.0e-300}, b(3);
+	std::vector<short> m = {0, 7, -1}, m2(3);
+	int it = 12345, it2 = 0;
+	float period = 0.125f, period2 = 0;
+	Blk blk;
+	CheckpointManager ck;
+	ck.start(dir, adios2::Mode::Write);
+	ck.saveLoadAttribute("LBM_iterations", it);
+	ck.saveLoadAttribute("State_counter_0_period", period);
+	ck.saveLoadVariable("LBM_df_0", blk, a);
+	ck.saveLoadLocalArray("LBM_map", 0, m);
+	ck.finalize();
+	ck.start(dir, adios2::Mode::Read);
+	ck.saveLoadAttribute("LBM_iterations", it2);
+	ck.saveLoadAttribute("State_counter_0_period", period2);
+	ck.saveLoadVariable("LBM_df_0", blk, b);
+	ck.saveLoadLocalArray("LBM_map", 0, m2);
+	std::vector<double> wrong(4);
+	bool refused = false;
+	try { ck.saveLoadVariable("LBM_df_0", blk, wrong); } catch (const std::runtime_error&) { refused = true; }
+	ck.finalize();
+	return (it2 == it && period2 == period && a == b && m == m2 && refused) ? 0 : 1;
+}
+'''
+    with tempfile.TemporaryDirectory() as tmp:
+        f = os.path.join(tmp, "ck.cpp")
+        open(f, "w").write(src)
+        exe = os.path.join(tmp, "ck")
+        r = subprocess.run(["g++", "-std=c++17", f"-I{ROOT}/tnl_lbm_b200/host", f"-I{ROOT}/include", f"-I{ROOT}/tests/solver_shims", f, "-o", exe,
+                            f"-L{ROOT}/tnl_lbm_b200", "-llbmx", f"-Wl,-rpath,{ROOT}/tnl_lbm_b200"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        d = os.path.join(tmp, "results_x", "checkpoint.bp")
+        r = subprocess.run([exe, d], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert sorted(os.listdir(d)) == ["LBM_df_0_block_3.bin", "LBM_map_rank_0.bin", "attributes.txt", "variables.txt"]
+        assert np.array_equal(np.fromfile(os.path.join(d, "LBM_df_0_block_3.bin")), [1.5, -2.25, 3.0e-300])

@@ -1,7 +1,7 @@
 """Build the C++ clients of the host mirror (tnl_lbm_b200/host) against liblbmx.so into examples/bin/ (git-ignored; the
 binaries travel with the working tree to the GPU box):
 
-  * examples/channel3d.cpp                     -- this repository's own solver in the reference's style
+  * examples/channel3d.cpp                     -- this repository's own solver in the reference's style (A-B and A-A builds)
   * /root/reference/sim_NSE/sim_1.cu,          -- the reference's UNMODIFIED solver sources, when the reference tree is present;
     /root/reference/sim_2D/sim2d_1.cu             their third-party includes (argparse, fmt, spdlog) are satisfied by the stand-ins
                                                   under tests/solver_shims (the reference fetches the real ones with CMake)
@@ -21,7 +21,8 @@ LINK = [f"-L{ROOT}/tnl_lbm_b200", "-llbmx", "-Wl,-rpath,$ORIGIN/../../tnl_lbm_b2
 def build(reference: str = "/root/reference") -> list[str]:
     os.makedirs(BIN, exist_ok=True)
     built = []
-    jobs = [("channel3d", [os.path.join(ROOT, "examples", "channel3d.cpp")], [])]
+    jobs = [("channel3d", [os.path.join(ROOT, "examples", "channel3d.cpp")], []),
+            ("channel3d_aa", [os.path.join(ROOT, "examples", "channel3d.cpp")], ["-DAA_PATTERN"])]
     shims = [f"-I{ROOT}/tests/solver_shims"]
     for name, rel in (("ref_sim_1", "sim_NSE/sim_1.cu"), ("ref_sim2d_1", "sim_2D/sim2d_1.cu")):
         src = os.path.join(reference, rel)

@@ -5,8 +5,9 @@
 // paints the map through nse.setBoundaryX/Y/Z / setMap, sets block.data.* and calls execute(state) (include/lbm3d/core.h:38-101).
 // This header keeps those names, argument meanings and error behaviour (exceptions), but the trait classes are *tags*: they
 // carry no device code, they select a kernel family of liblbmx.so through the lbmx_desc enums.  Everything that touches the GPU
-// goes through the C ABI.  Out of scope here: writers (VTK/ADIOS), checkpoints, IBM, MPI -- the hooks exist and
-// are no-ops, so that unmodified solvers compile and run.
+// goes through the C ABI.  ADIOS2 is not a dependency: checkpoints and the 3-D / 2-D cut writers keep the reference's variable
+// names, 1-D local-storage shapes and (z,y,x) float ordering, but land in a raw-dump directory (one .bin per variable plus a
+// text index, see CheckpointManager / RawWriter below).  Out of scope: VTK/BP encoders, IBM, MPI.
 //
 // Device-side user code cannot cross a C ABI.  The finite set the reference's own solvers use is recognised structurally:
 //   DATA with member `vx_profile`           -> LBMX_INFLOW_PROFILE_YZ   (NSE_Data_XProfileInflow, sim_NSE/sim_2.cu:16-33)
@@ -17,14 +18,23 @@
 
 #include <chrono>
 #include <cmath>
+#include <algorithm>
+#include <cerrno>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
 #include <utility>
 #include <vector>
+
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "lbmx.h"
 
@@ -32,6 +42,7 @@
 #include <iostream>
 #if __has_include(<fmt/core.h>)
 	#include <fmt/core.h>
+	#define LBMX_HAVE_FMT 1
 #endif
 #if __has_include(<spdlog/spdlog.h>)
 	#include <spdlog/spdlog.h>
@@ -428,6 +439,221 @@ struct Lattice
 };
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// checkpoint.h: CheckpointManager with the reference's method names (include/lbm3d/checkpoint.h:6-135), raw-dump backend.
+// A checkpoint "file" is a directory (as a .bp is): attributes.txt (name <tab> value), variables.txt (name dtype count) and
+// <name>.bin per variable -- the same variable names ("LBM_df_0_block_0", ...) and 1-D local-storage shape (ghost planes
+// included) the reference hands to ADIOS2 (checkpoint.h:58-101), so the arrays are interchangeable with a BP dump of them.
+// ---------------------------------------------------------------------------------------------------------------------------
+#ifndef ADIOS2_H_
+namespace adios2 {
+enum class Mode { Undefined, Write, Read, Append };
+struct ADIOS {};
+}  // namespace adios2
+#endif
+
+namespace lbmx_host {
+inline bool file_exists(const std::string& path)
+{
+	struct stat st;
+	return ::stat(path.c_str(), &st) == 0;
+}
+inline void make_dirs(const std::string& path)
+{
+	for (size_t i = 1; i <= path.size(); i++)
+		if (i == path.size() || path[i] == '/')
+			::mkdir(path.substr(0, i).c_str(), 0777);
+}
+inline void remove_tree(const std::string& dir, const std::vector<std::string>& names)
+{
+	for (const auto& n : names)
+		::remove((dir + "/" + n).c_str());
+	::rmdir(dir.c_str());
+}
+template <typename T>
+constexpr const char* dtype_name()
+{
+	if (std::is_same<T, double>::value) return "float64";
+	if (std::is_same<T, float>::value) return "float32";
+	if (std::is_same<T, short>::value) return "int16";
+	if (std::is_same<T, int>::value) return "int32";
+	return sizeof(T) == 8 ? "int64" : "bytes";
+}
+}  // namespace lbmx_host
+
+class CheckpointManager
+{
+	std::string dir;
+	adios2::Mode mode = adios2::Mode::Undefined;
+	std::map<std::string, std::string> attributes;
+	std::map<std::string, std::pair<std::string, size_t>> variables;  // name -> (dtype, count)
+
+	std::vector<std::string> file_names() const
+	{
+		std::vector<std::string> n = {"attributes.txt", "variables.txt"};
+		for (const auto& v : variables)
+			n.push_back(v.first + ".bin");
+		return n;
+	}
+
+public:
+	CheckpointManager() = default;
+	explicit CheckpointManager(adios2::ADIOS&) {}
+
+	void start(const std::string filename, adios2::Mode m)
+	{
+		dir = filename;
+		mode = m;
+		attributes.clear();
+		variables.clear();
+		if (m == adios2::Mode::Write) {
+			lbmx_host::make_dirs(dir);
+			return;
+		}
+		std::ifstream fa(dir + "/attributes.txt"), fv(dir + "/variables.txt");
+		if (! fa || ! fv)
+			throw std::runtime_error("CheckpointManager: cannot open checkpoint " + dir);
+		std::string line;
+		while (std::getline(fa, line)) {
+			const size_t t = line.find('\t');
+			if (t != std::string::npos)
+				attributes[line.substr(0, t)] = line.substr(t + 1);
+		}
+		std::string name, dtype;
+		size_t count;
+		while (fv >> name >> dtype >> count)
+			variables[name] = {dtype, count};
+	}
+	void performDeferred() {}
+	void finalize()
+	{
+		if (mode == adios2::Mode::Write) {
+			std::ofstream fa(dir + "/attributes.txt"), fv(dir + "/variables.txt");
+			for (const auto& a : attributes)
+				fa << a.first << '\t' << a.second << '\n';
+			for (const auto& v : variables)
+				fv << v.first << ' ' << v.second.first << ' ' << v.second.second << '\n';
+			if (! fa || ! fv)
+				throw std::runtime_error("CheckpointManager: cannot write the index of " + dir);
+		}
+		mode = adios2::Mode::Undefined;
+	}
+	// removes a checkpoint directory written by this class (used when a staged checkpoint replaces the previous one)
+	static void discard(const std::string& path)
+	{
+		if (! lbmx_host::file_exists(path + "/variables.txt"))
+			return;
+		CheckpointManager old;
+		old.start(path, adios2::Mode::Read);
+		lbmx_host::remove_tree(path, old.file_names());
+	}
+
+	template <typename T, typename CastToType = T>
+	void saveLoadAttribute(const std::string& name, T& variable)
+	{
+		if (mode == adios2::Mode::Write) {
+			char buf[64];
+			if (std::is_floating_point<CastToType>::value)
+				std::snprintf(buf, sizeof buf, "%.17g", (double) static_cast<CastToType>(variable));
+			else
+				std::snprintf(buf, sizeof buf, "%lld", (long long) static_cast<CastToType>(variable));
+			attributes[name] = buf;
+		}
+		else {
+			auto it = attributes.find(name);
+			if (it == attributes.end())
+				throw std::runtime_error("CheckpointManager: attribute " + name + " is not in " + dir);
+			if (std::is_floating_point<CastToType>::value)
+				variable = static_cast<T>(static_cast<CastToType>(std::strtod(it->second.c_str(), nullptr)));
+			else
+				variable = static_cast<T>(static_cast<CastToType>(std::strtoll(it->second.c_str(), nullptr, 10)));
+		}
+	}
+
+	// raw 1-D array under its final name
+	template <typename T>
+	void saveLoadRaw(const std::string& name, T* data, size_t count)
+	{
+		const std::string path = dir + "/" + name + ".bin";
+		if (mode == adios2::Mode::Write) {
+			std::FILE* f = std::fopen(path.c_str(), "wb");
+			if (! f || std::fwrite(data, sizeof(T), count, f) != count) {
+				if (f)
+					std::fclose(f);
+				throw std::runtime_error("CheckpointManager: cannot write " + path);
+			}
+			std::fclose(f);
+			variables[name] = {lbmx_host::dtype_name<T>(), count};
+		}
+		else {
+			auto it = variables.find(name);
+			if (it == variables.end() || it->second.second != count || it->second.first != lbmx_host::dtype_name<T>())
+				throw std::runtime_error("CheckpointManager: variable " + name + " is missing from " + dir + " or has another shape/type");
+			std::FILE* f = std::fopen(path.c_str(), "rb");
+			if (! f || std::fread(data, sizeof(T), count, f) != count) {
+				if (f)
+					std::fclose(f);
+				throw std::runtime_error("CheckpointManager: cannot read " + path);
+			}
+			std::fclose(f);
+		}
+	}
+	// checkpoint.h:58-101: one variable per block, name + "_block_<id>", shape = local storage size
+	template <typename BLOCK, typename Array>
+	void saveLoadVariable(std::string name, BLOCK& block, Array& array)
+	{
+		saveLoadRaw(name + "_block_" + std::to_string(block.id), array.data(), array.size());
+	}
+	// checkpoint.h:106-133: per-rank independent arrays (std::vector or anything with data()/size())
+	template <typename Array>
+	void saveLoadLocalArray(std::string name, int rank, Array& array)
+	{
+		saveLoadRaw(name + "_rank_" + std::to_string(rank), array.data(), array.size());
+	}
+	adios2::Mode getMode() const { return mode; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// ADIOSWriter stand-in for the 3-D / cut writers (lbm_block.hpp:800-846, adios_writer.h): same variable names ("wall", "<id>",
+// "<id>X/Y/Z", "TIME") and (z,y,x) ordering, float32 / int32 payloads
+// ---------------------------------------------------------------------------------------------------------------------------
+struct RawWriter
+{
+	std::ofstream index;
+	std::FILE* payload = nullptr;
+	std::string base;
+	size_t offset = 0;
+	// two files per (file name, cycle): <filename>.<cycle>.txt = index (name dtype count dofs byte_offset), .bin = payloads
+	RawWriter(const std::string& filename, int cycle, const long (&global)[3], const long (&local)[3], const long (&off)[3], double dl)
+	{
+		base = filename + "." + std::to_string(cycle);
+		const size_t slash = base.rfind('/');
+		if (slash != std::string::npos)
+			lbmx_host::make_dirs(base.substr(0, slash));
+		index.open(base + ".txt");
+		payload = std::fopen((base + ".bin").c_str(), "wb");
+		if (! index || ! payload)
+			throw std::runtime_error("RawWriter: cannot create " + base);
+		index << "# global " << global[0] << ' ' << global[1] << ' ' << global[2] << " local " << local[0] << ' ' << local[1] << ' ' << local[2] << " offset "
+			  << off[0] << ' ' << off[1] << ' ' << off[2] << " physDl " << dl << " order zyx\n";
+	}
+	RawWriter(const RawWriter&) = delete;
+	~RawWriter()
+	{
+		if (payload)
+			std::fclose(payload);
+	}
+	template <typename T>
+	void write(const std::string& name, const std::vector<T>& v, int dofs)
+	{
+		if (std::fwrite(v.data(), sizeof(T), v.size(), payload) != v.size())
+			throw std::runtime_error("RawWriter: cannot write " + base + ".bin");
+		index << name << ' ' << lbmx_host::dtype_name<T>() << ' ' << v.size() << ' ' << dofs << ' ' << offset << '\n';
+		offset += v.size() * sizeof(T);
+	}
+	void write(const std::string& name, double value) { index << name << " scalar " << value << '\n'; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // lbm_block.h: one sub-domain = one engine handle + the host mirrors a solver reads and paints
 // ---------------------------------------------------------------------------------------------------------------------------
 template <typename CONFIG>
@@ -633,6 +859,113 @@ struct LBM_BLOCK
 	void setEquilibrium(real rho, real vx, real vy, real vz) { lbmx_host::check(lbmx_df_set_equilibrium(engine, rho, vx, vy, vz), "lbmx_df_set_equilibrium"); }
 	void computeInitialMacro() { lbmx_host::check(lbmx_macro_init(engine), "lbmx_macro_init"); }
 
+	// Checkpoint variables of this block (state.hpp:712-727): map, every DF copy and the macro array in LOCAL STORAGE shape, i.e.
+	// ghost x-planes included, moved straight between the engine and the checkpoint (no second host copy of 29 GB of DFs).
+	void checkpoint(CheckpointManager& ck)
+	{
+		lbmx_layout L{};
+		lbmx_host::check(lbmx_get_layout(engine, &L), "lbmx_get_layout");
+		const bool save = ck.getMode() == adios2::Mode::Write;
+		const std::string blk = "_block_" + std::to_string(id);
+		{
+			std::vector<map_t> m((size_t) L.XYZ);
+			if (save)
+				lbmx_host::check(lbmx_map_download(engine, m.data(), 1), "lbmx_map_download");
+			ck.saveLoadRaw("LBM_map" + blk, m.data(), m.size());
+			if (! save) {
+				lbmx_host::check(lbmx_map_upload(engine, m.data(), 1), "lbmx_map_upload");
+				copyMapToHost();
+			}
+		}
+		std::vector<dreal> a((size_t) L.XYZ * std::max<int>(L.Q, L.n_macro));
+		for (int dfty = 0; dfty < L.dfmax; dfty++) {
+			const size_t n = (size_t) L.XYZ * L.Q;
+			if (save)
+				lbmx_host::check(lbmx_df_download(engine, dfty, a.data(), 1), "lbmx_df_download");
+			ck.saveLoadRaw("LBM_df_" + std::to_string(dfty) + blk, a.data(), n);
+			if (! save)
+				lbmx_host::check(lbmx_df_upload(engine, dfty, a.data(), 1), "lbmx_df_upload");
+		}
+		if (MACRO::N > 0) {
+			const size_t n = (size_t) L.XYZ * L.n_macro;
+			if (save)
+				lbmx_host::check(lbmx_macro_download(engine, a.data(), 1), "lbmx_macro_download");
+			ck.saveLoadRaw("LBM_macro" + blk, a.data(), n);
+			if (! save) {
+				lbmx_host::check(lbmx_macro_upload(engine, a.data(), 1), "lbmx_macro_upload");
+				copyMacroToHost();
+			}
+		}
+	}
+
+	// Output of the solver's outputData() hook over a box of this block in the reference's (z, y, x) order and variable naming
+	// (writeVTK_3D / writeVTK_3Dcut / writeVTK_2DcutX/Y/Z, lbm_block.hpp:800-1110): "wall" = map as int32, then every field the
+	// hook enumerates, scalar "<id>" or vector components "<id>X/Y/Z", float32; box = origin o, extent g, stride `step`.
+	template <typename LAT, typename Output>
+	void writeBox(const LAT& lat, Output&& outputData, const std::string& filename, real time, int cycle, idx ox, idx oy, idx oz, idx gx, idx gy, idx gz, idx step) const
+	{
+		const idx x0 = std::max(ox, offset.x()), x1 = std::min(ox + gx, offset.x() + local.x());
+		const idx y0 = std::max(oy, offset.y()), y1 = std::min(oy + gy, offset.y() + local.y());
+		const idx z0 = std::max(oz, offset.z()), z1 = std::min(oz + gz, offset.z() + local.z());
+		if (x0 >= x1 || y0 >= y1 || z0 >= z1)
+			return;
+		auto cnt = [step](idx n) { return (long) ((n + step - 1) / step); };
+		const long G[3] = {cnt(gx), cnt(gy), cnt(gz)}, Lc[3] = {cnt(x1 - x0), cnt(y1 - y0), cnt(z1 - z0)};
+		const long O[3] = {cnt(x0 - ox), cnt(y0 - oy), cnt(z0 - oz)};
+		RawWriter out(filename, cycle, G, Lc, O, (double) lat.physDl * (double) step);
+		std::vector<int> wall;
+		for (idx z = z0; z < z1; z += step)
+			for (idx y = y0; y < y1; y += step)
+				for (idx x = x0; x < x1; x += step)
+					wall.push_back(hmap(x, y, z));
+		out.write("wall", wall, 1);
+		char idd[500];
+		real value;
+		int dofs = 1;
+		std::vector<float> field;
+		for (int index = 0; outputData(*this, index, 0, idd, offset.x(), offset.y(), offset.z(), value, dofs); index++) {
+			const std::string name(idd);
+			const int n = dofs;
+			for (int dof = 0; dof < n; dof++) {
+				field.clear();
+				for (idx z = z0; z < z1; z += step)
+					for (idx y = y0; y < y1; y += step)
+						for (idx x = x0; x < x1; x += step) {
+							outputData(*this, index, dof, idd, x, y, z, value, dofs);
+							field.push_back((float) value);
+						}
+				static const char* suffix[3] = {"X", "Y", "Z"};
+				out.write(n > 1 && dof < 3 ? name + suffix[dof] : name, field, n);
+			}
+		}
+		out.write("TIME", (double) time);
+	}
+	template <typename LAT, typename Output>
+	void writeVTK_3D(const LAT& lat, Output&& o, const std::string& f, real time, int cycle) const
+	{
+		writeBox(lat, o, f, time, cycle, 0, 0, 0, global.x(), global.y(), global.z(), 1);
+	}
+	template <typename LAT, typename Output>
+	void writeVTK_3Dcut(const LAT& lat, Output&& o, const std::string& f, real time, int cycle, idx ox, idx oy, idx oz, idx gx, idx gy, idx gz, idx step) const
+	{
+		writeBox(lat, o, f, time, cycle, ox, oy, oz, gx, gy, gz, step);
+	}
+	template <typename LAT, typename Output>
+	void writeVTK_2DcutX(const LAT& lat, Output&& o, const std::string& f, real time, int cycle, idx X) const
+	{
+		writeBox(lat, o, f, time, cycle, X, 0, 0, 1, global.y(), global.z(), 1);
+	}
+	template <typename LAT, typename Output>
+	void writeVTK_2DcutY(const LAT& lat, Output&& o, const std::string& f, real time, int cycle, idx Y) const
+	{
+		writeBox(lat, o, f, time, cycle, 0, Y, 0, global.x(), 1, global.z(), 1);
+	}
+	template <typename LAT, typename Output>
+	void writeVTK_2DcutZ(const LAT& lat, Output&& o, const std::string& f, real time, int cycle, idx Z) const
+	{
+		writeBox(lat, o, f, time, cycle, 0, 0, Z, global.x(), global.y(), 1, 1);
+	}
+
 	// block.data -> lbmx_params (what passing the POD by value to the kernel did in the reference, state.hpp:1039)
 	void pushParams()
 	{
@@ -835,7 +1168,24 @@ struct State
 	std::string id;
 	LBM<NSE> nse;
 	T_COUNTER cnt[MAX_COUNTER];
-	int n_cuts = 0;	 // cuts registered through add*cut*: the writers behind them are out of scope, the calls are accepted
+	CheckpointManager checkpoint;
+	int n_cuts = 0;	 // 1-D cuts registered through add1Dcut*: their text writers are out of scope, the calls are accepted
+
+	struct T_PROBE2DCUT
+	{
+		std::string name;
+		int type = 0;  // 0,1,2 = plane normal to x,y,z
+		int cycle = 0;
+		idx position = 0;
+	};
+	struct T_PROBE3DCUT
+	{
+		std::string name;
+		idx ox = 0, oy = 0, oz = 0, lx = 0, ly = 0, lz = 0, step = 1;
+		int cycle = 0;
+	};
+	std::vector<T_PROBE2DCUT> probe2Dvec;
+	std::vector<T_PROBE3DCUT> probe3Dvec;
 
 	virtual void probe1() {}
 	virtual void probe2() {}
@@ -851,18 +1201,79 @@ struct State
 		value = ivalue;
 		return true;
 	}
-	virtual void writeVTKs_2D() {}
-	virtual void writeVTKs_3D() {}
-	virtual void writeVTKs_3Dcut() {}
+	template <typename... ARGS>
+	static std::string cut_name(const char* fmts, ARGS... args)
+	{
+#ifdef LBMX_HAVE_FMT
+		return fmt::format(fmts, args...);
+#else
+		return fmts;
+#endif
+	}
+	auto output_hook()
+	{
+		return [this](const BLOCK_NSE& block, int index, int dof, char* desc, idx x, idx y, idx z, real& value, int& dofs)
+		{
+			return this->outputData(block, index, dof, desc, x, y, z, value, dofs);
+		};
+	}
+	// state.hpp:383-400, 410-470, 473-542: raw dumps results_<id>/output_3D.<cycle>.{txt,bin}, output_3Dcut_<name>.<cycle>.*,
+	// output_2D_<name>.<cycle>.* (RawWriter)
+	virtual void writeVTKs_3D()
+	{
+		lbmx_host::make_dirs("results_" + id);
+		for (const auto& block : nse.blocks)
+			block.writeVTK_3D(nse.lat, output_hook(), "results_" + id + "/output_3D", nse.physTime(), cnt[VTK3D].count);
+	}
+	virtual void writeVTKs_3Dcut()
+	{
+		lbmx_host::make_dirs("results_" + id);
+		for (auto& p : probe3Dvec) {
+			for (const auto& block : nse.blocks)
+				block.writeVTK_3Dcut(nse.lat, output_hook(), "results_" + id + "/output_3Dcut_" + p.name, nse.physTime(), p.cycle, p.ox, p.oy, p.oz, p.lx, p.ly, p.lz, p.step);
+			p.cycle++;
+		}
+	}
+	virtual void writeVTKs_2D()
+	{
+		lbmx_host::make_dirs("results_" + id);
+		for (auto& p : probe2Dvec) {
+			const std::string fname = "results_" + id + "/output_2D_" + p.name;
+			for (const auto& block : nse.blocks) {
+				if (p.type == 0)
+					block.writeVTK_2DcutX(nse.lat, output_hook(), fname, nse.physTime(), p.cycle, p.position);
+				else if (p.type == 1)
+					block.writeVTK_2DcutY(nse.lat, output_hook(), fname, nse.physTime(), p.cycle, p.position);
+				else
+					block.writeVTK_2DcutZ(nse.lat, output_hook(), fname, nse.physTime(), p.cycle, p.position);
+			}
+			p.cycle++;
+		}
+	}
 	virtual void writeVTKs_1D() {}
 	template <typename... ARGS>
-	void add2Dcut_X(idx, const char*, ARGS...) { n_cuts++; }
+	void add2Dcut(int type, idx pos, const char* fmts, ARGS... args)
+	{
+		T_PROBE2DCUT p;
+		p.name = cut_name(fmts, args...);
+		p.type = type;
+		p.position = pos;
+		probe2Dvec.push_back(p);
+	}
 	template <typename... ARGS>
-	void add2Dcut_Y(idx, const char*, ARGS...) { n_cuts++; }
+	void add2Dcut_X(idx x, const char* fmts, ARGS... args) { add2Dcut(0, x, fmts, args...); }
 	template <typename... ARGS>
-	void add2Dcut_Z(idx, const char*, ARGS...) { n_cuts++; }
+	void add2Dcut_Y(idx y, const char* fmts, ARGS... args) { add2Dcut(1, y, fmts, args...); }
 	template <typename... ARGS>
-	void add3Dcut(idx, idx, idx, idx, idx, idx, idx, const char*, ARGS...) { n_cuts++; }
+	void add2Dcut_Z(idx z, const char* fmts, ARGS... args) { add2Dcut(2, z, fmts, args...); }
+	template <typename... ARGS>
+	void add3Dcut(idx ox, idx oy, idx oz, idx lx, idx ly, idx lz, idx step, const char* fmts, ARGS... args)
+	{
+		T_PROBE3DCUT p;
+		p.name = cut_name(fmts, args...);
+		p.ox = ox, p.oy = oy, p.oz = oz, p.lx = lx, p.ly = ly, p.lz = lz, p.step = step;
+		probe3Dvec.push_back(p);
+	}
 	template <typename... ARGS>
 	void add1Dcut(point_t, point_t, const char*, ARGS...) { n_cuts++; }
 	template <typename... ARGS>
@@ -887,7 +1298,7 @@ struct State
 	}
 	virtual void resetDFs() { nse.setEquilibrium(1, 0, 0, 0); }
 	virtual void setupBoundaries() {}
-	// State::SimInit (state.hpp:907-977) without the checkpoint branch
+	// State::SimInit (state.hpp:907-977)
 	virtual void SimInit()
 	{
 		timer_SimInit.start();
@@ -895,10 +1306,14 @@ struct State
 		nse.iterations = 0;
 		for (auto& c : cnt)
 			c.count = 0;
-		reset();
+		cnt[SAVESTATE].count = 1;  // skip the initial save of state
+		if (flagExists("loadstate"))
+			loadState();  // engine arrays and host mirrors come from results_<id>/checkpoint.bp
+		else
+			reset();
 		lbmx_host::log_info("lbmx: %s lattice %ld x %ld x %ld, %s, %s, %s", NSE::COLL::id, (long) nse.lat.global.x(), (long) nse.lat.global.y(),
 							(long) nse.lat.global.z(), NSE::lbmx_precision == LBMX_F64 ? "fp64" : "fp32", NSE::lbmx_streaming == LBMX_STREAM_AA ? "A-A" : "A-B",
-							n_cuts ? "output cuts registered but writers are out of scope (DESIGN.md)" : "no output cuts");
+							n_cuts ? "1-D cuts registered: their writers are out of scope (DESIGN.md)" : "raw-dump writers");
 		timer_SimInit.stop();
 	}
 	// State::updateKernelData (state.hpp:1314-1321)
@@ -1015,13 +1430,84 @@ struct State
 		nse.copyMacroToHost();
 	}
 
-	bool canCompute() { return true; }	// result-directory locking and restart flags (state.hpp:13-66) are out of scope
-	void flagCreate(const char*) {}
-	void flagDelete(const char*) {}
-	bool flagExists(const char*) { return false; }
-	virtual void checkpointStateLocal(int) {}
-	void saveState() {}
-	void loadState() {}
+	// results-directory flags (state.hpp:13-66); directory locking is out of scope
+	std::string flag_path(const char* flagname) const { return "results_" + id + "/flag." + flagname; }
+	void flagCreate(const char* flagname)
+	{
+		if (nse.rank != 0)
+			return;
+		lbmx_host::make_dirs("results_" + id);
+		std::ofstream(flag_path(flagname)).put('\n');
+	}
+	void flagDelete(const char* flagname)
+	{
+		if (nse.rank == 0)
+			::remove(flag_path(flagname).c_str());
+	}
+	bool flagExists(const char* flagname) { return lbmx_host::file_exists(flag_path(flagname)); }
+	bool canCompute()
+	{
+		if (flagExists("loadstate"))
+			return true;
+		if (flagExists("finished") || flagExists("terminated")) {
+			lbmx_host::log_info("results_%s is in finished/terminated state, there is nothing to compute", id.c_str());
+			return false;
+		}
+		return true;
+	}
+
+	// State::checkpointState (state.hpp:677-738): same attribute and variable names
+	void checkpointState(adios2::Mode mode)
+	{
+		checkpoint.saveLoadAttribute("LBM_total_blocks", nse.total_blocks);
+		checkpoint.saveLoadAttribute("LBM_physCharLength", nse.physCharLength);
+		checkpoint.saveLoadAttribute("LBM_physFinalTime", nse.physFinalTime);
+		checkpoint.saveLoadAttribute("LBM_iterations", nse.iterations);
+		for (int c = 0; c < MAX_COUNTER; c++) {
+			const std::string name = "State_counter_" + std::to_string(c);
+			checkpoint.saveLoadAttribute(name + "_count", cnt[c].count);
+			checkpoint.saveLoadAttribute(name + "_period", cnt[c].period);
+		}
+		for (std::size_t i = 0; i < probe3Dvec.size(); i++)
+			checkpoint.saveLoadAttribute("State_probe3D_" + std::to_string(i) + "_cycle", probe3Dvec[i].cycle);
+		for (std::size_t i = 0; i < probe2Dvec.size(); i++)
+			checkpoint.saveLoadAttribute("State_probe2D_" + std::to_string(i) + "_cycle", probe2Dvec[i].cycle);
+		for (auto& block : nse.blocks)
+			block.checkpoint(checkpoint);
+		if (mode == adios2::Mode::Read) {
+			nse.physStartTime = nse.physTime();
+			nse.startIterations = nse.iterations;
+			glups_prev_iterations = nse.startIterations;
+			glups_prev_time = timer_total.getRealTime();
+			nse.updateKernelData();	 // A-A parity and A-B rotation follow the restored iteration count
+		}
+	}
+	virtual void checkpointStateLocal(adios2::Mode) {}
+	// State::saveState / loadState (state.hpp:740-781): stage, swap, flag
+	void saveState()
+	{
+		const std::string tmp = "results_" + id + "/checkpoint_tmp.bp", fin = "results_" + id + "/checkpoint.bp";
+		lbmx_host::log_info("Saving checkpoint in %s", tmp.c_str());
+		checkpoint.start(tmp, adios2::Mode::Write);
+		checkpointState(adios2::Mode::Write);
+		checkpointStateLocal(adios2::Mode::Write);
+		checkpoint.finalize();
+		if (nse.rank == 0) {
+			CheckpointManager::discard(fin);
+			if (::rename(tmp.c_str(), fin.c_str()) != 0)
+				throw std::runtime_error("saveState: cannot move " + tmp + " to " + fin + ": " + std::strerror(errno));
+		}
+		flagCreate("loadstate");
+	}
+	void loadState()
+	{
+		const std::string fin = "results_" + id + "/checkpoint.bp";
+		lbmx_host::log_info("Loading data from checkpoint in %s", fin.c_str());
+		checkpoint.start(fin, adios2::Mode::Read);
+		checkpointState(adios2::Mode::Read);
+		checkpointStateLocal(adios2::Mode::Read);
+		checkpoint.finalize();
+	}
 
 	TNL::Timer timer_total;
 	long wallTime = -1;
