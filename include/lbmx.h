@@ -45,7 +45,8 @@ enum lbmx_coll {
 	LBMX_COLL_SRT = 1,	   /* D3Q27_SRT      d3q27/col_srt.h:16-108   | D2Q9_SRT  d2q9/col_srt.h:16-44 */
 	LBMX_COLL_BGK = 2,	   /* D3Q27_BGK      d3q27/col_bgk.h:16-145 */
 	LBMX_COLL_MRT_LES = 3, /* D3Q27_MRT      d3q27/col_mrt.h:13-141 */
-	LBMX_COLL_CLBM = 4	   /* D2Q9_CLBM      d2q9/col_clbm.h:13-89 */
+	LBMX_COLL_CLBM = 4,	   /* D2Q9_CLBM      d2q9/col_clbm.h:13-89    | D3Q27_CLBM d3q27/col_clbm.h:6-447 (by lattice) */
+	LBMX_COLL_SRT_MODIF_FORCE = 5 /* D3Q27_SRT_MODIF_FORCE  d3q27/col_srt_modif_force.h:9-120 */
 };
 enum lbmx_eq { LBMX_EQ_STD = 0 /* D3Q27_EQ eq.h:8-130, D2Q9_EQ */, LBMX_EQ_INV_CUM = 1 /* D3Q27_EQ_INV_CUM eq_inv_cum.h:13-137 */ };
 enum lbmx_streaming { LBMX_STREAM_AB = 0 /* streaming_AB.h */, LBMX_STREAM_AA = 1 /* streaming_AA.h */ };

@@ -660,6 +660,8 @@ void collide_clbm9(Cell<R, 9>& K)  // d2q9/col_clbm.h:13-89 (cascaded operator +
 	K.f[E(1, -1)] += (c6 * m1 - c6 * m2 + c2 * m3 - c9 * m5 + c3 * m6 - c3 * m7 + m8) / c36;
 }
 
+#include "lbm_oracle_ext.h"
+
 template <typename R>
 void collide(Cell<R, 27>& K, const oracle_desc& d)
 {
@@ -668,6 +670,8 @@ void collide(Cell<R, 27>& K, const oracle_desc& d)
 		case ORC_COLL_SRT: collide_srt27(K, d.eq); break;
 		case ORC_COLL_BGK: collide_bgk27(K); break;
 		case ORC_COLL_MRT_LES: collide_mrt27(K); break;
+		case ORC_COLL_CLBM: collide_clbm27(K); break;
+		case ORC_COLL_SRT_MODIF_FORCE: collide_srt_modif27(K, d.eq); break;
 	}
 }
 // D3Q19 (unpinned): SRT and MRT_LES with the formulas of col_srt.h / col_mrt.h over 19 velocities
@@ -1161,7 +1165,7 @@ bool supported(const oracle_desc* d)
 	if (d->streaming != ORC_STREAM_AB && d->streaming != ORC_STREAM_AA)
 		return false;
 	if (d->lattice == ORC_D3Q27)
-		return d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_MRT_LES && (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM);
+		return d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE && (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM);
 	if (d->lattice == ORC_D2Q9)
 		return (d->coll == ORC_COLL_SRT || d->coll == ORC_COLL_CLBM) && d->eq == ORC_EQ_STD && d->Z == 1;
 	if (d->lattice == ORC_D3Q19)  // no reference implementation: PARITY UNPINNED (see L19)

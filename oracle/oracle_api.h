@@ -23,8 +23,19 @@ extern "C" {
 #endif
 
 enum { ORC_D3Q27 = 0, ORC_D2Q9 = 1, ORC_D3Q19 = 2 };
-enum { ORC_COLL_CUM = 0, ORC_COLL_SRT = 1, ORC_COLL_BGK = 2, ORC_COLL_MRT_LES = 3, ORC_COLL_CLBM = 4 };
-enum { ORC_EQ_STD = 0, ORC_EQ_INV_CUM = 1 };
+enum {
+	ORC_COLL_CUM = 0,
+	ORC_COLL_SRT = 1,
+	ORC_COLL_BGK = 2,
+	ORC_COLL_MRT_LES = 3,
+	ORC_COLL_CLBM = 4,			   /* D2Q9_CLBM or D3Q27_CLBM, by lattice */
+	ORC_COLL_SRT_MODIF_FORCE = 5,  /* D3Q27 only from here on */
+	ORC_COLL_SRT_WELL = 6,
+	ORC_COLL_BGK_WELL = 7,
+	ORC_COLL_CLBM_WELL = 8,
+	ORC_COLL_CUM_WELL = 9
+};
+enum { ORC_EQ_STD = 0, ORC_EQ_INV_CUM = 1, ORC_EQ_WELL = 2 };
 enum { ORC_STREAM_AB = 0, ORC_STREAM_AA = 1 };
 enum { ORC_MACRO_VOID = 0, ORC_MACRO_DEFAULT = 1, ORC_MACRO_MEAN = 2 };
 enum { ORC_INFLOW_NONE = 0, ORC_INFLOW_CONST = 1, ORC_INFLOW_PROFILE_YZ = 2 };

@@ -253,4 +253,6 @@ int ref_dispatch_d3q27_cum(const RefCall& c);
 int ref_dispatch_d3q27_srt(const RefCall& c);
 int ref_dispatch_d3q27_bgk(const RefCall& c);
 int ref_dispatch_d3q27_mrt(const RefCall& c);
+int ref_dispatch_d3q27_clbm(const RefCall& c);
+int ref_dispatch_d3q27_srtmf(const RefCall& c);
 int ref_dispatch_d2q9(const RefCall& c);

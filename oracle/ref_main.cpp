@@ -12,6 +12,10 @@ static int ref_dispatch(const RefCall& c)
 		return r;
 	if ((r = ref_dispatch_d3q27_mrt(c)) != -1)
 		return r;
+	if ((r = ref_dispatch_d3q27_clbm(c)) != -1)
+		return r;
+	if ((r = ref_dispatch_d3q27_srtmf(c)) != -1)
+		return r;
 	if ((r = ref_dispatch_d2q9(c)) != -1)
 		return r;
 	return -1;

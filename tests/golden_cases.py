@@ -67,6 +67,11 @@ CASES = [
          lambda d: lc.map_and_coeffs_bouzidi(d)[0], 4, seed=5),
     Case("cum_f64_ab_profile", O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, inflow=O.INFLOW_PROFILE_YZ, X=10, Y=9, Z=8),
          O.Params(lbmViscosity=0.004, fx=1e-5, vx_profile=(0.05 * np.random.RandomState(5).random_sample((8, 9)))), lambda d: _profile_map(d), 6),
+    Case("clbm3d_f64_ab_zoo", O.Desc(coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("clbm3d_f32_aa_zoo", O.Desc(coll=O.CLBM, eq=O.EQ_STD, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("clbm3d_f64_aa_box", O.Desc(coll=O.CLBM, eq=O.EQ_STD, streaming=O.AA, X=12, Y=12, Z=12), O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 40, "smooth"),
+    Case("srtmf_f64_aa_zoo", O.Desc(coll=O.SRT_MODIF_FORCE, eq=O.EQ_STD, streaming=O.AA, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("srtmf_f32_ab_zoo", O.Desc(coll=O.SRT_MODIF_FORCE, eq=O.EQ_INV_CUM, streaming=O.AB, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("cum_f64_ab_void", O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, macro=O.MACRO_VOID, X=8, Y=7, Z=6), _p3(), lambda d: lc.map_random_ab(d, seed=3), 3),
 ]
 

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "liblbmx.so")
 
 # selectors (include/lbmx.h)
 D3Q27, D2Q9, D3Q19 = 0, 1, 2
-CUM, SRT, BGK, MRT_LES, CLBM = 0, 1, 2, 3, 4
+CUM, SRT, BGK, MRT_LES, CLBM, SRT_MODIF_FORCE = 0, 1, 2, 3, 4, 5
 EQ_STD, EQ_INV_CUM = 0, 1
 AB, AA = 0, 1
 MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN = 0, 1, 2

@@ -30,6 +30,8 @@ FAMILIES = [
     ("d3q27_srt", "D3Q27", "K_SRT"),
     ("d3q27_bgk", "D3Q27", "K_BGK"),
     ("d3q27_mrt", "D3Q27", "K_MRT"),
+    ("d3q27_clbm", "D3Q27", "K_CLBM"),
+    ("d3q27_srtmf", "D3Q27", "K_SRT_MF"),
     ("d3q19_srt", "D3Q19", "K_SRT"),
     ("d3q19_mrt", "D3Q19", "K_MRT"),
     ("d2q9_srt", "D2Q9", "K_SRT"),

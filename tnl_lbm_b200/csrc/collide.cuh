@@ -26,6 +26,7 @@ struct Phys
 	#define LBMX_STRICT 0
 #endif
 #include "collide_strict.cuh"
+#include "collide_ext.cuh"
 
 namespace lbmx {
 constexpr bool kStrict = LBMX_STRICT != 0;
@@ -607,12 +608,19 @@ LBMX_D void collide_mrt(R (&f)[19], const Phys<R>& P, R rho, R vx, R vy, R vz)
 // --------------------------------------------------------------------------------------------------------------------
 // operator tags: what COLL means for a kernel instantiation
 // --------------------------------------------------------------------------------------------------------------------
-enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 };
+enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 /* D2Q9_CLBM or D3Q27_CLBM, by lattice */, K_SRT_MF = 5 };
 
 template <int KIND, typename R>
 LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
-	if constexpr (kStrict) {
+	if constexpr (KIND == K_CLBM)
+		ext::collide_clbm<! kStrict>(f, P, rho, vx, vy, vz);
+	else if constexpr (KIND == K_SRT_MF) {
+		R feq[27];
+		equilibrium(feq, eqkind, rho, vx, vy, vz);
+		ext::collide_srt_modif(f, feq, P, vx, vy, vz);
+	}
+	else if constexpr (kStrict) {
 		if constexpr (KIND == K_CUM)
 			strict::collide_cum(f, P, rho, vx, vy, vz);
 		else if constexpr (KIND == K_SRT) {

@@ -383,6 +383,8 @@ bool pick_kernels(lbmx_engine* e)
 				case LBMX_COLL_SRT: return e->f64() ? get_kernels_d3q27_srt_strict(e->kd) : get_kernels_d3q27_srt_strict(e->kf);
 				case LBMX_COLL_BGK: return e->f64() ? get_kernels_d3q27_bgk_strict(e->kd) : get_kernels_d3q27_bgk_strict(e->kf);
 				case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt_strict(e->kd) : get_kernels_d3q27_mrt_strict(e->kf);
+				case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm_strict(e->kd) : get_kernels_d3q27_clbm_strict(e->kf);
+				case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf_strict(e->kd) : get_kernels_d3q27_srtmf_strict(e->kf);
 			}
 		}
 		else if (d.lattice == LBMX_D2Q9) {
@@ -399,6 +401,8 @@ bool pick_kernels(lbmx_engine* e)
 			case LBMX_COLL_SRT: return e->f64() ? get_kernels_d3q27_srt(e->kd) : get_kernels_d3q27_srt(e->kf);
 			case LBMX_COLL_BGK: return e->f64() ? get_kernels_d3q27_bgk(e->kd) : get_kernels_d3q27_bgk(e->kf);
 			case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt(e->kd) : get_kernels_d3q27_mrt(e->kf);
+			case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm(e->kd) : get_kernels_d3q27_clbm(e->kf);
+			case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf(e->kd) : get_kernels_d3q27_srtmf(e->kf);
 		}
 	}
 	else if (d.lattice == LBMX_D3Q19) {

@@ -663,7 +663,15 @@ bool get_kernels_d3q27_bgk(StepKernels<float>&);
 bool get_kernels_d3q27_bgk(StepKernels<double>&);
 bool get_kernels_d3q27_mrt(StepKernels<float>&);
 bool get_kernels_d3q27_mrt(StepKernels<double>&);
+bool get_kernels_d3q27_clbm(StepKernels<float>&);
+bool get_kernels_d3q27_clbm(StepKernels<double>&);
+bool get_kernels_d3q27_srtmf(StepKernels<float>&);
+bool get_kernels_d3q27_srtmf(StepKernels<double>&);
 // the same families in parity arithmetic (collide_strict.cuh, -fmad=false)
+bool get_kernels_d3q27_clbm_strict(StepKernels<float>&);
+bool get_kernels_d3q27_clbm_strict(StepKernels<double>&);
+bool get_kernels_d3q27_srtmf_strict(StepKernels<float>&);
+bool get_kernels_d3q27_srtmf_strict(StepKernels<double>&);
 bool get_kernels_d3q27_cum_strict(StepKernels<float>&);
 bool get_kernels_d3q27_cum_strict(StepKernels<double>&);
 bool get_kernels_d3q27_srt_strict(StepKernels<float>&);

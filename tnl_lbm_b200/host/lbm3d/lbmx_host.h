@@ -239,6 +239,8 @@ LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM, "CUM")
 LBMX_COLL_TAG(D3Q27_SRT, D3Q27_EQ, LBMX_COLL_SRT, "SRT")
 LBMX_COLL_TAG(D3Q27_BGK, D3Q27_EQ, LBMX_COLL_BGK, "BGK")
 LBMX_COLL_TAG(D3Q27_MRT, D3Q27_EQ, LBMX_COLL_MRT_LES, "MRT_LES")
+LBMX_COLL_TAG(D3Q27_CLBM, D3Q27_EQ, LBMX_COLL_CLBM, "CLBM")
+LBMX_COLL_TAG(D3Q27_SRT_MODIF_FORCE, D3Q27_EQ, LBMX_COLL_SRT_MODIF_FORCE, "SRT_MRT_MODIF_FORCE")
 LBMX_COLL_TAG(D2Q9_SRT, D2Q9_EQ, LBMX_COLL_SRT, "SRT")
 LBMX_COLL_TAG(D2Q9_CLBM, D2Q9_EQ, LBMX_COLL_CLBM, "CLBM")
 #undef LBMX_COLL_TAG

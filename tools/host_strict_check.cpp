@@ -56,5 +56,9 @@ int main()
 	r |= run<float, K_SRT>(ORC_COLL_SRT, ORC_EQ_STD, ORC_F32);
 	r |= run<float, K_BGK>(ORC_COLL_BGK, ORC_EQ_STD, ORC_F32);
 	r |= run<float, K_MRT>(ORC_COLL_MRT_LES, ORC_EQ_STD, ORC_F32);
+	r |= run<float, K_CLBM>(ORC_COLL_CLBM, ORC_EQ_STD, ORC_F32);
+	r |= run<double, K_CLBM>(ORC_COLL_CLBM, ORC_EQ_STD, ORC_F64);
+	r |= run<float, K_SRT_MF>(ORC_COLL_SRT_MODIF_FORCE, ORC_EQ_INV_CUM, ORC_F32);
+	r |= run<double, K_SRT_MF>(ORC_COLL_SRT_MODIF_FORCE, ORC_EQ_STD, ORC_F64);
 	return r;
 }
