@@ -275,6 +275,11 @@ def main():
     ms_max = allmax(ms)
     value = cells_global * a.steps / (ms_max * 1e-3) / 1e6
     assert not eng.has_nan(), "NaN in the density field after the timed steps"
+    # the halo exchange of one step, alone on the communication stream (inside a step it runs concurrently with the interior update)
+    halo_ms = None
+    if halo_bytes > 0:
+        barrier()
+        halo_ms = allmax(eng.halo_time(20))
 
     # ---- end-to-end through the C ABI with host buffers: upload map + initial fields, K steps, download macros
     barrier()
@@ -332,6 +337,12 @@ def main():
                              "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_update": B_PER_UPDATE,
                              "kernel": f"k_bulk<D3Q27,CUM,double,{'A-A even/odd' if a.streaming == 'AA' else 'A-B'}>", "registers": st.bulk_regs, "block": st.bulk_block},
                 "halo_bytes_per_step_per_gpu": halo_bytes / a.steps}
+        if halo_ms is not None:
+            hb = halo_bytes / a.steps
+            line["halo"] = {"bytes_per_step_per_gpu": hb, "exchange_ms_alone": halo_ms, "nvlink_bound_ms": hb / 900e9 * 1e3,
+                            "nvlink_peak": "900 GB/s per direction (NVLink 5); each GPU sends and receives bytes_per_step_per_gpu per step",
+                            "step_ms": ms_max / a.steps, "hidden_behind_interior": bool(halo_ms < ms_max / a.steps),
+                            "transport": "NCCL send/recv, 9 plane messages per direction in one group" if N > 1 else "device copy kernel (single slab with ghost planes)"}
     eng.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's CPU code on a bounded sample of the same workload

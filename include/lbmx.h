@@ -203,6 +203,10 @@ int lbmx_sync(lbmx_engine* e);
 /* same, bracketed by CUDA events on the engine's own compute stream; synchronises; elapsed device time in ms */
 int lbmx_step_timed(lbmx_engine* e, int64_t nsteps, float* elapsed_ms);
 
+/* Measurement aid: repeat the halo exchange of the last completed step `reps` times, ALONE on the communication stream, and
+ * return the device time per exchange (CUDA events).  Idempotent on the data; collective over the ranks of the communicator.
+ * Reported by bench.py next to the NVLink-bound time of the same bytes. */
+int lbmx_halo_time(lbmx_engine* e, int32_t reps, float* ms_per_exchange);
 int lbmx_get_iterations(const lbmx_engine* e, int64_t* it);
 int lbmx_set_iterations(lbmx_engine* e, int64_t it); /* checkpoint restore: parity travels with the raw arrays */
 

@@ -42,6 +42,11 @@ def run_ghost_single(case):
         e.sync()
         st = e.stats()
         assert st.halo_bytes_sent > 0
+        # lbmx_halo_time repeats the last exchange alone on the communication stream: a positive device time, and the state
+        # (ghost planes included) is untouched
+        before = e.df_download(0, with_ghosts=True)
+        assert e.halo_time(5) > 0.0
+        assert np.array_equal(before, e.df_download(0, with_ghosts=True))
         return e.df_download(0), e.macro_download()
 
 

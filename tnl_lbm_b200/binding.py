@@ -63,7 +63,7 @@ SYMBOLS = [
     "lbmx_last_error", "lbmx_version", "lbmx_decompose_x", "lbmx_halo_directions", "lbmx_halo_plan", "lbmx_create", "lbmx_destroy", "lbmx_get_layout",
     "lbmx_comm_unique_id", "lbmx_comm_init", "lbmx_map_upload", "lbmx_map_download", "lbmx_df_set_equilibrium", "lbmx_df_set_equilibrium_field",
     "lbmx_df_upload", "lbmx_df_download", "lbmx_df_sync_ghosts", "lbmx_macro_init", "lbmx_macro_download", "lbmx_macro_upload", "lbmx_set_params",
-    "lbmx_set_inflow_profile", "lbmx_bouzidi_upload", "lbmx_step", "lbmx_sync", "lbmx_step_timed", "lbmx_get_iterations", "lbmx_set_iterations", "lbmx_has_nan",
+    "lbmx_set_inflow_profile", "lbmx_bouzidi_upload", "lbmx_step", "lbmx_sync", "lbmx_step_timed", "lbmx_halo_time", "lbmx_get_iterations", "lbmx_set_iterations", "lbmx_has_nan",
     "lbmx_get_device_ptrs", "lbmx_get_stats",
 ]
 
@@ -103,6 +103,7 @@ def lib():
         L.lbmx_step.argtypes = [vp, i64]
         L.lbmx_sync.argtypes = [vp]
         L.lbmx_step_timed.argtypes = [vp, i64, C.POINTER(C.c_float)]
+        L.lbmx_halo_time.argtypes = [vp, i32, C.POINTER(C.c_float)]
         L.lbmx_get_iterations.argtypes = [vp, C.POINTER(i64)]
         L.lbmx_set_iterations.argtypes = [vp, i64]
         L.lbmx_has_nan.argtypes = [vp, C.POINTER(i32)]
@@ -260,6 +261,12 @@ class Engine:
     def step_timed(self, n) -> float:
         ms = C.c_float()
         _check(lib().lbmx_step_timed(self._h, n, C.byref(ms)), "lbmx_step_timed")
+        return ms.value
+
+    def halo_time(self, reps: int = 20) -> float:
+        """Device time (ms) of one halo exchange run alone on the communication stream; collective over the ranks."""
+        ms = C.c_float()
+        _check(lib().lbmx_halo_time(self._h, reps, C.byref(ms)), "lbmx_halo_time")
         return ms.value
 
     @property

@@ -1045,6 +1045,32 @@ int lbmx_step_timed(lbmx_engine* e, int64_t nsteps, float* elapsed_ms)
 	return lbmx_sync(e);
 }
 
+int lbmx_halo_time(lbmx_engine* e, int32_t reps, float* ms_per_exchange)
+{
+	if (! e || ! ms_per_exchange || reps < 1)
+		return fail(LBMX_ERR_ARG, "lbmx_halo_time: bad argument");
+	if (e->ox == 0 || e->iter == 0)
+		return fail(LBMX_ERR_STATE, "lbmx_halo_time: needs ghost planes and at least one completed step");
+	int rc = lbmx_sync(e);
+	if (rc)
+		return rc;
+	CU(cudaEventRecord(e->ev_t0, e->s_comm));
+	for (int32_t r = 0; r < reps; r++) {
+		e->iter--;	// the exchange that follows step (iter - 1): same planes, same slots, same values -> idempotent
+		void* arr = e->aa() ? e->df[0] : e->other();
+		rc = e->f64() ? exchange<double>(e, arr) : exchange<float>(e, arr);
+		e->iter++;
+		if (rc)
+			return rc;
+	}
+	CU(cudaEventRecord(e->ev_t1, e->s_comm));
+	CU(cudaEventSynchronize(e->ev_t1));
+	float ms = 0;
+	CU(cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1));
+	*ms_per_exchange = ms / (float) reps;
+	return lbmx_sync(e);
+}
+
 int lbmx_get_iterations(const lbmx_engine* e, int64_t* it)
 {
 	if (! e || ! it)
