@@ -133,17 +133,25 @@ struct IsBoundaryCell
 	}
 };
 
-__global__ void k_count_boundary_cells(const int16_t* map, long long first_cell, int YZ, int periodic, unsigned* per_plane)
+// per_plane[x] += boundary cells of plane x; per_plane[gridDim.y] += cells of type `reads_neighbour` (GEO_OUTFLOW_RIGHT: pulls the
+// populations of the cell at x-1, bc.h:63-65 -- under A-A that is an in-place array another cell updates in the same step)
+__global__ void k_count_boundary_cells(const int16_t* map, long long first_cell, int YZ, int periodic, int reads_neighbour, unsigned* per_plane)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	bool b = false;
+	bool b = false, r = false;
 	if (i < YZ) {
 		const int m = map[first_cell + (long long) blockIdx.y * YZ + i];
 		b = m != 0 && m != periodic;
+		r = m == reads_neighbour;
 	}
 	const unsigned n = __popc(__ballot_sync(0xffffffffu, b));
-	if ((threadIdx.x & 31) == 0 && n)
-		atomicAdd(per_plane + blockIdx.y, n);
+	const unsigned nr = __popc(__ballot_sync(0xffffffffu, r));
+	if ((threadIdx.x & 31) == 0) {
+		if (n)
+			atomicAdd(per_plane + blockIdx.y, n);
+		if (nr)
+			atomicAdd(per_plane + gridDim.y, nr);
+	}
 }
 
 // =====================================================================================================================
@@ -174,6 +182,7 @@ struct lbmx_engine
 
 	std::vector<int64_t> plane_start;  // boundary-list offsets per local x plane, size X+1
 	int64_t nb = 0, n_bulk = 0;
+	bool list_after_bulk = false;  // see lbmx_map_upload
 	bool map_ready = false;
 
 	unsigned ydiv_mul = 0, ydiv_shift = 0;
@@ -242,10 +251,14 @@ KParams<R> make_params(const lbmx_engine* e)
 
 constexpr int BLOCK = LBMX_BULK_BLOCK;
 
-// launch the two step kernels over local planes [xb, xe) on `st`
+// launch the two step kernels over local planes [xb, xe): the bulk kernel on `st`, the boundary-list kernel on `st_list` (default:
+// the same stream).  Within one step the two kernels touch disjoint cells and every population slot has exactly one writer, so
+// they may run concurrently.
 template <typename R>
-int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, int xe, cudaStream_t st)
+int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, int xe, cudaStream_t st, cudaStream_t st_list = nullptr)
 {
+	if (! st_list)
+		st_list = st;
 	if (xe <= xb)
 		return LBMX_OK;
 	p.x_begin = xb;
@@ -257,7 +270,7 @@ int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, 
 	e->stats.kernel_launches++;
 	const int nbl = p.nb_end - p.nb_begin;
 	if (nbl > 0) {
-		K.boundary<<<(nbl + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(p);
+		K.boundary<<<(nbl + BLOCK - 1) / BLOCK, BLOCK, 0, st_list>>>(p);
 		e->stats.kernel_launches++;
 	}
 	CU(cudaGetLastError());
@@ -321,6 +334,7 @@ template <typename R>
 int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 {
 	const bool ghosts = e->ox > 0;
+	CU(cudaEventRecord(e->ev_main, e->s_main));	 // everything enqueued on the compute stream so far (uploads, initialisation) precedes the side streams' work
 	for (int64_t s = 0; s < nsteps; s++) {
 		KParams<R> p = make_params<R>(e);
 		const bool last = s == nsteps - 1;
@@ -331,8 +345,20 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 		p.stat_counter = e->prm.stat_counter + (int) s;
 		int rc;
 		if (! ghosts) {
-			if ((rc = launch_range(e, K, p, 0, (int) e->X, e->s_main)))
-				return rc;
+			if (e->nb == 0 || e->list_after_bulk) {
+				if ((rc = launch_range(e, K, p, 0, (int) e->X, e->s_main)))
+					return rc;
+			}
+			else {
+				// the boundary-list kernel (a few thousand cells: a latency chain of its own) runs beside the bulk kernel on the second
+				// stream; both kernels of a step wait for both kernels of the previous one
+				CU(cudaStreamWaitEvent(e->s_edge, e->ev_main, 0));
+				CU(cudaStreamWaitEvent(e->s_main, e->ev_edge, 0));
+				if ((rc = launch_range(e, K, p, 0, (int) e->X, e->s_main, e->s_edge)))
+					return rc;
+				CU(cudaEventRecord(e->ev_main, e->s_main));
+				CU(cudaEventRecord(e->ev_edge, e->s_edge));
+			}
 		}
 		else {
 			// boundary planes first on the high-priority stream, then the exchange, interior concurrently (state.hpp:1060-1108)
@@ -357,11 +383,11 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 		e->iter++;
 	}
 	e->prm.stat_counter += (int) nsteps;
-	if (ghosts) {
-		// leave the engine in a state where s_main alone orders everything that was enqueued
+	// leave the engine in a state where s_main alone orders everything that was enqueued
+	if (ghosts)
 		CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
+	if (ghosts || (e->nb > 0 && ! e->list_after_bulk))
 		CU(cudaStreamWaitEvent(e->s_main, e->ev_edge, 0));
-	}
 	return LBMX_OK;
 }
 
@@ -787,15 +813,19 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	// the device: the map never travels back to the host.
 	const int periodic = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::PERIODIC : (int) D3Q27::PERIODIC;	// D3Q19 shares the D3Q27 cell types
 	const long long first_cell = (long long) e->ox * e->YZ, n_cells = (long long) e->X * e->YZ;
+	const int outflow_right = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::OUTFLOW_RIGHT : (int) D3Q27::OUTFLOW_RIGHT;
 	unsigned* d_counts = nullptr;
-	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) e->X));
-	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) e->X, e->s_main));
-	k_count_boundary_cells<<<dim3((unsigned) ((e->YZ + 255) / 256), (unsigned) e->X), 256, 0, e->s_main>>>(e->map, first_cell, (int) e->YZ, periodic, d_counts);
+	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) (e->X + 1)));
+	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) (e->X + 1), e->s_main));
+	k_count_boundary_cells<<<dim3((unsigned) ((e->YZ + 255) / 256), (unsigned) e->X), 256, 0, e->s_main>>>(e->map, first_cell, (int) e->YZ, periodic, outflow_right, d_counts);
 	e->stats.kernel_launches++;
-	std::vector<unsigned> counts((size_t) e->X);
-	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) e->X, cudaMemcpyDeviceToHost, e->s_main));
+	std::vector<unsigned> counts((size_t) e->X + 1);
+	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) (e->X + 1), cudaMemcpyDeviceToHost, e->s_main));
 	CU(cudaStreamSynchronize(e->s_main));
 	CU(cudaFree(d_counts));
+	// Under A-A such a cell reads, in place, populations that the cell to its left rewrites in the same step (the reference has the
+	// same race).  Keeping the boundary list strictly after the bulk kernel makes the outcome reproducible.
+	e->list_after_bulk = e->aa() && counts[(size_t) e->X] > 0;
 	e->plane_start.assign((size_t) e->X + 1, 0);
 	for (int64_t x = 0; x < e->X; x++)
 		e->plane_start[(size_t) x + 1] = e->plane_start[(size_t) x] + counts[(size_t) x];
