@@ -618,7 +618,7 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 	else if constexpr (KIND == K_SRT_MF) {
 		R feq[27];
 		equilibrium(feq, eqkind, rho, vx, vy, vz);
-		ext::collide_srt_modif(f, feq, P, vx, vy, vz);
+		ext::collide_srt_modif<kStrict>(f, feq, P, vx, vy, vz);
 	}
 	else if constexpr (kStrict) {
 		if constexpr (KIND == K_CUM)

@@ -248,7 +248,7 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 template <int KIND, typename R, int MODE>
 constexpr int bulk_minblocks()
 {
-	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK))
+	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_SRT_MF || KIND == K_CLBM))
 		return LBMX_BULK_MINBLOCKS < 3 ? LBMX_BULK_MINBLOCKS : 3;
 	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;
 }

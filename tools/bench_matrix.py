@@ -16,12 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tnl_lbm_b200 import binding as B  # noqa: E402
 
-NAMES = {B.CUM: "CUM", B.SRT: "SRT", B.BGK: "BGK", B.MRT_LES: "MRT_LES", B.CLBM: "CLBM"}
+NAMES = {B.CUM: "CUM", B.SRT: "SRT", B.BGK: "BGK", B.MRT_LES: "MRT_LES", B.CLBM: "CLBM", B.SRT_MODIF_FORCE: "SRT_MODIF_FORCE"}
 
 
-def run(lattice, coll, eq, prec, streaming, shape, steps, map_kind="periodic"):
+def run(lattice, coll, eq, prec, streaming, shape, steps, map_kind="periodic", macro=B.MACRO_DEFAULT, flags=0):
     X, Y, Z = shape
-    e = B.Engine(lattice=lattice, coll=coll, eq=eq, streaming=streaming, macro=B.MACRO_DEFAULT, inflow=B.INFLOW_CONST, precision=prec, X=X, Y=Y, Z=Z)
+    e = B.Engine(lattice=lattice, coll=coll, eq=eq, streaming=streaming, macro=macro, flags=flags, inflow=B.INFLOW_CONST, precision=prec, X=X, Y=Y, Z=Z)
     per = 6 if lattice == B.D2Q9 else 7
     m = np.full((X, Z, Y), per, dtype=np.int16)
     if map_kind == "cavity":  # SURVEY §8d cfg 2: walls on x faces and y=0, lid row y=Y-1 = GEO_INFLOW
@@ -49,6 +49,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "bench_matrix_r1.md"))
     ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--only", default="", help="run only the rows whose name contains this string (e.g. 'ext' = the rows added after the first table)")
     a = ap.parse_args()
     peak = 6446.9
     pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -71,8 +72,21 @@ def main():
                 cfgs.append(("D2Q9", B.D2Q9, coll, B.EQ_STD, prec, st, (8192, 8192, 1), "periodic"))
     cfgs.append(("D2Q9 cavity 1024^2 (cfg 2, 151 MB: L2-resident)", B.D2Q9, B.SRT, B.EQ_STD, B.F64, B.AB, (1024, 1024, 1), "cavity"))
     cfgs.append(("D2Q9 cavity 8192^2", B.D2Q9, B.SRT, B.EQ_STD, B.F64, B.AB, (8192, 8192, 1), "cavity"))
-    for name, lat, coll, eq, prec, st, shape, mk in cfgs:
-        mlups, gbs, regs, bpu = run(lat, coll, eq, prec, st, shape, a.steps, mk)
+    cfgs = [c + (B.MACRO_DEFAULT, 0) for c in cfgs]
+    # rows added after the first table: further D3Q27 operators, MACRO_Mean (13 read-modify-write fields per cell on top of the DFs:
+    # its own bytes-per-update figure), and the parity-arithmetic build of the headline kernel
+    for coll, eq in ((B.CLBM, B.EQ_STD), (B.SRT_MODIF_FORCE, B.EQ_STD)):
+        for prec in (B.F64, B.F32):
+            for st in (B.AA, B.AB):
+                cfgs.append(("D3Q27 ext", B.D3Q27, coll, eq, prec, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, 0))
+    for st in (B.AA, B.AB):
+        cfgs.append(("D3Q27 ext MACRO_Mean (+13 RMW fields: 640 B per update)", B.D3Q27, B.CUM, B.EQ_INV_CUM, B.F64, st, (320, 320, 320), "periodic", B.MACRO_MEAN, 0))
+        cfgs.append(("D3Q27 ext parity arithmetic", B.D3Q27, B.CUM, B.EQ_INV_CUM, B.F64, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, B.FLAG_STRICT_ARITH))
+        cfgs.append(("D3Q27 ext parity arithmetic", B.D3Q27, B.CUM, B.EQ_INV_CUM, B.F32, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, B.FLAG_STRICT_ARITH))
+    if a.only:
+        cfgs = [c for c in cfgs if a.only in c[0]]
+    for name, lat, coll, eq, prec, st, shape, mk, macro, flags in cfgs:
+        mlups, gbs, regs, bpu = run(lat, coll, eq, prec, st, shape, a.steps, mk, macro, flags)
         row = f"| {name} | {NAMES[coll]} | {'fp64' if prec == B.F64 else 'fp32'} | {'A-A' if st == B.AA else 'A-B'} | {shape[0]}x{shape[1]}x{shape[2]} | {bpu} | {mlups:,.0f} | {gbs:,.0f} | {gbs / peak * 100:.0f} % | {regs} |"
         print(row, flush=True)
         rows.append(row)

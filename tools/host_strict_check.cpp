@@ -8,7 +8,9 @@
 #include <cstring>
 #include <vector>
 using std::sqrt;
+#ifndef LBMX_STRICT
 #define LBMX_STRICT 1
+#endif
 #include "../tnl_lbm_b200/csrc/collide.cuh"
 #include "../oracle/oracle_api.h"
 using namespace lbmx;
