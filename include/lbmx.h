@@ -46,7 +46,12 @@ enum lbmx_coll {
 	LBMX_COLL_BGK = 2,	   /* D3Q27_BGK      d3q27/col_bgk.h:16-145 */
 	LBMX_COLL_MRT_LES = 3, /* D3Q27_MRT      d3q27/col_mrt.h:13-141 */
 	LBMX_COLL_CLBM = 4,	   /* D2Q9_CLBM      d2q9/col_clbm.h:13-89    | D3Q27_CLBM d3q27/col_clbm.h:6-447 (by lattice) */
-	LBMX_COLL_SRT_MODIF_FORCE = 5 /* D3Q27_SRT_MODIF_FORCE  d3q27/col_srt_modif_force.h:9-120 */
+	LBMX_COLL_SRT_MODIF_FORCE = 5, /* D3Q27_SRT_MODIF_FORCE  d3q27/col_srt_modif_force.h:9-120 */
+	/* 6-9: the *_WELL operators -- not instantiable in the reference itself (D3Q27_COMMON_WELL lacks setEquilibriumLat /
+	 * setEquilibriumDecomposition, which lbm_block.hpp:243 and d3q27/bc.h:141 require), so there is no behaviour to match */
+	LBMX_COLL_CUM_2017 = 10,		   /* D3Q27_CUM built with -DUSE_GEIER_CUM_2017 (defs.h:254; col_cum.h:177-208,258-276) */
+	LBMX_COLL_CUM_ANTIALIAS = 11,	   /* D3Q27_CUM built with -DUSE_GEIER_CUM_ANTIALIAS (defs.h:255; col_cum.h:215-229) */
+	LBMX_COLL_CUM_2017_ANTIALIAS = 12 /* both switches */
 };
 enum lbmx_eq { LBMX_EQ_STD = 0 /* D3Q27_EQ eq.h:8-130, D2Q9_EQ */, LBMX_EQ_INV_CUM = 1 /* D3Q27_EQ_INV_CUM eq_inv_cum.h:13-137 */ };
 enum lbmx_streaming { LBMX_STREAM_AB = 0 /* streaming_AB.h */, LBMX_STREAM_AA = 1 /* streaming_AA.h */ };

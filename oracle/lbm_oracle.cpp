@@ -357,7 +357,18 @@ inline void from_central(R& lo, R& mid, R& hi, R v)	 // Eq G2015(88)-(96) (col_c
 	hi = fp;
 }
 
+// rate limiter of the 2017 parametrisation (col_cum.h:183-197): w + (1 - w) * fabs(x) / (rho * lambda + fabs(x)).  The
+// reference calls an unqualified fabs(): in its host build that is ::fabs(double), so for dreal = float everything downstream
+// of it is evaluated in double and rounded once when stored (same situation as sqrt() in col_mrt.h).
 template <typename R>
+inline R limited_rate(R w, R x, R rho, R lambda)
+{
+	const double ax = std::fabs((double) x);
+	return (R) ((double) w + (double) ((R) 1.0 - w) * ax / ((double) (rho * lambda) + ax));
+}
+
+// G2017: -DUSE_GEIER_CUM_2017 (parametrised rates, limiter, A and B terms); ANTIALIAS: -DUSE_GEIER_CUM_ANTIALIAS (velocity derivatives)
+template <typename R, bool G2017 = false, bool ANTIALIAS = false>
 void collide_cum(Cell<R, 27>& K)
 {
 	const R one = 1, two = 2, three = 3, four = 4, sixteen = 16, half = (R) 0.5;
@@ -405,9 +416,43 @@ void collide_cum(Cell<R, 27>& K)
 	// and the velocity-derivative (antialias) terms are 0.  They stay in the formulas so that the evaluation,
 	// including products with 0 and 1, is the reference's.
 	const R omega1 = one / (three * K.nu + half);
-	const R omega2 = one, omega3 = one, omega4 = one, omega5 = one, omega6 = one, omega7 = one, omega8 = one, omega9 = one, omega10 = one;
-	const R A = 0, B = 0;
-	const R Dxu = 0, Dyv = 0, Dzw = 0, DxvDyu = 0, DxwDzu = 0, DywDzv = 0;
+	const R omega2 = one;
+	R omega3 = one, omega4 = one, omega5 = one, A = 0, B = 0;
+	const R omega6 = one, omega7 = one, omega8 = one, omega9 = one, omega10 = one;
+	R w120p102 = 0, w210p012 = 0, w201p021 = 0, w120m102 = 0, w210m012 = 0, w201m021 = 0, w111 = 0;
+	if (G2017) {  // col_cum.h:177-208
+		const R five = 5, seven = 7, eight = 8, nine = 9, n10 = 10, n11 = 11, n13 = 13, n15 = 15, n18 = 18, n24 = 24, n26 = 26, n28 = 28, n42 = 42, n46 = 46,
+				n48 = 48, n56 = 56, n216 = 216, six = 6;
+		const R lambda3 = (R) 0.01, lambda4 = (R) 0.01, lambda5 = (R) 0.01;
+		omega3 = eight * (omega1 - two) * (omega2 * (three * omega1 - one) - five * omega1)
+			   / (eight * (five - two * omega1) * omega1 + omega2 * (eight + omega1 * (nine * omega1 - n26)));
+		w120p102 = limited_rate(omega3, C[1][2][0] + C[1][0][2], rho, lambda3);
+		w210p012 = limited_rate(omega3, C[2][1][0] + C[0][1][2], rho, lambda3);
+		w201p021 = limited_rate(omega3, C[2][0][1] + C[0][2][1], rho, lambda3);
+		omega4 = eight * (omega1 - two) * (omega1 + omega2 * (three * omega1 - seven)) / (omega2 * (n56 - n42 * omega1 + nine * omega1 * omega1) - eight * omega1);
+		w120m102 = limited_rate(omega4, C[1][2][0] - C[1][0][2], rho, lambda4);
+		w210m012 = limited_rate(omega4, C[2][1][0] - C[0][1][2], rho, lambda4);
+		w201m021 = limited_rate(omega4, C[2][0][1] - C[0][2][1], rho, lambda4);
+		omega5 = n24 * (omega1 - two)
+			   * (four * omega1 * omega1 + omega1 * omega2 * (n18 - n13 * omega1) + omega2 * omega2 * (two + omega1 * (six * omega1 - n11)))
+			   / (sixteen * omega1 * omega1 * (omega1 - six) - two * omega1 * omega2 * (n216 + five * omega1 * (nine * omega1 - n46))
+				  + omega2 * omega2 * (omega1 * (three * omega1 - n10) * (n15 * omega1 - n28) - n48));
+		w111 = limited_rate(omega5, C[1][1][1], rho, lambda5);
+		A = (four * omega1 * omega1 + two * omega1 * omega2 * (omega1 - six) + omega2 * omega2 * (omega1 * (n10 - three * omega1) - four)) / (omega1 - omega2)
+		  / (omega2 * (two + three * omega1) - eight * omega1);
+		B = (four * omega1 * omega2 * (nine * omega1 - sixteen) - four * omega1 * omega1 - two * omega2 * omega2 * (two + nine * omega1 * (omega1 - two))) / three
+		  / (omega1 - omega2) / (omega2 * (two + three * omega1) - eight * omega1);
+	}
+	R Dxu = 0, Dyv = 0, Dzw = 0, DxvDyu = 0, DxwDzu = 0, DywDzv = 0;
+	if (ANTIALIAS) {  // col_cum.h:215-229
+		const R n3o2 = (R) 1.5;
+		Dxu = -omega1 / two / rho * (two * C[2][0][0] - C[0][2][0] - C[0][0][2]) - omega2 / two / rho * (C[2][0][0] + C[0][2][0] + C[0][0][2] - (-one + rho));
+		Dyv = Dxu + n3o2 * omega1 / rho * (C[2][0][0] - C[0][2][0]);
+		Dzw = Dxu + n3o2 * omega1 / rho * (C[2][0][0] - C[0][0][2]);
+		DxvDyu = -three * omega1 / rho * C[1][1][0];
+		DxwDzu = -three * omega1 / rho * C[1][0][1];
+		DywDzv = -three * omega1 / rho * C[0][1][1];
+	}
 
 	R S[3][3][3];  // post-collision cumulants (Cs_*), then central moments (ks_*)
 	S[1][1][0] = (one - omega1) * C[1][1][0];
@@ -421,14 +466,31 @@ void collide_cum(Cell<R, 27>& K)
 	S[2][0][0] = third * (r33 + r34 + r35);
 	S[0][2][0] = third * (-two * r33 + r34 + r35);
 	S[0][0][2] = third * (r33 - two * r34 + r35);
-	// Eq 36-41 (col_cum.h:278-285)
-	S[1][2][0] = (-C[1][0][2] - C[1][2][0]) * omega3 * half + (C[1][0][2] - C[1][2][0]) * omega4 * half + C[1][2][0];
-	S[1][0][2] = (-C[1][0][2] - C[1][2][0]) * omega3 * half + (-C[1][0][2] + C[1][2][0]) * omega4 * half + C[1][0][2];
-	S[2][1][0] = (-C[0][1][2] - C[2][1][0]) * omega3 * half + (C[0][1][2] - C[2][1][0]) * omega4 * half + C[2][1][0];
-	S[0][1][2] = (-C[0][1][2] - C[2][1][0]) * omega3 * half + (-C[0][1][2] + C[2][1][0]) * omega4 * half + C[0][1][2];
-	S[0][2][1] = (-C[0][2][1] - C[2][0][1]) * omega3 * half + (-C[0][2][1] + C[2][0][1]) * omega4 * half + C[0][2][1];
-	S[2][0][1] = (-C[0][2][1] - C[2][0][1]) * omega3 * half + (C[0][2][1] - C[2][0][1]) * omega4 * half + C[2][0][1];
-	S[1][1][1] = (one - omega5) * C[1][1][1];  // Eq 42
+	if (G2017) {  // limited rates, col_cum.h:258-276
+		const R e117 = (one - w120p102) * (C[1][2][0] + C[1][0][2]);
+		const R e118 = (one - w210p012) * (C[2][1][0] + C[0][1][2]);
+		const R e119 = (one - w201p021) * (C[2][0][1] + C[0][2][1]);
+		const R e120 = (one - w120m102) * (C[1][2][0] - C[1][0][2]);
+		const R e121 = (one - w210m012) * (C[2][1][0] - C[0][1][2]);
+		const R e122 = (one - w201m021) * (C[2][0][1] - C[0][2][1]);
+		S[1][2][0] = half * (e120 + e117);
+		S[1][0][2] = half * (-e120 + e117);
+		S[2][1][0] = half * (e121 + e118);
+		S[0][1][2] = half * (-e121 + e118);
+		S[0][2][1] = half * (-e122 + e119);
+		S[2][0][1] = half * (e122 + e119);
+		S[1][1][1] = (one - w111) * C[1][1][1];
+	}
+	else {
+		// Eq 36-41 (col_cum.h:278-285)
+		S[1][2][0] = (-C[1][0][2] - C[1][2][0]) * omega3 * half + (C[1][0][2] - C[1][2][0]) * omega4 * half + C[1][2][0];
+		S[1][0][2] = (-C[1][0][2] - C[1][2][0]) * omega3 * half + (-C[1][0][2] + C[1][2][0]) * omega4 * half + C[1][0][2];
+		S[2][1][0] = (-C[0][1][2] - C[2][1][0]) * omega3 * half + (C[0][1][2] - C[2][1][0]) * omega4 * half + C[2][1][0];
+		S[0][1][2] = (-C[0][1][2] - C[2][1][0]) * omega3 * half + (-C[0][1][2] + C[2][1][0]) * omega4 * half + C[0][1][2];
+		S[0][2][1] = (-C[0][2][1] - C[2][0][1]) * omega3 * half + (-C[0][2][1] + C[2][0][1]) * omega4 * half + C[0][2][1];
+		S[2][0][1] = (-C[0][2][1] - C[2][0][1]) * omega3 * half + (C[0][2][1] - C[2][0][1]) * omega4 * half + C[2][0][1];
+		S[1][1][1] = (one - omega5) * C[1][1][1];  // Eq 42
+	}
 	// Eq 43-45 (col_cum.h:288-297)
 	const R r43 = n2o3 * (one / omega1 - half) * omega6 * A * rho * (Dxu - two * Dyv + Dzw) + (one - omega6) * (C[2][2][0] - two * C[2][0][2] + C[0][2][2]);
 	const R r44 = n2o3 * (one / omega1 - half) * omega6 * A * rho * (Dxu + Dyv - two * Dzw) + (one - omega6) * (C[2][2][0] + C[2][0][2] - two * C[0][2][2]);
@@ -672,6 +734,9 @@ void collide(Cell<R, 27>& K, const oracle_desc& d)
 		case ORC_COLL_MRT_LES: collide_mrt27(K); break;
 		case ORC_COLL_CLBM: collide_clbm27(K); break;
 		case ORC_COLL_SRT_MODIF_FORCE: collide_srt_modif27(K, d.eq); break;
+		case ORC_COLL_CUM_2017: collide_cum<R, true, false>(K); break;
+		case ORC_COLL_CUM_ANTIALIAS: collide_cum<R, false, true>(K); break;
+		case ORC_COLL_CUM_2017_ANTIALIAS: collide_cum<R, true, true>(K); break;
 	}
 }
 // D3Q19 (unpinned): SRT and MRT_LES with the formulas of col_srt.h / col_mrt.h over 19 velocities
@@ -1165,7 +1230,8 @@ bool supported(const oracle_desc* d)
 	if (d->streaming != ORC_STREAM_AB && d->streaming != ORC_STREAM_AA)
 		return false;
 	if (d->lattice == ORC_D3Q27)
-		return d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE && (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM);
+		return ((d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE) || (d->coll >= ORC_COLL_CUM_2017 && d->coll <= ORC_COLL_CUM_2017_ANTIALIAS))
+			&& (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM);
 	if (d->lattice == ORC_D2Q9)
 		return (d->coll == ORC_COLL_SRT || d->coll == ORC_COLL_CLBM) && d->eq == ORC_EQ_STD && d->Z == 1;
 	if (d->lattice == ORC_D3Q19)  // no reference implementation: PARITY UNPINNED (see L19)

@@ -19,7 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 D3Q27, D2Q9, D3Q19 = 0, 1, 2
-CUM, SRT, BGK, MRT_LES, CLBM, SRT_MODIF_FORCE, SRT_WELL, BGK_WELL, CLBM_WELL, CUM_WELL = range(10)
+CUM, SRT, BGK, MRT_LES, CLBM, SRT_MODIF_FORCE, SRT_WELL, BGK_WELL, CLBM_WELL, CUM_WELL, CUM_2017, CUM_ANTIALIAS, CUM_2017_ANTIALIAS = range(13)
 EQ_STD, EQ_INV_CUM, EQ_WELL = 0, 1, 2
 AB, AA = 0, 1
 MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN = 0, 1, 2

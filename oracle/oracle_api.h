@@ -33,7 +33,10 @@ enum {
 	ORC_COLL_SRT_WELL = 6,
 	ORC_COLL_BGK_WELL = 7,
 	ORC_COLL_CLBM_WELL = 8,
-	ORC_COLL_CUM_WELL = 9
+	ORC_COLL_CUM_WELL = 9,
+	ORC_COLL_CUM_2017 = 10,			 /* D3Q27_CUM compiled with -DUSE_GEIER_CUM_2017 (defs.h:254) */
+	ORC_COLL_CUM_ANTIALIAS = 11,	 /* ... with -DUSE_GEIER_CUM_ANTIALIAS (defs.h:255) */
+	ORC_COLL_CUM_2017_ANTIALIAS = 12 /* ... with both */
 };
 enum { ORC_EQ_STD = 0, ORC_EQ_INV_CUM = 1, ORC_EQ_WELL = 2 };
 enum { ORC_STREAM_AB = 0, ORC_STREAM_AA = 1 };

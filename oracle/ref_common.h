@@ -255,4 +255,7 @@ int ref_dispatch_d3q27_bgk(const RefCall& c);
 int ref_dispatch_d3q27_mrt(const RefCall& c);
 int ref_dispatch_d3q27_clbm(const RefCall& c);
 int ref_dispatch_d3q27_srtmf(const RefCall& c);
+int ref_dispatch_d3q27_cum2017(const RefCall& c);
+int ref_dispatch_d3q27_cumaa(const RefCall& c);
+int ref_dispatch_d3q27_cum2017aa(const RefCall& c);
 int ref_dispatch_d2q9(const RefCall& c);

@@ -16,6 +16,12 @@ static int ref_dispatch(const RefCall& c)
 		return r;
 	if ((r = ref_dispatch_d3q27_srtmf(c)) != -1)
 		return r;
+	if ((r = ref_dispatch_d3q27_cum2017(c)) != -1)
+		return r;
+	if ((r = ref_dispatch_d3q27_cumaa(c)) != -1)
+		return r;
+	if ((r = ref_dispatch_d3q27_cum2017aa(c)) != -1)
+		return r;
 	if ((r = ref_dispatch_d2q9(c)) != -1)
 		return r;
 	return -1;

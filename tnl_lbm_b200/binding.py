@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "liblbmx.so")
 # selectors (include/lbmx.h)
 D3Q27, D2Q9, D3Q19 = 0, 1, 2
 CUM, SRT, BGK, MRT_LES, CLBM, SRT_MODIF_FORCE = 0, 1, 2, 3, 4, 5
+CUM_2017, CUM_ANTIALIAS, CUM_2017_ANTIALIAS = 10, 11, 12  # D3Q27_CUM built with the switches of defs.h:254-255
 EQ_STD, EQ_INV_CUM = 0, 1
 AB, AA = 0, 1
 MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN = 0, 1, 2

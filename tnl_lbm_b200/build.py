@@ -32,6 +32,9 @@ FAMILIES = [
     ("d3q27_mrt", "D3Q27", "K_MRT"),
     ("d3q27_clbm", "D3Q27", "K_CLBM"),
     ("d3q27_srtmf", "D3Q27", "K_SRT_MF"),
+    ("d3q27_cum2017", "D3Q27", "K_CUM_2017"),
+    ("d3q27_cumaa", "D3Q27", "K_CUM_AALIAS"),
+    ("d3q27_cum2017aa", "D3Q27", "K_CUM_2017_AALIAS"),
     ("d3q19_srt", "D3Q19", "K_SRT"),
     ("d3q19_mrt", "D3Q19", "K_MRT"),
     ("d2q9_srt", "D2Q9", "K_SRT"),

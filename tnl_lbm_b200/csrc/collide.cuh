@@ -608,13 +608,19 @@ LBMX_D void collide_mrt(R (&f)[19], const Phys<R>& P, R rho, R vx, R vy, R vz)
 // --------------------------------------------------------------------------------------------------------------------
 // operator tags: what COLL means for a kernel instantiation
 // --------------------------------------------------------------------------------------------------------------------
-enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 /* D2Q9_CLBM or D3Q27_CLBM, by lattice */, K_SRT_MF = 5 };
+enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 /* D2Q9_CLBM or D3Q27_CLBM, by lattice */, K_SRT_MF = 5, K_CUM_2017 = 10, K_CUM_AALIAS = 11, K_CUM_2017_AALIAS = 12 /* D3Q27_CUM built with the switches of defs.h:254-255 */ };
 
 template <int KIND, typename R>
 LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
 	if constexpr (KIND == K_CLBM)
 		ext::collide_clbm<! kStrict>(f, P, rho, vx, vy, vz);
+	else if constexpr (KIND == K_CUM_2017)
+		strict::collide_cum<true, false>(f, P, rho, vx, vy, vz);
+	else if constexpr (KIND == K_CUM_AALIAS)
+		strict::collide_cum<false, true>(f, P, rho, vx, vy, vz);
+	else if constexpr (KIND == K_CUM_2017_AALIAS)
+		strict::collide_cum<true, true>(f, P, rho, vx, vy, vz);
 	else if constexpr (KIND == K_SRT_MF) {
 		R feq[27];
 		equilibrium(feq, eqkind, rho, vx, vy, vz);

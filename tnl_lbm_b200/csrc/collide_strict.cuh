@@ -79,16 +79,28 @@ LBMX_D void from_central(R& lo, R& mid, R& hi, R v)
 	hi = (k0 * (v * v + v) + k1 * (two * v + one) + k2) * half;
 }
 
-// d3q27/col_cum.h:14-485, default build (omega2..omega10 = 1, A = B = 0, no velocity-derivative terms), evaluated the way the
-// reference evaluates it: all 27 central moments, and the third-order cumulants keep the rounding residue that
-// (-a-b)/2 + (a-b)/2 + b leaves behind (col_cum.h:278-285) -- dropping it changes single bits, and a single bit is enough for two
-// fp32 runs to drift apart like two different roundings.  Only terms that are exactly +-0 for finite inputs are left out:
-// (1 - omega_n) * C with omega_n = 1, and every product with A, B or a velocity derivative.
+// rate limiter of the 2017 parametrisation (col_cum.h:183-197): w + (1 - w) * fabs(x) / (rho * lambda + fabs(x)).  The reference's
+// unqualified fabs() is ::fabs(double) in the host build: for dreal = float everything downstream of it is evaluated in double and
+// rounded once when stored (like sqrt() in col_mrt.h).
 template <typename R>
-LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+LBMX_D R limited_rate(R w, R x, R rho, R lambda)
+{
+	const double ax = fabs(double(x));
+	return R(double(w) + double(R(1) - w) * ax / (double(rho * lambda) + ax));
+}
+
+// d3q27/col_cum.h:14-485, evaluated the way the reference evaluates it: all 27 central moments, and the third-order cumulants
+// keep the rounding residue that (-a-b)/2 + (a-b)/2 + b leaves behind (col_cum.h:278-285) -- dropping it changes single bits, and a
+// single bit is enough for two fp32 runs to drift apart like two different roundings.  Only terms that are exactly +-0 for finite
+// inputs are left out: (1 - omega_n) * C with omega_n = 1, and products with A, B or a velocity derivative that is a constant 0.
+//   G2017     = the reference compiled with -DUSE_GEIER_CUM_2017 (defs.h:254): parametrised omega3..5 with limiter, A and B
+//   ANTIALIAS = ... with -DUSE_GEIER_CUM_ANTIALIAS (defs.h:255): velocity-derivative terms of Eq 33-35, 43-48
+// Default build of the reference: both off (omega2..omega10 = 1, A = B = 0).
+template <bool G2017 = false, bool ANTIALIAS = false, typename R, typename PHYS>
+LBMX_D void collide_cum(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
-	const R one = R(1), two = R(2), four = R(4), half = R(0.5), third = R(1.0 / 3.0);
+	const R one = R(1), two = R(2), three = R(3), four = R(4), half = R(0.5), third = R(1.0 / 3.0);
 	R m[3][3][3];  // index 0,1,2 = velocity sign -,0,+ before an axis is transformed, moment order 0,1,2 after
 #pragma unroll
 	for (int a = 0; a < 3; a++)
@@ -113,8 +125,10 @@ LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 		for (int c = 0; c < 3; c++)
 			to_central(m[0][b][c], m[1][b][c], m[2][b][c], vx);
 
-	const R omega1 = one / (R(3) * P.nu + half);
+	const R omega1 = one / (three * P.nu + half);
+	const R omega2 = one;
 	const R keep = one - omega1;
+	R A = R(0), B = R(0);
 	R S[3][3][3];
 	S[0][0][0] = m[0][0][0];
 	S[1][0][0] = -m[1][0][0];  // col_cum.h:341-345
@@ -123,30 +137,85 @@ LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 	S[1][1][0] = keep * m[1][1][0];
 	S[1][0][1] = keep * m[1][0][1];
 	S[0][1][1] = keep * m[0][1][1];
-	const R r33 = keep * (m[2][0][0] - m[0][2][0]), r34 = keep * (m[2][0][0] - m[0][0][2]), r35 = m[0][0][0];
+	// cumulants of order <= 3 equal the central moments (col_cum.h:151-171 only changes orders 4-6, which relax to 0 here)
+	if constexpr (G2017) {	// col_cum.h:177-208, 258-276
+		const R five = 5, six = 6, seven = 7, eight = 8, nine = 9, n10 = 10, n11 = 11, n13 = 13, n15 = 15, n16 = 16, n18 = 18, n24 = 24, n26 = 26, n28 = 28,
+				n42 = 42, n46 = 46, n48 = 48, n56 = 56, n216 = 216;
+		const R lambda3 = R(0.01), lambda4 = R(0.01), lambda5 = R(0.01);
+		const R omega3 = eight * (omega1 - two) * (omega2 * (three * omega1 - one) - five * omega1)
+					   / (eight * (five - two * omega1) * omega1 + omega2 * (eight + omega1 * (nine * omega1 - n26)));
+		const R omega4 = eight * (omega1 - two) * (omega1 + omega2 * (three * omega1 - seven)) / (omega2 * (n56 - n42 * omega1 + nine * omega1 * omega1) - eight * omega1);
+		const R omega5 = n24 * (omega1 - two)
+					   * (four * omega1 * omega1 + omega1 * omega2 * (n18 - n13 * omega1) + omega2 * omega2 * (two + omega1 * (six * omega1 - n11)))
+					   / (n16 * omega1 * omega1 * (omega1 - six) - two * omega1 * omega2 * (n216 + five * omega1 * (nine * omega1 - n46))
+						  + omega2 * omega2 * (omega1 * (three * omega1 - n10) * (n15 * omega1 - n28) - n48));
+		A = (four * omega1 * omega1 + two * omega1 * omega2 * (omega1 - six) + omega2 * omega2 * (omega1 * (n10 - three * omega1) - four)) / (omega1 - omega2)
+		  / (omega2 * (two + three * omega1) - eight * omega1);
+		B = (four * omega1 * omega2 * (nine * omega1 - n16) - four * omega1 * omega1 - two * omega2 * omega2 * (two + nine * omega1 * (omega1 - two))) / three
+		  / (omega1 - omega2) / (omega2 * (two + three * omega1) - eight * omega1);
+		const R e117 = (one - limited_rate(omega3, m[1][2][0] + m[1][0][2], rho, lambda3)) * (m[1][2][0] + m[1][0][2]);
+		const R e118 = (one - limited_rate(omega3, m[2][1][0] + m[0][1][2], rho, lambda3)) * (m[2][1][0] + m[0][1][2]);
+		const R e119 = (one - limited_rate(omega3, m[2][0][1] + m[0][2][1], rho, lambda3)) * (m[2][0][1] + m[0][2][1]);
+		const R e120 = (one - limited_rate(omega4, m[1][2][0] - m[1][0][2], rho, lambda4)) * (m[1][2][0] - m[1][0][2]);
+		const R e121 = (one - limited_rate(omega4, m[2][1][0] - m[0][1][2], rho, lambda4)) * (m[2][1][0] - m[0][1][2]);
+		const R e122 = (one - limited_rate(omega4, m[2][0][1] - m[0][2][1], rho, lambda4)) * (m[2][0][1] - m[0][2][1]);
+		S[1][2][0] = half * (e120 + e117);
+		S[1][0][2] = half * (-e120 + e117);
+		S[2][1][0] = half * (e121 + e118);
+		S[0][1][2] = half * (-e121 + e118);
+		S[0][2][1] = half * (-e122 + e119);
+		S[2][0][1] = half * (e122 + e119);
+		S[1][1][1] = (one - limited_rate(omega5, m[1][1][1], rho, lambda5)) * m[1][1][1];
+	}
+	else {	// Eq 36-41 with omega3 = omega4 = 1 (x * 1 is exact), Eq 42 with omega5 = 1
+		S[1][2][0] = (-m[1][0][2] - m[1][2][0]) * half + (m[1][0][2] - m[1][2][0]) * half + m[1][2][0];
+		S[1][0][2] = (-m[1][0][2] - m[1][2][0]) * half + (-m[1][0][2] + m[1][2][0]) * half + m[1][0][2];
+		S[2][1][0] = (-m[0][1][2] - m[2][1][0]) * half + (m[0][1][2] - m[2][1][0]) * half + m[2][1][0];
+		S[0][1][2] = (-m[0][1][2] - m[2][1][0]) * half + (-m[0][1][2] + m[2][1][0]) * half + m[0][1][2];
+		S[0][2][1] = (-m[0][2][1] - m[2][0][1]) * half + (-m[0][2][1] + m[2][0][1]) * half + m[0][2][1];
+		S[2][0][1] = (-m[0][2][1] - m[2][0][1]) * half + (m[0][2][1] - m[2][0][1]) * half + m[2][0][1];
+		S[1][1][1] = R(0);
+	}
+	R r33 = keep * (m[2][0][0] - m[0][2][0]), r34 = keep * (m[2][0][0] - m[0][0][2]), r35 = m[0][0][0];
+	R c220 = R(0), c202 = R(0), c022 = R(0), c211 = R(0), c121 = R(0), c112 = R(0);	 // post-collision cumulants of order 4
+	if constexpr (ANTIALIAS) {	// col_cum.h:215-229 and the derivative terms of Eq 33-35, 43-48
+		const R n3o2 = R(1.5), n2o3 = R(2.0 / 3.0), n4o3 = R(4.0 / 3.0);
+		const R Dxu = -omega1 / two / rho * (two * m[2][0][0] - m[0][2][0] - m[0][0][2]) - omega2 / two / rho * (m[2][0][0] + m[0][2][0] + m[0][0][2] - (-one + rho));
+		const R Dyv = Dxu + n3o2 * omega1 / rho * (m[2][0][0] - m[0][2][0]);
+		const R Dzw = Dxu + n3o2 * omega1 / rho * (m[2][0][0] - m[0][0][2]);
+		r33 = r33 - three * rho * (one - omega1 * half) * (vx * vx * Dxu - vy * vy * Dyv);
+		r34 = r34 - three * rho * (one - omega1 * half) * (vx * vx * Dxu - vz * vz * Dzw);
+		r35 = r35 - three * rho * (one - omega2 / two) * (vx * vx * Dxu + vy * vy * Dyv + vz * vz * Dzw);
+		if constexpr (G2017) {	// A, B != 0 only in the 2017 parametrisation
+			const R DxvDyu = -three * omega1 / rho * m[1][1][0];
+			const R DxwDzu = -three * omega1 / rho * m[1][0][1];
+			const R DywDzv = -three * omega1 / rho * m[0][1][1];
+			const R e43 = n2o3 * (one / omega1 - half) * A * rho * (Dxu - two * Dyv + Dzw);
+			const R e44 = n2o3 * (one / omega1 - half) * A * rho * (Dxu + Dyv - two * Dzw);
+			const R e45 = -n4o3 * (one / omega1 - half) * A * rho * (Dxu + Dyv + Dzw);
+			c220 = third * (e43 + e44 + e45);
+			c202 = third * (-e43 + e45);
+			c022 = third * (-e44 + e45);
+			c211 = -third * (one / omega1 - half) * B * rho * DywDzv;
+			c121 = -third * (one / omega1 - half) * B * rho * DxwDzu;
+			c112 = -third * (one / omega1 - half) * B * rho * DxvDyu;
+		}
+	}
 	S[2][0][0] = third * (r33 + r34 + r35);
 	S[0][2][0] = third * (-two * r33 + r34 + r35);
 	S[0][0][2] = third * (r33 - two * r34 + r35);
-	// Eq 36-41 with omega3 = omega4 = 1 (x * 1 is exact)
-	S[1][2][0] = (-m[1][0][2] - m[1][2][0]) * half + (m[1][0][2] - m[1][2][0]) * half + m[1][2][0];
-	S[1][0][2] = (-m[1][0][2] - m[1][2][0]) * half + (-m[1][0][2] + m[1][2][0]) * half + m[1][0][2];
-	S[2][1][0] = (-m[0][1][2] - m[2][1][0]) * half + (m[0][1][2] - m[2][1][0]) * half + m[2][1][0];
-	S[0][1][2] = (-m[0][1][2] - m[2][1][0]) * half + (-m[0][1][2] + m[2][1][0]) * half + m[0][1][2];
-	S[0][2][1] = (-m[0][2][1] - m[2][0][1]) * half + (-m[0][2][1] + m[2][0][1]) * half + m[0][2][1];
-	S[2][0][1] = (-m[0][2][1] - m[2][0][1]) * half + (m[0][2][1] - m[2][0][1]) * half + m[2][0][1];
-	// Eq G2015(81)-(84), col_cum.h:312-338; the post-collision cumulants of order >= 4 and Cs_111 are +-0
+	// Eq G2015(81)-(84), col_cum.h:312-338; the post-collision cumulants of order 5 and 6 are +-0
 #define s(a, b, c) S[a][b][c]
-	S[2][1][1] = (s(2, 0, 0) * s(0, 1, 1) + two * s(1, 0, 1) * s(1, 1, 0)) / rho;
-	S[1][2][1] = (s(0, 2, 0) * s(1, 0, 1) + two * s(1, 1, 0) * s(0, 1, 1)) / rho;
-	S[1][1][2] = (s(0, 0, 2) * s(1, 1, 0) + two * s(0, 1, 1) * s(1, 0, 1)) / rho;
-	S[2][2][0] = (s(0, 2, 0) * s(2, 0, 0) + two * s(1, 1, 0) * s(1, 1, 0)) / rho;
-	S[0][2][2] = (s(0, 0, 2) * s(0, 2, 0) + two * s(0, 1, 1) * s(0, 1, 1)) / rho;
-	S[2][0][2] = (s(2, 0, 0) * s(0, 0, 2) + two * s(1, 0, 1) * s(1, 0, 1)) / rho;
-	S[1][2][2] = (s(0, 2, 0) * s(1, 0, 2) + s(0, 0, 2) * s(1, 2, 0) + two * (s(1, 1, 0) * s(0, 1, 2) + s(1, 0, 1) * s(0, 2, 1))) / rho;
-	S[2][1][2] = (s(0, 0, 2) * s(2, 1, 0) + s(2, 0, 0) * s(0, 1, 2) + two * (s(0, 1, 1) * s(2, 0, 1) + s(1, 1, 0) * s(1, 0, 2))) / rho;
-	S[2][2][1] = (s(2, 0, 0) * s(0, 2, 1) + s(0, 2, 0) * s(2, 0, 1) + two * (s(1, 0, 1) * s(1, 2, 0) + s(0, 1, 1) * s(2, 1, 0))) / rho;
-	S[1][1][1] = R(0);
-	S[2][2][2] = (s(2, 0, 0) * s(0, 2, 2) + s(0, 2, 0) * s(2, 0, 2) + s(0, 0, 2) * s(2, 2, 0)
+	S[2][1][1] = c211 + (s(2, 0, 0) * s(0, 1, 1) + two * s(1, 0, 1) * s(1, 1, 0)) / rho;
+	S[1][2][1] = c121 + (s(0, 2, 0) * s(1, 0, 1) + two * s(1, 1, 0) * s(0, 1, 1)) / rho;
+	S[1][1][2] = c112 + (s(0, 0, 2) * s(1, 1, 0) + two * s(0, 1, 1) * s(1, 0, 1)) / rho;
+	S[2][2][0] = c220 + (s(0, 2, 0) * s(2, 0, 0) + two * s(1, 1, 0) * s(1, 1, 0)) / rho;
+	S[0][2][2] = c022 + (s(0, 0, 2) * s(0, 2, 0) + two * s(0, 1, 1) * s(0, 1, 1)) / rho;
+	S[2][0][2] = c202 + (s(2, 0, 0) * s(0, 0, 2) + two * s(1, 0, 1) * s(1, 0, 1)) / rho;
+	S[1][2][2] = (s(0, 2, 0) * s(1, 0, 2) + s(0, 0, 2) * s(1, 2, 0) + four * s(0, 1, 1) * s(1, 1, 1) + two * (s(1, 1, 0) * s(0, 1, 2) + s(1, 0, 1) * s(0, 2, 1))) / rho;
+	S[2][1][2] = (s(0, 0, 2) * s(2, 1, 0) + s(2, 0, 0) * s(0, 1, 2) + four * s(1, 0, 1) * s(1, 1, 1) + two * (s(0, 1, 1) * s(2, 0, 1) + s(1, 1, 0) * s(1, 0, 2))) / rho;
+	S[2][2][1] = (s(2, 0, 0) * s(0, 2, 1) + s(0, 2, 0) * s(2, 0, 1) + four * s(1, 1, 0) * s(1, 1, 1) + two * (s(1, 0, 1) * s(1, 2, 0) + s(0, 1, 1) * s(2, 1, 0))) / rho;
+	S[2][2][2] = (four * s(1, 1, 1) * s(1, 1, 1) + s(2, 0, 0) * s(0, 2, 2) + s(0, 2, 0) * s(2, 0, 2) + s(0, 0, 2) * s(2, 2, 0)
 				  + four * (s(0, 1, 1) * s(2, 1, 1) + s(1, 0, 1) * s(1, 2, 1) + s(1, 1, 0) * s(1, 1, 2))
 				  + two * (s(1, 2, 0) * s(1, 0, 2) + s(2, 1, 0) * s(0, 1, 2) + s(2, 0, 1) * s(0, 2, 1)))
 					 / rho

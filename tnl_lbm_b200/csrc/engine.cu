@@ -411,6 +411,9 @@ bool pick_kernels(lbmx_engine* e)
 				case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt_strict(e->kd) : get_kernels_d3q27_mrt_strict(e->kf);
 				case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm_strict(e->kd) : get_kernels_d3q27_clbm_strict(e->kf);
 				case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf_strict(e->kd) : get_kernels_d3q27_srtmf_strict(e->kf);
+				case LBMX_COLL_CUM_2017: return e->f64() ? get_kernels_d3q27_cum2017_strict(e->kd) : get_kernels_d3q27_cum2017_strict(e->kf);
+				case LBMX_COLL_CUM_ANTIALIAS: return e->f64() ? get_kernels_d3q27_cumaa_strict(e->kd) : get_kernels_d3q27_cumaa_strict(e->kf);
+				case LBMX_COLL_CUM_2017_ANTIALIAS: return e->f64() ? get_kernels_d3q27_cum2017aa_strict(e->kd) : get_kernels_d3q27_cum2017aa_strict(e->kf);
 			}
 		}
 		else if (d.lattice == LBMX_D2Q9) {
@@ -429,6 +432,9 @@ bool pick_kernels(lbmx_engine* e)
 			case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt(e->kd) : get_kernels_d3q27_mrt(e->kf);
 			case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm(e->kd) : get_kernels_d3q27_clbm(e->kf);
 			case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf(e->kd) : get_kernels_d3q27_srtmf(e->kf);
+			case LBMX_COLL_CUM_2017: return e->f64() ? get_kernels_d3q27_cum2017(e->kd) : get_kernels_d3q27_cum2017(e->kf);
+			case LBMX_COLL_CUM_ANTIALIAS: return e->f64() ? get_kernels_d3q27_cumaa(e->kd) : get_kernels_d3q27_cumaa(e->kf);
+			case LBMX_COLL_CUM_2017_ANTIALIAS: return e->f64() ? get_kernels_d3q27_cum2017aa(e->kd) : get_kernels_d3q27_cum2017aa(e->kf);
 		}
 	}
 	else if (d.lattice == LBMX_D3Q19) {

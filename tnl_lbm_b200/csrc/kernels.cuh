@@ -663,6 +663,18 @@ bool get_kernels_d3q27_bgk(StepKernels<float>&);
 bool get_kernels_d3q27_bgk(StepKernels<double>&);
 bool get_kernels_d3q27_mrt(StepKernels<float>&);
 bool get_kernels_d3q27_mrt(StepKernels<double>&);
+bool get_kernels_d3q27_cum2017(StepKernels<float>&);
+bool get_kernels_d3q27_cum2017(StepKernels<double>&);
+bool get_kernels_d3q27_cum2017_strict(StepKernels<float>&);
+bool get_kernels_d3q27_cum2017_strict(StepKernels<double>&);
+bool get_kernels_d3q27_cumaa(StepKernels<float>&);
+bool get_kernels_d3q27_cumaa(StepKernels<double>&);
+bool get_kernels_d3q27_cumaa_strict(StepKernels<float>&);
+bool get_kernels_d3q27_cumaa_strict(StepKernels<double>&);
+bool get_kernels_d3q27_cum2017aa(StepKernels<float>&);
+bool get_kernels_d3q27_cum2017aa(StepKernels<double>&);
+bool get_kernels_d3q27_cum2017aa_strict(StepKernels<float>&);
+bool get_kernels_d3q27_cum2017aa_strict(StepKernels<double>&);
 bool get_kernels_d3q27_clbm(StepKernels<float>&);
 bool get_kernels_d3q27_clbm(StepKernels<double>&);
 bool get_kernels_d3q27_srtmf(StepKernels<float>&);

@@ -235,7 +235,16 @@ struct D2Q9_EQ { static constexpr int lbmx_eq = LBMX_EQ_STD; };
 		static constexpr const char* id = ID;                     \
 		static constexpr int lbmx_coll = COLL;                    \
 	};
+// the reference's cumulant switches (defs.h:254-255) select a kernel family instead of an #ifdef branch
+#if defined(USE_GEIER_CUM_2017) && defined(USE_GEIER_CUM_ANTIALIAS)
+LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM_2017_ANTIALIAS, "CUM")
+#elif defined(USE_GEIER_CUM_2017)
+LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM_2017, "CUM")
+#elif defined(USE_GEIER_CUM_ANTIALIAS)
+LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM_ANTIALIAS, "CUM")
+#else
 LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM, "CUM")
+#endif
 LBMX_COLL_TAG(D3Q27_SRT, D3Q27_EQ, LBMX_COLL_SRT, "SRT")
 LBMX_COLL_TAG(D3Q27_BGK, D3Q27_EQ, LBMX_COLL_BGK, "BGK")
 LBMX_COLL_TAG(D3Q27_MRT, D3Q27_EQ, LBMX_COLL_MRT_LES, "MRT_LES")

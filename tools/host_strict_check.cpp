@@ -62,5 +62,11 @@ int main()
 	r |= run<double, K_CLBM>(ORC_COLL_CLBM, ORC_EQ_STD, ORC_F64);
 	r |= run<float, K_SRT_MF>(ORC_COLL_SRT_MODIF_FORCE, ORC_EQ_INV_CUM, ORC_F32);
 	r |= run<double, K_SRT_MF>(ORC_COLL_SRT_MODIF_FORCE, ORC_EQ_STD, ORC_F64);
+	r |= run<float, K_CUM_2017>(ORC_COLL_CUM_2017, ORC_EQ_INV_CUM, ORC_F32);
+	r |= run<double, K_CUM_2017>(ORC_COLL_CUM_2017, ORC_EQ_INV_CUM, ORC_F64);
+	r |= run<float, K_CUM_AALIAS>(ORC_COLL_CUM_ANTIALIAS, ORC_EQ_INV_CUM, ORC_F32);
+	r |= run<double, K_CUM_AALIAS>(ORC_COLL_CUM_ANTIALIAS, ORC_EQ_INV_CUM, ORC_F64);
+	r |= run<float, K_CUM_2017_AALIAS>(ORC_COLL_CUM_2017_ANTIALIAS, ORC_EQ_INV_CUM, ORC_F32);
+	r |= run<double, K_CUM_2017_AALIAS>(ORC_COLL_CUM_2017_ANTIALIAS, ORC_EQ_INV_CUM, ORC_F64);
 	return r;
 }
