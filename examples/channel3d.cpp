@@ -126,11 +126,15 @@ int run(int X, int Y, int Z, int steps, const char* prefix, int halt, bool dump)
 	auto& block = state.nse.blocks.front();
 	state.nse.copyMacroToHost();
 	state.nse.copyMapToHost();
-	std::ofstream(std::string(prefix) + ".map", std::ios::binary).write((const char*) block.hmap.v.data(), block.hmap.v.size() * sizeof(short));
-	std::ofstream(std::string(prefix) + ".macro", std::ios::binary)
-		.write((const char*) block.hmacro.v.data(), block.hmacro.v.size() * sizeof(typename TRAITS::dreal));
-	std::printf("iterations=%d mass=%.12f lbmViscosity=%.17g inflow_vx=%.17g\n", state.nse.iterations, state.probed_mass, (double) block.data.lbmViscosity,
-				(double) block.data.inflow_vx);
+	// one piece per rank (x-slab [offset.x, offset.x + local.x) of the global lattice), named like the single-process output when alone
+	const std::string piece = std::string(prefix) + (state.nse.nproc > 1 ? ".rank" + std::to_string(state.nse.rank) : "");
+	std::ofstream(piece + ".map", std::ios::binary).write((const char*) block.hmap.v.data(), block.hmap.v.size() * sizeof(short));
+	std::ofstream(piece + ".macro", std::ios::binary).write((const char*) block.hmacro.v.data(), block.hmacro.v.size() * sizeof(typename TRAITS::dreal));
+	const double mass = TNL::MPI::reduce(state.probed_mass, MPI_SUM, MPI_COMM_WORLD);  // as sim_NSE/sim_2.cu:259-260 reduces its error norms
+	if (state.nse.rank == 0)
+		std::printf("iterations=%d mass=%.12f lbmViscosity=%.17g inflow_vx=%.17g ranks=%d\n", state.nse.iterations, mass, (double) block.data.lbmViscosity,
+					(double) block.data.inflow_vx, state.nse.nproc);
+	std::printf("rank %d: x-slab offset %ld size %ld\n", state.nse.rank, (long) block.offset.x(), (long) block.local.x());
 	return 0;
 }
 

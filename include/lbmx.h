@@ -155,6 +155,8 @@ int lbmx_halo_plan(int32_t lattice, int32_t streaming, int64_t iteration, int64_
 /* Engine life cycle ------------------------------------------------------------------------------------------------------ */
 
 /* replaces LBM ctor + LBM_BLOCK::allocateDeviceData (lbm.hpp:6-22, lbm_block.hpp:525-595) */
+/* number of CUDA devices this process sees (a launcher that starts one process per GPU picks device = local rank % count) */
+int lbmx_device_count(int32_t* count);
 int lbmx_create(const lbmx_desc* desc, lbmx_engine** out);
 int lbmx_destroy(lbmx_engine* e);
 int lbmx_get_layout(const lbmx_engine* e, lbmx_layout* out);

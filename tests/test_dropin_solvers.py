@@ -135,7 +135,7 @@ def _read_dump(base):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("exe_name,halt", [("channel3d", 30), ("channel3d_aa", 31)])
+@pytest.mark.parametrize("exe_name,halt", [("channel3d", 30), ("channel3d", 31), ("channel3d_aa", 31)])
 def test_checkpoint_restart_is_bit_identical(exe_name, halt):
     """Stop after `halt` steps, saveState(), start again in the same results directory: loadState() restores map, DFs (ghost planes
     and A-A parity included), macro, iteration and counters, and the run ends bit-identical to an uninterrupted one."""
@@ -246,3 +246,105 @@ int main(int, char** argv)
         assert r.returncode == 0, r.stdout + r.stderr
         assert sorted(os.listdir(d)) == ["LBM_df_0_block_3.bin", "LBM_map_rank_0.bin", "attributes.txt", "variables.txt"]
         assert np.array_equal(np.fromfile(os.path.join(d, "LBM_df_0_block_3.bin")), [1.5, -2.25, 3.0e-300])
+
+
+def test_process_group_collectives_without_mpi():
+    """lbmx_host::World (the stand-in for the reference's MPI ranks): 3 processes found through LBMX_RANK / LBMX_WORLD_SIZE, TCP
+    rendezvous on rank 0, and the TNL::MPI calls the reference's solvers and State use -- reduce (SUM, LOR, MAX), Bcast, Barrier."""
+    src = r'''
+#include "lbm3d/core.h"
+int main(int argc, char** argv)
+{
+	TNLMPI_INIT mpi(argc, argv);
+	const int r = TNL::MPI::GetRank(MPI_COMM_WORLD), n = TNL::MPI::GetSize(MPI_COMM_WORLD);
+	const double sum = TNL::MPI::reduce(1.5 * (r + 1), MPI_SUM, MPI_COMM_WORLD);
+	const bool any = TNL::MPI::reduce(r == 2, MPI_LOR, MPI_COMM_WORLD), all = TNL::MPI::reduce(r == 2, MPI_LAND, MPI_COMM_WORLD);
+	const float mx = TNL::MPI::reduce((float) r, MPI_MAX, MPI_COMM_WORLD);
+	int token[2] = {r == 1 ? 4711 : 0, r == 1 ? -3 : 0};
+	TNL::MPI::Bcast(token, 2, 1, MPI_COMM_WORLD);
+	TNL::MPI::Barrier(MPI_COMM_WORLD);
+	const bool ok = n == 3 && sum == 1.5 * 6 && any && ! all && mx == 2.0f && token[0] == 4711 && token[1] == -3;
+	std::printf("rank %d of %d ok=%d\\n", r, n, (int) ok);
+	return ok ? 0 : 1;
+}
+'''
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    with tempfile.TemporaryDirectory() as tmp:
+        f = os.path.join(tmp, "pg.cpp")
+        open(f, "w").write(src)
+        exe = os.path.join(tmp, "pg")
+        r = subprocess.run(["g++", "-std=c++17", f"-I{ROOT}/tnl_lbm_b200/host", f"-I{ROOT}/include", f"-I{ROOT}/tests/solver_shims", f, "-o", exe,
+                            f"-L{ROOT}/tnl_lbm_b200", "-llbmx", f"-Wl,-rpath,{ROOT}/tnl_lbm_b200"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        procs = []
+        for rank in (2, 0, 1):  # start order must not matter
+            env = dict(os.environ, LBMX_RANK=str(rank), LBMX_WORLD_SIZE="3", LBMX_MASTER_ADDR="127.0.0.1", LBMX_MASTER_PORT=str(port))
+            procs.append(subprocess.Popen([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=120)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+
+
+def _gpu_count():
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe_name", ["channel3d", "channel3d_aa"])
+def test_two_ranks_through_the_host_mirror_equal_one(exe_name):
+    """The same solver binary started as two processes (one per GPU; ranks from the environment, NCCL id over the process group):
+    the two x-slabs assembled equal the single-process result bit for bit (A-B), and a stop / saveState / restart on two ranks
+    reproduces the uninterrupted two-rank run."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    exe = os.path.join(BIN, exe_name)
+    if not os.path.exists(exe):
+        pytest.skip(f"examples/bin/{exe_name} not built")
+    import socket
+
+    X, Y, Z, steps = 48, 16, 16, 60
+
+    def launch(tmp, out, extra):
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        procs = []
+        for rank in range(2):
+            env = dict(os.environ, LBMX_RANK=str(rank), LBMX_WORLD_SIZE="2", LBMX_LOCAL_RANK=str(rank), LBMX_MASTER_ADDR="127.0.0.1", LBMX_MASTER_PORT=str(port))
+            procs.append(subprocess.Popen([exe, str(X), str(Y), str(Z), str(steps), os.path.join(tmp, out)] + extra, env=env, cwd=tmp,
+                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+        return outs
+
+    def assemble(tmp, out):
+        parts = [np.fromfile(os.path.join(tmp, f"{out}.rank{r}.macro"), dtype=np.float64).reshape(4, X // 2, Z, Y) for r in range(2)]
+        return np.concatenate(parts, axis=1)
+
+    with tempfile.TemporaryDirectory() as t1, tempfile.TemporaryDirectory() as t2, tempfile.TemporaryDirectory() as t3:
+        outs = launch(t2, "two", [])
+        assert any("ranks=2" in o for o in outs), outs
+        two = assemble(t2, "two")
+        if not exe_name.endswith("_aa"):
+            r = subprocess.run([exe, str(X), str(Y), str(Z), str(steps), os.path.join(t1, "one")], capture_output=True, text=True, timeout=300, cwd=t1)
+            assert r.returncode == 0, r.stdout + r.stderr
+            one = np.fromfile(os.path.join(t1, "one.macro"), dtype=np.float64).reshape(4, X, Z, Y)
+            assert np.array_equal(two, one), f"max |two - one| = {np.abs(two - one).max():.3e} in x-planes {np.where(np.abs(two - one).max(axis=(0, 2, 3)) > 0)[0].tolist()}"
+        # (A-A on non-periodic faces: a single process has no ghost planes for the x +- 1 accesses of its face cells -- out of bounds in the
+        # reference, kernels.h:30-38 -- so only runs with the same decomposition are comparable there)
+        assert np.isfinite(two).all() and abs(two[0].mean() - 1.0) < 0.05
+        launch(t3, "part", ["halt=31"])
+        ck = os.path.join(t3, "results_channel3d", "checkpoint.bp")
+        assert sorted(f for f in os.listdir(ck) if f.endswith(".txt")) == ["attributes.txt", "variables_rank_0.txt", "variables_rank_1.txt"]
+        outs = launch(t3, "resumed", [])
+        assert any("Loading data from checkpoint" in o for o in outs) and any(f"iterations={steps} " in o for o in outs), outs
+        resumed = assemble(t3, "resumed")
+        assert np.array_equal(resumed, two), f"max |resumed - two| = {np.abs(resumed - two).max():.3e}"

@@ -62,7 +62,7 @@ class HaloMsg(C.Structure):
 # every symbol include/lbmx.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "lbmx_last_error", "lbmx_version", "lbmx_decompose_x", "lbmx_halo_directions", "lbmx_halo_plan", "lbmx_create", "lbmx_destroy", "lbmx_get_layout",
-    "lbmx_comm_unique_id", "lbmx_comm_init", "lbmx_map_upload", "lbmx_map_download", "lbmx_df_set_equilibrium", "lbmx_df_set_equilibrium_field",
+    "lbmx_device_count", "lbmx_comm_unique_id", "lbmx_comm_init", "lbmx_map_upload", "lbmx_map_download", "lbmx_df_set_equilibrium", "lbmx_df_set_equilibrium_field",
     "lbmx_df_upload", "lbmx_df_download", "lbmx_df_sync_ghosts", "lbmx_macro_init", "lbmx_macro_download", "lbmx_macro_upload", "lbmx_set_params",
     "lbmx_set_inflow_profile", "lbmx_bouzidi_upload", "lbmx_step", "lbmx_sync", "lbmx_step_timed", "lbmx_halo_time", "lbmx_get_iterations", "lbmx_set_iterations", "lbmx_has_nan",
     "lbmx_get_device_ptrs", "lbmx_get_stats",

@@ -360,6 +360,18 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 				CU(cudaEventRecord(e->ev_edge, e->s_edge));
 			}
 		}
+		else if (e->list_after_bulk) {
+			// A-A slab with GEO_OUTFLOW_RIGHT cells: those read a neighbour's populations in place, so the whole boundary list has to
+			// follow the whole bulk kernel (as on a single slab) -- no edge-first overlap for this slab, the result stays reproducible
+			CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
+			if ((rc = launch_range(e, K, p, 0, (int) e->X, e->s_main)))
+				return rc;
+			CU(cudaEventRecord(e->ev_main, e->s_main));
+			CU(cudaStreamWaitEvent(e->s_comm, e->ev_main, 0));
+			if ((rc = exchange<R>(e, e->df[0])))
+				return rc;
+			CU(cudaEventRecord(e->ev_comm, e->s_comm));
+		}
 		else {
 			// boundary planes first on the high-priority stream, then the exchange, interior concurrently (state.hpp:1060-1108)
 			CU(cudaStreamWaitEvent(e->s_edge, e->ev_main, 0));	// previous step's interior (reads/writes next to the edge planes)
@@ -386,7 +398,7 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 	// leave the engine in a state where s_main alone orders everything that was enqueued
 	if (ghosts)
 		CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
-	if (ghosts || (e->nb > 0 && ! e->list_after_bulk))
+	if ((ghosts || e->nb > 0) && ! e->list_after_bulk)
 		CU(cudaStreamWaitEvent(e->s_main, e->ev_edge, 0));
 	return LBMX_OK;
 }
@@ -569,6 +581,16 @@ int lbmx_halo_plan(int32_t lattice, int32_t streaming, int64_t iteration, int64_
 		toL.src_plane = gL;
 		toL.dst_plane = last;
 	}
+	return LBMX_OK;
+}
+
+int lbmx_device_count(int32_t* count)
+{
+	if (! count)
+		return fail(LBMX_ERR_ARG, "lbmx_device_count: null argument");
+	int n = 0;
+	CU(cudaGetDeviceCount(&n));
+	*count = n;
 	return LBMX_OK;
 }
 

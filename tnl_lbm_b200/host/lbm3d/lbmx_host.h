@@ -33,6 +33,12 @@
 #include <utility>
 #include <vector>
 
+#include <arpa/inet.h>
+#include <dirent.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/socket.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -59,7 +65,175 @@
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// the sliver of TNL the solvers name themselves (StaticVector, MPI::Comm, sqr); single process, no MPI underneath
+// Process group without MPI (the reference runs one MPI rank per GPU, lbm.h:38-45; MPI is not a dependency here).
+// Rank, size and local rank come from the launcher's environment -- torchrun (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR /
+// MASTER_PORT), mpirun or srun if one is used, or LBMX_RANK / LBMX_WORLD_SIZE / LBMX_LOCAL_RANK set by hand.  Host-side
+// collectives (the few reductions and broadcasts of the control plane, and the 128-byte NCCL id) travel over TCP in a star on
+// rank 0; the data path is NCCL inside the engine.  Example, 4 GPUs of one node:
+//     python -m torch.distributed.run --no-python --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29500 ./sim_1 4
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace lbmx_host {
+struct World
+{
+	int rank = 0, size = 1, local_rank = 0;
+	bool connected = false;
+	std::vector<int> peers;	 // rank 0: socket of every other rank (index = rank); other ranks: peers[0] = socket to rank 0
+
+	static World& get()
+	{
+		static World w = make();
+		return w;
+	}
+	static int env_int(std::initializer_list<const char*> names, int fallback)
+	{
+		for (const char* n : names)
+			if (const char* v = std::getenv(n))
+				if (*v)
+					return std::atoi(v);
+		return fallback;
+	}
+	static World make()
+	{
+		World w;
+		w.size = env_int({"LBMX_WORLD_SIZE", "WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS"}, 1);
+		w.rank = env_int({"LBMX_RANK", "RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID"}, 0);
+		w.local_rank = env_int({"LBMX_LOCAL_RANK", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID"}, w.rank);
+		if (w.size < 1 || w.rank < 0 || w.rank >= w.size)
+			throw std::runtime_error("lbmx: inconsistent rank / world size in the environment");
+		return w;
+	}
+	static void send_all(int fd, const void* buf, size_t n)
+	{
+		const char* p = (const char*) buf;
+		while (n > 0) {
+			const ssize_t k = ::send(fd, p, n, MSG_NOSIGNAL);
+			if (k <= 0)
+				throw std::runtime_error("lbmx: lost the connection to a peer rank (send)");
+			p += k;
+			n -= (size_t) k;
+		}
+	}
+	static void recv_all(int fd, void* buf, size_t n)
+	{
+		char* p = (char*) buf;
+		while (n > 0) {
+			const ssize_t k = ::recv(fd, p, n, 0);
+			if (k <= 0)
+				throw std::runtime_error("lbmx: lost the connection to a peer rank (recv)");
+			p += k;
+			n -= (size_t) k;
+		}
+	}
+	// rendezvous: rank 0 listens on LBMX_MASTER_PORT (default: MASTER_PORT + 1, torchrun keeps MASTER_PORT for its own store)
+	void connect()
+	{
+		if (connected || size == 1)
+			return;
+		const char* addr = std::getenv("LBMX_MASTER_ADDR");
+		if (! addr)
+			addr = std::getenv("MASTER_ADDR");
+		if (! addr)
+			addr = "127.0.0.1";
+		const int port = env_int({"LBMX_MASTER_PORT"}, env_int({"MASTER_PORT"}, 29576) + 1);
+		const int one = 1;
+		if (rank == 0) {
+			const int ls = ::socket(AF_INET, SOCK_STREAM, 0);
+			::setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+			sockaddr_in sa{};
+			sa.sin_family = AF_INET;
+			sa.sin_addr.s_addr = htonl(INADDR_ANY);
+			sa.sin_port = htons((uint16_t) port);
+			if (::bind(ls, (sockaddr*) &sa, sizeof sa) != 0 || ::listen(ls, size) != 0)
+				throw std::runtime_error("lbmx: rank 0 cannot listen on port " + std::to_string(port) + ": " + std::strerror(errno));
+			peers.assign((size_t) size, -1);
+			for (int k = 1; k < size; k++) {
+				const int fd = ::accept(ls, nullptr, nullptr);
+				if (fd < 0)
+					throw std::runtime_error(std::string("lbmx: accept failed: ") + std::strerror(errno));
+				::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+				int32_t r = -1;
+				recv_all(fd, &r, sizeof r);
+				if (r < 1 || r >= size || peers[(size_t) r] != -1)
+					throw std::runtime_error("lbmx: unexpected rank announced itself at the rendezvous");
+				peers[(size_t) r] = fd;
+			}
+			::close(ls);
+		}
+		else {
+			addrinfo hints{}, *res = nullptr;
+			hints.ai_family = AF_INET;
+			hints.ai_socktype = SOCK_STREAM;
+			if (::getaddrinfo(addr, std::to_string(port).c_str(), &hints, &res) != 0 || ! res)
+				throw std::runtime_error(std::string("lbmx: cannot resolve ") + addr);
+			int fd = -1;
+			for (int attempt = 0; attempt < 600 && fd < 0; attempt++) {	 // up to 60 s for rank 0 to come up
+				fd = ::socket(AF_INET, SOCK_STREAM, 0);
+				if (::connect(fd, res->ai_addr, res->ai_addrlen) != 0) {
+					::close(fd);
+					fd = -1;
+					::usleep(100000);
+				}
+			}
+			::freeaddrinfo(res);
+			if (fd < 0)
+				throw std::runtime_error(std::string("lbmx: cannot reach rank 0 at ") + addr + ":" + std::to_string(port));
+			::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+			const int32_t r = rank;
+			send_all(fd, &r, sizeof r);
+			peers.assign(1, fd);
+		}
+		connected = true;
+	}
+	enum Op { SUM, MAX, MIN };
+	void allreduce(double* v, int n, Op op)
+	{
+		if (size == 1)
+			return;
+		connect();
+		if (rank == 0) {
+			std::vector<double> in((size_t) n);
+			for (int r = 1; r < size; r++) {
+				recv_all(peers[(size_t) r], in.data(), sizeof(double) * (size_t) n);
+				for (int i = 0; i < n; i++)
+					v[i] = op == SUM ? v[i] + in[(size_t) i] : (op == MAX ? std::max(v[i], in[(size_t) i]) : std::min(v[i], in[(size_t) i]));
+			}
+			for (int r = 1; r < size; r++)
+				send_all(peers[(size_t) r], v, sizeof(double) * (size_t) n);
+		}
+		else {
+			send_all(peers[0], v, sizeof(double) * (size_t) n);
+			recv_all(peers[0], v, sizeof(double) * (size_t) n);
+		}
+	}
+	void bcast(void* buf, size_t bytes, int root = 0)
+	{
+		if (size == 1)
+			return;
+		connect();
+		if (root != 0) {  // relay through rank 0
+			if (rank == root)
+				send_all(peers[0], buf, bytes);
+			else if (rank == 0)
+				recv_all(peers[(size_t) root], buf, bytes);
+		}
+		if (rank == 0) {
+			for (int r = 1; r < size; r++)
+				if (r != root)
+					send_all(peers[(size_t) r], buf, bytes);
+		}
+		else if (rank != root)
+			recv_all(peers[0], buf, bytes);
+	}
+	void barrier()
+	{
+		double x = 0;
+		allreduce(&x, 1, SUM);
+	}
+};
+}  // namespace lbmx_host
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// the sliver of TNL the solvers name themselves (StaticVector, MPI::Comm, sqr); TNL::MPI maps onto lbmx_host::World
 // ---------------------------------------------------------------------------------------------------------------------------
 #ifndef LBMX_HAVE_REAL_TNL
 namespace TNL {
@@ -96,18 +270,25 @@ struct Comm
 };
 struct ScopedInitializer
 {
-	ScopedInitializer(int&, char**&) {}
+	ScopedInitializer(int&, char**&) { lbmx_host::World::get().connect(); }
 };
-inline int GetSize(const Comm&) { return 1; }
-inline int GetRank(const Comm&) { return 0; }
+inline int GetSize(const Comm& = Comm{}) { return lbmx_host::World::get().size; }
+inline int GetRank(const Comm& = Comm{}) { return lbmx_host::World::get().rank; }
+// Op is one of the MPI_* constants below; values travel as double (the control plane reduces a handful of scalars)
 template <typename T, typename Op>
-inline T reduce(T v, Op, const Comm&)
+inline T reduce(T v, Op op, const Comm& = Comm{})
 {
-	return v;
+	double x = (double) v;
+	const int o = (int) op;	 // MPI_SUM, MPI_LOR, MPI_LAND, MPI_MAX, MPI_MIN
+	lbmx_host::World::get().allreduce(&x, 1, o == 0 ? lbmx_host::World::SUM : ((o == 1 || o == 3) ? lbmx_host::World::MAX : lbmx_host::World::MIN));
+	return (T) x;
 }
 template <typename T>
-inline void Bcast(T*, int, int, const Comm&)
-{}
+inline void Bcast(T* data, int count, int root, const Comm& = Comm{})
+{
+	lbmx_host::World::get().bcast(data, sizeof(T) * (size_t) count, root);
+}
+inline void Barrier(const Comm& = Comm{}) { lbmx_host::World::get().barrier(); }
 }  // namespace MPI
 template <typename T>
 inline T sqr(T v)
@@ -474,12 +655,6 @@ inline void make_dirs(const std::string& path)
 		if (i == path.size() || path[i] == '/')
 			::mkdir(path.substr(0, i).c_str(), 0777);
 }
-inline void remove_tree(const std::string& dir, const std::vector<std::string>& names)
-{
-	for (const auto& n : names)
-		::remove((dir + "/" + n).c_str());
-	::rmdir(dir.c_str());
-}
 template <typename T>
 constexpr const char* dtype_name()
 {
@@ -498,12 +673,11 @@ class CheckpointManager
 	std::map<std::string, std::string> attributes;
 	std::map<std::string, std::pair<std::string, size_t>> variables;  // name -> (dtype, count)
 
-	std::vector<std::string> file_names() const
+	// every rank keeps the index of its own variables; rank 0 also writes the attributes (identical on all ranks)
+	static std::string index_name()
 	{
-		std::vector<std::string> n = {"attributes.txt", "variables.txt"};
-		for (const auto& v : variables)
-			n.push_back(v.first + ".bin");
-		return n;
+		const lbmx_host::World& w = lbmx_host::World::get();
+		return w.size > 1 ? "variables_rank_" + std::to_string(w.rank) + ".txt" : "variables.txt";
 	}
 
 public:
@@ -520,7 +694,7 @@ public:
 			lbmx_host::make_dirs(dir);
 			return;
 		}
-		std::ifstream fa(dir + "/attributes.txt"), fv(dir + "/variables.txt");
+		std::ifstream fa(dir + "/attributes.txt"), fv(dir + "/" + index_name());
 		if (! fa || ! fv)
 			throw std::runtime_error("CheckpointManager: cannot open checkpoint " + dir);
 		std::string line;
@@ -538,12 +712,17 @@ public:
 	void finalize()
 	{
 		if (mode == adios2::Mode::Write) {
-			std::ofstream fa(dir + "/attributes.txt"), fv(dir + "/variables.txt");
-			for (const auto& a : attributes)
-				fa << a.first << '\t' << a.second << '\n';
+			std::ofstream fv(dir + "/" + index_name());
 			for (const auto& v : variables)
 				fv << v.first << ' ' << v.second.first << ' ' << v.second.second << '\n';
-			if (! fa || ! fv)
+			bool ok = (bool) fv;
+			if (lbmx_host::World::get().rank == 0) {
+				std::ofstream fa(dir + "/attributes.txt");
+				for (const auto& a : attributes)
+					fa << a.first << '\t' << a.second << '\n';
+				ok = ok && (bool) fa;
+			}
+			if (! ok)
 				throw std::runtime_error("CheckpointManager: cannot write the index of " + dir);
 		}
 		mode = adios2::Mode::Undefined;
@@ -551,11 +730,17 @@ public:
 	// removes a checkpoint directory written by this class (used when a staged checkpoint replaces the previous one)
 	static void discard(const std::string& path)
 	{
-		if (! lbmx_host::file_exists(path + "/variables.txt"))
+		if (! lbmx_host::file_exists(path + "/attributes.txt"))
 			return;
-		CheckpointManager old;
-		old.start(path, adios2::Mode::Read);
-		lbmx_host::remove_tree(path, old.file_names());
+		if (DIR* d = ::opendir(path.c_str())) {
+			while (dirent* ent = ::readdir(d)) {
+				const std::string n = ent->d_name;
+				if (n != "." && n != "..")
+					::remove((path + "/" + n).c_str());
+			}
+			::closedir(d);
+		}
+		::rmdir(path.c_str());
 	}
 
 	template <typename T, typename CastToType = T>
@@ -636,7 +821,8 @@ struct RawWriter
 	// two files per (file name, cycle): <filename>.<cycle>.txt = index (name dtype count dofs byte_offset), .bin = payloads
 	RawWriter(const std::string& filename, int cycle, const long (&global)[3], const long (&local)[3], const long (&off)[3], double dl)
 	{
-		base = filename + "." + std::to_string(cycle);
+		const lbmx_host::World& w = lbmx_host::World::get();
+		base = filename + "." + std::to_string(cycle) + (w.size > 1 ? ".rank" + std::to_string(w.rank) : "");  // one piece per rank; the header says where it sits
 		const size_t slash = base.rfind('/');
 		if (slash != std::string::npos)
 			lbmx_host::make_dirs(base.substr(0, slash));
@@ -813,9 +999,25 @@ struct LBM_BLOCK
 		d.rank = rank;
 		d.nranks = nproc;
 		d.device = -1;
+		if (nproc > 1) {  // one process per GPU: the launcher's local rank picks the device
+			int32_t ndev = 0;
+			lbmx_host::check(lbmx_device_count(&ndev), "lbmx_device_count");
+			if (ndev < 1)
+				throw std::runtime_error("lbmx: no CUDA device visible to rank " + std::to_string(rank));
+			d.device = lbmx_host::World::get().local_rank % ndev;
+		}
 		d.ghost_x = nproc > 1;
 		d.periodic_x = periodic_lattice;
 		lbmx_host::check(lbmx_create(&d, &engine), "lbmx_create");
+		if (nproc > 1) {
+			// the communicator of the reference's synchronisers (lbm_block.hpp:410-473) becomes the engine's NCCL communicator:
+			// rank 0 draws the id, the process group broadcasts its 128 bytes
+			unsigned char id128[128] = {};
+			if (rank == 0)
+				lbmx_host::check(lbmx_comm_unique_id(id128), "lbmx_comm_unique_id");
+			lbmx_host::World::get().bcast(id128, sizeof id128, 0);
+			lbmx_host::check(lbmx_comm_init(engine, id128), "lbmx_comm_init");
+		}
 		refreshPointers();
 	}
 	void refreshPointers()
@@ -1041,6 +1243,7 @@ struct LBM
 		blocks.emplace_back(lat.global, idx3d((idx) xl, lat.global.y(), lat.global.z()), idx3d((idx) x0, 0, 0));
 		blocks.back().rank = rank;
 		blocks.back().nproc = nproc;
+		blocks.back().id = rank;
 		total_blocks = nproc;
 		physCharLength = lat.physDl * (real) lat.global.y();
 	}
@@ -1367,6 +1570,7 @@ struct State
 		if (cnt[PRINT].action(t)) {
 			int32_t nan = 0;
 			lbmx_host::check(lbmx_has_nan(nse.blocks.front().engine, &nan), "lbmx_has_nan");
+			nan = TNL::MPI::reduce(nan, MPI_LOR, nse.communicator);	 // every rank must take the same decision (state.hpp:1166-1188)
 			if (nan) {
 				lbmx_host::log_info("nan detected");
 				nse.terminate = true;
@@ -1458,13 +1662,17 @@ struct State
 	bool flagExists(const char* flagname) { return lbmx_host::file_exists(flag_path(flagname)); }
 	bool canCompute()
 	{
-		if (flagExists("loadstate"))
-			return true;
-		if (flagExists("finished") || flagExists("terminated")) {
-			lbmx_host::log_info("results_%s is in finished/terminated state, there is nothing to compute", id.c_str());
-			return false;
+		int result = 1;
+		if (nse.rank == 0) {
+			if (flagExists("loadstate"))
+				result = 1;
+			else if (flagExists("finished") || flagExists("terminated")) {
+				lbmx_host::log_info("results_%s is in finished/terminated state, there is nothing to compute", id.c_str());
+				result = 0;
+			}
 		}
-		return true;
+		TNL::MPI::Bcast(&result, 1, 0, nse.communicator);
+		return result != 0;
 	}
 
 	// State::checkpointState (state.hpp:677-738): same attribute and variable names
@@ -1483,8 +1691,11 @@ struct State
 			checkpoint.saveLoadAttribute("State_probe3D_" + std::to_string(i) + "_cycle", probe3Dvec[i].cycle);
 		for (std::size_t i = 0; i < probe2Dvec.size(); i++)
 			checkpoint.saveLoadAttribute("State_probe2D_" + std::to_string(i) + "_cycle", probe2Dvec[i].cycle);
-		for (auto& block : nse.blocks)
+		for (auto& block : nse.blocks) {
+			if (mode == adios2::Mode::Read)	 // "df_cur" / "df_out" are roles that rotate with the iteration count (lbm.hpp:314-330): restore it first
+				lbmx_host::check(lbmx_set_iterations(block.engine, nse.iterations), "lbmx_set_iterations");
 			block.checkpoint(checkpoint);
+		}
 		if (mode == adios2::Mode::Read) {
 			nse.physStartTime = nse.physTime();
 			nse.startIterations = nse.iterations;
@@ -1499,16 +1710,21 @@ struct State
 	{
 		const std::string tmp = "results_" + id + "/checkpoint_tmp.bp", fin = "results_" + id + "/checkpoint.bp";
 		lbmx_host::log_info("Saving checkpoint in %s", tmp.c_str());
+		if (nse.rank == 0)
+			CheckpointManager::discard(tmp);  // leftovers of an interrupted save
+		TNL::MPI::Barrier(nse.communicator);
 		checkpoint.start(tmp, adios2::Mode::Write);
 		checkpointState(adios2::Mode::Write);
 		checkpointStateLocal(adios2::Mode::Write);
 		checkpoint.finalize();
+		TNL::MPI::Barrier(nse.communicator);  // every rank's piece is on disk before the staged directory replaces the old one
 		if (nse.rank == 0) {
 			CheckpointManager::discard(fin);
 			if (::rename(tmp.c_str(), fin.c_str()) != 0)
 				throw std::runtime_error("saveState: cannot move " + tmp + " to " + fin + ": " + std::strerror(errno));
 		}
 		flagCreate("loadstate");
+		TNL::MPI::Barrier(nse.communicator);
 	}
 	void loadState()
 	{
@@ -1522,8 +1738,16 @@ struct State
 
 	TNL::Timer timer_total;
 	long wallTime = -1;
-	bool wallTimeReached() { return wallTime > 0 && timer_total.getRealTime() >= (double) wallTime; }
-	double getWallTime(bool = false) { return timer_total.getRealTime(); }
+	bool wallTimeReached()	// collective: all ranks stop together (state.hpp:783-795)
+	{
+		const bool local = wallTime > 0 && timer_total.getRealTime() >= (double) wallTime;
+		return TNL::MPI::reduce(local, MPI_LOR, nse.communicator);
+	}
+	double getWallTime(bool collective = false)
+	{
+		const double t = timer_total.getRealTime();
+		return collective ? TNL::MPI::reduce(t, MPI_MAX, nse.communicator) : t;
+	}
 	int glups_prev_iterations = 0;
 	double glups_prev_time = 0;
 	TNL::Timer timer_SimInit, timer_SimUpdate, timer_AfterSimUpdate, timer_compute, timer_compute_overlaps, timer_wait_communication, timer_wait_computation;
