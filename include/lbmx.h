@@ -51,9 +51,22 @@ enum lbmx_coll {
 	 * setEquilibriumDecomposition, which lbm_block.hpp:243 and d3q27/bc.h:141 require), so there is no behaviour to match */
 	LBMX_COLL_CUM_2017 = 10,		   /* D3Q27_CUM built with -DUSE_GEIER_CUM_2017 (defs.h:254; col_cum.h:177-208,258-276) */
 	LBMX_COLL_CUM_ANTIALIAS = 11,	   /* D3Q27_CUM built with -DUSE_GEIER_CUM_ANTIALIAS (defs.h:255; col_cum.h:215-229) */
-	LBMX_COLL_CUM_2017_ANTIALIAS = 12 /* both switches */
+	LBMX_COLL_CUM_2017_ANTIALIAS = 12, /* both switches */
+	LBMX_COLL_KBC_N1 = 13,			   /* D3Q27_KBC_N1..N4  d3q27/col_kbc_n.h:254-1272 (shear part from raw moments: D, D+T, D+Q, D+T+Q) */
+	LBMX_COLL_KBC_N2 = 14,
+	LBMX_COLL_KBC_N3 = 15,
+	LBMX_COLL_KBC_N4 = 16,
+	LBMX_COLL_KBC_C1 = 17,			   /* D3Q27_KBC_C1..C4  d3q27/col_kbc_c.h:283-1301 (shear part from central moments) */
+	LBMX_COLL_KBC_C2 = 18,
+	LBMX_COLL_KBC_C3 = 19,
+	LBMX_COLL_KBC_C4 = 20
 };
-enum lbmx_eq { LBMX_EQ_STD = 0 /* D3Q27_EQ eq.h:8-130, D2Q9_EQ */, LBMX_EQ_INV_CUM = 1 /* D3Q27_EQ_INV_CUM eq_inv_cum.h:13-137 */ };
+enum lbmx_eq {
+	LBMX_EQ_STD = 0,	  /* D3Q27_EQ eq.h:8-130, D2Q9_EQ */
+	LBMX_EQ_INV_CUM = 1,  /* D3Q27_EQ_INV_CUM eq_inv_cum.h:13-137 */
+	/* 2: D3Q27_EQ_WELL belongs to the *_WELL operators (not instantiable in the reference, see above) */
+	LBMX_EQ_ENTROPIC = 3  /* D3Q27_EQ_ENTROPIC eq_entropic.h:11-211; initialisation and boundary cells of the KBC operators */
+};
 enum lbmx_streaming { LBMX_STREAM_AB = 0 /* streaming_AB.h */, LBMX_STREAM_AA = 1 /* streaming_AA.h */ };
 enum lbmx_macro { LBMX_MACRO_VOID = 0, LBMX_MACRO_DEFAULT = 1, LBMX_MACRO_MEAN = 2 }; /* d3q27/macro.h:50-188, d2q9/macro.h */
 enum lbmx_inflow {

@@ -295,9 +295,37 @@ R eq9_std(int q, R rho, R vx, R vy)
 	return w * rho * poly;
 }
 
+// d3q27/eq_entropic.h:11-211: rho * W(cx) W(cy) W(cz) * prod_a (2 - s_a) * prod_a B_a^{c_a}, s_a = sqrt(1 + 3 v_a^2),
+// B_a = (2 v_a + s_a) / (1 - v_a), evaluated left to right: weights, the three (2 - s_a), then per axis "* 1 / B_a" (c_a = -1) or
+// "* B_a" (c_a = +1).  The reference's unqualified sqrt() is ::sqrt(double) in the host build, so for dreal = float the chain is
+// in double from the first (2 - s_a) on and rounded once when returned.
+template <typename R>
+R eq27_entropic(int q, R rho, R vx, R vy, R vz)
+{
+	const R v[3] = {vx, vy, vz};
+	const int c[3] = {C27[q][0], C27[q][1], C27[q][2]};
+	const R w6 = (R) (1.0 / 6.0), w23 = (R) (2.0 / 3.0);
+	const R w = (c[0] ? w6 : w23) * (c[1] ? w6 : w23) * (c[2] ? w6 : w23);
+	double s[3], B[3];
+	for (int a = 0; a < 3; a++) {
+		s[a] = ::sqrt((double) ((R) 1.0 + (R) 3.0 * v[a] * v[a]));
+		B[a] = ((double) ((R) 2.0 * v[a]) + s[a]) / (double) ((R) 1.0 - v[a]);
+	}
+	double chain = (double) w * (2.0 - s[0]) * (2.0 - s[1]) * (2.0 - s[2]);
+	for (int a = 0; a < 3; a++) {
+		if (c[a] < 0)
+			chain = chain * 1.0 / B[a];
+		else if (c[a] > 0)
+			chain = chain * B[a];
+	}
+	return (R) ((double) rho * chain);
+}
+
 template <typename R>
 R equilibrium(const Cell<R, 27>&, int eqkind, int q, R rho, R vx, R vy, R vz)
 {
+	if (eqkind == ORC_EQ_ENTROPIC)
+		return eq27_entropic(q, rho, vx, vy, vz);
 	return eqkind == ORC_EQ_INV_CUM ? eq27_inv_cum(q, rho, vx, vy, vz) : eq27_std(q, rho, vx, vy, vz);
 }
 template <typename R>
@@ -734,6 +762,12 @@ void collide(Cell<R, 27>& K, const oracle_desc& d)
 		case ORC_COLL_MRT_LES: collide_mrt27(K); break;
 		case ORC_COLL_CLBM: collide_clbm27(K); break;
 		case ORC_COLL_SRT_MODIF_FORCE: collide_srt_modif27(K, d.eq); break;
+		case ORC_COLL_KBC_N1: case ORC_COLL_KBC_N2: case ORC_COLL_KBC_N3: case ORC_COLL_KBC_N4:
+		case ORC_COLL_KBC_C1: case ORC_COLL_KBC_C2: case ORC_COLL_KBC_C3: case ORC_COLL_KBC_C4: {
+			const int k = (d.coll - ORC_COLL_KBC_N1) % 4;  // 0: D, 1: D+T, 2: D+Q, 3: D+T+Q
+			collide_kbc27(K, d.coll >= ORC_COLL_KBC_C1, k == 1 || k == 3, k >= 2);
+			break;
+		}
 		case ORC_COLL_CUM_2017: collide_cum<R, true, false>(K); break;
 		case ORC_COLL_CUM_ANTIALIAS: collide_cum<R, false, true>(K); break;
 		case ORC_COLL_CUM_2017_ANTIALIAS: collide_cum<R, true, true>(K); break;
@@ -1230,8 +1264,8 @@ bool supported(const oracle_desc* d)
 	if (d->streaming != ORC_STREAM_AB && d->streaming != ORC_STREAM_AA)
 		return false;
 	if (d->lattice == ORC_D3Q27)
-		return ((d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE) || (d->coll >= ORC_COLL_CUM_2017 && d->coll <= ORC_COLL_CUM_2017_ANTIALIAS))
-			&& (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM);
+		return ((d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE) || (d->coll >= ORC_COLL_CUM_2017 && d->coll <= ORC_COLL_KBC_C4))
+			&& (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM || d->eq == ORC_EQ_ENTROPIC);
 	if (d->lattice == ORC_D2Q9)
 		return (d->coll == ORC_COLL_SRT || d->coll == ORC_COLL_CLBM) && d->eq == ORC_EQ_STD && d->Z == 1;
 	if (d->lattice == ORC_D3Q19)  // no reference implementation: PARITY UNPINNED (see L19)

@@ -3,6 +3,8 @@
 //
 //   D3Q27_CLBM             include/lbm3d/d3q27/col_clbm.h:6-447
 //   D3Q27_SRT_MODIF_FORCE  include/lbm3d/d3q27/col_srt_modif_force.h:9-120
+//   D3Q27_KBC_N1..N4       include/lbm3d/d3q27/col_kbc_n.h:254-1272
+//   D3Q27_KBC_C1..C4       include/lbm3d/d3q27/col_kbc_c.h:283-1301
 #pragma once
 
 // ---------------------------------------------------------------------------------------------
@@ -226,4 +228,199 @@ void collide_srt_modif27(Cell<R, 27>& K, int eqkind)
 	}
 	for (int q = 0; q < 27; q++)
 		K.f[q] += (feq[q] - K.f[q]) / tau + (one - half / tau) * S[q];
+}
+
+// ---------------------------------------------------------------------------------------------
+// KBC family (col_kbc_n.h:254-1272, col_kbc_c.h:283-1301): f = k + s + h; the shear part s relaxes with 2 beta, the higher-order
+// part h with gamma * beta, gamma = the entropic stabiliser.  The eight models differ in the shear part only:
+//   N1..N4: s built from raw moments,     D | D+T | D+Q | D+T+Q     (col_kbc_n.h:28-252)
+//   C1..C4: s built from central moments, D~| D~+T~ | D~+Q~ | D~+T~+Q~ (col_kbc_c.h:56-281)
+// ---------------------------------------------------------------------------------------------
+// raw moments M_abc = sum_i cx^a cy^b cz^c f_i, summed left to right in the order the reference lists the populations
+// (col_kbc_n.h:351-386); direction codes m, z, p = -1, 0, +1 for (x, y, z)
+struct KbcMoment
+{
+	int a, b, c;
+	const char* order;
+};
+static const KbcMoment KBC_MOMENTS[13] = {
+	{2, 0, 0, "mmm mmp mmz mpm mpp mpz mzm mzp mzz pmm pmp pmz ppm ppp ppz pzm pzp pzz"},
+	{0, 2, 0, "mmm mmp mmz mpm mpp mpz zmm zmp zmz zpm zpp zpz pmm pmp pmz ppm ppp ppz"},
+	{0, 0, 2, "mmm mmp mzm mzp mpm mpp zmm zmp zzm zzp zpm zpp pmm pmp pzm pzp ppm ppp"},
+	{1, 1, 0, "mmm mmz mmp mpm mpz mpp pmm pmz pmp ppm ppz ppp"},
+	{1, 0, 1, "mmm mmp mzm mzp mpm mpp pmm pmp pzm pzp ppm ppp"},
+	{0, 1, 1, "mmm mmp mpm mpp zmm zmp zpm zpp pmm pmp ppm ppp"},
+	{1, 1, 1, "ppp mmp mpm mpp pmm pmp ppm mmm"},
+	{2, 0, 1, "ppp mmp mzm mzp mpm mpp pmm pmp pzm pzp ppm mmm"},
+	{1, 0, 2, "ppp mmp mzm mzp mpm mpp pmm pmp pzm pzp ppm mmm"},
+	{2, 1, 0, "ppp mmz mmp mpm mpz mpp pmm pmz pmp ppm ppz mmm"},
+	{1, 2, 0, "ppp mmz mmp mpm mpz mpp pmm pmz pmp ppm ppz mmm"},
+	{0, 2, 1, "ppp mmp mpm mpp zmm zmp zpm zpp pmm pmp ppm mmm"},
+	{0, 1, 2, "ppp mmp mpm mpp zmm zmp zpm zpp pmm pmp ppm mmm"},
+};
+enum { KM200, KM020, KM002, KM110, KM101, KM011, KM111, KM201, KM102, KM210, KM120, KM021, KM012 };
+
+template <typename R>
+void collide_kbc27(Cell<R, 27>& K, bool central, bool useT, bool useQ)
+{
+	const R zero = 0, one = 1, two = 2, three = 3, four = 4, six = 6, eight = 8, half = (R) 0.5, third = (R) (1.0 / 3.0);
+	const R n1o4 = (R) 0.25, n1o6 = (R) (1.0 / 6.0), n1o8 = (R) 0.125;
+	const R rho = K.rho, vx = K.vx, vy = K.vy, vz = K.vz;
+	const R v[3] = {vx, vy, vz};
+	// product-form equilibrium (col_kbc_n.h:293-321), as in col_bgk.h
+	R g[3][3];
+	for (int a = 0; a < 3; a++) {
+		const R z = third - one + v[a] * v[a];
+		const R p = -half * (z + one + v[a]);
+		g[a][1] = z;
+		g[a][2] = p;
+		g[a][0] = p + v[a];
+	}
+	R feq[27], ifeq[27];
+	for (int q = 0; q < 27; q++) {
+		feq[q] = -rho * g[0][C27[q][0] + 1] * g[1][C27[q][1] + 1] * g[2][C27[q][2] + 1];
+		ifeq[q] = one / feq[q];
+	}
+	R M[13];
+	for (int k = 0; k < 13; k++) {
+		const KbcMoment& mo = KBC_MOMENTS[k];
+		R acc = 0;
+		bool first = true;
+		for (const char* s = mo.order; *s; s += (s[3] ? 4 : 3)) {
+			auto comp = [](char ch) { return ch == 'm' ? -1 : (ch == 'p' ? 1 : 0); };
+			const int cx = comp(s[0]), cy = comp(s[1]), cz = comp(s[2]);
+			int sign = 1;
+			for (int i = 0; i < mo.a; i++) sign *= cx;
+			for (int i = 0; i < mo.b; i++) sign *= cy;
+			for (int i = 0; i < mo.c; i++) sign *= cz;
+			const R t = K.f[find27(cx, cy, cz)];
+			acc = first ? (sign > 0 ? t : -t) : (sign > 0 ? acc + t : acc - t);
+			first = false;
+		}
+		M[k] = acc;
+	}
+	// the "special moments" and their equilibria (col_kbc_n.h:28-54, col_kbc_c.h:56-83)
+	R T = (M[KM200] + M[KM020] + M[KM002]), Nxz = (M[KM200] - M[KM002]), Nyz = (M[KM020] - M[KM002]);
+	R Pxy = M[KM110], Pxz = M[KM101], Pyz = M[KM011];
+	R Qxxy = M[KM210], Qxxz = M[KM201], Qxyy = M[KM120], Qyyz = M[KM021], Qxzz = M[KM102], Qyzz = M[KM012], Qxyz = M[KM111];
+	R eT, eNxz = 0, eNyz = 0, ePxy = 0, ePxz = 0, ePyz = 0, eQxxy = 0, eQxxz = 0, eQxyy = 0, eQyyz = 0, eQxzz = 0, eQyzz = 0, eQxyz = 0;
+	if (! central) {
+		eT = (rho * (three * third + vx * vx + vy * vy + vz * vz));
+		eNxz = (rho * (vx * vx - vz * vz));
+		eNyz = (rho * (vy * vy - vz * vz));
+		ePxy = (rho * vx * vy);
+		ePxz = (rho * vx * vz);
+		ePyz = (rho * vy * vz);
+		eQxxy = (rho * vy * (third + vx * vx));
+		eQxxz = (rho * vz * (third + vx * vx));
+		eQxyy = (rho * vx * (third + vy * vy));
+		eQyyz = (rho * vz * (third + vy * vy));
+		eQxzz = (rho * vx * (third + vz * vz));
+		eQyzz = (rho * vy * (third + vz * vz));
+		eQxyz = (rho * vx * vy * vz);
+	}
+	else {
+		const R rT = T, rNxz = Nxz, rNyz = Nyz, rPxy = Pxy, rPxz = Pxz, rPyz = Pyz;
+		const R rQxxy = Qxxy, rQxxz = Qxxz, rQxyy = Qxyy, rQyyz = Qyyz, rQxzz = Qxzz, rQyzz = Qyzz, rQxyz = Qxyz;
+		T = (rT - rho * (vx * vx + vy * vy + vz * vz));
+		Nxz = (rNxz + rho * (vz * vz - vx * vx));
+		Nyz = (rNyz + rho * (vz * vz - vy * vy));
+		Pxy = (rPxy - rho * vx * vy);
+		Pxz = (rPxz - rho * vx * vz);
+		Pyz = (rPyz - rho * vy * vz);
+		Qxxy = (rQxxy - third * (six * vx * Pxy + vy * (three * vx * vx + two * Nxz - Nyz + T)));
+		Qxxz = (rQxxz - third * (six * vx * Pxz + vz * (three * vx * vx + two * Nxz - Nyz + T)));
+		Qxyy = (rQxyy - third * (six * vy * Pxy + vx * (three * vy * vy + two * Nyz - Nxz + T)));
+		Qyyz = (rQyyz - third * (six * vy * Pyz + vz * (three * vy * vy + two * Nyz - Nxz + T)));
+		Qxzz = (rQxzz - third * (six * vz * Pxz + vx * (three * vz * vz - Nyz - Nxz + T)));
+		Qyzz = (rQyzz - third * (six * vz * Pyz + vy * (three * vz * vz - Nyz - Nxz + T)));
+		Qxyz = (rQxyz - vx * Pyz - vy * Pxz - vz * Pxy - vx * vy * vz);
+		eT = (rho * three * third);
+	}
+	// scaling of a tensor entry: the raw-moment models multiply by 1/6, 1/4, 1/2, 1/8, the central-moment models divide by 6, 4, 2, 8
+	auto sc = [&](R x, int den) -> R {
+		if (central)
+			return x / (den == 6 ? six : den == 4 ? four : den == 2 ? two : eight);
+		return x * (den == 6 ? n1o6 : den == 4 ? n1o4 : den == 2 ? half : n1o8);
+	};
+	// shear-part tensors per direction (col_kbc_n.h:56-252, col_kbc_c.h:85-281); has = the entry is not the constant 0
+	auto tensorD = [&](int cx, int cy, int cz, R nxz, R nyz, R pxy, R pxz, R pyz, bool& has) -> R {
+		const int n = (cx != 0) + (cy != 0) + (cz != 0);
+		has = n == 1 || n == 2;
+		if (n == 1)
+			return cx != 0 ? sc(two * nxz - nyz, 6) : (cy != 0 ? sc(-nxz + two * nyz, 6) : sc(-nxz - nyz, 6));
+		if (n == 2) {
+			const R p = cz == 0 ? pxy : (cy == 0 ? pxz : pyz);
+			const int s = cz == 0 ? cx * cy : (cy == 0 ? cx * cz : cy * cz);
+			return s > 0 ? sc(p, 4) : sc(-p, 4);
+		}
+		return zero;
+	};
+	auto tensorT = [&](int cx, int cy, int cz, R t, bool& has) -> R {
+		const int n = (cx != 0) + (cy != 0) + (cz != 0);
+		has = n <= 1;
+		return n == 0 ? -t : (n == 1 ? sc(t, 6) : zero);
+	};
+	auto tensorQ = [&](int cx, int cy, int cz, R qxxy, R qxxz, R qxyy, R qyyz, R qxzz, R qyzz, R qxyz, bool& has) -> R {
+		const int n = (cx != 0) + (cy != 0) + (cz != 0);
+		has = n >= 1;
+		if (n == 1) {
+			const R s = cx != 0 ? (qxyy + qxzz) : (cy != 0 ? (qxxy + qyzz) : (qxxz + qyyz));
+			return (cx + cy + cz) > 0 ? sc(-s, 2) : sc(s, 2);
+		}
+		if (n == 2) {
+			const R a = cz == 0 ? qxyy : (cy == 0 ? qxzz : qyzz), b = cz == 0 ? qxxy : (cy == 0 ? qxxz : qyyz);
+			const int sa = cz == 0 ? cx : (cy == 0 ? cx : cy), sb = cz == 0 ? cy : cz;
+			const R ta = sa > 0 ? a : -a;
+			return sc(sb > 0 ? ta + b : ta - b, 4);
+		}
+		if (n == 3)
+			return cx * cy * cz > 0 ? sc(qxyz, 8) : sc(-qxyz, 8);
+		return zero;
+	};
+	R Ds[27], Dh[27];
+	for (int q = 0; q < 27; q++) {
+		const int cx = C27[q][0], cy = C27[q][1], cz = C27[q][2];
+		R acc = zero;
+		bool has;
+		const R d = tensorD(cx, cy, cz, Nxz, Nyz, Pxy, Pxz, Pyz, has);
+		if (has) {
+			acc = d;
+			if (! central)	// the central-moment equilibria of D~ are the constant 0
+				acc = acc - tensorD(cx, cy, cz, eNxz, eNyz, ePxy, ePxz, ePyz, has);
+		}
+		if (useT) {
+			const R t = tensorT(cx, cy, cz, T, has);
+			if (has)
+				acc = (acc + t) - tensorT(cx, cy, cz, eT, has);
+		}
+		if (useQ) {
+			const R qq = tensorQ(cx, cy, cz, Qxxy, Qxxz, Qxyy, Qyyz, Qxzz, Qyzz, Qxyz, has);
+			if (has) {
+				acc = acc + qq;
+				if (! central)
+					acc = acc - tensorQ(cx, cy, cz, eQxxy, eQxxz, eQxyy, eQyyz, eQxzz, eQyzz, eQxyz, has);
+			}
+		}
+		Ds[q] = acc;
+		Dh[q] = K.f[q] - feq[q] - Ds[q];
+	}
+	const R beta = (one / (two * K.nu / third + one));
+	// <Ds|Dh> and <Dh|Dh>, summed in the order mmm, mmz, mmp, mzm, ... ppp (col_kbc_n.h:233-252)
+	R sd = 0, hh = 0;
+	bool first = true;
+	for (int a = -1; a <= 1; a++)
+		for (int b = -1; b <= 1; b++)
+			for (int c = -1; c <= 1; c++) {
+				const int q = find27(a, b, c);
+				const R t1 = Ds[q] * Dh[q] * ifeq[q], t2 = Dh[q] * Dh[q] * ifeq[q];
+				sd = first ? t1 : sd + t1;
+				hh = first ? t2 : hh + t2;
+				first = false;
+			}
+	const R gamma = (one / beta - (two - one / beta) * sd / hh);
+	for (int q = 0; q < 27; q++) {
+		const R S = force_projection(q, vx, vy, vz, K.fx, K.fy, K.fz) / rho;
+		K.f[q] -= beta * (two * Ds[q] + gamma * Dh[q]) - (one - beta) * S * feq[q];
+	}
 }

@@ -36,9 +36,17 @@ enum {
 	ORC_COLL_CUM_WELL = 9,
 	ORC_COLL_CUM_2017 = 10,			 /* D3Q27_CUM compiled with -DUSE_GEIER_CUM_2017 (defs.h:254) */
 	ORC_COLL_CUM_ANTIALIAS = 11,	 /* ... with -DUSE_GEIER_CUM_ANTIALIAS (defs.h:255) */
-	ORC_COLL_CUM_2017_ANTIALIAS = 12 /* ... with both */
+	ORC_COLL_CUM_2017_ANTIALIAS = 12, /* ... with both */
+	ORC_COLL_KBC_N1 = 13, /* D3Q27_KBC_N1..N4 (col_kbc_n.h), C1..C4 (col_kbc_c.h): 13..20 */
+	ORC_COLL_KBC_N2 = 14,
+	ORC_COLL_KBC_N3 = 15,
+	ORC_COLL_KBC_N4 = 16,
+	ORC_COLL_KBC_C1 = 17,
+	ORC_COLL_KBC_C2 = 18,
+	ORC_COLL_KBC_C3 = 19,
+	ORC_COLL_KBC_C4 = 20
 };
-enum { ORC_EQ_STD = 0, ORC_EQ_INV_CUM = 1, ORC_EQ_WELL = 2 };
+enum { ORC_EQ_STD = 0, ORC_EQ_INV_CUM = 1, ORC_EQ_WELL = 2, ORC_EQ_ENTROPIC = 3 };
 enum { ORC_STREAM_AB = 0, ORC_STREAM_AA = 1 };
 enum { ORC_MACRO_VOID = 0, ORC_MACRO_DEFAULT = 1, ORC_MACRO_MEAN = 2 };
 enum { ORC_INFLOW_NONE = 0, ORC_INFLOW_CONST = 1, ORC_INFLOW_PROFILE_YZ = 2 };

@@ -258,4 +258,6 @@ int ref_dispatch_d3q27_srtmf(const RefCall& c);
 int ref_dispatch_d3q27_cum2017(const RefCall& c);
 int ref_dispatch_d3q27_cumaa(const RefCall& c);
 int ref_dispatch_d3q27_cum2017aa(const RefCall& c);
+int ref_dispatch_d3q27_kbc_n(const RefCall& c);
+int ref_dispatch_d3q27_kbc_c(const RefCall& c);
 int ref_dispatch_d2q9(const RefCall& c);

@@ -7,6 +7,7 @@
 #include "lbm3d/d3q27/bc.h"
 #include "lbm3d/d3q27/eq.h"
 #include "lbm3d/d3q27/eq_inv_cum.h"
+#include "lbm3d/d3q27/eq_entropic.h"
 #ifdef AA_PATTERN
 	#include "lbm3d/d3q27/streaming_AA.h"
 #else
@@ -50,7 +51,7 @@ int ref_dispatch3_te(const RefCall& c)
 }
 
 // EXTRAS_INV: also instantiate the non-default MACRO / inflow flavours for the EQ_INV_CUM composition
-template <template <typename, typename> class COLLT, bool EXTRAS_INV>
+template <template <typename, typename> class COLLT, bool EXTRAS_INV, bool ENTROPIC = false>
 int ref_dispatch3(const RefCall& c)
 {
 	if (c.d->lattice != ORC_D3Q27)
@@ -68,5 +69,9 @@ int ref_dispatch3(const RefCall& c)
 	if (c.d->eq == ORC_EQ_INV_CUM)
 		return dp ? ref_dispatch3_te<TraitsDP, COLLT, D3Q27_EQ_INV_CUM, EXTRAS_INV>(c)
 				  : ref_dispatch3_te<TraitsSP, COLLT, D3Q27_EQ_INV_CUM, EXTRAS_INV>(c);
+	if constexpr (ENTROPIC) {
+		if (c.d->eq == ORC_EQ_ENTROPIC)
+			return dp ? ref_dispatch3_te<TraitsDP, COLLT, D3Q27_EQ_ENTROPIC, false>(c) : ref_dispatch3_te<TraitsSP, COLLT, D3Q27_EQ_ENTROPIC, false>(c);
+	}
 	return -1;
 }

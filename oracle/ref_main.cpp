@@ -22,6 +22,10 @@ static int ref_dispatch(const RefCall& c)
 		return r;
 	if ((r = ref_dispatch_d3q27_cum2017aa(c)) != -1)
 		return r;
+	if ((r = ref_dispatch_d3q27_kbc_n(c)) != -1)
+		return r;
+	if ((r = ref_dispatch_d3q27_kbc_c(c)) != -1)
+		return r;
 	if ((r = ref_dispatch_d2q9(c)) != -1)
 		return r;
 	return -1;

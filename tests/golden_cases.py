@@ -78,6 +78,15 @@ CASES = [
     Case("cum2017aa_f64_ab_zoo", O.Desc(coll=O.CUM_2017_ANTIALIAS, eq=O.EQ_INV_CUM, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("cum2017aa_f32_ab_zoo", O.Desc(coll=O.CUM_2017_ANTIALIAS, eq=O.EQ_INV_CUM, streaming=O.AB, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("cum2017aa_f64_aa_box", O.Desc(coll=O.CUM_2017_ANTIALIAS, eq=O.EQ_INV_CUM, streaming=O.AA, X=12, Y=12, Z=12), O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 40, "smooth"),
+    Case("kbcn1_f64_ab_zoo", O.Desc(coll=O.KBC_N1, eq=O.EQ_STD, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("kbcn2_f32_aa_zoo", O.Desc(coll=O.KBC_N2, eq=O.EQ_ENTROPIC, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("kbcn3_f64_aa_zoo", O.Desc(coll=O.KBC_N3, eq=O.EQ_ENTROPIC, streaming=O.AA, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("kbcn4_f32_ab_zoo", O.Desc(coll=O.KBC_N4, eq=O.EQ_ENTROPIC, streaming=O.AB, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("kbcc1_f32_ab_zoo", O.Desc(coll=O.KBC_C1, eq=O.EQ_STD, streaming=O.AB, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("kbcc2_f64_ab_zoo", O.Desc(coll=O.KBC_C2, eq=O.EQ_ENTROPIC, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("kbcc3_f32_aa_zoo", O.Desc(coll=O.KBC_C3, eq=O.EQ_ENTROPIC, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("kbcc4_f64_aa_zoo", O.Desc(coll=O.KBC_C4, eq=O.EQ_ENTROPIC, streaming=O.AA, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("kbcn4_f64_aa_box", O.Desc(coll=O.KBC_N4, eq=O.EQ_ENTROPIC, streaming=O.AA, X=12, Y=12, Z=12), O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 40, "smooth"),
     Case("cum_f64_ab_void", O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, macro=O.MACRO_VOID, X=8, Y=7, Z=6), _p3(), lambda d: lc.map_random_ab(d, seed=3), 3),
 ]
 

@@ -87,6 +87,13 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
             cmd = [NVCC, *ARCH, *COMMON, "-fmad=false", "-DLBMX_STRICT=1", "-Xptxas", "-v", f"-DLBMX_FAMILY={fam}_strict", f"-DLBMX_LAT={lat}",
                    f"-DLBMX_KIND={kind}", f"-DLBMX_REAL={real}", "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]
             tasks.append((cmd, obj))
+    # KBC family: built once, in the reference's association without FMA contraction; serves both arithmetic modes
+    for name, kind in (("n1", "K_KBC_N1"), ("n2", "K_KBC_N2"), ("n3", "K_KBC_N3"), ("n4", "K_KBC_N4"), ("c1", "K_KBC_C1"), ("c2", "K_KBC_C2"), ("c3", "K_KBC_C3"), ("c4", "K_KBC_C4")):
+        for real in ("float", "double"):
+            obj = os.path.join(OBJ, f"inst_d3q27_kbc{name}_{real}_strict.o")
+            cmd = [NVCC, *ARCH, *COMMON, "-fmad=false", "-DLBMX_STRICT=1", "-Xptxas", "-v", f"-DLBMX_FAMILY=d3q27_kbc{name}_strict", "-DLBMX_LAT=D3Q27",
+                   f"-DLBMX_KIND={kind}", f"-DLBMX_REAL={real}", "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]
+            tasks.append((cmd, obj))
     eng = os.path.join(OBJ, "engine.o")
     tasks.append(([NVCC, *ARCH, *COMMON, "-c", os.path.join(CSRC, "engine.cu"), "-o", eng], eng))
     jobs = jobs or min(len(tasks), os.cpu_count() or 4)

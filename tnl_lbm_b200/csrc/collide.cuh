@@ -140,6 +140,39 @@ LBMX_D void equilibrium(R (&feq)[27], int eqkind, R rho, R vx, R vy, R vz)
 	}
 }
 
+// d3q27/eq_entropic.h:11-211 (default equilibrium of D3Q27_KBC_N2..N4, C2..C4): rho * W(cx) W(cy) W(cz) * prod_a (2 - s_a) *
+// prod_a B_a^{c_a}, s_a = sqrt(1 + 3 v_a^2), B_a = (2 v_a + s_a) / (1 - v_a), evaluated left to right as the reference writes it.
+// Its unqualified sqrt() is ::sqrt(double) in the host build: for dreal = float the chain is in double from the first (2 - s_a)
+// on and rounded once at the end.  Only initialisation and boundary cells use an equilibrium of this family, so the double
+// arithmetic is off the hot path.
+template <typename R>
+LBMX_D void equilibrium_entropic(R (&feq)[27], R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R v[3] = {vx, vy, vz};
+	double s[3], B[3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		s[a] = sqrt(double(R(1) + R(3) * v[a] * v[a]));
+		B[a] = (double(R(2) * v[a]) + s[a]) / double(R(1) - v[a]);
+	}
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr R w6 = R(1.0 / 6.0), w23 = R(2.0 / 3.0);
+		constexpr R w = (L::cx(q) ? w6 : w23) * (L::cy(q) ? w6 : w23) * (L::cz(q) ? w6 : w23);
+		double chain = double(w) * (2.0 - s[0]) * (2.0 - s[1]) * (2.0 - s[2]);
+		static_for<3>([&](auto ac) {
+			constexpr int a = ac;
+			constexpr int c = a == 0 ? L::cx(q) : (a == 1 ? L::cy(q) : L::cz(q));
+			if constexpr (c < 0)
+				chain = chain * 1.0 / B[a];
+			else if constexpr (c > 0)
+				chain = chain * B[a];
+		});
+		feq[q] = R(double(rho) * chain);
+	});
+}
+
 template <typename R>
 LBMX_D void equilibrium(R (&feq)[9], int, R rho, R vx, R vy, R)
 {
@@ -605,16 +638,34 @@ LBMX_D void collide_mrt(R (&f)[19], const Phys<R>& P, R rho, R vx, R vy, R vz)
 	});
 }
 
+// equilibrium for initialisation and boundary cells: every family the solver may name as EQ (eqkind 3 = entropic, D3Q27 only)
+template <typename R>
+LBMX_D void equilibrium_any(R (&feq)[27], int eqkind, R rho, R vx, R vy, R vz)
+{
+	if (eqkind == 3)
+		equilibrium_entropic(feq, rho, vx, vy, vz);
+	else
+		equilibrium(feq, eqkind, rho, vx, vy, vz);
+}
+template <typename R, int Q>
+LBMX_D void equilibrium_any(R (&feq)[Q], int eqkind, R rho, R vx, R vy, R vz)
+{
+	equilibrium(feq, eqkind, rho, vx, vy, vz);
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // operator tags: what COLL means for a kernel instantiation
 // --------------------------------------------------------------------------------------------------------------------
-enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 /* D2Q9_CLBM or D3Q27_CLBM, by lattice */, K_SRT_MF = 5, K_CUM_2017 = 10, K_CUM_AALIAS = 11, K_CUM_2017_AALIAS = 12 /* D3Q27_CUM built with the switches of defs.h:254-255 */ };
+enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 /* D2Q9_CLBM or D3Q27_CLBM, by lattice */, K_SRT_MF = 5, K_CUM_2017 = 10, K_CUM_AALIAS = 11, K_CUM_2017_AALIAS = 12 /* D3Q27_CUM built with the switches of defs.h:254-255 */,
+						K_KBC_N1 = 13, K_KBC_N2, K_KBC_N3, K_KBC_N4, K_KBC_C1, K_KBC_C2, K_KBC_C3, K_KBC_C4 };
 
 template <int KIND, typename R>
 LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
 	if constexpr (KIND == K_CLBM)
 		ext::collide_clbm<! kStrict>(f, P, rho, vx, vy, vz);
+	else if constexpr (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
+		ext::collide_kbc<(KIND >= K_KBC_C1), ((KIND - K_KBC_N1) % 4 == 1 || (KIND - K_KBC_N1) % 4 == 3), ((KIND - K_KBC_N1) % 4 >= 2)>(f, P, rho, vx, vy, vz);
 	else if constexpr (KIND == K_CUM_2017)
 		strict::collide_cum<true, false>(f, P, rho, vx, vy, vz);
 	else if constexpr (KIND == K_CUM_AALIAS)

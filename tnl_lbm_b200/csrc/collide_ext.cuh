@@ -7,6 +7,7 @@
 //
 //   D3Q27_CLBM             d3q27/col_clbm.h:6-447
 //   D3Q27_SRT_MODIF_FORCE  d3q27/col_srt_modif_force.h:9-120
+//   D3Q27_KBC_N1..N4, C1..C4  d3q27/col_kbc_n.h:254-1272, col_kbc_c.h:283-1301
 #pragma once
 #include "lattice.cuh"
 
@@ -300,6 +301,211 @@ LBMX_D void collide_srt_modif(R (&f)[27], const R (&feq)[27], const PHYS& P, R v
 			f[q] += (feq[q] - f[q]) * itau + pre * modif_force_source_fast<q>(v, F);
 		});
 	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// KBC family (d3q27/col_kbc_n.h:254-1272, col_kbc_c.h:283-1301): f = k + s + h, the shear part s relaxes with 2 beta, the
+// higher-order part h with gamma * beta (gamma: entropic stabiliser).  One template covers the eight models:
+//   CENTRAL = false: N1..N4, s from raw moments;  true: C1..C4, s from central moments
+//   USE_T, USE_Q: s = D (+ T) (+ Q)   ->   N1/C1: D, N2/C2: D+T, N3/C3: D+Q, N4/C4: D+T+Q
+// ---------------------------------------------------------------------------------------------------------------------------
+struct KbcMoments
+{
+	enum { M200, M020, M002, M110, M101, M011, M111, M201, M102, M210, M120, M021, M012, COUNT };
+	// populations of every raw moment in the order the reference adds them up (col_kbc_n.h:351-386); -1 = end of list
+	LBMX_HD static constexpr int member(int moment, int i)
+	{
+		constexpr signed char t[COUNT][18] = {
+			{20, 22,  8, 24, 26, 10, 12, 14,  2, 25, 23,  9, 21, 19,  7, 13, 11,  1},  // M200
+			{20, 22,  8, 24, 26, 10, 16, 18,  4, 17, 15,  3, 25, 23,  9, 21, 19,  7},  // M020
+			{20, 22, 12, 14, 24, 26, 16, 18,  6,  5, 17, 15, 25, 23, 13, 11, 21, 19},  // M002
+			{20,  8, 22, 24, 10, 26, 25,  9, 23, 21,  7, 19, -1, -1, -1, -1, -1, -1},  // M110
+			{20, 22, 12, 14, 24, 26, 25, 23, 13, 11, 21, 19, -1, -1, -1, -1, -1, -1},  // M101
+			{20, 22, 24, 26, 16, 18, 17, 15, 25, 23, 21, 19, -1, -1, -1, -1, -1, -1},  // M011
+			{19, 22, 24, 26, 25, 23, 21, 20, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1},  // M111
+			{19, 22, 12, 14, 24, 26, 25, 23, 13, 11, 21, 20, -1, -1, -1, -1, -1, -1},  // M201
+			{19, 22, 12, 14, 24, 26, 25, 23, 13, 11, 21, 20, -1, -1, -1, -1, -1, -1},  // M102
+			{19,  8, 22, 24, 10, 26, 25,  9, 23, 21,  7, 20, -1, -1, -1, -1, -1, -1},  // M210
+			{19,  8, 22, 24, 10, 26, 25,  9, 23, 21,  7, 20, -1, -1, -1, -1, -1, -1},  // M120
+			{19, 22, 24, 26, 16, 18, 17, 15, 25, 23, 21, 20, -1, -1, -1, -1, -1, -1},  // M021
+			{19, 22, 24, 26, 16, 18, 17, 15, 25, 23, 21, 20, -1, -1, -1, -1, -1, -1},  // M012
+		};
+		return t[moment][i];
+	}
+	LBMX_HD static constexpr int power(int moment, int axis)
+	{
+		constexpr signed char t[COUNT][3] = {{2, 0, 0}, {0, 2, 0}, {0, 0, 2}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}, {2, 0, 1}, {1, 0, 2}, {2, 1, 0}, {1, 2, 0}, {0, 2, 1}, {0, 1, 2}};
+		return t[moment][axis];
+	}
+	LBMX_HD static constexpr int sign(int moment, int q)
+	{
+		int s = 1;
+		for (int a = 0; a < 3; a++)
+			for (int i = 0; i < power(moment, a); i++)
+				s *= dir_comp(q, a);
+		return s;
+	}
+};
+
+template <bool CENTRAL, typename R>
+LBMX_D R kbc_scale(R x, int den)  // raw-moment models multiply by 1/6, 1/4, 1/2, 1/8; central-moment models divide by 6, 4, 2, 8
+{
+	if constexpr (CENTRAL)
+		return x / R(den);
+	else
+		return x * (den == 6 ? R(1.0 / 6.0) : den == 4 ? R(0.25) : den == 2 ? R(0.5) : R(0.125));
+}
+
+// the shear-part tensors per direction (col_kbc_n.h:56-252, col_kbc_c.h:85-281)
+template <bool CENTRAL, int q, typename R>
+LBMX_D R kbc_tensor_d(R nxz, R nyz, R pxy, R pxz, R pyz)
+{
+	constexpr int cx = dir_comp(q, 0), cy = dir_comp(q, 1), cz = dir_comp(q, 2), n = (cx != 0) + (cy != 0) + (cz != 0);
+	if constexpr (n == 1)
+		return cx != 0 ? kbc_scale<CENTRAL>(R(2) * nxz - nyz, 6) : (cy != 0 ? kbc_scale<CENTRAL>(-nxz + R(2) * nyz, 6) : kbc_scale<CENTRAL>(-nxz - nyz, 6));
+	else if constexpr (n == 2) {
+		const R p = cz == 0 ? pxy : (cy == 0 ? pxz : pyz);
+		constexpr int s = cz == 0 ? cx * cy : (cy == 0 ? cx * cz : cy * cz);
+		return s > 0 ? kbc_scale<CENTRAL>(p, 4) : kbc_scale<CENTRAL>(-p, 4);
+	}
+	else
+		return R(0);
+}
+template <bool CENTRAL, int q, typename R>
+LBMX_D R kbc_tensor_q(R qxxy, R qxxz, R qxyy, R qyyz, R qxzz, R qyzz, R qxyz)
+{
+	constexpr int cx = dir_comp(q, 0), cy = dir_comp(q, 1), cz = dir_comp(q, 2), n = (cx != 0) + (cy != 0) + (cz != 0);
+	if constexpr (n == 1) {
+		const R s = cx != 0 ? (qxyy + qxzz) : (cy != 0 ? (qxxy + qyzz) : (qxxz + qyyz));
+		return (cx + cy + cz) > 0 ? kbc_scale<CENTRAL>(-s, 2) : kbc_scale<CENTRAL>(s, 2);
+	}
+	else if constexpr (n == 2) {
+		const R a = cz == 0 ? qxyy : (cy == 0 ? qxzz : qyzz), b = cz == 0 ? qxxy : (cy == 0 ? qxxz : qyyz);
+		constexpr int sa = cz == 0 ? cx : (cy == 0 ? cx : cy), sb = cz == 0 ? cy : cz;
+		const R ta = sa > 0 ? a : -a;
+		return kbc_scale<CENTRAL>(sb > 0 ? ta + b : ta - b, 4);
+	}
+	else if constexpr (n == 3)
+		return cx * cy * cz > 0 ? kbc_scale<CENTRAL>(qxyz, 8) : kbc_scale<CENTRAL>(-qxyz, 8);
+	else
+		return R(0);
+}
+
+template <bool CENTRAL, bool USE_T, bool USE_Q, typename R, typename PHYS>
+LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	using KM = KbcMoments;
+	const R one = R(1), two = R(2), three = R(3), six = R(6), half = R(0.5), third = R(1.0 / 3.0);
+	const R v[3] = {vx, vy, vz};
+	R g[3][3];	// product-form equilibrium factors (col_kbc_n.h:293-321), as in col_bgk.h
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R z = third - one + v[a] * v[a];
+		const R p = -half * (z + one + v[a]);
+		g[a][1] = z;
+		g[a][2] = p;
+		g[a][0] = p + v[a];
+	}
+	R M[KM::COUNT];
+	static_for<KM::COUNT>([&](auto kc) {
+		constexpr int k = kc;
+		R acc = R(0);
+		static_for<18>([&](auto ic) {
+			constexpr int i = ic;
+			constexpr int q = KM::member(k, i);
+			if constexpr (q >= 0) {
+				if constexpr (i == 0)
+					acc = KM::sign(k, q) > 0 ? f[q] : -f[q];
+				else
+					acc = KM::sign(k, q) > 0 ? acc + f[q] : acc - f[q];
+			}
+		});
+		M[k] = acc;
+	});
+	R T = (M[KM::M200] + M[KM::M020] + M[KM::M002]), Nxz = (M[KM::M200] - M[KM::M002]), Nyz = (M[KM::M020] - M[KM::M002]);
+	R Pxy = M[KM::M110], Pxz = M[KM::M101], Pyz = M[KM::M011];
+	R Qxxy = M[KM::M210], Qxxz = M[KM::M201], Qxyy = M[KM::M120], Qyyz = M[KM::M021], Qxzz = M[KM::M102], Qyzz = M[KM::M012], Qxyz = M[KM::M111];
+	R eT, eNxz = 0, eNyz = 0, ePxy = 0, ePxz = 0, ePyz = 0, eQxxy = 0, eQxxz = 0, eQxyy = 0, eQyyz = 0, eQxzz = 0, eQyzz = 0, eQxyz = 0;
+	if constexpr (! CENTRAL) {	// col_kbc_n.h:28-54
+		eT = (rho * (three * third + vx * vx + vy * vy + vz * vz));
+		eNxz = (rho * (vx * vx - vz * vz));
+		eNyz = (rho * (vy * vy - vz * vz));
+		ePxy = (rho * vx * vy);
+		ePxz = (rho * vx * vz);
+		ePyz = (rho * vy * vz);
+		eQxxy = (rho * vy * (third + vx * vx));
+		eQxxz = (rho * vz * (third + vx * vx));
+		eQxyy = (rho * vx * (third + vy * vy));
+		eQyyz = (rho * vz * (third + vy * vy));
+		eQxzz = (rho * vx * (third + vz * vz));
+		eQyzz = (rho * vy * (third + vz * vz));
+		eQxyz = (rho * vx * vy * vz);
+	}
+	else {	// col_kbc_c.h:56-83: central moments; their equilibria are 0 except the trace
+		const R rT = T, rNxz = Nxz, rNyz = Nyz, rPxy = Pxy, rPxz = Pxz, rPyz = Pyz;
+		const R rQxxy = Qxxy, rQxxz = Qxxz, rQxyy = Qxyy, rQyyz = Qyyz, rQxzz = Qxzz, rQyzz = Qyzz, rQxyz = Qxyz;
+		T = (rT - rho * (vx * vx + vy * vy + vz * vz));
+		Nxz = (rNxz + rho * (vz * vz - vx * vx));
+		Nyz = (rNyz + rho * (vz * vz - vy * vy));
+		Pxy = (rPxy - rho * vx * vy);
+		Pxz = (rPxz - rho * vx * vz);
+		Pyz = (rPyz - rho * vy * vz);
+		Qxxy = (rQxxy - third * (six * vx * Pxy + vy * (three * vx * vx + two * Nxz - Nyz + T)));
+		Qxxz = (rQxxz - third * (six * vx * Pxz + vz * (three * vx * vx + two * Nxz - Nyz + T)));
+		Qxyy = (rQxyy - third * (six * vy * Pxy + vx * (three * vy * vy + two * Nyz - Nxz + T)));
+		Qyyz = (rQyyz - third * (six * vy * Pyz + vz * (three * vy * vy + two * Nyz - Nxz + T)));
+		Qxzz = (rQxzz - third * (six * vz * Pxz + vx * (three * vz * vz - Nyz - Nxz + T)));
+		Qyzz = (rQyzz - third * (six * vz * Pyz + vy * (three * vz * vz - Nyz - Nxz + T)));
+		Qxyz = (rQxyz - vx * Pyz - vy * Pxz - vz * Pxy - vx * vy * vz);
+		eT = (rho * three * third);
+	}
+	R feq[27], Ds[27], Dh[27];
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int n = (L::cx(q) != 0) + (L::cy(q) != 0) + (L::cz(q) != 0);
+		feq[q] = -rho * g[0][L::cx(q) + 1] * g[1][L::cy(q) + 1] * g[2][L::cz(q) + 1];
+		R acc = R(0);
+		if constexpr (n == 1 || n == 2) {
+			acc = kbc_tensor_d<CENTRAL, q>(Nxz, Nyz, Pxy, Pxz, Pyz);
+			if constexpr (! CENTRAL)
+				acc = acc - kbc_tensor_d<CENTRAL, q>(eNxz, eNyz, ePxy, ePxz, ePyz);
+		}
+		if constexpr (USE_T && n <= 1) {
+			const R t = n == 0 ? -T : kbc_scale<CENTRAL>(T, 6), et = n == 0 ? -eT : kbc_scale<CENTRAL>(eT, 6);
+			acc = (acc + t) - et;
+		}
+		if constexpr (USE_Q && n >= 1) {
+			acc = acc + kbc_tensor_q<CENTRAL, q>(Qxxy, Qxxz, Qxyy, Qyyz, Qxzz, Qyzz, Qxyz);
+			if constexpr (! CENTRAL)
+				acc = acc - kbc_tensor_q<CENTRAL, q>(eQxxy, eQxxz, eQxyy, eQyyz, eQxzz, eQyzz, eQxyz);
+		}
+		Ds[q] = acc;
+		Dh[q] = f[q] - feq[q] - Ds[q];
+	});
+	const R beta = (one / (two * P.nu / third + one));
+	// <Ds|Dh> and <Dh|Dh> (weights 1/feq), summed in the order mmm, mmz, mmp, mzm, ... ppp (col_kbc_n.h:233-252)
+	R sd = R(0), hh = R(0);
+	static_for<27>([&](auto ic) {
+		constexpr int i = ic;
+		constexpr int q = L::find(i / 9 - 1, (i / 3) % 3 - 1, i % 3 - 1);
+		const R ifeq = one / feq[q];
+		const R t1 = Ds[q] * Dh[q] * ifeq, t2 = Dh[q] * Dh[q] * ifeq;
+		if constexpr (i == 0) {
+			sd = t1;
+			hh = t2;
+		}
+		else {
+			sd = sd + t1;
+			hh = hh + t2;
+		}
+	});
+	const R gamma = (one / beta - (two - one / beta) * sd / hh);
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		const R S = strict::force_projection(L::cx(q), L::cy(q), L::cz(q), vx, vy, vz, P) / rho;
+		f[q] -= beta * (two * Ds[q] + gamma * Dh[q]) - (one - beta) * S * feq[q];
+	});
 }
 
 }  // namespace ext

@@ -414,6 +414,18 @@ int step_dispatch(lbmx_engine* e, int64_t nsteps)
 bool pick_kernels(lbmx_engine* e)
 {
 	const lbmx_desc& d = e->d;
+	if (d.lattice == LBMX_D3Q27 && d.coll >= LBMX_COLL_KBC_N1 && d.coll <= LBMX_COLL_KBC_C4) {
+		switch (d.coll) {
+			case LBMX_COLL_KBC_N1: return e->f64() ? get_kernels_d3q27_kbcn1_strict(e->kd) : get_kernels_d3q27_kbcn1_strict(e->kf);
+			case LBMX_COLL_KBC_N2: return e->f64() ? get_kernels_d3q27_kbcn2_strict(e->kd) : get_kernels_d3q27_kbcn2_strict(e->kf);
+			case LBMX_COLL_KBC_N3: return e->f64() ? get_kernels_d3q27_kbcn3_strict(e->kd) : get_kernels_d3q27_kbcn3_strict(e->kf);
+			case LBMX_COLL_KBC_N4: return e->f64() ? get_kernels_d3q27_kbcn4_strict(e->kd) : get_kernels_d3q27_kbcn4_strict(e->kf);
+			case LBMX_COLL_KBC_C1: return e->f64() ? get_kernels_d3q27_kbcc1_strict(e->kd) : get_kernels_d3q27_kbcc1_strict(e->kf);
+			case LBMX_COLL_KBC_C2: return e->f64() ? get_kernels_d3q27_kbcc2_strict(e->kd) : get_kernels_d3q27_kbcc2_strict(e->kf);
+			case LBMX_COLL_KBC_C3: return e->f64() ? get_kernels_d3q27_kbcc3_strict(e->kd) : get_kernels_d3q27_kbcc3_strict(e->kf);
+			case LBMX_COLL_KBC_C4: return e->f64() ? get_kernels_d3q27_kbcc4_strict(e->kd) : get_kernels_d3q27_kbcc4_strict(e->kf);
+		}
+	}
 	if (d.flags & LBMX_FLAG_STRICT_ARITH) {	 // parity arithmetic (lattices checked by the caller)
 		if (d.lattice == LBMX_D3Q27) {
 			switch (d.coll) {
@@ -614,8 +626,10 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 		return fail(LBMX_ERR_ARG, "lbmx_create: streaming");
 	if (d.macro < LBMX_MACRO_VOID || d.macro > LBMX_MACRO_MEAN || d.inflow < LBMX_INFLOW_NONE || d.inflow > LBMX_INFLOW_PROFILE_YZ)
 		return fail(LBMX_ERR_ARG, "lbmx_create: macro / inflow selector");
-	if (d.eq != LBMX_EQ_STD && d.eq != LBMX_EQ_INV_CUM)
+	if (d.eq != LBMX_EQ_STD && d.eq != LBMX_EQ_INV_CUM && d.eq != LBMX_EQ_ENTROPIC)
 		return fail(LBMX_ERR_ARG, "lbmx_create: eq selector");
+	if (d.eq == LBMX_EQ_ENTROPIC && ! (d.lattice == LBMX_D3Q27 && d.coll >= LBMX_COLL_KBC_N1 && d.coll <= LBMX_COLL_KBC_C4))
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: LBMX_EQ_ENTROPIC is available with the D3Q27 KBC operators (where only initialisation and boundary cells evaluate it)");
 	if (d.lattice == LBMX_D2Q9 && d.eq != LBMX_EQ_STD)
 		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: D2Q9 has only the polynomial equilibrium (d2q9/eq.h)");
 	if (d.nranks < 1 || d.rank < 0 || d.rank >= d.nranks)

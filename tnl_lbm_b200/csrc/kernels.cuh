@@ -248,6 +248,8 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 template <int KIND, typename R, int MODE>
 constexpr int bulk_minblocks()
 {
+	if (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)  // f, feq, delta-s and delta-h of all 27 populations are live at once
+		return sizeof(R) == 8 ? 2 : 3;
 	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_SRT_MF || KIND == K_CLBM))
 		return LBMX_BULK_MINBLOCKS < 3 ? LBMX_BULK_MINBLOCKS : 3;
 	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
 	};
 	auto set_equilibrium = [&]() {
 		R feq[L::Q];
-		equilibrium(feq, p.eq, rho, vx, vy, vz);
+		equilibrium_any(feq, p.eq, rho, vx, vy, vz);
 		static_for<L::Q>([&](auto qc) { f[qc] = feq[qc]; });
 	};
 	if (m == L::INFLOW) {
@@ -516,8 +518,8 @@ __global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
 	else if (m == L::OUTFLOW_RIGHT_INTERP) {
 		density_velocity(f, p.phys, rho, vx, vy, vz);
 		R e1[L::Q], e0[L::Q];
-		equilibrium(e1, p.eq, R(1), vx, vy, vz);
-		equilibrium(e0, p.eq, rho, vx, vy, vz);
+		equilibrium_any(e1, p.eq, R(1), vx, vy, vz);
+		equilibrium_any(e0, p.eq, rho, vx, vy, vz);
 		static_for<L::Q>([&](auto qc) { f[qc] += e1[qc] - e0[qc]; });  // setEquilibriumDecomposition (common.h:94-124)
 		rho = R(1);
 	}
@@ -581,7 +583,7 @@ __global__ void k_set_equilibrium(R* df, long long XYZ, long long n_cells, long 
 	// the reference narrows the `real` (double) arguments to dreal at the call of EQ::eq_* (common.h:126-158)
 	const R r = (R) (rho ? rho[i] : crho), ux = (R) (rho ? vx[i] : cvx), uy = (R) (rho ? vy[i] : cvy), uz = (R) (rho ? (vz ? vz[i] : 0.0) : cvz);
 	R feq[L::Q];
-	equilibrium(feq, eq, r, ux, uy, uz);
+	equilibrium_any(feq, eq, r, ux, uy, uz);
 	static_for<L::Q>([&](auto qc) { df[qc * XYZ + cell0 + i] = feq[qc]; });
 }
 
@@ -675,6 +677,23 @@ bool get_kernels_d3q27_cum2017aa(StepKernels<float>&);
 bool get_kernels_d3q27_cum2017aa(StepKernels<double>&);
 bool get_kernels_d3q27_cum2017aa_strict(StepKernels<float>&);
 bool get_kernels_d3q27_cum2017aa_strict(StepKernels<double>&);
+// KBC family: one build, in the reference's association without FMA contraction (serves both arithmetic modes)
+bool get_kernels_d3q27_kbcn1_strict(StepKernels<float>&);
+bool get_kernels_d3q27_kbcn1_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcn2_strict(StepKernels<float>&);
+bool get_kernels_d3q27_kbcn2_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcn3_strict(StepKernels<float>&);
+bool get_kernels_d3q27_kbcn3_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcn4_strict(StepKernels<float>&);
+bool get_kernels_d3q27_kbcn4_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcc1_strict(StepKernels<float>&);
+bool get_kernels_d3q27_kbcc1_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcc2_strict(StepKernels<float>&);
+bool get_kernels_d3q27_kbcc2_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcc3_strict(StepKernels<float>&);
+bool get_kernels_d3q27_kbcc3_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcc4_strict(StepKernels<float>&);
+bool get_kernels_d3q27_kbcc4_strict(StepKernels<double>&);
 bool get_kernels_d3q27_clbm(StepKernels<float>&);
 bool get_kernels_d3q27_clbm(StepKernels<double>&);
 bool get_kernels_d3q27_srtmf(StepKernels<float>&);

@@ -405,6 +405,8 @@ struct D3Q27_EQ { static constexpr int lbmx_eq = LBMX_EQ_STD; };
 template <typename TRAITS>
 struct D3Q27_EQ_INV_CUM { static constexpr int lbmx_eq = LBMX_EQ_INV_CUM; };
 template <typename TRAITS>
+struct D3Q27_EQ_ENTROPIC { static constexpr int lbmx_eq = LBMX_EQ_ENTROPIC; };
+template <typename TRAITS>
 struct D2Q9_EQ { static constexpr int lbmx_eq = LBMX_EQ_STD; };
 
 // collision operators (tags; `id` strings as in the reference, e.g. col_cum.h:11)
@@ -431,6 +433,14 @@ LBMX_COLL_TAG(D3Q27_BGK, D3Q27_EQ, LBMX_COLL_BGK, "BGK")
 LBMX_COLL_TAG(D3Q27_MRT, D3Q27_EQ, LBMX_COLL_MRT_LES, "MRT_LES")
 LBMX_COLL_TAG(D3Q27_CLBM, D3Q27_EQ, LBMX_COLL_CLBM, "CLBM")
 LBMX_COLL_TAG(D3Q27_SRT_MODIF_FORCE, D3Q27_EQ, LBMX_COLL_SRT_MODIF_FORCE, "SRT_MRT_MODIF_FORCE")
+LBMX_COLL_TAG(D3Q27_KBC_N1, D3Q27_EQ, LBMX_COLL_KBC_N1, "KBC_N1")
+LBMX_COLL_TAG(D3Q27_KBC_N2, D3Q27_EQ_ENTROPIC, LBMX_COLL_KBC_N2, "KBC_N2")
+LBMX_COLL_TAG(D3Q27_KBC_N3, D3Q27_EQ_ENTROPIC, LBMX_COLL_KBC_N3, "KBC_N3")
+LBMX_COLL_TAG(D3Q27_KBC_N4, D3Q27_EQ_ENTROPIC, LBMX_COLL_KBC_N4, "KBC_N4")
+LBMX_COLL_TAG(D3Q27_KBC_C1, D3Q27_EQ, LBMX_COLL_KBC_C1, "KBC_C1")
+LBMX_COLL_TAG(D3Q27_KBC_C2, D3Q27_EQ_ENTROPIC, LBMX_COLL_KBC_C2, "KBC_C2")
+LBMX_COLL_TAG(D3Q27_KBC_C3, D3Q27_EQ_ENTROPIC, LBMX_COLL_KBC_C3, "KBC_C3")
+LBMX_COLL_TAG(D3Q27_KBC_C4, D3Q27_EQ_ENTROPIC, LBMX_COLL_KBC_C4, "KBC_C4")
 LBMX_COLL_TAG(D2Q9_SRT, D2Q9_EQ, LBMX_COLL_SRT, "SRT")
 LBMX_COLL_TAG(D2Q9_CLBM, D2Q9_EQ, LBMX_COLL_CLBM, "CLBM")
 #undef LBMX_COLL_TAG

@@ -68,5 +68,14 @@ int main()
 	r |= run<double, K_CUM_AALIAS>(ORC_COLL_CUM_ANTIALIAS, ORC_EQ_INV_CUM, ORC_F64);
 	r |= run<float, K_CUM_2017_AALIAS>(ORC_COLL_CUM_2017_ANTIALIAS, ORC_EQ_INV_CUM, ORC_F32);
 	r |= run<double, K_CUM_2017_AALIAS>(ORC_COLL_CUM_2017_ANTIALIAS, ORC_EQ_INV_CUM, ORC_F64);
+	r |= run<float, K_KBC_N1>(ORC_COLL_KBC_N1, ORC_EQ_STD, ORC_F32);
+	r |= run<double, K_KBC_N2>(ORC_COLL_KBC_N2, ORC_EQ_STD, ORC_F64);
+	r |= run<float, K_KBC_N3>(ORC_COLL_KBC_N3, ORC_EQ_STD, ORC_F32);
+	r |= run<double, K_KBC_N4>(ORC_COLL_KBC_N4, ORC_EQ_STD, ORC_F64);
+	r |= run<float, K_KBC_C1>(ORC_COLL_KBC_C1, ORC_EQ_STD, ORC_F32);
+	r |= run<double, K_KBC_C2>(ORC_COLL_KBC_C2, ORC_EQ_STD, ORC_F64);
+	r |= run<float, K_KBC_C3>(ORC_COLL_KBC_C3, ORC_EQ_STD, ORC_F32);
+	r |= run<float, K_KBC_C4>(ORC_COLL_KBC_C4, ORC_EQ_STD, ORC_F32);
+	r |= run<double, K_KBC_C4>(ORC_COLL_KBC_C4, ORC_EQ_STD, ORC_F64);
 	return r;
 }
