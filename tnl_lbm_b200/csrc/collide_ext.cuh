@@ -460,11 +460,16 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 		Qxyz = (rQxyz - vx * Pyz - vy * Pxz - vz * Pxy - vx * vy * vz);
 		eT = (rho * three * third);
 	}
-	R feq[27], Ds[27], Dh[27];
-	static_for<27>([&](auto qc) {
+	// feq, delta-s and delta-h of a population are cheap functions of 9 equilibrium factors and 13 moments: they are recomputed
+	// in the two passes below instead of being stored (4 x 27 live values cost more registers than the kernel can keep resident;
+	// the recomputation is the same expression, so the result is unchanged)
+	auto feq_of = [&](auto qc) -> R {
+		constexpr int q = qc;
+		return -rho * g[0][L::cx(q) + 1] * g[1][L::cy(q) + 1] * g[2][L::cz(q) + 1];
+	};
+	auto ds_of = [&](auto qc) -> R {
 		constexpr int q = qc;
 		constexpr int n = (L::cx(q) != 0) + (L::cy(q) != 0) + (L::cz(q) != 0);
-		feq[q] = -rho * g[0][L::cx(q) + 1] * g[1][L::cy(q) + 1] * g[2][L::cz(q) + 1];
 		R acc = R(0);
 		if constexpr (n == 1 || n == 2) {
 			acc = kbc_tensor_d<CENTRAL, q>(Nxz, Nyz, Pxy, Pxz, Pyz);
@@ -480,17 +485,18 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 			if constexpr (! CENTRAL)
 				acc = acc - kbc_tensor_q<CENTRAL, q>(eQxxy, eQxxz, eQxyy, eQyyz, eQxzz, eQyzz, eQxyz);
 		}
-		Ds[q] = acc;
-		Dh[q] = f[q] - feq[q] - Ds[q];
-	});
+		return acc;
+	};
 	const R beta = (one / (two * P.nu / third + one));
 	// <Ds|Dh> and <Dh|Dh> (weights 1/feq), summed in the order mmm, mmz, mmp, mzm, ... ppp (col_kbc_n.h:233-252)
 	R sd = R(0), hh = R(0);
 	static_for<27>([&](auto ic) {
 		constexpr int i = ic;
 		constexpr int q = L::find(i / 9 - 1, (i / 3) % 3 - 1, i % 3 - 1);
-		const R ifeq = one / feq[q];
-		const R t1 = Ds[q] * Dh[q] * ifeq, t2 = Dh[q] * Dh[q] * ifeq;
+		const R fe = feq_of(std::integral_constant<int, q>{}), ds = ds_of(std::integral_constant<int, q>{});
+		const R dh = f[q] - fe - ds;
+		const R ifeq = one / fe;
+		const R t1 = ds * dh * ifeq, t2 = dh * dh * ifeq;
 		if constexpr (i == 0) {
 			sd = t1;
 			hh = t2;
@@ -503,8 +509,10 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 	const R gamma = (one / beta - (two - one / beta) * sd / hh);
 	static_for<27>([&](auto qc) {
 		constexpr int q = qc;
+		const R fe = feq_of(qc), ds = ds_of(qc);
+		const R dh = f[q] - fe - ds;
 		const R S = strict::force_projection(L::cx(q), L::cy(q), L::cz(q), vx, vy, vz, P) / rho;
-		f[q] -= beta * (two * Ds[q] + gamma * Dh[q]) - (one - beta) * S * feq[q];
+		f[q] -= beta * (two * ds + gamma * dh) - (one - beta) * S * fe;
 	});
 }
 

@@ -24,6 +24,10 @@
 #ifndef LBMX_BULK_MINBLOCKS
 	#define LBMX_BULK_MINBLOCKS 4  // __launch_bounds__ second argument (register cap = 65536 / (BLOCK * MINBLOCKS) = 128: 16 warps per SM)
 #endif
+#ifndef LBMX_KBC_MINBLOCKS_F64
+	#define LBMX_KBC_MINBLOCKS_F64 2  // KBC kernels: 27 populations + 13 moments + 9 equilibrium factors live
+	#define LBMX_KBC_MINBLOCKS_F32 3
+#endif
 #ifndef LBMX_BULK_MINBLOCKS_AB
 	#define LBMX_BULK_MINBLOCKS_AB 5  // the A-B kernel fits 96 registers without spilling and likes the extra occupancy (kbench: 6.68 vs 6.33 TB/s)
 #endif
@@ -248,8 +252,8 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 template <int KIND, typename R, int MODE>
 constexpr int bulk_minblocks()
 {
-	if (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)  // f, feq, delta-s and delta-h of all 27 populations are live at once
-		return sizeof(R) == 8 ? 2 : 3;
+	if (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
+		return sizeof(R) == 8 ? LBMX_KBC_MINBLOCKS_F64 : LBMX_KBC_MINBLOCKS_F32;
 	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_SRT_MF || KIND == K_CLBM))
 		return LBMX_BULK_MINBLOCKS < 3 ? LBMX_BULK_MINBLOCKS : 3;
 	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;

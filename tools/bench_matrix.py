@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tnl_lbm_b200 import binding as B  # noqa: E402
 
-NAMES = {B.CUM: "CUM", B.SRT: "SRT", B.BGK: "BGK", B.MRT_LES: "MRT_LES", B.CLBM: "CLBM", B.SRT_MODIF_FORCE: "SRT_MODIF_FORCE"}
+NAMES = {B.CUM: "CUM", B.SRT: "SRT", B.BGK: "BGK", B.MRT_LES: "MRT_LES", B.CLBM: "CLBM", B.SRT_MODIF_FORCE: "SRT_MODIF_FORCE", B.KBC_N1: "KBC_N1", B.KBC_N4: "KBC_N4", B.KBC_C4: "KBC_C4",
+         B.CUM_2017: "CUM (USE_GEIER_CUM_2017)", B.CUM_2017_ANTIALIAS: "CUM (2017 + ANTIALIAS)"}
 
 
 def run(lattice, coll, eq, prec, streaming, shape, steps, map_kind="periodic", macro=B.MACRO_DEFAULT, flags=0):
@@ -79,6 +80,9 @@ def main():
         for prec in (B.F64, B.F32):
             for st in (B.AA, B.AB):
                 cfgs.append(("D3Q27 ext", B.D3Q27, coll, eq, prec, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, 0))
+    for coll, eq in ((B.KBC_N1, B.EQ_STD), (B.KBC_N4, B.EQ_ENTROPIC), (B.KBC_C4, B.EQ_ENTROPIC), (B.CUM_2017, B.EQ_INV_CUM), (B.CUM_2017_ANTIALIAS, B.EQ_INV_CUM)):
+        for prec in (B.F64, B.F32):
+            cfgs.append(("D3Q27 ext2", B.D3Q27, coll, eq, prec, B.AA, (384, 384, 384), "periodic", B.MACRO_DEFAULT, 0))
     for st in (B.AA, B.AB):
         cfgs.append(("D3Q27 ext MACRO_Mean (+13 RMW fields: 640 B per update)", B.D3Q27, B.CUM, B.EQ_INV_CUM, B.F64, st, (320, 320, 320), "periodic", B.MACRO_MEAN, 0))
         cfgs.append(("D3Q27 ext parity arithmetic", B.D3Q27, B.CUM, B.EQ_INV_CUM, B.F64, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, B.FLAG_STRICT_ARITH))
