@@ -69,6 +69,20 @@ def test_step_batching_is_invisible(name):
     assert np.array_equal(a_df, c_df) and np.array_equal(a_mac, c_mac)
 
 
+@pytest.mark.parametrize("name", ["d2q9_srt_f64_ab_cavity", "cum_f64_aa_box", "cum_f64_ab_sim1", "cum_f64_aa_duct", "d2q9_clbm_f64_ab_channel"])
+@pytest.mark.parametrize("policy", ["last", "every"])
+def test_graph_replay_is_invisible(name, policy):
+    """Batches of >= 8 steps on a small single slab replay captured step pairs (CUDA graph); odd chunk sizes make the batches start
+    at odd iterations and change the parameters in between.  Identical to stepping one by one, for both macro policies."""
+    case = gc.BY_NAME[name]
+    kw = dict(macro_policy=B.MACRO_EVERY_STEP) if policy == "every" else {}
+    one_df, one_mac, one_stats = run_case_engine(case, chunk=1, **kw)
+    for chunk in (None, 9, 11):
+        df, mac, stats = run_case_engine(case, chunk=chunk, **kw)
+        assert np.array_equal(df, one_df) and np.array_equal(mac, one_mac), (name, policy, chunk)
+        assert stats.kernel_launches == one_stats.kernel_launches  # replayed launches are counted like plain ones
+
+
 def test_map_round_trip_is_bit_exact():
     case = gc.BY_NAME["cum_f64_ab_zoo"]
     m = case.make_map(case.desc)

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -189,6 +190,13 @@ struct lbmx_engine
 	int64_t iter = 0;
 	cudaStream_t s_main = nullptr, s_edge = nullptr, s_comm = nullptr;
 	cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_main = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+	// two consecutive steps (even + odd iteration) of the single-slab path as a CUDA graph, replayed inside long batches of a small
+	// lattice where the gaps between dependent launches are a visible share of a 10-30 us step
+	cudaGraphExec_t pair_exec = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	uint64_t state_version = 1, pair_version = 0;  // state_version: bumped by whatever changes the kernel parameters
+	int pair_out_mode = -1, pair_launches = 0;
+	bool graphs_enabled = true;
 	ncclComm_t comm = nullptr;
 
 	StepKernels<float> kf{};
@@ -330,12 +338,100 @@ int exchange(lbmx_engine* e, void* arr)
 	return LBMX_OK;
 }
 
+// capture steps (iter, iter + 1) of the single-slab path, iter even, with every step using `out_mode`
+template <typename R>
+int capture_pair(lbmx_engine* e, const StepKernels<R>& K, int out_mode)
+{
+	if (e->pair_exec) {
+		CU(cudaGraphExecDestroy(e->pair_exec));
+		e->pair_exec = nullptr;
+	}
+	const int64_t launches0 = e->stats.kernel_launches, iter0 = e->iter;
+	cudaGraph_t graph = nullptr;
+	CU(cudaStreamBeginCapture(e->s_main, cudaStreamCaptureModeThreadLocal));
+	int rc = LBMX_OK;
+	for (int k = 0; k < 2 && rc == LBMX_OK; k++) {
+		e->iter = iter0 + k;  // parity / rotation of this step
+		KParams<R> p = make_params<R>(e);
+		p.out_mode = out_mode;
+		if (e->nb == 0 || e->list_after_bulk)
+			rc = launch_range(e, K, p, 0, (int) e->X, e->s_main);
+		else {	// fork: the boundary-list kernel beside the bulk kernel; join before the next step
+			cudaEventRecord(e->ev_fork, e->s_main);
+			cudaStreamWaitEvent(e->s_edge, e->ev_fork, 0);
+			rc = launch_range(e, K, p, 0, (int) e->X, e->s_main, e->s_edge);
+			cudaEventRecord(e->ev_join, e->s_edge);
+			cudaStreamWaitEvent(e->s_main, e->ev_join, 0);
+		}
+	}
+	e->iter = iter0;
+	e->pair_launches = (int) (e->stats.kernel_launches - launches0);
+	e->stats.kernel_launches = launches0;  // nothing ran yet
+	const cudaError_t ce = cudaStreamEndCapture(e->s_main, &graph);
+	if (rc != LBMX_OK || ce != cudaSuccess || ! graph) {
+		if (graph)
+			cudaGraphDestroy(graph);
+		cudaGetLastError();
+		e->graphs_enabled = false;	// fall back to plain launches for the life of this engine
+		return rc != LBMX_OK ? rc : LBMX_OK;
+	}
+	if (cudaGraphInstantiate(&e->pair_exec, graph, 0) != cudaSuccess) {
+		cudaGetLastError();
+		e->pair_exec = nullptr;
+		e->graphs_enabled = false;
+	}
+	cudaGraphDestroy(graph);
+	e->pair_version = e->state_version;
+	e->pair_out_mode = out_mode;
+	return LBMX_OK;
+}
+
 template <typename R>
 int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 {
 	const bool ghosts = e->ox > 0;
 	CU(cudaEventRecord(e->ev_main, e->s_main));	 // everything enqueued on the compute stream so far (uploads, initialisation) precedes the side streams' work
-	for (int64_t s = 0; s < nsteps; s++) {
+	int64_t first_plain = 0;
+	// Small single-slab lattices (steps of tens of microseconds): replay step pairs as a graph.  Pairs start at even iterations (A-A
+	// parity, A-B rotation); the last step of the batch stays a plain launch when it alone writes the macroscopic fields.
+	constexpr int64_t kGraphMaxCells = 16ll << 20, kGraphMinSteps = 8;
+	if (! ghosts && e->graphs_enabled && e->d.macro != LBMX_MACRO_MEAN && nsteps >= kGraphMinSteps && e->X * e->YZ <= kGraphMaxCells) {
+		const bool last_writes = e->d.macro == LBMX_MACRO_DEFAULT && e->d.macro_policy == LBMX_MACRO_LAST_STEP;
+		const int out_mode = (e->d.macro == LBMX_MACRO_DEFAULT && e->d.macro_policy == LBMX_MACRO_EVERY_STEP) ? OUT_DEFAULT : OUT_NONE;
+		const int64_t head = e->iter & 1, tail = last_writes ? 1 : 0;
+		const int64_t pairs = (nsteps - head - tail) / 2;
+		if (pairs > 0) {
+			if (head) {	 // one plain step up to an even iteration: recurse with a batch below the graph threshold
+				const lbmx_desc saved = e->d;
+				const int saved_counter = e->prm.stat_counter;
+				if (last_writes)
+					e->d.macro_policy = LBMX_MACRO_NEVER;  // not the last step of the caller's batch
+				const int rc1 = step_impl<R>(e, K, 1);
+				e->d = saved;
+				e->prm.stat_counter = saved_counter;
+				if (rc1)
+					return rc1;
+				CU(cudaEventRecord(e->ev_main, e->s_main));
+			}
+			if (! e->pair_exec || e->pair_version != e->state_version || e->pair_out_mode != out_mode) {
+				const int rc2 = capture_pair<R>(e, K, out_mode);
+				if (rc2)
+					return rc2;
+			}
+			if (e->pair_exec) {
+				for (int64_t i = 0; i < pairs; i++) {
+					CU(cudaGraphLaunch(e->pair_exec, e->s_main));
+					e->iter += 2;
+					e->stats.kernel_launches += e->pair_launches;
+				}
+				first_plain = head + 2 * pairs;
+				CU(cudaEventRecord(e->ev_main, e->s_main));	 // what follows on the side stream waits for the replayed steps
+			}
+			else
+				first_plain = head;
+		}
+	}
+	for (int64_t s = first_plain; s < nsteps; s++) {
 		KParams<R> p = make_params<R>(e);
 		const bool last = s == nsteps - 1;
 		if (e->d.macro == LBMX_MACRO_MEAN)
@@ -700,6 +796,9 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 	CUX(cudaEventCreateWithFlags(&e->ev_edge, cudaEventDisableTiming));
 	CUX(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
 	CUX(cudaEventCreateWithFlags(&e->ev_main, cudaEventDisableTiming));
+	CUX(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+	CUX(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+	e->graphs_enabled = std::getenv("LBMX_NO_GRAPH") == nullptr;
 	CUX(cudaEventCreate(&e->ev_t0));
 	CUX(cudaEventCreate(&e->ev_t1));
 	const size_t df_bytes = (size_t) e->Q * e->XYZ * e->rs;
@@ -745,7 +844,9 @@ int lbmx_destroy(lbmx_engine* e)
 	for (void* p : {e->df[0], e->df[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs})
 		if (p)
 			cudaFree(p);
-	for (cudaEvent_t ev : {e->ev_edge, e->ev_comm, e->ev_main, e->ev_t0, e->ev_t1})
+	if (e->pair_exec)
+		cudaGraphExecDestroy(e->pair_exec);
+	for (cudaEvent_t ev : {e->ev_edge, e->ev_comm, e->ev_main, e->ev_t0, e->ev_t1, e->ev_fork, e->ev_join})
 		if (ev)
 			cudaEventDestroy(ev);
 	for (cudaStream_t s : {e->s_main, e->s_edge, e->s_comm})
@@ -900,6 +1001,7 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	e->stats.boundary_cells = e->nb;
 	e->stats.bulk_cells = e->n_bulk;
 	e->map_ready = true;
+	e->state_version++;
 	return LBMX_OK;
 }
 
@@ -1048,6 +1150,8 @@ int lbmx_set_params(lbmx_engine* e, const lbmx_params* p)
 		return fail(LBMX_ERR_ARG, "lbmx_set_params: null argument");
 	if (p->lbmViscosity == 0.0)
 		return fail(LBMX_ERR_ARG, "lbmx_set_params: lbmViscosity must not be 0 (state.hpp:985-990 aborts on it)");
+	if (std::memcmp(&e->prm, p, sizeof(lbmx_params)) != 0)
+		e->state_version++;	 // captured step pairs carry the parameters by value
 	e->prm = *p;
 	return LBMX_OK;
 }
@@ -1064,6 +1168,7 @@ int lbmx_set_inflow_profile(lbmx_engine* e, const void* host_profile, int64_t si
 	CU(cudaMalloc(&e->profile, (size_t) (size_y * size_z) * e->rs));
 	CU(cudaMemcpy(e->profile, host_profile, (size_t) (size_y * size_z) * e->rs, cudaMemcpyHostToDevice));
 	e->profile_sy = size_y;
+	e->state_version++;
 	return LBMX_OK;
 }
 
@@ -1077,6 +1182,7 @@ int lbmx_bouzidi_upload(lbmx_engine* e, const void* host_coeff)
 	if (! e->bouzidi) {
 		CU(cudaMalloc(&e->bouzidi, (size_t) 8 * e->XYZ * e->rs));
 		CU(cudaMemset(e->bouzidi, 0xbf, (size_t) 8 * e->XYZ * e->rs));	// ghost planes: a negative value (0xbfbf... < 0 in both precisions)
+		e->state_version++;
 	}
 	return copy_components(e, e->bouzidi, (void*) host_coeff, 8, e->rs, false, true);
 }
