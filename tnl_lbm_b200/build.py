@@ -35,6 +35,14 @@ FAMILIES = [
     ("d3q27_cum2017", "D3Q27", "K_CUM_2017"),
     ("d3q27_cumaa", "D3Q27", "K_CUM_AALIAS"),
     ("d3q27_cum2017aa", "D3Q27", "K_CUM_2017_AALIAS"),
+    ("d3q27_kbcn1", "D3Q27", "K_KBC_N1"),
+    ("d3q27_kbcn2", "D3Q27", "K_KBC_N2"),
+    ("d3q27_kbcn3", "D3Q27", "K_KBC_N3"),
+    ("d3q27_kbcn4", "D3Q27", "K_KBC_N4"),
+    ("d3q27_kbcc1", "D3Q27", "K_KBC_C1"),
+    ("d3q27_kbcc2", "D3Q27", "K_KBC_C2"),
+    ("d3q27_kbcc3", "D3Q27", "K_KBC_C3"),
+    ("d3q27_kbcc4", "D3Q27", "K_KBC_C4"),
     ("d3q19_srt", "D3Q19", "K_SRT"),
     ("d3q19_mrt", "D3Q19", "K_MRT"),
     ("d2q9_srt", "D2Q9", "K_SRT"),
@@ -85,13 +93,6 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
         for real in ("float", "double"):
             obj = os.path.join(OBJ, f"inst_{fam}_{real}_strict.o")
             cmd = [NVCC, *ARCH, *COMMON, "-fmad=false", "-DLBMX_STRICT=1", "-Xptxas", "-v", f"-DLBMX_FAMILY={fam}_strict", f"-DLBMX_LAT={lat}",
-                   f"-DLBMX_KIND={kind}", f"-DLBMX_REAL={real}", "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]
-            tasks.append((cmd, obj))
-    # KBC family: built once, in the reference's association without FMA contraction; serves both arithmetic modes
-    for name, kind in (("n1", "K_KBC_N1"), ("n2", "K_KBC_N2"), ("n3", "K_KBC_N3"), ("n4", "K_KBC_N4"), ("c1", "K_KBC_C1"), ("c2", "K_KBC_C2"), ("c3", "K_KBC_C3"), ("c4", "K_KBC_C4")):
-        for real in ("float", "double"):
-            obj = os.path.join(OBJ, f"inst_d3q27_kbc{name}_{real}_strict.o")
-            cmd = [NVCC, *ARCH, *COMMON, "-fmad=false", "-DLBMX_STRICT=1", "-Xptxas", "-v", f"-DLBMX_FAMILY=d3q27_kbc{name}_strict", "-DLBMX_LAT=D3Q27",
                    f"-DLBMX_KIND={kind}", f"-DLBMX_REAL={real}", "-c", os.path.join(CSRC, "inst.cu"), "-o", obj]
             tasks.append((cmd, obj))
     eng = os.path.join(OBJ, "engine.o")

@@ -665,7 +665,7 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 	if constexpr (KIND == K_CLBM)
 		ext::collide_clbm<! kStrict>(f, P, rho, vx, vy, vz);
 	else if constexpr (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
-		ext::collide_kbc<(KIND >= K_KBC_C1), ((KIND - K_KBC_N1) % 4 == 1 || (KIND - K_KBC_N1) % 4 == 3), ((KIND - K_KBC_N1) % 4 >= 2)>(f, P, rho, vx, vy, vz);
+		ext::collide_kbc<(KIND >= K_KBC_C1), ((KIND - K_KBC_N1) % 4 == 1 || (KIND - K_KBC_N1) % 4 == 3), ((KIND - K_KBC_N1) % 4 >= 2), kStrict>(f, P, rho, vx, vy, vz);
 	else if constexpr (KIND == K_CUM_2017)
 		strict::collide_cum<true, false>(f, P, rho, vx, vy, vz);
 	else if constexpr (KIND == K_CUM_AALIAS)

@@ -391,7 +391,9 @@ LBMX_D R kbc_tensor_q(R qxxy, R qxxz, R qxyy, R qyyz, R qxzz, R qyzz, R qxyz)
 		return R(0);
 }
 
-template <bool CENTRAL, bool USE_T, bool USE_Q, typename R, typename PHYS>
+// EXACT = the reference's arithmetic as written (parity build).  The default build uses 1/feq_i = (-1/rho) (1/g_x)(1/g_y)(1/g_z)
+// and S_i * (1/rho): 10 reciprocals per cell instead of 54 divisions, which is what bounds the exact form.
+template <bool CENTRAL, bool USE_T, bool USE_Q, bool EXACT, typename R, typename PHYS>
 LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
@@ -488,6 +490,15 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 		return acc;
 	};
 	const R beta = (one / (two * P.nu / third + one));
+	const R irho = one / rho, nirho = -irho;
+	R ig[3][3];
+	if constexpr (! EXACT) {
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+#pragma unroll
+			for (int c = 0; c < 3; c++)
+				ig[a][c] = one / g[a][c];
+	}
 	// <Ds|Dh> and <Dh|Dh> (weights 1/feq), summed in the order mmm, mmz, mmp, mzm, ... ppp (col_kbc_n.h:233-252)
 	R sd = R(0), hh = R(0);
 	static_for<27>([&](auto ic) {
@@ -495,7 +506,11 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 		constexpr int q = L::find(i / 9 - 1, (i / 3) % 3 - 1, i % 3 - 1);
 		const R fe = feq_of(std::integral_constant<int, q>{}), ds = ds_of(std::integral_constant<int, q>{});
 		const R dh = f[q] - fe - ds;
-		const R ifeq = one / fe;
+		R ifeq;
+		if constexpr (EXACT)
+			ifeq = one / fe;
+		else
+			ifeq = (nirho * ig[0][L::cx(q) + 1]) * (ig[1][L::cy(q) + 1] * ig[2][L::cz(q) + 1]);
 		const R t1 = ds * dh * ifeq, t2 = dh * dh * ifeq;
 		if constexpr (i == 0) {
 			sd = t1;
@@ -511,7 +526,11 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 		constexpr int q = qc;
 		const R fe = feq_of(qc), ds = ds_of(qc);
 		const R dh = f[q] - fe - ds;
-		const R S = strict::force_projection(L::cx(q), L::cy(q), L::cz(q), vx, vy, vz, P) / rho;
+		R S = strict::force_projection(L::cx(q), L::cy(q), L::cz(q), vx, vy, vz, P);
+		if constexpr (EXACT)
+			S = S / rho;
+		else
+			S = S * irho;
 		f[q] -= beta * (two * ds + gamma * dh) - (one - beta) * S * fe;
 	});
 }

@@ -510,18 +510,6 @@ int step_dispatch(lbmx_engine* e, int64_t nsteps)
 bool pick_kernels(lbmx_engine* e)
 {
 	const lbmx_desc& d = e->d;
-	if (d.lattice == LBMX_D3Q27 && d.coll >= LBMX_COLL_KBC_N1 && d.coll <= LBMX_COLL_KBC_C4) {
-		switch (d.coll) {
-			case LBMX_COLL_KBC_N1: return e->f64() ? get_kernels_d3q27_kbcn1_strict(e->kd) : get_kernels_d3q27_kbcn1_strict(e->kf);
-			case LBMX_COLL_KBC_N2: return e->f64() ? get_kernels_d3q27_kbcn2_strict(e->kd) : get_kernels_d3q27_kbcn2_strict(e->kf);
-			case LBMX_COLL_KBC_N3: return e->f64() ? get_kernels_d3q27_kbcn3_strict(e->kd) : get_kernels_d3q27_kbcn3_strict(e->kf);
-			case LBMX_COLL_KBC_N4: return e->f64() ? get_kernels_d3q27_kbcn4_strict(e->kd) : get_kernels_d3q27_kbcn4_strict(e->kf);
-			case LBMX_COLL_KBC_C1: return e->f64() ? get_kernels_d3q27_kbcc1_strict(e->kd) : get_kernels_d3q27_kbcc1_strict(e->kf);
-			case LBMX_COLL_KBC_C2: return e->f64() ? get_kernels_d3q27_kbcc2_strict(e->kd) : get_kernels_d3q27_kbcc2_strict(e->kf);
-			case LBMX_COLL_KBC_C3: return e->f64() ? get_kernels_d3q27_kbcc3_strict(e->kd) : get_kernels_d3q27_kbcc3_strict(e->kf);
-			case LBMX_COLL_KBC_C4: return e->f64() ? get_kernels_d3q27_kbcc4_strict(e->kd) : get_kernels_d3q27_kbcc4_strict(e->kf);
-		}
-	}
 	if (d.flags & LBMX_FLAG_STRICT_ARITH) {	 // parity arithmetic (lattices checked by the caller)
 		if (d.lattice == LBMX_D3Q27) {
 			switch (d.coll) {
@@ -531,6 +519,14 @@ bool pick_kernels(lbmx_engine* e)
 				case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt_strict(e->kd) : get_kernels_d3q27_mrt_strict(e->kf);
 				case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm_strict(e->kd) : get_kernels_d3q27_clbm_strict(e->kf);
 				case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf_strict(e->kd) : get_kernels_d3q27_srtmf_strict(e->kf);
+				case LBMX_COLL_KBC_N1: return e->f64() ? get_kernels_d3q27_kbcn1_strict(e->kd) : get_kernels_d3q27_kbcn1_strict(e->kf);
+				case LBMX_COLL_KBC_N2: return e->f64() ? get_kernels_d3q27_kbcn2_strict(e->kd) : get_kernels_d3q27_kbcn2_strict(e->kf);
+				case LBMX_COLL_KBC_N3: return e->f64() ? get_kernels_d3q27_kbcn3_strict(e->kd) : get_kernels_d3q27_kbcn3_strict(e->kf);
+				case LBMX_COLL_KBC_N4: return e->f64() ? get_kernels_d3q27_kbcn4_strict(e->kd) : get_kernels_d3q27_kbcn4_strict(e->kf);
+				case LBMX_COLL_KBC_C1: return e->f64() ? get_kernels_d3q27_kbcc1_strict(e->kd) : get_kernels_d3q27_kbcc1_strict(e->kf);
+				case LBMX_COLL_KBC_C2: return e->f64() ? get_kernels_d3q27_kbcc2_strict(e->kd) : get_kernels_d3q27_kbcc2_strict(e->kf);
+				case LBMX_COLL_KBC_C3: return e->f64() ? get_kernels_d3q27_kbcc3_strict(e->kd) : get_kernels_d3q27_kbcc3_strict(e->kf);
+				case LBMX_COLL_KBC_C4: return e->f64() ? get_kernels_d3q27_kbcc4_strict(e->kd) : get_kernels_d3q27_kbcc4_strict(e->kf);
 				case LBMX_COLL_CUM_2017: return e->f64() ? get_kernels_d3q27_cum2017_strict(e->kd) : get_kernels_d3q27_cum2017_strict(e->kf);
 				case LBMX_COLL_CUM_ANTIALIAS: return e->f64() ? get_kernels_d3q27_cumaa_strict(e->kd) : get_kernels_d3q27_cumaa_strict(e->kf);
 				case LBMX_COLL_CUM_2017_ANTIALIAS: return e->f64() ? get_kernels_d3q27_cum2017aa_strict(e->kd) : get_kernels_d3q27_cum2017aa_strict(e->kf);
@@ -552,6 +548,14 @@ bool pick_kernels(lbmx_engine* e)
 			case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt(e->kd) : get_kernels_d3q27_mrt(e->kf);
 			case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm(e->kd) : get_kernels_d3q27_clbm(e->kf);
 			case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf(e->kd) : get_kernels_d3q27_srtmf(e->kf);
+			case LBMX_COLL_KBC_N1: return e->f64() ? get_kernels_d3q27_kbcn1(e->kd) : get_kernels_d3q27_kbcn1(e->kf);
+			case LBMX_COLL_KBC_N2: return e->f64() ? get_kernels_d3q27_kbcn2(e->kd) : get_kernels_d3q27_kbcn2(e->kf);
+			case LBMX_COLL_KBC_N3: return e->f64() ? get_kernels_d3q27_kbcn3(e->kd) : get_kernels_d3q27_kbcn3(e->kf);
+			case LBMX_COLL_KBC_N4: return e->f64() ? get_kernels_d3q27_kbcn4(e->kd) : get_kernels_d3q27_kbcn4(e->kf);
+			case LBMX_COLL_KBC_C1: return e->f64() ? get_kernels_d3q27_kbcc1(e->kd) : get_kernels_d3q27_kbcc1(e->kf);
+			case LBMX_COLL_KBC_C2: return e->f64() ? get_kernels_d3q27_kbcc2(e->kd) : get_kernels_d3q27_kbcc2(e->kf);
+			case LBMX_COLL_KBC_C3: return e->f64() ? get_kernels_d3q27_kbcc3(e->kd) : get_kernels_d3q27_kbcc3(e->kf);
+			case LBMX_COLL_KBC_C4: return e->f64() ? get_kernels_d3q27_kbcc4(e->kd) : get_kernels_d3q27_kbcc4(e->kf);
 			case LBMX_COLL_CUM_2017: return e->f64() ? get_kernels_d3q27_cum2017(e->kd) : get_kernels_d3q27_cum2017(e->kf);
 			case LBMX_COLL_CUM_ANTIALIAS: return e->f64() ? get_kernels_d3q27_cumaa(e->kd) : get_kernels_d3q27_cumaa(e->kf);
 			case LBMX_COLL_CUM_2017_ANTIALIAS: return e->f64() ? get_kernels_d3q27_cum2017aa(e->kd) : get_kernels_d3q27_cum2017aa(e->kf);

@@ -681,21 +681,36 @@ bool get_kernels_d3q27_cum2017aa(StepKernels<float>&);
 bool get_kernels_d3q27_cum2017aa(StepKernels<double>&);
 bool get_kernels_d3q27_cum2017aa_strict(StepKernels<float>&);
 bool get_kernels_d3q27_cum2017aa_strict(StepKernels<double>&);
-// KBC family: one build, in the reference's association without FMA contraction (serves both arithmetic modes)
+bool get_kernels_d3q27_kbcn1(StepKernels<float>&);
+bool get_kernels_d3q27_kbcn1(StepKernels<double>&);
 bool get_kernels_d3q27_kbcn1_strict(StepKernels<float>&);
 bool get_kernels_d3q27_kbcn1_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcn2(StepKernels<float>&);
+bool get_kernels_d3q27_kbcn2(StepKernels<double>&);
 bool get_kernels_d3q27_kbcn2_strict(StepKernels<float>&);
 bool get_kernels_d3q27_kbcn2_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcn3(StepKernels<float>&);
+bool get_kernels_d3q27_kbcn3(StepKernels<double>&);
 bool get_kernels_d3q27_kbcn3_strict(StepKernels<float>&);
 bool get_kernels_d3q27_kbcn3_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcn4(StepKernels<float>&);
+bool get_kernels_d3q27_kbcn4(StepKernels<double>&);
 bool get_kernels_d3q27_kbcn4_strict(StepKernels<float>&);
 bool get_kernels_d3q27_kbcn4_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcc1(StepKernels<float>&);
+bool get_kernels_d3q27_kbcc1(StepKernels<double>&);
 bool get_kernels_d3q27_kbcc1_strict(StepKernels<float>&);
 bool get_kernels_d3q27_kbcc1_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcc2(StepKernels<float>&);
+bool get_kernels_d3q27_kbcc2(StepKernels<double>&);
 bool get_kernels_d3q27_kbcc2_strict(StepKernels<float>&);
 bool get_kernels_d3q27_kbcc2_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcc3(StepKernels<float>&);
+bool get_kernels_d3q27_kbcc3(StepKernels<double>&);
 bool get_kernels_d3q27_kbcc3_strict(StepKernels<float>&);
 bool get_kernels_d3q27_kbcc3_strict(StepKernels<double>&);
+bool get_kernels_d3q27_kbcc4(StepKernels<float>&);
+bool get_kernels_d3q27_kbcc4(StepKernels<double>&);
 bool get_kernels_d3q27_kbcc4_strict(StepKernels<float>&);
 bool get_kernels_d3q27_kbcc4_strict(StepKernels<double>&);
 bool get_kernels_d3q27_clbm(StepKernels<float>&);
