@@ -244,13 +244,18 @@ def main():
     keep.append(tmac)
     log(f"[rank {rank}] host inputs ready in {time.perf_counter() - t_in:.1f}s; slab x0={x0} xl={xl}")
 
+    upload_log = []
+
     def upload_state():
+        t0 = time.perf_counter()
         eng.map_upload(h_map)
+        t1 = time.perf_counter()
         if channel:
             eng.set_equilibrium(1.0, 0.0, 0.0, 0.0)  # State::resetDFs (state.hpp:880-896)
         else:
             eng.set_equilibrium_field(*fields)
         eng.iterations = 0
+        upload_log.append((t1 - t0, time.perf_counter() - t1))
 
     eng.set_params(lbmViscosity=1e-3, fx=1e-7 if channel else 1e-6, fy=0.0, fz=0.0)
 
@@ -293,7 +298,8 @@ def main():
     eng.sync()
     torch.cuda.synchronize()
     te1 = time.perf_counter()
-    log(f"[rank {rank}] e2e phases: upload {te_up - te0:.3f}s, {a.steps} steps {te_st - te_up:.3f}s, macro download {te1 - te_st:.3f}s")
+    log(f"[rank {rank}] e2e phases: upload {te_up - te0:.3f}s (map + boundary list {upload_log[-1][0]:.3f}s, initial fields {upload_log[-1][1]:.3f}s), "
+        f"{a.steps} steps {te_st - te_up:.3f}s, macro download {te1 - te_st:.3f}s")
     te = allmax(te1 - te0)
     e2e_value = cells_global * a.steps / te / 1e6
     h2d = (h_map.nbytes + sum(f.nbytes for f in fields)) * N

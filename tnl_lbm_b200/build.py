@@ -50,16 +50,25 @@ FAMILIES = [
 ]
 
 
-def _sources_digest() -> str:
+def _digest(names_filter) -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h")):
+            if name.endswith((".cu", ".cuh", ".h")) and names_filter(name):
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode())
                     h.update(f.read())
     h.update(" ".join(COMMON + ARCH).encode())
     return h.hexdigest()
+
+
+def _sources_digest() -> str:
+    return _digest(lambda name: True)
+
+
+def _kernel_digest() -> str:
+    """What the kernel-family objects (inst.cu compiled once per family) depend on: everything but engine.cu."""
+    return _digest(lambda name: name != "engine.cu")
 
 
 def _run(cmd, log):
@@ -97,6 +106,13 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
             tasks.append((cmd, obj))
     eng = os.path.join(OBJ, "engine.o")
     tasks.append(([NVCC, *ARCH, *COMMON, "-c", os.path.join(CSRC, "engine.cu"), "-o", eng], eng))
+    # kernel-family objects are reused when only engine.cu (host code) changed
+    kstamp = os.path.join(OBJ, "kernel_digest.txt")
+    kdigest = _kernel_digest()
+    reuse = not force and os.path.exists(kstamp) and open(kstamp).read() == kdigest
+    all_objs = [obj for _, obj in tasks]
+    if reuse:
+        tasks = [(cmd, obj) for cmd, obj in tasks if obj == eng or not os.path.exists(obj)]
     jobs = jobs or min(len(tasks), os.cpu_count() or 4)
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
         futs = [ex.submit(_run, cmd, obj + ".log") for cmd, obj in tasks]
@@ -104,10 +120,11 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
             out = f.result()
             if verbose:
                 print(out)
-    objs = [obj for _, obj in tasks]
-    _run([NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-o", LIB, *objs, "-cudart", "static", "-ldl"], os.path.join(OBJ, "link.log"))
+    _run([NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-o", LIB, *all_objs, "-cudart", "static", "-ldl"], os.path.join(OBJ, "link.log"))
     with open(stamp, "w") as f:
         f.write(digest)
+    with open(kstamp, "w") as f:
+        f.write(kdigest)
     return LIB
 
 

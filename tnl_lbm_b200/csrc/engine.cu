@@ -197,6 +197,8 @@ struct lbmx_engine
 	uint64_t state_version = 1, pair_version = 0;  // state_version: bumped by whatever changes the kernel parameters
 	int pair_out_mode = -1, pair_launches = 0;
 	bool graphs_enabled = true;
+	double* eq_stage[2] = {nullptr, nullptr};  // staging sets of lbmx_df_set_equilibrium_field
+	int64_t eq_stage_cells = 0;
 	ncclComm_t comm = nullptr;
 
 	StepKernels<float> kf{};
@@ -850,6 +852,9 @@ int lbmx_destroy(lbmx_engine* e)
 			cudaFree(p);
 	if (e->pair_exec)
 		cudaGraphExecDestroy(e->pair_exec);
+	for (double* p : e->eq_stage)
+		if (p)
+			cudaFree(p);
 	for (cudaEvent_t ev : {e->ev_edge, e->ev_comm, e->ev_main, e->ev_t0, e->ev_t1, e->ev_fork, e->ev_join})
 		if (ev)
 			cudaEventDestroy(ev);
@@ -1022,31 +1027,70 @@ static int set_eq_common(lbmx_engine* e, const double* rho, const double* vx, co
 	const bool field = rho != nullptr;
 	const int64_t n = field ? e->X * e->YZ : e->XYZ;
 	const int64_t cell0 = field ? e->ox * e->YZ : 0;
-	double* dev_fields[4] = {nullptr, nullptr, nullptr, nullptr};
 	const double* src[4] = {rho, vx, vy, vz};
 	int rc = LBMX_OK;
-	if (field) {
-		for (int k = 0; k < 4 && rc == LBMX_OK; k++) {
-			if (! src[k])
-				continue;
-			if (cudaMalloc(&dev_fields[k], (size_t) n * sizeof(double)) != cudaSuccess
-				|| cudaMemcpyAsync(dev_fields[k], src[k], (size_t) n * sizeof(double), cudaMemcpyHostToDevice, e->s_main) != cudaSuccess)
+	auto launch = [&](int64_t cells, int64_t first, const double* f0, const double* f1, const double* f2, const double* f3) {
+		const unsigned blocks = (unsigned) ((cells + 127) / 128);
+		if (e->f64())
+			e->kd.set_equilibrium<<<blocks, 128, 0, e->s_main>>>((double*) e->df[0], e->XYZ, cells, first, e->d.eq, f0, f1, f2, f3, crho, cvx, cvy, cvz);
+		else
+			e->kf.set_equilibrium<<<blocks, 128, 0, e->s_main>>>((float*) e->df[0], e->XYZ, cells, first, e->d.eq, f0, f1, f2, f3, crho, cvx, cvy, cvz);
+		e->stats.kernel_launches++;
+	};
+	if (! field)
+		launch(n, cell0, nullptr, nullptr, nullptr, nullptr);
+	else {
+		// The four host fields stream through two staging sets of `chunk` cells: the copy of chunk c+1 (on the communication stream)
+		// overlaps the equilibrium kernel of chunk c, and no lattice-sized temporary is allocated.
+		int64_t chunk_cells = 8ll << 20;
+		if (const char* v = std::getenv("LBMX_EQ_CHUNK"))
+			chunk_cells = std::max<int64_t>(1, std::atoll(v));
+		const int64_t chunk = std::min<int64_t>(n, chunk_cells);
+		// the staging sets live as long as the engine (0.5 GB at the default chunk): a solver that re-initialises pays for them once
+		if (e->eq_stage_cells != chunk) {
+			for (int b = 0; b < 2; b++) {
+				if (e->eq_stage[b])
+					cudaFree(e->eq_stage[b]);
+				e->eq_stage[b] = nullptr;
+			}
+			e->eq_stage_cells = 0;
+			if (cudaMalloc(&e->eq_stage[0], (size_t) chunk * 4 * sizeof(double)) != cudaSuccess || cudaMalloc(&e->eq_stage[1], (size_t) chunk * 4 * sizeof(double)) != cudaSuccess)
 				rc = fail(LBMX_ERR_CUDA, std::string("lbmx_df_set_equilibrium_field: ") + cudaGetErrorString(cudaGetLastError()));
+			else
+				e->eq_stage_cells = chunk;
+		}
+		double* stage[2] = {e->eq_stage[0], e->eq_stage[1]};
+		cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+		for (int b = 0; b < 2 && rc == LBMX_OK; b++)
+			if (cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming) != cudaSuccess)
+				rc = fail(LBMX_ERR_CUDA, std::string("lbmx_df_set_equilibrium_field: ") + cudaGetErrorString(cudaGetLastError()));
+		if (rc == LBMX_OK) {
+			cudaEventRecord(consumed[0], e->s_main);  // also orders the copies after whatever the compute stream did before
+			cudaEventRecord(consumed[1], e->s_main);
+		}
+		for (int64_t off = 0, c = 0; off < n && rc == LBMX_OK; off += chunk, c++) {
+			const int b = (int) (c & 1);
+			const int64_t len = std::min(chunk, n - off);
+			cudaStreamWaitEvent(e->s_comm, consumed[b], 0);
+			for (int k = 0; k < 4; k++)
+				if (src[k] && cudaMemcpyAsync(stage[b] + (size_t) k * chunk, src[k] + off, (size_t) len * sizeof(double), cudaMemcpyHostToDevice, e->s_comm) != cudaSuccess)
+					rc = fail(LBMX_ERR_CUDA, std::string("lbmx_df_set_equilibrium_field: ") + cudaGetErrorString(cudaGetLastError()));
+			cudaEventRecord(copied[b], e->s_comm);
+			cudaStreamWaitEvent(e->s_main, copied[b], 0);
+			launch(len, cell0 + off, stage[b], stage[b] + chunk, stage[b] + 2 * chunk, src[3] ? stage[b] + 3 * chunk : nullptr);
+			cudaEventRecord(consumed[b], e->s_main);
+		}
+		if (cudaStreamSynchronize(e->s_comm) != cudaSuccess || cudaStreamSynchronize(e->s_main) != cudaSuccess)
+			rc = rc ? rc : fail(LBMX_ERR_CUDA, "lbmx_df_set_equilibrium_field: transfer failed");
+		for (int b = 0; b < 2; b++) {
+			if (copied[b])
+				cudaEventDestroy(copied[b]);
+			if (consumed[b])
+				cudaEventDestroy(consumed[b]);
 		}
 	}
-	if (rc == LBMX_OK) {
-		const unsigned blocks = (unsigned) ((n + 127) / 128);
-		if (e->f64())
-			e->kd.set_equilibrium<<<blocks, 128, 0, e->s_main>>>((double*) e->df[0], e->XYZ, n, cell0, e->d.eq, dev_fields[0], dev_fields[1], dev_fields[2], dev_fields[3], crho, cvx, cvy, cvz);
-		else
-			e->kf.set_equilibrium<<<blocks, 128, 0, e->s_main>>>((float*) e->df[0], e->XYZ, n, cell0, e->d.eq, dev_fields[0], dev_fields[1], dev_fields[2], dev_fields[3], crho, cvx, cvy, cvz);
-		e->stats.kernel_launches++;
-		if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(e->s_main) != cudaSuccess)
-			rc = fail(LBMX_ERR_CUDA, "lbmx_df_set_equilibrium: kernel failed");
-	}
-	for (double* p : dev_fields)
-		if (p)
-			cudaFree(p);
+	if (rc == LBMX_OK && (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(e->s_main) != cudaSuccess))
+		rc = fail(LBMX_ERR_CUDA, "lbmx_df_set_equilibrium: kernel failed");
 	if (rc)
 		return rc;
 	if (field && e->ox) {
