@@ -348,7 +348,8 @@ def main():
             line["halo"] = {"bytes_per_step_per_gpu": hb, "exchange_ms_alone": halo_ms, "nvlink_bound_ms": hb / 900e9 * 1e3,
                             "nvlink_peak": "900 GB/s per direction (NVLink 5); each GPU sends and receives bytes_per_step_per_gpu per step",
                             "step_ms": ms_max / a.steps, "hidden_behind_interior": bool(halo_ms < ms_max / a.steps),
-                            "transport": "NCCL send/recv, 9 plane messages per direction in one group" if N > 1 else "device copy kernel (single slab with ghost planes)"}
+                            "transport": ("stores into the neighbour's planes over NVLink (CUDA IPC peer mapping) + arrival counter" if st.halo_peer_memory
+                                          else "NCCL send/recv, 9 plane messages per direction in one group") if N > 1 else "device copy kernel (single slab with ghost planes)"}
     eng.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's CPU code on a bounded sample of the same workload

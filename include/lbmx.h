@@ -174,6 +174,11 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out);
 int lbmx_destroy(lbmx_engine* e);
 int lbmx_get_layout(const lbmx_engine* e, lbmx_layout* out);
 
+/* Halo transport.  After lbmx_comm_init the ranks try to map each other's distribution arrays (CUDA IPC): if every rank succeeds, the
+ * exchange of a step is two copy kernels that store the 9 crossing populations of a boundary plane directly into the neighbour's
+ * ghost (or, on A-A odd steps, boundary) plane over NVLink, each followed by a bump of an arrival counter in the neighbour's memory;
+ * the neighbour's edge-plane kernels of the next step poll that counter.  Otherwise (or with LBMX_HALO=nccl) the exchange is
+ * ncclSend/ncclRecv, 9 plane messages per direction in one group.  Both are bit-identical. */
 /* Multi-GPU: rank 0 makes an id (128 bytes), the host distributes it (any broadcast the launcher offers), every rank joins.
  * Replaces the MPI communicator of DistributedNDArraySynchronizer.  NCCL is bound at run time (dlopen "libnccl.so.2"). */
 int lbmx_comm_unique_id(void* id128);
@@ -244,7 +249,9 @@ typedef struct lbmx_stats
 	int64_t boundary_cells;	   /* cells handled by the boundary-list kernel */
 	int64_t bulk_cells;		   /* cells handled by the bulk kernel */
 	int32_t bulk_regs, boundary_regs; /* registers per thread of the two step kernels (cudaFuncGetAttributes) */
-	int32_t bulk_block, reserved;
+	int32_t bulk_block;
+	int32_t halo_peer_memory; /* 1: halos are stored straight into the neighbours' arrays over NVLink (CUDA IPC peer mappings, arrival counters);
+								 0: NCCL send/recv (multi-node, IPC unavailable, or LBMX_HALO=nccl in the environment) */
 } lbmx_stats;
 int lbmx_get_stats(lbmx_engine* e, lbmx_stats* out);
 

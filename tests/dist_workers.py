@@ -65,8 +65,12 @@ def gloo_slab_worker(rank, world, port, case_name, outdir):
     dist.destroy_process_group()
 
 
-def nccl_engine_worker(rank, world, port, case_name, outdir):
-    """GPU: one engine slab per process / device; ghost planes exchanged by the engine itself over NCCL."""
+def nccl_engine_worker(rank, world, port, case_name, outdir, transport="auto"):
+    """GPU: one engine slab per process / device; ghost planes exchanged by the engine itself (peer memory or NCCL send/recv)."""
+    if transport == "nccl":
+        os.environ["LBMX_HALO"] = "nccl"
+    else:
+        os.environ.pop("LBMX_HALO", None)
     import torch
 
     import golden_cases as gc
@@ -102,7 +106,7 @@ def nccl_engine_worker(rank, world, port, case_name, outdir):
     np.save(os.path.join(outdir, f"df_{rank}.npy"), e.df_download(0))
     np.save(os.path.join(outdir, f"mac_{rank}.npy"), e.macro_download())
     st = e.stats()
-    np.save(os.path.join(outdir, f"halo_{rank}.npy"), np.array([st.halo_bytes_sent, st.kernel_launches]))
+    np.save(os.path.join(outdir, f"halo_{rank}.npy"), np.array([st.halo_bytes_sent, st.kernel_launches, st.halo_peer_memory]))
     dist.barrier()
     e.close()
     dist.destroy_process_group()

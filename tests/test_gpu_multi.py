@@ -63,8 +63,11 @@ def test_ghost_planes_with_self_exchange_equal_plain_run(case_name):
     assert lc.rel_err_df(df, ref_df, case.desc) <= 1e-12
 
 
+@pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
 @pytest.mark.parametrize("case_name", ["duct_ab", "duct_aa", "box_ab", "box_aa"])
-def test_two_gpus_nccl_halo_exchange(case_name):
+def test_two_gpus_halo_exchange(case_name, transport):
+    """Two slabs, two processes, two GPUs.  Default transport: stores into the neighbour's array over NVLink (CUDA IPC peer
+    mappings + arrival counters); LBMX_HALO=nccl: NCCL send/recv.  Either way identical to one slab with a self-exchange."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -75,13 +78,17 @@ def test_two_gpus_nccl_halo_exchange(case_name):
 
     world = 2
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(W.nccl_engine_worker, args=(world, free_port(), case_name, tmp), nprocs=world, join=True)
+        mp.spawn(W.nccl_engine_worker, args=(world, free_port(), case_name, tmp, transport), nprocs=world, join=True)
         df, mac = W.gather(tmp, world)
         halo = np.load(f"{tmp}/halo_0.npy")
     case = W.DIST_CASES[case_name]()
     assert halo[0] == case.nsteps * 2 * 9 * case.desc.Y * case.desc.Z * 8, "9 populations per direction per step"
+    if transport == "nccl":
+        assert halo[2] == 0
+    else:
+        assert halo[2] == 1, "peer-memory halo exchange not available on this box (CUDA IPC between the two processes failed)"
     one_df, one_mac = run_ghost_single(case)
-    assert np.array_equal(df, one_df), "2 slabs over NCCL must be identical to 1 slab with self-exchange"
+    assert np.array_equal(df, one_df), "2 slabs must be identical to 1 slab with self-exchange"
     assert np.array_equal(mac, one_mac)
     ref_df, ref_mac = gc.run_case(case, "port", nthreads=4)
     assert lc.rel_err_df(df, ref_df, case.desc) <= 1e-12

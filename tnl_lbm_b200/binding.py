@@ -53,7 +53,7 @@ class Ptrs(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("kernel_launches", "halo_bytes_sent", "boundary_cells", "bulk_cells")] + [(n, C.c_int32) for n in ("bulk_regs", "boundary_regs", "bulk_block", "reserved")]
+    _fields_ = [(n, C.c_int64) for n in ("kernel_launches", "halo_bytes_sent", "boundary_cells", "bulk_cells")] + [(n, C.c_int32) for n in ("bulk_regs", "boundary_regs", "bulk_block", "halo_peer_memory")]
 
 
 class HaloMsg(C.Structure):

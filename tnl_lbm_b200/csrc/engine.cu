@@ -50,6 +50,7 @@ struct NcclApi
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -78,6 +79,7 @@ struct NcclApi
 		SYM(CommDestroy, "ncclCommDestroy")
 		SYM(Send, "ncclSend")
 		SYM(Recv, "ncclRecv")
+		SYM(AllReduce, "ncclAllReduce")
 		SYM(GroupStart, "ncclGroupStart")
 		SYM(GroupEnd, "ncclGroupEnd")
 		SYM(GetErrorString, "ncclGetErrorString")
@@ -197,6 +199,18 @@ struct lbmx_engine
 	uint64_t state_version = 1, pair_version = 0;  // state_version: bumped by whatever changes the kernel parameters
 	int pair_out_mode = -1, pair_launches = 0;
 	bool graphs_enabled = true;
+	// peer-memory halo exchange (one node, NVLink): the neighbours' distribution arrays and arrival counters mapped through CUDA IPC
+	struct Peer
+	{
+		void* df[2] = {nullptr, nullptr};  // the neighbour's df[0], df[1] in this process' address space
+		long long* flags = nullptr;		   // the neighbour's arrival counters: [0] bumped by its left neighbour, [1] by its right one
+		int64_t X = 0, XYZ = 0;			   // the neighbour's slab
+		bool mapped = false;
+	};
+	Peer peer_left, peer_right;
+	long long* my_flags = nullptr;	// [0]: exchanges that arrived from the left, [1]: from the right
+	bool p2p = false;
+	int64_t xcount = 0;	 // halo exchanges enqueued so far (identical on every rank)
 	double* eq_stage[2] = {nullptr, nullptr};  // staging sets of lbmx_df_set_equilibrium_field
 	int64_t eq_stage_cells = 0;
 	ncclComm_t comm = nullptr;
@@ -292,6 +306,33 @@ size_t plane_bytes(const lbmx_engine* e)
 	return (size_t) e->YZ * e->rs;
 }
 
+// peer-memory exchange: arrival counter in the receiver's memory, written after the planes (the copy kernel before it in the
+// stream has completed, i.e. its stores are performed) and polled by the receiver before the kernels that read those planes
+__global__ void k_signal_arrival(long long* peer_counter, long long value)
+{
+	__threadfence_system();
+	*(volatile long long*) peer_counter = value;
+	__threadfence_system();
+}
+__global__ void k_await_arrival(const long long* from_left, const long long* from_right, long long expected, long long* error_word)
+{
+	const long long t0 = clock64();
+	const long long limit = 40ll * 1000 * 1000 * 1000;	// ~20 s at 2 GHz: a lost neighbour must not hang the GPU
+	for (int side = 0; side < 2; side++) {
+		const long long* c = side == 0 ? from_left : from_right;
+		if (! c)
+			continue;
+		while (*(volatile const long long*) c < expected) {
+			if (clock64() - t0 > limit) {
+				*error_word = expected;	 // reported by lbmx_sync
+				return;
+			}
+			__nanosleep(100);
+		}
+	}
+	__threadfence_system();
+}
+
 // enqueue the halo exchange that follows the step at e->iter on s_comm (replaces synchronizeDFsAndMacroDevice, lbm.hpp:196-280)
 template <typename R>
 int exchange(lbmx_engine* e, void* arr)
@@ -318,6 +359,27 @@ int exchange(lbmx_engine* e, void* arr)
 		return LBMX_OK;	 // ghost planes without a periodic partner: nothing to exchange
 	if (! e->comm)
 		return fail(LBMX_ERR_STATE, "lbmx_step: nranks > 1 but lbmx_comm_init was not called");
+	if (e->p2p) {
+		// One copy kernel per direction stores the 9 planes straight into the neighbour's array over NVLink, then bumps the
+		// neighbour's arrival counter.  Which of my arrays `arr` is tells which of the neighbour's it goes to (same rotation).
+		const int which = arr == e->df[0] ? 0 : 1;
+		e->xcount++;
+		for (int k = 0; k < 2; k++) {
+			const lbmx_halo_msg& m = msgs[k];
+			lbmx_engine::Peer& peer = m.to_right ? e->peer_right : e->peer_left;
+			if (! peer.mapped)
+				continue;
+			lbmx_halo_msg pm[2];
+			lbmx_halo_plan(e->d.lattice, e->d.streaming, e->iter, peer.X, pm);	// where the receiver keeps what arrives (its own layout)
+			const int* dirs = e->d_dirs + (m.dirs[0] == e->h_dirs[0][0] ? 0 : 9);
+			k_copy_planes<R><<<grid, 256, 0, e->s_comm>>>((R*) peer.df[which], a, e->XYZ, (int) e->YZ, nd, dirs, m.src_plane, pm[k].dst_plane, peer.XYZ);
+			k_signal_arrival<<<1, 1, 0, e->s_comm>>>(peer.flags + (m.to_right ? 0 : 1), (long long) e->xcount);
+			e->stats.kernel_launches += 2;
+			e->stats.halo_bytes_sent += (int64_t) nd * plane_bytes(e);
+		}
+		CU(cudaGetLastError());
+		return LBMX_OK;
+	}
 	// the 9 crossing populations of a plane are 9 separate contiguous runs of Y*Z reals (x is the slowest storage
 	// dimension): they go out as 9 sends per direction inside one NCCL group -- no pack/unpack kernels at all
 	NC(g_nccl.GroupStart());
@@ -338,6 +400,15 @@ int exchange(lbmx_engine* e, void* arr)
 	NC(g_nccl.GroupEnd());
 	e->stats.kernel_launches++;
 	return LBMX_OK;
+}
+
+// peer-memory exchange: what the neighbours pushed after their last step has arrived before `st` continues
+static void await_halo(lbmx_engine* e, cudaStream_t st)
+{
+	if (! e->p2p)
+		return;
+	k_await_arrival<<<1, 1, 0, st>>>(e->peer_left.mapped ? e->my_flags : nullptr, e->peer_right.mapped ? e->my_flags + 1 : nullptr, (long long) e->xcount, e->my_flags + 2);
+	e->stats.kernel_launches++;
 }
 
 // capture steps (iter, iter + 1) of the single-slab path, iter even, with every step using `out_mode`
@@ -462,6 +533,7 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 			// A-A slab with GEO_OUTFLOW_RIGHT cells: those read a neighbour's populations in place, so the whole boundary list has to
 			// follow the whole bulk kernel (as on a single slab) -- no edge-first overlap for this slab, the result stays reproducible
 			CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
+			await_halo(e, e->s_main);
 			if ((rc = launch_range(e, K, p, 0, (int) e->X, e->s_main)))
 				return rc;
 			CU(cudaEventRecord(e->ev_main, e->s_main));
@@ -474,6 +546,7 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 			// boundary planes first on the high-priority stream, then the exchange, interior concurrently (state.hpp:1060-1108)
 			CU(cudaStreamWaitEvent(e->s_edge, e->ev_main, 0));	// previous step's interior (reads/writes next to the edge planes)
 			CU(cudaStreamWaitEvent(e->s_edge, e->ev_comm, 0));	// previous exchange filled the ghost planes this step reads
+			await_halo(e, e->s_edge);							// ... including what the neighbours pushed (peer-memory exchange)
 			if ((rc = launch_range(e, K, p, 0, 1, e->s_edge)))
 				return rc;
 			if (e->X > 1 && (rc = launch_range(e, K, p, (int) e->X - 1, (int) e->X, e->s_edge)))
@@ -494,8 +567,10 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 	}
 	e->prm.stat_counter += (int) nsteps;
 	// leave the engine in a state where s_main alone orders everything that was enqueued
-	if (ghosts)
+	if (ghosts) {
 		CU(cudaStreamWaitEvent(e->s_main, e->ev_comm, 0));
+		await_halo(e, e->s_main);
+	}
 	if ((ghosts || e->nb > 0) && ! e->list_after_bulk)
 		CU(cudaStreamWaitEvent(e->s_main, e->ev_edge, 0));
 	return LBMX_OK;
@@ -839,14 +914,19 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 	return LBMX_OK;
 }
 
+static void release_peer_memory(lbmx_engine* e);
+
 int lbmx_destroy(lbmx_engine* e)
 {
 	if (! e)
 		return LBMX_OK;
 	cudaSetDevice(e->dev);
 	cudaDeviceSynchronize();
+	release_peer_memory(e);
 	if (e->comm && g_nccl.CommDestroy)
 		g_nccl.CommDestroy(e->comm);
+	if (e->my_flags)
+		cudaFree(e->my_flags);
 	for (void* p : {e->df[0], e->df[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs})
 		if (p)
 			cudaFree(p);
@@ -894,6 +974,101 @@ int lbmx_comm_unique_id(void* id128)
 	return LBMX_OK;
 }
 
+static void release_peer_memory(lbmx_engine* e)
+{
+	const bool shared = e->peer_right.mapped && e->peer_left.mapped && e->peer_right.flags == e->peer_left.flags;
+	for (lbmx_engine::Peer* peer : {&e->peer_left, &e->peer_right}) {
+		if (peer == &e->peer_right && shared) {
+			*peer = lbmx_engine::Peer{};
+			continue;
+		}
+		for (void* p : {peer->df[0], peer->df[1], (void*) peer->flags})
+			if (p)
+				cudaIpcCloseMemHandle(p);
+		*peer = lbmx_engine::Peer{};
+	}
+	cudaGetLastError();
+}
+
+// Peer-memory halo exchange: map the neighbours' distribution arrays and arrival counters into this process (CUDA IPC; one node,
+// GPUs connected by NVLink / NVSwitch).  The handles travel over the NCCL communicator that was just created.  Every rank must
+// succeed, otherwise all of them keep the NCCL send/recv exchange (also selectable with LBMX_HALO=nccl).
+static int setup_peer_memory(lbmx_engine* e)
+{
+	struct Packet
+	{
+		cudaIpcMemHandle_t df[2];
+		cudaIpcMemHandle_t flags;
+		int64_t X, XYZ;
+		int32_t ok, pad;
+	};
+	const char* mode = std::getenv("LBMX_HALO");
+	int ok = ! (mode && std::strcmp(mode, "nccl") == 0);
+	CU(cudaMalloc(&e->my_flags, 3 * sizeof(long long)));  // [0], [1]: arrival counters; [2]: set when a wait gave up
+	CU(cudaMemset(e->my_flags, 0, 3 * sizeof(long long)));
+	Packet mine{};
+	if (ok) {
+		ok = cudaIpcGetMemHandle(&mine.df[0], e->df[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, e->my_flags) == cudaSuccess;
+		if (ok && e->df[1])
+			ok = cudaIpcGetMemHandle(&mine.df[1], e->df[1]) == cudaSuccess;
+		cudaGetLastError();
+	}
+	mine.X = e->X;
+	mine.XYZ = e->XYZ;
+	mine.ok = ok;
+	Packet* d_pk = nullptr;	 // [0] mine, [1] from the left neighbour, [2] from the right neighbour
+	CU(cudaMalloc(&d_pk, 3 * sizeof(Packet)));
+	CU(cudaMemset(d_pk, 0, 3 * sizeof(Packet)));
+	CU(cudaMemcpy(d_pk, &mine, sizeof(Packet), cudaMemcpyHostToDevice));
+	NC(g_nccl.GroupStart());  // same posting order as exchange_full_planes (left and right may be the same rank)
+	if (e->right >= 0)
+		NC(g_nccl.Send(d_pk, sizeof(Packet), ncclInt8, e->right, e->comm, e->s_main));
+	if (e->left >= 0)
+		NC(g_nccl.Recv(d_pk + 1, sizeof(Packet), ncclInt8, e->left, e->comm, e->s_main));
+	if (e->left >= 0)
+		NC(g_nccl.Send(d_pk, sizeof(Packet), ncclInt8, e->left, e->comm, e->s_main));
+	if (e->right >= 0)
+		NC(g_nccl.Recv(d_pk + 2, sizeof(Packet), ncclInt8, e->right, e->comm, e->s_main));
+	NC(g_nccl.GroupEnd());
+	CU(cudaStreamSynchronize(e->s_main));
+	Packet got[3];
+	CU(cudaMemcpy(got, d_pk, 3 * sizeof(Packet), cudaMemcpyDeviceToHost));
+	ok = ok && (e->left < 0 || got[1].ok) && (e->right < 0 || got[2].ok);
+	auto map_peer = [&](lbmx_engine::Peer& peer, const Packet& pk) {
+		if (cudaIpcOpenMemHandle(&peer.df[0], pk.df[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+			return false;
+		if (e->df[1] && cudaIpcOpenMemHandle(&peer.df[1], pk.df[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+			return false;
+		if (cudaIpcOpenMemHandle((void**) &peer.flags, pk.flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+			return false;
+		peer.X = pk.X;
+		peer.XYZ = pk.XYZ;
+		peer.mapped = true;
+		return true;
+	};
+	if (ok && e->left >= 0)
+		ok = map_peer(e->peer_left, got[1]);
+	if (ok && e->right >= 0) {
+		if (e->right == e->left)
+			e->peer_right = e->peer_left;  // two slabs, periodic: one neighbour on both sides, one mapping
+		else
+			ok = map_peer(e->peer_right, got[2]);
+	}
+	cudaGetLastError();
+	// agreement: the exchange protocol must be the same on every rank
+	int* d_ok = (int*) d_pk;
+	CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+	NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, e->comm, e->s_main));
+	CU(cudaStreamSynchronize(e->s_main));
+	int all_ok = 0;
+	CU(cudaMemcpy(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+	CU(cudaFree(d_pk));
+	e->p2p = all_ok != 0;
+	if (! e->p2p)
+		release_peer_memory(e);
+	return LBMX_OK;
+}
+
 int lbmx_comm_init(lbmx_engine* e, const void* id128)
 {
 	if (! e || ! id128)
@@ -907,7 +1082,7 @@ int lbmx_comm_init(lbmx_engine* e, const void* id128)
 	ncclUniqueId id;
 	std::memcpy(&id, id128, 128);
 	NC(g_nccl.CommInitRank(&e->comm, e->d.nranks, id, e->d.rank));
-	return LBMX_OK;
+	return setup_peer_memory(e);
 }
 
 static int exchange_full_planes(lbmx_engine* e, void* arr, int ncomp, size_t elem)
@@ -1252,6 +1427,12 @@ int lbmx_sync(lbmx_engine* e)
 	CU(cudaStreamSynchronize(e->s_main));
 	CU(cudaStreamSynchronize(e->s_edge));
 	CU(cudaStreamSynchronize(e->s_comm));
+	if (e->p2p) {
+		long long gave_up = 0;
+		CU(cudaMemcpy(&gave_up, e->my_flags + 2, sizeof(long long), cudaMemcpyDeviceToHost));
+		if (gave_up)
+			return fail(LBMX_ERR_STATE, "lbmx_sync: the peer-memory halo exchange waited 20 s for exchange " + std::to_string(gave_up) + " of a neighbour and gave up (a neighbour rank stopped stepping?)");
+	}
 	return LBMX_OK;
 }
 
@@ -1289,6 +1470,7 @@ int lbmx_halo_time(lbmx_engine* e, int32_t reps, float* ms_per_exchange)
 		if (rc)
 			return rc;
 	}
+	await_halo(e, e->s_comm);  // peer-memory exchange: the neighbours' planes have arrived as well
 	CU(cudaEventRecord(e->ev_t1, e->s_comm));
 	CU(cudaEventSynchronize(e->ev_t1));
 	float ms = 0;
@@ -1353,6 +1535,7 @@ int lbmx_get_stats(lbmx_engine* e, lbmx_stats* out)
 	if (! e || ! out)
 		return fail(LBMX_ERR_ARG, "lbmx_get_stats: null argument");
 	*out = e->stats;
+	out->halo_peer_memory = e->p2p ? 1 : 0;
 	return LBMX_OK;
 }
 

@@ -624,13 +624,14 @@ __global__ void k_has_nan(const R* rho, long long n, int* flag)
 
 // copy `n_dirs` population planes (Y*Z reals each) between storage planes of one or two arrays: self halo exchange and packing
 template <typename R>
-__global__ void k_copy_planes(R* dst, const R* src, long long XYZ, int YZ, int n_dirs, const int* dirs, long long src_plane, long long dst_plane)
+__global__ void k_copy_planes(R* dst, const R* src, long long XYZ, int YZ, int n_dirs, const int* dirs, long long src_plane, long long dst_plane,
+							  long long dst_XYZ = 0)  // dst_XYZ: component stride of the destination array when it is another slab's (0 = same as XYZ)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= YZ)
 		return;
 	const int q = dirs[blockIdx.y];
-	dst[q * XYZ + dst_plane * YZ + i] = src[q * XYZ + src_plane * YZ + i];
+	dst[q * (dst_XYZ ? dst_XYZ : XYZ) + dst_plane * YZ + i] = src[q * XYZ + src_plane * YZ + i];
 }
 
 // launcher table filled by the per-family translation units ---------------------------------------------------------
