@@ -64,6 +64,30 @@ def test_ghost_planes_with_self_exchange_equal_plain_run(case_name):
 
 
 @pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
+@pytest.mark.parametrize("case_name", ["duct_aa", "box_ab"])
+def test_four_gpus_halo_exchange(case_name, transport):
+    """Four slabs in a periodic ring: every rank has two different neighbours (two peer mappings per rank)."""
+    import torch
+
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
+    import torch.multiprocessing as mp
+
+    import dist_workers as W
+
+    world = 4
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(W.nccl_engine_worker, args=(world, free_port(), case_name, tmp, transport), nprocs=world, join=True)
+        df, mac = W.gather(tmp, world)
+        halo = np.load(f"{tmp}/halo_0.npy")
+    case = W.DIST_CASES[case_name]()
+    assert halo[2] == (0 if transport == "nccl" else 1)
+    one_df, one_mac = run_ghost_single(case)
+    assert np.array_equal(df, one_df), "4 slabs must be identical to 1 slab with self-exchange"
+    assert np.array_equal(mac, one_mac)
+
+
+@pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
 @pytest.mark.parametrize("case_name", ["duct_ab", "duct_aa", "box_ab", "box_aa"])
 def test_two_gpus_halo_exchange(case_name, transport):
     """Two slabs, two processes, two GPUs.  Default transport: stores into the neighbour's array over NVLink (CUDA IPC peer
