@@ -305,7 +305,9 @@ def test_parity_arithmetic_is_bit_exact(name):
 
 
 @pytest.mark.parametrize("coll,eq,st,prec,nu", [(O.SRT, O.EQ_STD, O.AB, O.F32, 0.02), (O.CUM, O.EQ_INV_CUM, O.AA, O.F32, 1e-3), (O.MRT_LES, O.EQ_STD, O.AA, O.F32, 1e-3),
-                                                 (O.CUM, O.EQ_INV_CUM, O.AB, O.F64, 1e-3)])
+                                                 (O.CUM, O.EQ_INV_CUM, O.AB, O.F64, 1e-3), (O.KBC_N4, O.EQ_ENTROPIC, O.AA, O.F32, 1e-3), (O.KBC_C1, O.EQ_STD, O.AB, O.F64, 5e-3),
+                                                 (O.CLBM, O.EQ_STD, O.AB, O.F64, 1e-3), (O.CUM_2017_ANTIALIAS, O.EQ_INV_CUM, O.AA, O.F32, 1e-3),
+                                                 (O.SRT_MODIF_FORCE, O.EQ_STD, O.AA, O.F32, 0.02)])
 def test_1000_steps_parity_arithmetic_is_bit_exact(coll, eq, st, prec, nu):
     """The fp32 case on which the reference differs from itself by 2e-5 (strict vs FMA build): in parity arithmetic the engine
     stays identical to the strict reference over 1000 steps -- distributions, density and velocity."""
