@@ -24,7 +24,7 @@ def _build_and_run(strict: bool):
         assert r.returncode == 0, r.stderr[-3000:]
         r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     rows = re.findall(r"coll (\d+) eq (\d+) prec (\d+): (\d+) of (\d+) differ, max abs (\S+)", r.stdout)
-    assert len(rows) >= 24, r.stdout
+    assert len(rows) >= 28 and "(D2Q9)" in r.stdout, r.stdout
     return r.returncode, rows
 
 

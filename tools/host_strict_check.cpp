@@ -1,4 +1,5 @@
-// Host-side check of collide_strict.cuh against the CPU restatement (test tool; g++ -ffp-contract=off).
+// Host-side check of the engine's per-cell operators (collide*.cuh) against the CPU restatement (test tool; g++ -ffp-contract=off;
+// driven by tests/test_operators_on_host.py).
 #define __host__
 #define __device__
 #define __forceinline__ inline
@@ -50,6 +51,44 @@ int run(int coll, int eq, int prec)
 	printf("coll %d eq %d prec %d: %zu of %zu differ, max abs %.3e\n", coll, eq, prec, nd, 27 * XYZ, mx);
 	return nd != 0;
 }
+// D2Q9 (d2q9/col_srt.h, col_clbm.h): X x Y x 1 periodic box, storage index (x * Z + z) * Y + y with Z = 1
+template <typename R, int KIND>
+int run2d(int coll, int prec)
+{
+	const int NX = 7, NY = 6;
+	oracle_desc d{};
+	d.lattice = ORC_D2Q9; d.coll = coll; d.eq = ORC_EQ_STD; d.streaming = ORC_STREAM_AB; d.macro = ORC_MACRO_DEFAULT; d.inflow = ORC_INFLOW_CONST;
+	d.precision = prec; d.nproc = 1; d.X = NX; d.Y = NY; d.Z = 1; d.ox = 0;
+	oracle_params p{};
+	p.lbmViscosity = 2e-2; p.fx = 2e-6; p.fy = -1e-6;
+	const size_t XYZ = (size_t) NX * NY;
+	std::vector<R> a(9 * XYZ), b(9 * XYZ), mac(3 * XYZ), mine(9 * XYZ);
+	std::vector<int16_t> map(XYZ, 6);  // D2Q9 GEO_PERIODIC
+	srand(7);
+	for (int q = 0; q < 9; q++) {
+		int n = (D2Q9::cx(q) != 0) + (D2Q9::cy(q) != 0);
+		double w = n == 0 ? 4. / 9 : n == 1 ? 1. / 9 : 1. / 36;
+		for (size_t i = 0; i < XYZ; i++) a[q * XYZ + i] = (R) (w * (1 + 0.05 * (rand() / (double) RAND_MAX - 0.5)));
+	}
+	Phys<R> P; P.nu = (R) p.lbmViscosity; P.omega1 = R(1) / (R(3) * P.nu + R(0.5)); P.fx = (R) p.fx; P.fy = (R) p.fy; P.fz = 0;
+	for (int x = 0; x < NX; x++) for (int y = 0; y < NY; y++) {
+		R f[9];
+		for (int q = 0; q < 9; q++) {
+			int xs = (x - D2Q9::cx(q) + NX) % NX, ys = (y - D2Q9::cy(q) + NY) % NY;
+			f[q] = a[q * XYZ + (size_t) xs * NY + ys];
+		}
+		R rho, vx, vy, vz;
+		density_velocity(f, P, rho, vx, vy, vz);
+		collide<KIND>(f, P, 0, rho, vx, vy, vz);
+		for (int q = 0; q < 9; q++) mine[q * XYZ + (size_t) x * NY + y] = f[q];
+	}
+	oracle_step(&d, &p, a.data(), b.data(), mac.data(), map.data(), 0, 1, 1);
+	size_t nd = 0; double mx = 0;
+	for (size_t i = 0; i < 9 * XYZ; i++) if (mine[i] != b[i]) { nd++; mx = std::fmax(mx, std::fabs((double) mine[i] - (double) b[i])); }
+	printf("coll %d eq %d prec %d: %zu of %zu differ, max abs %.3e (D2Q9)\n", coll, 0, prec, nd, 9 * XYZ, mx);
+	return nd != 0;
+}
+
 int main()
 {
 	int r = 0;
@@ -77,5 +116,9 @@ int main()
 	r |= run<float, K_KBC_C3>(ORC_COLL_KBC_C3, ORC_EQ_STD, ORC_F32);
 	r |= run<float, K_KBC_C4>(ORC_COLL_KBC_C4, ORC_EQ_STD, ORC_F32);
 	r |= run<double, K_KBC_C4>(ORC_COLL_KBC_C4, ORC_EQ_STD, ORC_F64);
+	r |= run2d<float, K_SRT>(ORC_COLL_SRT, ORC_F32);
+	r |= run2d<double, K_SRT>(ORC_COLL_SRT, ORC_F64);
+	r |= run2d<float, K_CLBM>(ORC_COLL_CLBM, ORC_F32);
+	r |= run2d<double, K_CLBM>(ORC_COLL_CLBM, ORC_F64);
 	return r;
 }
