@@ -32,7 +32,7 @@ struct StateLocal : State<NSE>
 
 	void computeAfterLBMKernel() override
 	{
-		if (halt_at > 0 && nse.iterations + 1 >= halt_at)
+		if (halt_at > 0 && nse.iterations >= halt_at)	 // the hook runs in AfterSimUpdate, after the step was counted (state.hpp:1153)
 			nse.terminate = true;
 	}
 
@@ -116,6 +116,9 @@ int run(int X, int Y, int Z, int steps, const char* prefix, int halt, bool dump)
 		state.add2Dcut_X(X / 2, "cutsX/cut_X");
 		state.add2Dcut_Z(Z / 2, "cut_Z");
 		state.add3Dcut(X / 4, Y / 4, Z / 4, X / 2, Y / 2, Z / 2, 2, "box");
+		state.cnt[VTK1D].period = 30 * lat.physDt;
+		state.add1Dcut_X(lat.lbm2physY(Y / 2), lat.lbm2physZ(Z / 2), "centre_line");
+		state.add1Dcut_Z(lat.lbm2physX(X / 2), lat.lbm2physY(Y / 2), "profile_z");
 	}
 	execute(state);
 	if (halt > 0) {	 // what core.h does when the wall time runs out (core.h:57-63)

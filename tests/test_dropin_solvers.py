@@ -186,6 +186,9 @@ def test_raw_dump_writers_keep_reference_ordering():
         hb, db = _read_dump(os.path.join(res, "output_3Dcut_box.2"))
         hx, dx = _read_dump(os.path.join(res, "output_2D_cutsX", "cut_X.3"))  # steps 0, 20, 40, 60
         hz, dz = _read_dump(os.path.join(res, "output_2D_cut_Z.3"))
+        line_x = np.loadtxt(os.path.join(res, "probes1D", "centre_line_rank000_000002"))  # cycles at steps 0, 30, 60
+        line_z = np.loadtxt(os.path.join(res, "probes1D", "profile_z_rank000_000002"))
+        header = open(os.path.join(res, "probes1D", "centre_line_rank000_000002")).read().splitlines()[:2]
     zyx = lambda a: a.transpose(1, 2, 0)  # [x, z, y] -> [z, y, x]
     assert h3["global"] == [X, Y, Z] and sorted(d3) == ["TIME", "lbm_density", "velocityX", "velocityY", "velocityZ", "wall"]
     assert np.array_equal(d3["wall"].reshape(Z, Y, X), zyx(cmap).astype(np.int32))
@@ -348,3 +351,8 @@ def test_two_ranks_through_the_host_mirror_equal_one(exe_name):
         assert any("Loading data from checkpoint" in o for o in outs) and any(f"iterations={steps} " in o for o in outs), outs
         resumed = assemble(t3, "resumed")
         assert np.array_equal(resumed, two), f"max |resumed - two| = {np.abs(resumed - two).max():.3e}"
+    # 1-D cuts: text tables "#time", "#1:x  2:lbm_density  3:velocity[0] ..." (state.hpp:225-238), %e formatting
+    assert header[0].startswith("#time ") and header[1].split("\t") == ["#1:x", "2:lbm_density", "3:velocity[0]", "4:velocity[1]", "5:velocity[2]"]
+    assert line_x.shape == (X, 5) and line_z.shape == (Z, 5)
+    assert np.allclose(line_x[:, 1], mac[0][:, Z // 2, Y // 2], rtol=1e-6) and np.allclose(line_x[:, 2], mac[1][:, Z // 2, Y // 2], rtol=1e-6, atol=1e-12)
+    assert np.allclose(line_z[:, 1], mac[0][X // 2, :, Y // 2], rtol=1e-6) and np.allclose(line_z[:, 4], mac[3][X // 2, :, Y // 2], rtol=1e-6, atol=1e-12)

@@ -1393,7 +1393,6 @@ struct State
 	LBM<NSE> nse;
 	T_COUNTER cnt[MAX_COUNTER];
 	CheckpointManager checkpoint;
-	int n_cuts = 0;	 // 1-D cuts registered through add1Dcut*: their text writers are out of scope, the calls are accepted
 
 	struct T_PROBE2DCUT
 	{
@@ -1408,8 +1407,23 @@ struct State
 		idx ox = 0, oy = 0, oz = 0, lx = 0, ly = 0, lz = 0, step = 1;
 		int cycle = 0;
 	};
+	struct T_PROBE1DCUT
+	{
+		std::string name;
+		int type = 0;  // 0,1,2 = the line runs along x,y,z
+		idx pos1 = 0, pos2 = 0;
+		int cycle = 0;
+	};
+	struct T_PROBE1DLINECUT
+	{
+		std::string name;
+		point_t from, to;
+		int cycle = 0;
+	};
 	std::vector<T_PROBE2DCUT> probe2Dvec;
 	std::vector<T_PROBE3DCUT> probe3Dvec;
+	std::vector<T_PROBE1DCUT> probe1Dvec;
+	std::vector<T_PROBE1DLINECUT> probe1Dlinevec;
 
 	virtual void probe1() {}
 	virtual void probe2() {}
@@ -1474,7 +1488,107 @@ struct State
 			p.cycle++;
 		}
 	}
-	virtual void writeVTKs_1D() {}
+	// 1-D cuts along an axis (add1Dcut_X/Y/Z) and along a physical line (add1Dcut): text tables of the outputData() fields in the
+	// reference's format, results_<id>/probes1D/<name>_rank<rrr>_<cycle> (state.hpp:175-340)
+	virtual void writeVTKs_1D()
+	{
+		for (auto& pr : probe1Dvec) {
+			char suffix[64];
+			std::snprintf(suffix, sizeof suffix, "_rank%03d_%06d", nse.rank, pr.cycle);
+			const std::string fname = "results_" + id + "/probes1D/" + pr.name + suffix;
+			const size_t slash = fname.rfind('/');
+			lbmx_host::make_dirs(fname.substr(0, slash));
+			write1Dcut_axis(pr.type, pr.pos1, pr.pos2, fname);
+			pr.cycle++;
+		}
+		for (auto& pr : probe1Dlinevec) {
+			char suffix[64];
+			std::snprintf(suffix, sizeof suffix, "_rank%03d_%06d", nse.rank, pr.cycle);
+			const std::string fname = "results_" + id + "/probes1D/" + pr.name + suffix;
+			const size_t slash = fname.rfind('/');
+			lbmx_host::make_dirs(fname.substr(0, slash));
+			write1Dcut(pr.from, pr.to, fname);
+			pr.cycle++;
+		}
+	}
+	// header "#time ...", "#1:<coordinate>  2:<field> ..." as the reference writes it (state.hpp:225-238)
+	void write_1d_header(std::FILE* fout, const char* coordinate)
+	{
+		char idd[500];
+		real value;
+		int dofs = 1;
+		std::fprintf(fout, "#time %f s\n", (double) nse.physTime());
+		std::fprintf(fout, "#1:%s", coordinate);
+		const BLOCK_NSE& b0 = nse.blocks.front();
+		int count = 2;
+		for (int index = 0; outputData(b0, index, 0, idd, b0.offset.x(), b0.offset.y(), b0.offset.z(), value, dofs); index++) {
+			if (dofs == 1)
+				std::fprintf(fout, "\t%d:%s", count++, idd);
+			else
+				for (int i = 0; i < dofs; i++)
+					std::fprintf(fout, "\t%d:%s[%d]", count++, idd, i);
+		}
+		std::fprintf(fout, "\n");
+	}
+	void write_1d_row(std::FILE* fout, const BLOCK_NSE& block, double coordinate, idx x, idx y, idx z)
+	{
+		char idd[500];
+		real value;
+		int dofs = 1;
+		std::fprintf(fout, "%e", coordinate);
+		for (int index = 0; outputData(block, index, 0, idd, block.offset.x(), block.offset.y(), block.offset.z(), value, dofs); index++) {
+			const int n = dofs;
+			for (int dof = 0; dof < n; dof++) {
+				outputData(block, index, dof, idd, x, y, z, value, dofs);
+				std::fprintf(fout, "\t%e", (double) value);
+			}
+		}
+		std::fprintf(fout, "\n");
+	}
+	// type 0/1/2: the line runs along x/y/z through the two given lattice coordinates of the other axes (state.hpp:262-340)
+	void write1Dcut_axis(int type, idx pos1, idx pos2, const std::string& fname)
+	{
+		std::FILE* fout = std::fopen(fname.c_str(), "wt");
+		if (! fout)
+			throw std::runtime_error("write1Dcut: cannot create " + fname);
+		write_1d_header(fout, type == 0 ? "x" : (type == 1 ? "y" : "z"));
+		for (const auto& block : nse.blocks) {
+			const idx lo = type == 0 ? block.offset.x() : (type == 1 ? block.offset.y() : block.offset.z());
+			const idx n = type == 0 ? block.local.x() : (type == 1 ? block.local.y() : block.local.z());
+			for (idx i = lo; i < lo + n; i++) {
+				const idx x = type == 0 ? i : pos1, y = type == 1 ? i : (type == 0 ? pos1 : pos2), z = type == 2 ? i : pos2;
+				if (! block.isLocalIndex(x, y, z))
+					continue;
+				const double coordinate = type == 0 ? nse.lat.lbm2physX(i) : (type == 1 ? nse.lat.lbm2physY(i) : nse.lat.lbm2physZ(i));
+				write_1d_row(fout, block, coordinate, x, y, z);
+			}
+		}
+		std::fclose(fout);
+	}
+	void write1Dcut_X(idx y, idx z, const std::string& fname) { write1Dcut_axis(0, y, z, fname); }
+	void write1Dcut_Y(idx x, idx z, const std::string& fname) { write1Dcut_axis(1, x, z, fname); }
+	void write1Dcut_Z(idx x, idx y, const std::string& fname) { write1Dcut_axis(2, x, y, fname); }
+	// sampling along a physical line (state.hpp:210-259)
+	void write1Dcut(point_t from, point_t to, const std::string& fname)
+	{
+		std::FILE* fout = std::fopen(fname.c_str(), "wt");
+		if (! fout)
+			throw std::runtime_error("write1Dcut: cannot create " + fname);
+		const point_t i = nse.lat.phys2lbmPoint(from), f = nse.lat.phys2lbmPoint(to);
+		const real dx = i.x() - f.x(), dy = i.y() - f.y(), dz = i.z() - f.z();
+		const real dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+		real ds = (real) 1.0 / (dist * (real) 2.0);
+		if ((i[0] == f[0] && i[1] == f[1]) || (i[1] == f[1] && i[2] == f[2]) || (i[0] == f[0] && i[2] == f[2]))
+			ds = (real) 1.0 / dist;	 // sampling along an axis: one sample per cell
+		write_1d_header(fout, "rel_pos");
+		for (real sv = 0; sv <= (real) 1.0; sv += ds) {
+			const real px = i.x() + sv * (f.x() - i.x()), py = i.y() + sv * (f.y() - i.y()), pz = i.z() + sv * (f.z() - i.z());
+			for (const auto& block : nse.blocks)
+				if (block.isLocalIndex((idx) px, (idx) py, (idx) pz))
+					write_1d_row(fout, block, (double) ((sv * dist - (real) 0.5) * nse.lat.physDl), (idx) px, (idx) py, (idx) pz);
+		}
+		std::fclose(fout);
+	}
 	template <typename... ARGS>
 	void add2Dcut(int type, idx pos, const char* fmts, ARGS... args)
 	{
@@ -1498,14 +1612,32 @@ struct State
 		p.ox = ox, p.oy = oy, p.oz = oz, p.lx = lx, p.ly = ly, p.lz = lz, p.step = step;
 		probe3Dvec.push_back(p);
 	}
+	// state.hpp:72-170: a line between two physical points, or along an axis through two physical coordinates of the other axes
 	template <typename... ARGS>
-	void add1Dcut(point_t, point_t, const char*, ARGS...) { n_cuts++; }
+	void add1Dcut(point_t from, point_t to, const char* fmts, ARGS... args)
+	{
+		T_PROBE1DLINECUT p;
+		p.name = cut_name(fmts, args...);
+		p.from = from;
+		p.to = to;
+		probe1Dlinevec.push_back(p);
+	}
 	template <typename... ARGS>
-	void add1Dcut_X(real, real, const char*, ARGS...) { n_cuts++; }
+	void add1Dcut_axis(int type, idx pos1, idx pos2, const char* fmts, ARGS... args)
+	{
+		T_PROBE1DCUT p;
+		p.name = cut_name(fmts, args...);
+		p.type = type;
+		p.pos1 = pos1;
+		p.pos2 = pos2;
+		probe1Dvec.push_back(p);
+	}
 	template <typename... ARGS>
-	void add1Dcut_Y(real, real, const char*, ARGS...) { n_cuts++; }
+	void add1Dcut_X(real y, real z, const char* fmts, ARGS... args) { add1Dcut_axis(0, nse.lat.phys2lbmY(y), nse.lat.phys2lbmZ(z), fmts, args...); }
 	template <typename... ARGS>
-	void add1Dcut_Z(real, real, const char*, ARGS...) { n_cuts++; }
+	void add1Dcut_Y(real x, real z, const char* fmts, ARGS... args) { add1Dcut_axis(1, nse.lat.phys2lbmX(x), nse.lat.phys2lbmZ(z), fmts, args...); }
+	template <typename... ARGS>
+	void add1Dcut_Z(real x, real y, const char* fmts, ARGS... args) { add1Dcut_axis(2, nse.lat.phys2lbmX(x), nse.lat.phys2lbmY(y), fmts, args...); }
 
 	virtual bool outputData(const BLOCK_NSE&, int, int, char*, idx, idx, idx, real&, int&) { return false; }
 
@@ -1537,7 +1669,7 @@ struct State
 			reset();
 		lbmx_host::log_info("lbmx: %s lattice %ld x %ld x %ld, %s, %s, %s", NSE::COLL::id, (long) nse.lat.global.x(), (long) nse.lat.global.y(),
 							(long) nse.lat.global.z(), NSE::lbmx_precision == LBMX_F64 ? "fp64" : "fp32", NSE::lbmx_streaming == LBMX_STREAM_AA ? "A-A" : "A-B",
-							n_cuts ? "1-D cuts registered: their writers are out of scope (DESIGN.md)" : "raw-dump writers");
+							"raw-dump writers");
 		timer_SimInit.stop();
 	}
 	// State::updateKernelData (state.hpp:1314-1321)
@@ -1563,7 +1695,6 @@ struct State
 			b.pushParams();
 			lbmx_host::check(lbmx_step(b.engine, 1), "lbmx_step");
 		}
-		computeAfterLBMKernel();
 		nse.iterations++;
 		bool doCopy = false;
 		for (int c = 0; c < MAX_COUNTER; c++)
@@ -1573,36 +1704,27 @@ struct State
 			nse.copyMacroToHost();
 		timer_SimUpdate.stop();
 	}
-	// State::AfterSimUpdate (state.hpp:1148-1278): cadence-driven hooks, NaN scan, GLUPS line
+	// State::AfterSimUpdate (state.hpp:1148-1278): hook, NaN scan on the cadence of the other actions, probes and writers in the
+	// reference's order, statistics resets last (followed by a macro upload), GLUPS line on rank 0
 	virtual void AfterSimUpdate()
 	{
+		computeAfterLBMKernel();
 		const real t = nse.physTime();
-		if (cnt[PRINT].action(t)) {
+		bool write_info = false;
+		for (int c : {(int) PRINT, (int) VTK1D, (int) VTK2D, (int) VTK3D, (int) VTK3DCUT, (int) PROBE1, (int) PROBE2, (int) PROBE3})
+			write_info |= cnt[c].action(t);
+		if (write_info)
+			cnt[PRINT].count++;
+		bool nan_detected = false;
+		if (nse.iterations > 1 && write_info && MACRO::N > 0) {
 			int32_t nan = 0;
 			lbmx_host::check(lbmx_has_nan(nse.blocks.front().engine, &nan), "lbmx_has_nan");
-			nan = TNL::MPI::reduce(nan, MPI_LOR, nse.communicator);	 // every rank must take the same decision (state.hpp:1166-1188)
-			if (nan) {
-				lbmx_host::log_info("nan detected");
+			nan_detected = TNL::MPI::reduce(nan != 0, MPI_LOR, nse.communicator);  // every rank takes the same decision (state.hpp:1166-1188)
+			if (nan_detected) {
+				lbmx_host::log_info("Detected NaN, terminating the simulation.");
 				nse.terminate = true;
+				nse.copyMacroToHost();
 			}
-			for (auto& b : nse.blocks)
-				lbmx_host::check(lbmx_sync(b.engine), "lbmx_sync");
-			const double now = timer_total.getRealTime();
-			const double glups = (nse.iterations - glups_prev_iterations) / (now - glups_prev_time + 1e-30) * (double) nse.lat.global.x() * (double) nse.lat.global.y()
-							   * (double) nse.lat.global.z() * 1e-9;
-			lbmx_host::log_info("GLUPS=%.3f iter=%d t=%1.3fs dt=%1.2e lbmVisc=%1.2e WT=%.0fs", glups, nse.iterations, (double) t, (double) nse.lat.physDt,
-								(double) nse.lat.lbmViscosity(), now);
-			glups_prev_iterations = nse.iterations;
-			glups_prev_time = now;
-			cnt[PRINT].count++;
-		}
-		if (cnt[STAT_RESET].action(t)) {
-			statReset();
-			cnt[STAT_RESET].count++;
-		}
-		if (cnt[STAT2_RESET].action(t)) {
-			stat2Reset();
-			cnt[STAT2_RESET].count++;
 		}
 		if (cnt[PROBE1].action(t)) {
 			probe1();
@@ -1616,21 +1738,43 @@ struct State
 			probe3();
 			cnt[PROBE3].count++;
 		}
-		if (cnt[VTK1D].action(t)) {
-			writeVTKs_1D();
-			cnt[VTK1D].count++;
-		}
-		if (cnt[VTK2D].action(t)) {
-			writeVTKs_2D();
-			cnt[VTK2D].count++;
-		}
-		if (cnt[VTK3D].action(t)) {
+		if (cnt[VTK3D].action(t) || nan_detected) {
 			writeVTKs_3D();
 			cnt[VTK3D].count++;
 		}
 		if (cnt[VTK3DCUT].action(t)) {
 			writeVTKs_3Dcut();
 			cnt[VTK3DCUT].count++;
+		}
+		if (cnt[VTK2D].action(t) || nan_detected) {
+			writeVTKs_2D();
+			cnt[VTK2D].count++;
+		}
+		if (cnt[VTK1D].action(t)) {
+			writeVTKs_1D();
+			cnt[VTK1D].count++;
+		}
+		// statReset is called after all probes and output; the cleared statistics go back to the device (state.hpp:1231-1242)
+		if (cnt[STAT_RESET].action(t)) {
+			statReset();
+			nse.copyMacroToDevice();
+			cnt[STAT_RESET].count++;
+		}
+		if (cnt[STAT2_RESET].action(t)) {
+			stat2Reset();
+			nse.copyMacroToDevice();
+			cnt[STAT2_RESET].count++;
+		}
+		if (write_info && nse.iterations > 1 && nse.rank == 0) {
+			for (auto& b : nse.blocks)
+				lbmx_host::check(lbmx_sync(b.engine), "lbmx_sync");
+			const double now = timer_total.getRealTime();
+			const double glups = (nse.iterations - glups_prev_iterations) / std::max(1e-6, now - glups_prev_time) * (double) nse.lat.global.x()
+							   * (double) nse.lat.global.y() * (double) nse.lat.global.z() * 1e-9;
+			lbmx_host::log_info("GLUPS=%.3f iter=%d t=%1.3fs dt=%1.2e lbmVisc=%1.2e WT=%.0fs", glups, nse.iterations, (double) t, (double) nse.lat.physDt,
+								(double) nse.lat.lbmViscosity(), now);
+			glups_prev_iterations = nse.iterations;
+			glups_prev_time = now;
 		}
 	}
 	virtual void AfterSimFinished()
@@ -1701,6 +1845,10 @@ struct State
 			checkpoint.saveLoadAttribute("State_probe3D_" + std::to_string(i) + "_cycle", probe3Dvec[i].cycle);
 		for (std::size_t i = 0; i < probe2Dvec.size(); i++)
 			checkpoint.saveLoadAttribute("State_probe2D_" + std::to_string(i) + "_cycle", probe2Dvec[i].cycle);
+		for (std::size_t i = 0; i < probe1Dvec.size(); i++)
+			checkpoint.saveLoadAttribute("State_probe1D_" + std::to_string(i) + "_cycle", probe1Dvec[i].cycle);
+		for (std::size_t i = 0; i < probe1Dlinevec.size(); i++)
+			checkpoint.saveLoadAttribute("State_probe1Dline_" + std::to_string(i) + "_cycle", probe1Dlinevec[i].cycle);
 		for (auto& block : nse.blocks) {
 			if (mode == adios2::Mode::Read)	 // "df_cur" / "df_out" are roles that rotate with the iteration count (lbm.hpp:314-330): restore it first
 				lbmx_host::check(lbmx_set_iterations(block.engine, nse.iterations), "lbmx_set_iterations");
