@@ -29,7 +29,7 @@ def test_clients_compile_against_the_host_mirror():
     names = {os.path.basename(b) for b in built}
     assert "channel3d" in names
     if HAVE_REF:
-        assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa"} <= names
+        assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim_2_ab", "ref_sim_2_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa"} <= names
 
 
 def test_custom_device_traits_are_rejected_at_compile_time():
@@ -356,3 +356,29 @@ def test_two_ranks_through_the_host_mirror_equal_one(exe_name):
     assert line_x.shape == (X, 5) and line_z.shape == (Z, 5)
     assert np.allclose(line_x[:, 1], mac[0][:, Z // 2, Y // 2], rtol=1e-6) and np.allclose(line_x[:, 2], mac[1][:, Z // 2, Y // 2], rtol=1e-6, atol=1e-12)
     assert np.allclose(line_z[:, 1], mac[0][X // 2, :, Y // 2], rtol=1e-6) and np.allclose(line_z[:, 4], mac[3][X // 2, :, Y // 2], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe_name,args", [("ref_sim_2_ab", ["--use-forcing"]), ("ref_sim_2_aa", ["--use-forcing"]), ("ref_sim_2_ab", []), ("ref_sim_2_ab", ["--precision", "double"])])
+def test_reference_duct_verification_solver(exe_name, args):
+    """sim_NSE/sim_2.cu, unmodified: the reference's own verification case (square duct against the analytical series solution,
+    sim_2.cu:63-88).  With --use-forcing the flow spins up from rest (periodic, body force); without it the analytical profile is the
+    inflow (NSE_Data_XProfileInflow, a DATA class defined in the solver itself: its host-side vx_profile array is uploaded by the
+    mirror).  The solver prints its L1 / L2 error against the analytical solution at every probe: it must be finite and shrink."""
+    exe = os.path.join(BIN, exe_name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe_name} not built (needs /root/reference at build time)")
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([exe, "--min-resolution", "1", "--max-resolution", "1", "--final-time", "40"] + args, capture_output=True, text=True, timeout=900, cwd=tmp)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    errs = [(float(a), float(b)) for a, b in re.findall(r"l1error_phys=(\S+) l2error_phys=(\S+)", r.stdout)]
+    assert len(errs) >= 10, r.stdout[-2000:]
+    l1 = np.array([e[0] for e in errs])
+    assert np.isfinite(l1).all() and (l1 > 0).all()
+    if "--use-forcing" in args:
+        # spin-up from rest towards the analytical profile: the viscous time H^2 / nu is ~4000 s, so 40 s only start the approach --
+        # the error must fall monotonically
+        assert np.all(np.diff(l1[1:]) <= 0) and l1[-1] < 0.97 * l1[1], f"error against the analytical profile does not shrink: {l1[1]:.3e} -> {l1[-1]:.3e}"
+    else:
+        assert l1[-1] < 0.5 * l1[1] or l1[-1] < 1e-9, f"{l1[1]:.3e} -> {l1[-1]:.3e}"  # the inflow already carries the analytical profile
+    print(exe_name, args, "l1 error:", l1[1], "->", l1[-1], "| last line:", r.stdout.strip().splitlines()[-1][:120])

@@ -38,6 +38,8 @@
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <math.h>    // the C++ wrappers of <math.h> / <stdlib.h> put the float / double overloads of abs, sqrt, fabs ... into the global
+#include <stdlib.h>  // namespace, as the CUDA headers do for the reference's solvers (sim_NSE/sim_2.cu:243 calls abs() on a real)
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -59,6 +61,9 @@
 #endif
 #ifndef CUDA_HOSTDEV
 	#define CUDA_HOSTDEV
+#endif
+#ifndef PI
+	#define PI 3.1415926535897932384	 // lbm_common/ciselnik.h:4 (solvers use it, e.g. sim_NSE/sim_2.cu:76)
 #endif
 #ifndef __cuda_callable__
 	#define __cuda_callable__
@@ -372,6 +377,26 @@ struct Traits
 	using map_t = _map_t;
 	using point_t = TNL::Containers::StaticVector<3, real>;
 	using idx3d = TNL::Containers::StaticVector<3, idx>;
+	// host-side NDArray of the reference's layout (defs.h:85-100: permutation (x, z, y), y fastest) for solver-owned fields such as
+	// the analytical profile cache of sim_NSE/sim_2.cu:52-113; device-side arrays live behind the C ABI
+	template <typename T, typename Device = TNL::Devices::Host>
+	struct array3d
+	{
+		std::vector<T> v;
+		idx nx = 0, ny = 0, nz = 0;
+		void setSizes(idx x, idx y, idx z)
+		{
+			nx = x, ny = y, nz = z;
+			v.assign((size_t) x * y * z, T());
+		}
+		void allocate() {}
+		T* getData() { return v.empty() ? nullptr : v.data(); }
+		const T* getData() const { return v.empty() ? nullptr : v.data(); }
+		T& operator()(idx x, idx y, idx z) { return v[((size_t) x * nz + z) * ny + y]; }
+		const T& operator()(idx x, idx y, idx z) const { return v[((size_t) x * nz + z) * ny + y]; }
+		void setValue(T value) { std::fill(v.begin(), v.end(), value); }
+		idx getStorageSize() const { return (idx) v.size(); }
+	};
 	static_assert(std::is_same<_dreal, float>::value || std::is_same<_dreal, double>::value, "dreal must be float or double");
 	static_assert(sizeof(_map_t) == 2, "the engine stores cell types as 16-bit integers (defs.h:75)");
 	static constexpr int lbmx_precision = std::is_same<_dreal, double>::value ? LBMX_F64 : LBMX_F32;
@@ -923,6 +948,9 @@ struct LBM_BLOCK
 	HostField hBouzidi;	   // D2Q9 near-wall coefficients [8][local], allocated by allocateBouzidiCoeffArrays (lbm_block.hpp:740-770)
 	DeviceBouzidi dBouzidi;
 	lbmx_engine* engine = nullptr;
+	const dreal* uploaded_profile = nullptr;  // inflow profile last handed to the engine (pushParams)
+	int64_t uploaded_profile_sy = 0;
+	bool profile_uploaded = false;
 
 	LBM_BLOCK(idx3d global_, idx3d local_, idx3d offset_) : global(global_), local(local_), offset(offset_) { dBouzidi.owner = this; }
 	LBM_BLOCK(const LBM_BLOCK&) = delete;
@@ -1205,6 +1233,23 @@ struct LBM_BLOCK
 			p.inflow_vz = data.inflow_vz;
 		p.stat_counter = data.stat_counter;
 		lbmx_host::check(lbmx_set_params(engine, &p), "lbmx_set_params");
+		if constexpr (lbmx_host::has_vx_profile<typename CONFIG::DATA>::value) {
+			// NSE_Data_XProfileInflow (sim_NSE/sim_2.cu:16-33): the solver owns a host array dreal[y + z * size_y]; it is uploaded when the
+			// pointer or its size changes.  Without a profile (periodic runs with forcing) the inflow cells do not exist: a zero profile.
+			const dreal* src = data.vx_profile;
+			const int64_t sy = src ? (int64_t) data.size_y : (int64_t) local.y();
+			if (src != uploaded_profile || sy != uploaded_profile_sy || ! profile_uploaded) {
+				std::vector<dreal> zeros;
+				if (! src) {
+					zeros.assign((size_t) local.y() * local.z(), (dreal) 0);
+					src = zeros.data();
+				}
+				lbmx_host::check(lbmx_set_inflow_profile(engine, src, sy, (int64_t) local.z()), "lbmx_set_inflow_profile");
+				uploaded_profile = data.vx_profile;
+				uploaded_profile_sy = sy;
+				profile_uploaded = true;
+			}
+		}
 	}
 };
 
