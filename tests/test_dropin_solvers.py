@@ -29,7 +29,7 @@ def test_clients_compile_against_the_host_mirror():
     names = {os.path.basename(b) for b in built}
     assert "channel3d" in names
     if HAVE_REF:
-        assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim_2_ab", "ref_sim_2_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa"} <= names
+        assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim_2_ab", "ref_sim_2_aa", "ref_sim_3_ab", "ref_sim_3_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa"} <= names
 
 
 def test_custom_device_traits_are_rejected_at_compile_time():
@@ -100,13 +100,13 @@ def test_channel3d_matches_oracle(prec):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("exe_name,arg", [("ref_sim_1_ab", "1"), ("ref_sim_1_aa", "1"), ("ref_sim2d_1_ab", "1")])
+@pytest.mark.parametrize("exe_name,arg", [("ref_sim_1_ab", "1"), ("ref_sim_1_aa", "1"), ("ref_sim2d_1_ab", "1"), ("ref_sim_3_ab", None)])  # sim_3 paints GEO_OUTFLOW_RIGHT_INTERP, which exists for A-B only (streaming_AA.h has no streamingInterpRight)
 def test_unmodified_reference_solvers_run(exe_name, arg):
     exe = os.path.join(BIN, exe_name)
     if not os.path.exists(exe):
         pytest.skip(f"{exe_name} not built (needs /root/reference at build time)")
     with tempfile.TemporaryDirectory() as tmp:
-        r = subprocess.run([exe, arg], capture_output=True, text=True, timeout=600, cwd=tmp)
+        r = subprocess.run([exe] + ([arg] if arg else []), capture_output=True, text=True, timeout=600, cwd=tmp)
         dumps = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp) for f in fs if f.endswith(".txt")]
         flags = [f for dp, _, fs in os.walk(tmp) for f in fs if f.startswith("flag.")]
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
