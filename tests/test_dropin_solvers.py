@@ -382,3 +382,71 @@ def test_reference_duct_verification_solver(exe_name, args):
     else:
         assert l1[-1] < 0.5 * l1[1] or l1[-1] < 1e-9, f"{l1[1]:.3e} -> {l1[-1]:.3e}"  # the inflow already carries the analytical profile
     print(exe_name, args, "l1 error:", l1[1], "->", l1[-1], "| last line:", r.stdout.strip().splitlines()[-1][:120])
+
+
+def test_obstacle_painters_on_cpu():
+    """lbm3d/obstacles_lbm.h (lbmDrawSphere / Cylinder / Cube / BoundingBox) paints exactly the cells the reference's formulas select
+    (obstacles_lbm.h:3-87), checked against numpy; host-only, no engine."""
+    src = r'''
+#include "lbm3d/core.h"
+#include "lbm3d/obstacles_lbm.h"
+#include <fstream>
+using T = TraitsDP;
+using COLL = D3Q27_CUM<T, D3Q27_EQ_INV_CUM<T>>;
+using NSE = LBM_CONFIG<T, D3Q27_KernelStruct, NSE_Data_ConstInflow<T>, COLL, typename COLL::EQ, D3Q27_STREAMING<T>, D3Q27_BC_All, D3Q27_MACRO_Default<T>>;
+int main(int argc, char** argv)
+{
+	TNLMPI_INIT mpi(argc, argv);
+	using lat_t = Lattice<3, double, long>;
+	lat_t lat;
+	lat.global = lat_t::CoordinatesType(40, 24, 20);
+	lat.physOrigin = {0., 0., 0.};
+	lat.physDl = 0.05;
+	lat.physDt = 1e-3;
+	lat.physViscosity = 1e-5;
+	LBM<NSE> nse(MPI_COMM_WORLD, lat);
+	nse.allocateHostData();
+	nse.resetMap(0);
+	lbmDrawSphere(nse, 1, {0.52, 0.61, 0.49}, 0.21);
+	lbmDrawCylinder(nse, 2, {1.31, 0.3, 0.52}, 0.16);
+	lbmDrawCube(nse, 3, {1.71, 0.92, 0.71}, 0.11);
+	lbmDrawBoundingBox(nse, 4, {0.2, 0.1, 0.1}, {0.45, 0.3, 0.25});
+	auto& m = nse.blocks.front().hmap.v;
+	std::ofstream(argv[1], std::ios::binary).write((const char*) m.data(), m.size() * sizeof(short));
+	return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as tmp:
+        f = os.path.join(tmp, "paint.cpp")
+        open(f, "w").write(src)
+        exe = os.path.join(tmp, "paint")
+        r = subprocess.run(["g++", "-std=c++17", f"-I{ROOT}/tnl_lbm_b200/host", f"-I{ROOT}/include", f"-I{ROOT}/tests/solver_shims", f, "-o", exe,
+                            f"-L{ROOT}/tnl_lbm_b200", "-llbmx", f"-Wl,-rpath,{ROOT}/tnl_lbm_b200"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        out = os.path.join(tmp, "map.bin")
+        r = subprocess.run([exe, out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        got = np.fromfile(out, dtype=np.int16).reshape(40, 20, 24)  # [x, z, y]
+    X, Y, Z, dl = 40, 24, 20, 0.05
+    cell = lambda p: tuple(int(c / dl + 0.5) for c in p)  # Lattice::phys2lbm: (x - origin) / dl + 1/2, truncated
+    x, z, y = np.meshgrid(np.arange(X), np.arange(Z), np.arange(Y), indexing="ij")
+    ref = np.zeros((X, Z, Y), dtype=np.int16)
+    c, r_ = cell((0.52, 0.61, 0.49)), 0.21 / dl
+    rng = int(np.ceil(r_)) + 1
+    box = lambda c, rng: (abs(x - c[0]) <= rng) & (abs(y - c[1]) <= rng) & (abs(z - c[2]) <= rng)
+    ref[box(c, rng) & (np.sqrt((x - c[0]) ** 2.0 + (y - c[1]) ** 2.0 + (z - c[2]) ** 2.0) < r_)] = 1
+    c, r_ = cell((1.31, 0.3, 0.52)), 0.16 / dl
+    rng = int(np.ceil(r_)) + 1
+    ref[(abs(x - c[0]) <= rng) & (abs(z - c[2]) <= rng) & (np.sqrt((x - c[0]) ** 2.0 + (z - c[2]) ** 2.0) < r_)] = 2
+    c, r_ = cell((1.71, 0.92, 0.71)), 0.11 / dl
+    rng = int(np.ceil(r_)) + 1
+    ref[box(c, rng) & (x - c[0] < r_) & (y - c[1] < r_) & (z - c[2] < r_)] = 3
+    p1 = [v / dl + 0.5 + 0.5 for v in (0.2, 0.1, 0.1)]
+    p2 = [v / dl + 0.5 - 0.5 for v in (0.45, 0.3, 0.25)]
+    ext = [int(round(abs(a - b))) for a, b in zip(p1, p2)]
+    for i in range(ext[0] + 1):
+        for j in range(ext[1] + 1):
+            for k in range(ext[2] + 1):
+                ref[int(p1[0] + i), int(p1[2] + k), int(p1[1] + j)] = 4
+    assert np.array_equal(got, ref), f"{(got != ref).sum()} cells differ; painted counts {[(int(t), int((got == t).sum())) for t in range(5)]}"
+    assert all((got == t).sum() > 0 for t in (1, 2, 3, 4))
