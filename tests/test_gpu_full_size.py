@@ -1,4 +1,4 @@
-"""Properties at BASELINE.json's full single-GPU size (512^3, D3Q27 cumulant fp64 A-A -- 29 GB of distributions), where the CPU
+"""BASELINE.json configs[0] at its full size against the CPU oracle, and properties at BASELINE.json's full single-GPU size (512^3, D3Q27 cumulant fp64 A-A -- 29 GB of distributions), where the CPU
 oracle cannot follow:
 
 * periodic replication -- a 512^3 periodic box initialised with a field of period 64 must reproduce, bit for bit, the 64^3 box
@@ -58,3 +58,26 @@ def test_512_cube_replicates_the_64_cube_and_conserves():
     jx0 = float((m0[0] * m0[1]).sum(dtype=np.float64))   # macro_init zeroes the force: rho*u = j
     jx1 = float((big[0] * big[1]).sum(dtype=np.float64))  # last step's pre-collision state: j after STEPS-1 steps, + F/2
     assert abs((jx1 - jx0) / n - (STEPS - 0.5) * FX) < 1e-12
+
+
+def test_sim1_resolution_4_against_the_cpu_oracle():
+    """BASELINE.json configs[0] / SURVEY 8d cfg 1: the geometry of sim_NSE/sim_1.cu at resolution 4 (512 x 128 x 128, orifice channel,
+    inflow / outflow / walls / GEO_NOTHING shell), D3Q27 cumulant fp64, A-B, 40 steps from rest -- the case the reference runs on
+    its CPU build.  Default kernels within 1e-12 of the CPU oracle, parity-arithmetic kernels bit-identical, at full size."""
+    import os
+
+    from engine_runner import run_case_engine
+
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, precision=O.F64, X=512, Y=128, Z=128)
+    dl = 0.41 / 126
+    dt = 1e-5 / 1.5e-5 * dl * dl
+    case = gc.Case("sim1_res4", d, O.Params(lbmViscosity=1e-5, inflow_vx=1.0 * dt / dl), lc.map_sim1_channel, 40, "uniform")
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=os.cpu_count() or 8)
+    df, mac, _ = run_case_engine(case)
+    assert np.isfinite(df).all()
+    assert lc.rel_err_df(df, df_ref, d) <= 1e-12
+    for lo, hi, label in lc.macro_groups(d):
+        assert lc.rel_err(mac[lo:hi], mac_ref[lo:hi]) <= 1e-12, label
+    del df, mac
+    df, mac, _ = run_case_engine(case, flags=B.FLAG_STRICT_ARITH)
+    assert np.array_equal(df, df_ref) and np.array_equal(mac, mac_ref), "parity-arithmetic kernels differ from the CPU oracle at full size"
