@@ -27,7 +27,7 @@ def test_clients_compile_against_the_host_mirror():
 
     built = build_examples.build()
     names = {os.path.basename(b) for b in built}
-    assert "channel3d" in names
+    assert "channel3d" in names and "abi_minimal" in names  # the latter is compiled as C99 with -pedantic -Werror
     if HAVE_REF:
         assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim_2_ab", "ref_sim_2_aa", "ref_sim_3_ab", "ref_sim_3_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa"} <= names
 
@@ -450,3 +450,14 @@ int main(int argc, char** argv)
                 ref[int(p1[0] + i), int(p1[2] + k), int(p1[1] + j)] = 4
     assert np.array_equal(got, ref), f"{(got != ref).sum()} cells differ; painted counts {[(int(t), int((got == t).sum())) for t in range(5)]}"
     assert all((got == t).sum() > 0 for t in (1, 2, 3, 4))
+
+
+@pytest.mark.gpu
+def test_plain_c_client_of_the_abi():
+    """examples/abi_minimal.c: include/lbmx.h used from C99 -- create, upload, step, download; mass and momentum budget on the host."""
+    exe = os.path.join(BIN, "abi_minimal")
+    if not os.path.exists(exe):
+        pytest.skip("examples/bin/abi_minimal not built")
+    r = subprocess.run([exe, "48", "101"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "nan=0" in r.stdout and "48^3 cells, 101 steps" in r.stdout

@@ -1,6 +1,7 @@
 """Build the C++ clients of the host mirror (tnl_lbm_b200/host) against liblbmx.so into examples/bin/ (git-ignored; the
 binaries travel with the working tree to the GPU box):
 
+  * examples/abi_minimal.c                     -- the C ABI from plain C99
   * examples/channel3d.cpp                     -- this repository's own solver in the reference's style (A-B and A-A builds)
   * /root/reference/sim_NSE/sim_1.cu,          -- the reference's UNMODIFIED solver sources, when the reference tree is present;
     /root/reference/sim_NSE/sim_2.cu, sim_3.cu,   their third-party includes (argparse, fmt, spdlog, magic_enum) are satisfied by the
@@ -29,6 +30,14 @@ def build(reference: str = "/root/reference") -> list[str]:
         if os.path.exists(src):
             for pat in ("AB", "AA"):
                 jobs.append((f"{name}_{pat.lower()}", ["-x", "c++", src], shims + [f"-D{pat}_PATTERN"]))
+    # plain C (C99, -pedantic): the header is a C header, and this is the call sequence a binding in any language reproduces
+    c_out = os.path.join(BIN, "abi_minimal")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT}/include", os.path.join(ROOT, "examples", "abi_minimal.c"), "-o", c_out] + LINK + ["-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"building abi_minimal failed:\n{r.stderr}")
+    built.append(c_out)
     for name, src, extra in jobs:
         out = os.path.join(BIN, name)
         cmd = BASE + extra + src + ["-o", out] + LINK
