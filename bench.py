@@ -323,7 +323,7 @@ def main():
         # duration is the event time per step; per launch it processes cells_local updates of 432 algorithmic bytes each
         achieved = cells_local * B_PER_UPDATE / (ms_max * 1e-3 / a.steps) / 1e9
         # DRAM bytes per launch from the committed ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of k_bulk), which was
-        # taken at 256^3; per lattice update it is size-independent, so it is scaled by this run's cells per launch
+        # taken at this workload's size (512^3 per launch); for other sizes it is scaled by the cells per launch
         traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
