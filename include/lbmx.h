@@ -72,7 +72,9 @@ enum lbmx_macro { LBMX_MACRO_VOID = 0, LBMX_MACRO_DEFAULT = 1, LBMX_MACRO_MEAN =
 enum lbmx_inflow {
 	LBMX_INFLOW_NONE = 0,	  /* NSE_Data_NoInflow      lbm_data.h:117-131 */
 	LBMX_INFLOW_CONST = 1,	  /* NSE_Data_ConstInflow   lbm_data.h:98-115, NSE2D_Data_ConstInflow sim_2D/sim2d_1.cu:20-35 */
-	LBMX_INFLOW_PROFILE_YZ = 2 /* NSE_Data_XProfileInflow sim_NSE/sim_2.cu:16-33 */
+	LBMX_INFLOW_PROFILE_YZ = 2, /* NSE_Data_XProfileInflow sim_NSE/sim_2.cu:16-33 */
+	LBMX_INFLOW_PARABOLIC_Y = 3 /* NSE2D_Data_ParabolicInflow sim_2D/sim2d_3.cu:36-55 (D2Q9): vx = u_max * 4 s (1 - s), s = clamp((y - y0) * inv_den, 0, 1);
+								  lbmx_params carries u_max in inflow_vx, y0 in inflow_vy and inv_den in inflow_vz */
 };
 enum lbmx_precision { LBMX_F32 = 0 /* TraitsSP */, LBMX_F64 = 1 /* TraitsDP */ }; /* defs.h:118-119 */
 

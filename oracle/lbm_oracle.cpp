@@ -892,6 +892,16 @@ void inflow(const Block<R>& B, Cell<R, Q>& K, idx, idx y, idx z)
 			K.vy = 0;
 			K.vz = 0;
 			break;
+		case ORC_INFLOW_PARABOLIC_Y: {	// sim_2D/sim2d_3.cu:46-53: the double literals make the profile a double expression
+			R s = (R) (y - (idx) B.in_vy) * B.in_vz;  // in_vy carries y0, in_vz carries 1 / (y1 - y0)
+			if (s < 0)
+				s = 0;
+			else if (s > 1)
+				s = 1;
+			K.vx = (R) ((double) B.in_vx * (4.0 * (double) s * (1.0 - (double) s)));
+			K.vy = 0;
+			break;
+		}
 		default:
 			K.rho = 1;
 			K.vx = 0;

@@ -24,7 +24,7 @@ KBC_N1, KBC_N2, KBC_N3, KBC_N4, KBC_C1, KBC_C2, KBC_C3, KBC_C4 = range(13, 21)
 EQ_STD, EQ_INV_CUM, EQ_WELL, EQ_ENTROPIC = 0, 1, 2, 3
 AB, AA = 0, 1
 MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN = 0, 1, 2
-INFLOW_NONE, INFLOW_CONST, INFLOW_PROFILE_YZ = 0, 1, 2
+INFLOW_NONE, INFLOW_CONST, INFLOW_PROFILE_YZ, INFLOW_PARABOLIC_Y = 0, 1, 2, 3
 F32, F64 = 0, 1
 
 Q_OF = {D3Q27: 27, D2Q9: 9, D3Q19: 19}

@@ -49,7 +49,8 @@ enum {
 enum { ORC_EQ_STD = 0, ORC_EQ_INV_CUM = 1, ORC_EQ_WELL = 2, ORC_EQ_ENTROPIC = 3 };
 enum { ORC_STREAM_AB = 0, ORC_STREAM_AA = 1 };
 enum { ORC_MACRO_VOID = 0, ORC_MACRO_DEFAULT = 1, ORC_MACRO_MEAN = 2 };
-enum { ORC_INFLOW_NONE = 0, ORC_INFLOW_CONST = 1, ORC_INFLOW_PROFILE_YZ = 2 };
+enum { ORC_INFLOW_NONE = 0, ORC_INFLOW_CONST = 1, ORC_INFLOW_PROFILE_YZ = 2,
+	   ORC_INFLOW_PARABOLIC_Y = 3 /* sim_2D/sim2d_3.cu:36-55; inflow_vx = u_max_lbm, inflow_vy = y0, inflow_vz = inv_den */ };
 enum { ORC_F32 = 0, ORC_F64 = 1 };
 
 typedef struct oracle_desc

@@ -104,6 +104,37 @@ template <typename T>
 inline void ref_bind_inflow(Ref_Data2D_NoInflow<T>&, const oracle_params*)
 {}
 
+// sim_2D/sim2d_3.cu:36-55 (and sim2d_2.cu:108-133): Poiseuille profile over y computed per cell
+template <typename TRAITS>
+struct Ref_Data2D_ParabolicInflow : NSE_Data<TRAITS>
+{
+	using idx = typename TRAITS::idx;
+	using dreal = typename TRAITS::dreal;
+	dreal u_max_lbm = 0;
+	idx y0 = 1;
+	idx y1 = 1;
+	dreal inv_den = 1;
+	template <typename LBM_KS>
+	void inflow(LBM_KS& KS, idx, idx y, idx)
+	{
+		dreal s = (dreal) (y - y0) * inv_den;
+		if (s < 0)
+			s = 0;
+		else if (s > 1)
+			s = 1;
+		KS.vx = u_max_lbm * (4.0 * s * (1.0 - s));
+		KS.vy = 0;
+	}
+};
+template <typename T>
+inline void ref_bind_inflow(Ref_Data2D_ParabolicInflow<T>& SD, const oracle_params* p)
+{
+	using dreal = typename T::dreal;
+	SD.u_max_lbm = (dreal) p->inflow_vx;
+	SD.y0 = (typename T::idx) p->inflow_vy;
+	SD.inv_den = (dreal) p->inflow_vz;
+}
+
 template <typename NSE>
 inline typename NSE::DATA ref_make_data(const oracle_desc* d, const oracle_params* p)
 {

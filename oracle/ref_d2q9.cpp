@@ -40,6 +40,8 @@ int ref_dispatch2_t(const RefCall& c)
 		return ref_invoke<RefCfg2<TRAITS, COLLT, Ref_Data2D_ConstInflow<TRAITS>, D2Q9_MACRO_Mean<TRAITS>>>(c);
 	if (m == ORC_MACRO_DEFAULT && f == ORC_INFLOW_NONE)
 		return ref_invoke<RefCfg2<TRAITS, COLLT, Ref_Data2D_NoInflow<TRAITS>, D2Q9_MACRO_Default<TRAITS>>>(c);
+	if (m == ORC_MACRO_DEFAULT && f == ORC_INFLOW_PARABOLIC_Y)
+		return ref_invoke<RefCfg2<TRAITS, COLLT, Ref_Data2D_ParabolicInflow<TRAITS>, D2Q9_MACRO_Default<TRAITS>>>(c);
 	return -1;
 }
 

@@ -87,6 +87,10 @@ CASES = [
     Case("kbcc3_f32_aa_zoo", O.Desc(coll=O.KBC_C3, eq=O.EQ_ENTROPIC, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("kbcc4_f64_aa_zoo", O.Desc(coll=O.KBC_C4, eq=O.EQ_ENTROPIC, streaming=O.AA, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("kbcn4_f64_aa_box", O.Desc(coll=O.KBC_N4, eq=O.EQ_ENTROPIC, streaming=O.AA, X=12, Y=12, Z=12), O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 40, "smooth"),
+    Case("d2q9_clbm_f64_ab_parabolic", O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, inflow=O.INFLOW_PARABOLIC_Y, X=40, Y=16, Z=1),
+         O.Params(lbmViscosity=0.01, inflow_vx=0.05, inflow_vy=1.0, inflow_vz=1.0 / 13), lc.map_sim2d1_channel, 40, "uniform"),
+    Case("d2q9_srt_f32_ab_parabolic_zoo", O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, inflow=O.INFLOW_PARABOLIC_Y, precision=O.F32, X=13, Y=11, Z=1),
+         _p2(inflow_vx=0.07, inflow_vy=1.0, inflow_vz=0.125), zoo, 4),
     Case("cum_f64_ab_void", O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, macro=O.MACRO_VOID, X=8, Y=7, Z=6), _p3(), lambda d: lc.map_random_ab(d, seed=3), 3),
 ]
 

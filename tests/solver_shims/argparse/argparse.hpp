@@ -68,7 +68,7 @@ public:
 	template <typename T> T get(const std::string& n) const
 	{
 		for (auto& a : args)
-			if (a.name == n) {
+			if (a.name == n || a.name == "-" + n || a.name == "--" + n) {  // like argparse: a name without its dashes finds the option
 				if constexpr (std::is_same<T, std::string>::value) return a.text;
 				else if constexpr (std::is_same<T, bool>::value) return a.text == "1" || a.text == "true";
 				else if constexpr (std::is_floating_point<T>::value) return (T) std::atof(a.text.c_str());

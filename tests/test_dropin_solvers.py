@@ -29,7 +29,7 @@ def test_clients_compile_against_the_host_mirror():
     names = {os.path.basename(b) for b in built}
     assert "channel3d" in names and "abi_minimal" in names  # the latter is compiled as C99 with -pedantic -Werror
     if HAVE_REF:
-        assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim_2_ab", "ref_sim_2_aa", "ref_sim_3_ab", "ref_sim_3_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa"} <= names
+        assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim_2_ab", "ref_sim_2_aa", "ref_sim_3_ab", "ref_sim_3_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa", "ref_sim2d_3_ab"} <= names
 
 
 def test_custom_device_traits_are_rejected_at_compile_time():
@@ -461,3 +461,68 @@ def test_plain_c_client_of_the_abi():
     r = subprocess.run([exe, "48", "101"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "nan=0" in r.stdout and "48^3 cells, 101 steps" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_sim2d_3_with_geometry_file_matches_the_oracle():
+    """sim_2D/sim2d_3.cu, unmodified: D2Q9_CLBM with a solver-defined parabolic inflow (NSE2D_Data_ParabolicInflow), a geometry file with
+    per-cell types and Bouzidi thetas, and one number as output -- the kinetic energy integrated over the third quarter of the channel.
+    The geometry (a cylinder) is synthesised here; the same run is repeated on the CPU oracle and must give the same number."""
+    exe = os.path.join(BIN, "ref_sim2d_3_ab")
+    if not os.path.exists(exe):
+        pytest.skip("ref_sim2d_3_ab not built (needs /root/reference at build time)")
+    X, Y = 128, 32
+    cx, cy, rad = 40.3, 15.6, 4.2
+    xs, ys = np.meshgrid(np.arange(X), np.arange(Y), indexing="ij")
+    solid = (xs - cx) ** 2 + (ys - cy) ** 2 <= rad ** 2
+    links = [(1, 0), (0, 1), (-1, 0), (0, -1), (1, 1), (-1, 1), (-1, -1), (1, -1)]  # E N W S NE NW SW SE (lbm_data.h:69-83)
+    theta = np.full((8, X, Y), -1.0)
+    for k, (dx, dy) in enumerate(links):
+        for x in range(1, X - 1):
+            for y in range(1, Y - 1):
+                if solid[x, y] or not solid[x + dx, y + dy]:
+                    continue
+                # first crossing of the link p + t (dx, dy), t in (0, 1], with the circle
+                a, b, c = dx * dx + dy * dy, 2 * ((x - cx) * dx + (y - cy) * dy), (x - cx) ** 2 + (y - cy) ** 2 - rad ** 2
+                t = (-b - np.sqrt(b * b - 4 * a * c)) / (2 * a)
+                theta[k, x, y] = min(max(t, 1e-3), 1.0)
+    near = (theta > 0).any(axis=0)
+    ctype = np.where(solid, 2, np.where(near, 1, 0))
+    with tempfile.TemporaryDirectory() as tmp:
+        geo = os.path.join(tmp, "cyl.txt")
+        with open(geo, "w") as f:
+            for x in range(X):
+                for y in range(Y):
+                    f.write(f"{x} {y} {ctype[x, y]} " + " ".join(repr(float(theta[k, x, y])) for k in range(8)) + "\n")
+        r = subprocess.run([exe, "1", geo], capture_output=True, text=True, timeout=600, cwd=tmp)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        value = float(open(os.path.join(tmp, "sim_2D", "values", "value_cyl.txt")).read())
+    assert "physFinalTime reached" in r.stdout
+    # the same run on the CPU oracle, set up the way the solver sets it up (sim2d_3.cu:82-99, 268-318)
+    g = lc.G2
+    d = O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, inflow=O.INFLOW_PARABOLIC_Y, X=X, Y=Y, Z=1)
+    m = d.new_map(g["FLUID"])
+    m[:, 0, :] = np.where(ctype == 2, g["WALL"], np.where(ctype == 1, 12, g["FLUID"]))  # 12 = GEO_FLUID_NEAR_WALL
+    m[0], m[X - 1] = g["INFLOW"], g["OUTFLOW_RIGHT"]
+    m[:, :, 1] = m[:, :, Y - 2] = g["WALL"]
+    m[:, :, 0] = m[:, :, Y - 1] = g["NOTHING"]
+    dl = 0.50 / (Y - 2)
+    dt = 1.0e-3 / 1.0e-3 * dl * dl
+    nu = dt / dl / dl * 1.0e-3  # Lattice::phys2lbmViscosity
+    steps = 0
+    while dt * steps <= 4.0:  # core.h: quit once physTime() > physFinalTime
+        steps += 1
+    p = O.Params(lbmViscosity=nu, inflow_vx=1.5 * dt / dl, inflow_vy=1.0, inflow_vz=1.0 / 29.0, bouzidi=np.ascontiguousarray(theta[:, :, None, :]))
+    orc = O.Oracle(d, "port")
+    a = d.new_df()
+    orc.set_equilibrium(a, 1.0, 0.0, 0.0, 0.0)
+    b = a.copy()
+    mac = d.new_macro()
+    orc.step(p, a, b, mac, m, 0, steps, os.cpu_count() or 4)
+    fluid = (m[:, 0, :] == g["FLUID"]) | (m[:, 0, :] == 12)
+    roi = np.zeros((X, Y), dtype=bool)
+    roi[64:96, 1:Y - 1] = True
+    ux, uy = mac[1][:, 0, :] / dt * dl, mac[2][:, 0, :] / dt * dl
+    expect = float((0.5 * (ux * ux + uy * uy))[roi & fluid].sum() * dl * dl)
+    assert value > 0 and abs(value - expect) <= 1e-9 * expect, (value, expect)
+    print(f"sim2d_3 kinetic-energy integral: solver {value:.12e}, oracle {expect:.12e}, {steps} steps")

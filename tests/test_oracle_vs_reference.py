@@ -128,3 +128,15 @@ def test_d2q9_bouzidi_near_wall(coll, prec):
     p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.05, inflow_vy=-0.01, bouzidi=bz)
     ref, port = run_pair(d, m, p, nsteps=3, seed=5)
     assert_same(ref, port, f"bouzidi coll={coll} prec={prec}")
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+def test_d2q9_parabolic_inflow(streaming, prec):
+    """NSE2D_Data_ParabolicInflow (sim_2D/sim2d_3.cu:36-55): Poiseuille profile over y evaluated per inflow cell, with the double
+    literals of the reference."""
+    d = O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=streaming, inflow=O.INFLOW_PARABOLIC_Y, precision=prec, X=13, Y=11, Z=1)
+    m = lc.map_random_ab(d) if streaming == O.AB else lc.map_random_aa(d)
+    p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.07, inflow_vy=1.0, inflow_vz=1.0 / (d.Y - 3))
+    ref, port = run_pair(d, m, p, nsteps=4)
+    assert_same(ref, port, f"2d parabolic st={streaming} prec={prec}")

@@ -21,7 +21,7 @@ KBC_N1, KBC_N2, KBC_N3, KBC_N4, KBC_C1, KBC_C2, KBC_C3, KBC_C4 = range(13, 21)
 EQ_STD, EQ_INV_CUM, EQ_ENTROPIC = 0, 1, 3
 AB, AA = 0, 1
 MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN = 0, 1, 2
-INFLOW_NONE, INFLOW_CONST, INFLOW_PROFILE_YZ = 0, 1, 2
+INFLOW_NONE, INFLOW_CONST, INFLOW_PROFILE_YZ, INFLOW_PARABOLIC_Y = 0, 1, 2, 3
 F32, F64 = 0, 1
 MACRO_EVERY_STEP, MACRO_LAST_STEP, MACRO_NEVER = 0, 1, 2
 FLAG_STRICT_ARITH = 1

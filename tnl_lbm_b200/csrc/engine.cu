@@ -801,8 +801,10 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 		return fail(LBMX_ERR_ARG, "lbmx_create: precision");
 	if (d.streaming != LBMX_STREAM_AB && d.streaming != LBMX_STREAM_AA)
 		return fail(LBMX_ERR_ARG, "lbmx_create: streaming");
-	if (d.macro < LBMX_MACRO_VOID || d.macro > LBMX_MACRO_MEAN || d.inflow < LBMX_INFLOW_NONE || d.inflow > LBMX_INFLOW_PROFILE_YZ)
+	if (d.macro < LBMX_MACRO_VOID || d.macro > LBMX_MACRO_MEAN || d.inflow < LBMX_INFLOW_NONE || d.inflow > LBMX_INFLOW_PARABOLIC_Y)
 		return fail(LBMX_ERR_ARG, "lbmx_create: macro / inflow selector");
+	if (d.inflow == LBMX_INFLOW_PARABOLIC_Y && d.lattice != LBMX_D2Q9)
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: LBMX_INFLOW_PARABOLIC_Y is the 2-D inflow of sim_2D/sim2d_3.cu (D2Q9)");
 	if (d.eq != LBMX_EQ_STD && d.eq != LBMX_EQ_INV_CUM && d.eq != LBMX_EQ_ENTROPIC)
 		return fail(LBMX_ERR_ARG, "lbmx_create: eq selector");
 	if (d.eq == LBMX_EQ_ENTROPIC && ! (d.lattice == LBMX_D3Q27 && d.coll >= LBMX_COLL_KBC_N1 && d.coll <= LBMX_COLL_KBC_C4))

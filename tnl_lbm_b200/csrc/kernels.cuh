@@ -491,6 +491,12 @@ __global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
 			vy = R(0);
 			vz = R(0);
 		}
+		else if (p.inflow == 3) {  // Poiseuille profile over y (sim_2D/sim2d_3.cu:46-53); in_vy carries y0, in_vz carries 1 / (y1 - y0)
+			R s = R(y - (int) p.in_vy) * p.in_vz;
+			s = s < R(0) ? R(0) : (s > R(1) ? R(1) : s);
+			vx = R(double(p.in_vx) * (4.0 * double(s) * (1.0 - double(s))));  // the reference's double literals: evaluated in double
+			vy = R(0);
+		}
 		else {
 			rho = R(1);
 			vx = vy = vz = R(0);

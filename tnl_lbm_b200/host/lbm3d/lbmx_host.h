@@ -11,6 +11,7 @@
 //
 // Device-side user code cannot cross a C ABI.  The finite set the reference's own solvers use is recognised structurally:
 //   DATA with member `vx_profile`           -> LBMX_INFLOW_PROFILE_YZ   (NSE_Data_XProfileInflow, sim_NSE/sim_2.cu:16-33)
+//   DATA with members `u_max_lbm, y0, inv_den` -> LBMX_INFLOW_PARABOLIC_Y (NSE2D_Data_ParabolicInflow, sim_2D/sim2d_3.cu:36-55)
 //   DATA with member `inflow_vx`            -> LBMX_INFLOW_CONST        (NSE_Data_ConstInflow lbm_data.h:98-115, NSE2D_Data_ConstInflow)
 //   otherwise                               -> LBMX_INFLOW_NONE         (NSE_Data_NoInflow lbm_data.h:117-131)
 // Custom MACRO / COLL / BC classes are rejected at compile time (they lack the lbmx_* tag constants).
@@ -346,6 +347,10 @@ struct has_vx_profile : std::false_type {};
 template <typename T>
 struct has_vx_profile<T, std::void_t<decltype(std::declval<T&>().vx_profile)>> : std::true_type {};
 template <typename T, typename = void>
+struct has_u_max_lbm : std::false_type {};
+template <typename T>
+struct has_u_max_lbm<T, std::void_t<decltype(std::declval<T&>().u_max_lbm), decltype(std::declval<T&>().inv_den), decltype(std::declval<T&>().y0)>> : std::true_type {};
+template <typename T, typename = void>
 struct has_inflow_vx : std::false_type {};
 template <typename T>
 struct has_inflow_vx<T, std::void_t<decltype(std::declval<T&>().inflow_vx)>> : std::true_type {};
@@ -623,7 +628,9 @@ struct LBM_CONFIG
 	static constexpr int lbmx_macro = MACRO::lbmx_macro;
 	static constexpr int lbmx_precision = TRAITS::lbmx_precision;
 	static constexpr int lbmx_inflow =
-		lbmx_host::has_vx_profile<DATA>::value ? LBMX_INFLOW_PROFILE_YZ : (lbmx_host::has_inflow_vx<DATA>::value ? LBMX_INFLOW_CONST : LBMX_INFLOW_NONE);
+		lbmx_host::has_vx_profile<DATA>::value
+			? LBMX_INFLOW_PROFILE_YZ
+			: (lbmx_host::has_u_max_lbm<DATA>::value ? LBMX_INFLOW_PARABOLIC_Y : (lbmx_host::has_inflow_vx<DATA>::value ? LBMX_INFLOW_CONST : LBMX_INFLOW_NONE));
 	static_assert(std::is_base_of<NSE_Data<TRAITS>, DATA>::value, "DATA must derive from NSE_Data<TRAITS> (lbm_data.h:87-96)");
 };
 
@@ -1225,6 +1232,11 @@ struct LBM_BLOCK
 		p.fx = data.fx;
 		p.fy = data.fy;
 		p.fz = data.fz;
+		if constexpr (lbmx_host::has_u_max_lbm<typename CONFIG::DATA>::value) {	 // NSE2D_Data_ParabolicInflow (sim_2D/sim2d_3.cu:36-55)
+			p.inflow_vx = data.u_max_lbm;
+			p.inflow_vy = (double) data.y0;
+			p.inflow_vz = data.inv_den;
+		}
 		if constexpr (lbmx_host::has_inflow_vx<typename CONFIG::DATA>::value)
 			p.inflow_vx = data.inflow_vx;
 		if constexpr (lbmx_host::has_inflow_vy<typename CONFIG::DATA>::value)
