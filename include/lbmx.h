@@ -68,7 +68,14 @@ enum lbmx_eq {
 	LBMX_EQ_ENTROPIC = 3  /* D3Q27_EQ_ENTROPIC eq_entropic.h:11-211; initialisation and boundary cells of the KBC operators */
 };
 enum lbmx_streaming { LBMX_STREAM_AB = 0 /* streaming_AB.h */, LBMX_STREAM_AA = 1 /* streaming_AA.h */ };
-enum lbmx_macro { LBMX_MACRO_VOID = 0, LBMX_MACRO_DEFAULT = 1, LBMX_MACRO_MEAN = 2 }; /* d3q27/macro.h:50-188, d2q9/macro.h */
+enum lbmx_macro {
+	LBMX_MACRO_VOID = 0,
+	LBMX_MACRO_DEFAULT = 1,
+	LBMX_MACRO_MEAN = 2, /* d3q27/macro.h:50-188, d2q9/macro.h */
+	/* D2Q9 only, 10 channels: rho, vx, vy, sum vx, sum vy, frozen <vx>, frozen <vy>, sum |u'|, sum u'^2, sum v'^2
+	 * (D2Q9_MACRO_WithMean, sim_2D/sim2d_2.cu:53-104); the sums advance only while the gates in lbmx_params.macro_gates are set */
+	LBMX_MACRO_WITH_MEAN_2D = 3
+};
 enum lbmx_inflow {
 	LBMX_INFLOW_NONE = 0,	  /* NSE_Data_NoInflow      lbm_data.h:117-131 */
 	LBMX_INFLOW_CONST = 1,	  /* NSE_Data_ConstInflow   lbm_data.h:98-115, NSE2D_Data_ConstInflow sim_2D/sim2d_1.cu:20-35 */
@@ -118,8 +125,11 @@ typedef struct lbmx_params
 	double fx, fy, fz;
 	double inflow_vx, inflow_vy, inflow_vz;
 	int32_t stat_counter; /* MACRO_Mean sample index; lbmx_step(n>1) increments it per step */
-	int32_t reserved;
+	int32_t macro_gates;  /* LBMX_MACRO_WITH_MEAN_2D: LBMX_GATE_* bits = block.data.accumulate_means / accumulate_flucs
+							 (sim_2D/sim2d_2.cu:121-122); 0 otherwise */
 } lbmx_params;
+#define LBMX_GATE_MEANS 1
+#define LBMX_GATE_FLUCS 2
 
 typedef struct lbmx_layout
 {

@@ -93,6 +93,7 @@ struct Block
 	const R* profile;
 	idx profile_sy;
 	int stat_counter;
+	int macro_gates = 0;
 	int inflow_kind;
 	const R* bouzidi;  // [8][XYZ] or nullptr
 
@@ -1123,6 +1124,21 @@ void output_macro(const Block<R>& B, const Cell<R, Q>& K, const oracle_desc& d, 
 	M[0 * B.XYZ + c] = K.rho;
 	for (int a = 0; a < nd; a++)
 		M[(1 + a) * B.XYZ + c] = v[a];
+	if (d.macro == ORC_MACRO_WITH_MEAN_2D) {  // D2Q9_MACRO_WithMean::outputMacro, sim_2D/sim2d_2.cu:75-95
+		if (B.macro_gates & ORC_GATE_MEANS) {
+			M[3 * B.XYZ + c] += K.vx;
+			M[4 * B.XYZ + c] += K.vy;
+		}
+		if (B.macro_gates & ORC_GATE_FLUCS) {
+			const R dux = K.vx - M[5 * B.XYZ + c];
+			const R duy = K.vy - M[6 * B.XYZ + c];
+			const R mag = (R) std::sqrt(dux * dux + duy * duy);
+			M[7 * B.XYZ + c] += mag;
+			M[8 * B.XYZ + c] += dux * dux;
+			M[9 * B.XYZ + c] += duy * duy;
+		}
+		return;
+	}
 	if (d.macro != ORC_MACRO_MEAN)
 		return;
 	// running mean and Welford co-moments; component order: means, then xx,yy,zz,xy,xz,yz (3-D) / xx,yy,xy (2-D)
@@ -1194,6 +1210,7 @@ Block<R> make_block(const oracle_desc* d, const oracle_params* p)
 		B.profile = (const R*) p->vx_profile;
 		B.profile_sy = p->profile_size_y;
 		B.stat_counter = p->stat_counter;
+		B.macro_gates = p->macro_gates;
 		B.bouzidi = (const R*) p->bouzidi_coeff;
 	}
 	return B;
@@ -1272,6 +1289,8 @@ bool supported(const oracle_desc* d)
 	if (d->precision != ORC_F32 && d->precision != ORC_F64)
 		return false;
 	if (d->streaming != ORC_STREAM_AB && d->streaming != ORC_STREAM_AA)
+		return false;
+	if (d->macro < ORC_MACRO_VOID || d->macro > ORC_MACRO_WITH_MEAN_2D || (d->macro == ORC_MACRO_WITH_MEAN_2D && d->lattice != ORC_D2Q9))
 		return false;
 	if (d->lattice == ORC_D3Q27)
 		return ((d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE) || (d->coll >= ORC_COLL_CUM_2017 && d->coll <= ORC_COLL_KBC_C4))

@@ -23,7 +23,8 @@ CUM, SRT, BGK, MRT_LES, CLBM, SRT_MODIF_FORCE, SRT_WELL, BGK_WELL, CLBM_WELL, CU
 KBC_N1, KBC_N2, KBC_N3, KBC_N4, KBC_C1, KBC_C2, KBC_C3, KBC_C4 = range(13, 21)
 EQ_STD, EQ_INV_CUM, EQ_WELL, EQ_ENTROPIC = 0, 1, 2, 3
 AB, AA = 0, 1
-MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN = 0, 1, 2
+MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN, MACRO_WITH_MEAN_2D = 0, 1, 2, 3
+GATE_MEANS, GATE_FLUCS = 1, 2
 INFLOW_NONE, INFLOW_CONST, INFLOW_PROFILE_YZ, INFLOW_PARABOLIC_Y = 0, 1, 2, 3
 F32, F64 = 0, 1
 
@@ -35,7 +36,7 @@ def n_macro(lattice: int, macro: int) -> int:
     if macro == MACRO_VOID:
         return 0
     if lattice == D2Q9:
-        return 3 if macro == MACRO_DEFAULT else 8
+        return {MACRO_DEFAULT: 3, MACRO_MEAN: 8, MACRO_WITH_MEAN_2D: 10}[macro]
     return 4 if macro == MACRO_DEFAULT else 13
 
 
@@ -50,7 +51,7 @@ class _Params(C.Structure):
         ("vx_profile", C.c_void_p),
         ("profile_size_y", C.c_int64),
         ("stat_counter", C.c_int32),
-        ("pad_", C.c_int32),
+        ("macro_gates", C.c_int32),
         ("bouzidi_coeff", C.c_void_p),
     ]
 
@@ -111,6 +112,7 @@ class Params:
     inflow_vz: float = 0.0
     vx_profile: np.ndarray | None = None  # dreal[z, y]
     stat_counter: int = 0
+    macro_gates: int = 0
     bouzidi: np.ndarray | None = None  # dreal[8, x, z, y] (D2Q9 near-wall interpolation coefficients)
     _keep: list = field(default_factory=list, repr=False)
 
@@ -124,7 +126,7 @@ class Params:
         if self.bouzidi is not None:
             assert self.bouzidi.flags["C_CONTIGUOUS"] and self.bouzidi.shape[0] == 8
             bz = self.bouzidi.ctypes.data
-        return _Params(self.lbmViscosity, self.fx, self.fy, self.fz, self.inflow_vx, self.inflow_vy, self.inflow_vz, ptr, sy, self.stat_counter, 0, bz)
+        return _Params(self.lbmViscosity, self.fx, self.fy, self.fz, self.inflow_vx, self.inflow_vy, self.inflow_vz, ptr, sy, self.stat_counter, self.macro_gates, bz)
 
 
 def _path(kind: str, streaming: int, fast: bool) -> str:

@@ -48,7 +48,8 @@ enum {
 };
 enum { ORC_EQ_STD = 0, ORC_EQ_INV_CUM = 1, ORC_EQ_WELL = 2, ORC_EQ_ENTROPIC = 3 };
 enum { ORC_STREAM_AB = 0, ORC_STREAM_AA = 1 };
-enum { ORC_MACRO_VOID = 0, ORC_MACRO_DEFAULT = 1, ORC_MACRO_MEAN = 2 };
+enum { ORC_MACRO_VOID = 0, ORC_MACRO_DEFAULT = 1, ORC_MACRO_MEAN = 2, ORC_MACRO_WITH_MEAN_2D = 3 /* sim_2D/sim2d_2.cu:53-104, D2Q9 */ };
+enum { ORC_GATE_MEANS = 1, ORC_GATE_FLUCS = 2 }; /* block.data.accumulate_means / accumulate_flucs (sim2d_2.cu:121-122) */
 enum { ORC_INFLOW_NONE = 0, ORC_INFLOW_CONST = 1, ORC_INFLOW_PROFILE_YZ = 2,
 	   ORC_INFLOW_PARABOLIC_Y = 3 /* sim_2D/sim2d_3.cu:36-55; inflow_vx = u_max_lbm, inflow_vy = y0, inflow_vz = inv_den */ };
 enum { ORC_F32 = 0, ORC_F64 = 1 };
@@ -69,7 +70,7 @@ typedef struct oracle_params
 	const void* vx_profile; /* ORC_INFLOW_PROFILE_YZ: dreal[y + z*profile_size_y] (sim_NSE/sim_2.cu:16-33) */
 	int64_t profile_size_y;
 	int32_t stat_counter; /* MACRO_Mean sample index (d3q27/macro.h:117) */
-	int32_t pad_;
+	int32_t macro_gates; /* ORC_GATE_* bits, ORC_MACRO_WITH_MEAN_2D only */
 	const void* bouzidi_coeff; /* D2Q9 GEO_FLUID_NEAR_WALL: dreal[8][XYZ], direction order E,N,W,S,NE,NW,SW,SE, < 0 = link does not hit a wall
 								  (lbm_data.h:69-83); NULL = every coefficient reads -1 */
 } oracle_params;

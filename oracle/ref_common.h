@@ -114,6 +114,8 @@ struct Ref_Data2D_ParabolicInflow : NSE_Data<TRAITS>
 	idx y0 = 1;
 	idx y1 = 1;
 	dreal inv_den = 1;
+	bool accumulate_means = false;	// gates read by the solver's macro class (sim2d_2.cu:121-122)
+	bool accumulate_flucs = false;
 	template <typename LBM_KS>
 	void inflow(LBM_KS& KS, idx, idx y, idx)
 	{
@@ -133,6 +135,8 @@ inline void ref_bind_inflow(Ref_Data2D_ParabolicInflow<T>& SD, const oracle_para
 	SD.u_max_lbm = (dreal) p->inflow_vx;
 	SD.y0 = (typename T::idx) p->inflow_vy;
 	SD.inv_den = (dreal) p->inflow_vz;
+	SD.accumulate_means = (p->macro_gates & ORC_GATE_MEANS) != 0;
+	SD.accumulate_flucs = (p->macro_gates & ORC_GATE_FLUCS) != 0;
 }
 
 template <typename NSE>

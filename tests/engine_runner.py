@@ -39,7 +39,18 @@ def run_case_engine(case: gc.Case, chunk: int | None = None, **kw):
         set_params(e, case.params)
         e.macro_init()
         n = case.nsteps
-        if chunk:
+        if d.macro == O.MACRO_WITH_MEAN_2D:  # the two phases of gc.run_case, through the C ABI
+            half = n // 2
+            e.set_params(macro_gates=O.GATE_MEANS)
+            for k in ([1] * half if chunk == 1 else [half]):
+                e.step(k)
+            mac = e.macro_download()
+            gc.freeze_means(mac, half)
+            e.macro_upload(mac)
+            e.set_params(macro_gates=O.GATE_FLUCS)
+            for k in ([1] * (n - half) if chunk == 1 else [n - half]):
+                e.step(k)
+        elif chunk:
             done = 0
             while done < n:
                 k = min(chunk, n - done)

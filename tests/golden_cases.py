@@ -91,6 +91,11 @@ CASES = [
          O.Params(lbmViscosity=0.01, inflow_vx=0.05, inflow_vy=1.0, inflow_vz=1.0 / 13), lc.map_sim2d1_channel, 40, "uniform"),
     Case("d2q9_srt_f32_ab_parabolic_zoo", O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, inflow=O.INFLOW_PARABOLIC_Y, precision=O.F32, X=13, Y=11, Z=1),
          _p2(inflow_vx=0.07, inflow_vy=1.0, inflow_vz=0.125), zoo, 4),
+    # sim_2D/sim2d_2.cu's macro class: velocity sums for the first half, host freeze, fluctuation sums for the second (run_case below)
+    Case("d2q9_clbm_f64_ab_withmean", O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, macro=O.MACRO_WITH_MEAN_2D, inflow=O.INFLOW_PARABOLIC_Y, X=40, Y=16, Z=1),
+         O.Params(lbmViscosity=0.01, inflow_vx=0.05, inflow_vy=1.0, inflow_vz=1.0 / 13), lc.map_sim2d1_channel, 40, "uniform"),
+    Case("d2q9_srt_f32_aa_withmean_zoo", O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AA, macro=O.MACRO_WITH_MEAN_2D, inflow=O.INFLOW_PARABOLIC_Y, precision=O.F32, X=13, Y=11, Z=1),
+         _p2(inflow_vx=0.07, inflow_vy=1.0, inflow_vz=0.125), zoo, 6),
     Case("cum_f64_ab_void", O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, macro=O.MACRO_VOID, X=8, Y=7, Z=6), _p3(), lambda d: lc.map_random_ab(d, seed=3), 3),
 ]
 
@@ -129,6 +134,16 @@ def initial_df(case: Case, orc) -> np.ndarray:
     return df
 
 
+def freeze_means(mac: np.ndarray, samples: int) -> None:
+    """What the solver does on the host between the two phases (sim_2D/sim2d_2.cu:471-505): frozen mean = sum / samples on the interior
+    cells, fluctuation sums cleared; the array then goes back to the device."""
+    inner = (slice(1, -1), slice(None), slice(1, -1))
+    for sum_ch, mean_ch in ((3, 5), (4, 6)):
+        mac[mean_ch][inner] = mac[sum_ch][inner] / mac.dtype.type(samples)
+    for ch in (7, 8, 9):
+        mac[ch][inner] = 0
+
+
 def run_case(case: Case, kind: str, nthreads: int = 1):
     """Run a case on a CPU checker; returns (df holding the current state, macro)."""
     d, p = case.desc, case.params
@@ -144,6 +159,14 @@ def run_case(case: Case, kind: str, nthreads: int = 1):
         for it in range(case.nsteps):
             p.stat_counter = it
             orc.step(p, a, b, mac, m, it, 1, nthreads)
+    elif d.macro == O.MACRO_WITH_MEAN_2D:
+        half = case.nsteps // 2
+        p.macro_gates = O.GATE_MEANS
+        orc.step(p, a, b, mac, m, 0, half, nthreads)
+        freeze_means(mac, half)
+        p.macro_gates = O.GATE_FLUCS
+        orc.step(p, a, b, mac, m, half, case.nsteps - half, nthreads)
+        p.macro_gates = 0
     else:
         orc.step(p, a, b, mac, m, 0, case.nsteps, nthreads)
     cur = a if (d.streaming == O.AA or case.nsteps % 2 == 0) else b

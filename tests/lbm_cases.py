@@ -179,6 +179,8 @@ def macro_groups(d: O.Desc):
     groups = [(0, 1, "rho"), (1, 1 + nd, "velocity")]
     if d.macro == O.MACRO_MEAN:
         groups += [(1 + nd, 1 + 2 * nd, "mean velocity"), (1 + 2 * nd, d.n_macro, "co-moments")]
+    if d.macro == O.MACRO_WITH_MEAN_2D:
+        groups += [(3, 5, "velocity sums"), (5, 7, "frozen mean"), (7, 8, "sum |u'|"), (8, 10, "sums of squares")]
     return groups
 
 

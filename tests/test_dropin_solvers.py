@@ -14,6 +14,7 @@ import tempfile
 import numpy as np
 import pytest
 
+import golden_cases as gc
 import lbm_cases as lc
 from oracle import oracle as O
 
@@ -29,12 +30,13 @@ def test_clients_compile_against_the_host_mirror():
     names = {os.path.basename(b) for b in built}
     assert "channel3d" in names and "abi_minimal" in names  # the latter is compiled as C99 with -pedantic -Werror
     if HAVE_REF:
-        assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim_2_ab", "ref_sim_2_aa", "ref_sim_3_ab", "ref_sim_3_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa", "ref_sim2d_3_ab"} <= names
+        assert {"ref_sim_1_ab", "ref_sim_1_aa", "ref_sim_2_ab", "ref_sim_2_aa", "ref_sim_3_ab", "ref_sim_3_aa", "ref_sim2d_1_ab", "ref_sim2d_1_aa", "ref_sim2d_2_ab", "ref_sim2d_2_aa", "ref_sim2d_3_ab"} <= names
 
 
 def test_custom_device_traits_are_rejected_at_compile_time():
-    """A user-defined MACRO (device-side code in the reference, e.g. sim_2D/sim2d_2.cu:53-133) cannot cross the C ABI:
-    the mirror must refuse it when the solver is compiled, not at run time."""
+    """A user-defined MACRO is device-side code in the reference and cannot cross the C ABI: unless it is one the engine has built in
+    (D2Q9_MACRO_WithMean of sim_2D/sim2d_2.cu:53-104, recognised by its channel list), the mirror must refuse it when the solver is
+    compiled, not at run time."""
     src = r'''
 #include "lbm3d/core.h"
 template <typename TRAITS> struct MyMacro { enum { e_rho, N }; };
@@ -461,6 +463,148 @@ def test_plain_c_client_of_the_abi():
     r = subprocess.run([exe, "48", "101"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "nan=0" in r.stdout and "48^3 cells, 101 steps" in r.stdout
+
+
+def _cylinder_geometry(X, Y, cx, cy, rad):
+    """Per-cell types (0 fluid, 1 fluid next to the body, 2 solid) and the eight link fractions to a cylinder, in the file format of
+    sim_2D/sim2d_2.cu:214-330 / sim2d_3.cu: `x y type theta_E theta_N theta_W theta_S theta_NE theta_NW theta_SW theta_SE`."""
+    xs, ys = np.meshgrid(np.arange(X), np.arange(Y), indexing="ij")
+    solid = (xs - cx) ** 2 + (ys - cy) ** 2 <= rad ** 2
+    links = [(1, 0), (0, 1), (-1, 0), (0, -1), (1, 1), (-1, 1), (-1, -1), (1, -1)]  # lbm_data.h:69-83
+    theta = np.full((8, X, Y), -1.0)
+    for k, (dx, dy) in enumerate(links):
+        for x in range(1, X - 1):
+            for y in range(1, Y - 1):
+                if solid[x, y] or not solid[x + dx, y + dy]:
+                    continue
+                a, b, c = dx * dx + dy * dy, 2 * ((x - cx) * dx + (y - cy) * dy), (x - cx) ** 2 + (y - cy) ** 2 - rad ** 2
+                t = (-b - np.sqrt(b * b - 4 * a * c)) / (2 * a)
+                theta[k, x, y] = min(max(t, 1e-3), 1.0)
+    near = (theta > 0).any(axis=0)
+    return np.where(solid, 2, np.where(near, 1, 0)), theta
+
+
+def _write_geometry(path, ctype, theta):
+    X, Y = ctype.shape
+    with open(path, "w") as f:
+        for x in range(X):
+            for y in range(Y):
+                f.write(f"{x} {y} {ctype[x, y]} " + " ".join(repr(float(theta[k, x, y])) for k in range(8)) + "\n")
+
+
+def _sim2d_2_on_oracle(ctype, theta):
+    """sim_2D/sim2d_2.cu at resolution 1 on the CPU oracle, with the solver's host logic (sim2d_2.cu:391-436, 471-505, 741-801) restated
+    step by step; returns (TKE integral, [(tag, time, mean_samples, fluc_samples)], steps)."""
+    X, Y = ctype.shape
+    g = lc.G2
+    d = O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, macro=O.MACRO_WITH_MEAN_2D, inflow=O.INFLOW_PARABOLIC_Y, X=X, Y=Y, Z=1)
+    m = d.new_map(g["FLUID"])
+    m[:, 0, :] = np.where(ctype == 2, g["WALL"], np.where(ctype == 1, 12, g["FLUID"]))  # 12 = GEO_FLUID_NEAR_WALL
+    m[0], m[X - 1] = g["INFLOW"], g["OUTFLOW_RIGHT"]
+    m[:, :, 1] = m[:, :, Y - 2] = g["WALL"]
+    m[:, :, 0] = m[:, :, Y - 1] = g["NOTHING"]
+    dl = 0.50 / (Y - 2)
+    dt = 1.0e-3 / 1.0e-3 * dl * dl
+    vscale = dl / dt
+    p = O.Params(lbmViscosity=dt / dl / dl * 1.0e-3, inflow_vx=1.5 * dt / dl, inflow_vy=1.0, inflow_vz=1.0 / 29.0, bouzidi=np.ascontiguousarray(theta[:, :, None, :]))
+    orc = O.Oracle(d, "port")
+    a = d.new_df()
+    orc.set_equilibrium(a, 1.0, 0.0, 0.0, 0.0)
+    b = a.copy()
+    mac = d.new_macro()
+    orc.initial_macro(p, a, mac)
+    fluid = (m[:, 0, :] == g["FLUID"]) | (m[:, 0, :] == 12)
+    roi = np.zeros((X, Y), dtype=bool)
+    roi[64:96, 3:29] = True
+    roi &= fluid
+    ch = lambda k: mac[k][:, 0, :]  # noqa: E731
+    mean_samples = fluc_samples = 0
+    means_frozen = flucs_frozen = False
+    mean_freeze_time, next_mean_check, prev_mean, mean_hits = -1.0, 1.5 + 0.05, -1.0, 0
+    next_fluc_check, prev_fluc, fluc_hits = -1.0, -1.0, 0
+    expect, events, it = None, [], 0
+
+    def roi_mean_speed():
+        if mean_samples <= 0:
+            return 0.0
+        return float(np.sqrt((vscale * (ch(3) / mean_samples)) ** 2 + (vscale * (ch(4) / mean_samples)) ** 2)[roi].mean())
+
+    def roi_rms_fluc():
+        if fluc_samples <= 0:
+            return 0.0
+        return float(np.sqrt(max(0.0, (ch(8) / fluc_samples + ch(9) / fluc_samples)[roi].sum() / roi.sum() * vscale * vscale)))
+
+    def freeze():
+        gc.freeze_means(mac, mean_samples)
+        events.append(("mean_frozen", dt * it, mean_samples, fluc_samples))
+
+    while True:
+        t = dt * it
+        acc_means = (not means_frozen) and 1.5 <= t < 5.5
+        if acc_means:
+            mean_samples += 1
+        acc_flucs = False
+        if not means_frozen:
+            if t >= 1.5 + 1.0 and not t + 1e-12 < next_mean_check:
+                curr = roi_mean_speed()
+                mean_hits = 0 if prev_mean < 0 else (mean_hits + 1 if abs(curr - prev_mean) <= max(1e-3, 1e-3 * max(curr, 1e-6)) else 0)
+                prev_mean, next_mean_check = curr, next_mean_check + 0.05
+                if mean_hits >= 10:
+                    means_frozen, mean_freeze_time = True, t
+            if not means_frozen and t >= 5.5:
+                means_frozen, mean_freeze_time = True, 5.5
+            if means_frozen:
+                acc_means = False
+                freeze()
+                fluc_samples, flucs_frozen, prev_fluc, next_fluc_check = 0, False, -1.0, mean_freeze_time + 0.05
+        if means_frozen:
+            acc_flucs = (not flucs_frozen) and t >= mean_freeze_time + 1.0
+            if acc_flucs:
+                fluc_samples += 1
+            if not flucs_frozen and fluc_samples > 0 and not (t + 1e-12 < next_fluc_check or t < mean_freeze_time + 1.0):
+                curr = roi_rms_fluc()
+                fluc_hits = 0 if prev_fluc < 0 else (fluc_hits + 1 if abs(curr - prev_fluc) <= max(1e-3, 1e-3 * max(curr, 1e-6)) else 0)
+                prev_fluc, next_fluc_check = curr, next_fluc_check + 0.05
+                if fluc_hits >= 10:
+                    flucs_frozen, acc_flucs = True, False
+                    events.append(("fluc_frozen", t, mean_samples, fluc_samples))
+            if flucs_frozen:
+                events.append(("export", t, mean_samples, fluc_samples))
+                expect = float((0.5 * (ch(8) / fluc_samples + ch(9) / fluc_samples) * vscale * vscale)[roi].sum() * dl * dl)
+                break
+        p.macro_gates = (O.GATE_MEANS if acc_means else 0) | (O.GATE_FLUCS if acc_flucs else 0)
+        orc.step(p, a, b, mac, m, it, 1, 1)
+        it += 1
+        assert dt * it <= 10.0, "the restated solver logic never froze the fluctuation statistics"
+    return expect, events, it
+
+
+@pytest.mark.gpu
+def test_reference_sim2d_2_turbulence_statistics_match_the_oracle():
+    """sim_2D/sim2d_2.cu, unmodified: its solver-defined macro class (velocity sums, a mean the host freezes once it has settled, then
+    fluctuation sums about it), the per-step gates in block.data, the macro round trip through the host at the freeze, and the
+    turbulent kinetic energy of the wake integrated over a window as its one output.  Run in parity arithmetic (LBMX_STRICT_ARITH=1)
+    the device state is the oracle's bit for bit, so every threshold decision of the solver falls on the same step here and there."""
+    exe = os.path.join(BIN, "ref_sim2d_2_ab")
+    if not os.path.exists(exe):
+        pytest.skip("ref_sim2d_2_ab not built (needs /root/reference at build time)")
+    X, Y = 128, 32
+    ctype, theta = _cylinder_geometry(X, Y, 30.3, 15.2, 4.2)
+    with tempfile.TemporaryDirectory() as tmp:
+        geo = os.path.join(tmp, "cyl.txt")
+        _write_geometry(geo, ctype, theta)
+        r = subprocess.run([exe, "1", geo], capture_output=True, text=True, timeout=900, cwd=tmp, env=dict(os.environ, LBMX_STRICT_ARITH="1"))
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        value = float(open(os.path.join(tmp, "sim_2D", "values", "value_cyl.txt")).read())
+        stats = [line.strip().split(",") for line in open(os.path.join(tmp, "sim_2D", "stats", "stats_cyl.csv"))][1:]
+    assert "terminate flag triggered" in r.stdout
+    expect, events, it = _sim2d_2_on_oracle(ctype, theta)
+    # the solver's own log of its decisions: same tags, same times, same sample counts
+    assert [s[0] for s in stats] == [e[0] for e in events], (stats, events)
+    for s, e in zip(stats, events):
+        assert abs(float(s[1]) - e[1]) <= 1e-7 and int(s[6]) == e[2] and int(s[7]) == e[3], (s, e)  # the CSV holds %.9g; one step is 2.8e-4 s
+    assert expect > 0 and abs(value - expect) <= 1e-9 * expect, (value, expect)
+    print(f"sim2d_2 wake TKE integral: solver {value:.12e}, oracle {expect:.12e}; mean frozen at t={events[0][1]:.4f} s, exported at t={events[-1][1]:.4f} s ({it} steps)")
 
 
 @pytest.mark.gpu

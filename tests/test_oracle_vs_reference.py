@@ -84,6 +84,30 @@ def test_d3q27_cum_macro_and_inflow_flavours(macro, inflow, prec):
     assert_same(ref, port, f"macro={macro} inflow={inflow} prec={prec}")
 
 
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+@pytest.mark.parametrize("gates", [0, O.GATE_MEANS, O.GATE_FLUCS, O.GATE_MEANS | O.GATE_FLUCS])
+def test_d2q9_with_mean_macro(gates, streaming, prec):
+    """The solver-defined macro class of sim_2D/sim2d_2.cu:53-104 (gated velocity sums and fluctuation sums about a frozen mean),
+    restated on the reference's D2Q9_MACRO_Base in oracle/ref_d2q9.cpp and driven by the reference's own kernel."""
+    d = O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=streaming, macro=O.MACRO_WITH_MEAN_2D, inflow=O.INFLOW_PARABOLIC_Y, precision=prec, X=13, Y=11, Z=1)
+    m = lc.map_random_ab(d) if streaming == O.AB else lc.map_random_aa(d)
+    p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.07, inflow_vy=1.0, inflow_vz=0.125, macro_gates=gates)
+    out = []
+    for kind in ("reference", "port"):
+        orc = O.Oracle(d, kind)
+        a = lc.noisy_df(d, orc, seed=11)
+        b = a.copy()
+        mac = d.new_macro()
+        mac[5:7] = (0.01 * np.random.RandomState(3).standard_normal(mac[5:7].shape)).astype(d.dtype)  # a frozen mean to fluctuate about
+        orc.initial_macro(p, a, mac)
+        orc.step(p, a, b, mac, m, 0, 5, 1)
+        out.append((a, b, mac))
+    assert_same(out[0], out[1], f"with-mean gates={gates} st={streaming} prec={prec}")
+    mac = out[1][2]
+    assert (np.abs(mac[3:5]).max() > 0) == bool(gates & O.GATE_MEANS) and (mac[7:].max() > 0) == bool(gates & O.GATE_FLUCS)
+
+
 @pytest.mark.parametrize("macro", [O.MACRO_VOID, O.MACRO_MEAN])
 def test_d2q9_macro_flavours(macro):
     d = O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, macro=macro, X=10, Y=9, Z=1)

@@ -20,7 +20,8 @@ CUM_2017, CUM_ANTIALIAS, CUM_2017_ANTIALIAS = 10, 11, 12  # D3Q27_CUM built with
 KBC_N1, KBC_N2, KBC_N3, KBC_N4, KBC_C1, KBC_C2, KBC_C3, KBC_C4 = range(13, 21)
 EQ_STD, EQ_INV_CUM, EQ_ENTROPIC = 0, 1, 3
 AB, AA = 0, 1
-MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN = 0, 1, 2
+MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN, MACRO_WITH_MEAN_2D = 0, 1, 2, 3
+GATE_MEANS, GATE_FLUCS = 1, 2
 INFLOW_NONE, INFLOW_CONST, INFLOW_PROFILE_YZ, INFLOW_PARABOLIC_Y = 0, 1, 2, 3
 F32, F64 = 0, 1
 MACRO_EVERY_STEP, MACRO_LAST_STEP, MACRO_NEVER = 0, 1, 2
@@ -41,7 +42,7 @@ class Desc(C.Structure):
 
 
 class Params(C.Structure):
-    _fields_ = [(n, C.c_double) for n in ("lbmViscosity", "fx", "fy", "fz", "inflow_vx", "inflow_vy", "inflow_vz")] + [("stat_counter", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [(n, C.c_double) for n in ("lbmViscosity", "fx", "fy", "fz", "inflow_vx", "inflow_vy", "inflow_vz")] + [("stat_counter", C.c_int32), ("macro_gates", C.c_int32)]
 
 
 class Layout(C.Structure):

@@ -25,7 +25,7 @@ def build(reference: str = "/root/reference") -> list[str]:
     jobs = [("channel3d", [os.path.join(ROOT, "examples", "channel3d.cpp")], []),
             ("channel3d_aa", [os.path.join(ROOT, "examples", "channel3d.cpp")], ["-DAA_PATTERN"])]
     shims = [f"-I{ROOT}/tests/solver_shims"]
-    for name, rel in (("ref_sim_1", "sim_NSE/sim_1.cu"), ("ref_sim_2", "sim_NSE/sim_2.cu"), ("ref_sim_3", "sim_NSE/sim_3.cu"), ("ref_sim2d_1", "sim_2D/sim2d_1.cu"), ("ref_sim2d_3", "sim_2D/sim2d_3.cu")):
+    for name, rel in (("ref_sim_1", "sim_NSE/sim_1.cu"), ("ref_sim_2", "sim_NSE/sim_2.cu"), ("ref_sim_3", "sim_NSE/sim_3.cu"), ("ref_sim2d_1", "sim_2D/sim2d_1.cu"), ("ref_sim2d_2", "sim_2D/sim2d_2.cu"), ("ref_sim2d_3", "sim_2D/sim2d_3.cu")):
         src = os.path.join(reference, rel)
         if os.path.exists(src):
             for pat in ("AB", "AA"):

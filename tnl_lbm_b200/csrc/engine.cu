@@ -105,7 +105,7 @@ int n_macro_of(int lattice, int macro)
 	if (macro == LBMX_MACRO_VOID)
 		return 0;
 	if (lattice == LBMX_D2Q9)
-		return macro == LBMX_MACRO_DEFAULT ? 3 : 8;
+		return macro == LBMX_MACRO_DEFAULT ? 3 : (macro == LBMX_MACRO_MEAN ? 8 : 10);
 	return macro == LBMX_MACRO_DEFAULT ? 4 : 13;
 }
 
@@ -468,7 +468,7 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 	// Small single-slab lattices (steps of tens of microseconds): replay step pairs as a graph.  Pairs start at even iterations (A-A
 	// parity, A-B rotation); the last step of the batch stays a plain launch when it alone writes the macroscopic fields.
 	constexpr int64_t kGraphMaxCells = 16ll << 20, kGraphMinSteps = 8;
-	if (! ghosts && e->graphs_enabled && e->d.macro != LBMX_MACRO_MEAN && nsteps >= kGraphMinSteps && e->X * e->YZ <= kGraphMaxCells) {
+	if (! ghosts && e->graphs_enabled && e->d.macro != LBMX_MACRO_MEAN && e->d.macro != LBMX_MACRO_WITH_MEAN_2D && nsteps >= kGraphMinSteps && e->X * e->YZ <= kGraphMaxCells) {
 		const bool last_writes = e->d.macro == LBMX_MACRO_DEFAULT && e->d.macro_policy == LBMX_MACRO_LAST_STEP;
 		const int out_mode = (e->d.macro == LBMX_MACRO_DEFAULT && e->d.macro_policy == LBMX_MACRO_EVERY_STEP) ? OUT_DEFAULT : OUT_NONE;
 		const int64_t head = e->iter & 1, tail = last_writes ? 1 : 0;
@@ -511,6 +511,12 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 			p.out_mode = OUT_MEAN;
 		else if (e->d.macro == LBMX_MACRO_DEFAULT && (e->d.macro_policy == LBMX_MACRO_EVERY_STEP || (e->d.macro_policy == LBMX_MACRO_LAST_STEP && last)))
 			p.out_mode = OUT_DEFAULT;
+		else if (e->d.macro == LBMX_MACRO_WITH_MEAN_2D) {
+			// the sums advance every step while a gate is open; with both closed the instantaneous fields follow the policy
+			const int gates = e->prm.macro_gates & (LBMX_GATE_MEANS | LBMX_GATE_FLUCS);
+			if (e->d.macro_policy != LBMX_MACRO_NEVER && (gates || e->d.macro_policy == LBMX_MACRO_EVERY_STEP || last))
+				p.out_mode = OUT_WITH_MEAN_2D + gates;
+		}
 		p.stat_counter = e->prm.stat_counter + (int) s;
 		int rc;
 		if (! ghosts) {
@@ -801,8 +807,10 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 		return fail(LBMX_ERR_ARG, "lbmx_create: precision");
 	if (d.streaming != LBMX_STREAM_AB && d.streaming != LBMX_STREAM_AA)
 		return fail(LBMX_ERR_ARG, "lbmx_create: streaming");
-	if (d.macro < LBMX_MACRO_VOID || d.macro > LBMX_MACRO_MEAN || d.inflow < LBMX_INFLOW_NONE || d.inflow > LBMX_INFLOW_PARABOLIC_Y)
+	if (d.macro < LBMX_MACRO_VOID || d.macro > LBMX_MACRO_WITH_MEAN_2D || d.inflow < LBMX_INFLOW_NONE || d.inflow > LBMX_INFLOW_PARABOLIC_Y)
 		return fail(LBMX_ERR_ARG, "lbmx_create: macro / inflow selector");
+	if (d.macro == LBMX_MACRO_WITH_MEAN_2D && d.lattice != LBMX_D2Q9)
+		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: LBMX_MACRO_WITH_MEAN_2D is the macro class of sim_2D/sim2d_2.cu (D2Q9)");
 	if (d.inflow == LBMX_INFLOW_PARABOLIC_Y && d.lattice != LBMX_D2Q9)
 		return fail(LBMX_ERR_UNSUPPORTED, "lbmx_create: LBMX_INFLOW_PARABOLIC_Y is the 2-D inflow of sim_2D/sim2d_3.cu (D2Q9)");
 	if (d.eq != LBMX_EQ_STD && d.eq != LBMX_EQ_INV_CUM && d.eq != LBMX_EQ_ENTROPIC)
@@ -1326,6 +1334,13 @@ int lbmx_df_sync_ghosts(lbmx_engine* e)
 	return LBMX_OK;
 }
 
+static int init_out_mode(const lbmx_engine* e)
+{
+	if (e->d.macro == LBMX_MACRO_WITH_MEAN_2D)	// computeInitialMacro calls the same outputMacro, open gates included
+		return OUT_WITH_MEAN_2D + (e->prm.macro_gates & (LBMX_GATE_MEANS | LBMX_GATE_FLUCS));
+	return e->d.macro == LBMX_MACRO_MEAN ? OUT_MEAN : OUT_DEFAULT;
+}
+
 int lbmx_macro_init(lbmx_engine* e)
 {
 	if (! e)
@@ -1337,12 +1352,12 @@ int lbmx_macro_init(lbmx_engine* e)
 	const unsigned blocks = (unsigned) ((n + 127) / 128);
 	if (e->f64()) {
 		KParams<double> p = make_params<double>(e);
-		p.out_mode = e->d.macro == LBMX_MACRO_MEAN ? OUT_MEAN : OUT_DEFAULT;
+		p.out_mode = init_out_mode(e);
 		e->kd.initial_macro<<<blocks, 128, 0, e->s_main>>>(p);
 	}
 	else {
 		KParams<float> p = make_params<float>(e);
-		p.out_mode = e->d.macro == LBMX_MACRO_MEAN ? OUT_MEAN : OUT_DEFAULT;
+		p.out_mode = init_out_mode(e);
 		e->kf.initial_macro<<<blocks, 128, 0, e->s_main>>>(p);
 	}
 	e->stats.kernel_launches++;

@@ -41,7 +41,7 @@
 namespace lbmx {
 
 enum StreamMode : int { S_AB = 0, S_AA_EVEN = 1, S_AA_ODD = 2 };
-enum OutMode : int { OUT_NONE = 0, OUT_DEFAULT = 1, OUT_MEAN = 2 };
+enum OutMode : int { OUT_NONE = 0, OUT_DEFAULT = 1, OUT_MEAN = 2, OUT_WITH_MEAN_2D = 4 };  // OUT_WITH_MEAN_2D + LBMX_GATE_* bits (4..7)
 
 template <typename R>
 struct KParams
@@ -221,6 +221,23 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 #pragma unroll
 	for (int a = 0; a < nd; a++)
 		M[(1 + a) * S + c] = v[a];
+	if constexpr (nd == 2) {
+		// D2Q9_MACRO_WithMean (sim_2D/sim2d_2.cu:75-95): gated velocity sums, and fluctuation sums about a mean the host froze
+		if (p.out_mode >= OUT_WITH_MEAN_2D) {
+			if (p.out_mode & 1) {
+				M[3 * S + c] += vx;
+				M[4 * S + c] += vy;
+			}
+			if (p.out_mode & 2) {
+				const R dux = vx - M[5 * S + c];
+				const R duy = vy - M[6 * S + c];
+				M[7 * S + c] += sqrt(dux * dux + duy * duy);  // IEEE sqrt in R = the reference's sqrt(double) rounded to dreal
+				M[8 * S + c] += dux * dux;
+				M[9 * S + c] += duy * duy;
+			}
+			return;
+		}
+	}
 	if (p.out_mode != OUT_MEAN)
 		return;
 	// running mean + Welford co-moments, components: means then xx,yy,zz,xy,xz,yz (3-D) / xx,yy,xy (2-D)

@@ -351,6 +351,36 @@ struct has_u_max_lbm : std::false_type {};
 template <typename T>
 struct has_u_max_lbm<T, std::void_t<decltype(std::declval<T&>().u_max_lbm), decltype(std::declval<T&>().inv_den), decltype(std::declval<T&>().y0)>> : std::true_type {};
 template <typename T, typename = void>
+struct has_accumulate_gates : std::false_type {};
+template <typename T>
+struct has_accumulate_gates<T, std::void_t<decltype(std::declval<T&>().accumulate_means), decltype(std::declval<T&>().accumulate_flucs)>> : std::true_type {};
+// MACRO -> descriptor enum: the mirror's own classes carry a tag; a solver-defined class is recognised by its channel list where the engine
+// has that output built in (D2Q9_MACRO_WithMean, sim_2D/sim2d_2.cu:53-104); anything else is device code that cannot cross the C ABI
+template <typename M, typename = void>
+struct has_macro_tag : std::false_type {};
+template <typename M>
+struct has_macro_tag<M, std::void_t<decltype(M::lbmx_macro)>> : std::true_type {};
+template <typename M, typename = void>
+struct is_with_mean_2d : std::false_type {};
+template <typename M>
+struct is_with_mean_2d<M, std::void_t<decltype(M::e_svx), decltype(M::e_svy), decltype(M::e_mean_vx_frozen), decltype(M::e_mean_vy_frozen),
+										  decltype(M::e_smag_uprime), decltype(M::e_suprime2_sum), decltype(M::e_svprime2_sum)>>
+: std::integral_constant<bool, (int) M::e_rho == 0 && (int) M::e_vx == 1 && (int) M::e_vy == 2 && (int) M::e_svx == 3 && (int) M::e_svy == 4
+									   && (int) M::e_mean_vx_frozen == 5 && (int) M::e_mean_vy_frozen == 6 && (int) M::e_smag_uprime == 7
+									   && (int) M::e_suprime2_sum == 8 && (int) M::e_svprime2_sum == 9 && (int) M::N == 10>
+{};
+template <typename M, bool TAGGED = has_macro_tag<M>::value>
+struct macro_kind
+{
+	static constexpr int lbmx_macro = M::lbmx_macro;
+};
+template <typename M>
+struct macro_kind<M, false>
+{
+	static_assert(is_with_mean_2d<M>::value, "MACRO has no lbmx_macro tag: a solver-defined macro class is device code and cannot cross the C ABI");
+	static constexpr int lbmx_macro = LBMX_MACRO_WITH_MEAN_2D;
+};
+template <typename T, typename = void>
 struct has_inflow_vx : std::false_type {};
 template <typename T>
 struct has_inflow_vx<T, std::void_t<decltype(std::declval<T&>().inflow_vx)>> : std::true_type {};
@@ -556,6 +586,13 @@ struct D2Q9_MACRO_Mean
 	static constexpr int overlap_width = 1;
 	static constexpr int lbmx_macro = LBMX_MACRO_MEAN;
 };
+// base of solver-defined macro classes (d2q9/macro.h:5-46); the derived class supplies the channel enum and is recognised structurally
+template <typename TRAITS>
+struct D2Q9_MACRO_Base
+{
+	static const bool use_syncMacro = false;
+	static constexpr int overlap_width = 1;
+};
 template <typename TRAITS>
 struct D2Q9_MACRO_Void
 {
@@ -625,7 +662,7 @@ struct LBM_CONFIG
 	static constexpr int lbmx_coll = COLL::lbmx_coll;
 	static constexpr int lbmx_eq = EQ::lbmx_eq;
 	static constexpr int lbmx_streaming = STREAMING::lbmx_streaming;
-	static constexpr int lbmx_macro = MACRO::lbmx_macro;
+	static constexpr int lbmx_macro = lbmx_host::macro_kind<MACRO>::lbmx_macro;
 	static constexpr int lbmx_precision = TRAITS::lbmx_precision;
 	static constexpr int lbmx_inflow =
 		lbmx_host::has_vx_profile<DATA>::value
@@ -1038,6 +1075,9 @@ struct LBM_BLOCK
 		d.inflow = CONFIG::lbmx_inflow;
 		d.precision = CONFIG::lbmx_precision;
 		d.macro_policy = LBMX_MACRO_EVERY_STEP;	 // the drop-in keeps the reference's observable behaviour; solvers may relax it
+		if (const char* v = std::getenv("LBMX_STRICT_ARITH"))  // run an unmodified solver in the reference's own rounding (lbmx.h: LBMX_FLAG_STRICT_ARITH)
+			if (v[0] && v[0] != '0')
+				d.flags |= LBMX_FLAG_STRICT_ARITH;
 		d.X = global.x();
 		d.Y = global.y();
 		d.Z = global.z();
@@ -1244,6 +1284,8 @@ struct LBM_BLOCK
 		if constexpr (lbmx_host::has_inflow_vz<typename CONFIG::DATA>::value)
 			p.inflow_vz = data.inflow_vz;
 		p.stat_counter = data.stat_counter;
+		if constexpr (lbmx_host::has_accumulate_gates<typename CONFIG::DATA>::value)  // gates of D2Q9_MACRO_WithMean (sim_2D/sim2d_2.cu:121-122)
+			p.macro_gates = (data.accumulate_means ? LBMX_GATE_MEANS : 0) | (data.accumulate_flucs ? LBMX_GATE_FLUCS : 0);
 		lbmx_host::check(lbmx_set_params(engine, &p), "lbmx_set_params");
 		if constexpr (lbmx_host::has_vx_profile<typename CONFIG::DATA>::value) {
 			// NSE_Data_XProfileInflow (sim_NSE/sim_2.cu:16-33): the solver owns a host array dreal[y + z * size_y]; it is uploaded when the
