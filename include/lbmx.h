@@ -264,6 +264,11 @@ typedef struct lbmx_stats
 	int32_t bulk_block;
 	int32_t halo_peer_memory; /* 1: halos are stored straight into the neighbours' arrays over NVLink (CUDA IPC peer mappings, arrival counters);
 								 0: NCCL send/recv (multi-node, IPC unavailable, or LBMX_HALO=nccl in the environment) */
+	int64_t aa_cells_reaching_outside; /* A-A only, set by lbmx_map_upload: cells on a lattice face (y, z; x too on a slab without ghost planes)
+										  that are neither GEO_NOTHING nor wrapped.  The A-A index rule is unclamped (kernels.h:30-37), so their
+										  neighbours lie outside the lattice: undefined behaviour in the reference.  Here the arrays carry a zeroed
+										  guard band, so the accesses stay inside the engine's memory, but the values at those cells are as
+										  meaningless as there -- give A-A lattices a GEO_NOTHING (or periodic) skin, as sim_2.cu:125-138 does. */
 } lbmx_stats;
 int lbmx_get_stats(lbmx_engine* e, lbmx_stats* out);
 

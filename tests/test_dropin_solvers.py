@@ -204,6 +204,11 @@ def test_raw_dump_writers_keep_reference_ordering():
     assert np.array_equal(db["lbm_density"].reshape(Z // 4, Y // 4, X // 4), zyx(mac[0][sl(X), sl(Z), sl(Y)]).astype(np.float32))
     assert hx["global"] == [1, Y, Z] and np.array_equal(dx["velocityX"].reshape(Z, Y), mac[1][X // 2].astype(np.float32))
     assert hz["global"] == [X, Y, 1] and np.array_equal(dz["lbm_density"].reshape(Y, X), mac[0][:, Z // 2, :].T.astype(np.float32))
+    # 1-D cuts: text tables "#time", "#1:x  2:lbm_density  3:velocity[0] ..." (state.hpp:225-238), %e formatting
+    assert header[0].startswith("#time ") and header[1].split("\t") == ["#1:x", "2:lbm_density", "3:velocity[0]", "4:velocity[1]", "5:velocity[2]"]
+    assert line_x.shape == (X, 5) and line_z.shape == (Z, 5)
+    assert np.allclose(line_x[:, 1], mac[0][:, Z // 2, Y // 2], rtol=1e-6) and np.allclose(line_x[:, 2], mac[1][:, Z // 2, Y // 2], rtol=1e-6, atol=1e-12)
+    assert np.allclose(line_z[:, 1], mac[0][X // 2, :, Y // 2], rtol=1e-6) and np.allclose(line_z[:, 4], mac[3][X // 2, :, Y // 2], rtol=1e-6, atol=1e-12)
 
 
 def test_checkpoint_manager_round_trip_on_cpu():
@@ -353,11 +358,6 @@ def test_two_ranks_through_the_host_mirror_equal_one(exe_name):
         assert any("Loading data from checkpoint" in o for o in outs) and any(f"iterations={steps} " in o for o in outs), outs
         resumed = assemble(t3, "resumed")
         assert np.array_equal(resumed, two), f"max |resumed - two| = {np.abs(resumed - two).max():.3e}"
-    # 1-D cuts: text tables "#time", "#1:x  2:lbm_density  3:velocity[0] ..." (state.hpp:225-238), %e formatting
-    assert header[0].startswith("#time ") and header[1].split("\t") == ["#1:x", "2:lbm_density", "3:velocity[0]", "4:velocity[1]", "5:velocity[2]"]
-    assert line_x.shape == (X, 5) and line_z.shape == (Z, 5)
-    assert np.allclose(line_x[:, 1], mac[0][:, Z // 2, Y // 2], rtol=1e-6) and np.allclose(line_x[:, 2], mac[1][:, Z // 2, Y // 2], rtol=1e-6, atol=1e-12)
-    assert np.allclose(line_z[:, 1], mac[0][X // 2, :, Y // 2], rtol=1e-6) and np.allclose(line_z[:, 4], mac[3][X // 2, :, Y // 2], rtol=1e-6, atol=1e-12)
 
 
 @pytest.mark.gpu

@@ -83,6 +83,50 @@ def test_graph_replay_is_invisible(name, policy):
         assert stats.kernel_launches == one_stats.kernel_launches  # replayed launches are counted like plain ones
 
 
+def test_aa_cells_on_bare_faces_are_counted_and_stay_inside_the_engine():
+    """The A-A index rule is unclamped (kernels.h:30-37): a face cell that is neither GEO_NOTHING nor periodic, on a slab without ghost
+    planes, addresses x+-1 / y+-1 / z+-1 outside the lattice -- undefined in the reference.  lbmx_map_upload counts such cells, and
+    the guard band around the distribution arrays keeps their accesses off every other allocation: a second engine created around the
+    first one (its arrays are the neighbours in device memory) keeps its state to the bit."""
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AA, X=10, Y=9, Z=8)
+    bare = gc.Case("bare", d, O.Params(lbmViscosity=0.01, fx=1e-5), lambda dd: dd.new_map(lc.G3["FLUID"]), 6, "uniform")
+    witness_case = gc.BY_NAME["cum_f64_ab_box"]
+    wd = witness_case.desc
+    with engine_for(witness_case) as w1, engine_for(bare) as e, engine_for(witness_case) as w2:
+        for w in (w1, w2):
+            w.map_upload(lc.map_periodic(wd))
+            w.set_equilibrium_field(*lc.smooth_fields(wd))
+            w.macro_init()
+        before = [(w.df_download(0), w.df_download(1), w.macro_download(), w.map_download()) for w in (w1, w2)]
+        m = bare.make_map(d)
+        e.map_upload(m)
+        faces = np.ones(m.shape, dtype=bool)
+        faces[1:-1, 1:-1, 1:-1] = False
+        assert e.stats().aa_cells_reaching_outside == int(faces.sum())
+        e.set_equilibrium(1.0, 0.01, 0.0, 0.0)
+        set_params(e, bare.params)
+        e.step(6)
+        e.sync()
+        assert np.array_equal(e.map_download(), m)
+        after = [(w.df_download(0), w.df_download(1), w.macro_download(), w.map_download()) for w in (w1, w2)]
+        for b4, af in zip(before, after):
+            for x, y in zip(b4, af):
+                assert np.array_equal(x, y)
+        # a GEO_NOTHING skin with the walls one cell inside (what the reference's A-A solvers paint in y and z, sim_2.cu:125-138) leaves
+        # nothing to count; walls that touch a periodic x face of a slab without ghost planes are counted (SURVEY §8d cfg 4)
+        skin = d.new_map(lc.G3["NOTHING"])
+        skin[1:-1, 1:-1, 1:-1] = lc.G3["WALL"]
+        skin[2:-2, 2:-2, 2:-2] = lc.G3["FLUID"]
+        e.map_upload(skin)
+        assert e.stats().aa_cells_reaching_outside == 0
+        duct = d.new_map(lc.G3["PERIODIC"])
+        duct[:, 0, :] = duct[:, -1, :] = duct[:, :, 0] = duct[:, :, -1] = lc.G3["NOTHING"]
+        duct[:, 1, 1:-1] = duct[:, -2, 1:-1] = duct[:, 1:-1, 1] = duct[:, 1:-1, -2] = lc.G3["WALL"]
+        e.map_upload(duct)
+        ring = 2 * (d.Y - 2) + 2 * (d.Z - 2) - 4
+        assert e.stats().aa_cells_reaching_outside == 2 * ring
+
+
 def test_map_round_trip_is_bit_exact():
     case = gc.BY_NAME["cum_f64_ab_zoo"]
     m = case.make_map(case.desc)

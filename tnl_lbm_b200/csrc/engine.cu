@@ -138,22 +138,34 @@ struct IsBoundaryCell
 
 // per_plane[x] += boundary cells of plane x; per_plane[gridDim.y] += cells of type `reads_neighbour` (GEO_OUTFLOW_RIGHT: pulls the
 // populations of the cell at x-1, bc.h:63-65 -- under A-A that is an in-place array another cell updates in the same step)
-__global__ void k_count_boundary_cells(const int16_t* map, long long first_cell, int YZ, int periodic, int reads_neighbour, unsigned* per_plane)
+// per_plane[gridDim.y + 1] += (face_rule != 0) cells on a lattice face whose A-A neighbours lie outside the lattice: not GEO_NOTHING, not
+// wrapped, on a y/z face or (face_rule == 2: no ghost planes) an x face -- kernels.h:30-37 takes +-1 unclamped there
+__global__ void k_count_boundary_cells(const int16_t* map, long long first_cell, int YZ, int periodic, int reads_neighbour, unsigned* per_plane, int Y, int Z,
+									   int face_rule, int nothing)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	bool b = false, r = false;
+	bool b = false, r = false, o = false;
 	if (i < YZ) {
 		const int m = map[first_cell + (long long) blockIdx.y * YZ + i];
 		b = m != 0 && m != periodic;
 		r = m == reads_neighbour;
+		if (face_rule && m != nothing && m != periodic) {  // periodic cells wrap (y, z always; x unless there are ghost planes)
+			const int y = i % Y, z = i / Y;
+			const bool yz_face = y == 0 || y == Y - 1 || (Z > 1 && (z == 0 || z == Z - 1));
+			const bool x_face = face_rule == 2 && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1);
+			o = yz_face || x_face;
+		}
 	}
 	const unsigned n = __popc(__ballot_sync(0xffffffffu, b));
 	const unsigned nr = __popc(__ballot_sync(0xffffffffu, r));
+	const unsigned no = __popc(__ballot_sync(0xffffffffu, o));
 	if ((threadIdx.x & 31) == 0) {
 		if (n)
 			atomicAdd(per_plane + blockIdx.y, n);
 		if (nr)
 			atomicAdd(per_plane + gridDim.y, nr);
+		if (no)
+			atomicAdd(per_plane + gridDim.y + 1, no);
 	}
 }
 
@@ -172,6 +184,11 @@ struct lbmx_engine
 	bool self_exchange = false;
 
 	void* df[2] = {nullptr, nullptr};
+	// The allocations behind df[]: a guard band of one x-plane + one row + one cell (zeroed) on either side of the populations.  The
+	// A-A index rule takes x+-1, y+-1, z+-1 unclamped (kernels.h:30-37); at a face cell that is neither GEO_NOTHING nor periodic, on a
+	// slab without ghost planes, the reference steps outside its array.  Here such a map stays inside this engine's own memory.
+	void* df_alloc[2] = {nullptr, nullptr};
+	size_t df_guard = 0;  // bytes
 	void* macro = nullptr;
 	int16_t* map = nullptr;
 	uint32_t* blist = nullptr;
@@ -203,6 +220,7 @@ struct lbmx_engine
 	struct Peer
 	{
 		void* df[2] = {nullptr, nullptr};  // the neighbour's df[0], df[1] in this process' address space
+		void* df_base[2] = {nullptr, nullptr};	// what cudaIpcOpenMemHandle returned (the neighbour's allocation, guard band first)
 		long long* flags = nullptr;		   // the neighbour's arrival counters: [0] bumped by its left neighbour, [1] by its right one
 		int64_t X = 0, XYZ = 0;			   // the neighbour's slab
 		bool mapped = false;
@@ -894,9 +912,11 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 	CUX(cudaEventCreate(&e->ev_t1));
 	const size_t df_bytes = (size_t) e->Q * e->XYZ * e->rs;
 	const int ncopies = e->aa() ? 1 : 2;
+	e->df_guard = (((size_t) (e->YZ + e->Y + 1) * e->rs) + 511) / 512 * 512;
 	for (int i = 0; i < ncopies; i++) {
-		CUX(cudaMalloc(&e->df[i], df_bytes));
-		CUX(cudaMemsetAsync(e->df[i], 0, df_bytes, e->s_main));
+		CUX(cudaMalloc(&e->df_alloc[i], df_bytes + 2 * e->df_guard));
+		CUX(cudaMemsetAsync(e->df_alloc[i], 0, df_bytes + 2 * e->df_guard, e->s_main));
+		e->df[i] = (char*) e->df_alloc[i] + e->df_guard;
 	}
 	if (e->NM > 0) {
 		CUX(cudaMalloc(&e->macro, (size_t) e->NM * e->XYZ * e->rs));
@@ -937,7 +957,7 @@ int lbmx_destroy(lbmx_engine* e)
 		g_nccl.CommDestroy(e->comm);
 	if (e->my_flags)
 		cudaFree(e->my_flags);
-	for (void* p : {e->df[0], e->df[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs})
+	for (void* p : {e->df_alloc[0], e->df_alloc[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs})
 		if (p)
 			cudaFree(p);
 	if (e->pair_exec)
@@ -992,7 +1012,7 @@ static void release_peer_memory(lbmx_engine* e)
 			*peer = lbmx_engine::Peer{};
 			continue;
 		}
-		for (void* p : {peer->df[0], peer->df[1], (void*) peer->flags})
+		for (void* p : {peer->df_base[0], peer->df_base[1], (void*) peer->flags})
 			if (p)
 				cudaIpcCloseMemHandle(p);
 		*peer = lbmx_engine::Peer{};
@@ -1009,7 +1029,7 @@ static int setup_peer_memory(lbmx_engine* e)
 	{
 		cudaIpcMemHandle_t df[2];
 		cudaIpcMemHandle_t flags;
-		int64_t X, XYZ;
+		int64_t X, XYZ, guard;
 		int32_t ok, pad;
 	};
 	const char* mode = std::getenv("LBMX_HALO");
@@ -1018,13 +1038,14 @@ static int setup_peer_memory(lbmx_engine* e)
 	CU(cudaMemset(e->my_flags, 0, 3 * sizeof(long long)));
 	Packet mine{};
 	if (ok) {
-		ok = cudaIpcGetMemHandle(&mine.df[0], e->df[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, e->my_flags) == cudaSuccess;
+		ok = cudaIpcGetMemHandle(&mine.df[0], e->df_alloc[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, e->my_flags) == cudaSuccess;
 		if (ok && e->df[1])
-			ok = cudaIpcGetMemHandle(&mine.df[1], e->df[1]) == cudaSuccess;
+			ok = cudaIpcGetMemHandle(&mine.df[1], e->df_alloc[1]) == cudaSuccess;
 		cudaGetLastError();
 	}
 	mine.X = e->X;
 	mine.XYZ = e->XYZ;
+	mine.guard = (int64_t) e->df_guard;
 	mine.ok = ok;
 	Packet* d_pk = nullptr;	 // [0] mine, [1] from the left neighbour, [2] from the right neighbour
 	CU(cudaMalloc(&d_pk, 3 * sizeof(Packet)));
@@ -1045,10 +1066,16 @@ static int setup_peer_memory(lbmx_engine* e)
 	CU(cudaMemcpy(got, d_pk, 3 * sizeof(Packet), cudaMemcpyDeviceToHost));
 	ok = ok && (e->left < 0 || got[1].ok) && (e->right < 0 || got[2].ok);
 	auto map_peer = [&](lbmx_engine::Peer& peer, const Packet& pk) {
-		if (cudaIpcOpenMemHandle(&peer.df[0], pk.df[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+		if (pk.guard != (int64_t) e->df_guard)	// same Y, Z and precision on every slab
 			return false;
-		if (e->df[1] && cudaIpcOpenMemHandle(&peer.df[1], pk.df[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+		if (cudaIpcOpenMemHandle(&peer.df_base[0], pk.df[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
 			return false;
+		peer.df[0] = (char*) peer.df_base[0] + e->df_guard;
+		if (e->df[1]) {
+			if (cudaIpcOpenMemHandle(&peer.df_base[1], pk.df[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+				return false;
+			peer.df[1] = (char*) peer.df_base[1] + e->df_guard;
+		}
 		if (cudaIpcOpenMemHandle((void**) &peer.flags, pk.flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
 			return false;
 		peer.X = pk.X;
@@ -1152,12 +1179,15 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	const long long first_cell = (long long) e->ox * e->YZ, n_cells = (long long) e->X * e->YZ;
 	const int outflow_right = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::OUTFLOW_RIGHT : (int) D3Q27::OUTFLOW_RIGHT;
 	unsigned* d_counts = nullptr;
-	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) (e->X + 1)));
-	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) (e->X + 1), e->s_main));
-	k_count_boundary_cells<<<dim3((unsigned) ((e->YZ + 255) / 256), (unsigned) e->X), 256, 0, e->s_main>>>(e->map, first_cell, (int) e->YZ, periodic, outflow_right, d_counts);
+	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) (e->X + 2)));
+	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) (e->X + 2), e->s_main));
+	const int nothing = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::NOTHING : (int) D3Q27::NOTHING;
+	const int face_rule = ! e->aa() ? 0 : (e->ox == 0 ? 2 : 1);
+	k_count_boundary_cells<<<dim3((unsigned) ((e->YZ + 255) / 256), (unsigned) e->X), 256, 0, e->s_main>>>(e->map, first_cell, (int) e->YZ, periodic, outflow_right, d_counts,
+																											(int) e->Y, (int) e->Z, face_rule, nothing);
 	e->stats.kernel_launches++;
-	std::vector<unsigned> counts((size_t) e->X + 1);
-	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) (e->X + 1), cudaMemcpyDeviceToHost, e->s_main));
+	std::vector<unsigned> counts((size_t) e->X + 2);
+	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) (e->X + 2), cudaMemcpyDeviceToHost, e->s_main));
 	CU(cudaStreamSynchronize(e->s_main));
 	CU(cudaFree(d_counts));
 	// Under A-A such a cell reads, in place, populations that the cell to its left rewrites in the same step (the reference has the
@@ -1194,6 +1224,7 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	}
 	e->stats.boundary_cells = e->nb;
 	e->stats.bulk_cells = e->n_bulk;
+	e->stats.aa_cells_reaching_outside = counts[(size_t) e->X + 1];
 	e->map_ready = true;
 	e->state_version++;
 	return LBMX_OK;

@@ -1131,7 +1131,15 @@ struct LBM_BLOCK
 		lbmx_host::check(lbmx_map_upload(engine, hmap.v.data(), 0), "lbmx_map_upload");
 		if (hBouzidi.getData() != nullptr)
 			dBouzidi = hBouzidi;
+		lbmx_stats st{};
+		if (lbmx_get_stats(engine, &st) == LBMX_OK && st.aa_cells_reaching_outside > 0 && ! warned_aa_faces) {
+			warned_aa_faces = true;	 // once per block: the map is uploaded again after every repaint
+			lbmx_host::log_info("warning: %lld cells on the lattice faces take A-A neighbours outside the lattice (kernels.h:30-37 is unclamped: undefined in the "
+								"reference, meaningless values there here); give the faces a GEO_NOTHING or periodic skin",
+								(long long) st.aa_cells_reaching_outside);
+		}
 	}
+	bool warned_aa_faces = false;
 	void copyMapToHost() { lbmx_host::check(lbmx_map_download(engine, hmap.v.data(), 0), "lbmx_map_download"); }
 	void copyMacroToHost()
 	{
