@@ -114,3 +114,13 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no CPU fallback", ""), f"{f} mentions the oracle"
+
+
+def test_engine_copies_are_ordered_on_its_own_streams():
+    """The engine's streams are non-blocking: work on the legacy default stream is not ordered with them, and a plain cudaMemcpy from
+    pageable memory may return before the DMA has landed.  With several processes sharing one GPU that showed up as a boundary list
+    counted on a half-uploaded map.  Every copy / memset in the engine therefore names a stream."""
+    text = open(os.path.join(ROOT, "tnl_lbm_b200", "csrc", "engine.cu")).read()
+    code = "\n".join(line.split("//")[0] for line in text.splitlines())
+    assert not re.findall(r"\bcudaMem(?:cpy|set)(?:2D|3D)?\s*\(", code), "synchronous cudaMemcpy/cudaMemset on the default stream in engine.cu"
+    assert "cudaStreamNonBlocking" in code

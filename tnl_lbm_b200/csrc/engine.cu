@@ -680,12 +680,17 @@ bool pick_kernels(lbmx_engine* e)
 // host <-> device copies of [ncomp][X(+2ox)][Z][Y] arrays with or without the ghost planes
 int copy_components(lbmx_engine* e, void* dev, void* host, int ncomp, size_t elem, bool with_ghosts, bool to_device)
 {
+	// Every copy is enqueued on the compute stream and waited for there.  A plain cudaMemcpy from pageable host memory runs on the
+	// legacy default stream, which the engine's non-blocking streams do not synchronise with, and may return once the data sit in the
+	// driver's staging buffer -- before the DMA has landed: a kernel launched on s_main right afterwards could still read the old
+	// contents (seen as a miscounted boundary list when several processes share one GPU).
 	CU(cudaSetDevice(e->dev));
-	CU(cudaStreamSynchronize(e->s_main));
+	const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
 	const size_t comp_dev = (size_t) e->XYZ * elem;
 	if (with_ghosts || e->ox == 0) {
 		const size_t bytes = comp_dev * ncomp;
-		CU(to_device ? cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice) : cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
+		CU(to_device ? cudaMemcpyAsync(dev, host, bytes, kind, e->s_main) : cudaMemcpyAsync(host, dev, bytes, kind, e->s_main));
+		CU(cudaStreamSynchronize(e->s_main));
 		return LBMX_OK;
 	}
 	const size_t comp_host = (size_t) e->X * e->YZ * elem;
@@ -693,8 +698,9 @@ int copy_components(lbmx_engine* e, void* dev, void* host, int ncomp, size_t ele
 	for (int c = 0; c < ncomp; c++) {  // the interior planes of one component are contiguous on both sides
 		char* dp = (char*) dev + (size_t) c * comp_dev + skip;
 		char* hp = (char*) host + (size_t) c * comp_host;
-		CU(to_device ? cudaMemcpy(dp, hp, comp_host, cudaMemcpyHostToDevice) : cudaMemcpy(hp, dp, comp_host, cudaMemcpyDeviceToHost));
+		CU(to_device ? cudaMemcpyAsync(dp, hp, comp_host, kind, e->s_main) : cudaMemcpyAsync(hp, dp, comp_host, kind, e->s_main));
 	}
+	CU(cudaStreamSynchronize(e->s_main));
 	return LBMX_OK;
 }
 
@@ -1035,7 +1041,7 @@ static int setup_peer_memory(lbmx_engine* e)
 	const char* mode = std::getenv("LBMX_HALO");
 	int ok = ! (mode && std::strcmp(mode, "nccl") == 0);
 	CU(cudaMalloc(&e->my_flags, 3 * sizeof(long long)));  // [0], [1]: arrival counters; [2]: set when a wait gave up
-	CU(cudaMemset(e->my_flags, 0, 3 * sizeof(long long)));
+	CU(cudaMemsetAsync(e->my_flags, 0, 3 * sizeof(long long), e->s_main));
 	Packet mine{};
 	if (ok) {
 		ok = cudaIpcGetMemHandle(&mine.df[0], e->df_alloc[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, e->my_flags) == cudaSuccess;
@@ -1049,8 +1055,9 @@ static int setup_peer_memory(lbmx_engine* e)
 	mine.ok = ok;
 	Packet* d_pk = nullptr;	 // [0] mine, [1] from the left neighbour, [2] from the right neighbour
 	CU(cudaMalloc(&d_pk, 3 * sizeof(Packet)));
-	CU(cudaMemset(d_pk, 0, 3 * sizeof(Packet)));
-	CU(cudaMemcpy(d_pk, &mine, sizeof(Packet), cudaMemcpyHostToDevice));
+	CU(cudaMemsetAsync(d_pk, 0, 3 * sizeof(Packet), e->s_main));  // stream-ordered before the sends below (see copy_components)
+	CU(cudaMemcpyAsync(d_pk, &mine, sizeof(Packet), cudaMemcpyHostToDevice, e->s_main));
+	CU(cudaStreamSynchronize(e->s_main));
 	NC(g_nccl.GroupStart());  // same posting order as exchange_full_planes (left and right may be the same rank)
 	if (e->right >= 0)
 		NC(g_nccl.Send(d_pk, sizeof(Packet), ncclInt8, e->right, e->comm, e->s_main));
@@ -1063,7 +1070,8 @@ static int setup_peer_memory(lbmx_engine* e)
 	NC(g_nccl.GroupEnd());
 	CU(cudaStreamSynchronize(e->s_main));
 	Packet got[3];
-	CU(cudaMemcpy(got, d_pk, 3 * sizeof(Packet), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpyAsync(got, d_pk, 3 * sizeof(Packet), cudaMemcpyDeviceToHost, e->s_main));
+	CU(cudaStreamSynchronize(e->s_main));
 	ok = ok && (e->left < 0 || got[1].ok) && (e->right < 0 || got[2].ok);
 	auto map_peer = [&](lbmx_engine::Peer& peer, const Packet& pk) {
 		if (pk.guard != (int64_t) e->df_guard)	// same Y, Z and precision on every slab
@@ -1094,11 +1102,12 @@ static int setup_peer_memory(lbmx_engine* e)
 	cudaGetLastError();
 	// agreement: the exchange protocol must be the same on every rank
 	int* d_ok = (int*) d_pk;
-	CU(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+	CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, e->s_main));
 	NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, e->comm, e->s_main));
 	CU(cudaStreamSynchronize(e->s_main));
 	int all_ok = 0;
-	CU(cudaMemcpy(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, e->s_main));
+	CU(cudaStreamSynchronize(e->s_main));
 	CU(cudaFree(d_pk));
 	e->p2p = all_ok != 0;
 	if (! e->p2p)
@@ -1437,7 +1446,8 @@ int lbmx_set_inflow_profile(lbmx_engine* e, const void* host_profile, int64_t si
 		CU(cudaFree(e->profile));
 	e->profile = nullptr;
 	CU(cudaMalloc(&e->profile, (size_t) (size_y * size_z) * e->rs));
-	CU(cudaMemcpy(e->profile, host_profile, (size_t) (size_y * size_z) * e->rs, cudaMemcpyHostToDevice));
+	CU(cudaMemcpyAsync(e->profile, host_profile, (size_t) (size_y * size_z) * e->rs, cudaMemcpyHostToDevice, e->s_main));	 // stream-ordered, see copy_components
+	CU(cudaStreamSynchronize(e->s_main));
 	e->profile_sy = size_y;
 	e->state_version++;
 	return LBMX_OK;
@@ -1452,7 +1462,7 @@ int lbmx_bouzidi_upload(lbmx_engine* e, const void* host_coeff)
 	CU(cudaSetDevice(e->dev));
 	if (! e->bouzidi) {
 		CU(cudaMalloc(&e->bouzidi, (size_t) 8 * e->XYZ * e->rs));
-		CU(cudaMemset(e->bouzidi, 0xbf, (size_t) 8 * e->XYZ * e->rs));	// ghost planes: a negative value (0xbfbf... < 0 in both precisions)
+		CU(cudaMemsetAsync(e->bouzidi, 0xbf, (size_t) 8 * e->XYZ * e->rs, e->s_main));	// ghost planes: a negative value (0xbfbf... < 0 in both precisions)
 		e->state_version++;
 	}
 	return copy_components(e, e->bouzidi, (void*) host_coeff, 8, e->rs, false, true);
@@ -1477,7 +1487,8 @@ int lbmx_sync(lbmx_engine* e)
 	CU(cudaStreamSynchronize(e->s_comm));
 	if (e->p2p) {
 		long long gave_up = 0;
-		CU(cudaMemcpy(&gave_up, e->my_flags + 2, sizeof(long long), cudaMemcpyDeviceToHost));
+		CU(cudaMemcpyAsync(&gave_up, e->my_flags + 2, sizeof(long long), cudaMemcpyDeviceToHost, e->s_main));
+		CU(cudaStreamSynchronize(e->s_main));
 		if (gave_up)
 			return fail(LBMX_ERR_STATE, "lbmx_sync: the peer-memory halo exchange waited 20 s for exchange " + std::to_string(gave_up) + " of a neighbour and gave up (a neighbour rank stopped stepping?)");
 	}
