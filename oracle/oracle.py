@@ -135,6 +135,10 @@ def _path(kind: str, streaming: int, fast: bool) -> str:
         return os.path.join(HERE, "_ref", f"libref_{'aa' if streaming == AA else 'ab'}{suf}.so")
     if kind == "port":
         return os.path.join(HERE, f"liboracle_port{suf}.so")
+    if kind == "engine_host":
+        # not a checker: the engine's CUDA kernels compiled for the host (tools/engine_host.cpp) behind this same C interface, so that the
+        # tests can run them against the checkers without a GPU.  fast = the default arithmetic, otherwise the parity arithmetic.
+        return os.path.join(os.path.dirname(HERE), "tools", "bin", f"libengine_host{suf}.so")
     raise ValueError(kind)
 
 
@@ -161,7 +165,7 @@ def _load(kind: str, streaming: int, fast: bool):
 
 
 class Oracle:
-    """One CPU checker bound to a descriptor.  `kind` is "reference" or "port"."""
+    """One CPU checker bound to a descriptor.  `kind` is "reference" or "port" ("engine_host": see _path)."""
 
     def __init__(self, desc: Desc, kind: str = "port", fast: bool = False):
         self.desc = desc

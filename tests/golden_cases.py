@@ -144,11 +144,12 @@ def freeze_means(mac: np.ndarray, samples: int) -> None:
         mac[ch][inner] = 0
 
 
-def run_case(case: Case, kind: str, nthreads: int = 1):
-    """Run a case on a CPU checker; returns (df holding the current state, macro)."""
+def run_case(case: Case, kind: str, nthreads: int = 1, fast: bool = False, init_kind: str | None = None):
+    """Run a case on a CPU checker; returns (df holding the current state, macro).  `init_kind`: take the initial state from that
+    checker instead (the way the engine tests upload the port's initial arrays)."""
     d, p = case.desc, case.params
-    orc = O.Oracle(d, kind)
-    a = initial_df(case, orc)
+    orc = O.Oracle(d, kind, fast=fast)
+    a = initial_df(case, O.Oracle(d, init_kind) if init_kind else orc)
     b = a.copy()
     mac = d.new_macro()
     m = case.make_map(d)

@@ -1,0 +1,176 @@
+"""The engine's CUDA kernels themselves -- k_bulk, k_boundary, k_set_equilibrium, k_initial_macro of tnl_lbm_b200/csrc/kernels.cuh with
+all they include -- compiled for the HOST (tools/engine_host.cpp supplies the handful of CUDA built-ins they use) and run thread by
+thread over the grid the engine launches, on every golden case:
+
+  * parity arithmetic (LBMX_STRICT=1, -ffp-contract=off): bit-identical to the CPU restatement of the reference and to the committed
+    samples the reference's own code produced -- the statement tests/test_gpu_parity.py makes on the GPU, here without one;
+  * default arithmetic: within the north-star tolerance (g++ does not contract to FMA here, nvcc does: this pins the association of
+    the fast operators, the GPU tests pin the rest).
+
+What this covers beyond tests/test_operators_on_host.py (per-cell operators on a periodic box): streaming offsets of all three
+modes, speculative wrapped loads and the A-B face re-load, cells per thread, the invariant division, the boundary list and the
+whole cell-type dispatch, Bouzidi links, inflow profiles, every macro mode.  tools/engine_host.cpp is a test tool; the product has
+no CPU path (tests/test_abi.py::test_no_cpu_fallback_without_a_gpu)."""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import lbm_cases as lc
+from oracle import oracle as O
+from tnl_lbm_b200.build import FAMILIES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+SRC = os.path.join(ROOT, "tools", "engine_host.cpp")
+BIN = os.path.join(ROOT, "tools", "bin")
+KIND_NUMBER = {"K_CUM": 0, "K_SRT": 1, "K_BGK": 2, "K_MRT": 3, "K_CLBM": 4, "K_SRT_MF": 5, "K_CUM_2017": 10, "K_CUM_AALIAS": 11, "K_CUM_2017_AALIAS": 12,
+               **{f"K_KBC_{g}{i}": 13 + 4 * k + i - 1 for k, g in enumerate("NC") for i in (1, 2, 3, 4)}}
+TOL = {O.F64: 1e-12, O.F32: 1e-5}
+
+pytestmark = pytest.mark.skipif(not O.available("port"), reason="oracle port not built")
+
+
+def _sources_mtime() -> float:
+    csrc = os.path.join(ROOT, "tnl_lbm_b200", "csrc")
+    files = [SRC, os.path.join(ROOT, "oracle", "oracle_api.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    return max(os.path.getmtime(f) for f in files)
+
+
+def _build(strict: bool) -> str:
+    lib = O._path("engine_host", O.AB, fast=not strict)
+    if os.path.exists(lib) and os.path.getmtime(lib) >= _sources_mtime():
+        return lib
+    tag = "strict" if strict else "fast"
+    objdir = os.path.join(BIN, f"hk_{tag}_{os.getpid()}")  # private to this process: parallel test workers may build at the same time
+    os.makedirs(objdir, exist_ok=True)
+    base = ["g++", "-std=c++17", "-O1", "-fPIC", "-w", "-ffp-contract=off", f"-DLBMX_STRICT={1 if strict else 0}"]
+    jobs = [(base + ["-DHK_MAIN", "-c", SRC, "-o", os.path.join(objdir, "main.o")])]
+    for _, lat, kind in FAMILIES:
+        if strict and lat == "D3Q19":
+            continue  # no parity arithmetic without a reference (include/lbmx.h: LBMX_FLAG_STRICT_ARITH)
+        name = f"{lat.lower()}_{KIND_NUMBER[kind]}"
+        jobs.append(base + [f"-DHK_LAT={lat}", f"-DHK_KIND={kind}", f"-DHK_NAME={name}", "-c", SRC, "-o", os.path.join(objdir, f"{name}.o")])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, " ".join(cmd) + "\n" + r.stderr[-3000:]
+        return cmd[-1]
+
+    with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        objs = list(ex.map(run, jobs))
+    run(["g++", "-shared", "-o", os.path.join(objdir, "lib.so")] + objs + ["-ldl"])
+    os.replace(os.path.join(objdir, "lib.so"), lib)
+    shutil.rmtree(objdir, ignore_errors=True)
+    return lib
+
+
+@pytest.fixture(scope="module")
+def strict_lib():
+    return _build(strict=True)
+
+
+@pytest.fixture(scope="module")
+def fast_lib():
+    return _build(strict=False)
+
+
+def _bit_exact(a, ref, what):
+    if not np.array_equal(a, ref):
+        diff = np.abs(a.astype(np.float64) - ref.astype(np.float64))
+        i = np.unravel_index(np.argmax(diff), diff.shape)
+        raise AssertionError(f"{what}: {int((a != ref).sum())} of {a.size} values differ, max abs {diff.max():.3e} at {tuple(int(v) for v in i)} got={a[i]!r} ref={ref[i]!r}")
+
+
+@pytest.mark.parametrize("name", [c.name for c in gc.CASES])
+def test_kernels_in_parity_arithmetic_are_bit_identical_on_the_host(strict_lib, name):
+    case = gc.BY_NAME[name]
+    df, mac = gc.run_case(case, "engine_host", init_kind="port")
+    df_ref, mac_ref = gc.run_case(case, "port")
+    _bit_exact(df, df_ref, name + ": distributions vs port")
+    if case.desc.macro != O.MACRO_VOID:
+        _bit_exact(mac, mac_ref, name + ": macro vs port")
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    s = int(z["stride"])
+    _bit_exact(gc.sample(df, s), z["df_sample"], name + ": distributions vs the reference's golden sample")
+    if case.desc.macro != O.MACRO_VOID:
+        _bit_exact(gc.sample(mac, s), z["macro_sample"], name + ": macro vs the reference's golden sample")
+
+
+@pytest.mark.parametrize("name", [c.name for c in gc.CASES])
+def test_kernels_in_default_arithmetic_stay_within_tolerance_on_the_host(fast_lib, name):
+    case = gc.BY_NAME[name]
+    tol = TOL[case.desc.precision]
+    df, mac = gc.run_case(case, "engine_host", fast=True, init_kind="port")
+    df_ref, mac_ref = gc.run_case(case, "port")
+    assert np.isfinite(df).all()
+    assert lc.rel_err_df(df, df_ref, case.desc) <= tol
+    if case.desc.macro != O.MACRO_VOID:
+        for lo, hi, label in lc.macro_groups(case.desc):
+            assert lc.rel_err(mac[lo:hi], mac_ref[lo:hi]) <= tol, label
+
+
+@pytest.mark.parametrize("name", ["cum_f64_aa_box", "cum_f64_ab_sim1", "d2q9_srt_f64_ab_cavity", "srt_f64_ab_zoo"])
+def test_initial_state_kernels_on_the_host(strict_lib, name):
+    """k_set_equilibrium (uniform and per-cell fields) and k_initial_macro against the restatement, bit for bit."""
+    case = gc.BY_NAME[name]
+    d = case.desc
+    host, port = O.Oracle(d, "engine_host"), O.Oracle(d, "port")
+    a, b = d.new_df(), d.new_df()
+    host.set_equilibrium(a, 1.02, 0.03, -0.01, 0.0 if d.lattice == O.D2Q9 else 0.02)
+    port.set_equilibrium(b, 1.02, 0.03, -0.01, 0.0 if d.lattice == O.D2Q9 else 0.02)
+    _bit_exact(a, b, "uniform equilibrium")
+    fields = lc.smooth_fields(d)
+    host.set_equilibrium_field(a, *fields)
+    port.set_equilibrium_field(b, *fields)
+    _bit_exact(a, b, "equilibrium of per-cell fields")
+    ma, mb = d.new_macro(), d.new_macro()
+    host.initial_macro(case.params, a, ma)
+    port.initial_macro(case.params, b, mb)
+    _bit_exact(ma, mb, "initial macroscopic fields")
+
+
+def test_d3q19_kernels_on_the_host_conserve_and_match_the_cpu_implementation(fast_lib):
+    """D3Q19 has no reference (parity unpinned): the host build of its kernels against this repository's independent CPU
+    implementation, as tests/test_d3q19.py does on the GPU."""
+    d = O.Desc(lattice=O.D3Q19, coll=O.SRT, eq=O.EQ_STD, streaming=O.AA, X=10, Y=9, Z=8)
+    case = gc.Case("d3q19", d, O.Params(lbmViscosity=0.02, fx=1e-5), lc.map_periodic, 12, "smooth")
+    df, mac = gc.run_case(case, "engine_host", fast=True, init_kind="port")
+    df_ref, mac_ref = gc.run_case(case, "port")
+    assert lc.rel_err_df(df, df_ref, d) <= 1e-12
+    assert abs(float(df.sum()) / float(df_ref.sum()) - 1.0) < 1e-13
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+def test_ghosted_slabs_of_the_host_kernels_equal_the_undivided_run(strict_lib, streaming, nslabs):
+    """The kernels under the ghost-plane rule (ox = 1, no wrap in x) with the planes of lbmx_halo_plan exchanged by hand after every
+    step (tests/slab_emulation.py): N slabs of the engine's kernels == the undivided run of the restatement, bit for bit."""
+    from slab_emulation import run_slabs_oracle
+
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, X=12, Y=7, Z=6)
+    case = gc.Case("duct", d, O.Params(lbmViscosity=0.01, fx=2e-5, fy=-1e-5, fz=3e-5), lc.map_duct_slab_safe, 7, "noisy")
+    ref_df, ref_mac = gc.run_case(case, "port")
+    df, mac = run_slabs_oracle(case, nslabs, kind="engine_host")
+    _bit_exact(df, ref_df, "distributions")
+    _bit_exact(mac, ref_mac, "macro")
+
+
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+def test_walled_duct_slabs_of_the_host_kernels_equal_those_of_the_restatement(strict_lib, streaming):
+    """sim_2's duct, whose walls touch the periodic x faces: defined only under the ghost-plane rule."""
+    from slab_emulation import run_slabs_oracle
+
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, X=8, Y=8, Z=8)
+    case = gc.Case("duct", d, O.Params(lbmViscosity=5e-3, fx=1e-5), lc.map_duct_periodic_x, 9, "noisy")
+    for n in (1, 2):
+        ref_df, ref_mac = run_slabs_oracle(case, n, kind="port")
+        df, mac = run_slabs_oracle(case, n, kind="engine_host")
+        _bit_exact(df, ref_df, f"{n} slabs: distributions")
+        _bit_exact(mac, ref_mac, f"{n} slabs: macro")
