@@ -174,3 +174,21 @@ def test_walled_duct_slabs_of_the_host_kernels_equal_those_of_the_restatement(st
         df, mac = run_slabs_oracle(case, n, kind="engine_host")
         _bit_exact(df, ref_df, f"{n} slabs: distributions")
         _bit_exact(mac, ref_mac, f"{n} slabs: macro")
+
+
+@pytest.mark.parametrize("desc", [
+    O.Desc(coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, precision=O.F32, X=3, Y=23, Z=13),       # fp32 D3Q27: two cells per thread (A-B, A-A even)
+    O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AA, precision=O.F32, X=4, Y=23, Z=13),
+    O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AA, precision=O.F64, X=3, Y=37, Z=9),    # one cell per thread, ragged rows
+    O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AA, precision=O.F64, X=5, Y=301, Z=1),  # D2Q9: two cells per thread
+    O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, precision=O.F32, X=5, Y=300, Z=1),
+], ids=["srt_f32_ab", "cum_f32_aa", "cum_f64_aa", "d2q9_srt_f64_aa", "d2q9_clbm_f32_ab"])
+def test_rows_longer_than_a_thread_block_on_the_host(strict_lib, desc):
+    """Y*Z above one CTA's worth of cells and not a multiple of it: the second cell of a two-cell thread, the tail CTA and the
+    division of the flattened (y,z) index by a Y that is not a power of two (the golden cases all fit a single CTA per plane)."""
+    p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, fz=0.0 if desc.lattice == O.D2Q9 else 1e-5, inflow_vx=0.04, inflow_vy=0.01)
+    case = gc.Case("ragged", desc, p, gc.zoo, 5 if desc.streaming == O.AA else 4, "noisy", seed=3)
+    df, mac = gc.run_case(case, "engine_host", init_kind="port")
+    df_ref, mac_ref = gc.run_case(case, "port")
+    _bit_exact(df, df_ref, "distributions")
+    _bit_exact(mac, mac_ref, "macro")
