@@ -22,8 +22,9 @@ def _init(rank, world, port, backend):
     return dist
 
 
-def gloo_slab_worker(rank, world, port, case_name, outdir):
-    """CPU: one oracle slab per process; halo planes travel through torch.distributed (gloo) exactly as lbmx_halo_plan says."""
+def gloo_slab_worker(rank, world, port, case_name, outdir, kind="port"):
+    """CPU: one slab per process, stepped by the CPU checker (`kind` = "port") or by the engine's own kernels compiled for the host
+    (`kind` = "engine_host", tools/engine_host.cpp); halo planes travel through torch.distributed (gloo) exactly as lbmx_halo_plan says."""
     import torch
 
     import golden_cases as gc
@@ -43,7 +44,7 @@ def gloo_slab_worker(rank, world, port, case_name, outdir):
     x0, xl = B.decompose_x(dg.X, world, rank)
     d = copy.copy(dg)
     d.X, d.ox, d.nproc = xl, 1, 2
-    orc = O.Oracle(d, "port")
+    orc = O.Oracle(d, kind)
     mac = d.new_macro()
     aa = dg.streaming == O.AA
     left, right = (rank - 1) % world, (rank + 1) % world

@@ -18,15 +18,22 @@ def free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("kind", ["port", "engine_host"])
 @pytest.mark.parametrize("case_name", ["duct_ab", "duct_aa"])
-def test_two_process_gloo_slabs(case_name):
+def test_two_process_gloo_slabs(case_name, kind):
+    """kind = "engine_host": each process steps its slab with the engine's own CUDA kernels compiled for the host (parity arithmetic,
+    tools/engine_host.cpp) -- the kernels' ghost-plane rule and the halo plan across two processes, without a GPU."""
     import torch.multiprocessing as mp
 
     import dist_workers as W
 
+    if kind == "engine_host":
+        from test_kernels_on_host import _build
+
+        _build(strict=True)
     world = 2
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(W.gloo_slab_worker, args=(world, free_port(), case_name, tmp), nprocs=world, join=True)
+        mp.spawn(W.gloo_slab_worker, args=(world, free_port(), case_name, tmp, kind), nprocs=world, join=True)
         df, mac = W.gather(tmp, world)
     case = W.DIST_CASES[case_name]()
     ref_df, ref_mac = gc.run_case(case, "port")
