@@ -126,6 +126,25 @@ def cpu_reference_run(size: int, steps: int, warmup: int, threads: int, streamin
     return size ** 3 * steps / dt / 1e6, kind, dt / steps * 1e3
 
 
+def macro_every_step_run(a):
+    """Re-run the device-resident measurement with LBMX_MACRO_EVERY_STEP in a child process; returns a small dict for the JSON line."""
+    steps = int(min(a.steps, 50))
+    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--steps", str(steps), "--warmup", "3", "--size", str(a.size), "--streaming", a.streaming,
+           "--macro-policy", "every", "--no-cpu-baseline", "--no-extras"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+        rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not rows:
+            return {"error": f"child exited {r.returncode}: {r.stderr.strip()[-300:]}"}
+        child = json.loads(rows[-1])
+        bytes_per_update = B_PER_UPDATE + 4 * SIZEOF + 2  # populations + rho,u + the cell type
+        return {"value": child["value"], "unit": "MLUPS", "steps": steps, "ms_per_step": child["ms_per_step"], "clocks": child.get("clocks"),
+                "bytes_per_update_incl_macro_and_map": bytes_per_update, "GBs_incl_macro_and_map": child["value"] * 1e6 * bytes_per_update / 1e9,
+                "what": "same workload, rho and u written by every step as the reference kernel does (lbmx_desc.macro_policy = LBMX_MACRO_EVERY_STEP)"}
+    except Exception as ex:
+        return {"error": repr(ex)}
+
+
 # ------------------------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -137,6 +156,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the periodic sub-box the CPU arm times")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streaming", default="AA", choices=["AA", "AB"])
+    ap.add_argument("--macro-policy", default="last", choices=["last", "every"],
+                    help="last: rho,u written by the last step of a batch (default; identical values wherever the host can observe them); "
+                         "every: written by every step, as the reference kernel does (+32 B per update)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements that start child processes")
     ap.add_argument("--workload", default="box", choices=["box", "channel"],
                     help="box: periodic 512^3 per GPU, weak scaling (the headline metric); channel: BASELINE.json configs[3], the 2048x512x512 "
                          "body-force duct of sim_NSE/sim_2.cu split into N x-slabs, strong scaling (N >= 2)")
@@ -156,7 +179,8 @@ def main():
     else:
         workload = f"D3Q27 cumulant (EQ_INV_CUM) fp64 A-{'A' if a.streaming == 'AA' else 'B'} periodic box, {a.size}^3 cells per GPU, nu=1e-3, fx=1e-6"
     config = {"workload": workload, "global_lattice": [Xg, a.size, a.size], "decomposition": f"x-slabs x{N}", "l2_policy": "working set (29 GB/GPU) larger than L2; no flush needed",
-              "macro_policy": "written by the last step of the batch (values identical at every host-observable point)"}
+              "macro_policy": ("written by the last step of the batch (values identical at every host-observable point)" if a.macro_policy == "last"
+                               else "written by every step, as the reference kernel does (d3q27/macro.h:64-71)")}
 
     # ---------------------------------------------------------------- reference arm: the CPU implementation, rank 0 only
     if a.impl == "reference":
@@ -199,7 +223,8 @@ def main():
     assert not (channel and N < 2), "--workload channel needs at least 2 GPUs (134 GB of distributions)"
     streaming = B.AA if a.streaming == "AA" else B.AB
     eng = B.Engine(lattice=B.D3Q27, coll=B.CUM, eq=B.EQ_INV_CUM, streaming=streaming, macro=B.MACRO_DEFAULT, inflow=B.INFLOW_NONE, precision=B.F64,
-                   X=Xg, Y=S, Z=S, rank=rank, nranks=N, device=local_rank, ghost_x=1 if (N > 1 or channel) else 0, periodic_x=1, macro_policy=B.MACRO_LAST_STEP)
+                   X=Xg, Y=S, Z=S, rank=rank, nranks=N, device=local_rank, ghost_x=1 if (N > 1 or channel) else 0, periodic_x=1,
+                   macro_policy=B.MACRO_LAST_STEP if a.macro_policy == "last" else B.MACRO_EVERY_STEP)
     if N > 1:
         idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -372,6 +397,10 @@ def main():
                 line["reference_gpu_kernel"] = json.loads(r.stdout.strip().splitlines()[-1])
             except Exception as ex:
                 line["reference_gpu_kernel"] = {"error": repr(ex)}
+    # ---- the same workload with the macroscopic fields written by EVERY step (the reference's behaviour), in a child process after this
+    #      engine has released its memory: a failure or time-out there cannot take the line above with it
+    if rank == 0 and N == 1 and not channel and a.macro_policy == "last" and not a.no_extras and not a.no_cpu_baseline:
+        line["macro_every_step"] = macro_every_step_run(a)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if N > 1:
