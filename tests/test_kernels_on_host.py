@@ -51,7 +51,7 @@ def _build(strict: bool) -> str:
     objdir = os.path.join(BIN, f"hk_{tag}_{os.getpid()}")  # private to this process: parallel test workers may build at the same time
     os.makedirs(objdir, exist_ok=True)
     base = ["g++", "-std=c++17", "-O1", "-fPIC", "-w", "-ffp-contract=off", f"-DLBMX_STRICT={1 if strict else 0}"]
-    jobs = [(base + ["-DHK_MAIN", "-c", SRC, "-o", os.path.join(objdir, "main.o")])]
+    jobs = [(base + ["-DHK_MAIN", "-c", SRC, "-o", os.path.join(objdir, "main.o")]), (base + ["-DHK_SERVICE", "-c", SRC, "-o", os.path.join(objdir, "service.o")])]
     for _, lat, kind in FAMILIES:
         if strict and lat == "D3Q19":
             continue  # no parity arithmetic without a reference (include/lbmx.h: LBMX_FLAG_STRICT_ARITH)
@@ -208,3 +208,36 @@ def test_1000_steps_of_the_cumulant_kernels_on_the_host(strict_lib, fast_lib, st
     assert lc.rel_err_df(df, df_ref, d) <= 1e-12
     for lo, hi, label in lc.macro_groups(d):
         assert lc.rel_err(mac[lo:hi], mac_ref[lo:hi]) <= 1e-12, label
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_plane_copy_kernel_on_the_host(strict_lib, dtype):
+    """k_copy_planes (the data mover of the halo exchange: self-exchange, and the push into a neighbour's array with its own component
+    stride) executing lbmx_halo_plan, against numpy."""
+    import ctypes as C
+
+    from tnl_lbm_b200 import binding as B
+
+    lib = C.CDLL(strict_lib)
+    lib.hk_copy_planes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong]
+    f64 = int(dtype == np.float64)
+    rs = np.random.RandomState(4)
+    Y, Z, Xa, Xb = 37, 9, 5, 7  # two slabs of different length: the receiver's component stride differs from the sender's
+    a = rs.random_sample((27, Xa + 2, Z, Y)).astype(dtype)
+    b = rs.random_sample((27, Xb + 2, Z, Y)).astype(dtype)
+    for streaming in (O.AB, O.AA):
+        for it in (0, 1):
+            plan_a, plan_b = B.halo_plan(O.D3Q27, streaming, it, Xa), B.halo_plan(O.D3Q27, streaming, it, Xb)
+            for k, msg in enumerate(plan_a):
+                want = b.copy()
+                want[msg["dirs"], plan_b[k]["dst_plane"]] = a[msg["dirs"], msg["src_plane"]]
+                got = b.copy()
+                dirs = np.asarray(msg["dirs"], dtype=np.int32)
+                lib.hk_copy_planes(f64, got.ctypes.data, a.ctypes.data, a[0].size, Y * Z, len(dirs), dirs.ctypes.data, msg["src_plane"], plan_b[k]["dst_plane"], b[0].size)
+                assert np.array_equal(got, want), (streaming, it, k)
+                # self-exchange: same array on both sides, stride argument 0
+                want = a.copy()
+                want[msg["dirs"], msg["dst_plane"]] = a[msg["dirs"], msg["src_plane"]]
+                got = a.copy()
+                lib.hk_copy_planes(f64, got.ctypes.data, got.ctypes.data, a[0].size, Y * Z, len(dirs), dirs.ctypes.data, msg["src_plane"], msg["dst_plane"], 0)
+                assert np.array_equal(got, want), (streaming, it, k, "self")

@@ -244,6 +244,30 @@ int initial_macro_family(const oracle_desc* d, const oracle_params* op, void* df
 
 }  // namespace
 
+	#ifdef HK_SERVICE
+// ---- the plane copies of the halo exchange (k_has_nan votes across a warp: not reproducible one thread at a time) ----------------
+extern "C" {
+// k_copy_planes as the engine launches it (exchange<R> in engine.cu): grid (ceil(YZ / 256), n_dirs), 256 threads
+int hk_copy_planes(int f64, void* dst, const void* src, long long XYZ, int YZ, int n_dirs, const int* dirs, long long src_plane, long long dst_plane, long long dst_XYZ)
+{
+	gridDim.x = (unsigned) ((YZ + 255) / 256);
+	gridDim.y = (unsigned) n_dirs;
+	blockDim.x = 256;
+	for (unsigned by = 0; by < gridDim.y; by++)
+		for (unsigned bx = 0; bx < gridDim.x; bx++)
+			for (unsigned t = 0; t < 256; t++) {
+				blockIdx.x = bx;
+				blockIdx.y = by;
+				threadIdx.x = t;
+				if (f64)
+					k_copy_planes<double>((double*) dst, (const double*) src, XYZ, YZ, n_dirs, dirs, src_plane, dst_plane, dst_XYZ);
+				else
+					k_copy_planes<float>((float*) dst, (const float*) src, XYZ, YZ, n_dirs, dirs, src_plane, dst_plane, dst_XYZ);
+			}
+	return 0;
+}
+}
+	#else
 	#define HK_CAT_(a, b) a##b
 	#define HK_CAT(a, b) HK_CAT_(a, b)
 extern "C" {
@@ -261,6 +285,7 @@ int HK_CAT(hk_initial_macro_, HK_NAME)(const oracle_desc* d, const oracle_params
 	return d->precision == ORC_F64 ? initial_macro_family<HK_LAT, HK_KIND, double>(d, p, df, mac) : initial_macro_family<HK_LAT, HK_KIND, float>(d, p, df, mac);
 }
 }
+	#endif	// HK_SERVICE
 
 #else  // HK_MAIN: the oracle_api.h entry points, dispatching on (lattice, operator) to the family objects that were linked in
 	#include <dlfcn.h>
