@@ -222,7 +222,8 @@ int lbmx_macro_download(lbmx_engine* e, void* host_macro, int with_ghosts);
 int lbmx_macro_upload(lbmx_engine* e, const void* host_macro, int with_ghosts);
 
 int lbmx_set_params(lbmx_engine* e, const lbmx_params* p);
-/* NSE_Data_XProfileInflow::vx_profile (sim_NSE/sim_2.cu:16-33): real[size_y*size_z] in the engine's precision */
+/* NSE_Data_XProfileInflow::vx_profile (sim_NSE/sim_2.cu:16-33): real[size_y*size_z] in the engine's precision, read as
+ * profile[y + z*size_y]; size_y >= Y and size_z >= Z (LBMX_ERR_ARG otherwise) */
 int lbmx_set_inflow_profile(lbmx_engine* e, const void* host_profile, int64_t size_y, int64_t size_z);
 
 /* D2Q9 GEO_FLUID_NEAR_WALL (Bouzidi interpolated bounce-back, d2q9/bc.h:61-87,140-167; A-B streaming only): the coefficient array

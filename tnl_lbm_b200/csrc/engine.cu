@@ -1440,6 +1440,8 @@ int lbmx_set_inflow_profile(lbmx_engine* e, const void* host_profile, int64_t si
 {
 	if (! e || ! host_profile || size_y < 1 || size_z < 1)
 		return fail(LBMX_ERR_ARG, "lbmx_set_inflow_profile: bad argument");
+	if (size_y < e->Y || size_z < e->Z)	 // the kernels read profile[y + z * size_y] for every inflow cell (y, z) of the lattice
+		return fail(LBMX_ERR_ARG, "lbmx_set_inflow_profile: the profile must cover the lattice's (y, z) cross-section");
 	CU(cudaSetDevice(e->dev));
 	CU(cudaStreamSynchronize(e->s_main));
 	if (e->profile)
