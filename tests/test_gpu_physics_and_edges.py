@@ -109,6 +109,10 @@ def test_state_and_argument_errors():
         e.map_upload(np.zeros((4, 4, 4), dtype=np.int16))
         with pytest.raises(B.LbmxError, match="inflow profile"):
             e.step(1)
+        with pytest.raises(B.LbmxError, match="cross-section"):
+            e.set_inflow_profile(np.zeros((3, 4), dtype=e.dtype))  # 4 x 3 (y, z): smaller than the 4 x 4 cross-section
+        e.set_inflow_profile(np.zeros((4, 4), dtype=e.dtype))
+        e.step(1)
     with B.Engine(X=4, Y=4, Z=4, macro=B.MACRO_VOID) as e:
         e.map_upload(np.zeros((4, 4, 4), dtype=np.int16))
         e.step(2)
