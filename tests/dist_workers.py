@@ -113,6 +113,37 @@ def nccl_engine_worker(rank, world, port, case_name, outdir, transport="auto"):
     dist.destroy_process_group()
 
 
+def shared_device_worker(rank, nprocs, names, reps, outdir, runner="engine"):
+    """Several processes drive small engines on ONE GPU at the same time (time-slicing stretches the gap between a host call returning
+    and its device work landing: the situation that exposed the copies on the legacy default stream, profiles/gpu_suite_r1_shared_gpu.md).
+    Every repetition of a case must reproduce the first bit for bit; the first result goes to `outdir` for the comparison with the
+    CPU checker.  runner = "engine_host": the same loop over the kernels' host build (checks this worker without a GPU)."""
+    import golden_cases as gc
+
+    if runner == "engine":
+        from engine_runner import run_case_engine
+
+        def run(case):
+            df, mac, _ = run_case_engine(case, chunk=9)  # batches of 9: graph replay on even starts, plain launches on odd ones
+            return df, mac
+    else:
+        def run(case):
+            return gc.run_case(case, "engine_host", fast=True, init_kind="port")
+
+    first, changed = {}, []
+    for r in range(reps):
+        for n in names:
+            df, mac = run(gc.BY_NAME[n])
+            if n not in first:
+                first[n] = (df, mac)
+                np.save(os.path.join(outdir, f"df_{n}_{rank}.npy"), df)
+                np.save(os.path.join(outdir, f"mac_{n}_{rank}.npy"), mac)
+            elif not (np.array_equal(df, first[n][0]) and np.array_equal(mac, first[n][1])):
+                changed.append((n, r))
+    with open(os.path.join(outdir, f"changed_{rank}.txt"), "w") as f:
+        f.write(repr(changed))
+
+
 def _duct(streaming, X=16, nsteps=9):
     import golden_cases as gc
     import lbm_cases as lc

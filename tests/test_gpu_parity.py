@@ -361,3 +361,13 @@ def test_1000_steps_parity_arithmetic_is_bit_exact(coll, eq, st, prec, nu):
     df_ref, mac_ref = gc.run_case(case, "port", nthreads=os.cpu_count() or 4)
     assert_bit_exact(df, df_ref, "1000 steps, parity arithmetic: distributions")
     assert_bit_exact(mac, mac_ref, "1000 steps, parity arithmetic: macro")
+
+
+def test_engines_of_several_processes_share_one_gpu():
+    """Six processes run small cases on the same GPU at the same time, ten times each, in batches of 9 steps.  With copies on the legacy
+    default stream (which the engine's non-blocking streams are not ordered against) this failed within seconds -- a boundary list
+    counted on a half-uploaded map, an upload landing after the first steps (profiles/gpu_suite_r1_shared_gpu.md); every copy is now
+    enqueued on the compute stream.  Each repetition must reproduce the first bit for bit, and the first must match the CPU checker."""
+    from test_kernels_on_host import check_shared_device_run
+
+    check_shared_device_run("engine", nprocs=6, reps=10, names=["cum_f64_ab_sim1", "d2q9_srt_f64_ab_cavity", "cum_f64_aa_duct"], tol=1e-12)

@@ -241,3 +241,29 @@ def test_plane_copy_kernel_on_the_host(strict_lib, dtype):
                 got = a.copy()
                 lib.hk_copy_planes(f64, got.ctypes.data, got.ctypes.data, a[0].size, Y * Z, len(dirs), dirs.ctypes.data, msg["src_plane"], msg["dst_plane"], 0)
                 assert np.array_equal(got, want), (streaming, it, k, "self")
+
+
+def check_shared_device_run(runner, nprocs, reps, names, tol):
+    """Spawn the workers of dist_workers.shared_device_worker and compare what they left behind with the CPU checker."""
+    import tempfile
+
+    import torch.multiprocessing as mp
+
+    import dist_workers as W
+
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(W.shared_device_worker, args=(nprocs, names, reps, tmp, runner), nprocs=nprocs, join=True)
+        for n in names:
+            case = gc.BY_NAME[n]
+            df_ref, mac_ref = gc.run_case(case, "port")
+            for r in range(nprocs):
+                assert open(os.path.join(tmp, f"changed_{r}.txt")).read() == "[]", (n, r)
+                df, mac = np.load(os.path.join(tmp, f"df_{n}_{r}.npy")), np.load(os.path.join(tmp, f"mac_{n}_{r}.npy"))
+                assert lc.rel_err_df(df, df_ref, case.desc) <= tol, (n, r)
+                for lo, hi, label in lc.macro_groups(case.desc):
+                    assert lc.rel_err(mac[lo:hi], mac_ref[lo:hi]) <= tol, (n, r, label)
+
+
+def test_concurrent_processes_over_the_host_kernels(fast_lib):
+    """The worker of tests/test_gpu_parity.py::test_engines_of_several_processes_share_one_gpu, run over the kernels' host build."""
+    check_shared_device_run("engine_host", nprocs=3, reps=2, names=["cum_f64_ab_sim1", "d2q9_srt_f64_ab_cavity"], tol=1e-12)
