@@ -251,7 +251,9 @@ int lbmx_set_iterations(lbmx_engine* e, int64_t it); /* checkpoint restore: pari
 /* the NaN scan of State::AfterSimUpdate (state.hpp:1166-1188): OR over rho != rho of the macro array */
 int lbmx_has_nan(lbmx_engine* e, int32_t* flag);
 
-/* escape hatch mirroring block.data (lbm_block.hpp:583-593) */
+/* escape hatch mirroring block.data (lbm_block.hpp:583-593).  The engine works on its own non-blocking streams: call lbmx_sync()
+ * before touching these arrays from other streams (the legacy default stream included), and finish that work before the next
+ * lbmx_step / upload / download. */
 int lbmx_get_device_ptrs(lbmx_engine* e, lbmx_ptrs* out);
 
 /* Introspection for the measurement harness -------------------------------------------------------------------------------- */
