@@ -267,3 +267,105 @@ def check_shared_device_run(runner, nprocs, reps, names, tol):
 def test_concurrent_processes_over_the_host_kernels(fast_lib):
     """The worker of tests/test_gpu_parity.py::test_engines_of_several_processes_share_one_gpu, run over the kernels' host build."""
     check_shared_device_run("engine_host", nprocs=3, reps=2, names=["cum_f64_ab_sim1", "d2q9_srt_f64_ab_cavity"], tol=1e-12)
+
+
+# ---- the sweep of tests/test_oracle_vs_reference.py (every operator x equilibrium x precision x streaming pattern over random maps with
+#      every cell type; macro and inflow flavours; the ghost-plane rule), with the kernels' host build in the reference's place ----------
+from test_oracle_vs_reference import COMBOS_3D  # noqa: E402
+
+
+def run_host_and_port(d, m, p, nsteps, per_step=True, prepare=None):
+    """Both from the port's initial state (as the GPU tests upload it); returns [(df_a, df_b, macro)] for engine_host and port."""
+    df0 = lc.noisy_df(d, O.Oracle(d, "port") if d.ox == 0 else O.Oracle(O.Desc(**{**d.__dict__, "ox": 0, "nproc": 1, "X": d.X + 2 * d.ox}), "port"), seed=11)
+    out = []
+    for kind in ("engine_host", "port"):
+        orc = O.Oracle(d, kind)
+        a = df0.reshape(d.new_df().shape).copy()
+        b = a.copy()
+        mac = d.new_macro()
+        if prepare:
+            prepare(mac)
+        p.stat_counter = 0
+        if d.macro != O.MACRO_VOID:
+            orc.initial_macro(p, a, mac)
+        if per_step:
+            for it in range(nsteps):
+                p.stat_counter = it
+                orc.step(p, a, b, mac, m, it, 1, 1)
+        else:
+            orc.step(p, a, b, mac, m, 0, nsteps, 1)
+        out.append((a, b, mac))
+    p.stat_counter = 0
+    return out
+
+
+def assert_host_equals_port(pair, d, what):
+    (ha, hb, hm), (pa, pb, pm) = pair
+    cur_is_a = d.streaming == O.AA
+    _bit_exact(ha, pa, what + ": df_a")
+    if not cur_is_a:
+        _bit_exact(hb, pb, what + ": df_b")
+    if d.macro != O.MACRO_VOID:
+        _bit_exact(hm, pm, what + ": macro")
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+@pytest.mark.parametrize("coll,eq", COMBOS_3D)
+def test_d3q27_random_zoo_on_the_host(strict_lib, coll, eq, streaming, prec):
+    d = O.Desc(lattice=O.D3Q27, coll=coll, eq=eq, streaming=streaming, precision=prec, X=9, Y=8, Z=7)
+    m = lc.map_random_ab(d) if streaming == O.AB else lc.map_random_aa(d)
+    p = O.Params(lbmViscosity=0.013, fx=3e-5, fy=-2e-5, fz=1e-5, inflow_vx=0.04, inflow_vy=0.01, inflow_vz=-0.02)
+    assert_host_equals_port(run_host_and_port(d, m, p, 4), d, f"coll={coll} eq={eq} st={streaming} prec={prec}")
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+@pytest.mark.parametrize("coll", [O.SRT, O.CLBM])
+def test_d2q9_random_zoo_on_the_host(strict_lib, coll, streaming, prec):
+    d = O.Desc(lattice=O.D2Q9, coll=coll, eq=O.EQ_STD, streaming=streaming, precision=prec, X=13, Y=11, Z=1)
+    m = lc.map_random_ab(d) if streaming == O.AB else lc.map_random_aa(d)
+    p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.05, inflow_vy=-0.01)
+    assert_host_equals_port(run_host_and_port(d, m, p, 4), d, f"2d coll={coll} st={streaming} prec={prec}")
+
+
+@pytest.mark.parametrize("macro,inflow", [(O.MACRO_VOID, O.INFLOW_CONST), (O.MACRO_MEAN, O.INFLOW_CONST), (O.MACRO_DEFAULT, O.INFLOW_PROFILE_YZ), (O.MACRO_DEFAULT, O.INFLOW_NONE)])
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+def test_macro_and_inflow_flavours_on_the_host(strict_lib, macro, inflow, prec):
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AB, macro=macro, inflow=inflow, precision=prec, X=8, Y=7, Z=6)
+    m = lc.map_random_ab(d, seed=3)
+    prof = (0.05 * np.random.RandomState(5).random_sample((d.Z, d.Y))).astype(d.dtype)
+    p = O.Params(lbmViscosity=0.004, fx=1e-5, inflow_vx=0.03, vx_profile=prof if inflow == O.INFLOW_PROFILE_YZ else None)
+    assert_host_equals_port(run_host_and_port(d, m, p, 5), d, f"macro={macro} inflow={inflow} prec={prec}")
+
+
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+@pytest.mark.parametrize("gates", [0, O.GATE_MEANS, O.GATE_FLUCS, O.GATE_MEANS | O.GATE_FLUCS])
+def test_d2q9_with_mean_macro_on_the_host(strict_lib, gates, streaming, prec):
+    d = O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=streaming, macro=O.MACRO_WITH_MEAN_2D, inflow=O.INFLOW_PARABOLIC_Y, precision=prec, X=13, Y=11, Z=1)
+    m = lc.map_random_ab(d) if streaming == O.AB else lc.map_random_aa(d)
+    p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.07, inflow_vy=1.0, inflow_vz=0.125, macro_gates=gates)
+
+    def frozen_mean(mac):
+        mac[5:7] = (0.01 * np.random.RandomState(3).standard_normal(mac[5:7].shape)).astype(d.dtype)
+
+    assert_host_equals_port(run_host_and_port(d, m, p, 5, per_step=False, prepare=frozen_mean), d, f"with-mean gates={gates} st={streaming} prec={prec}")
+
+
+@pytest.mark.parametrize("macro", [O.MACRO_VOID, O.MACRO_MEAN])
+def test_d2q9_macro_flavours_on_the_host(strict_lib, macro):
+    d = O.Desc(lattice=O.D2Q9, coll=O.CLBM, eq=O.EQ_STD, streaming=O.AB, macro=macro, X=10, Y=9, Z=1)
+    m = lc.map_random_ab(d, seed=4)
+    p = O.Params(lbmViscosity=0.01, fx=1e-5, inflow_vx=0.03)
+    assert_host_equals_port(run_host_and_port(d, m, p, 5), d, f"2d macro={macro}")
+
+
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+def test_ghost_plane_rule_on_the_host(strict_lib, streaming):
+    """nproc > 1 index rule with one ghost x-plane per side (kernels.h:21-29,39-48): no wrapping in x."""
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, X=6, Y=8, Z=8, ox=1, nproc=2)
+    m = lc.map_duct_periodic_x(d)
+    m[0], m[-1] = m[-2], m[1]  # ghost map planes = periodic neighbours
+    p = O.Params(lbmViscosity=0.01, fx=1e-5)
+    assert_host_equals_port(run_host_and_port(d, m, p, 2), d, f"ghost st={streaming}")
