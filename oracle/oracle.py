@@ -136,9 +136,9 @@ def _path(kind: str, streaming: int, fast: bool) -> str:
     if kind == "port":
         return os.path.join(HERE, f"liboracle_port{suf}.so")
     if kind == "engine_host":
-        # not a checker: the engine's CUDA kernels compiled for the host (tools/engine_host.cpp) behind this same C interface, so that the
+        # not a checker: the engine's CUDA kernels compiled for the host (tests/host_harness/engine_host.cpp) behind this same C interface, so that the
         # tests can run them against the checkers without a GPU.  fast = the default arithmetic, otherwise the parity arithmetic.
-        return os.path.join(os.path.dirname(HERE), "tools", "bin", f"libengine_host{suf}.so")
+        return os.path.join(os.path.dirname(HERE), "tests", "host_harness", "bin", f"libengine_host{suf}.so")
     raise ValueError(kind)
 
 

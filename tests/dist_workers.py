@@ -24,7 +24,7 @@ def _init(rank, world, port, backend):
 
 def gloo_slab_worker(rank, world, port, case_name, outdir, kind="port"):
     """CPU: one slab per process, stepped by the CPU checker (`kind` = "port") or by the engine's own kernels compiled for the host
-    (`kind` = "engine_host", tools/engine_host.cpp); halo planes travel through torch.distributed (gloo) exactly as lbmx_halo_plan says."""
+    (`kind` = "engine_host", tests/host_harness/engine_host.cpp); halo planes travel through torch.distributed (gloo) exactly as lbmx_halo_plan says."""
     import torch
 
     import golden_cases as gc

@@ -17,7 +17,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../oracle/oracle_api.h"
+#include "../../oracle/oracle_api.h"
 
 #ifndef HK_MAIN
 // ---- what kernels.cuh needs from the CUDA language ----------------------------------------------------------------------------
@@ -88,7 +88,7 @@ inline int atomicOr(int* p, int v)
 	#ifndef LBMX_STRICT
 		#define LBMX_STRICT 1
 	#endif
-	#include "../tnl_lbm_b200/csrc/kernels.cuh"
+	#include "../../tnl_lbm_b200/csrc/kernels.cuh"
 using namespace lbmx;
 
 namespace {

@@ -12,8 +12,8 @@ using std::sqrt;
 #ifndef LBMX_STRICT
 #define LBMX_STRICT 1
 #endif
-#include "../tnl_lbm_b200/csrc/collide.cuh"
-#include "../oracle/oracle_api.h"
+#include "../../tnl_lbm_b200/csrc/collide.cuh"
+#include "../../oracle/oracle_api.h"
 using namespace lbmx;
 template <typename R, int KIND>
 int run(int coll, int eq, int prec)

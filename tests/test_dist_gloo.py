@@ -22,7 +22,7 @@ def free_port():
 @pytest.mark.parametrize("case_name", ["duct_ab", "duct_aa"])
 def test_two_process_gloo_slabs(case_name, kind):
     """kind = "engine_host": each process steps its slab with the engine's own CUDA kernels compiled for the host (parity arithmetic,
-    tools/engine_host.cpp) -- the kernels' ghost-plane rule and the halo plan across two processes, without a GPU."""
+    tests/host_harness/engine_host.cpp) -- the kernels' ghost-plane rule and the halo plan across two processes, without a GPU."""
     import torch.multiprocessing as mp
 
     import dist_workers as W

@@ -1,5 +1,5 @@
 """The engine's CUDA kernels themselves -- k_bulk, k_boundary, k_set_equilibrium, k_initial_macro of tnl_lbm_b200/csrc/kernels.cuh with
-all they include -- compiled for the HOST (tools/engine_host.cpp supplies the handful of CUDA built-ins they use) and run thread by
+all they include -- compiled for the HOST (tests/host_harness/engine_host.cpp supplies the handful of CUDA built-ins they use) and run thread by
 thread over the grid the engine launches, on every golden case:
 
   * parity arithmetic (LBMX_STRICT=1, -ffp-contract=off): bit-identical to the CPU restatement of the reference and to the committed
@@ -9,7 +9,7 @@ thread over the grid the engine launches, on every golden case:
 
 What this covers beyond tests/test_operators_on_host.py (per-cell operators on a periodic box): streaming offsets of all three
 modes, speculative wrapped loads and the A-B face re-load, cells per thread, the invariant division, the boundary list and the
-whole cell-type dispatch, Bouzidi links, inflow profiles, every macro mode.  tools/engine_host.cpp is a test tool; the product has
+whole cell-type dispatch, Bouzidi links, inflow profiles, every macro mode.  tests/host_harness/engine_host.cpp is a test tool; the product has
 no CPU path (tests/test_abi.py::test_no_cpu_fallback_without_a_gpu)."""
 from __future__ import annotations
 
@@ -28,8 +28,8 @@ from tnl_lbm_b200.build import FAMILIES
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-SRC = os.path.join(ROOT, "tools", "engine_host.cpp")
-BIN = os.path.join(ROOT, "tools", "bin")
+SRC = os.path.join(ROOT, "tests", "host_harness", "engine_host.cpp")
+BIN = os.path.join(ROOT, "tests", "host_harness", "bin")
 KIND_NUMBER = {"K_CUM": 0, "K_SRT": 1, "K_BGK": 2, "K_MRT": 3, "K_CLBM": 4, "K_SRT_MF": 5, "K_CUM_2017": 10, "K_CUM_AALIAS": 11, "K_CUM_2017_AALIAS": 12,
                **{f"K_KBC_{g}{i}": 13 + 4 * k + i - 1 for k, g in enumerate("NC") for i in (1, 2, 3, 4)}}
 TOL = {O.F64: 1e-12, O.F32: 1e-5}

@@ -1,6 +1,6 @@
 """The per-cell operators of the CUDA engine (tnl_lbm_b200/csrc/collide*.cuh) compiled for the HOST with g++ -ffp-contract=off and run
 against the CPU restatement on a periodic box: in parity arithmetic (LBMX_STRICT=1) every operator must be bit-identical -- the same
-check the GPU tests make, available without a GPU.  tools/host_strict_check.cpp is the harness."""
+check the GPU tests make, available without a GPU.  tests/host_harness/host_strict_check.cpp is the harness."""
 import os
 import re
 import subprocess
@@ -18,7 +18,7 @@ pytestmark = pytest.mark.skipif(not O.available("port"), reason="oracle port not
 def _build_and_run(strict: bool):
     with tempfile.TemporaryDirectory() as tmp:
         exe = os.path.join(tmp, "check")
-        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", f"-DLBMX_STRICT={1 if strict else 0}", os.path.join(ROOT, "tools", "host_strict_check.cpp"), "-o", exe,
+        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", f"-DLBMX_STRICT={1 if strict else 0}", os.path.join(ROOT, "tests", "host_harness", "host_strict_check.cpp"), "-o", exe,
                f"-L{ROOT}/oracle", "-loracle_port", f"-Wl,-rpath,{ROOT}/oracle"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
