@@ -1,7 +1,12 @@
 #!/usr/bin/env python
-"""Every golden case once through the C ABI, in default and in parity arithmetic, plus a two-batch graph-replay run -- the workload
-tools/sanitize.sh puts under compute-sanitizer (memcheck / initcheck).  Results are still compared with the CPU restatement, so a run
-that the sanitizer slowed down is also a run that was checked."""
+"""Every golden case once through the C ABI, in default and in parity arithmetic, plus a two-batch graph-replay run -- the workload to put
+under compute-sanitizer on a GPU box:
+
+    compute-sanitizer --tool memcheck  python tests/sanitize_cases.py [case-name substrings]
+    compute-sanitizer --tool initcheck python tests/sanitize_cases.py cum_f64
+
+Results are still compared with the CPU restatement, so a run that the sanitizer slowed down is also a run that was checked.
+(Not collected by pytest: no test_ prefix.)"""
 import os
 import sys
 
