@@ -369,3 +369,14 @@ def test_ghost_plane_rule_on_the_host(strict_lib, streaming):
     m[0], m[-1] = m[-2], m[1]  # ghost map planes = periodic neighbours
     p = O.Params(lbmViscosity=0.01, fx=1e-5)
     assert_host_equals_port(run_host_and_port(d, m, p, 2), d, f"ghost st={streaming}")
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 5, 1), (3, 1, 2), (2, 33, 3), (5, 129, 2), (4, 7, 131)])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+def test_degenerate_periodic_lattices_on_the_host(strict_lib, shape, streaming):
+    """One-cell axes (a cell is its own neighbour), Y = 1 (no invariant division) and rows that are not multiples of the warp / CTA
+    width, from a noisy state: the shapes of tests/test_gpu_physics_and_edges.py::test_ragged_and_degenerate_lattices, bit for bit."""
+    X, Y, Z = shape
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, X=X, Y=Y, Z=Z)
+    p = O.Params(lbmViscosity=0.01, fx=1e-5, fy=-2e-5, fz=3e-5)
+    assert_host_equals_port(run_host_and_port(d, lc.map_periodic(d), p, 6), d, f"shape={shape} st={streaming}")
