@@ -446,3 +446,35 @@ def test_random_sweep_in_default_arithmetic_on_the_host(fast_lib, streaming):
         assert err <= TOL[d.precision], f"trial {trial}: {d}: {err:.3e}"
         checked += 1
     assert checked >= 130
+
+
+def test_random_sweep_of_the_d3q19_kernels_on_the_host(fast_lib):
+    """D3Q19 (SRT, MRT_LES; no reference, parity unpinned): the kernels' host build against this repository's independent CPU
+    implementation over random shapes, maps with every cell type, macro flavours, both streaming patterns and precisions."""
+    rs = np.random.RandomState(5)
+    checked = 0
+    for trial in range(80):
+        streaming = (O.AB, O.AA)[rs.randint(2)]
+        aa = streaming == O.AA
+        lo = 3 if aa else 1
+        d = O.Desc(lattice=O.D3Q19, coll=(O.SRT, O.MRT_LES)[rs.randint(2)], eq=O.EQ_STD, streaming=streaming, precision=(O.F64, O.F32)[rs.randint(2)],
+                   X=int(rs.randint(lo, 7)), Y=int(rs.randint(lo, 40)), Z=int(rs.randint(lo, 12)), macro=(O.MACRO_DEFAULT, O.MACRO_MEAN, O.MACRO_VOID)[rs.randint(3)])
+        p = O.Params(lbmViscosity=0.013, fx=3e-5, fy=-2e-5, fz=1e-5, inflow_vx=0.04, inflow_vy=0.01, inflow_vz=-0.02)
+        seed, share = int(rs.randint(1 << 30)), float(rs.rand())
+        m = lc.map_random_aa(d, seed=seed, frac_special=0.6 * share) if aa else lc.map_random_ab(d, seed=seed, frac_special=share)
+        port, host = O.Oracle(d, "port"), O.Oracle(d, "engine_host", fast=True)
+        df0 = lc.noisy_df(d, port, seed=11)
+        nsteps, res = int(rs.randint(1, 6)), []
+        for orc in (host, port):
+            a, mac = df0.copy(), d.new_macro()
+            b = a.copy()
+            for it in range(nsteps):
+                p.stat_counter = it
+                orc.step(p, a, b, mac, m, it, 1, 1)
+            res.append(a if (aa or nsteps % 2 == 0) else b)
+        if not np.isfinite(res[1]).all():
+            continue
+        err = lc.rel_err_df(res[0], res[1], d)
+        assert err <= TOL[d.precision], f"trial {trial}: {d}: {err:.3e}"
+        checked += 1
+    assert checked >= 70
