@@ -509,3 +509,21 @@ def test_random_sweep_under_the_ghost_plane_rule_on_the_host(strict_lib):
         _bit_exact(hm[:, 1:-1], pm[:, 1:-1], what + ": macro")
         checked += 1
     assert checked >= 140
+
+
+def test_random_sweep_of_the_bouzidi_links_on_the_host(strict_lib):
+    """D2Q9 GEO_FLUID_NEAR_WALL (d2q9/bc.h:61-87,140-167) on random shapes and maps with ~30 % near-wall cells, coefficients in
+    [-0.8, 1.2] for all eight links (and without a coefficient array: every link reads -1), both operators and precisions."""
+    rs = np.random.RandomState(21)
+    checked = 0
+    for trial in range(120):
+        d = O.Desc(lattice=O.D2Q9, coll=(O.SRT, O.CLBM)[rs.randint(2)], eq=O.EQ_STD, streaming=O.AB, precision=(O.F64, O.F32)[rs.randint(2)], X=int(rs.randint(1, 9)),
+                   Y=int(rs.randint(1, 150)), Z=1, macro=(O.MACRO_DEFAULT, O.MACRO_MEAN, O.MACRO_VOID)[rs.randint(3)])
+        m, bz = lc.map_and_coeffs_bouzidi(d, seed=int(rs.randint(1 << 30)))
+        p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.05, inflow_vy=-0.01, bouzidi=bz if rs.rand() < 0.8 else None)
+        pair = run_host_and_port(d, m, p, int(rs.randint(1, 6)))
+        if not all(np.isfinite(x).all() for x in pair[1]):
+            continue
+        assert_host_equals_port(pair, d, f"trial {trial}: {d}")
+        checked += 1
+    assert checked >= 110
