@@ -527,3 +527,22 @@ def test_random_sweep_of_the_bouzidi_links_on_the_host(strict_lib):
         assert_host_equals_port(pair, d, f"trial {trial}: {d}")
         checked += 1
     assert checked >= 110
+
+
+def test_random_sweep_with_a_profile_inflow_on_the_host(strict_lib):
+    """NSE_Data_XProfileInflow (sim_NSE/sim_2.cu:16-33): inflow cells anywhere in random maps read vx from a random (y, z) profile."""
+    rs = np.random.RandomState(33)
+    checked = 0
+    for trial in range(100):
+        coll, eq = COMBOS_3D[rs.randint(len(COMBOS_3D))]
+        d = O.Desc(coll=coll, eq=eq, streaming=O.AB, inflow=O.INFLOW_PROFILE_YZ, precision=(O.F64, O.F32)[rs.randint(2)], X=int(rs.randint(1, 7)), Y=int(rs.randint(1, 40)),
+                   Z=int(rs.randint(1, 12)))
+        prof = (0.05 * rs.random_sample((d.Z, d.Y))).astype(d.dtype)
+        p = O.Params(lbmViscosity=0.004, fx=1e-5, vx_profile=prof)
+        m = lc.map_random_ab(d, seed=int(rs.randint(1 << 30)), frac_special=float(rs.rand()))
+        pair = run_host_and_port(d, m, p, int(rs.randint(1, 6)))
+        if not all(np.isfinite(x).all() for x in pair[1]):
+            continue
+        assert_host_equals_port(pair, d, f"trial {trial}: {d}")
+        checked += 1
+    assert checked >= 90
