@@ -55,7 +55,7 @@ class Ptrs(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("kernel_launches", "halo_bytes_sent", "boundary_cells", "bulk_cells")] + [(n, C.c_int32) for n in ("bulk_regs", "boundary_regs", "bulk_block", "halo_peer_memory")] + [
-        ("aa_cells_reaching_outside", C.c_int64)]
+        ("aa_cells_reaching_outside", C.c_int64), ("tma_launches", C.c_int64)]
 
 
 class HaloMsg(C.Structure):

@@ -7,6 +7,7 @@
 // No CPU fallback anywhere: without a CUDA device every call fails with LBMX_ERR_CUDA.
 #include "../../include/lbmx.h"
 #include "kernels.cuh"
+#include "tma_host.h"
 
 #include <cuda_runtime.h>
 #include <cub/device/device_select.cuh>
@@ -216,6 +217,7 @@ struct lbmx_engine
 	uint64_t state_version = 1, pair_version = 0;  // state_version: bumped by whatever changes the kernel parameters
 	int pair_out_mode = -1, pair_launches = 0;
 	bool graphs_enabled = true;
+	bool in_head_step = false;	// step_impl recursing for the odd head of a graph-replayed batch
 	// peer-memory halo exchange (one node, NVLink): the neighbours' distribution arrays and arrival counters mapped through CUDA IPC
 	struct Peer
 	{
@@ -226,9 +228,17 @@ struct lbmx_engine
 		bool mapped = false;
 	};
 	Peer peer_left, peer_right;
-	long long* my_flags = nullptr;	// [0]: exchanges that arrived from the left, [1]: from the right
+	// my_flags[0], [1]: exchanges that arrived from the left / right neighbour; [3], [4]: the last step batch the left / right neighbour
+	// has declared itself ready to receive for (its arrays are no longer written from the host side)
+	long long* my_flags = nullptr;
 	bool p2p = false;
 	int64_t xcount = 0;	 // halo exchanges enqueued so far (identical on every rank)
+	int64_t batch = 0, batch_awaited = 0;  // lbmx_step calls so far (identical on every rank); the last one whose readiness was awaited
+	// set by a halo wait that gave up (a neighbour that stopped stepping): host-mapped, so every later call can read it without a
+	// stream synchronisation and fail -- the fields computed after it are stale
+	long long* h_halo_error = nullptr;
+	long long* d_halo_error = nullptr;
+	long long halo_timeout_ns = 120ll * 1000 * 1000 * 1000;
 	double* eq_stage[2] = {nullptr, nullptr};  // staging sets of lbmx_df_set_equilibrium_field
 	int64_t eq_stage_cells = 0;
 	ncclComm_t comm = nullptr;
@@ -236,6 +246,10 @@ struct lbmx_engine
 	StepKernels<float> kf{};
 	StepKernels<double> kd{};
 	lbmx_stats stats{};
+	// k_bulk_tma (A-A only): tensor map over df[0], tile geometry, and which step parities go through it
+	CUtensorMap tmap{};
+	int tile_y = 0, tile_y_shift = 0;
+	bool use_tma[3] = {false, false, false};  // by StreamMode
 
 	bool f64() const { return d.precision == LBMX_F64; }
 	bool aa() const { return d.streaming == LBMX_STREAM_AA; }
@@ -268,6 +282,8 @@ KParams<R> make_params(const lbmx_engine* e)
 	}
 	p.ydiv_mul = e->ydiv_mul;
 	p.ydiv_shift = e->ydiv_shift;
+	p.tile_y = e->tile_y;
+	p.tile_y_shift = e->tile_y_shift;
 	p.x_begin = 0;
 	p.nb_begin = 0;
 	p.nb_end = (int) e->nb;
@@ -292,6 +308,9 @@ KParams<R> make_params(const lbmx_engine* e)
 }
 
 constexpr int BLOCK = LBMX_BULK_BLOCK;
+#ifndef LBMX_TMA_DEFAULT
+	#define LBMX_TMA_DEFAULT "0"
+#endif
 
 // launch the two step kernels over local planes [xb, xe): the bulk kernel on `st`, the boundary-list kernel on `st_list` (default:
 // the same stream).  Within one step the two kernels touch disjoint cells and every population slot has exactly one writer, so
@@ -306,9 +325,18 @@ int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, 
 	p.x_begin = xb;
 	p.nb_begin = (int) e->plane_start[xb];
 	p.nb_end = (int) e->plane_start[xe];
-	const int per_cta = BLOCK * K.cpt[p.stream];
-	dim3 grid((unsigned) ((e->YZ + per_cta - 1) / per_cta), (unsigned) (xe - xb));
-	K.bulk[p.stream]<<<grid, BLOCK, 0, st>>>(p);
+	if (e->use_tma[p.stream]) {
+		// one CTA per tile of tile_y x (128 / tile_y) cells; the populations travel as tensor boxes (kernels_tma.cuh)
+		const int tz = tma::TILE / e->tile_y;
+		dim3 grid((unsigned) ((e->Y / e->tile_y) * ((e->Z + tz - 1) / tz)), (unsigned) (xe - xb));
+		K.bulk_tma[p.stream]<<<grid, tma::TILE, 0, st>>>(p, e->tmap);
+		e->stats.tma_launches++;
+	}
+	else {
+		const int per_cta = BLOCK * K.cpt[p.stream];
+		dim3 grid((unsigned) ((e->YZ + per_cta - 1) / per_cta), (unsigned) (xe - xb));
+		K.bulk[p.stream]<<<grid, BLOCK, 0, st>>>(p);
+	}
 	e->stats.kernel_launches++;
 	const int nbl = p.nb_end - p.nb_begin;
 	if (nbl > 0) {
@@ -332,20 +360,28 @@ __global__ void k_signal_arrival(long long* peer_counter, long long value)
 	*(volatile long long*) peer_counter = value;
 	__threadfence_system();
 }
-__global__ void k_await_arrival(const long long* from_left, const long long* from_right, long long expected, long long* error_word)
+__device__ __forceinline__ long long wall_ns()
 {
-	const long long t0 = clock64();
-	const long long limit = 40ll * 1000 * 1000 * 1000;	// ~20 s at 2 GHz: a lost neighbour must not hang the GPU
+	long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+// limit_ns <= 0: wait for ever, as an MPI receive would.  Otherwise a neighbour that is later than limit_ns (wall clock) makes the
+// wait give up: the error word (host-mapped) is set, stays set, and every later call on this engine fails with LBMX_ERR_STATE.
+__global__ void k_await_arrival(const long long* from_left, const long long* from_right, long long expected, long long* error_word, long long limit_ns, long long code)
+{
+	const long long t0 = wall_ns();
 	for (int side = 0; side < 2; side++) {
 		const long long* c = side == 0 ? from_left : from_right;
 		if (! c)
 			continue;
 		while (*(volatile const long long*) c < expected) {
-			if (clock64() - t0 > limit) {
-				*error_word = expected;	 // reported by lbmx_sync
+			if (limit_ns > 0 && wall_ns() - t0 > limit_ns) {
+				*(volatile long long*) error_word = code;
+				__threadfence_system();
 				return;
 			}
-			__nanosleep(100);
+			__nanosleep(200);
 		}
 	}
 	__threadfence_system();
@@ -382,6 +418,15 @@ int exchange(lbmx_engine* e, void* arr)
 		// neighbour's arrival counter.  Which of my arrays `arr` is tells which of the neighbour's it goes to (same rotation).
 		const int which = arr == e->df[0] ? 0 : 1;
 		e->xcount++;
+		if (e->batch_awaited < e->batch) {
+			// One-sided stores need a receiver that has stopped writing its arrays from the host side (initialisation, uploads, a
+			// restored checkpoint): every rank announces "ready for batch b" on its compute stream when lbmx_step is entered, i.e.
+			// after everything it did before; the first push of the batch waits for both neighbours' announcements.
+			k_await_arrival<<<1, 1, 0, e->s_comm>>>(e->peer_left.mapped ? e->my_flags + 3 : nullptr, e->peer_right.mapped ? e->my_flags + 4 : nullptr, (long long) e->batch,
+													e->d_halo_error, e->halo_timeout_ns, 2);
+			e->stats.kernel_launches++;
+			e->batch_awaited = e->batch;
+		}
 		for (int k = 0; k < 2; k++) {
 			const lbmx_halo_msg& m = msgs[k];
 			lbmx_engine::Peer& peer = m.to_right ? e->peer_right : e->peer_left;
@@ -425,7 +470,8 @@ static void await_halo(lbmx_engine* e, cudaStream_t st)
 {
 	if (! e->p2p)
 		return;
-	k_await_arrival<<<1, 1, 0, st>>>(e->peer_left.mapped ? e->my_flags : nullptr, e->peer_right.mapped ? e->my_flags + 1 : nullptr, (long long) e->xcount, e->my_flags + 2);
+	k_await_arrival<<<1, 1, 0, st>>>(e->peer_left.mapped ? e->my_flags : nullptr, e->peer_right.mapped ? e->my_flags + 1 : nullptr, (long long) e->xcount, e->d_halo_error,
+									 e->halo_timeout_ns, 1);
 	e->stats.kernel_launches++;
 }
 
@@ -481,6 +527,15 @@ template <typename R>
 int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 {
 	const bool ghosts = e->ox > 0;
+	if (e->p2p && ! e->in_head_step) {
+		// "ready for batch b": see exchange().  On the compute stream, behind every upload / initialisation kernel of this rank.
+		e->batch++;
+		if (e->peer_left.mapped)
+			k_signal_arrival<<<1, 1, 0, e->s_main>>>(e->peer_left.flags + 4, (long long) e->batch);	 // I am my left neighbour's right neighbour
+		if (e->peer_right.mapped)
+			k_signal_arrival<<<1, 1, 0, e->s_main>>>(e->peer_right.flags + 3, (long long) e->batch);
+		e->stats.kernel_launches += 2;
+	}
 	CU(cudaEventRecord(e->ev_main, e->s_main));	 // everything enqueued on the compute stream so far (uploads, initialisation) precedes the side streams' work
 	int64_t first_plain = 0;
 	// Small single-slab lattices (steps of tens of microseconds): replay step pairs as a graph.  Pairs start at even iterations (A-A
@@ -497,7 +552,9 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 				const int saved_counter = e->prm.stat_counter;
 				if (last_writes)
 					e->d.macro_policy = LBMX_MACRO_NEVER;  // not the last step of the caller's batch
+				e->in_head_step = true;
 				const int rc1 = step_impl<R>(e, K, 1);
+				e->in_head_step = false;
 				e->d = saved;
 				e->prm.stat_counter = saved_counter;
 				if (rc1)
@@ -677,6 +734,20 @@ bool pick_kernels(lbmx_engine* e)
 	return false;
 }
 
+// A halo wait that gave up leaves the ghost planes stale: whatever was computed afterwards is wrong.  The word is host-mapped and
+// sticky; every entry point that advances or reads the state checks it (after its own stream synchronisation where it has one).
+int halo_error(const lbmx_engine* e, const char* who)
+{
+	if (! e->h_halo_error)
+		return LBMX_OK;
+	const long long code = *(volatile const long long*) e->h_halo_error;
+	if (code == 0)
+		return LBMX_OK;
+	return fail(LBMX_ERR_STATE, std::string(who) + ": the peer-memory halo exchange gave up waiting for a neighbour (" +
+									(code == 2 ? "it never entered the same lbmx_step batch" : "its planes of an earlier step never arrived") + ", limit " +
+									std::to_string(e->halo_timeout_ns / 1000000000ll) + " s, LBMX_HALO_TIMEOUT_S); the fields of this engine are stale from that step on");
+}
+
 // host <-> device copies of [ncomp][X(+2ox)][Z][Y] arrays with or without the ghost planes
 int copy_components(lbmx_engine* e, void* dev, void* host, int ncomp, size_t elem, bool with_ghosts, bool to_device)
 {
@@ -691,7 +762,7 @@ int copy_components(lbmx_engine* e, void* dev, void* host, int ncomp, size_t ele
 		const size_t bytes = comp_dev * ncomp;
 		CU(to_device ? cudaMemcpyAsync(dev, host, bytes, kind, e->s_main) : cudaMemcpyAsync(host, dev, bytes, kind, e->s_main));
 		CU(cudaStreamSynchronize(e->s_main));
-		return LBMX_OK;
+		return halo_error(e, "lbmx copy");
 	}
 	const size_t comp_host = (size_t) e->X * e->YZ * elem;
 	const size_t skip = (size_t) e->ox * e->YZ * elem;
@@ -701,7 +772,7 @@ int copy_components(lbmx_engine* e, void* dev, void* host, int ncomp, size_t ele
 		CU(to_device ? cudaMemcpyAsync(dp, hp, comp_host, kind, e->s_main) : cudaMemcpyAsync(hp, dp, comp_host, kind, e->s_main));
 	}
 	CU(cudaStreamSynchronize(e->s_main));
-	return LBMX_OK;
+	return halo_error(e, "lbmx copy");
 }
 
 }  // namespace
@@ -924,6 +995,21 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 		CUX(cudaMemsetAsync(e->df_alloc[i], 0, df_bytes + 2 * e->df_guard, e->s_main));
 		e->df[i] = (char*) e->df_alloc[i] + e->df_guard;
 	}
+	if (e->aa()) {
+		// LBMX_TMA = 0 | even | odd | both: which A-A parities run k_bulk_tma (default: see DESIGN.md section 3.3)
+		const char* want = std::getenv("LBMX_TMA");
+		const std::string w = want ? want : LBMX_TMA_DEFAULT;
+		e->tile_y = tma_tile_y(e->Y, (int) e->rs);
+		std::string why;
+		if (w != "0" && e->tile_y > 0 && make_df_tensor_map(&e->tmap, e->df[0], (int) e->rs, e->Y, e->Z, e->X + 2 * e->ox, e->Q, e->tile_y, &why)) {
+			while ((1 << e->tile_y_shift) < e->tile_y)
+				e->tile_y_shift++;
+			e->use_tma[S_AA_EVEN] = w == "even" || w == "both";
+			e->use_tma[S_AA_ODD] = w == "odd" || w == "both";
+		}
+		else
+			e->tile_y = 0;
+	}
 	if (e->NM > 0) {
 		CUX(cudaMalloc(&e->macro, (size_t) e->NM * e->XYZ * e->rs));
 		CUX(cudaMemsetAsync(e->macro, 0, (size_t) e->NM * e->XYZ * e->rs, e->s_main));
@@ -963,6 +1049,8 @@ int lbmx_destroy(lbmx_engine* e)
 		g_nccl.CommDestroy(e->comm);
 	if (e->my_flags)
 		cudaFree(e->my_flags);
+	if (e->h_halo_error)
+		cudaFreeHost(e->h_halo_error);
 	for (void* p : {e->df_alloc[0], e->df_alloc[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs})
 		if (p)
 			cudaFree(p);
@@ -1040,8 +1128,15 @@ static int setup_peer_memory(lbmx_engine* e)
 	};
 	const char* mode = std::getenv("LBMX_HALO");
 	int ok = ! (mode && std::strcmp(mode, "nccl") == 0);
-	CU(cudaMalloc(&e->my_flags, 3 * sizeof(long long)));  // [0], [1]: arrival counters; [2]: set when a wait gave up
-	CU(cudaMemsetAsync(e->my_flags, 0, 3 * sizeof(long long), e->s_main));
+	CU(cudaMalloc(&e->my_flags, 8 * sizeof(long long)));  // [0], [1]: arrival counters; [3], [4]: the neighbours' ready-for-batch announcements
+	CU(cudaMemsetAsync(e->my_flags, 0, 8 * sizeof(long long), e->s_main));
+	if (! e->h_halo_error) {
+		CU(cudaHostAlloc((void**) &e->h_halo_error, sizeof(long long), cudaHostAllocMapped));
+		*e->h_halo_error = 0;
+		CU(cudaHostGetDevicePointer((void**) &e->d_halo_error, e->h_halo_error, 0));
+	}
+	if (const char* v = std::getenv("LBMX_HALO_TIMEOUT_S"))	 // 0: wait for ever (what an MPI receive does); default 120 s
+		e->halo_timeout_ns = (long long) (std::atof(v) * 1e9);
 	Packet mine{};
 	if (ok) {
 		ok = cudaIpcGetMemHandle(&mine.df[0], e->df_alloc[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, e->my_flags) == cudaSuccess;
@@ -1201,7 +1296,9 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	CU(cudaFree(d_counts));
 	// Under A-A such a cell reads, in place, populations that the cell to its left rewrites in the same step (the reference has the
 	// same race).  Keeping the boundary list strictly after the bulk kernel makes the outcome reproducible.
-	e->list_after_bulk = e->aa() && counts[(size_t) e->X] > 0;
+	// The same holds for A-A cells on a bare lattice face (counts[X + 1], the reference steps out of its array there): their
+	// stores land in slots other cells own.
+	e->list_after_bulk = e->aa() && (counts[(size_t) e->X] > 0 || counts[(size_t) e->X + 1] > 0);
 	e->plane_start.assign((size_t) e->X + 1, 0);
 	for (int64_t x = 0; x < e->X; x++)
 		e->plane_start[(size_t) x + 1] = e->plane_start[(size_t) x] + counts[(size_t) x];
@@ -1476,6 +1573,8 @@ int lbmx_step(lbmx_engine* e, int64_t nsteps)
 		return fail(LBMX_ERR_ARG, "lbmx_step: bad argument");
 	if (e->d.inflow == LBMX_INFLOW_PROFILE_YZ && ! e->profile)
 		return fail(LBMX_ERR_STATE, "lbmx_step: inflow profile selected but lbmx_set_inflow_profile was not called");
+	if (int rc = halo_error(e, "lbmx_step"))
+		return rc;
 	return step_dispatch(e, nsteps);
 }
 
@@ -1487,14 +1586,7 @@ int lbmx_sync(lbmx_engine* e)
 	CU(cudaStreamSynchronize(e->s_main));
 	CU(cudaStreamSynchronize(e->s_edge));
 	CU(cudaStreamSynchronize(e->s_comm));
-	if (e->p2p) {
-		long long gave_up = 0;
-		CU(cudaMemcpyAsync(&gave_up, e->my_flags + 2, sizeof(long long), cudaMemcpyDeviceToHost, e->s_main));
-		CU(cudaStreamSynchronize(e->s_main));
-		if (gave_up)
-			return fail(LBMX_ERR_STATE, "lbmx_sync: the peer-memory halo exchange waited 20 s for exchange " + std::to_string(gave_up) + " of a neighbour and gave up (a neighbour rank stopped stepping?)");
-	}
-	return LBMX_OK;
+	return halo_error(e, "lbmx_sync");
 }
 
 int lbmx_step_timed(lbmx_engine* e, int64_t nsteps, float* elapsed_ms)
@@ -1575,7 +1667,7 @@ int lbmx_has_nan(lbmx_engine* e, int32_t* flag)
 	CU(cudaMemcpyAsync(&h, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->s_main));
 	CU(cudaStreamSynchronize(e->s_main));
 	*flag = h;
-	return LBMX_OK;
+	return halo_error(e, "lbmx_has_nan");
 }
 
 int lbmx_get_device_ptrs(lbmx_engine* e, lbmx_ptrs* out)

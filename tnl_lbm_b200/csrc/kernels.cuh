@@ -37,6 +37,11 @@
 #ifndef LBMX_ST_HINT
 	#define LBMX_ST_HINT 1	// 0 plain, 1 st.global.cs, 2 st.global.cg, 3 st.global.wt
 #endif
+// macroscopic fields: written once per step and never read back by a step kernel (MACRO_Mean: read and written once), so they
+// should not take L2 lines from the populations either -- 0 plain, 1 streaming (ld.global.cs / st.global.cs)
+#ifndef LBMX_MACRO_HINT
+	#define LBMX_MACRO_HINT 1
+#endif
 
 namespace lbmx {
 
@@ -63,6 +68,7 @@ struct KParams
 	int nb_begin, nb_end; // boundary-list range handled by this launch
 	int wrap;		   // 1: the reference's nproc==1 rule (GEO_PERIODIC cells wrap), 0: ghost-plane rule
 	int profile_sy;
+	int tile_y, tile_y_shift;  // k_bulk_tma: cells of one row per CTA (power of two dividing Y) and its log2
 	int eq, inflow, stream, out_mode, stat_counter;
 	Phys<R> phys;
 	R in_vx, in_vy, in_vz;
@@ -208,6 +214,25 @@ LBMX_D void stream_out(const KParams<R>& p, const R (&f)[L::Q], int c, const Del
 }
 
 // ---- macroscopic output (d3q27/macro.h:50-171, d2q9/macro.h:49-140) ----
+template <typename R>
+LBMX_D R ld_macro(const R* ptr)
+{
+#if LBMX_MACRO_HINT == 1
+	return __ldcs(ptr);
+#else
+	return *ptr;
+#endif
+}
+template <typename R>
+LBMX_D void st_macro(R* ptr, R v)
+{
+#if LBMX_MACRO_HINT == 1
+	__stcs(ptr, v);
+#else
+	*ptr = v;
+#endif
+}
+
 template <typename L, typename R>
 LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 {
@@ -217,23 +242,23 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 	R* M = p.macro;
 	const long long S = p.XYZ;
 	const R v[3] = {vx, vy, vz};
-	M[c] = rho;
+	st_macro(M + c, rho);
 #pragma unroll
 	for (int a = 0; a < nd; a++)
-		M[(1 + a) * S + c] = v[a];
+		st_macro(M + ((1 + a) * S + c), v[a]);
 	if constexpr (nd == 2) {
 		// D2Q9_MACRO_WithMean (sim_2D/sim2d_2.cu:75-95): gated velocity sums, and fluctuation sums about a mean the host froze
 		if (p.out_mode >= OUT_WITH_MEAN_2D) {
 			if (p.out_mode & 1) {
-				M[3 * S + c] += vx;
-				M[4 * S + c] += vy;
+				st_macro(M + (3 * S + c), ld_macro(M + (3 * S + c)) + vx);
+				st_macro(M + (4 * S + c), ld_macro(M + (4 * S + c)) + vy);
 			}
 			if (p.out_mode & 2) {
-				const R dux = vx - M[5 * S + c];
-				const R duy = vy - M[6 * S + c];
-				M[7 * S + c] += sqrt(dux * dux + duy * duy);  // IEEE sqrt in R = the reference's sqrt(double) rounded to dreal
-				M[8 * S + c] += dux * dux;
-				M[9 * S + c] += duy * duy;
+				const R dux = vx - ld_macro(M + (5 * S + c));
+				const R duy = vy - ld_macro(M + (6 * S + c));
+				st_macro(M + (7 * S + c), ld_macro(M + (7 * S + c)) + sqrt(dux * dux + duy * duy));  // IEEE sqrt in R = the reference's sqrt(double) rounded to dreal
+				st_macro(M + (8 * S + c), ld_macro(M + (8 * S + c)) + dux * dux);
+				st_macro(M + (9 * S + c), ld_macro(M + (9 * S + c)) + duy * duy);
 			}
 			return;
 		}
@@ -245,11 +270,11 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 	R delta[3], delta_new[3];
 #pragma unroll
 	for (int a = 0; a < nd; a++) {
-		const R old = M[(1 + nd + a) * S + c];
+		const R old = ld_macro(M + ((1 + nd + a) * S + c));
 		delta[a] = v[a] - old;
 		const R now = old + delta[a] * denom;
 		delta_new[a] = v[a] - now;
-		M[(1 + nd + a) * S + c] = now;
+		st_macro(M + ((1 + nd + a) * S + c), now);
 	}
 	constexpr int np = nd == 3 ? 6 : 3;
 	constexpr int pa[6] = {0, 1, nd == 3 ? 2 : 0, 0, 0, 1};
@@ -257,7 +282,7 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 #pragma unroll
 	for (int i = 0; i < np; i++) {
 		const long long o = (long long) (1 + 2 * nd + i) * S + c;
-		M[o] = M[o] + delta_new[pa[i]] * delta[pb[i]];
+		st_macro(M + o, ld_macro(M + o) + delta_new[pa[i]] * delta[pb[i]]);
 	}
 }
 
@@ -657,12 +682,19 @@ __global__ void k_copy_planes(R* dst, const R* src, long long XYZ, int YZ, int n
 	dst[q * (dst_XYZ ? dst_XYZ : XYZ) + dst_plane * YZ + i] = src[q * XYZ + src_plane * YZ + i];
 }
 
+}  // namespace lbmx
+#include "kernels_tma.cuh"
+namespace lbmx {
+
 // launcher table filled by the per-family translation units ---------------------------------------------------------
 template <typename R>
 struct StepKernels
 {
 	void (*bulk[3])(const KParams<R>);	// by StreamMode
 	int cpt[3];						// cells per thread of the bulk kernels, by StreamMode
+#if defined(__CUDACC__)
+	void (*bulk_tma[3])(const KParams<R>, const CUtensorMap);  // by StreamMode; A-A only ([S_AB] stays null)
+#endif
 	void (*boundary)(const KParams<R>);
 	void (*initial_macro)(const KParams<R>);
 	void (*set_equilibrium)(R*, long long, long long, long long, int, const double*, const double*, const double*, const double*, double, double, double, double);
@@ -678,6 +710,11 @@ StepKernels<R> make_step_kernels()
 	k.cpt[S_AB] = bulk_cpt<L, R, S_AB>();
 	k.cpt[S_AA_EVEN] = bulk_cpt<L, R, S_AA_EVEN>();
 	k.cpt[S_AA_ODD] = bulk_cpt<L, R, S_AA_ODD>();
+#if defined(__CUDACC__)
+	k.bulk_tma[S_AB] = nullptr;
+	k.bulk_tma[S_AA_EVEN] = k_bulk_tma<L, KIND, R, S_AA_EVEN>;
+	k.bulk_tma[S_AA_ODD] = k_bulk_tma<L, KIND, R, S_AA_ODD>;
+#endif
 	k.boundary = k_boundary<L, KIND, R>;
 	k.initial_macro = k_initial_macro<L, R>;
 	k.set_equilibrium = k_set_equilibrium<L, R>;
