@@ -60,12 +60,56 @@ def pinned(shape, dtype):
 
 # ------------------------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons DURING the timed region.  Default: NVML in this process (one light query set every 50 ms from a
+    thread); --clock-sampler smi: an `nvidia-smi -lms` child as in /opt/skills/guides/B200_PROFILING.md; none: no sampling."""
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, how: str = "nvml"):
+        self.index, self.rows, self.proc, self.how, self.stop_flag, self.thread, self.smax = index, [], None, how, False, None, None
 
     def start(self):
+        if self.how == "none":
+            return
+        if self.how == "nvml":
+            try:
+                import pynvml
+
+                pynvml.nvmlInit()
+                # CUDA_VISIBLE_DEVICES may renumber: find the handle by the PCI bus id of the CUDA device
+                import torch
+
+                bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+                h = None
+                if bus is not None:
+                    for i in range(pynvml.nvmlDeviceGetCount()):
+                        hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                        if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                            h = hi
+                            break
+                if h is None:
+                    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                    phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+                    h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+                self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+                bits = [(pynvml.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"), (pynvml.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                        (pynvml.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"), (pynvml.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+
+                def pump():
+                    while not self.stop_flag:
+                        try:
+                            sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                            self.rows.append((time.perf_counter(), sm, [n for b, n in bits if mask & b]))
+                        except Exception:
+                            pass
+                        time.sleep(0.05)
+
+                self.thread = threading.Thread(target=pump, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.how = "smi"  # fall through to the child process
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -78,11 +122,22 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.how == "none":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled (--clock-sampler none)"]}
+        if self.how == "nvml":
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            sm, reasons = [], set()
+            for t, mhz, why in self.rows:
+                if t0 <= t <= t1 + 0.08:
+                    sm.append(mhz)
+                    reasons.update(why)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(reasons), "samples": len(sm), "how": "NVML, 50 ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, line in self.rows:
             if not (t0 <= t <= t1 + 0.15):
                 continue
@@ -92,10 +147,10 @@ class ClockSampler:
                 smax = float(parts[1])
             except Exception:
                 continue
-            for n, v in zip(names, parts[3:7]):
+            for n, v in zip(self.NAMES, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm), "how": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------------------------ CPU arm
@@ -145,6 +200,123 @@ def macro_every_step_run(a):
         return {"error": repr(ex)}
 
 
+# ------------------------------------------------------------------------------------------------------------------ multi-GPU parity leg
+def duct_map(Xg, x0, xl, S, out=None):
+    """sim_NSE/sim_2.cu:125-138, painted in that order: global x planes 0 and X-1 GEO_PERIODIC, GEO_WALL at y,z = 1 / N-2, GEO_NOTHING
+    at y,z = 0 / N-1 (cell types d3q27/bc.h:17-34: 0 fluid, 1 wall, 7 periodic, 8 nothing); local planes [x0, x0 + xl)."""
+    m = out if out is not None else np.empty((xl, S, S), dtype=np.int16)
+    m[...] = 0
+    if x0 == 0:
+        m[0] = 7
+    if x0 + xl == Xg:
+        m[xl - 1] = 7
+    m[:, 1, :] = 1
+    m[:, S - 2, :] = 1
+    m[:, :, 1] = 1
+    m[:, :, S - 2] = 1
+    m[:, 0, :] = 8
+    m[:, S - 1, :] = 8
+    m[:, :, 0] = 8
+    m[:, :, S - 1] = 8
+    return m
+
+
+def halo_parity(rank, N, local_rank, dist, torch, B, threads):
+    """CHECKER LEG, before any timing (SURVEY 8d cfg 4): the 256 x 64 x 64 miniature of the duct, 12 steps, A-A and A-B,
+    over the N ranks with each halo transport (peer-memory stores over NVLink, NCCL send/recv).  The slabs are gathered on rank 0 and must
+    be BIT-IDENTICAL to one slab with ghost planes and a self-exchange on rank 0's GPU, which in turn must agree to 1e-12 with the CPU
+    checker (oracle port under the reference's ghost-plane index rule, kernels.h:39-48, planes exchanged by hand as lbmx_halo_plan says).
+    Replaces nothing in the reference -- it pins what lbm.hpp:196-280 / lbm_block.hpp:428-442 do through TNL's synchroniser."""
+    X, S, STEPS = (256 if 256 % N == 0 else 32 * N), 64, 12
+    prm = dict(lbmViscosity=1e-3, fx=1e-5, fy=2e-6, fz=-1e-6)
+
+    def fields(x0, xl):
+        rho, vx, vy, vz = initial_fields(X, x0, xl, S, S)
+        return [np.ascontiguousarray(f) for f in (rho, vx, vy)] + [np.full((xl, S, S), vz)]
+
+    def run_engine(streaming, nranks, r, comm):
+        e = B.Engine(lattice=B.D3Q27, coll=B.CUM, eq=B.EQ_INV_CUM, streaming=streaming, macro=B.MACRO_DEFAULT, inflow=B.INFLOW_NONE, precision=B.F64, X=X, Y=S, Z=S,
+                     rank=r, nranks=nranks, device=local_rank, ghost_x=1, periodic_x=1, macro_policy=B.MACRO_LAST_STEP)
+        try:
+            if nranks > 1:
+                idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if r == 0:
+                    idbuf.copy_(torch.frombuffer(bytearray(B.comm_unique_id()), dtype=torch.uint8))
+                dist.broadcast(idbuf, 0)
+                e.comm_init(bytes(idbuf.cpu().numpy().tobytes()))
+            x0, xl = e.layout.x_offset, e.layout.X_local
+            e.map_upload(duct_map(X, x0, xl, S))
+            e.set_equilibrium_field(*fields(x0, xl))
+            e.set_params(**prm)
+            e.step(STEPS)
+            e.sync()
+            return e.df_download(0), e.macro_download(), e.stats().halo_peer_memory
+        finally:
+            e.close()
+
+    cases, worst = [], 0.0
+    for streaming, sname in ((B.AA, "AA"), (B.AB, "AB")):
+        one = None
+        for transport in ("peer_memory", "nccl"):
+            if transport == "nccl":
+                os.environ["LBMX_HALO"] = "nccl"
+            else:
+                os.environ.pop("LBMX_HALO", None)
+            df, mac, peer = run_engine(streaming, N, rank, True)
+            os.environ.pop("LBMX_HALO", None)
+            parts = [torch.empty_like(torch.from_numpy(df).cuda()) for _ in range(N)] if rank == 0 else None
+            dist.gather(torch.from_numpy(df).cuda(), parts, dst=0)
+            mparts = [torch.empty_like(torch.from_numpy(mac).cuda()) for _ in range(N)] if rank == 0 else None
+            dist.gather(torch.from_numpy(mac).cuda(), mparts, dst=0)
+            if rank == 0:
+                df_all = np.concatenate([t.cpu().numpy() for t in parts], axis=1)
+                mac_all = np.concatenate([t.cpu().numpy() for t in mparts], axis=1)
+                if one is None:
+                    one = run_engine(streaming, 1, 0, False)
+                same = bool(np.array_equal(df_all, one[0]) and np.array_equal(mac_all, one[1]))
+                cases.append({"streaming": sname, "transport": transport if peer or transport == "nccl" else "nccl (peer memory unavailable)", "bit_identical_to_one_slab": same})
+                del parts, mparts, df_all, mac_all
+        if rank == 0:
+            # the CPU checker on the same inputs: one ghosted slab under the nproc > 1 index rule, ghost planes exchanged by hand
+            from oracle import oracle as O
+
+            if not O.available("port"):
+                subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, stdout=subprocess.DEVNULL)
+            d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=O.AA if streaming == B.AA else O.AB, precision=O.F64, X=X, Y=S, Z=S, ox=1, nproc=2)
+            orc = O.Oracle(d, "port")
+            idx = np.arange(-1, X + 1) % X
+            f = fields(0, X)
+            a = d.new_df()
+            orc.set_equilibrium_field(a, *[np.ascontiguousarray(v[idx]) for v in f])
+            b = a.copy()
+            m = np.ascontiguousarray(duct_map(X, 0, X, S)[idx])
+            mac = d.new_macro()
+            p = O.Params(**prm)
+            aa = streaming == B.AA
+            for it in range(STEPS):
+                orc.step(p, a, b, mac, m, it, 1, threads)
+                arr = a if (aa or it % 2 == 1) else b  # A-B: even iterations write df[1] (lbm.hpp:320-327)
+                for msg in B.halo_plan(B.D3Q27, streaming, it, X):
+                    arr[msg["dirs"], msg["dst_plane"]] = arr[msg["dirs"], msg["src_plane"]]
+            cur = a if (aa or STEPS % 2 == 0) else b
+            ref = cur[:, 1:-1]
+            w = np.array([8 / 27] + [2 / 27] * 6 + [1 / 54] * 12 + [1 / 216] * 8).reshape(27, 1, 1, 1)
+            err = float((np.abs(one[0] - ref) / np.maximum(np.abs(ref), w / 2)).max())
+            worst = max(worst, err)
+            for c in cases:
+                if c["streaming"] == sname:
+                    c["vs_oracle"] = err
+    out = None
+    if rank == 0:
+        ok = all(c["bit_identical_to_one_slab"] for c in cases)
+        out = {"slabs": N, "lattice": [X, S, S], "steps": STEPS, "bit_identical": ok, "vs_oracle": worst, "tolerance": 1e-12, "cases": cases,
+               "what": "N ghosted slabs (one process per GPU, both halo transports) == one slab with self-exchange, bit for bit; that run vs the CPU checker under the ghost-plane rule"}
+        assert ok, f"multi-GPU halo exchange is NOT bit-identical to the single-slab run: {cases}"
+        assert worst <= 1e-12, f"single-slab run differs from the CPU checker by {worst:.3e}"
+    dist.barrier()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -160,6 +332,8 @@ def main():
                     help="last: rho,u written by the last step of a batch (default; identical values wherever the host can observe them); "
                          "every: written by every step, as the reference kernel does (+32 B per update)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements that start child processes")
+    ap.add_argument("--no-halo-parity", action="store_true", help="skip the multi-GPU bit-identity leg that precedes the timing at N > 1")
+    ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"], help="how SM clocks / throttle reasons are sampled during the timed region")
     ap.add_argument("--workload", default="box", choices=["box", "channel"],
                     help="box: periodic 512^3 per GPU, weak scaling (the headline metric); channel: BASELINE.json configs[3], the 2048x512x512 "
                          "body-force duct of sim_NSE/sim_2.cu split into N x-slabs, strong scaling (N >= 2)")
@@ -220,7 +394,11 @@ def main():
         return float(t.item())
 
     S = a.size
-    assert not (channel and N < 2), "--workload channel needs at least 2 GPUs (134 GB of distributions)"
+    parity = None
+    if N > 1 and not a.no_halo_parity:
+        t_par = time.perf_counter()
+        parity = halo_parity(rank, N, local_rank, dist, torch, B, host_threads)
+        log(f"[rank {rank}] halo parity leg: {time.perf_counter() - t_par:.1f}s {'' if parity is None else json.dumps(parity['cases'])}")
     streaming = B.AA if a.streaming == "AA" else B.AB
     eng = B.Engine(lattice=B.D3Q27, coll=B.CUM, eq=B.EQ_INV_CUM, streaming=streaming, macro=B.MACRO_DEFAULT, inflow=B.INFLOW_NONE, precision=B.F64,
                    X=Xg, Y=S, Z=S, rank=rank, nranks=N, device=local_rank, ghost_x=1 if (N > 1 or channel) else 0, periodic_x=1,
@@ -243,20 +421,7 @@ def main():
     keep.append(tm)
     fields = []
     if channel:
-        # sim_NSE/sim_2.cu:125-138, painted in that order (global x planes 0 and X-1 periodic, walls at y,z = 1 / N-2, NOTHING outside)
-        h_map[...] = 0
-        if x0 == 0:
-            h_map[0] = 7
-        if x0 + xl == Xg:
-            h_map[xl - 1] = 7
-        h_map[:, 1, :] = 1
-        h_map[:, S - 2, :] = 1
-        h_map[:, :, 1] = 1
-        h_map[:, :, S - 2] = 1
-        h_map[:, 0, :] = 8
-        h_map[:, S - 1, :] = 8
-        h_map[:, :, 0] = 8
-        h_map[:, :, S - 1] = 8
+        duct_map(Xg, x0, xl, S, out=h_map)
     else:
         h_map[...] = 7  # GEO_PERIODIC (d3q27/bc.h:25)
         rho, vx, vy, vz = initial_fields(Xg, x0, xl, S, S)
@@ -289,7 +454,7 @@ def main():
     eng.step(a.warmup)
     eng.sync()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, a.clock_sampler)
     sampler.start()
     time.sleep(0.25)
     s0 = eng.stats()
@@ -367,7 +532,7 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                              "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_update": B_PER_UPDATE,
                              "kernel": f"k_bulk<D3Q27,CUM,double,{'A-A even/odd' if a.streaming == 'AA' else 'A-B'}>", "registers": st.bulk_regs, "block": st.bulk_block},
-                "halo_bytes_per_step_per_gpu": halo_bytes / a.steps}
+                "halo_bytes_per_step_per_gpu": halo_bytes / a.steps, "halo_parity": parity}
         if halo_ms is not None:
             hb = halo_bytes / a.steps
             line["halo"] = {"bytes_per_step_per_gpu": hb, "exchange_ms_alone": halo_ms, "nvlink_bound_ms": hb / 900e9 * 1e3,

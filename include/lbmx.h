@@ -272,7 +272,7 @@ typedef struct lbmx_stats
 										  neighbours lie outside the lattice: undefined behaviour in the reference.  Here the arrays carry a zeroed
 										  guard band, so the accesses stay inside the engine's memory, but the values at those cells are as
 										  meaningless as there -- give A-A lattices a GEO_NOTHING (or periodic) skin, as sim_2.cu:125-138 does. */
-	int64_t tma_launches;	   /* of kernel_launches: bulk kernels whose populations travelled as TMA tensor boxes (k_bulk_tma, A-A only) */
+	int64_t tma_launches;	   /* of kernel_launches: bulk kernels whose populations travelled as bulk copies of the TMA engine (k_bulk_tma, A-A only) */
 } lbmx_stats;
 int lbmx_get_stats(lbmx_engine* e, lbmx_stats* out);
 

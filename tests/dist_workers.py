@@ -66,8 +66,11 @@ def gloo_slab_worker(rank, world, port, case_name, outdir, kind="port"):
     dist.destroy_process_group()
 
 
-def nccl_engine_worker(rank, world, port, case_name, outdir, transport="auto"):
-    """GPU: one engine slab per process / device; ghost planes exchanged by the engine itself (peer memory or NCCL send/recv)."""
+def nccl_engine_worker(rank, world, port, case_name, outdir, transport="auto", delay=0.0):
+    """GPU: one engine slab per process / device; ghost planes exchanged by the engine itself (peer memory or NCCL send/recv).
+    delay > 0: the state arrives as arrays WITH ghost planes (the restore path of LBM_BLOCK checkpoints: no collective call after the
+    upload) and the last rank uploads `delay` seconds late, while its neighbours are already stepping -- their one-sided halo stores
+    must wait for it (receiver-ready handshake of the peer-memory exchange)."""
     if transport == "nccl":
         os.environ["LBMX_HALO"] = "nccl"
     else:
@@ -95,11 +98,23 @@ def nccl_engine_worker(rank, world, port, case_name, outdir, transport="auto"):
     e.comm_init(idt.numpy().tobytes())
     x0, xl = e.layout.x_offset, e.layout.X_local
     e.map_upload(np.ascontiguousarray(mapg[x0 : x0 + xl]))
-    mine = np.ascontiguousarray(df0[:, x0 : x0 + xl])
-    e.df_upload(mine, 0)
-    e.df_sync_ghosts()
-    if dg.streaming == O.AB:
-        e.df_upload(mine, 1)
+    if delay > 0:
+        import time
+
+        from slab_emulation import split
+
+        ghosted = split(df0, world, 1)[rank]
+        if rank == world - 1:
+            time.sleep(delay)
+        e.df_upload(ghosted, 0, with_ghosts=True)
+        if dg.streaming == O.AB:
+            e.df_upload(ghosted, 1, with_ghosts=True)
+    else:
+        mine = np.ascontiguousarray(df0[:, x0 : x0 + xl])
+        e.df_upload(mine, 0)
+        e.df_sync_ghosts()
+        if dg.streaming == O.AB:
+            e.df_upload(mine, 1)
     set_params(e, case.params)
     e.macro_init()
     e.step(case.nsteps)

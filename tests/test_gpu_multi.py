@@ -63,28 +63,23 @@ def test_ghost_planes_with_self_exchange_equal_plain_run(case_name):
     assert lc.rel_err_df(df, ref_df, case.desc) <= 1e-12
 
 
-@pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
-@pytest.mark.parametrize("case_name", ["duct_aa", "box_ab"])
-def test_four_gpus_halo_exchange(case_name, transport):
-    """Four slabs in a periodic ring: every rank has two different neighbours (two peer mappings per rank)."""
-    import torch
-
-    if torch.cuda.device_count() < 4:
-        pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
+def _run_ranks(world, case_name, transport, delay=0.0):
     import torch.multiprocessing as mp
 
     import dist_workers as W
 
-    world = 4
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(W.nccl_engine_worker, args=(world, free_port(), case_name, tmp, transport), nprocs=world, join=True)
+        mp.spawn(W.nccl_engine_worker, args=(world, free_port(), case_name, tmp, transport, delay), nprocs=world, join=True)
         df, mac = W.gather(tmp, world)
         halo = np.load(f"{tmp}/halo_0.npy")
-    case = W.DIST_CASES[case_name]()
-    assert halo[2] == (0 if transport == "nccl" else 1)
-    one_df, one_mac = run_ghost_single(case)
-    assert np.array_equal(df, one_df), "4 slabs must be identical to 1 slab with self-exchange"
-    assert np.array_equal(mac, one_mac)
+    return df, mac, halo
+
+
+def _need_gpus(n):
+    import torch
+
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs (gpurun --gpus {n})")
 
 
 @pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
@@ -92,19 +87,10 @@ def test_four_gpus_halo_exchange(case_name, transport):
 def test_two_gpus_halo_exchange(case_name, transport):
     """Two slabs, two processes, two GPUs.  Default transport: stores into the neighbour's array over NVLink (CUDA IPC peer
     mappings + arrival counters); LBMX_HALO=nccl: NCCL send/recv.  Either way identical to one slab with a self-exchange."""
-    import torch
-
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    import torch.multiprocessing as mp
-
     import dist_workers as W
 
-    world = 2
-    with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(W.nccl_engine_worker, args=(world, free_port(), case_name, tmp, transport), nprocs=world, join=True)
-        df, mac = W.gather(tmp, world)
-        halo = np.load(f"{tmp}/halo_0.npy")
+    _need_gpus(2)
+    df, mac, halo = _run_ranks(2, case_name, transport)
     case = W.DIST_CASES[case_name]()
     assert halo[0] == case.nsteps * 2 * 9 * case.desc.Y * case.desc.Z * 8, "9 populations per direction per step"
     if transport == "nccl":
@@ -116,3 +102,36 @@ def test_two_gpus_halo_exchange(case_name, transport):
     assert np.array_equal(mac, one_mac)
     ref_df, ref_mac = gc.run_case(case, "port", nthreads=4)
     assert lc.rel_err_df(df, ref_df, case.desc) <= 1e-12
+
+
+@pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
+@pytest.mark.parametrize("case_name", ["duct_aa", "duct_ab", "box_aa"])
+@pytest.mark.parametrize("world", [3, 4, 8])
+def test_n_gpus_halo_exchange(world, case_name, transport):
+    """3 (uneven: 6 + 5 + 5 planes), 4 and 8 slabs (2 planes each: every plane is an edge plane) in a periodic ring: every rank has two
+    different neighbours.  SURVEY 8d cfg 4: 8 == 4 == 2 == 1 slab with self-exchange, bit for bit."""
+    import dist_workers as W
+
+    _need_gpus(world)
+    df, mac, halo = _run_ranks(world, case_name, transport)
+    case = W.DIST_CASES[case_name]()
+    assert halo[2] == (0 if transport == "nccl" else 1)
+    one_df, one_mac = run_ghost_single(case)
+    assert np.array_equal(df, one_df), f"{world} slabs must be identical to 1 slab with self-exchange"
+    assert np.array_equal(mac, one_mac)
+
+
+@pytest.mark.parametrize("case_name", ["duct_aa", "duct_ab"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_late_rank_does_not_lose_halo_planes(world, case_name):
+    """The last rank uploads its (ghosted) state two seconds after the others have started stepping.  The peer-memory exchange is
+    one-sided: without the receiver-ready handshake the early neighbours' first planes would land in arrays the late rank then
+    overwrites from the host, and step 1 would read stale ghost populations (engine.cu exchange())."""
+    import dist_workers as W
+
+    _need_gpus(world)
+    df, mac, halo = _run_ranks(world, case_name, "peer_memory", delay=2.0)
+    assert halo[2] == 1
+    case = W.DIST_CASES[case_name]()
+    one_df, one_mac = run_ghost_single(case)
+    assert np.array_equal(df, one_df) and np.array_equal(mac, one_mac)

@@ -246,8 +246,7 @@ struct lbmx_engine
 	StepKernels<float> kf{};
 	StepKernels<double> kd{};
 	lbmx_stats stats{};
-	// k_bulk_tma (A-A only): tensor map over df[0], tile geometry, and which step parities go through it
-	CUtensorMap tmap{};
+	// k_bulk_tma (A-A only): tile geometry, and which step parities go through it
 	int tile_y = 0, tile_y_shift = 0;
 	bool use_tma[3] = {false, false, false};  // by StreamMode
 
@@ -326,10 +325,10 @@ int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, 
 	p.nb_begin = (int) e->plane_start[xb];
 	p.nb_end = (int) e->plane_start[xe];
 	if (e->use_tma[p.stream]) {
-		// one CTA per tile of tile_y x (128 / tile_y) cells; the populations travel as tensor boxes (kernels_tma.cuh)
+		// one CTA per tile of tile_y x (128 / tile_y) cells; the populations travel as bulk copies of the TMA engine (kernels_tma.cuh)
 		const int tz = tma::TILE / e->tile_y;
 		dim3 grid((unsigned) ((e->Y / e->tile_y) * ((e->Z + tz - 1) / tz)), (unsigned) (xe - xb));
-		K.bulk_tma[p.stream]<<<grid, tma::TILE, 0, st>>>(p, e->tmap);
+		K.bulk_tma[p.stream]<<<grid, tma::TILE, 0, st>>>(p);
 		e->stats.tma_launches++;
 	}
 	else {
@@ -1000,8 +999,7 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 		const char* want = std::getenv("LBMX_TMA");
 		const std::string w = want ? want : LBMX_TMA_DEFAULT;
 		e->tile_y = tma_tile_y(e->Y, (int) e->rs);
-		std::string why;
-		if (w != "0" && e->tile_y > 0 && make_df_tensor_map(&e->tmap, e->df[0], (int) e->rs, e->Y, e->Z, e->X + 2 * e->ox, e->Q, e->tile_y, &why)) {
+		if (w != "0" && e->tile_y > 0) {
 			while ((1 << e->tile_y_shift) < e->tile_y)
 				e->tile_y_shift++;
 			e->use_tma[S_AA_EVEN] = w == "even" || w == "both";

@@ -144,32 +144,45 @@ LBMX_D int dir_offset(const Deltas& d, int q, int sign)
 	return (cx > 0 ? d.xp : cx < 0 ? d.xm : 0) + (cy > 0 ? d.yp : cy < 0 ? d.ym : 0) + (cz > 0 ? d.zp : cz < 0 ? d.zm : 0);
 }
 
-template <typename R>
+template <int HINT = LBMX_LD_HINT, typename R>
 LBMX_D R ld_df(const R* ptr)
 {
-#if LBMX_LD_HINT == 1
-	return __ldcs(ptr);
-#elif LBMX_LD_HINT == 2
-	return __ldcg(ptr);
-#elif LBMX_LD_HINT == 3
-	return __ldlu(ptr);
-#else
-	return *ptr;
-#endif
+	if constexpr (HINT == 1)
+		return __ldcs(ptr);
+	else if constexpr (HINT == 2)
+		return __ldcg(ptr);
+	else if constexpr (HINT == 3)
+		return __ldlu(ptr);
+	else
+		return *ptr;
 }
-template <typename R>
+template <int HINT = LBMX_ST_HINT, typename R>
 LBMX_D void st_df(R* ptr, R v)
 {
-#if LBMX_ST_HINT == 1
-	__stcs(ptr, v);
-#elif LBMX_ST_HINT == 2
-	__stcg(ptr, v);
-#elif LBMX_ST_HINT == 3
-	__stwt(ptr, v);
-#else
-	*ptr = v;
-#endif
+	if constexpr (HINT == 1)
+		__stcs(ptr, v);
+	else if constexpr (HINT == 2)
+		__stcg(ptr, v);
+	else if constexpr (HINT == 3)
+		__stwt(ptr, v);
+	else
+		*ptr = v;
 }
+// A-A odd steps: the accesses of the populations that move in y are shifted by one element, so the last 32-byte sector of a warp's
+// request is the first sector of the next warp's (same CTA, same row).  Hints for those accesses alone (tools/kbench sweep):
+// LBMX_LD_HINT_YSHIFT / LBMX_ST_HINT_YSHIFT, same encoding as LBMX_LD_HINT / LBMX_ST_HINT.
+#ifndef LBMX_LD_HINT_YSHIFT
+	#define LBMX_LD_HINT_YSHIFT LBMX_LD_HINT
+#endif
+#ifndef LBMX_ST_HINT_YSHIFT
+	#define LBMX_ST_HINT_YSHIFT LBMX_ST_HINT
+#endif
+#ifndef LBMX_LD_HINT_ODD
+	#define LBMX_LD_HINT_ODD LBMX_LD_HINT
+#endif
+#ifndef LBMX_ST_HINT_ODD
+	#define LBMX_ST_HINT_ODD LBMX_ST_HINT
+#endif
 
 // ---- streaming (d3q27/streaming_AB.h:12-58, streaming_AA.h:12-116 and the D2Q9 twins) ----
 // NONNEG: the caller guarantees cell + offset >= 0 (bulk kernel: offsets wrap), so the index is zero-extended for free.
@@ -195,7 +208,7 @@ LBMX_D void stream_in(const KParams<R>& p, R (&f)[L::Q], int c, const Deltas& d)
 		else if constexpr (MODE == S_AA_EVEN)
 			f[q] = ld_df(p.rd[q] + cell_index<NONNEG>(c));
 		else
-			f[L::opp(q)] = ld_df(p.rd[q] + cell_index<NONNEG>(c + dir_offset<L, 1>(d, q, +1)));
+			f[L::opp(q)] = ld_df<(L::cy(q) != 0 ? LBMX_LD_HINT_YSHIFT : LBMX_LD_HINT_ODD)>(p.rd[q] + cell_index<NONNEG>(c + dir_offset<L, 1>(d, q, +1)));
 	});
 }
 
@@ -209,7 +222,7 @@ LBMX_D void stream_out(const KParams<R>& p, const R (&f)[L::Q], int c, const Del
 		else if constexpr (MODE == S_AA_EVEN)
 			st_df(p.wr[L::opp(q)] + cell_index<NONNEG>(c), f[q]);
 		else
-			st_df(p.wr[q] + cell_index<NONNEG>(c + dir_offset<L, 2>(d, q, +1)), f[q]);
+			st_df<(L::cy(q) != 0 ? LBMX_ST_HINT_YSHIFT : LBMX_ST_HINT_ODD)>(p.wr[q] + cell_index<NONNEG>(c + dir_offset<L, 2>(d, q, +1)), f[q]);
 	});
 }
 
@@ -693,7 +706,7 @@ struct StepKernels
 	void (*bulk[3])(const KParams<R>);	// by StreamMode
 	int cpt[3];						// cells per thread of the bulk kernels, by StreamMode
 #if defined(__CUDACC__)
-	void (*bulk_tma[3])(const KParams<R>, const CUtensorMap);  // by StreamMode; A-A only ([S_AB] stays null)
+	void (*bulk_tma[3])(const KParams<R>);	// by StreamMode; A-A only ([S_AB] stays null)
 #endif
 	void (*boundary)(const KParams<R>);
 	void (*initial_macro)(const KParams<R>);

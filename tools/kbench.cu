@@ -71,12 +71,10 @@ int main(int argc, char** argv)
 	auto grid_for = [&](int cpt) { return dim3((unsigned) ((p.YZ + BS * cpt - 1) / (BS * cpt)), (unsigned) S); };
 	const dim3 grid_e = grid_for(bulk_cpt<L, R, S_AA_EVEN>()), grid_o = grid_for(bulk_cpt<L, R, S_AA_ODD>()), grid_ab = grid_for(bulk_cpt<L, R, S_AB>());
 	// TMA flavour
-	CUtensorMap tm;
-	std::string why;
 	const int ty = tma_tile_y(S, (int) sizeof(R));
-	bool have_tma = ty > 0 && make_df_tensor_map(&tm, a, (int) sizeof(R), S, SZ, S, L::Q, ty, &why);
+	const bool have_tma = ty > 0;
 	if (! have_tma)
-		printf("no TMA flavour: %s\n", ty ? why.c_str() : "tile geometry");
+		printf("no TMA flavour: tile geometry\n");
 	p.tile_y = ty;
 	p.tile_y_shift = 0;
 	while ((1 << p.tile_y_shift) < ty) p.tile_y_shift++;
@@ -85,14 +83,22 @@ int main(int argc, char** argv)
 	cudaEvent_t e0, e1;
 	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 	float t_even[2] = {0, 0}, t_odd[2] = {0, 0}, t_ab = 0;
+	const double bytes = (double) XYZ * L::Q * 2 * sizeof(R);
+	cudaFuncAttributes fa, fo, ft; cudaFuncGetAttributes(&fa, k_bulk<L, KB_KIND, R, S_AA_EVEN>); cudaFuncGetAttributes(&fo, k_bulk<L, KB_KIND, R, S_AA_ODD>);
+	cudaFuncGetAttributes(&ft, k_bulk_tma<L, KB_KIND, R, S_AA_ODD>);
 	for (int tma_flavour = 0; tma_flavour < (have_tma ? 2 : 1); tma_flavour++) {
+		if (tma_flavour == 1) {
+			printf("%-22s S=%d macro=%d regs=%d/%d  even %.4f ms %.0f GB/s | odd %.4f ms %.0f GB/s | AA avg %.0f MLUPS\n", KB_NAME, S, macro, fa.numRegs, fo.numRegs,
+				   t_even[0] / iters, bytes / (t_even[0] / iters) / 1e6, t_odd[0] / iters, bytes / (t_odd[0] / iters) / 1e6, 2.0 * XYZ / ((t_even[0] + t_odd[0]) / iters) / 1e3);
+			fflush(stdout);
+		}
 		init();
 		for (int it = -4; it < 2 * iters; it++) {
 			const bool even = (it & 1) == 0;
 			p.stat_counter = it + 4;
 			CK(cudaEventRecord(e0));
 			if (tma_flavour) {
-				if (even) k_bulk_tma<L, KB_KIND, R, S_AA_EVEN><<<grid_t, 128>>>(p, tm); else k_bulk_tma<L, KB_KIND, R, S_AA_ODD><<<grid_t, 128>>>(p, tm);
+				if (even) k_bulk_tma<L, KB_KIND, R, S_AA_EVEN><<<grid_t, 128>>>(p); else k_bulk_tma<L, KB_KIND, R, S_AA_ODD><<<grid_t, 128>>>(p);
 			}
 			else {
 				if (even) k_bulk<L, KB_KIND, R, S_AA_EVEN><<<grid_e, BS>>>(p); else k_bulk<L, KB_KIND, R, S_AA_ODD><<<grid_o, BS>>>(p);
@@ -127,9 +133,6 @@ int main(int argc, char** argv)
 		R* t = p.cur; p.cur = p.out; p.out = t;
 	}
 	CK(cudaGetLastError());
-	const double bytes = (double) XYZ * L::Q * 2 * sizeof(R);
-	cudaFuncAttributes fa, fo, ft; cudaFuncGetAttributes(&fa, k_bulk<L, KB_KIND, R, S_AA_EVEN>); cudaFuncGetAttributes(&fo, k_bulk<L, KB_KIND, R, S_AA_ODD>);
-	cudaFuncGetAttributes(&ft, k_bulk_tma<L, KB_KIND, R, S_AA_ODD>);
 	printf("%-22s S=%d macro=%d regs=%d/%d  even %.4f ms %.0f GB/s | odd %.4f ms %.0f GB/s | AA avg %.0f MLUPS | AB %.4f ms %.0f GB/s  (f0=%.6f)\n", KB_NAME, S, macro, fa.numRegs, fo.numRegs,
 		   t_even[0] / iters, bytes / (t_even[0] / iters) / 1e6, t_odd[0] / iters, bytes / (t_odd[0] / iters) / 1e6, 2.0 * XYZ / ((t_even[0] + t_odd[0]) / iters) / 1e3, t_ab / iters, bytes / (t_ab / iters) / 1e6, (double) h[0]);
 	if (have_tma)

@@ -6,14 +6,15 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --expt-r
 # name:defines:macro modes to run (0 none, 1 rho,u every step, 2 MACRO_Mean)
 variants=(
  "default::0 1 2"
- "macro_plain:-DLBMX_MACRO_HINT=0:1 2"
- "tma_nohint:-DLBMX_TMA_LD_POLICY=0 -DLBMX_TMA_ST_POLICY=0:0"
- "tma_ldhint:-DLBMX_TMA_LD_POLICY=1 -DLBMX_TMA_ST_POLICY=0:0"
- "tma_sthint:-DLBMX_TMA_LD_POLICY=0 -DLBMX_TMA_ST_POLICY=1:0"
- "tma_occ5:-DLBMX_TMA_MINBLOCKS=5:0"
- "tma_occ3:-DLBMX_TMA_MINBLOCKS=3:0"
- "f32::0 1"
- "f32_macro_plain:-DLBMX_MACRO_HINT=0:1"
+ "odd_ld_plain_y:-DLBMX_LD_HINT_YSHIFT=0:0"
+ "odd_ld_plain_all:-DLBMX_LD_HINT_YSHIFT=0 -DLBMX_LD_HINT_ODD=0:0"
+ "odd_st_plain_y:-DLBMX_ST_HINT_YSHIFT=0:0"
+ "odd_ldst_plain_y:-DLBMX_LD_HINT_YSHIFT=0 -DLBMX_ST_HINT_YSHIFT=0:0"
+ "odd_ldst_plain_all:-DLBMX_LD_HINT_YSHIFT=0 -DLBMX_ST_HINT_YSHIFT=0 -DLBMX_LD_HINT_ODD=0 -DLBMX_ST_HINT_ODD=0:0"
+ "odd_ld_plain_st_cg_y:-DLBMX_LD_HINT_YSHIFT=0 -DLBMX_ST_HINT_YSHIFT=2:0"
+ "odd_ld_cs_y:-DLBMX_LD_HINT_YSHIFT=1:0"
+ "f32::0"
+ "f32_odd_ld_plain_y:-DLBMX_LD_HINT_YSHIFT=0:0"
 )
 if [ "$1" = "build" ]; then
   for v in "${variants[@]}"; do
