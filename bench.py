@@ -200,6 +200,37 @@ def macro_every_step_run(a):
         return {"error": repr(ex)}
 
 
+def dropin_mirror_run(a):
+    """The same workload as an ordinary solver written against the host mirror of the reference's interface (examples/box3d.cpp:
+    LBM_CONFIG + State<NSE> + execute(), nothing batch-aware in it), in a child process; the figure is the mirror's own GLUPS= line
+    (State::AfterSimUpdate, state.hpp:1244-1262).  VERDICT r1 'next' #2: an unmodified solver has to reach the headline rate."""
+    exe = os.path.join(ROOT, "examples", "bin", "box3d_aa" if a.streaming == "AA" else "box3d")
+    if not os.path.exists(exe):
+        return {"error": "examples/bin/box3d[_aa] not built (python -m tnl_lbm_b200.build_examples)"}
+    import re
+    import tempfile
+
+    steps, period = 330, 110
+    out = {}
+    try:
+        for mode in ("1", "0"):
+            with tempfile.TemporaryDirectory() as tmp:
+                n = steps if mode == "1" else 120
+                r = subprocess.run([exe, str(a.size), str(a.size), str(a.size), str(n), str(period if mode == "1" else 60)], capture_output=True, text=True, timeout=420, cwd=tmp,
+                                   env=dict(os.environ, LBMX_HOST_BATCH=mode))
+            g = [float(x) for x in re.findall(r"GLUPS=([0-9.]+)", r.stdout)]
+            b = re.search(r"lbmx: (\d+) steps enqueued in (\d+) batches", r.stdout)
+            if r.returncode != 0 or not g or not b:
+                return {"error": f"child exited {r.returncode}: {(r.stdout + r.stderr).strip()[-300:]}"}
+            out[mode] = {"MLUPS": g[-1] * 1e3, "all_GLUPS_lines": g, "steps": int(b.group(1)), "batches": int(b.group(2))}
+        return {"value": out["1"]["MLUPS"], "unit": "MLUPS", "steps": out["1"]["steps"], "batches": out["1"]["batches"], "glups_lines": out["1"]["all_GLUPS_lines"],
+                "one_launch_per_SimUpdate": {"value": out["0"]["MLUPS"], "steps": out["0"]["steps"], "batches": out["0"]["batches"], "how": "LBMX_HOST_BATCH=0"},
+                "what": f"examples/box3d.cpp ({a.size}^3 periodic, D3Q27 CUM fp64, {'A-A' if a.streaming == 'AA' else 'A-B'}) through State<NSE>/execute() of the host mirror; "
+                        f"last GLUPS= line of the run (interval of {period} steps, includes the NaN scan of AfterSimUpdate)"}
+    except Exception as ex:
+        return {"error": repr(ex)}
+
+
 # ------------------------------------------------------------------------------------------------------------------ multi-GPU parity leg
 def duct_map(Xg, x0, xl, S, out=None):
     """sim_NSE/sim_2.cu:125-138, painted in that order: global x planes 0 and X-1 GEO_PERIODIC, GEO_WALL at y,z = 1 / N-2, GEO_NOTHING
@@ -317,6 +348,65 @@ def halo_parity(rank, N, local_rank, dist, torch, B, threads):
     return out
 
 
+# ------------------------------------------------------------------------------------------------------------------ strong-scaling leg
+def channel_strong(rank, N, local_rank, dist, torch, B, S, steps=10, warmup=3):
+    """BASELINE.json configs[3] inside every default run (VERDICT r1 'next' #5): the 4S x S x S body-force duct of sim_NSE/sim_2.cu
+    (2048 x 512 x 512 at S = 512; 116 GB of distributions + 17 GB of rho,u: one B200 holds it) stepped `steps` times
+      (1) on rank 0's GPU alone, as ONE slab with ghost planes and a self-exchange, and
+      (2) split into N x-slabs over the N ranks (default halo transport),
+    both timed with CUDA events on the engines' compute streams, (2) as the max over ranks.  Strong scaling: efficiency = t1 / (N tN)."""
+    Xg = 4 * S
+
+    def run(nranks, r):
+        e = B.Engine(lattice=B.D3Q27, coll=B.CUM, eq=B.EQ_INV_CUM, streaming=B.AA, macro=B.MACRO_DEFAULT, inflow=B.INFLOW_NONE, precision=B.F64, X=Xg, Y=S, Z=S,
+                     rank=r, nranks=nranks, device=local_rank, ghost_x=1, periodic_x=1, macro_policy=B.MACRO_LAST_STEP)
+        try:
+            if nranks > 1:
+                idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if r == 0:
+                    idbuf.copy_(torch.frombuffer(bytearray(B.comm_unique_id()), dtype=torch.uint8))
+                dist.broadcast(idbuf, 0)
+                e.comm_init(bytes(idbuf.cpu().numpy().tobytes()))
+            x0, xl = e.layout.x_offset, e.layout.X_local
+            e.map_upload(duct_map(Xg, x0, xl, S))
+            e.set_equilibrium(1.0, 0.0, 0.0, 0.0)
+            e.set_params(lbmViscosity=1e-3, fx=1e-7, fy=0.0, fz=0.0)
+            e.step(warmup)
+            e.sync()
+            if nranks > 1:
+                dist.barrier()
+            ms = e.step_timed(steps)
+            if nranks > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            assert not e.has_nan()
+            return ms / steps
+        finally:
+            e.close()
+
+    cells = Xg * S * S
+    out = {"lattice": [Xg, S, S], "steps": steps, "warmup": warmup, "unit": "MLUPS",
+           "what": "D3Q27 cumulant fp64 A-A duct of sim_NSE/sim_2.cu:125-138 (periodic x, GEO_WALL ring behind a GEO_NOTHING shell), fixed global lattice"}
+    one = None
+    if rank == 0:
+        try:
+            one = run(1, 0)
+            out["n1"] = {"ms_per_step": one, "value": cells / (one * 1e-3) / 1e6, "how": "one slab with ghost planes and a self-exchange on rank 0's GPU"}
+        except Exception as ex:  # e.g. a GPU with less memory
+            out["n1"] = {"error": repr(ex)[:300]}
+    if N > 1:
+        dist.barrier()
+        msN = run(N, rank)
+        out["value"] = cells / (msN * 1e-3) / 1e6
+        out["ms_per_step"] = msN
+        out["n_gpus"] = N
+        out["efficiency_vs_n1"] = (one / (N * msN)) if one else None
+    elif one:
+        out["value"], out["ms_per_step"], out["n_gpus"], out["efficiency_vs_n1"] = out["n1"]["value"], one, 1, 1.0
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -332,6 +422,7 @@ def main():
                     help="last: rho,u written by the last step of a batch (default; identical values wherever the host can observe them); "
                          "every: written by every step, as the reference kernel does (+32 B per update)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements that start child processes")
+    ap.add_argument("--no-channel-strong", action="store_true", help="skip the strong-scaling leg (BASELINE.json configs[3]) that follows the headline measurement")
     ap.add_argument("--no-halo-parity", action="store_true", help="skip the multi-GPU bit-identity leg that precedes the timing at N > 1")
     ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "none"], help="how SM clocks / throttle reasons are sampled during the timed region")
     ap.add_argument("--workload", default="box", choices=["box", "channel"],
@@ -541,6 +632,18 @@ def main():
                             "transport": ("stores into the neighbour's planes over NVLink (CUDA IPC peer mapping) + arrival counter" if st.halo_peer_memory
                                           else "NCCL send/recv, 9 plane messages per direction in one group") if N > 1 else "device copy kernel (single slab with ghost planes)"}
     eng.close()
+    del keep, h_mac, h_map, fields
+    # ---- strong scaling of the channel (configs[3]) at this N against one GPU, same run
+    if not channel and not a.no_channel_strong and not a.no_extras and a.streaming == "AA" and a.macro_policy == "last":
+        try:
+            cs = channel_strong(rank, N, local_rank, dist if N > 1 else None, torch, B, S)
+        except Exception as ex:
+            cs = {"error": repr(ex)[:300]}
+            if N > 1:
+                raise
+        if rank == 0:
+            line["channel_strong"] = cs
+            log(f"[rank 0] channel_strong: {json.dumps(cs)}")
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's CPU code on a bounded sample of the same workload
     if rank == 0 and N == 1 and not a.no_cpu_baseline:
@@ -566,6 +669,7 @@ def main():
     #      engine has released its memory: a failure or time-out there cannot take the line above with it
     if rank == 0 and N == 1 and not channel and a.macro_policy == "last" and not a.no_extras and not a.no_cpu_baseline:
         line["macro_every_step"] = macro_every_step_run(a)
+        line["dropin_mirror"] = dropin_mirror_run(a)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if N > 1:

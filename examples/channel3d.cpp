@@ -30,11 +30,6 @@ struct StateLocal : State<NSE>
 	double probed_mass = 0;
 	int halt_at = 0;  // stop the time loop after this many steps (stands in for the wall-time limit), 0 = never
 
-	void computeAfterLBMKernel() override
-	{
-		if (halt_at > 0 && nse.iterations >= halt_at)	 // the hook runs in AfterSimUpdate, after the step was counted (state.hpp:1153)
-			nse.terminate = true;
-	}
 
 	void setupBoundaries() override
 	{
@@ -58,6 +53,8 @@ struct StateLocal : State<NSE>
 	}
 	void updateKernelVelocities() override
 	{
+		if (halt_at > 0 && nse.iterations + 1 >= halt_at)  // the step about to run is the last one (the hook runs before SimUpdate, core.h:44-46)
+			nse.terminate = true;
 		for (auto& block : nse.blocks) {
 			block.data.inflow_vx = lbm_inflow_vx;
 			block.data.inflow_vy = 0;

@@ -93,11 +93,6 @@ using namespace lbmx;
 
 namespace {
 
-template <typename L>
-bool is_boundary(int m)
-{
-	return m != (int) L::FLUID && m != (int) L::PERIODIC;
-}
 
 // what lbmx_create / make_params / launch_range do for a single slab (tnl_lbm_b200/csrc/engine.cu), restated for the emulation
 template <typename L, typename R>
@@ -185,9 +180,11 @@ int step_family(const oracle_desc* d, const oracle_params* op, void* df_a, void*
 	const int YZ = (int) (d->Y * d->Z);
 	// boundary list in storage order over the interior planes (lbmx_map_upload)
 	std::vector<uint32_t> blist;
-	for (long long c = (long long) d->ox * YZ; c < (long long) (d->ox + d->X) * YZ; c++)
-		if (is_boundary<L>(map[c]))
+	for (long long c = (long long) d->ox * YZ; c < (long long) (d->ox + d->X) * YZ; c++) {
+		const int xs = (int) (c / YZ), yz = (int) (c - (long long) xs * YZ), z = yz / (int) d->Y;
+		if (cell_in_boundary_list(map[c], (int) L::FLUID, (int) L::PERIODIC, (int) L::WALL, cell_on_face(L::NDIM, (int) d->ox, (int) d->X, (int) d->Y, (int) d->Z, xs - (int) d->ox, yz - z * (int) d->Y, z)))
 			blist.push_back((uint32_t) c);
+	}
 	const StepKernels<R> K = make_step_kernels<L, KIND, R>();
 	for (int32_t s = 0; s < nsteps; s++) {
 		const int64_t it = iteration + s;

@@ -386,6 +386,68 @@ def test_reference_duct_verification_solver(exe_name, args):
     print(exe_name, args, "l1 error:", l1[1], "->", l1[-1], "| last line:", r.stdout.strip().splitlines()[-1][:120])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe_name", ["channel3d", "channel3d_aa"])
+def test_deferred_batches_are_invisible_in_the_mirror(exe_name):
+    """execute() records the steps between two host-observable points and hands them to the engine as one lbmx_step(n) batch
+    (LBM_BLOCK::pending in lbmx_host.h; the reference copies to the host only on the cadence of its counters, state.hpp:1134-1142).
+    Everything the solver writes must be bit-identical to LBMX_HOST_BATCH=0 (one launch per SimUpdate, as the reference does)."""
+    exe = os.path.join(BIN, exe_name)
+    if not os.path.exists(exe):
+        pytest.skip(f"examples/bin/{exe_name} not built")
+    X, Y, Z, steps = 40, 16, 16, 61
+    out = {}
+    for mode in ("0", "1"):
+        with tempfile.TemporaryDirectory() as tmp:
+            r = subprocess.run([exe, str(X), str(Y), str(Z), str(steps), os.path.join(tmp, "run"), "dump"], capture_output=True, text=True, timeout=300, cwd=tmp,
+                               env=dict(os.environ, LBMX_HOST_BATCH=mode))
+            assert r.returncode == 0, r.stdout + r.stderr
+            m = re.search(r"lbmx: (\d+) steps enqueued in (\d+) batches", r.stdout)
+            assert m, r.stdout[-2000:]
+            files = {}
+            for dp, _, fs in os.walk(tmp):
+                for f in fs:
+                    if f.endswith((".bin", ".macro", ".map", ".df")):
+                        files[os.path.relpath(os.path.join(dp, f), tmp)] = open(os.path.join(dp, f), "rb").read()
+            out[mode] = (int(m.group(1)), int(m.group(2)), files, [ln for ln in r.stdout.splitlines() if "mass=" in ln])
+    assert out["0"][0] == out["1"][0] == steps
+    assert out["0"][1] == steps and out["1"][1] < steps / 2, f"batches: {out['0'][1]} without, {out['1'][1]} with deferral"
+    assert out["0"][2].keys() == out["1"][2].keys() and len(out["0"][2]) >= 3
+    for k in out["0"][2]:
+        assert out["0"][2][k] == out["1"][2][k], f"{k} differs between per-step launches and deferred batches"
+    assert out["0"][3] == out["1"][3]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exe_name,arg", [("ref_sim_2_aa", ["--min-resolution", "1", "--max-resolution", "1", "--final-time", "20", "--use-forcing"]), ("ref_sim_1_ab", ["1"]), ("ref_sim2d_1_ab", ["1"])])
+def test_unmodified_solvers_print_the_same_with_deferred_batches(exe_name, arg):
+    """The reference's own solvers: every number they print or dump (probe errors of sim_2.cu:193-262, cuts of sim_1 / sim2d_1, which
+    override updateKernelVelocities with a constant inflow) is the same with and without deferral."""
+    exe = os.path.join(BIN, exe_name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe_name} not built (needs /root/reference at build time)")
+    got = {}
+    for mode in ("0", "1"):
+        with tempfile.TemporaryDirectory() as tmp:
+            r = subprocess.run([exe] + arg, capture_output=True, text=True, timeout=900, cwd=tmp, env=dict(os.environ, LBMX_HOST_BATCH=mode))
+            assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+            m = re.findall(r"lbmx: (\d+) steps enqueued in (\d+) batches", r.stdout)
+            assert m, r.stdout[-2000:]
+            files = {}
+            for dp, _, fs in os.walk(tmp):
+                for f in fs:
+                    if f.endswith(".bin"):
+                        files[os.path.relpath(os.path.join(dp, f), tmp)] = open(os.path.join(dp, f), "rb").read()
+            keep = [ln.split("] ", 1)[-1] for ln in r.stdout.splitlines() if "error_phys" in ln]
+            got[mode] = ([(int(a), int(b)) for a, b in m], files, keep)
+    assert [a for a, _ in got["0"][0]] == [a for a, _ in got["1"][0]]
+    assert all(a == b for a, b in got["0"][0]) and all(b < a / 4 for a, b in got["1"][0]), (got["0"][0], got["1"][0])
+    assert got["0"][1].keys() == got["1"][1].keys()
+    for k in got["0"][1]:
+        assert got["0"][1][k] == got["1"][1][k], k
+    assert got["0"][2] == got["1"][2]
+
+
 def test_obstacle_painters_on_cpu():
     """lbm3d/obstacles_lbm.h (lbmDrawSphere / Cylinder / Cube / BoundingBox) paints exactly the cells the reference's formulas select
     (obstacles_lbm.h:3-87), checked against numpy; host-only, no engine."""

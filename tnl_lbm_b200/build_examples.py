@@ -3,6 +3,7 @@ binaries travel with the working tree to the GPU box):
 
   * examples/abi_minimal.c                     -- the C ABI from plain C99
   * examples/channel3d.cpp                     -- this repository's own solver in the reference's style (A-B and A-A builds)
+  * examples/box3d.cpp                         -- the bench workload (periodic box, body force) as an ordinary solver: the drop-in rate
   * /root/reference/sim_NSE/sim_1.cu,          -- the reference's UNMODIFIED solver sources, when the reference tree is present;
     /root/reference/sim_NSE/sim_2.cu, sim_3.cu,   their third-party includes (argparse, fmt, spdlog, magic_enum) are satisfied by the
     /root/reference/sim_2D/sim2d_1.cu, sim2d_3.cu stand-ins under tests/solver_shims (the reference fetches the real ones with CMake)
@@ -23,7 +24,9 @@ def build(reference: str = "/root/reference") -> list[str]:
     os.makedirs(BIN, exist_ok=True)
     built = []
     jobs = [("channel3d", [os.path.join(ROOT, "examples", "channel3d.cpp")], []),
-            ("channel3d_aa", [os.path.join(ROOT, "examples", "channel3d.cpp")], ["-DAA_PATTERN"])]
+            ("channel3d_aa", [os.path.join(ROOT, "examples", "channel3d.cpp")], ["-DAA_PATTERN"]),
+            ("box3d", [os.path.join(ROOT, "examples", "box3d.cpp")], []),
+            ("box3d_aa", [os.path.join(ROOT, "examples", "box3d.cpp")], ["-DAA_PATTERN"])]
     shims = [f"-I{ROOT}/tests/solver_shims"]
     for name, rel in (("ref_sim_1", "sim_NSE/sim_1.cu"), ("ref_sim_2", "sim_NSE/sim_2.cu"), ("ref_sim_3", "sim_NSE/sim_3.cu"), ("ref_sim2d_1", "sim_2D/sim2d_1.cu"), ("ref_sim2d_2", "sim_2D/sim2d_2.cu"), ("ref_sim2d_3", "sim_2D/sim2d_3.cu")):
         src = os.path.join(reference, rel)

@@ -129,11 +129,17 @@ int halo_dirs(int32_t* to_right, int32_t* to_left)
 struct IsBoundaryCell
 {
 	const int16_t* map;
-	int periodic;
+	int periodic, ndim, ox, X, Y, Z;
 	__host__ __device__ bool operator()(uint32_t c) const
 	{
 		const int m = map[c];
-		return m != 0 && m != periodic;	 // neither GEO_FLUID nor GEO_PERIODIC
+		if (m == 0 || m == periodic)
+			return false;  // GEO_FLUID, GEO_PERIODIC
+		if (m != 1)
+			return true;
+		// GEO_WALL (1 in every lattice): the bulk kernel bounces the walls away from the lattice faces itself (kernels.cuh: cell_in_boundary_list)
+		const int YZ = Y * Z, xs = (int) (c / (uint32_t) YZ), yz = (int) (c - (uint32_t) xs * (uint32_t) YZ), z = yz / Y;
+		return lbmx::cell_on_face(ndim, ox, X, Y, Z, xs - ox, yz - z * Y, z);
 	}
 };
 
@@ -142,14 +148,15 @@ struct IsBoundaryCell
 // per_plane[gridDim.y + 1] += (face_rule != 0) cells on a lattice face whose A-A neighbours lie outside the lattice: not GEO_NOTHING, not
 // wrapped, on a y/z face or (face_rule == 2: no ghost planes) an x face -- kernels.h:30-37 takes +-1 unclamped there
 __global__ void k_count_boundary_cells(const int16_t* map, long long first_cell, int YZ, int periodic, int reads_neighbour, unsigned* per_plane, int Y, int Z,
-									   int face_rule, int nothing)
+									   int face_rule, int nothing, int ndim, int ox)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	bool b = false, r = false, o = false;
+	bool b = false, r = false, o = false, w = false;
 	if (i < YZ) {
 		const int m = map[first_cell + (long long) blockIdx.y * YZ + i];
-		b = m != 0 && m != periodic;
+		b = lbmx::cell_in_boundary_list(m, 0, periodic, 1, lbmx::cell_on_face(ndim, ox, (int) gridDim.y, Y, Z, (int) blockIdx.y, i % Y, i / Y));
 		r = m == reads_neighbour;
+		w = m == 1 && ! b;	// GEO_WALL kept by the bulk kernel
 		if (face_rule && m != nothing && m != periodic) {  // periodic cells wrap (y, z always; x unless there are ghost planes)
 			const int y = i % Y, z = i / Y;
 			const bool yz_face = y == 0 || y == Y - 1 || (Z > 1 && (z == 0 || z == Z - 1));
@@ -160,7 +167,10 @@ __global__ void k_count_boundary_cells(const int16_t* map, long long first_cell,
 	const unsigned n = __popc(__ballot_sync(0xffffffffu, b));
 	const unsigned nr = __popc(__ballot_sync(0xffffffffu, r));
 	const unsigned no = __popc(__ballot_sync(0xffffffffu, o));
+	const unsigned nw = __popc(__ballot_sync(0xffffffffu, w));
 	if ((threadIdx.x & 31) == 0) {
+		if (nw)
+			atomicAdd(per_plane + gridDim.y + 2, nw);
 		if (n)
 			atomicAdd(per_plane + blockIdx.y, n);
 		if (nr)
@@ -249,6 +259,7 @@ struct lbmx_engine
 	// k_bulk_tma (A-A only): tile geometry, and which step parities go through it
 	int tile_y = 0, tile_y_shift = 0;
 	bool use_tma[3] = {false, false, false};  // by StreamMode
+	int64_t walls_in_bulk = 0;				  // GEO_WALL cells away from the faces: bounced by the bulk kernel (kernels.cuh: cell_in_boundary_list)
 
 	bool f64() const { return d.precision == LBMX_F64; }
 	bool aa() const { return d.streaming == LBMX_STREAM_AA; }
@@ -324,7 +335,7 @@ int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, 
 	p.x_begin = xb;
 	p.nb_begin = (int) e->plane_start[xb];
 	p.nb_end = (int) e->plane_start[xe];
-	if (e->use_tma[p.stream]) {
+	if (e->use_tma[p.stream] && e->walls_in_bulk == 0) {  // the experimental tile kernels know fluid cells only
 		// one CTA per tile of tile_y x (128 / tile_y) cells; the populations travel as bulk copies of the TMA engine (kernels_tma.cuh)
 		const int tz = tma::TILE / e->tile_y;
 		dim3 grid((unsigned) ((e->Y / e->tile_y) * ((e->Z + tz - 1) / tz)), (unsigned) (xe - xb));
@@ -1274,22 +1285,23 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 			return rc;
 		CU(cudaStreamSynchronize(e->s_main));
 	}
-	// launch plan: cells that are neither GEO_FLUID nor GEO_PERIODIC go to the boundary list, ordered by storage index
+	// launch plan: cells that are neither GEO_FLUID nor GEO_PERIODIC nor a GEO_WALL away from the faces go to the boundary list, ordered by storage index
 	// (so list ranges per x-plane are contiguous and neighbouring entries are neighbouring cells).  Counted and compacted on
 	// the device: the map never travels back to the host.
 	const int periodic = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::PERIODIC : (int) D3Q27::PERIODIC;	// D3Q19 shares the D3Q27 cell types
 	const long long first_cell = (long long) e->ox * e->YZ, n_cells = (long long) e->X * e->YZ;
 	const int outflow_right = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::OUTFLOW_RIGHT : (int) D3Q27::OUTFLOW_RIGHT;
 	unsigned* d_counts = nullptr;
-	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) (e->X + 2)));
-	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) (e->X + 2), e->s_main));
+	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) (e->X + 3)));
+	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) (e->X + 3), e->s_main));
 	const int nothing = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::NOTHING : (int) D3Q27::NOTHING;
+	const int ndim = e->d.lattice == LBMX_D2Q9 ? 2 : 3;
 	const int face_rule = ! e->aa() ? 0 : (e->ox == 0 ? 2 : 1);
 	k_count_boundary_cells<<<dim3((unsigned) ((e->YZ + 255) / 256), (unsigned) e->X), 256, 0, e->s_main>>>(e->map, first_cell, (int) e->YZ, periodic, outflow_right, d_counts,
-																											(int) e->Y, (int) e->Z, face_rule, nothing);
+																											(int) e->Y, (int) e->Z, face_rule, nothing, ndim, (int) e->ox);
 	e->stats.kernel_launches++;
-	std::vector<unsigned> counts((size_t) e->X + 2);
-	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) (e->X + 2), cudaMemcpyDeviceToHost, e->s_main));
+	std::vector<unsigned> counts((size_t) e->X + 3);
+	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) (e->X + 3), cudaMemcpyDeviceToHost, e->s_main));
 	CU(cudaStreamSynchronize(e->s_main));
 	CU(cudaFree(d_counts));
 	// Under A-A such a cell reads, in place, populations that the cell to its left rewrites in the same step (the reference has the
@@ -1309,7 +1321,7 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	if (e->nb > 0) {
 		CU(cudaMalloc(&e->blist, (size_t) e->nb * sizeof(uint32_t)));
 		cub::CountingInputIterator<uint32_t> cells((uint32_t) first_cell);
-		IsBoundaryCell pred{e->map, periodic};
+		IsBoundaryCell pred{e->map, periodic, ndim, (int) e->ox, (int) e->X, (int) e->Y, (int) e->Z};
 		int* d_selected = nullptr;
 		void* d_temp = nullptr;
 		size_t temp_bytes = 0;
@@ -1329,6 +1341,7 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	e->stats.boundary_cells = e->nb;
 	e->stats.bulk_cells = e->n_bulk;
 	e->stats.aa_cells_reaching_outside = counts[(size_t) e->X + 1];
+	e->walls_in_bulk = counts[(size_t) e->X + 2];
 	e->map_ready = true;
 	e->state_version++;
 	return LBMX_OK;

@@ -299,8 +299,39 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 	}
 }
 
+// full-way bounce-back: swap opposite populations, no collision (d3q27/bc.h:147-165).
+// REFERENCE QUIRK kept for parity: in D2Q9_BC_All::preCollision the coordinate parameters zm/zp shadow the direction enumerators
+// (d2q9/bc.h:90 vs defs.h:262-263), so its swap(f[zm], f[zp]) degenerates to a no-op on the X x Y x 1 lattice: the straight +-y
+// populations are NOT bounced (nor mirrored by SYM_TOP/SYM_BOTTOM).
+template <typename L, typename R>
+LBMX_D void bounce_back(R (&f)[L::Q])
+{
+	static_for<L::Q>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int o = L::opp(q);
+		if constexpr (o > q && ! (L::NDIM == 2 && L::cx(q) == 0)) {
+			const R t = f[q];
+			f[q] = f[o];
+			f[o] = t;
+		}
+	});
+}
+
+// Which kernel owns a cell.  The bulk kernel takes GEO_FLUID and GEO_PERIODIC cells and -- so that obstacle-heavy maps (spheres,
+// cylinders, porous blocks of GEO_WALL) stream every population exactly once -- GEO_WALL cells away from the lattice faces, where the
+// wrapping neighbour rule it loads with coincides with the rule of a non-periodic cell (kernels.h:30-56).  Everything else, and walls on
+// a face, goes to the boundary list.  Shared by lbmx_map_upload (list construction) and the kernels.
+LBMX_HD bool cell_on_face(int ndim, int ox, int X, int Y, int Z, int x, int y, int z)
+{
+	return (ox == 0 && (x == 0 || x == X - 1)) || y == 0 || y == Y - 1 || (ndim == 3 && (z == 0 || z == Z - 1));
+}
+LBMX_HD bool cell_in_boundary_list(int m, int fluid, int periodic, int wall, bool face)
+{
+	return ! (m == fluid || m == periodic || (m == wall && ! face));
+}
+
 // =====================================================================================================================
-// bulk kernel: GEO_FLUID / GEO_PERIODIC cells
+// bulk kernel: GEO_FLUID / GEO_PERIODIC cells, GEO_WALL cells away from the faces
 // =====================================================================================================================
 // resident CTAs per SM the register allocation is sized for: the cumulant / MRT_LES kernels fit 128 (A-A) and 96 (A-B)
 // registers without spilling; fp64 SRT and BGK keep f[27], feq[27] and the source terms live and get 170
@@ -357,7 +388,7 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 			// like GEO_PERIODIC ones; the reference leaves that case undefined (it steps out of the array: kernels.h:31-38,
 			// SURVEY.md App. A).  A-B: such cells clamp in the reference (kernels.h:49-56) -- they are re-loaded below.
 			d[k] = neighbour_deltas<true>(p, true, x, y, z);
-			face[k] = (p.ox == 0 && (x == 0 || x == p.X - 1)) || y == 0 || y == p.Y - 1 || z == 0 || z == p.Z - 1;
+			face[k] = cell_on_face(L::NDIM, p.ox, p.X, p.Y, p.Z, x, y, z);
 			stream_in<L, MODE, true>(p, f[k], c[k], d[k]);
 			if constexpr (MODE == S_AB) {
 				if (face[k] && m[k] == L::FLUID) {
@@ -370,9 +401,15 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 	// ---- phase 2: collide and store, cell by cell
 #pragma unroll
 	for (int k = 0; k < CPT; k++) {
-		if (m[k] < 0 || ! L::bulk(m[k]))
+		if (m[k] < 0 || cell_in_boundary_list(m[k], L::FLUID, L::PERIODIC, L::WALL, face[k]))
 			continue;
 		R rho, vx, vy, vz;
+		if (m[k] == L::WALL) {	// interior obstacle cell: reported rho = 1, u = 0 (bc.h:147-165)
+			bounce_back<L>(f[k]);
+			rho = R(1);
+			vx = vy = vz = R(0);
+		}
+		else {
 #ifdef LBMX_EXP_NOCOLLIDE  // development experiment only: streaming without arithmetic = the memory-system ceiling of this access pattern
 		rho = f[k][0];
 		vx = vy = vz = R(0);
@@ -380,6 +417,7 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 		density_velocity(f[k], p.phys, rho, vx, vy, vz);
 		collide<KIND>(f[k], p.phys, p.eq, rho, vx, vy, vz);
 #endif
+		}
 		stream_out<L, MODE, true>(p, f[k], c[k], d[k]);
 		output_macro<L>(p, c[k], rho, vx, vy, vz);
 	}
@@ -588,21 +626,8 @@ __global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
 		static_for<L::Q>([&](auto qc) { f[qc] += e1[qc] - e0[qc]; });  // setEquilibriumDecomposition (common.h:94-124)
 		rho = R(1);
 	}
-	else if (m == L::WALL) {
-		// full-way bounce-back: swap opposite populations, no collision (bc.h:147-165).
-		// REFERENCE QUIRK kept for parity: in D2Q9_BC_All::preCollision the coordinate parameters zm/zp shadow the
-		// direction enumerators (d2q9/bc.h:90 vs defs.h:262-263), so its swap(f[zm], f[zp]) degenerates to a no-op on
-		// the X x Y x 1 lattice: the straight +-y populations are NOT bounced (nor mirrored by SYM_TOP/SYM_BOTTOM).
-		static_for<L::Q>([&](auto qc) {
-			constexpr int q = qc;
-			constexpr int o = L::opp(q);
-			if constexpr (o > q && ! (L::NDIM == 2 && L::cx(q) == 0)) {
-				const R t = f[q];
-				f[q] = f[o];
-				f[o] = t;
-			}
-		});
-	}
+	else if (m == L::WALL)
+		bounce_back<L>(f);
 	else {
 		if (m == L::SYM_TOP)
 			mirror_pops<L, L::NDIM - 1, -1>(f);

@@ -975,7 +975,7 @@ struct LBM_BLOCK
 		DeviceBouzidi& operator=(const HostField& h)
 		{
 			if (owner && owner->engine && ! h.v.empty()) {
-				lbmx_host::check(lbmx_bouzidi_upload(owner->engine, h.v.data()), "lbmx_bouzidi_upload");
+				lbmx_host::check(lbmx_bouzidi_upload(owner->eng(), h.v.data()), "lbmx_bouzidi_upload");
 				uploaded = true;
 			}
 			return *this;
@@ -995,6 +995,34 @@ struct LBM_BLOCK
 	const dreal* uploaded_profile = nullptr;  // inflow profile last handed to the engine (pushParams)
 	int64_t uploaded_profile_sy = 0;
 	bool profile_uploaded = false;
+
+	// Deferred stepping.  The reference launches one kernel per SimUpdate and copies the macroscopic fields to the host only on the
+	// cadence of its counters (state.hpp:1029-1042, 1134-1142); between two such points nothing on the host can see the device.
+	// step(defer = true) therefore only RECORDS the step; the recorded steps go to the engine as ONE lbmx_step(n) batch (graph replay
+	// on small lattices, rho/u written by the last step only -- LBMX_MACRO_LAST_STEP) as soon as anything needs the device state:
+	// every method of this block that touches the engine goes through eng(), which flushes first.  A step whose parameters differ
+	// from the recorded ones (viscosity, force, inflow, gates; stat_counter is expected to advance by one per step, as the engine
+	// advances it) closes the batch.  Values at every point the host can observe are bit-identical to stepping one at a time.
+	int64_t pending = 0;		 // steps recorded and not yet enqueued
+	lbmx_params pending_prm{};	 // their parameters (stat_counter: of the first recorded step)
+	int64_t steps_enqueued = 0;	 // diagnostics: steps / batches handed to lbmx_step
+	int64_t batches_enqueued = 0;
+	static constexpr int64_t max_pending = 256;	 // bounds how far the host loop (wall-time checks, flag files) runs ahead of the device
+	void flush()
+	{
+		if (pending > 0) {
+			const int64_t n = pending;
+			pending = 0;
+			lbmx_host::check(lbmx_step(engine, n), "lbmx_step");
+			steps_enqueued += n;
+			batches_enqueued++;
+		}
+	}
+	lbmx_engine* eng()
+	{
+		flush();
+		return engine;
+	}
 
 	LBM_BLOCK(idx3d global_, idx3d local_, idx3d offset_) : global(global_), local(local_), offset(offset_) { dBouzidi.owner = this; }
 	LBM_BLOCK(const LBM_BLOCK&) = delete;
@@ -1074,7 +1102,7 @@ struct LBM_BLOCK
 		d.macro = CONFIG::lbmx_macro;
 		d.inflow = CONFIG::lbmx_inflow;
 		d.precision = CONFIG::lbmx_precision;
-		d.macro_policy = LBMX_MACRO_EVERY_STEP;	 // the drop-in keeps the reference's observable behaviour; solvers may relax it
+		d.macro_policy = LBMX_MACRO_LAST_STEP;	 // rho,u by the last step of each batch; a batch is one step unless execute() defers (LBM_BLOCK::pending)
 		if (const char* v = std::getenv("LBMX_STRICT_ARITH"))  // run an unmodified solver in the reference's own rounding (lbmx.h: LBMX_FLAG_STRICT_ARITH)
 			if (v[0] && v[0] != '0')
 				d.flags |= LBMX_FLAG_STRICT_ARITH;
@@ -1109,13 +1137,26 @@ struct LBM_BLOCK
 	{
 		lbmx_ptrs p{};
 		lbmx_host::check(lbmx_get_device_ptrs(engine, &p), "lbmx_get_device_ptrs");
+		// with steps recorded but not yet enqueued: parity and A-B rotation as they will be once those have run (lbm.hpp:320-327)
+		const bool flip = (pending & 1) != 0;
 		data.dfs[df_cur] = (dreal*) p.dfs[0];
 #if defined(AB_PATTERN)
-		data.dfs[df_out] = (dreal*) p.dfs[1];
+		data.dfs[df_cur] = (dreal*) p.dfs[flip ? 1 : 0];
+		data.dfs[df_out] = (dreal*) p.dfs[flip ? 0 : 1];
 #endif
 		data.dmacro = (dreal*) p.dmacro;
 		data.dmap = (map_t*) p.dmap;
-		data.even_iter = p.even_iter != 0;
+		data.even_iter = (p.even_iter != 0) != flip;
+	}
+	// LBM::updateKernelData sets the iteration the next step runs as; a no-op while the recorded steps account for the difference
+	void setIterations(int64_t it)
+	{
+		int64_t have = 0;
+		lbmx_host::check(lbmx_get_iterations(engine, &have), "lbmx_get_iterations");
+		if (have + pending == it)
+			return;
+		flush();
+		lbmx_host::check(lbmx_set_iterations(engine, it), "lbmx_set_iterations");
 	}
 	void allocateBouzidiCoeffArrays()
 	{
@@ -1128,7 +1169,7 @@ struct LBM_BLOCK
 	// also moves the Bouzidi coefficients when they are allocated, like the reference (lbm_block.hpp:355-364)
 	void copyMapToDevice()
 	{
-		lbmx_host::check(lbmx_map_upload(engine, hmap.v.data(), 0), "lbmx_map_upload");
+		lbmx_host::check(lbmx_map_upload(eng(), hmap.v.data(), 0), "lbmx_map_upload");
 		if (hBouzidi.getData() != nullptr)
 			dBouzidi = hBouzidi;
 		lbmx_stats st{};
@@ -1140,16 +1181,16 @@ struct LBM_BLOCK
 		}
 	}
 	bool warned_aa_faces = false;
-	void copyMapToHost() { lbmx_host::check(lbmx_map_download(engine, hmap.v.data(), 0), "lbmx_map_download"); }
+	void copyMapToHost() { lbmx_host::check(lbmx_map_download(eng(), hmap.v.data(), 0), "lbmx_map_download"); }
 	void copyMacroToHost()
 	{
 		if (MACRO::N > 0)
-			lbmx_host::check(lbmx_macro_download(engine, hmacro.v.data(), 0), "lbmx_macro_download");
+			lbmx_host::check(lbmx_macro_download(eng(), hmacro.v.data(), 0), "lbmx_macro_download");
 	}
 	void copyMacroToDevice()
 	{
 		if (MACRO::N > 0)
-			lbmx_host::check(lbmx_macro_upload(engine, hmacro.v.data(), 0), "lbmx_macro_upload");
+			lbmx_host::check(lbmx_macro_upload(eng(), hmacro.v.data(), 0), "lbmx_macro_upload");
 	}
 	void copyDFsToHost(uint8_t dftype)
 	{
@@ -1159,27 +1200,27 @@ struct LBM_BLOCK
 		h.off = offset;
 		h.loc = local;
 		h.n = n;
-		lbmx_host::check(lbmx_df_download(engine, dftype == df_cur ? 0 : 1, h.v.data(), 0), "lbmx_df_download");
+		lbmx_host::check(lbmx_df_download(eng(), dftype == df_cur ? 0 : 1, h.v.data(), 0), "lbmx_df_download");
 	}
-	void copyDFsToDevice(uint8_t dftype) { lbmx_host::check(lbmx_df_upload(engine, dftype == df_cur ? 0 : 1, hfs[dftype].v.data(), 0), "lbmx_df_upload"); }
-	void setEquilibrium(real rho, real vx, real vy, real vz) { lbmx_host::check(lbmx_df_set_equilibrium(engine, rho, vx, vy, vz), "lbmx_df_set_equilibrium"); }
-	void computeInitialMacro() { lbmx_host::check(lbmx_macro_init(engine), "lbmx_macro_init"); }
+	void copyDFsToDevice(uint8_t dftype) { lbmx_host::check(lbmx_df_upload(eng(), dftype == df_cur ? 0 : 1, hfs[dftype].v.data(), 0), "lbmx_df_upload"); }
+	void setEquilibrium(real rho, real vx, real vy, real vz) { lbmx_host::check(lbmx_df_set_equilibrium(eng(), rho, vx, vy, vz), "lbmx_df_set_equilibrium"); }
+	void computeInitialMacro() { lbmx_host::check(lbmx_macro_init(eng()), "lbmx_macro_init"); }
 
 	// Checkpoint variables of this block (state.hpp:712-727): map, every DF copy and the macro array in LOCAL STORAGE shape, i.e.
 	// ghost x-planes included, moved straight between the engine and the checkpoint (no second host copy of 29 GB of DFs).
 	void checkpoint(CheckpointManager& ck)
 	{
 		lbmx_layout L{};
-		lbmx_host::check(lbmx_get_layout(engine, &L), "lbmx_get_layout");
+		lbmx_host::check(lbmx_get_layout(eng(), &L), "lbmx_get_layout");
 		const bool save = ck.getMode() == adios2::Mode::Write;
 		const std::string blk = "_block_" + std::to_string(id);
 		{
 			std::vector<map_t> m((size_t) L.XYZ);
 			if (save)
-				lbmx_host::check(lbmx_map_download(engine, m.data(), 1), "lbmx_map_download");
+				lbmx_host::check(lbmx_map_download(eng(), m.data(), 1), "lbmx_map_download");
 			ck.saveLoadRaw("LBM_map" + blk, m.data(), m.size());
 			if (! save) {
-				lbmx_host::check(lbmx_map_upload(engine, m.data(), 1), "lbmx_map_upload");
+				lbmx_host::check(lbmx_map_upload(eng(), m.data(), 1), "lbmx_map_upload");
 				copyMapToHost();
 			}
 		}
@@ -1187,18 +1228,18 @@ struct LBM_BLOCK
 		for (int dfty = 0; dfty < L.dfmax; dfty++) {
 			const size_t n = (size_t) L.XYZ * L.Q;
 			if (save)
-				lbmx_host::check(lbmx_df_download(engine, dfty, a.data(), 1), "lbmx_df_download");
+				lbmx_host::check(lbmx_df_download(eng(), dfty, a.data(), 1), "lbmx_df_download");
 			ck.saveLoadRaw("LBM_df_" + std::to_string(dfty) + blk, a.data(), n);
 			if (! save)
-				lbmx_host::check(lbmx_df_upload(engine, dfty, a.data(), 1), "lbmx_df_upload");
+				lbmx_host::check(lbmx_df_upload(eng(), dfty, a.data(), 1), "lbmx_df_upload");
 		}
 		if (MACRO::N > 0) {
 			const size_t n = (size_t) L.XYZ * L.n_macro;
 			if (save)
-				lbmx_host::check(lbmx_macro_download(engine, a.data(), 1), "lbmx_macro_download");
+				lbmx_host::check(lbmx_macro_download(eng(), a.data(), 1), "lbmx_macro_download");
 			ck.saveLoadRaw("LBM_macro" + blk, a.data(), n);
 			if (! save) {
-				lbmx_host::check(lbmx_macro_upload(engine, a.data(), 1), "lbmx_macro_upload");
+				lbmx_host::check(lbmx_macro_upload(eng(), a.data(), 1), "lbmx_macro_upload");
 				copyMacroToHost();
 			}
 		}
@@ -1273,7 +1314,7 @@ struct LBM_BLOCK
 	}
 
 	// block.data -> lbmx_params (what passing the POD by value to the kernel did in the reference, state.hpp:1039)
-	void pushParams()
+	lbmx_params makeParams() const
 	{
 		lbmx_params p{};
 		p.lbmViscosity = data.lbmViscosity;
@@ -1294,23 +1335,68 @@ struct LBM_BLOCK
 		p.stat_counter = data.stat_counter;
 		if constexpr (lbmx_host::has_accumulate_gates<typename CONFIG::DATA>::value)  // gates of D2Q9_MACRO_WithMean (sim_2D/sim2d_2.cu:121-122)
 			p.macro_gates = (data.accumulate_means ? LBMX_GATE_MEANS : 0) | (data.accumulate_flucs ? LBMX_GATE_FLUCS : 0);
-		lbmx_host::check(lbmx_set_params(engine, &p), "lbmx_set_params");
+		return p;
+	}
+	// NSE_Data_XProfileInflow (sim_NSE/sim_2.cu:16-33): the solver owns a host array dreal[y + z * size_y]; it is uploaded when the
+	// pointer or its size changes.  Without a profile (periodic runs with forcing) the inflow cells do not exist: a zero profile.
+	bool profileChanged() const
+	{
 		if constexpr (lbmx_host::has_vx_profile<typename CONFIG::DATA>::value) {
-			// NSE_Data_XProfileInflow (sim_NSE/sim_2.cu:16-33): the solver owns a host array dreal[y + z * size_y]; it is uploaded when the
-			// pointer or its size changes.  Without a profile (periodic runs with forcing) the inflow cells do not exist: a zero profile.
+			const int64_t sy = data.vx_profile ? (int64_t) data.size_y : (int64_t) local.y();
+			return data.vx_profile != uploaded_profile || sy != uploaded_profile_sy || ! profile_uploaded;
+		}
+		return false;
+	}
+	void pushProfile()
+	{
+		if constexpr (lbmx_host::has_vx_profile<typename CONFIG::DATA>::value) {
+			if (! profileChanged())
+				return;
 			const dreal* src = data.vx_profile;
 			const int64_t sy = src ? (int64_t) data.size_y : (int64_t) local.y();
-			if (src != uploaded_profile || sy != uploaded_profile_sy || ! profile_uploaded) {
-				std::vector<dreal> zeros;
-				if (! src) {
-					zeros.assign((size_t) local.y() * local.z(), (dreal) 0);
-					src = zeros.data();
-				}
-				lbmx_host::check(lbmx_set_inflow_profile(engine, src, sy, (int64_t) local.z()), "lbmx_set_inflow_profile");
-				uploaded_profile = data.vx_profile;
-				uploaded_profile_sy = sy;
-				profile_uploaded = true;
+			std::vector<dreal> zeros;
+			if (! src) {
+				zeros.assign((size_t) local.y() * local.z(), (dreal) 0);
+				src = zeros.data();
 			}
+			lbmx_host::check(lbmx_set_inflow_profile(eng(), src, sy, (int64_t) local.z()), "lbmx_set_inflow_profile");
+			uploaded_profile = data.vx_profile;
+			uploaded_profile_sy = sy;
+			profile_uploaded = true;
+		}
+	}
+	void pushParams()
+	{
+		const lbmx_params p = makeParams();
+		lbmx_host::check(lbmx_set_params(eng(), &p), "lbmx_set_params");
+		pushProfile();
+	}
+	// One time step with block.data as it stands now (the kernel launch of state.hpp:1034-1108).  defer: record it (see `pending`).
+	void step(bool defer)
+	{
+		const lbmx_params p = makeParams();
+		if (pending > 0) {
+			// stat_counter is read by the running means of MACRO_Mean only (d3q27/macro.h:120): there the engine advances it by one per
+			// step of a batch, so the solver's value has to advance the same way for the batch to continue; elsewhere it is unused
+			lbmx_params expect = pending_prm;
+			if (CONFIG::lbmx_macro == LBMX_MACRO_MEAN)
+				expect.stat_counter += (int) pending;
+			else
+				expect.stat_counter = p.stat_counter;
+			if (std::memcmp(&p, &expect, sizeof p) != 0 || profileChanged())
+				flush();
+		}
+		if (pending == 0) {
+			lbmx_host::check(lbmx_set_params(engine, &p), "lbmx_set_params");
+			pushProfile();
+			pending_prm = p;
+		}
+		pending++;
+		if (! defer)
+			flush();
+		else if (pending >= max_pending) {
+			lbmx_host::check(lbmx_sync(engine), "lbmx_sync");  // at most one batch in flight: the host loop stays within max_pending steps of the device
+			flush();
 		}
 	}
 };
@@ -1346,6 +1432,7 @@ struct LBM
 	int iterations = 0;
 	int startIterations = 0;
 	bool terminate = false;
+	bool defer_steps = false;  // set by execute() when the solver overrides none of the per-step hooks that could look at the device (LBM_BLOCK::pending)
 
 	LBM() = delete;
 	LBM(const LBM&) = delete;
@@ -1448,7 +1535,7 @@ struct LBM
 	void updateKernelData()
 	{
 		for (auto& b : blocks) {
-			lbmx_host::check(lbmx_set_iterations(b.engine, iterations), "lbmx_set_iterations");
+			b.setIterations(iterations);
 			b.refreshPointers();
 		}
 	}
@@ -1495,6 +1582,7 @@ struct State
 	using idx3d = typename TRAITS::idx3d;
 	using lat_t = typename LBM<NSE>::lat_t;
 	using T_COUNTER = counter<real>;
+	using lbmx_state_base = State;	// lets execute() tell inherited hooks from overridden ones
 
 	std::string id;
 	LBM<NSE> nse;
@@ -1798,10 +1886,8 @@ struct State
 			return;
 		}
 		computeBeforeLBMKernel();
-		for (auto& b : nse.blocks) {
-			b.pushParams();
-			lbmx_host::check(lbmx_step(b.engine, 1), "lbmx_step");
-		}
+		for (auto& b : nse.blocks)
+			b.step(nse.defer_steps);
 		nse.iterations++;
 		bool doCopy = false;
 		for (int c = 0; c < MAX_COUNTER; c++)
@@ -1825,7 +1911,7 @@ struct State
 		bool nan_detected = false;
 		if (nse.iterations > 1 && write_info && MACRO::N > 0) {
 			int32_t nan = 0;
-			lbmx_host::check(lbmx_has_nan(nse.blocks.front().engine, &nan), "lbmx_has_nan");
+			lbmx_host::check(lbmx_has_nan(nse.blocks.front().eng(), &nan), "lbmx_has_nan");
 			nan_detected = TNL::MPI::reduce(nan != 0, MPI_LOR, nse.communicator);  // every rank takes the same decision (state.hpp:1166-1188)
 			if (nan_detected) {
 				lbmx_host::log_info("Detected NaN, terminating the simulation.");
@@ -1874,7 +1960,7 @@ struct State
 		}
 		if (write_info && nse.iterations > 1 && nse.rank == 0) {
 			for (auto& b : nse.blocks)
-				lbmx_host::check(lbmx_sync(b.engine), "lbmx_sync");
+				lbmx_host::check(lbmx_sync(b.eng()), "lbmx_sync");
 			const double now = timer_total.getRealTime();
 			const double glups = (nse.iterations - glups_prev_iterations) / std::max(1e-6, now - glups_prev_time) * (double) nse.lat.global.x()
 							   * (double) nse.lat.global.y() * (double) nse.lat.global.z() * 1e-9;
@@ -1887,11 +1973,14 @@ struct State
 	virtual void AfterSimFinished()
 	{
 		for (auto& b : nse.blocks)
-			lbmx_host::check(lbmx_sync(b.engine), "lbmx_sync");
+			lbmx_host::check(lbmx_sync(b.eng()), "lbmx_sync");
 		const double total = timer_total.getRealTime(), upd = timer_SimUpdate.getRealTime();
 		const double cells = (double) nse.lat.global.x() * (double) nse.lat.global.y() * (double) nse.lat.global.z();
 		lbmx_host::log_info("total walltime: %.1f s, SimInit time: %.1f s, SimUpdate time: %.1f s", total, timer_SimInit.getRealTime(), upd);
 		lbmx_host::log_info("final GLUPS: average (based on total time) %.3f", cells * nse.iterations / (total + 1e-30) * 1e-9);
+		if (! nse.blocks.empty())
+			lbmx_host::log_info("lbmx: %lld steps enqueued in %lld batches (%s)", (long long) nse.blocks.front().steps_enqueued, (long long) nse.blocks.front().batches_enqueued,
+								nse.defer_steps ? "steps between host-observable points travel together" : "one batch per SimUpdate");
 	}
 	virtual void computeBeforeLBMKernel() {}
 	virtual void computeAfterLBMKernel() {}
@@ -1958,7 +2047,7 @@ struct State
 			checkpoint.saveLoadAttribute("State_probe1Dline_" + std::to_string(i) + "_cycle", probe1Dlinevec[i].cycle);
 		for (auto& block : nse.blocks) {
 			if (mode == adios2::Mode::Read)	 // "df_cur" / "df_out" are roles that rotate with the iteration count (lbm.hpp:314-330): restore it first
-				lbmx_host::check(lbmx_set_iterations(block.engine, nse.iterations), "lbmx_set_iterations");
+				block.setIterations(nse.iterations);
 			block.checkpoint(checkpoint);
 		}
 		if (mode == adios2::Mode::Read) {
@@ -2029,9 +2118,29 @@ struct State
 // ---------------------------------------------------------------------------------------------------------------------------
 // core.h: the time loop (include/lbm3d/core.h:38-101)
 // ---------------------------------------------------------------------------------------------------------------------------
+namespace lbmx_host {
+// true when STATE inherits State<NSE>::NAME unchanged: &STATE::NAME then still has the base's member-pointer type
+#define LBMX_NOT_OVERRIDDEN(STATE, NAME) std::is_same<decltype(&STATE::NAME), void (STATE::lbmx_state_base::*)()>::value
+template <typename STATE>
+constexpr bool steps_can_be_deferred()
+{
+	// hooks that run between two kernel launches and may look at the device through raw pointers (block.data.dmacro / dfs) or launch
+	// kernels of their own; updateKernelData / updateKernelVelocities only set block.data on the host and are called every step anyway
+	return LBMX_NOT_OVERRIDDEN(STATE, SimUpdate) && LBMX_NOT_OVERRIDDEN(STATE, AfterSimUpdate) && LBMX_NOT_OVERRIDDEN(STATE, computeBeforeLBMKernel)
+		&& LBMX_NOT_OVERRIDDEN(STATE, computeAfterLBMKernel);
+}
+#undef LBMX_NOT_OVERRIDDEN
+}  // namespace lbmx_host
+
 template <typename STATE>
 void execute(STATE& state)
 {
+	// Steps between two points where the host looks at the device travel as one batch (LBM_BLOCK::pending), unless the solver overrides a
+	// hook that could observe the device in between, or LBMX_HOST_BATCH=0 asks for one launch per SimUpdate as in the reference.
+	{
+		const char* v = std::getenv("LBMX_HOST_BATCH");
+		state.nse.defer_steps = lbmx_host::steps_can_be_deferred<STATE>() && ! (v && v[0] == '0');
+	}
 	state.SimInit();
 	state.AfterSimUpdate();	 // snapshot of the initial condition
 	bool quit = false;

@@ -2,7 +2,9 @@
 // Compiled several times with different -D tuning macros (see tools/kbench.sh); runs the KB_LAT / KB_KIND bulk kernels on an
 // all-GEO_PERIODIC box and reports the average even / odd / A-B step time measured with CUDA events, for the plain kernels and for the
 // TMA kernels (k_bulk_tma), with and without the macroscopic output, and checks that both kernel flavours leave identical bits.
-//   kbench [S] [iters] [macro: 0 none | 1 rho,u every step | 2 MACRO_Mean]
+//   kbench [S] [iters] [macro: 0 none | 1 rho,u every step | 2 MACRO_Mean] [field: 0 uniform | 1 the bench's sinusoidal field] [chain: 0 | 1]
+//   chain = 1 adds a line for 2*iters A-A steps enqueued back to back (no host synchronisation between kernels), timed as one region --
+//   what lbmx_step() does; the per-kernel figures above it are taken with a synchronisation after every kernel.
 #include "../tnl_lbm_b200/csrc/kernels.cuh"
 #include "../tnl_lbm_b200/csrc/tma_host.h"
 #include <cstdio>
@@ -34,6 +36,19 @@ __global__ void k_count_diff(const R* a, const R* b, long long n, unsigned long 
 		atomicAdd(cnt, local);
 }
 
+__global__ void k_bench_field(double* rho, double* vx, double* vy, double* vz, int S, int SZ)
+{
+	// bench.py initial_fields(): rho = 1 + 0.01 sin(2 pi x / X), vx = 0.05 sin(2 pi y / Y), vy = 0.02 cos(2 pi z / Z), vz = 0.01
+	const long long n = (long long) S * S * SZ;
+	for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+		const int y = (int) (i % S), z = (int) ((i / S) % SZ), x = (int) (i / ((long long) S * SZ));
+		rho[i] = 1.0 + 0.01 * sin(2.0 * 3.14159265358979323846 * x / S);
+		vx[i] = 0.05 * sin(2.0 * 3.14159265358979323846 * y / S);
+		vy[i] = 0.02 * cos(2.0 * 3.14159265358979323846 * z / SZ);
+		vz[i] = 0.01;
+	}
+}
+
 int main(int argc, char** argv)
 {
 	using R = KB_REAL;
@@ -41,6 +56,8 @@ int main(int argc, char** argv)
 	const int S = argc > 1 ? atoi(argv[1]) : 256;
 	const int iters = argc > 2 ? atoi(argv[2]) : 20;
 	const int macro = argc > 3 ? atoi(argv[3]) : 0;
+	const int field = argc > 4 ? atoi(argv[4]) : 0;
+	const int chain = argc > 5 ? atoi(argv[5]) : 0;
 	const int SZ = L::NDIM == 3 ? S : 1;
 	const long long XYZ = (long long) S * S * SZ;
 	const int NM = macro == 2 ? (L::NDIM == 3 ? 13 : 8) : 4;
@@ -56,7 +73,16 @@ int main(int argc, char** argv)
 	std::vector<int16_t> hm(XYZ, (int16_t) L::PERIODIC);
 	CK(cudaMemcpy(map, hm.data(), sizeof(int16_t) * XYZ, cudaMemcpyHostToDevice));
 	auto init = [&]() {
-		k_set_equilibrium<L, R><<<(unsigned) ((XYZ + 127) / 128), 128>>>(a, XYZ, XYZ, 0, L::Q == 27 ? 1 : 0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.03, 0.01, L::NDIM == 3 ? -0.02 : 0.0);
+		if (field) {
+			double* fld;
+			CK(cudaMalloc(&fld, sizeof(double) * 4 * XYZ));
+			k_bench_field<<<1184, 256>>>(fld, fld + XYZ, fld + 2 * XYZ, fld + 3 * XYZ, S, SZ);
+			k_set_equilibrium<L, R><<<(unsigned) ((XYZ + 127) / 128), 128>>>(a, XYZ, XYZ, 0, L::Q == 27 ? 1 : 0, fld, fld + XYZ, fld + 2 * XYZ, fld + 3 * XYZ, 1.0, 0.0, 0.0, 0.0);
+			CK(cudaDeviceSynchronize());
+			CK(cudaFree(fld));
+		}
+		else
+			k_set_equilibrium<L, R><<<(unsigned) ((XYZ + 127) / 128), 128>>>(a, XYZ, XYZ, 0, L::Q == 27 ? 1 : 0, nullptr, nullptr, nullptr, nullptr, 1.0, 0.03, 0.01, L::NDIM == 3 ? -0.02 : 0.0);
 		CK(cudaDeviceSynchronize());
 	};
 	init();
@@ -112,6 +138,23 @@ int main(int argc, char** argv)
 			CK(cudaMalloc(&ref, sizeof(R) * L::Q * XYZ));
 			CK(cudaMemcpy(ref, a, sizeof(R) * L::Q * XYZ, cudaMemcpyDeviceToDevice));
 		}
+	}
+	if (chain) {
+		init();
+		set_bases(true);
+		float ms = 0;
+		for (int rep = 0; rep < 2; rep++) {	 // the first repetition warms up
+			CK(cudaEventRecord(e0));
+			for (int it = 0; it < 2 * iters; it++) {
+				p.stat_counter = it;
+				if ((it & 1) == 0) k_bulk<L, KB_KIND, R, S_AA_EVEN><<<grid_e, BS>>>(p); else k_bulk<L, KB_KIND, R, S_AA_ODD><<<grid_o, BS>>>(p);
+			}
+			CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+			CK(cudaEventElapsedTime(&ms, e0, e1));
+		}
+		printf("%-22s S=%d macro=%d field=%d CHAINED %d steps: %.4f ms per step, %.0f GB/s, %.0f MLUPS\n", KB_NAME, S, macro, field, 2 * iters, ms / (2 * iters), bytes / (ms / (2 * iters)) / 1e6,
+			   XYZ / (ms / (2 * iters)) / 1e3);
+		fflush(stdout);
 	}
 	unsigned long long diff = 0;
 	if (have_tma) {
