@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../../oracle/oracle_api.h"
@@ -26,6 +27,7 @@
 	#define __global__
 	#define __forceinline__ inline
 	#define __launch_bounds__(...)
+	#define __noinline__
 using std::sqrt;
 struct HkDim3
 {
@@ -182,9 +184,22 @@ int step_family(const oracle_desc* d, const oracle_params* op, void* df_a, void*
 	std::vector<uint32_t> blist;
 	for (long long c = (long long) d->ox * YZ; c < (long long) (d->ox + d->X) * YZ; c++) {
 		const int xs = (int) (c / YZ), yz = (int) (c - (long long) xs * YZ), z = yz / (int) d->Y;
-		if (cell_in_boundary_list(map[c], (int) L::FLUID, (int) L::PERIODIC, (int) L::WALL, cell_on_face(L::NDIM, (int) d->ox, (int) d->X, (int) d->Y, (int) d->Z, xs - (int) d->ox, yz - z * (int) d->Y, z)))
+		if (cell_in_boundary_list(map[c], (int) L::FLUID, (int) L::PERIODIC, (int) L::WALL, (int) L::NOTHING, cell_on_face(L::NDIM, (int) d->ox, (int) d->X, (int) d->Y, (int) d->Z, xs - (int) d->ox, yz - z * (int) d->Y, z)))
 			blist.push_back((uint32_t) c);
 	}
+	// inert-chunk flags (lbmx_map_upload builds them for maps with sizeable GEO_NOTHING regions; here: whenever such a cell exists)
+	const int stride = (YZ + LBMX_BULK_BLOCK - 1) / LBMX_BULK_BLOCK;
+	std::vector<uint8_t> inert((size_t) stride * (size_t) (d->X + 2 * d->ox), 0);
+	bool any_inert = false;
+	for (long long xs = d->ox; xs < d->ox + d->X; xs++)
+		for (int ch = 0; ch < stride; ch++) {
+			bool all = true;
+			for (int i = ch * LBMX_BULK_BLOCK; i < std::min(YZ, (ch + 1) * LBMX_BULK_BLOCK); i++) {
+				all = all && map[xs * YZ + i] == (int) L::NOTHING;
+				any_inert = any_inert || map[xs * YZ + i] == (int) L::NOTHING;
+			}
+			inert[(size_t) xs * stride + ch] = all ? 1 : 0;
+		}
 	const StepKernels<R> K = make_step_kernels<L, KIND, R>();
 	for (int32_t s = 0; s < nsteps; s++) {
 		const int64_t it = iteration + s;
@@ -193,6 +208,8 @@ int step_family(const oracle_desc* d, const oracle_params* op, void* df_a, void*
 		KParams<R> p = params_for<L, R>(d, op, cur, out, (R*) macro, map, blist.data(), (int) blist.size(), it);
 		p.out_mode = out_mode_of(d, op);
 		p.stat_counter = op->stat_counter + s;
+		p.inert = any_inert ? inert.data() : nullptr;
+		p.inert_stride = stride;
 		const int per_cta = LBMX_BULK_BLOCK * K.cpt[p.stream];
 		launch(K.bulk[p.stream], (unsigned) ((YZ + per_cta - 1) / per_cta), (unsigned) d->X, LBMX_BULK_BLOCK, p);
 		if (! blist.empty())

@@ -160,9 +160,10 @@ def map_sim2d1_channel(d: O.Desc) -> np.ndarray:
     return m
 
 
-def rel_err(a: np.ndarray, b: np.ndarray) -> float:
-    """max |a-b| / max|b| -- the norm used for fields that cross zero (velocities)."""
-    scale = float(np.max(np.abs(b)))
+def rel_err(a: np.ndarray, b: np.ndarray, floor: float = 0.0) -> float:
+    """max |a-b| / max|b| -- the norm used for fields that cross zero (velocities).  floor: lower bound of the scale, for flows that
+    have barely left rest (|u| ~ 1e-4: one ulp of the O(1) population sums is then 1e-12 of it)."""
+    scale = max(float(np.max(np.abs(b))), floor)
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) / (scale if scale > 0 else 1.0)
 
 

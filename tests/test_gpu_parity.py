@@ -134,12 +134,12 @@ def test_map_round_trip_is_bit_exact():
         e.map_upload(m)
         assert np.array_equal(e.map_download(), m)
         st = e.stats()
-        # the bulk kernel keeps GEO_FLUID (0), GEO_PERIODIC (7) and the GEO_WALL (1) cells away from the lattice faces (kernels.cuh: cell_in_boundary_list)
+        # the bulk kernel keeps GEO_FLUID (0), GEO_PERIODIC (7), GEO_NOTHING (8) and the GEO_WALL (1) cells away from the lattice faces (kernels.cuh: cell_in_boundary_list)
         face = np.zeros(m.shape, dtype=bool)  # map arrays are (x, z, y)
         face[0] = face[-1] = True
         face[:, 0] = face[:, -1] = True
         face[:, :, 0] = face[:, :, -1] = True
-        assert st.boundary_cells == int(np.sum((m != 0) & (m != 7) & ~((m == 1) & ~face)))
+        assert st.boundary_cells == int(np.sum((m != 0) & (m != 7) & (m != 8) & ~((m == 1) & ~face)))
         assert st.bulk_cells + st.boundary_cells == m.size
 
 
@@ -187,10 +187,12 @@ def test_nan_scan():
         assert e.has_nan()
 
 
+@pytest.mark.parametrize("size", [32, 64])
 @pytest.mark.parametrize("streaming", [O.AA, O.AB])
-def test_1000_steps_cumulant_fp64_box(streaming):
-    """SURVEY §8d cfg 3 on a 32^3 copy: D3Q27 cumulant fp64, periodic box, smooth field + body force, 1000 steps."""
-    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, X=32, Y=32, Z=32)
+def test_1000_steps_cumulant_fp64_box(streaming, size):
+    """SURVEY §8d cfg 3: D3Q27 cumulant fp64, periodic box, the bench field (smooth) + body force, 1000 steps, on the 64^3 copy the
+    survey names and on a 32^3 one; tolerance 1e-12 (BASELINE.json north_star)."""
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, X=size, Y=size, Z=size)
     case = gc.Case("box1000", d, O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 1000, "smooth")
     df, mac, _ = run_case_engine(case)
     df_ref, mac_ref = gc.run_case(case, "port", nthreads=os.cpu_count() or 4)

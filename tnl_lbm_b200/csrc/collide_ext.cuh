@@ -462,6 +462,25 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 		Qxyz = (rQxyz - vx * Pyz - vy * Pxz - vz * Pxy - vx * vy * vz);
 		eT = (rho * three * third);
 	}
+	// Default arithmetic, raw-moment models: the shear tensors are linear in the moments, so the equilibrium moments are subtracted once
+	// here (13 values live instead of 26) instead of per direction as the reference does (col_kbc_n.h:56-252); parity arithmetic keeps
+	// the reference's association.
+	constexpr bool FOLD = ! EXACT && ! CENTRAL;
+	if constexpr (FOLD) {
+		T -= eT;
+		Nxz -= eNxz;
+		Nyz -= eNyz;
+		Pxy -= ePxy;
+		Pxz -= ePxz;
+		Pyz -= ePyz;
+		Qxxy -= eQxxy;
+		Qxxz -= eQxxz;
+		Qxyy -= eQxyy;
+		Qyyz -= eQyyz;
+		Qxzz -= eQxzz;
+		Qyzz -= eQyzz;
+		Qxyz -= eQxyz;
+	}
 	// feq, delta-s and delta-h of a population are cheap functions of 9 equilibrium factors and 13 moments: they are recomputed
 	// in the two passes below instead of being stored (4 x 27 live values cost more registers than the kernel can keep resident;
 	// the recomputation is the same expression, so the result is unchanged)
@@ -475,16 +494,21 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 		R acc = R(0);
 		if constexpr (n == 1 || n == 2) {
 			acc = kbc_tensor_d<CENTRAL, q>(Nxz, Nyz, Pxy, Pxz, Pyz);
-			if constexpr (! CENTRAL)
+			if constexpr (! CENTRAL && ! FOLD)
 				acc = acc - kbc_tensor_d<CENTRAL, q>(eNxz, eNyz, ePxy, ePxz, ePyz);
 		}
 		if constexpr (USE_T && n <= 1) {
-			const R t = n == 0 ? -T : kbc_scale<CENTRAL>(T, 6), et = n == 0 ? -eT : kbc_scale<CENTRAL>(eT, 6);
-			acc = (acc + t) - et;
+			const R t = n == 0 ? -T : kbc_scale<CENTRAL>(T, 6);
+			if constexpr (FOLD)
+				acc = acc + t;
+			else {
+				const R et = n == 0 ? -eT : kbc_scale<CENTRAL>(eT, 6);
+				acc = (acc + t) - et;
+			}
 		}
 		if constexpr (USE_Q && n >= 1) {
 			acc = acc + kbc_tensor_q<CENTRAL, q>(Qxxy, Qxxz, Qxyy, Qyyz, Qxzz, Qyzz, Qxyz);
-			if constexpr (! CENTRAL)
+			if constexpr (! CENTRAL && ! FOLD)
 				acc = acc - kbc_tensor_q<CENTRAL, q>(eQxxy, eQxxz, eQxyy, eQyyz, eQxzz, eQyzz, eQxyz);
 		}
 		return acc;
@@ -522,6 +546,16 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 		}
 	});
 	const R gamma = (one / beta - (two - one / beta) * sd / hh);
+#if defined(__CUDA_ARCH__) && ! defined(LBMX_KBC_NO_PASS_BARRIER)
+	// keep the compiler from carrying the 27 delta-s / feq values of the first pass over to the second (common subexpressions): the point of
+	// recomputing them is that they do NOT occupy registers in between
+	if constexpr (! EXACT) {
+		if constexpr (sizeof(R) == 8)
+			asm volatile("" : "+d"(T), "+d"(Nxz), "+d"(Nyz), "+d"(Pxy), "+d"(Pxz), "+d"(Pyz), "+d"(rho));
+		else
+			asm volatile("" : "+f"(T), "+f"(Nxz), "+f"(Nyz), "+f"(Pxy), "+f"(Pxz), "+f"(Pyz), "+f"(rho));
+	}
+#endif
 	static_for<27>([&](auto qc) {
 		constexpr int q = qc;
 		const R fe = feq_of(qc), ds = ds_of(qc);

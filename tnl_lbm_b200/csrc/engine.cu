@@ -129,12 +129,12 @@ int halo_dirs(int32_t* to_right, int32_t* to_left)
 struct IsBoundaryCell
 {
 	const int16_t* map;
-	int periodic, ndim, ox, X, Y, Z;
+	int periodic, nothing, ndim, ox, X, Y, Z;
 	__host__ __device__ bool operator()(uint32_t c) const
 	{
 		const int m = map[c];
-		if (m == 0 || m == periodic)
-			return false;  // GEO_FLUID, GEO_PERIODIC
+		if (m == 0 || m == periodic || m == nothing)
+			return false;  // GEO_FLUID, GEO_PERIODIC, GEO_NOTHING
 		if (m != 1)
 			return true;
 		// GEO_WALL (1 in every lattice): the bulk kernel bounces the walls away from the lattice faces itself (kernels.cuh: cell_in_boundary_list)
@@ -151,12 +151,13 @@ __global__ void k_count_boundary_cells(const int16_t* map, long long first_cell,
 									   int face_rule, int nothing, int ndim, int ox)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	bool b = false, r = false, o = false, w = false;
+	bool b = false, r = false, o = false, w = false, inert = false;
 	if (i < YZ) {
 		const int m = map[first_cell + (long long) blockIdx.y * YZ + i];
-		b = lbmx::cell_in_boundary_list(m, 0, periodic, 1, lbmx::cell_on_face(ndim, ox, (int) gridDim.y, Y, Z, (int) blockIdx.y, i % Y, i / Y));
+		b = lbmx::cell_in_boundary_list(m, 0, periodic, 1, nothing, lbmx::cell_on_face(ndim, ox, (int) gridDim.y, Y, Z, (int) blockIdx.y, i % Y, i / Y));
 		r = m == reads_neighbour;
 		w = m == 1 && ! b;	// GEO_WALL kept by the bulk kernel
+		inert = m == nothing;
 		if (face_rule && m != nothing && m != periodic) {  // periodic cells wrap (y, z always; x unless there are ghost planes)
 			const int y = i % Y, z = i / Y;
 			const bool yz_face = y == 0 || y == Y - 1 || (Z > 1 && (z == 0 || z == Z - 1));
@@ -168,9 +169,12 @@ __global__ void k_count_boundary_cells(const int16_t* map, long long first_cell,
 	const unsigned nr = __popc(__ballot_sync(0xffffffffu, r));
 	const unsigned no = __popc(__ballot_sync(0xffffffffu, o));
 	const unsigned nw = __popc(__ballot_sync(0xffffffffu, w));
+	const unsigned ni = __popc(__ballot_sync(0xffffffffu, inert));
 	if ((threadIdx.x & 31) == 0) {
 		if (nw)
 			atomicAdd(per_plane + gridDim.y + 2, nw);
+		if (ni)
+			atomicAdd(per_plane + gridDim.y + 3, ni);
 		if (n)
 			atomicAdd(per_plane + blockIdx.y, n);
 		if (nr)
@@ -178,6 +182,16 @@ __global__ void k_count_boundary_cells(const int16_t* map, long long first_cell,
 		if (no)
 			atomicAdd(per_plane + gridDim.y + 1, no);
 	}
+}
+
+// flags[plane][chunk] = 1 when the (up to) blockDim.x cells of that chunk of the plane are all GEO_NOTHING (KParams::inert)
+__global__ void k_flag_inert_chunks(const int16_t* map, long long first_cell, int YZ, int nothing, uint8_t* flags)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool ok = i >= YZ || map[first_cell + (long long) blockIdx.y * YZ + i] == nothing;
+	const int all = __syncthreads_and(ok);
+	if (threadIdx.x == 0)
+		flags[(size_t) blockIdx.y * gridDim.x + blockIdx.x] = all ? 1 : 0;
 }
 
 // =====================================================================================================================
@@ -227,6 +241,10 @@ struct lbmx_engine
 	uint64_t state_version = 1, pair_version = 0;  // state_version: bumped by whatever changes the kernel parameters
 	int pair_out_mode = -1, pair_launches = 0;
 	bool graphs_enabled = true;
+	bool pdl_enabled = true;  // LBMX_NO_PDL unsets it
+	// single slab of a small lattice: the kernels of consecutive steps form one chain on the compute stream under programmatic dependent
+	// launch (a step is tens of microseconds there; a dependent launch costs 2-3 of them, a fork/join through a second stream more)
+	bool pdl_chain(bool) const { return pdl_enabled && ox == 0 && X * YZ <= (16ll << 20) && ! use_tma[S_AA_EVEN] && ! use_tma[S_AA_ODD]; }
 	bool in_head_step = false;	// step_impl recursing for the odd head of a graph-replayed batch
 	// peer-memory halo exchange (one node, NVLink): the neighbours' distribution arrays and arrival counters mapped through CUDA IPC
 	struct Peer
@@ -259,6 +277,8 @@ struct lbmx_engine
 	// k_bulk_tma (A-A only): tile geometry, and which step parities go through it
 	int tile_y = 0, tile_y_shift = 0;
 	bool use_tma[3] = {false, false, false};  // by StreamMode
+	int64_t inert_cells = 0;				  // GEO_NOTHING cells
+	uint8_t* inert_flags = nullptr;			  // KParams::inert, allocated for maps with sizeable inert regions (lbmx_map_upload)
 	int64_t walls_in_bulk = 0;				  // GEO_WALL cells away from the faces: bounced by the bulk kernel (kernels.cuh: cell_in_boundary_list)
 
 	bool f64() const { return d.precision == LBMX_F64; }
@@ -280,6 +300,8 @@ KParams<R> make_params(const lbmx_engine* e)
 	p.profile = (const R*) e->profile;
 	p.bouzidi = (const R*) e->bouzidi;
 	p.blist = e->blist;
+	p.inert = e->inert_flags;
+	p.inert_stride = (int) ((e->YZ + LBMX_BULK_BLOCK - 1) / LBMX_BULK_BLOCK);
 	p.XYZ = e->XYZ;
 	p.X = (int) e->X;
 	p.Y = (int) e->Y;
@@ -326,7 +348,24 @@ constexpr int BLOCK = LBMX_BULK_BLOCK;
 // the same stream).  Within one step the two kernels touch disjoint cells and every population slot has exactly one writer, so
 // they may run concurrently.
 template <typename R>
-int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, int xe, cudaStream_t st, cudaStream_t st_list = nullptr)
+cudaError_t launch_pdl(void (*kernel)(KParams<R>), dim3 grid, int block, cudaStream_t st, const KParams<R>& p)
+{
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = grid;
+	cfg.blockDim = dim3((unsigned) block);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = st;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
+// chain: both kernels on `st` under programmatic dependent launch (kernels.cuh: pdl_wait) -- the single-slab path of small lattices
+template <typename R>
+int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, int xe, cudaStream_t st, cudaStream_t st_list = nullptr, bool chain = false)
 {
 	if (! st_list)
 		st_list = st;
@@ -335,7 +374,7 @@ int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, 
 	p.x_begin = xb;
 	p.nb_begin = (int) e->plane_start[xb];
 	p.nb_end = (int) e->plane_start[xe];
-	if (e->use_tma[p.stream] && e->walls_in_bulk == 0) {  // the experimental tile kernels know fluid cells only
+	if (e->use_tma[p.stream] && e->walls_in_bulk == 0 && e->inert_cells == 0) {  // the experimental tile kernels know fluid cells only
 		// one CTA per tile of tile_y x (128 / tile_y) cells; the populations travel as bulk copies of the TMA engine (kernels_tma.cuh)
 		const int tz = tma::TILE / e->tile_y;
 		dim3 grid((unsigned) ((e->Y / e->tile_y) * ((e->Z + tz - 1) / tz)), (unsigned) (xe - xb));
@@ -345,12 +384,20 @@ int launch_range(lbmx_engine* e, const StepKernels<R>& K, KParams<R> p, int xb, 
 	else {
 		const int per_cta = BLOCK * K.cpt[p.stream];
 		dim3 grid((unsigned) ((e->YZ + per_cta - 1) / per_cta), (unsigned) (xe - xb));
-		K.bulk[p.stream]<<<grid, BLOCK, 0, st>>>(p);
+		if (chain)
+			CU(launch_pdl<R>(K.bulk[p.stream], grid, BLOCK, st, p));
+		else
+			K.bulk[p.stream]<<<grid, BLOCK, 0, st>>>(p);
 	}
 	e->stats.kernel_launches++;
 	const int nbl = p.nb_end - p.nb_begin;
 	if (nbl > 0) {
-		K.boundary<<<(nbl + BLOCK - 1) / BLOCK, BLOCK, 0, st_list>>>(p);
+		if (chain) {
+			p.pdl = e->list_after_bulk ? 2 : 1;
+			CU(launch_pdl<R>(K.boundary, dim3((unsigned) ((nbl + BLOCK - 1) / BLOCK)), BLOCK, st, p));
+		}
+		else
+			K.boundary<<<(nbl + BLOCK - 1) / BLOCK, BLOCK, 0, st_list>>>(p);
 		e->stats.kernel_launches++;
 	}
 	CU(cudaGetLastError());
@@ -501,7 +548,9 @@ int capture_pair(lbmx_engine* e, const StepKernels<R>& K, int out_mode)
 		e->iter = iter0 + k;  // parity / rotation of this step
 		KParams<R> p = make_params<R>(e);
 		p.out_mode = out_mode;
-		if (e->nb == 0 || e->list_after_bulk)
+		if (e->pdl_chain(true))
+			rc = launch_range(e, K, p, 0, (int) e->X, e->s_main, nullptr, true);
+		else if (e->nb == 0 || e->list_after_bulk)
 			rc = launch_range(e, K, p, 0, (int) e->X, e->s_main);
 		else {	// fork: the boundary-list kernel beside the bulk kernel; join before the next step
 			cudaEventRecord(e->ev_fork, e->s_main);
@@ -605,7 +654,11 @@ int step_impl(lbmx_engine* e, const StepKernels<R>& K, int64_t nsteps)
 		p.stat_counter = e->prm.stat_counter + (int) s;
 		int rc;
 		if (! ghosts) {
-			if (e->nb == 0 || e->list_after_bulk) {
+			if (e->pdl_chain(false)) {
+				if ((rc = launch_range(e, K, p, 0, (int) e->X, e->s_main, nullptr, true)))
+					return rc;
+			}
+			else if (e->nb == 0 || e->list_after_bulk) {
 				if ((rc = launch_range(e, K, p, 0, (int) e->X, e->s_main)))
 					return rc;
 			}
@@ -995,6 +1048,7 @@ int lbmx_create(const lbmx_desc* desc, lbmx_engine** out)
 	CUX(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
 	CUX(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
 	e->graphs_enabled = std::getenv("LBMX_NO_GRAPH") == nullptr;
+	e->pdl_enabled = std::getenv("LBMX_NO_PDL") == nullptr;
 	CUX(cudaEventCreate(&e->ev_t0));
 	CUX(cudaEventCreate(&e->ev_t1));
 	const size_t df_bytes = (size_t) e->Q * e->XYZ * e->rs;
@@ -1060,7 +1114,7 @@ int lbmx_destroy(lbmx_engine* e)
 		cudaFree(e->my_flags);
 	if (e->h_halo_error)
 		cudaFreeHost(e->h_halo_error);
-	for (void* p : {e->df_alloc[0], e->df_alloc[1], e->macro, (void*) e->map, (void*) e->blist, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs})
+	for (void* p : {e->df_alloc[0], e->df_alloc[1], e->macro, (void*) e->map, (void*) e->blist, (void*) e->inert_flags, e->profile, e->bouzidi, (void*) e->d_flag, (void*) e->d_dirs})
 		if (p)
 			cudaFree(p);
 	if (e->pair_exec)
@@ -1292,16 +1346,16 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	const long long first_cell = (long long) e->ox * e->YZ, n_cells = (long long) e->X * e->YZ;
 	const int outflow_right = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::OUTFLOW_RIGHT : (int) D3Q27::OUTFLOW_RIGHT;
 	unsigned* d_counts = nullptr;
-	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) (e->X + 3)));
-	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) (e->X + 3), e->s_main));
+	CU(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t) (e->X + 4)));
+	CU(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * (size_t) (e->X + 4), e->s_main));
 	const int nothing = e->d.lattice == LBMX_D2Q9 ? (int) D2Q9::NOTHING : (int) D3Q27::NOTHING;
 	const int ndim = e->d.lattice == LBMX_D2Q9 ? 2 : 3;
 	const int face_rule = ! e->aa() ? 0 : (e->ox == 0 ? 2 : 1);
 	k_count_boundary_cells<<<dim3((unsigned) ((e->YZ + 255) / 256), (unsigned) e->X), 256, 0, e->s_main>>>(e->map, first_cell, (int) e->YZ, periodic, outflow_right, d_counts,
 																											(int) e->Y, (int) e->Z, face_rule, nothing, ndim, (int) e->ox);
 	e->stats.kernel_launches++;
-	std::vector<unsigned> counts((size_t) e->X + 3);
-	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) (e->X + 3), cudaMemcpyDeviceToHost, e->s_main));
+	std::vector<unsigned> counts((size_t) e->X + 4);
+	CU(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned) * (size_t) (e->X + 4), cudaMemcpyDeviceToHost, e->s_main));
 	CU(cudaStreamSynchronize(e->s_main));
 	CU(cudaFree(d_counts));
 	// Under A-A such a cell reads, in place, populations that the cell to its left rewrites in the same step (the reference has the
@@ -1321,7 +1375,7 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	if (e->nb > 0) {
 		CU(cudaMalloc(&e->blist, (size_t) e->nb * sizeof(uint32_t)));
 		cub::CountingInputIterator<uint32_t> cells((uint32_t) first_cell);
-		IsBoundaryCell pred{e->map, periodic, ndim, (int) e->ox, (int) e->X, (int) e->Y, (int) e->Z};
+		IsBoundaryCell pred{e->map, periodic, nothing, ndim, (int) e->ox, (int) e->X, (int) e->Y, (int) e->Z};
 		int* d_selected = nullptr;
 		void* d_temp = nullptr;
 		size_t temp_bytes = 0;
@@ -1342,6 +1396,21 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	e->stats.bulk_cells = e->n_bulk;
 	e->stats.aa_cells_reaching_outside = counts[(size_t) e->X + 1];
 	e->walls_in_bulk = counts[(size_t) e->X + 2];
+	e->inert_cells = counts[(size_t) e->X + 3];
+	// maps with sizeable GEO_NOTHING regions: one flag per 128 consecutive cells of a plane, so that CTAs of the bulk kernel whose cells
+	// are all inert skip their (speculative) population loads
+	if (e->inert_flags) {
+		CU(cudaFree(e->inert_flags));
+		e->inert_flags = nullptr;
+	}
+	if (e->inert_cells * 16 >= n_cells) {
+		const int stride = (int) ((e->YZ + BLOCK - 1) / BLOCK);
+		CU(cudaMalloc(&e->inert_flags, (size_t) stride * (size_t) (e->X + 2 * e->ox)));
+		CU(cudaMemsetAsync(e->inert_flags, 0, (size_t) stride * (size_t) (e->X + 2 * e->ox), e->s_main));
+		k_flag_inert_chunks<<<dim3((unsigned) stride, (unsigned) e->X), BLOCK, 0, e->s_main>>>(e->map, first_cell, (int) e->YZ, nothing, e->inert_flags + (size_t) e->ox * stride);
+		e->stats.kernel_launches++;
+		CU(cudaStreamSynchronize(e->s_main));
+	}
 	e->map_ready = true;
 	e->state_version++;
 	return LBMX_OK;

@@ -60,6 +60,8 @@ struct KParams
 	const R* profile;  // inflow vx profile [z*profile_sy + y] or nullptr
 	const R* bouzidi;  // D2Q9 near-wall interpolation coefficients [8][XYZ] or nullptr (lbm_data.h:69-83)
 	const uint32_t* blist;	// boundary list: storage cell indices
+	const uint8_t* inert;	// nullptr, or [storage plane][inert_stride] flags, one per LBMX_BULK_BLOCK consecutive cells of a plane: 1 = all of them GEO_NOTHING
+	int inert_stride;		// = ceil(YZ / LBMX_BULK_BLOCK)
 	long long XYZ;	   // storage cells per component
 	int X, Y, Z, ox;   // local slab size (no ghosts), ghost planes per side
 	int YZ;
@@ -70,6 +72,7 @@ struct KParams
 	int profile_sy;
 	int tile_y, tile_y_shift;  // k_bulk_tma: cells of one row per CTA (power of two dividing Y) and its log2
 	int eq, inflow, stream, out_mode, stat_counter;
+	int pdl;		   // k_boundary under programmatic dependent launch: 1 = runs beside the bulk kernel launched just before it (see pdl_wait)
 	Phys<R> phys;
 	R in_vx, in_vy, in_vz;
 };
@@ -169,20 +172,38 @@ LBMX_D void st_df(R* ptr, R v)
 		*ptr = v;
 }
 // A-A odd steps: the accesses of the populations that move in y are shifted by one element, so the last 32-byte sector of a warp's
-// request is the first sector of the next warp's (same CTA, same row).  Hints for those accesses alone (tools/kbench sweep):
-// LBMX_LD_HINT_YSHIFT / LBMX_ST_HINT_YSHIFT, same encoding as LBMX_LD_HINT / LBMX_ST_HINT.
+// request is the first sector of the next warp's (same CTA, same row): there the plain, L1-allocating forms win over the streaming
+// hints of the even / A-B kernels (tools/kbench sweeps of round 2, profiles/kbench_r2_odd_hints.txt: D3Q27 fp64 +0.4 %, D3Q19 fp32 +2 %,
+// D2Q9 fp32 +1 %, the rest neutral).  Same encoding as LBMX_LD_HINT / LBMX_ST_HINT; *_YSHIFT for the populations that move in y.
 #ifndef LBMX_LD_HINT_YSHIFT
-	#define LBMX_LD_HINT_YSHIFT LBMX_LD_HINT
+	#define LBMX_LD_HINT_YSHIFT 0
 #endif
 #ifndef LBMX_ST_HINT_YSHIFT
-	#define LBMX_ST_HINT_YSHIFT LBMX_ST_HINT
+	#define LBMX_ST_HINT_YSHIFT 0
 #endif
 #ifndef LBMX_LD_HINT_ODD
-	#define LBMX_LD_HINT_ODD LBMX_LD_HINT
+	#define LBMX_LD_HINT_ODD 0
 #endif
 #ifndef LBMX_ST_HINT_ODD
-	#define LBMX_ST_HINT_ODD LBMX_ST_HINT
+	#define LBMX_ST_HINT_ODD 0
 #endif
+
+// ---- programmatic dependent launch (small lattices: a step is tens of microseconds, the launch gap between two steps 2-3 of them) ----
+// Kernels of a step chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may start while its
+// predecessor in the stream drains, and pdl_wait() holds it until that predecessor has completed and its stores are visible.
+// Launched without the attribute both instructions do nothing.
+LBMX_D void pdl_wait()
+{
+#ifdef __CUDA_ARCH__
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+LBMX_D void pdl_trigger()
+{
+#ifdef __CUDA_ARCH__
+	asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
 
 // ---- streaming (d3q27/streaming_AB.h:12-58, streaming_AA.h:12-116 and the D2Q9 twins) ----
 // NONNEG: the caller guarantees cell + offset >= 0 (bulk kernel: offsets wrap), so the index is zero-extended for free.
@@ -247,13 +268,11 @@ LBMX_D void st_macro(R* ptr, R v)
 }
 
 template <typename L, typename R>
-LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
+LBMX_D void output_macro_impl(R* M, const long long S, const int out_mode, const int stat_counter, int c, R rho, R vx, R vy, R vz)
 {
-	if (p.out_mode == OUT_NONE)
+	if (out_mode == OUT_NONE)
 		return;
 	constexpr int nd = L::NDIM;
-	R* M = p.macro;
-	const long long S = p.XYZ;
 	const R v[3] = {vx, vy, vz};
 	st_macro(M + c, rho);
 #pragma unroll
@@ -261,12 +280,12 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 		st_macro(M + ((1 + a) * S + c), v[a]);
 	if constexpr (nd == 2) {
 		// D2Q9_MACRO_WithMean (sim_2D/sim2d_2.cu:75-95): gated velocity sums, and fluctuation sums about a mean the host froze
-		if (p.out_mode >= OUT_WITH_MEAN_2D) {
-			if (p.out_mode & 1) {
+		if (out_mode >= OUT_WITH_MEAN_2D) {
+			if (out_mode & 1) {
 				st_macro(M + (3 * S + c), ld_macro(M + (3 * S + c)) + vx);
 				st_macro(M + (4 * S + c), ld_macro(M + (4 * S + c)) + vy);
 			}
-			if (p.out_mode & 2) {
+			if (out_mode & 2) {
 				const R dux = vx - ld_macro(M + (5 * S + c));
 				const R duy = vy - ld_macro(M + (6 * S + c));
 				st_macro(M + (7 * S + c), ld_macro(M + (7 * S + c)) + sqrt(dux * dux + duy * duy));  // IEEE sqrt in R = the reference's sqrt(double) rounded to dreal
@@ -276,10 +295,10 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 			return;
 		}
 	}
-	if (p.out_mode != OUT_MEAN)
+	if (out_mode != OUT_MEAN)
 		return;
 	// running mean + Welford co-moments, components: means then xx,yy,zz,xy,xz,yz (3-D) / xx,yy,xy (2-D)
-	const R denom = R(1) / R(p.stat_counter + 1);
+	const R denom = R(1) / R(stat_counter + 1);
 	R delta[3], delta_new[3];
 #pragma unroll
 	for (int a = 0; a < nd; a++) {
@@ -297,6 +316,19 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 		const long long o = (long long) (1 + 2 * nd + i) * S + c;
 		st_macro(M + o, ld_macro(M + o) + delta_new[pa[i]] * delta[pb[i]]);
 	}
+}
+
+template <typename L, typename R>
+LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
+{
+	output_macro_impl<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, c, rho, vx, vy, vz);
+}
+// what GEO_WALL and GEO_NOTHING cells report: rho = 1, u = 0 (d3q27/bc.h:53-60, 147-165).  Out of line: it is called from the cold paths
+// of the bulk kernel only, whose code should stay small (instruction cache).
+template <typename L, typename R>
+__device__ __noinline__ void output_macro_at_rest(R* M, const long long S, const int out_mode, const int stat_counter, int c)
+{
+	output_macro_impl<L, R>(M, S, out_mode, stat_counter, c, R(1), R(0), R(0), R(0));
 }
 
 // full-way bounce-back: swap opposite populations, no collision (d3q27/bc.h:147-165).
@@ -319,15 +351,16 @@ LBMX_D void bounce_back(R (&f)[L::Q])
 
 // Which kernel owns a cell.  The bulk kernel takes GEO_FLUID and GEO_PERIODIC cells and -- so that obstacle-heavy maps (spheres,
 // cylinders, porous blocks of GEO_WALL) stream every population exactly once -- GEO_WALL cells away from the lattice faces, where the
-// wrapping neighbour rule it loads with coincides with the rule of a non-periodic cell (kernels.h:30-56).  Everything else, and walls on
-// a face, goes to the boundary list.  Shared by lbmx_map_upload (list construction) and the kernels.
+// wrapping neighbour rule it loads with coincides with the rule of a non-periodic cell (kernels.h:30-56), and GEO_NOTHING cells, which
+// only report rho = 1, u = 0.  Everything else, and walls on a face, goes to the boundary list.  Shared by lbmx_map_upload (list
+// construction) and the kernels.
 LBMX_HD bool cell_on_face(int ndim, int ox, int X, int Y, int Z, int x, int y, int z)
 {
 	return (ox == 0 && (x == 0 || x == X - 1)) || y == 0 || y == Y - 1 || (ndim == 3 && (z == 0 || z == Z - 1));
 }
-LBMX_HD bool cell_in_boundary_list(int m, int fluid, int periodic, int wall, bool face)
+LBMX_HD bool cell_in_boundary_list(int m, int fluid, int periodic, int wall, int nothing, bool face)
 {
-	return ! (m == fluid || m == periodic || (m == wall && ! face));
+	return ! (m == fluid || m == periodic || m == nothing || (m == wall && ! face));
 }
 
 // =====================================================================================================================
@@ -356,7 +389,7 @@ constexpr int bulk_cpt()
 	return LBMX_BULK_CPT;
 #else
 	if (L::Q >= 19)
-		return sizeof(R) == 8 ? 1 : (MODE == S_AA_ODD ? 1 : 2);
+		return sizeof(R) == 8 ? 1 : (MODE == S_AB ? 2 : 1);	 // fp32 A-A even: 2 cells per thread were 1.7 % faster until the obstacle path made the kernel outgrow the instruction cache
 	return sizeof(R) == 8 ? (MODE == S_AB ? 1 : 2) : 2;
 #endif
 }
@@ -372,6 +405,29 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 	Deltas d[CPT];
 	int c[CPT], m[CPT];
 	bool face[CPT];
+	pdl_wait();		// everything the previous kernel of the chain wrote is visible from here on
+	pdl_trigger();	// the next kernel may take the SM slots this grid frees while it drains
+	if (p.inert != nullptr) {
+		// maps with sizeable GEO_NOTHING regions (lbmx_map_upload decides): a CTA whose cells are all inert issues no population loads
+		bool all_inert = true;
+#pragma unroll
+		for (int k = 0; k < CPT; k++) {
+			const int first = blockIdx.x * (LBMX_BULK_BLOCK * CPT) + k * LBMX_BULK_BLOCK;
+			if (first < p.YZ)
+				all_inert = all_inert && p.inert[(long long) (x + p.ox) * p.inert_stride + first / LBMX_BULK_BLOCK] != 0;
+		}
+		if (all_inert) {
+			if (p.out_mode != OUT_NONE) {
+#pragma unroll
+				for (int k = 0; k < CPT; k++) {
+					const int yz = yz0 + k * LBMX_BULK_BLOCK;
+					if (yz < p.YZ)
+						output_macro_at_rest<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, (x + p.ox) * p.YZ + yz);
+				}
+			}
+			return;
+		}
+	}
 	// ---- phase 1: every load of every cell of this thread
 #pragma unroll
 	for (int k = 0; k < CPT; k++) {
@@ -401,15 +457,9 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 	// ---- phase 2: collide and store, cell by cell
 #pragma unroll
 	for (int k = 0; k < CPT; k++) {
-		if (m[k] < 0 || cell_in_boundary_list(m[k], L::FLUID, L::PERIODIC, L::WALL, face[k]))
+		if (m[k] < 0 || ! L::bulk(m[k]))
 			continue;
 		R rho, vx, vy, vz;
-		if (m[k] == L::WALL) {	// interior obstacle cell: reported rho = 1, u = 0 (bc.h:147-165)
-			bounce_back<L>(f[k]);
-			rho = R(1);
-			vx = vy = vz = R(0);
-		}
-		else {
 #ifdef LBMX_EXP_NOCOLLIDE  // development experiment only: streaming without arithmetic = the memory-system ceiling of this access pattern
 		rho = f[k][0];
 		vx = vy = vz = R(0);
@@ -417,9 +467,28 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 		density_velocity(f[k], p.phys, rho, vx, vy, vz);
 		collide<KIND>(f[k], p.phys, p.eq, rho, vx, vy, vz);
 #endif
-		}
 		stream_out<L, MODE, true>(p, f[k], c[k], d[k]);
 		output_macro<L>(p, c[k], rho, vx, vy, vz);
+	}
+	// ---- phase 3 (cold): obstacle cells away from the faces bounce back without colliding, inert cells only report rho = 1, u = 0
+	//      (d3q27/bc.h:53-60, 147-165).  Kept apart from phase 2, and re-deriving its indices from the cell type and the populations alone,
+	//      so that the fluid path keeps the registers and the schedule it has without it.
+#pragma unroll
+	for (int k = 0; k < CPT; k++) {
+		if (m[k] != L::WALL && m[k] != L::NOTHING)
+			continue;
+		const int yz = yz0 + k * LBMX_BULK_BLOCK;
+		const int z = div_by_Y(p, yz);
+		const int y = yz - z * p.Y;
+		const int cc = (x + p.ox) * p.YZ + yz;
+		if (m[k] == L::NOTHING)
+			output_macro_at_rest<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, cc);
+		else if (! cell_on_face(L::NDIM, p.ox, p.X, p.Y, p.Z, x, y, z)) {
+			const Deltas dd = neighbour_deltas<true>(p, true, x, y, z);
+			bounce_back<L>(f[k]);
+			stream_out<L, MODE, true>(p, f[k], cc, dd);
+			output_macro_at_rest<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, cc);
+		}
 	}
 }
 
@@ -525,6 +594,22 @@ template <typename L, int KIND, typename R, int ARITH = LBMX_STRICT>
 __global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
 {
 	const int i = p.nb_begin + blockIdx.x * blockDim.x + threadIdx.x;
+	// Chained behind the bulk kernel of the same step on one stream.  pdl == 1: the two are independent (disjoint cells, one writer per
+	// slot), so this kernel starts as soon as the bulk kernel's last CTAs are resident -- the bulk kernel triggers only after its own wait,
+	// so everything older has completed -- and waits for it just before it exits: the next step's wait on THIS kernel then covers both.
+	// Otherwise (A-A maps with GEO_OUTFLOW_RIGHT cells, which read a neighbour in place) it follows the whole bulk kernel.
+	struct ChainEnd
+	{
+		bool at_end;
+		LBMX_D ~ChainEnd()
+		{
+			if (at_end)
+				pdl_wait();
+		}
+	} chain_end{p.pdl == 1};
+	if (p.pdl != 1)
+		pdl_wait();
+	pdl_trigger();
 	if (i >= p.nb_end)
 		return;
 	const int c = (int) p.blist[i];
