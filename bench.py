@@ -583,6 +583,9 @@ def main():
         f"{a.steps} steps {te_st - te_up:.3f}s, macro download {te1 - te_st:.3f}s")
     te = allmax(te1 - te0)
     e2e_value = cells_global * a.steps / te / 1e6
+    # the three phases as the slowest rank saw them, and the host-link rates they imply (all ranks copy at the same time: GPUs that share a
+    # PCIe switch uplink or a memory controller share its bandwidth, which is what bounds e2e at N = 8)
+    ph_up, ph_st, ph_dn = allmax(te_up - te0), allmax(te_st - te_up), allmax(te1 - te_st)
     h2d = (h_map.nbytes + sum(f.nbytes for f in fields)) * N
     d2h = h_mac.nbytes * N
     rho_sum = float(h_mac[0].sum())
@@ -618,7 +621,10 @@ def main():
         line = {"metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": N, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps,
                 "higher_is_better": True, "scaling": "strong" if channel else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
-                        "what": "lbmx_map_upload + lbmx_df_set_equilibrium_field from pinned host buffers, lbmx_step(K), lbmx_macro_download"},
+                        "what": "lbmx_map_upload + lbmx_df_set_equilibrium_field from pinned host buffers, lbmx_step(K), lbmx_macro_download",
+                        "phases_s_slowest_rank": {"upload": ph_up, "steps": ph_st, "download": ph_dn},
+                        "host_link_GBs_per_gpu": {"h2d": h2d / N / ph_up / 1e9, "d2h": d2h / N / ph_dn / 1e9},
+                        "host_link_GBs_all_gpus": {"h2d": h2d / ph_up / 1e9, "d2h": d2h / ph_dn / 1e9}},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                              "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes_per_update": B_PER_UPDATE,

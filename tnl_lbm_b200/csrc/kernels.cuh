@@ -24,9 +24,17 @@
 #ifndef LBMX_BULK_MINBLOCKS
 	#define LBMX_BULK_MINBLOCKS 4  // __launch_bounds__ second argument (register cap = 65536 / (BLOCK * MINBLOCKS) = 128: 16 warps per SM)
 #endif
+// KBC kernels: 27 populations + 13 moments + 9 equilibrium factors and their reciprocals live.  fp32 fits 128 registers (4 CTAs per SM:
+// +9..21 % over 3); fp64 takes 168 with a few spilled doubles (3 CTAs: +11 % on the even and A-B kernels, -3 % on the odd one, which
+// stays at 2) -- tools/kbench, profiles/kbench_r2_kbc.txt
 #ifndef LBMX_KBC_MINBLOCKS_F64
-	#define LBMX_KBC_MINBLOCKS_F64 2  // KBC kernels: 27 populations + 13 moments + 9 equilibrium factors live
-	#define LBMX_KBC_MINBLOCKS_F32 3
+	#define LBMX_KBC_MINBLOCKS_F64 3
+#endif
+#ifndef LBMX_KBC_MINBLOCKS_F64_ODD
+	#define LBMX_KBC_MINBLOCKS_F64_ODD 2
+#endif
+#ifndef LBMX_KBC_MINBLOCKS_F32
+	#define LBMX_KBC_MINBLOCKS_F32 4
 #endif
 #ifndef LBMX_BULK_MINBLOCKS_AB
 	#define LBMX_BULK_MINBLOCKS_AB 5  // the A-B kernel fits 96 registers without spilling and likes the extra occupancy (kbench: 6.68 vs 6.33 TB/s)
@@ -267,6 +275,36 @@ LBMX_D void st_macro(R* ptr, R v)
 #endif
 }
 
+// The read-modify-write fields of MACRO_Mean / D2Q9_MACRO_WithMean are needed only after the collision, at the end of a thread's life:
+// asking L2 for them together with the populations takes one DRAM latency off that tail without holding registers for them.
+template <typename R>
+LBMX_D void prefetch_l2(const R* ptr)
+{
+#ifdef __CUDA_ARCH__
+	asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#endif
+}
+template <typename L, typename R>
+LBMX_D void prefetch_macro_sums(const KParams<R>& p, int c)
+{
+	constexpr int nd = L::NDIM;
+	const R* M = p.macro;
+	const long long S = p.XYZ;
+	// rolled loops on purpose: this sits in the fluid path of every bulk kernel, whose code size matters (see bulk_cold_cell)
+	int lo = 0, hi = 0;
+	if (p.out_mode == OUT_MEAN) {
+		lo = 1 + nd;
+		hi = 1 + 2 * nd + (nd == 3 ? 6 : 3);
+	}
+	else if (nd == 2 && p.out_mode >= OUT_WITH_MEAN_2D) {
+		lo = (p.out_mode & 1) ? 3 : 5;
+		hi = (p.out_mode & 2) ? 10 : 5;
+	}
+#pragma unroll 1
+	for (int i = lo; i < hi; i++)
+		prefetch_l2(M + (i * S + c));
+}
+
 template <typename L, typename R>
 LBMX_D void output_macro_impl(R* M, const long long S, const int out_mode, const int stat_counter, int c, R rho, R vx, R vy, R vz)
 {
@@ -323,14 +361,6 @@ LBMX_D void output_macro(const KParams<R>& p, int c, R rho, R vx, R vy, R vz)
 {
 	output_macro_impl<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, c, rho, vx, vy, vz);
 }
-// what GEO_WALL and GEO_NOTHING cells report: rho = 1, u = 0 (d3q27/bc.h:53-60, 147-165).  Out of line: it is called from the cold paths
-// of the bulk kernel only, whose code should stay small (instruction cache).
-template <typename L, typename R>
-__device__ __noinline__ void output_macro_at_rest(R* M, const long long S, const int out_mode, const int stat_counter, int c)
-{
-	output_macro_impl<L, R>(M, S, out_mode, stat_counter, c, R(1), R(0), R(0), R(0));
-}
-
 // full-way bounce-back: swap opposite populations, no collision (d3q27/bc.h:147-165).
 // REFERENCE QUIRK kept for parity: in D2Q9_BC_All::preCollision the coordinate parameters zm/zp shadow the direction enumerators
 // (d2q9/bc.h:90 vs defs.h:262-263), so its swap(f[zm], f[zp]) degenerates to a no-op on the X x Y x 1 lattice: the straight +-y
@@ -366,13 +396,57 @@ LBMX_HD bool cell_in_boundary_list(int m, int fluid, int periodic, int wall, int
 // =====================================================================================================================
 // bulk kernel: GEO_FLUID / GEO_PERIODIC cells, GEO_WALL cells away from the faces
 // =====================================================================================================================
+// what GEO_WALL and GEO_NOTHING cells report: rho = 1, u = 0 (d3q27/bc.h:53-60, 147-165), out of line
+template <typename L, typename R>
+__device__ __noinline__ void output_macro_at_rest(R* M, const long long S, const int out_mode, const int stat_counter, int c)
+{
+	output_macro_impl<L, R>(M, S, out_mode, stat_counter, c, R(1), R(0), R(0), R(0));
+}
+// How the bulk kernel carries its cold path (phase 3), from the tools/kbench comparison of round 2 (profiles/kbench_r2_cold_path.txt): as a
+// call to bulk_cold_cell everywhere except the A-A odd kernels of D3Q27 and D2Q9, which lose 4-5 % with the call in them and nothing with
+// the same code in line (the fp32 kernels with two cells per thread and the D3Q19 A-B kernel lose 6-10 % with it in line).
+#ifndef LBMX_COLD_INLINE_ODD_Q27
+	#define LBMX_COLD_INLINE_ODD_Q27 1
+#endif
+template <typename L, typename R, int MODE>
+constexpr bool bulk_cold_inline()
+{
+#ifdef LBMX_COLD_INLINE_ALL
+	return LBMX_COLD_INLINE_ALL;
+#else
+	return LBMX_COLD_INLINE_ODD_Q27 && MODE == S_AA_ODD && L::Q != 19;
+#endif
+}
+
+// Cold path of the bulk kernel, out of line so that the fluid path keeps its size (instruction cache: the fp32 kernels with two cells per
+// thread sit right below the 32 KB where fetch starts to cost) and its registers: obstacle cells away from the faces bounce back without
+// colliding, inert cells only report rho = 1, u = 0 (d3q27/bc.h:53-60, 147-165).  The populations are loaded again here rather than handed
+// over in registers (they are in L2: the calling warp has just fetched these lines).
+template <typename L, int MODE, typename R>
+__device__ __noinline__ void bulk_cold_cell(const KParams<R>& p, int x, int yz, int m)
+{
+	const int c = (x + p.ox) * p.YZ + yz;
+	if (m == L::WALL) {
+		const int z = div_by_Y(p, yz);
+		const int y = yz - z * p.Y;
+		if (cell_on_face(L::NDIM, p.ox, p.X, p.Y, p.Z, x, y, z))
+			return;	 // a boundary-list cell
+		const Deltas d = neighbour_deltas<true>(p, true, x, y, z);
+		R f[L::Q];
+		stream_in<L, MODE, true>(p, f, c, d);
+		bounce_back<L>(f);
+		stream_out<L, MODE, true>(p, f, c, d);
+	}
+	output_macro_impl<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, c, R(1), R(0), R(0), R(0));
+}
+
 // resident CTAs per SM the register allocation is sized for: the cumulant / MRT_LES kernels fit 128 (A-A) and 96 (A-B)
 // registers without spilling; fp64 SRT and BGK keep f[27], feq[27] and the source terms live and get 170
 template <int KIND, typename R, int MODE>
 constexpr int bulk_minblocks()
 {
 	if (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
-		return sizeof(R) == 8 ? LBMX_KBC_MINBLOCKS_F64 : LBMX_KBC_MINBLOCKS_F32;
+		return sizeof(R) == 8 ? (MODE == S_AA_ODD ? LBMX_KBC_MINBLOCKS_F64_ODD : LBMX_KBC_MINBLOCKS_F64) : LBMX_KBC_MINBLOCKS_F32;
 	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_SRT_MF || KIND == K_CLBM))
 		return LBMX_BULK_MINBLOCKS < 3 ? LBMX_BULK_MINBLOCKS : 3;
 	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;
@@ -389,14 +463,14 @@ constexpr int bulk_cpt()
 	return LBMX_BULK_CPT;
 #else
 	if (L::Q >= 19)
-		return sizeof(R) == 8 ? 1 : (MODE == S_AB ? 2 : 1);	 // fp32 A-A even: 2 cells per thread were 1.7 % faster until the obstacle path made the kernel outgrow the instruction cache
+		return sizeof(R) == 8 ? 1 : (MODE == S_AA_ODD ? 1 : 2);
 	return sizeof(R) == 8 ? (MODE == S_AB ? 1 : 2) : 2;
 #endif
 }
 
 // ARITH (= LBMX_STRICT of the object file) only makes the kernel symbols of the fast and the parity-arithmetic builds distinct
 template <typename L, int KIND, typename R, int MODE, int ARITH = LBMX_STRICT>
-__global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>()) k_bulk(const KParams<R> p)
+__global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>()) k_bulk(const LBMX_GRID_CONSTANT KParams<R> p)
 {
 	constexpr int CPT = bulk_cpt<L, R, MODE>();
 	const int x = p.x_begin + blockIdx.y;
@@ -419,11 +493,9 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 		if (all_inert) {
 			if (p.out_mode != OUT_NONE) {
 #pragma unroll
-				for (int k = 0; k < CPT; k++) {
-					const int yz = yz0 + k * LBMX_BULK_BLOCK;
-					if (yz < p.YZ)
-						output_macro_at_rest<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, (x + p.ox) * p.YZ + yz);
-				}
+				for (int k = 0; k < CPT; k++)
+					if (yz0 + k * LBMX_BULK_BLOCK < p.YZ)
+						bulk_cold_cell<L, MODE>(p, x, yz0 + k * LBMX_BULK_BLOCK, L::NOTHING);
 			}
 			return;
 		}
@@ -446,6 +518,8 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 			d[k] = neighbour_deltas<true>(p, true, x, y, z);
 			face[k] = cell_on_face(L::NDIM, p.ox, p.X, p.Y, p.Z, x, y, z);
 			stream_in<L, MODE, true>(p, f[k], c[k], d[k]);
+			if (p.out_mode >= OUT_MEAN)
+				prefetch_macro_sums<L>(p, c[k]);
 			if constexpr (MODE == S_AB) {
 				if (face[k] && m[k] == L::FLUID) {
 					d[k] = neighbour_deltas<false>(p, false, x, y, z);
@@ -470,23 +544,26 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 		stream_out<L, MODE, true>(p, f[k], c[k], d[k]);
 		output_macro<L>(p, c[k], rho, vx, vy, vz);
 	}
-	// ---- phase 3 (cold): obstacle cells away from the faces bounce back without colliding, inert cells only report rho = 1, u = 0
-	//      (d3q27/bc.h:53-60, 147-165).  Kept apart from phase 2, and re-deriving its indices from the cell type and the populations alone,
-	//      so that the fluid path keeps the registers and the schedule it has without it.
+	// ---- phase 3 (cold): obstacle cells away from the faces, inert cells
 #pragma unroll
 	for (int k = 0; k < CPT; k++) {
 		if (m[k] != L::WALL && m[k] != L::NOTHING)
 			continue;
 		const int yz = yz0 + k * LBMX_BULK_BLOCK;
-		const int z = div_by_Y(p, yz);
-		const int y = yz - z * p.Y;
-		const int cc = (x + p.ox) * p.YZ + yz;
-		if (m[k] == L::NOTHING)
-			output_macro_at_rest<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, cc);
-		else if (! cell_on_face(L::NDIM, p.ox, p.X, p.Y, p.Z, x, y, z)) {
-			const Deltas dd = neighbour_deltas<true>(p, true, x, y, z);
-			bounce_back<L>(f[k]);
-			stream_out<L, MODE, true>(p, f[k], cc, dd);
+		if constexpr (! bulk_cold_inline<L, R, MODE>())
+			bulk_cold_cell<L, MODE>(p, x, yz, m[k]);
+		else {
+			// same thing in line, on the populations this thread already holds
+			const int cc = (x + p.ox) * p.YZ + yz;
+			if (m[k] == L::WALL) {
+				const int z = div_by_Y(p, yz);
+				const int y = yz - z * p.Y;
+				if (cell_on_face(L::NDIM, p.ox, p.X, p.Y, p.Z, x, y, z))
+					continue;
+				const Deltas dd = neighbour_deltas<true>(p, true, x, y, z);
+				bounce_back<L>(f[k]);
+				stream_out<L, MODE, true>(p, f[k], cc, dd);
+			}
 			output_macro_at_rest<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, cc);
 		}
 	}

@@ -5,6 +5,11 @@
 
 #define LBMX_HD __host__ __device__ __forceinline__
 #define LBMX_D __device__ __forceinline__
+#ifdef __CUDACC__
+	#define LBMX_GRID_CONSTANT __grid_constant__  // kernel parameter whose address may be handed to an out-of-line device function
+#else
+	#define LBMX_GRID_CONSTANT
+#endif
 
 namespace lbmx {
 
