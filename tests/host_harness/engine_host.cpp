@@ -184,7 +184,7 @@ int step_family(const oracle_desc* d, const oracle_params* op, void* df_a, void*
 	std::vector<uint32_t> blist;
 	for (long long c = (long long) d->ox * YZ; c < (long long) (d->ox + d->X) * YZ; c++) {
 		const int xs = (int) (c / YZ), yz = (int) (c - (long long) xs * YZ), z = yz / (int) d->Y;
-		if (cell_in_boundary_list(map[c], (int) L::FLUID, (int) L::PERIODIC, (int) L::WALL, (int) L::NOTHING, cell_on_face(L::NDIM, (int) d->ox, (int) d->X, (int) d->Y, (int) d->Z, xs - (int) d->ox, yz - z * (int) d->Y, z)))
+		if (cell_in_boundary_list(map[c], (int) L::FLUID, (int) L::PERIODIC, (int) L::WALL, (int) L::NOTHING, cell_on_face(L::NDIM, (int) d->ox, (int) d->X, (int) d->Y, (int) d->Z, xs - (int) d->ox, yz - z * (int) d->Y, z), ! aa))
 			blist.push_back((uint32_t) c);
 	}
 	// inert-chunk flags (lbmx_map_upload builds them for maps with sizeable GEO_NOTHING regions; here: whenever such a cell exists)

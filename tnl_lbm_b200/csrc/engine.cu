@@ -130,16 +130,18 @@ struct IsBoundaryCell
 {
 	const int16_t* map;
 	int periodic, nothing, ndim, ox, X, Y, Z;
+	bool ab;
 	__host__ __device__ bool operator()(uint32_t c) const
 	{
 		const int m = map[c];
-		if (m == 0 || m == periodic || m == nothing)
-			return false;  // GEO_FLUID, GEO_PERIODIC, GEO_NOTHING
-		if (m != 1)
+		if (m == periodic || m == nothing || (m == 0 && ! ab))
+			return false;  // GEO_PERIODIC, GEO_NOTHING, GEO_FLUID under A-A
+		if (m > 1)
 			return true;
-		// GEO_WALL (1 in every lattice): the bulk kernel bounces the walls away from the lattice faces itself (kernels.cuh: cell_in_boundary_list)
+		// GEO_WALL (1 in every lattice) away from the lattice faces is bounced by the bulk kernel itself; GEO_FLUID (0) on a face clamps under A-B
+		// (kernels.cuh: cell_in_boundary_list)
 		const int YZ = Y * Z, xs = (int) (c / (uint32_t) YZ), yz = (int) (c - (uint32_t) xs * (uint32_t) YZ), z = yz / Y;
-		return lbmx::cell_on_face(ndim, ox, X, Y, Z, xs - ox, yz - z * Y, z);
+		return lbmx::cell_in_boundary_list(m, 0, periodic, 1, nothing, lbmx::cell_on_face(ndim, ox, X, Y, Z, xs - ox, yz - z * Y, z), ab);
 	}
 };
 
@@ -154,7 +156,7 @@ __global__ void k_count_boundary_cells(const int16_t* map, long long first_cell,
 	bool b = false, r = false, o = false, w = false, inert = false;
 	if (i < YZ) {
 		const int m = map[first_cell + (long long) blockIdx.y * YZ + i];
-		b = lbmx::cell_in_boundary_list(m, 0, periodic, 1, nothing, lbmx::cell_on_face(ndim, ox, (int) gridDim.y, Y, Z, (int) blockIdx.y, i % Y, i / Y));
+		b = lbmx::cell_in_boundary_list(m, 0, periodic, 1, nothing, lbmx::cell_on_face(ndim, ox, (int) gridDim.y, Y, Z, (int) blockIdx.y, i % Y, i / Y), face_rule == 0);
 		r = m == reads_neighbour;
 		w = m == 1 && ! b;	// GEO_WALL kept by the bulk kernel
 		inert = m == nothing;
@@ -1375,7 +1377,7 @@ int lbmx_map_upload(lbmx_engine* e, const int16_t* host_map, int with_ghosts)
 	if (e->nb > 0) {
 		CU(cudaMalloc(&e->blist, (size_t) e->nb * sizeof(uint32_t)));
 		cub::CountingInputIterator<uint32_t> cells((uint32_t) first_cell);
-		IsBoundaryCell pred{e->map, periodic, nothing, ndim, (int) e->ox, (int) e->X, (int) e->Y, (int) e->Z};
+		IsBoundaryCell pred{e->map, periodic, nothing, ndim, (int) e->ox, (int) e->X, (int) e->Y, (int) e->Z, ! e->aa()};
 		int* d_selected = nullptr;
 		void* d_temp = nullptr;
 		size_t temp_bytes = 0;

@@ -39,6 +39,12 @@
 #ifndef LBMX_BULK_MINBLOCKS_AB
 	#define LBMX_BULK_MINBLOCKS_AB 5  // the A-B kernel fits 96 registers without spilling and likes the extra occupancy (kbench: 6.68 vs 6.33 TB/s)
 #endif
+#ifndef LBMX_AB_WHOLE_SECTORS
+	#define LBMX_AB_WHOLE_SECTORS 1	 // A-B bulk kernel: obstacle / inert lanes store with their warp (k_bulk phase 2)
+#endif
+#ifndef LBMX_BOUNDARY_MINBLOCKS
+	#define LBMX_BOUNDARY_MINBLOCKS 1  // __launch_bounds__ second argument of the boundary-list kernel (4 CTAs per SM, i.e. 128 registers with ~100 spilled doubles in fp64, changed nothing measurable: profiles/solid_maps_r2.md)
+#endif
 #ifndef LBMX_LD_HINT
 	#define LBMX_LD_HINT 2	// 0 plain, 1 ld.global.cs (evict-first), 2 ld.global.cg (L2 only), 3 ld.global.lu
 #endif
@@ -290,19 +296,23 @@ LBMX_D void prefetch_macro_sums(const KParams<R>& p, int c)
 	constexpr int nd = L::NDIM;
 	const R* M = p.macro;
 	const long long S = p.XYZ;
-	// rolled loops on purpose: this sits in the fluid path of every bulk kernel, whose code size matters (see bulk_cold_cell)
-	int lo = 0, hi = 0;
+	// unrolled on purpose: rolled loops (or an out-of-line call) here cost the fp32 A-A odd kernel 10 % (profiles/kbench_r2_prefetch.txt)
 	if (p.out_mode == OUT_MEAN) {
-		lo = 1 + nd;
-		hi = 1 + 2 * nd + (nd == 3 ? 6 : 3);
+#pragma unroll
+		for (int i = 1 + nd; i < 1 + 2 * nd + (nd == 3 ? 6 : 3); i++)
+			prefetch_l2(M + (i * S + c));
 	}
 	else if (nd == 2 && p.out_mode >= OUT_WITH_MEAN_2D) {
-		lo = (p.out_mode & 1) ? 3 : 5;
-		hi = (p.out_mode & 2) ? 10 : 5;
+		if (p.out_mode & 1) {
+			prefetch_l2(M + (3 * S + c));
+			prefetch_l2(M + (4 * S + c));
+		}
+		if (p.out_mode & 2) {
+#pragma unroll
+			for (int i = 5; i < 10; i++)
+				prefetch_l2(M + (i * S + c));
+		}
 	}
-#pragma unroll 1
-	for (int i = lo; i < hi; i++)
-		prefetch_l2(M + (i * S + c));
 }
 
 template <typename L, typename R>
@@ -382,15 +392,17 @@ LBMX_D void bounce_back(R (&f)[L::Q])
 // Which kernel owns a cell.  The bulk kernel takes GEO_FLUID and GEO_PERIODIC cells and -- so that obstacle-heavy maps (spheres,
 // cylinders, porous blocks of GEO_WALL) stream every population exactly once -- GEO_WALL cells away from the lattice faces, where the
 // wrapping neighbour rule it loads with coincides with the rule of a non-periodic cell (kernels.h:30-56), and GEO_NOTHING cells, which
-// only report rho = 1, u = 0.  Everything else, and walls on a face, goes to the boundary list.  Shared by lbmx_map_upload (list
-// construction) and the kernels.
+// only report rho = 1, u = 0.  Everything else, walls on a face, and under A-B the GEO_FLUID cells on a face (they clamp instead of
+// wrapping) go to the boundary list.  Shared by lbmx_map_upload (list construction) and the kernels.
 LBMX_HD bool cell_on_face(int ndim, int ox, int X, int Y, int Z, int x, int y, int z)
 {
 	return (ox == 0 && (x == 0 || x == X - 1)) || y == 0 || y == Y - 1 || (ndim == 3 && (z == 0 || z == Z - 1));
 }
-LBMX_HD bool cell_in_boundary_list(int m, int fluid, int periodic, int wall, int nothing, bool face)
+LBMX_HD bool cell_in_boundary_list(int m, int fluid, int periodic, int wall, int nothing, bool face, bool ab)
 {
-	return ! (m == fluid || m == periodic || m == nothing || (m == wall && ! face));
+	if (m == fluid)
+		return ab && face;	// A-B: a GEO_FLUID cell on a lattice face clamps its neighbour indices (kernels.h:49-56): not the rule the bulk kernel loads with
+	return ! (m == periodic || m == nothing || (m == wall && ! face));
 }
 
 // =====================================================================================================================
@@ -416,6 +428,16 @@ constexpr bool bulk_cold_inline()
 #else
 	return LBMX_COLD_INLINE_ODD_Q27 && MODE == S_AA_ODD && L::Q != 19;
 #endif
+}
+
+// Which bulk kernels ask L2 for the MACRO_Mean / WithMean sums while the populations load (prefetch_macro_sums: MACRO_Mean A-A 8.2 -> 10.2
+// GLUPS, i.e. 78 % -> 100 % of the measured HBM rate on 640 B per update).  The few instructions cost kernels that never use them nothing
+// on D3Q27 cumulant fp64 / fp32, but 5-9 % on the D3Q19 A-B and the KBC A-A odd kernels (code placement; profiles/kbench_r2_prefetch.txt),
+// and neither has a mean-collecting macro class in the reference: left out there.
+template <typename L, int KIND>
+constexpr bool bulk_prefetches_macro()
+{
+	return L::Q != 19 && ! (KIND >= K_KBC_N1 && KIND <= K_KBC_C4);
 }
 
 // Cold path of the bulk kernel, out of line so that the fluid path keeps its size (instruction cache: the fp32 kernels with two cells per
@@ -462,9 +484,11 @@ constexpr int bulk_cpt()
 #ifdef LBMX_BULK_CPT
 	return LBMX_BULK_CPT;
 #else
+	// round 2 (profiles/kbench_r2_cpt.txt), after the A-B kernels lost their face re-load: fp32 A-B is best with one cell per thread
+	// (D3Q19 MRT 5.83 -> 6.35 TB/s, D3Q27 cumulant 5.25 -> 6.16 TB/s), D2Q9 fp32 A-A odd as well (4.83 -> 5.09 TB/s)
 	if (L::Q >= 19)
-		return sizeof(R) == 8 ? 1 : (MODE == S_AA_ODD ? 1 : 2);
-	return sizeof(R) == 8 ? (MODE == S_AB ? 1 : 2) : 2;
+		return sizeof(R) == 8 ? 1 : (MODE == S_AA_EVEN ? 2 : 1);
+	return sizeof(R) == 8 ? (MODE == S_AB ? 1 : 2) : (MODE == S_AA_ODD ? 1 : 2);
 #endif
 }
 
@@ -514,39 +538,58 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 			// always in bounds: the Q population loads are in flight before the cell-type load has returned (one memory latency
 			// off the critical path of a latency-bound kernel).  A-A: GEO_FLUID cells on an unghosted domain face thereby wrap
 			// like GEO_PERIODIC ones; the reference leaves that case undefined (it steps out of the array: kernels.h:31-38,
-			// SURVEY.md App. A).  A-B: such cells clamp in the reference (kernels.h:49-56) -- they are re-loaded below.
+			// SURVEY.md App. A).  A-B: such cells clamp in the reference (kernels.h:49-56) -- they belong to the boundary list.
 			d[k] = neighbour_deltas<true>(p, true, x, y, z);
 			face[k] = cell_on_face(L::NDIM, p.ox, p.X, p.Y, p.Z, x, y, z);
 			stream_in<L, MODE, true>(p, f[k], c[k], d[k]);
-			if (p.out_mode >= OUT_MEAN)
-				prefetch_macro_sums<L>(p, c[k]);
-			if constexpr (MODE == S_AB) {
-				if (face[k] && m[k] == L::FLUID) {
-					d[k] = neighbour_deltas<false>(p, false, x, y, z);
-					stream_in<L, MODE, true>(p, f[k], c[k], d[k]);
-				}
+			if constexpr (bulk_prefetches_macro<L, KIND>()) {
+				if (p.out_mode >= OUT_MEAN)
+					prefetch_macro_sums<L>(p, c[k]);
 			}
 		}
 	}
 	// ---- phase 2: collide and store, cell by cell
 #pragma unroll
 	for (int k = 0; k < CPT; k++) {
-		if (m[k] < 0 || ! L::bulk(m[k]))
+		if (m[k] < 0)
 			continue;
 		R rho, vx, vy, vz;
+		if (L::bulk(m[k]) && ! (MODE == S_AB && face[k] && m[k] == L::FLUID)) {	 // (A-B: fluid cells on a face clamp -- boundary list)
 #ifdef LBMX_EXP_NOCOLLIDE  // development experiment only: streaming without arithmetic = the memory-system ceiling of this access pattern
-		rho = f[k][0];
-		vx = vy = vz = R(0);
+			rho = f[k][0];
+			vx = vy = vz = R(0);
 #else
-		density_velocity(f[k], p.phys, rho, vx, vy, vz);
-		collide<KIND>(f[k], p.phys, p.eq, rho, vx, vy, vz);
+			density_velocity(f[k], p.phys, rho, vx, vy, vz);
+			collide<KIND>(f[k], p.phys, p.eq, rho, vx, vy, vz);
 #endif
+		}
+		else {
+			if constexpr (MODE != S_AB || ! LBMX_AB_WHOLE_SECTORS)
+				continue;  // A-A: phase 3
+			else {
+				// A-B writes the OTHER array: a 32-byte sector that a warp's store covers only in part is not in L2 and costs DRAM a
+				// read-modify-write -- two such lanes per lattice row (the wall / GEO_NOTHING skin of a duct) slow the whole kernel by
+				// 8-14 % (profiles/solid_maps_r2_ab_features.txt).  So the obstacle and inert lanes store TOGETHER with the fluid lanes
+				// of their warp: walls their bounced populations, inert cells the values the other array already holds there (which
+				// the reference never touches: bc.h:53-60).
+				if (m[k] == L::WALL && ! face[k])
+					bounce_back<L>(f[k]);
+				else if (m[k] == L::NOTHING)
+					static_for<L::Q>([&](auto qc) { f[k][qc] = p.wr[qc][cell_index<true>(c[k])]; });
+				else
+					continue;  // a boundary-list cell
+				rho = R(1);
+				vx = vy = vz = R(0);
+			}
+		}
 		stream_out<L, MODE, true>(p, f[k], c[k], d[k]);
 		output_macro<L>(p, c[k], rho, vx, vy, vz);
 	}
-	// ---- phase 3 (cold): obstacle cells away from the faces, inert cells
+	// ---- phase 3 (cold; A-A, where stores land on sectors the warp has just read): obstacle cells away from the faces, inert cells
 #pragma unroll
 	for (int k = 0; k < CPT; k++) {
+		if (MODE == S_AB && LBMX_AB_WHOLE_SECTORS)
+			break;
 		if (m[k] != L::WALL && m[k] != L::NOTHING)
 			continue;
 		const int yz = yz0 + k * LBMX_BULK_BLOCK;
@@ -668,7 +711,7 @@ LBMX_D void mirror_pops(R (&f)[L::Q])
 }
 
 template <typename L, int KIND, typename R, int ARITH = LBMX_STRICT>
-__global__ void __launch_bounds__(128) k_boundary(const KParams<R> p)
+__global__ void __launch_bounds__(128, LBMX_BOUNDARY_MINBLOCKS) k_boundary(const KParams<R> p)
 {
 	const int i = p.nb_begin + blockIdx.x * blockDim.x + threadIdx.x;
 	// Chained behind the bulk kernel of the same step on one stream.  pdl == 1: the two are independent (disjoint cells, one writer per

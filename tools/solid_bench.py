@@ -26,6 +26,21 @@ def make_map(kind, S, streaming):
     m = np.full((S, S, S), PERIODIC, dtype=np.int16)  # (x, z, y)
     if kind == "periodic":
         return m
+    if kind == "fluid":  # every cell GEO_FLUID: under A-B the face cells clamp (and are loaded twice by the bulk kernel)
+        m[...] = FLUID
+        return m
+    if kind == "shell":  # only the GEO_NOTHING skin of the duct
+        m[:, 0, :] = m[:, S - 1, :] = m[:, :, 0] = m[:, :, S - 1] = NOTHING
+        return m
+    if kind == "ring":  # only the wall ring of the duct
+        m[:, 1, :] = m[:, S - 2, :] = m[:, :, 1] = m[:, :, S - 2] = WALL
+        return m
+    if kind == "plane":  # one wall plane: whole rows of obstacle cells, none inside the other rows
+        m[:, 1, :] = WALL
+        return m
+    if kind == "columns":  # two obstacle cells in every row
+        m[:, :, 1] = m[:, :, S - 2] = WALL
+        return m
     if kind == "duct":  # sim_NSE/sim_2.cu:125-138
         m[:, 1, :] = m[:, S - 2, :] = m[:, :, 1] = m[:, :, S - 2] = WALL
         m[:, 0, :] = m[:, S - 1, :] = m[:, :, 0] = m[:, :, S - 1] = NOTHING
