@@ -59,7 +59,8 @@ enum lbmx_coll {
 	LBMX_COLL_KBC_C1 = 17,			   /* D3Q27_KBC_C1..C4  d3q27/col_kbc_c.h:283-1301 (shear part from central moments) */
 	LBMX_COLL_KBC_C2 = 18,
 	LBMX_COLL_KBC_C3 = 19,
-	LBMX_COLL_KBC_C4 = 20
+	LBMX_COLL_KBC_C4 = 20,
+	LBMX_COLL_BGK_GALILEAN = 21		   /* D3Q27_BGK built with -DUSE_GALILEAN_CORRECTION (defs.h:253; col_bgk.h:20-45) */
 };
 enum lbmx_eq {
 	LBMX_EQ_STD = 0,	  /* D3Q27_EQ eq.h:8-130, D2Q9_EQ */

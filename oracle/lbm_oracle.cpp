@@ -607,15 +607,43 @@ void collide_srt27(Cell<R, 27>& K, int eqkind)	// col_srt.h:16-108
 		K.f[q] += (feq[q] - K.f[q]) / tau + (one - half / tau) * S[q] * feq[q];
 }
 
-template <typename R>
-void collide_bgk27(Cell<R, 27>& K)	// col_bgk.h:16-145 (no Galilean correction); product-form equilibrium, EQ argument unused
+// col_bgk.h:16-145; product-form equilibrium, EQ argument unused.  GALILEAN: the build with -DUSE_GALILEAN_CORRECTION (defs.h:253,
+// col_bgk.h:20-45): the diagonal second moments, summed in the reference's order, correct the zero-velocity factor of each axis.
+template <typename R, bool GALILEAN = false>
+void collide_bgk27(Cell<R, 27>& K)
 {
-	const R one = 1, half = (R) 0.5, third = (R) (1.0 / 3.0);
+	const R one = 1, half = (R) 0.5, third = (R) (1.0 / 3.0), three = 3;
 	const R omega1 = one / ((R) 3.0 * K.nu + half);
 	R g[3][3];	// g[axis][sign+1]
 	const R v[3] = {K.vx, K.vy, K.vz};
+	R G[3] = {0, 0, 0};
+	if (GALILEAN) {
+		// m_200: x in (-,+), (y,z) in the order mm mp mz pm pp pz zm zp zz; m_020: x in (-,0,+), y in (-,+), z in (-,+,0);
+		// m_002: x in (-,0,+), y in (-,0,+), z in (-,+)   (col_bgk.h:21-26)
+		static const int o9[9][2] = {{-1, -1}, {-1, 1}, {-1, 0}, {1, -1}, {1, 1}, {1, 0}, {0, -1}, {0, 1}, {0, 0}};
+		static const int x3[3] = {-1, 0, 1}, z3[3] = {-1, 1, 0};
+		R m[3] = {0, 0, 0};
+		int n = 0;
+		for (int a = -1; a <= 1; a += 2)
+			for (int i = 0; i < 9; i++, n++)
+				m[0] = n == 0 ? K.f[find27(a, o9[i][0], o9[i][1])] : m[0] + K.f[find27(a, o9[i][0], o9[i][1])];
+		n = 0;
+		for (int a = 0; a < 3; a++)
+			for (int b = -1; b <= 1; b += 2)
+				for (int c = 0; c < 3; c++, n++)
+					m[1] = n == 0 ? K.f[find27(x3[a], b, z3[c])] : m[1] + K.f[find27(x3[a], b, z3[c])];
+		n = 0;
+		for (int a = 0; a < 3; a++)
+			for (int b = 0; b < 3; b++)
+				for (int c = -1; c <= 1; c += 2, n++)
+					m[2] = n == 0 ? K.f[find27(x3[a], x3[b], c)] : m[2] + K.f[find27(x3[a], x3[b], c)];
+		for (int a = 0; a < 3; a++) {
+			const R D = -omega1 * half * (three * m[a] / K.rho - one - three * v[a] * v[a]);
+			G[a] = -three * v[a] * v[a] * D * (one / omega1 - half);
+		}
+	}
 	for (int a = 0; a < 3; a++) {
-		const R z = third - one + v[a] * v[a];
+		const R z = GALILEAN ? third - one + v[a] * v[a] + G[a] : third - one + v[a] * v[a];
 		const R p = -half * (z + one + v[a]);
 		g[a][1] = z;
 		g[a][2] = p;
@@ -760,6 +788,7 @@ void collide(Cell<R, 27>& K, const oracle_desc& d)
 		case ORC_COLL_CUM: collide_cum(K); break;
 		case ORC_COLL_SRT: collide_srt27(K, d.eq); break;
 		case ORC_COLL_BGK: collide_bgk27(K); break;
+		case ORC_COLL_BGK_GALILEAN: collide_bgk27<R, true>(K); break;
 		case ORC_COLL_MRT_LES: collide_mrt27(K); break;
 		case ORC_COLL_CLBM: collide_clbm27(K); break;
 		case ORC_COLL_SRT_MODIF_FORCE: collide_srt_modif27(K, d.eq); break;
@@ -1293,7 +1322,7 @@ bool supported(const oracle_desc* d)
 	if (d->macro < ORC_MACRO_VOID || d->macro > ORC_MACRO_WITH_MEAN_2D || (d->macro == ORC_MACRO_WITH_MEAN_2D && d->lattice != ORC_D2Q9))
 		return false;
 	if (d->lattice == ORC_D3Q27)
-		return ((d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE) || (d->coll >= ORC_COLL_CUM_2017 && d->coll <= ORC_COLL_KBC_C4))
+		return ((d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE) || (d->coll >= ORC_COLL_CUM_2017 && d->coll <= ORC_COLL_BGK_GALILEAN))
 			&& (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM || d->eq == ORC_EQ_ENTROPIC);
 	if (d->lattice == ORC_D2Q9)
 		return (d->coll == ORC_COLL_SRT || d->coll == ORC_COLL_CLBM) && d->eq == ORC_EQ_STD && d->Z == 1;

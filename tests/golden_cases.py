@@ -54,6 +54,10 @@ CASES = [
     Case("srtinv_f32_aa_zoo", O.Desc(coll=O.SRT, eq=O.EQ_INV_CUM, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("bgk_f64_aa_zoo", O.Desc(coll=O.BGK, eq=O.EQ_STD, streaming=O.AA, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("bgk_f32_ab_zoo", O.Desc(coll=O.BGK, eq=O.EQ_STD, streaming=O.AB, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    # D3Q27_BGK built with USE_GALILEAN_CORRECTION (defs.h:253, col_bgk.h:20-45)
+    Case("bgkgal_f64_ab_zoo", O.Desc(coll=O.BGK_GALILEAN, eq=O.EQ_STD, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("bgkgal_f32_aa_zoo", O.Desc(coll=O.BGK_GALILEAN, eq=O.EQ_STD, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("bgkgal_f64_aa_box", O.Desc(coll=O.BGK_GALILEAN, eq=O.EQ_STD, streaming=O.AA, X=12, Y=12, Z=12), O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 40, "smooth"),
     Case("mrt_f64_ab_zoo", O.Desc(coll=O.MRT_LES, eq=O.EQ_STD, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("mrt_f32_aa_zoo", O.Desc(coll=O.MRT_LES, eq=O.EQ_STD, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("d2q9_srt_f64_ab_cavity", O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, X=24, Y=24, Z=1), O.Params(lbmViscosity=0.05, inflow_vx=0.1), lc.map_cavity_2d, 40, "uniform"),

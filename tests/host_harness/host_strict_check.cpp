@@ -96,6 +96,8 @@ int main()
 	r |= run<double, K_CUM>(ORC_COLL_CUM, ORC_EQ_INV_CUM, ORC_F64);
 	r |= run<float, K_SRT>(ORC_COLL_SRT, ORC_EQ_STD, ORC_F32);
 	r |= run<float, K_BGK>(ORC_COLL_BGK, ORC_EQ_STD, ORC_F32);
+	r |= run<float, K_BGK_GAL>(ORC_COLL_BGK_GALILEAN, ORC_EQ_STD, ORC_F32);
+	r |= run<double, K_BGK_GAL>(ORC_COLL_BGK_GALILEAN, ORC_EQ_STD, ORC_F64);
 	r |= run<float, K_MRT>(ORC_COLL_MRT_LES, ORC_EQ_STD, ORC_F32);
 	r |= run<float, K_CLBM>(ORC_COLL_CLBM, ORC_EQ_STD, ORC_F32);
 	r |= run<double, K_CLBM>(ORC_COLL_CLBM, ORC_EQ_STD, ORC_F64);

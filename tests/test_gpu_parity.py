@@ -83,6 +83,78 @@ def test_graph_replay_is_invisible(name, policy):
         assert stats.kernel_launches == one_stats.kernel_launches  # replayed launches are counted like plain ones
 
 
+def _map_inert_regions(d):
+    """Large GEO_NOTHING regions (whole 128-cell chunks of a plane: the bulk kernel's inert-chunk flags are built and used), a wall layer
+    in front of them, obstacle blocks inside the fluid, and -- A-B -- a few single inert / obstacle cells inside otherwise fluid rows
+    (lanes that must store together with their warp)."""
+    g = lc.geo(d)
+    m = d.new_map(g["PERIODIC"])
+    Z = d.Z
+    if Z > 1:
+        m[:, Z // 2 :, :] = g["NOTHING"]
+        m[:, Z // 2 - 1, :] = g["WALL"]
+        m[:, 1, :] = g["WALL"]
+        m[:, 0, :] = g["NOTHING"]
+        m[2:5, 3:6, 5:40] = g["WALL"]
+        m[1::3, 2, 7] = g["NOTHING"] if d.streaming == O.AB else g["WALL"]
+        m[2::3, 4, 9::17] = g["WALL"]
+    else:
+        m[:, 0, d.Y // 2 :] = g["NOTHING"]
+        m[:, 0, d.Y // 2 - 1] = g["PERIODIC"]
+    return m
+
+
+@pytest.mark.parametrize("coll,eq,st,prec,macro", [(O.CUM, O.EQ_INV_CUM, O.AA, O.F64, O.MACRO_DEFAULT), (O.CUM, O.EQ_INV_CUM, O.AB, O.F64, O.MACRO_DEFAULT),
+                                                   (O.SRT, O.EQ_STD, O.AB, O.F32, O.MACRO_DEFAULT), (O.MRT_LES, O.EQ_STD, O.AA, O.F32, O.MACRO_DEFAULT),
+                                                   (O.CUM, O.EQ_INV_CUM, O.AA, O.F64, O.MACRO_MEAN), (O.BGK, O.EQ_STD, O.AB, O.F64, O.MACRO_MEAN)])
+def test_obstacles_and_inert_regions_owned_by_the_bulk_kernel(coll, eq, st, prec, macro):
+    """Round 2: GEO_WALL cells away from the faces and GEO_NOTHING cells belong to the bulk kernel (kernels.cuh: cell_in_boundary_list;
+    d3q27/bc.h:53-60, 147-165), inert 128-cell chunks skip their loads, A-B obstacle / inert lanes store with their warp.  Against the CPU
+    checker, distributions and macroscopic fields (MACRO_Mean exercises the prefetched read-modify-write fields), in batches and one by one."""
+    d = O.Desc(coll=coll, eq=eq, streaming=st, precision=prec, macro=macro, X=7, Y=160, Z=12)
+    case = gc.Case("inert", d, O.Params(lbmViscosity=5e-3, fx=1e-5, fy=-2e-6), _map_inert_regions, 11, "noisy")
+    df, mac, stats = run_case_engine(case)
+    m = case.make_map(d)
+    assert stats.boundary_cells < int(np.sum(m == 1)) and stats.bulk_cells > int(np.sum(m == 8))
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=4)
+    compare(case, df, mac, df_ref, mac_ref, TOL[prec], "obstacles / inert regions")
+    df1, mac1, _ = run_case_engine(case, chunk=1, macro_policy=B.MACRO_EVERY_STEP)
+    if macro == O.MACRO_DEFAULT:
+        assert np.array_equal(df, df1) and np.array_equal(mac, mac1)
+
+
+@pytest.mark.parametrize("name", ["d2q9_srt_f64_ab_cavity", "d2q9_srt_f64_aa_cavity", "cum_f64_ab_sim1", "cum_f64_aa_duct", "cum_f32_ab_zoo"])
+def test_programmatic_dependent_launch_is_invisible(name):
+    """Small single-slab lattices chain bulk and boundary-list kernels on one stream under programmatic dependent launch (the list kernel
+    starts beside the bulk kernel of its step and waits for it before it exits); LBMX_NO_PDL=1 restores the fork / join through a second
+    stream.  Same bits either way, with and without graph replay."""
+    if name not in gc.BY_NAME:
+        pytest.skip(f"no golden case {name}")
+    case = gc.BY_NAME[name]
+    out = {}
+    for no_pdl in ("", "1"):
+        for no_graph in ("", "1"):
+            env = {"LBMX_NO_PDL": no_pdl, "LBMX_NO_GRAPH": no_graph}
+            old = {k: os.environ.get(k) for k in env}
+            try:
+                for k, v in env.items():
+                    if v:
+                        os.environ[k] = v
+                    else:
+                        os.environ.pop(k, None)
+                big = gc.Case(case.name + "_long", case.desc, case.params, case.make_map, max(case.nsteps, 24), case.init)
+                out[(no_pdl, no_graph)] = run_case_engine(big)
+            finally:
+                for k, v in old.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+    ref = out[("1", "1")]
+    for key, got in out.items():
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), (name, key)
+
+
 def test_aa_cells_on_bare_faces_are_counted_and_stay_inside_the_engine():
     """The A-A index rule is unclamped (kernels.h:30-37): a face cell that is neither GEO_NOTHING nor periodic, on a slab without ghost
     planes, addresses x+-1 / y+-1 / z+-1 outside the lattice -- undefined in the reference.  lbmx_map_upload counts such cells, and

@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 SRC = os.path.join(ROOT, "tests", "host_harness", "engine_host.cpp")
 BIN = os.path.join(ROOT, "tests", "host_harness", "bin")
-KIND_NUMBER = {"K_CUM": 0, "K_SRT": 1, "K_BGK": 2, "K_MRT": 3, "K_CLBM": 4, "K_SRT_MF": 5, "K_CUM_2017": 10, "K_CUM_AALIAS": 11, "K_CUM_2017_AALIAS": 12,
+KIND_NUMBER = {"K_CUM": 0, "K_SRT": 1, "K_BGK": 2, "K_MRT": 3, "K_CLBM": 4, "K_SRT_MF": 5, "K_CUM_2017": 10, "K_CUM_AALIAS": 11, "K_CUM_2017_AALIAS": 12, "K_BGK_GAL": 21,
                **{f"K_KBC_{g}{i}": 13 + 4 * k + i - 1 for k, g in enumerate("NC") for i in (1, 2, 3, 4)}}
 TOL = {O.F64: 1e-12, O.F32: 1e-5}
 
@@ -317,6 +317,22 @@ def test_d3q27_random_zoo_on_the_host(strict_lib, coll, eq, streaming, prec):
     m = lc.map_random_ab(d) if streaming == O.AB else lc.map_random_aa(d)
     p = O.Params(lbmViscosity=0.013, fx=3e-5, fy=-2e-5, fz=1e-5, inflow_vx=0.04, inflow_vy=0.01, inflow_vz=-0.02)
     assert_host_equals_port(run_host_and_port(d, m, p, 4), d, f"coll={coll} eq={eq} st={streaming} prec={prec}")
+
+
+@pytest.mark.parametrize("macro", [O.MACRO_DEFAULT, O.MACRO_MEAN])
+@pytest.mark.parametrize("prec", [O.F64, O.F32])
+@pytest.mark.parametrize("streaming", [O.AB, O.AA])
+def test_obstacles_and_inert_regions_in_the_bulk_kernel_on_the_host(strict_lib, streaming, prec, macro):
+    """GEO_WALL cells away from the faces and GEO_NOTHING cells are owned by the bulk kernel (kernels.cuh: cell_in_boundary_list): whole
+    inert 128-cell chunks (skipped through the inert flags), obstacle blocks, single obstacle / inert cells inside fluid rows (A-B: they
+    store with their warp), a wall layer on a lattice face (stays in the boundary list), rows longer than a thread block."""
+    from test_gpu_parity import _map_inert_regions
+
+    d = O.Desc(coll=O.CUM, eq=O.EQ_INV_CUM, streaming=streaming, precision=prec, macro=macro, X=7, Y=160, Z=12)
+    m = _map_inert_regions(d)
+    assert (m == 8).mean() > 1 / 16 and (m == 1).sum() > 100
+    p = O.Params(lbmViscosity=5e-3, fx=1e-5, fy=-2e-6)
+    assert_host_equals_port(run_host_and_port(d, m, p, 5), d, f"inert regions st={streaming} prec={prec} macro={macro}")
 
 
 @pytest.mark.parametrize("prec", [O.F64, O.F32])

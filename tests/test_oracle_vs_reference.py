@@ -17,7 +17,7 @@ pytestmark = pytest.mark.skipif(
     reason="oracle/_ref (reference build) or the port library is not built",
 )
 
-COMBOS_3D = [(O.CUM, O.EQ_INV_CUM), (O.CUM, O.EQ_STD), (O.SRT, O.EQ_STD), (O.SRT, O.EQ_INV_CUM), (O.BGK, O.EQ_STD), (O.MRT_LES, O.EQ_STD), (O.MRT_LES, O.EQ_INV_CUM),
+COMBOS_3D = [(O.CUM, O.EQ_INV_CUM), (O.CUM, O.EQ_STD), (O.SRT, O.EQ_STD), (O.SRT, O.EQ_INV_CUM), (O.BGK, O.EQ_STD), (O.BGK_GALILEAN, O.EQ_STD), (O.MRT_LES, O.EQ_STD), (O.MRT_LES, O.EQ_INV_CUM),
              (O.CLBM, O.EQ_STD), (O.CLBM, O.EQ_INV_CUM), (O.SRT_MODIF_FORCE, O.EQ_STD), (O.SRT_MODIF_FORCE, O.EQ_INV_CUM),
              (O.CUM_2017, O.EQ_INV_CUM), (O.CUM_ANTIALIAS, O.EQ_INV_CUM), (O.CUM_2017_ANTIALIAS, O.EQ_INV_CUM), (O.CUM_2017_ANTIALIAS, O.EQ_STD),
              (O.KBC_N1, O.EQ_STD), (O.KBC_N2, O.EQ_ENTROPIC), (O.KBC_N3, O.EQ_ENTROPIC), (O.KBC_N4, O.EQ_ENTROPIC), (O.KBC_N4, O.EQ_INV_CUM),

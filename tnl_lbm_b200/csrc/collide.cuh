@@ -375,17 +375,37 @@ LBMX_D void collide_srt(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R
 	});
 }
 
-template <typename R>
+// GALILEAN: the build with USE_GALILEAN_CORRECTION (defs.h:253, col_bgk.h:20-45) -- the diagonal second moments (here from the
+// z-column sums, any order: default arithmetic) correct the zero-velocity factor of each axis
+template <bool GALILEAN = false, typename R>
 LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
 	const R omega1 = P.omega1;
 	const R pre = (R(1) - R(0.5) * omega1) * (R(3) / rho);
 	const R v[3] = {vx, vy, vz};
+	R G[3] = {R(0), R(0), R(0)};
+	if constexpr (GALILEAN) {
+		R m[3] = {R(0), R(0), R(0)};
+		static_for<27>([&](auto qc) {
+			constexpr int q = qc;
+			if constexpr (L::cx(q) != 0)
+				m[0] += f[q];
+			if constexpr (L::cy(q) != 0)
+				m[1] += f[q];
+			if constexpr (L::cz(q) != 0)
+				m[2] += f[q];
+		});
+		const R k = (R(1) / omega1 - R(0.5)) * (R(1.5) * omega1);  // -3 v^2 D (1/omega - 1/2) with D = -omega/2 (3 m/rho - 1 - 3 v^2)
+		const R irho3 = R(3) / rho;
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+			G[a] = (v[a] * v[a]) * k * ((m[a] * irho3 - R(1)) - R(3) * (v[a] * v[a]));
+	}
 	R g[3][3];
 #pragma unroll
 	for (int a = 0; a < 3; a++) {
-		const R z = (R(1.0 / 3.0) - R(1)) + v[a] * v[a];
+		const R z = ((R(1.0 / 3.0) - R(1)) + v[a] * v[a]) + G[a];
 		const R p = R(-0.5) * ((z + R(1)) + v[a]);
 		g[a][1] = z;
 		g[a][2] = p;
@@ -657,7 +677,8 @@ LBMX_D void equilibrium_any(R (&feq)[Q], int eqkind, R rho, R vx, R vy, R vz)
 // operator tags: what COLL means for a kernel instantiation
 // --------------------------------------------------------------------------------------------------------------------
 enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 /* D2Q9_CLBM or D3Q27_CLBM, by lattice */, K_SRT_MF = 5, K_CUM_2017 = 10, K_CUM_AALIAS = 11, K_CUM_2017_AALIAS = 12 /* D3Q27_CUM built with the switches of defs.h:254-255 */,
-						K_KBC_N1 = 13, K_KBC_N2, K_KBC_N3, K_KBC_N4, K_KBC_C1, K_KBC_C2, K_KBC_C3, K_KBC_C4 };
+						K_KBC_N1 = 13, K_KBC_N2, K_KBC_N3, K_KBC_N4, K_KBC_C1, K_KBC_C2, K_KBC_C3, K_KBC_C4,
+						K_BGK_GAL = 21 /* D3Q27_BGK built with USE_GALILEAN_CORRECTION (defs.h:253) */ };
 
 template <int KIND, typename R>
 LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
@@ -687,6 +708,8 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 		}
 		else if constexpr (KIND == K_BGK)
 			strict::collide_bgk(f, P, rho, vx, vy, vz);
+		else if constexpr (KIND == K_BGK_GAL)
+			strict::collide_bgk<true>(f, P, rho, vx, vy, vz);
 		else
 			strict::collide_mrt(f, P, rho, vx, vy, vz);
 	}
@@ -696,6 +719,8 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 		collide_srt(f, P, eqkind, rho, vx, vy, vz);
 	else if constexpr (KIND == K_BGK)
 		collide_bgk(f, P, rho, vx, vy, vz);
+	else if constexpr (KIND == K_BGK_GAL)
+		collide_bgk<true>(f, P, rho, vx, vy, vz);
 	else
 		collide_mrt(f, P, rho, vx, vy, vz);
 }

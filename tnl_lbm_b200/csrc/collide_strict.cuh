@@ -274,18 +274,47 @@ LBMX_D void collide_srt(R (&f)[27], const R (&feq)[27], const Phys<R>& P, R rho,
 	});
 }
 
-// col_bgk.h:16-145 (no Galilean correction)
-template <typename R>
+// col_bgk.h:16-145; GALILEAN: built with USE_GALILEAN_CORRECTION (defs.h:253, col_bgk.h:20-45), second moments summed in the
+// reference's order: m_200 over x in (-,+) with (y,z) = mm mp mz pm pp pz zm zp zz; m_020 over x in (-,0,+), y in (-,+), z in (-,+,0);
+// m_002 over x, y in (-,0,+), z in (-,+)
+template <bool GALILEAN = false, typename R>
 LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
-	const R one = R(1), half = R(0.5), third = R(1.0 / 3.0);
+	const R one = R(1), half = R(0.5), third = R(1.0 / 3.0), three = R(3);
 	const R omega1 = one / (R(3) * P.nu + half);
 	const R v[3] = {vx, vy, vz};
+	R G[3] = {R(0), R(0), R(0)};
+	if constexpr (GALILEAN) {
+		R m[3];
+		static_for<18>([&](auto ic) {
+			constexpr int i = ic;
+			constexpr int s3[3] = {-1, 1, 0}, x3[3] = {-1, 0, 1};
+			constexpr int o9[9][2] = {{-1, -1}, {-1, 1}, {-1, 0}, {1, -1}, {1, 1}, {1, 0}, {0, -1}, {0, 1}, {0, 0}};
+			constexpr int q0 = L::find(i < 9 ? -1 : 1, o9[i % 9][0], o9[i % 9][1]);
+			constexpr int q1 = L::find(x3[i / 6], (i / 3) % 2 == 0 ? -1 : 1, s3[i % 3]);
+			constexpr int q2 = L::find(x3[i / 6], x3[(i / 2) % 3], i % 2 == 0 ? -1 : 1);
+			if constexpr (i == 0) {
+				m[0] = f[q0];
+				m[1] = f[q1];
+				m[2] = f[q2];
+			}
+			else {
+				m[0] = m[0] + f[q0];
+				m[1] = m[1] + f[q1];
+				m[2] = m[2] + f[q2];
+			}
+		});
+#pragma unroll
+		for (int a = 0; a < 3; a++) {
+			const R D = -omega1 * half * (three * m[a] / rho - one - three * v[a] * v[a]);
+			G[a] = -three * v[a] * v[a] * D * (one / omega1 - half);
+		}
+	}
 	R g[3][3];
 #pragma unroll
 	for (int a = 0; a < 3; a++) {
-		const R z = third - one + v[a] * v[a];
+		const R z = GALILEAN ? third - one + v[a] * v[a] + G[a] : third - one + v[a] * v[a];
 		const R p = -half * (z + one + v[a]);
 		g[a][1] = z;
 		g[a][2] = p;

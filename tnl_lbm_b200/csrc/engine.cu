@@ -739,6 +739,7 @@ bool pick_kernels(lbmx_engine* e)
 				case LBMX_COLL_CUM: return e->f64() ? get_kernels_d3q27_cum_strict(e->kd) : get_kernels_d3q27_cum_strict(e->kf);
 				case LBMX_COLL_SRT: return e->f64() ? get_kernels_d3q27_srt_strict(e->kd) : get_kernels_d3q27_srt_strict(e->kf);
 				case LBMX_COLL_BGK: return e->f64() ? get_kernels_d3q27_bgk_strict(e->kd) : get_kernels_d3q27_bgk_strict(e->kf);
+				case LBMX_COLL_BGK_GALILEAN: return e->f64() ? get_kernels_d3q27_bgkgal_strict(e->kd) : get_kernels_d3q27_bgkgal_strict(e->kf);
 				case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt_strict(e->kd) : get_kernels_d3q27_mrt_strict(e->kf);
 				case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm_strict(e->kd) : get_kernels_d3q27_clbm_strict(e->kf);
 				case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf_strict(e->kd) : get_kernels_d3q27_srtmf_strict(e->kf);
@@ -768,6 +769,7 @@ bool pick_kernels(lbmx_engine* e)
 			case LBMX_COLL_CUM: return e->f64() ? get_kernels_d3q27_cum(e->kd) : get_kernels_d3q27_cum(e->kf);
 			case LBMX_COLL_SRT: return e->f64() ? get_kernels_d3q27_srt(e->kd) : get_kernels_d3q27_srt(e->kf);
 			case LBMX_COLL_BGK: return e->f64() ? get_kernels_d3q27_bgk(e->kd) : get_kernels_d3q27_bgk(e->kf);
+			case LBMX_COLL_BGK_GALILEAN: return e->f64() ? get_kernels_d3q27_bgkgal(e->kd) : get_kernels_d3q27_bgkgal(e->kf);
 			case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt(e->kd) : get_kernels_d3q27_mrt(e->kf);
 			case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm(e->kd) : get_kernels_d3q27_clbm(e->kf);
 			case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf(e->kd) : get_kernels_d3q27_srtmf(e->kf);

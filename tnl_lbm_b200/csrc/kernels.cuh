@@ -469,7 +469,7 @@ constexpr int bulk_minblocks()
 {
 	if (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
 		return sizeof(R) == 8 ? (MODE == S_AA_ODD ? LBMX_KBC_MINBLOCKS_F64_ODD : LBMX_KBC_MINBLOCKS_F64) : LBMX_KBC_MINBLOCKS_F32;
-	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_SRT_MF || KIND == K_CLBM))
+	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_BGK_GAL || KIND == K_SRT_MF || KIND == K_CLBM))
 		return LBMX_BULK_MINBLOCKS < 3 ? LBMX_BULK_MINBLOCKS : 3;
 	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;
 }
@@ -971,6 +971,8 @@ bool get_kernels_d3q27_srt(StepKernels<float>&);
 bool get_kernels_d3q27_srt(StepKernels<double>&);
 bool get_kernels_d3q27_bgk(StepKernels<float>&);
 bool get_kernels_d3q27_bgk(StepKernels<double>&);
+bool get_kernels_d3q27_bgkgal(StepKernels<float>&);
+bool get_kernels_d3q27_bgkgal(StepKernels<double>&);
 bool get_kernels_d3q27_mrt(StepKernels<float>&);
 bool get_kernels_d3q27_mrt(StepKernels<double>&);
 bool get_kernels_d3q27_cum2017(StepKernels<float>&);
@@ -1032,6 +1034,8 @@ bool get_kernels_d3q27_srt_strict(StepKernels<float>&);
 bool get_kernels_d3q27_srt_strict(StepKernels<double>&);
 bool get_kernels_d3q27_bgk_strict(StepKernels<float>&);
 bool get_kernels_d3q27_bgk_strict(StepKernels<double>&);
+bool get_kernels_d3q27_bgkgal_strict(StepKernels<float>&);
+bool get_kernels_d3q27_bgkgal_strict(StepKernels<double>&);
 bool get_kernels_d3q27_mrt_strict(StepKernels<float>&);
 bool get_kernels_d3q27_mrt_strict(StepKernels<double>&);
 bool get_kernels_d2q9_srt_strict(StepKernels<float>&);

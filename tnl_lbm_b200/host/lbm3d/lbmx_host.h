@@ -489,7 +489,11 @@ LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM_ANTIALIAS, "CUM")
 LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM, "CUM")
 #endif
 LBMX_COLL_TAG(D3Q27_SRT, D3Q27_EQ, LBMX_COLL_SRT, "SRT")
+#if defined(USE_GALILEAN_CORRECTION)  // defs.h:253: the solver was built with the switch, the engine has that build of the operator too
+LBMX_COLL_TAG(D3Q27_BGK, D3Q27_EQ, LBMX_COLL_BGK_GALILEAN, "BGK")
+#else
 LBMX_COLL_TAG(D3Q27_BGK, D3Q27_EQ, LBMX_COLL_BGK, "BGK")
+#endif
 LBMX_COLL_TAG(D3Q27_MRT, D3Q27_EQ, LBMX_COLL_MRT_LES, "MRT_LES")
 LBMX_COLL_TAG(D3Q27_CLBM, D3Q27_EQ, LBMX_COLL_CLBM, "CLBM")
 LBMX_COLL_TAG(D3Q27_SRT_MODIF_FORCE, D3Q27_EQ, LBMX_COLL_SRT_MODIF_FORCE, "SRT_MRT_MODIF_FORCE")
