@@ -98,6 +98,12 @@ def _map_inert_regions(d):
         m[2:5, 3:6, 5:40] = g["WALL"]
         m[1::3, 2, 7] = g["NOTHING"] if d.streaming == O.AB else g["WALL"]
         m[2::3, 4, 9::17] = g["WALL"]
+        if d.streaming == O.AA:
+            # A-A takes neighbours at +-1 unclamped (kernels.h:30-37): a cell on a bare lattice face that is not periodic reaches outside
+            # the lattice -- undefined in the reference.  A periodic skin keeps the case well defined (as lc.map_random_aa does).
+            m[0] = m[-1] = g["PERIODIC"]
+            m[:, 0, :] = m[:, -1, :] = g["PERIODIC"]
+            m[:, :, 0] = m[:, :, -1] = g["PERIODIC"]
     else:
         m[:, 0, d.Y // 2 :] = g["NOTHING"]
         m[:, 0, d.Y // 2 - 1] = g["PERIODIC"]
