@@ -139,7 +139,7 @@ KParams<R> params_for(const oracle_desc* d, const oracle_params* op, R* cur, R* 
 	p.stat_counter = op->stat_counter;
 	const bool vm = d->macro == ORC_MACRO_VOID;	 // MACRO_Void::copyQuantities is empty: viscosity 1, no force (d3q27/macro.h:174-188)
 	p.phys.nu = vm ? R(1) : (R) op->lbmViscosity;
-	p.phys.omega1 = R(1) / (R(3) * p.phys.nu + R(0.5));
+	set_rates(p.phys);
 	p.phys.fx = vm ? R(0) : (R) op->fx;
 	p.phys.fy = vm ? R(0) : (R) op->fy;
 	p.phys.fz = (vm || d->lattice == ORC_D2Q9) ? R(0) : (R) op->fz;

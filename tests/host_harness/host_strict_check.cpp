@@ -33,7 +33,7 @@ int run(int coll, int eq, int prec)
 		double w = n == 0 ? 8. / 27 : n == 1 ? 2. / 27 : n == 2 ? 1. / 54 : 1. / 216;
 		for (size_t i = 0; i < XYZ; i++) a[q * XYZ + i] = (R) (w * (1 + 0.05 * (rand() / (double) RAND_MAX - 0.5)));
 	}
-	Phys<R> P; P.nu = (R) p.lbmViscosity; P.omega1 = R(1) / (R(3) * P.nu + R(0.5)); P.fx = (R) p.fx; P.fy = (R) p.fy; P.fz = (R) p.fz;
+	Phys<R> P; P.nu = (R) p.lbmViscosity; set_rates(P); P.fx = (R) p.fx; P.fy = (R) p.fy; P.fz = (R) p.fz;
 	for (int x = 0; x < N; x++) for (int z = 0; z < N; z++) for (int y = 0; y < N; y++) {
 		R f[27];
 		for (int q = 0; q < 27; q++) {
@@ -70,7 +70,7 @@ int run2d(int coll, int prec)
 		double w = n == 0 ? 4. / 9 : n == 1 ? 1. / 9 : 1. / 36;
 		for (size_t i = 0; i < XYZ; i++) a[q * XYZ + i] = (R) (w * (1 + 0.05 * (rand() / (double) RAND_MAX - 0.5)));
 	}
-	Phys<R> P; P.nu = (R) p.lbmViscosity; P.omega1 = R(1) / (R(3) * P.nu + R(0.5)); P.fx = (R) p.fx; P.fy = (R) p.fy; P.fz = 0;
+	Phys<R> P; P.nu = (R) p.lbmViscosity; set_rates(P); P.fx = (R) p.fx; P.fy = (R) p.fy; P.fz = 0;
 	for (int x = 0; x < NX; x++) for (int y = 0; y < NY; y++) {
 		R f[9];
 		for (int q = 0; q < 9; q++) {

@@ -17,7 +17,28 @@ struct Phys
 	R nu;		  // lbmViscosity (KS.lbmViscosity)
 	R omega1;	  // 1 / (3 nu + 1/2), evaluated once on the host in precision R (col_cum.h:175, col_srt.h:19, col_bgk.h:19)
 	R fx, fy, fz; // homogeneous body force (NSE_Data, lbm_data.h:87-96)
+	R g17[5];	  // omega3, omega4, omega5, A, B of the 2017 cumulant parametrisation (col_cum.h:177-208): functions of nu alone, evaluated
+				  // once on the host (set_rates) for the default-arithmetic kernels; the parity-arithmetic kernels evaluate them per cell as the reference does
 };
+
+// every rate that depends on the viscosity alone; call after setting P.nu
+template <typename R>
+inline __host__ __device__ void set_rates(Phys<R>& P)
+{
+	const R one = 1, two = 2, three = 3, four = 4, five = 5, six = 6, seven = 7, eight = 8, nine = 9, n10 = 10, n11 = 11, n13 = 13, n15 = 15, n16 = 16, n18 = 18, n24 = 24, n26 = 26,
+			n28 = 28, n42 = 42, n46 = 46, n48 = 48, n56 = 56, n216 = 216;
+	P.omega1 = one / (three * P.nu + R(0.5));  // IEEE division in precision R: the same bits the reference computes per cell
+	const R omega1 = P.omega1, omega2 = one;
+	P.g17[0] = eight * (omega1 - two) * (omega2 * (three * omega1 - one) - five * omega1) / (eight * (five - two * omega1) * omega1 + omega2 * (eight + omega1 * (nine * omega1 - n26)));
+	P.g17[1] = eight * (omega1 - two) * (omega1 + omega2 * (three * omega1 - seven)) / (omega2 * (n56 - n42 * omega1 + nine * omega1 * omega1) - eight * omega1);
+	P.g17[2] = n24 * (omega1 - two) * (four * omega1 * omega1 + omega1 * omega2 * (n18 - n13 * omega1) + omega2 * omega2 * (two + omega1 * (six * omega1 - n11)))
+			 / (n16 * omega1 * omega1 * (omega1 - six) - two * omega1 * omega2 * (n216 + five * omega1 * (nine * omega1 - n46))
+				+ omega2 * omega2 * (omega1 * (three * omega1 - n10) * (n15 * omega1 - n28) - n48));
+	P.g17[3] = (four * omega1 * omega1 + two * omega1 * omega2 * (omega1 - six) + omega2 * omega2 * (omega1 * (n10 - three * omega1) - four)) / (omega1 - omega2)
+			 / (omega2 * (two + three * omega1) - eight * omega1);
+	P.g17[4] = (four * omega1 * omega2 * (nine * omega1 - n16) - four * omega1 * omega1 - two * omega2 * omega2 * (two + nine * omega1 * (omega1 - two))) / three / (omega1 - omega2)
+			 / (omega2 * (two + three * omega1) - eight * omega1);
+}
 
 }  // namespace lbmx
 
@@ -231,8 +252,10 @@ LBMX_D void back_coeffs(R v, R (&c)[6])
 	c[5] = v + R(0.5);
 }
 
+// forward transform to the central moments of order <= 2 (col_cum.h:52-148 pruned; the same equations open col_clbm.h:18-117): all the
+// default builds of D3Q27_CUM and D3Q27_CLBM relax
 template <typename R>
-LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+LBMX_D void central_moments_to_second_order(const R (&f)[27], R vx, R vy, R vz, R& k000, R& k100, R& k200, R& k010, R& k110, R& k001, R& k101, R& k020, R& k002, R& k011)
 {
 	using L = D3Q27;
 	// ---- forward, z: per (x,y) column, orders 0..2 (Eq 6-8)
@@ -274,7 +297,6 @@ LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 		}
 	}
 	// ---- forward, x: alpha + beta + gamma <= 2 (Eq 12-14)
-	R k000, k100, k200, k010, k110, k001, k101, k020, k002, k011;
 	{
 		const R vv = vx * vx, m2v = R(-2) * vx;
 		{
@@ -297,6 +319,14 @@ LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 		k002 = (y02[2] + y02[0]) + y02[1];
 		k011 = (y11[2] + y11[0]) + y11[1];
 	}
+}
+
+template <typename R>
+LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	R k000, k100, k200, k010, k110, k001, k101, k020, k002, k011;
+	central_moments_to_second_order(f, vx, vy, vz, k000, k100, k200, k010, k110, k001, k101, k020, k002, k011);
 	// ---- relaxation (col_cum.h:175,223-256): second order with omega1, trace with omega2 = 1, first order sign flip
 	const R omega1 = P.omega1;
 	const R keep = R(1) - omega1;
@@ -341,6 +371,217 @@ LBMX_D void collide_cum(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 #pragma unroll
 		for (int g = 0; g < 3; g++)
 			back3<false, false, false>(x[a][0][g], x[a][1][g], x[a][2][g], cy_, yb[0][g], yb[1][g], yb[2][g]);
+#pragma unroll
+		for (int b = 0; b < 3; b++) {
+			R fm, f0, fp;
+			back3<false, false, false>(yb[b][0], yb[b][1], yb[b][2], cz_, fm, f0, fp);
+			f[L::find(a - 1, b - 1, -1)] = fm;
+			f[L::find(a - 1, b - 1, 0)] = f0;
+			f[L::find(a - 1, b - 1, 1)] = fp;
+		}
+	}
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// D3Q27_CUM built with USE_GEIER_CUM_2017 and / or USE_GEIER_CUM_ANTIALIAS (defs.h:254-255; col_cum.h:177-229, 258-276), default
+// arithmetic.  Same organisation as collide_cum: one reciprocal of rho, coefficient form of the backward chain, forward transform
+// pruned by the compiler to the moments that are read (order <= 3 with the 2017 limiter, <= 2 without); omega3..5, A and B come from
+// Phys::g17 (they depend on the viscosity alone: ~100 operations and 8 divisions per cell in the reference's form), and the limiter is
+// evaluated in R (the reference's ::fabs(double) promotes it to double for dreal = float: kept in the parity-arithmetic build).
+// --------------------------------------------------------------------------------------------------------------------
+template <typename R>
+LBMX_D void fwd3(R& lo, R& mid, R& hi, R v, R vv, R m2v)
+{
+	const R s = hi + lo, d = hi - lo;
+	const R k0 = s + mid;
+	lo = k0;
+	mid = d - v * k0;
+	hi = (s + m2v * d) + vv * k0;
+}
+
+template <bool G2017, bool ANTIALIAS, typename R>
+LBMX_D void collide_cum_switches(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R one = R(1), two = R(2), three = R(3), four = R(4), half = R(0.5), third = R(1.0 / 3.0);
+	R m[3][3][3];
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+#pragma unroll
+		for (int b = 0; b < 3; b++)
+#pragma unroll
+			for (int c = 0; c < 3; c++)
+				m[a][b][c] = f[L::find(a - 1, b - 1, c - 1)];
+	{
+		const R vv = vz * vz, m2v = R(-2) * vz;
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+#pragma unroll
+			for (int b = 0; b < 3; b++)
+				fwd3(m[a][b][0], m[a][b][1], m[a][b][2], vz, vv, m2v);
+	}
+	{
+		const R vv = vy * vy, m2v = R(-2) * vy;
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+#pragma unroll
+			for (int c = 0; c < 3; c++)
+				fwd3(m[a][0][c], m[a][1][c], m[a][2][c], vy, vv, m2v);
+	}
+	{
+		const R vv = vx * vx, m2v = R(-2) * vx;
+#pragma unroll
+		for (int b = 0; b < 3; b++)
+#pragma unroll
+			for (int c = 0; c < 3; c++)
+				fwd3(m[0][b][c], m[1][b][c], m[2][b][c], vx, vv, m2v);
+	}
+	const R omega1 = P.omega1, keep = one - omega1;
+	const R ir = one / rho;
+	const R s000 = m[0][0][0];
+	const R s100 = -m[1][0][0], s010 = -m[0][1][0], s001 = -m[0][0][1];	 // col_cum.h:341-345
+	const R s110 = keep * m[1][1][0], s101 = keep * m[1][0][1], s011 = keep * m[0][1][1];
+	R s120 = 0, s102 = 0, s210 = 0, s012 = 0, s021 = 0, s201 = 0, s111 = 0;
+	if constexpr (G2017) {	// col_cum.h:183-197, 258-276: limited rates on the sums and differences of the third-order cumulants
+		const R lam = rho * R(0.01);
+		auto relax = [&](R w, R x) -> R {
+			const R ax = x < R(0) ? -x : x;
+			return (one - (w + (one - w) * ax * ext::rcp_fast(lam + ax))) * x;
+		};
+		const R e117 = relax(P.g17[0], m[1][2][0] + m[1][0][2]), e118 = relax(P.g17[0], m[2][1][0] + m[0][1][2]), e119 = relax(P.g17[0], m[2][0][1] + m[0][2][1]);
+		const R e120 = relax(P.g17[1], m[1][2][0] - m[1][0][2]), e121 = relax(P.g17[1], m[2][1][0] - m[0][1][2]), e122 = relax(P.g17[1], m[2][0][1] - m[0][2][1]);
+		s120 = half * (e120 + e117);
+		s102 = half * (e117 - e120);
+		s210 = half * (e121 + e118);
+		s012 = half * (e118 - e121);
+		s021 = half * (e119 - e122);
+		s201 = half * (e122 + e119);
+		s111 = relax(P.g17[2], m[1][1][1]);
+	}
+	R r33 = keep * (m[2][0][0] - m[0][2][0]), r34 = keep * (m[2][0][0] - m[0][0][2]), r35 = m[0][0][0];
+	R c220 = 0, c202 = 0, c022 = 0, c211 = 0, c121 = 0, c112 = 0;
+	if constexpr (ANTIALIAS) {	// col_cum.h:215-229 and the derivative terms of Eq 33-35, 43-48 (omega2 = 1)
+		const R ho = half * omega1 * ir;
+		const R Dxu = -ho * ((two * m[2][0][0] - m[0][2][0]) - m[0][0][2]) - half * ir * (((m[2][0][0] + m[0][2][0]) + m[0][0][2]) - (rho - one));
+		const R Dyv = Dxu + three * ho * (m[2][0][0] - m[0][2][0]);
+		const R Dzw = Dxu + three * ho * (m[2][0][0] - m[0][0][2]);
+		const R xx = vx * vx * Dxu, yy = vy * vy * Dyv, zz = vz * vz * Dzw;
+		const R k1 = three * rho * (one - omega1 * half);
+		r33 = r33 - k1 * (xx - yy);
+		r34 = r34 - k1 * (xx - zz);
+		r35 = r35 - (R(1.5) * rho) * ((xx + yy) + zz);
+		if constexpr (G2017) {
+			const R w = (one / omega1 - half) * rho;
+			const R ka = R(2.0 / 3.0) * w * P.g17[3];
+			const R e43 = ka * ((Dxu - two * Dyv) + Dzw), e44 = ka * ((Dxu + Dyv) - two * Dzw), e45 = -two * ka * ((Dxu + Dyv) + Dzw);
+			c220 = third * ((e43 + e44) + e45);
+			c202 = third * (e45 - e43);
+			c022 = third * (e45 - e44);
+			const R kb = (w * P.g17[4]) * (omega1 * ir);  // -1/3 (1/omega1 - 1/2) B rho * (-3 omega1 / rho * C)
+			c211 = kb * m[0][1][1];
+			c121 = kb * m[1][0][1];
+			c112 = kb * m[1][1][0];
+		}
+	}
+	const R s200 = third * ((r33 + r34) + r35);
+	const R s020 = third * ((r34 - two * r33) + r35);
+	const R s002 = third * ((r33 - two * r34) + r35);
+	// cumulants -> central moments, Eq G2015(81)-(84), col_cum.h:312-338; post-collision cumulants of order 5 and 6 are zero
+	const R s211 = c211 + (s200 * s011 + two * s101 * s110) * ir;
+	const R s121 = c121 + (s020 * s101 + two * s110 * s011) * ir;
+	const R s112 = c112 + (s002 * s110 + two * s011 * s101) * ir;
+	const R s220 = c220 + (s020 * s200 + two * s110 * s110) * ir;
+	const R s022 = c022 + (s002 * s020 + two * s011 * s011) * ir;
+	const R s202 = c202 + (s200 * s002 + two * s101 * s101) * ir;
+	R s122 = 0, s212 = 0, s221 = 0;
+	R s222 = (((s200 * s022 + s020 * s202) + s002 * s220) + four * ((s011 * s211 + s101 * s121) + s110 * s112)) * ir
+		   - ((R(16) * s110 * s101 * s011 + four * ((s101 * s101 * s020 + s011 * s011 * s200) + s110 * s110 * s002)) + two * s200 * s020 * s002) * (ir * ir);
+	if constexpr (G2017) {
+		s122 = (((s020 * s102 + s002 * s120) + four * s011 * s111) + two * (s110 * s012 + s101 * s021)) * ir;
+		s212 = (((s002 * s210 + s200 * s012) + four * s101 * s111) + two * (s011 * s201 + s110 * s102)) * ir;
+		s221 = (((s200 * s021 + s020 * s201) + four * s110 * s111) + two * (s101 * s120 + s011 * s210)) * ir;
+		s222 = s222 + (four * s111 * s111 + two * ((s120 * s102 + s210 * s012) + s201 * s021)) * ir;
+	}
+	R cx_[6], cy_[6], cz_[6];
+	back_coeffs(vx, cx_);
+	back_coeffs(vy, cy_);
+	back_coeffs(vz, cz_);
+	R x[3][3][3];  // x[a][beta][gamma]
+	back3<false, false, false>(s000, s100, s200, cx_, x[0][0][0], x[1][0][0], x[2][0][0]);
+	back3<false, false, ! G2017>(s001, s101, s201, cx_, x[0][0][1], x[1][0][1], x[2][0][1]);
+	back3<false, ! G2017, false>(s002, s102, s202, cx_, x[0][0][2], x[1][0][2], x[2][0][2]);
+	back3<false, false, ! G2017>(s010, s110, s210, cx_, x[0][1][0], x[1][1][0], x[2][1][0]);
+	back3<false, ! G2017, false>(s011, s111, s211, cx_, x[0][1][1], x[1][1][1], x[2][1][1]);
+	back3<! G2017, false, ! G2017>(s012, s112, s212, cx_, x[0][1][2], x[1][1][2], x[2][1][2]);
+	back3<false, ! G2017, false>(s020, s120, s220, cx_, x[0][2][0], x[1][2][0], x[2][2][0]);
+	back3<! G2017, false, ! G2017>(s021, s121, s221, cx_, x[0][2][1], x[1][2][1], x[2][2][1]);
+	back3<false, ! G2017, false>(s022, s122, s222, cx_, x[0][2][2], x[1][2][2], x[2][2][2]);
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		R yb[3][3];	 // [b][gamma]
+#pragma unroll
+		for (int g = 0; g < 3; g++)
+			back3<false, false, false>(x[a][0][g], x[a][1][g], x[a][2][g], cy_, yb[0][g], yb[1][g], yb[2][g]);
+#pragma unroll
+		for (int b = 0; b < 3; b++) {
+			R fm, f0, fp;
+			back3<false, false, false>(yb[b][0], yb[b][1], yb[b][2], cz_, fm, f0, fp);
+			f[L::find(a - 1, b - 1, -1)] = fm;
+			f[L::find(a - 1, b - 1, 0)] = f0;
+			f[L::find(a - 1, b - 1, 1)] = fp;
+		}
+	}
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// D3Q27 cascaded operator, default build of the reference (d3q27/col_clbm.h:6-447 with omega2..omega10 = 1 and no antialias
+// derivatives, col_clbm.h:119-200), default arithmetic.
+//
+// With those rates the post-collision central moments of order >= 3 are constants of the cell: 0, rho/9 (k220, k202, k022) and rho/27
+// (k222); the third-order expressions (-a - b)/2 + (a - b)/2 + b of col_clbm.h:157-162 are zero up to the rounding of a third-order
+// moment.  So the forward transform stops at order 2 like the cumulant operator's (102 instead of 162 operations) and the backward chain
+// (col_clbm.h:202-300 = Eq G2015(88)-(96)) loses its zero inputs at compile time.
+// The forcing term (col_clbm.h:303-443) is the population set whose raw moments are M_abc = F . grad_u (u^a v^b w^c), a, b, c <= 2, which the
+// reference builds as 27 source moments times a dense 27 x 27 matrix (~600 operations).  Its CENTRAL moments about u are F . grad_u' of
+// (u' - u)^a (v' - v)^b (w' - w)^c at u' = u: (Fx, Fy, Fz) at first order and zero everywhere else -- so here the force is added to the three
+// first-order central moments before the backward transform, which is the same linear map applied to the same input.
+// The parity-arithmetic build keeps the reference's form (ext::collide_clbm).
+// --------------------------------------------------------------------------------------------------------------------
+template <typename R>
+LBMX_D void collide_clbm_fast(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	R k000, k100, k200, k010, k110, k001, k101, k020, k002, k011;
+	central_moments_to_second_order(f, vx, vy, vz, k000, k100, k200, k010, k110, k001, k101, k020, k002, k011);
+	const R keep = R(1) - P.omega1;
+	const R third = R(1.0 / 3.0);
+	const R d4 = keep * (k200 - k020), d5 = keep * (k200 - k002), d6 = rho;	 // col_clbm.h:147-154
+	const R s200 = third * ((d4 + d5) + d6);
+	const R s020 = third * ((d5 - R(2) * d4) + d6);
+	const R s002 = third * ((d4 - R(2) * d5) + d6);
+	const R s110 = keep * k110, s101 = keep * k101, s011 = keep * k011;	 // col_clbm.h:196-198
+	const R s100 = k100 + P.fx, s010 = k010 + P.fy, s001 = k001 + P.fz;	 // col_clbm.h:191-193 and the forcing term
+	const R s22 = rho * R(1.0 / 9.0), s222 = rho * R(1.0 / 27.0);			 // col_clbm.h:172-186
+	R cx_[6], cy_[6], cz_[6];
+	back_coeffs(vx, cx_);
+	back_coeffs(vy, cy_);
+	back_coeffs(vz, cz_);
+	// ---- backward, x: x[a][beta][gamma]; the rows (beta, gamma) = (1,2) and (2,1) are zero
+	R x[3][3][3];
+	back3<false, false, false>(k000, s100, s200, cx_, x[0][0][0], x[1][0][0], x[2][0][0]);
+	back3<false, false, true>(s001, s101, R(0), cx_, x[0][0][1], x[1][0][1], x[2][0][1]);
+	back3<false, true, false>(s002, R(0), s22, cx_, x[0][0][2], x[1][0][2], x[2][0][2]);
+	back3<false, false, true>(s010, s110, R(0), cx_, x[0][1][0], x[1][1][0], x[2][1][0]);
+	back3<false, true, true>(s011, R(0), R(0), cx_, x[0][1][1], x[1][1][1], x[2][1][1]);
+	back3<false, true, false>(s020, R(0), s22, cx_, x[0][2][0], x[1][2][0], x[2][2][0]);
+	back3<false, true, false>(s22, R(0), s222, cx_, x[0][2][2], x[1][2][2], x[2][2][2]);
+	// ---- backward, y then z
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		R yb[3][3];	 // [b][gamma]
+		back3<false, false, false>(x[a][0][0], x[a][1][0], x[a][2][0], cy_, yb[0][0], yb[1][0], yb[2][0]);
+		back3<false, false, true>(x[a][0][1], x[a][1][1], R(0), cy_, yb[0][1], yb[1][1], yb[2][1]);
+		back3<false, true, false>(x[a][0][2], R(0), x[a][2][2], cy_, yb[0][2], yb[1][2], yb[2][2]);
 #pragma unroll
 		for (int b = 0; b < 3; b++) {
 			R fm, f0, fp;
@@ -675,24 +916,43 @@ LBMX_D void equilibrium_any(R (&feq)[Q], int eqkind, R rho, R vx, R vy, R vz)
 
 // --------------------------------------------------------------------------------------------------------------------
 // operator tags: what COLL means for a kernel instantiation
+// HW_RCP: fp32 KBC weights from the hardware reciprocal (ext::rcp_fast); the A-B bulk kernel turns it off (see there)
 // --------------------------------------------------------------------------------------------------------------------
 enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 /* D2Q9_CLBM or D3Q27_CLBM, by lattice */, K_SRT_MF = 5, K_CUM_2017 = 10, K_CUM_AALIAS = 11, K_CUM_2017_AALIAS = 12 /* D3Q27_CUM built with the switches of defs.h:254-255 */,
 						K_KBC_N1 = 13, K_KBC_N2, K_KBC_N3, K_KBC_N4, K_KBC_C1, K_KBC_C2, K_KBC_C3, K_KBC_C4,
 						K_BGK_GAL = 21 /* D3Q27_BGK built with USE_GALILEAN_CORRECTION (defs.h:253) */ };
 
-template <int KIND, typename R>
+template <int KIND, bool HW_RCP = true, typename R>
 LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
-	if constexpr (KIND == K_CLBM)
-		ext::collide_clbm<! kStrict>(f, P, rho, vx, vy, vz);
-	else if constexpr (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
-		ext::collide_kbc<(KIND >= K_KBC_C1), ((KIND - K_KBC_N1) % 4 == 1 || (KIND - K_KBC_N1) % 4 == 3), ((KIND - K_KBC_N1) % 4 >= 2), kStrict>(f, P, rho, vx, vy, vz);
-	else if constexpr (KIND == K_CUM_2017)
-		strict::collide_cum<true, false>(f, P, rho, vx, vy, vz);
-	else if constexpr (KIND == K_CUM_AALIAS)
-		strict::collide_cum<false, true>(f, P, rho, vx, vy, vz);
-	else if constexpr (KIND == K_CUM_2017_AALIAS)
-		strict::collide_cum<true, true>(f, P, rho, vx, vy, vz);
+	if constexpr (KIND == K_CLBM) {
+		if constexpr (kStrict)
+			ext::collide_clbm<false>(f, P, rho, vx, vy, vz);
+		else
+			collide_clbm_fast(f, P, rho, vx, vy, vz);
+	}
+	else if constexpr (KIND >= K_KBC_N1 && KIND <= K_KBC_C4) {
+		constexpr bool central = KIND >= K_KBC_C1, use_t = (KIND - K_KBC_N1) % 4 == 1 || (KIND - K_KBC_N1) % 4 == 3, use_q = (KIND - K_KBC_N1) % 4 >= 2;
+#ifdef LBMX_KBC_REFERENCE_ORDER	 // the reference's statement order in default arithmetic (tools/kbench comparison)
+		ext::collide_kbc<central, use_t, use_q, kStrict>(f, P, rho, vx, vy, vz);
+#else
+		if constexpr (kStrict)
+			ext::collide_kbc<central, use_t, use_q, true>(f, P, rho, vx, vy, vz);
+		else
+			ext::collide_kbc_fast<central, use_t, use_q, HW_RCP>(f, P, rho, vx, vy, vz);
+#endif
+	}
+	else if constexpr (KIND == K_CUM_2017 || KIND == K_CUM_AALIAS || KIND == K_CUM_2017_AALIAS) {
+		constexpr bool g2017 = KIND != K_CUM_AALIAS, aalias = KIND != K_CUM_2017;
+#ifdef LBMX_CUM_REFERENCE_ORDER	 // the reference's statement order in default arithmetic (tools/kbench comparison)
+		strict::collide_cum<g2017, aalias>(f, P, rho, vx, vy, vz);
+#else
+		if constexpr (kStrict)
+			strict::collide_cum<g2017, aalias>(f, P, rho, vx, vy, vz);
+		else
+			collide_cum_switches<g2017, aalias>(f, P, rho, vx, vy, vz);
+#endif
+	}
 	else if constexpr (KIND == K_SRT_MF) {
 		R feq[27];
 		equilibrium(feq, eqkind, rho, vx, vy, vz);
@@ -724,7 +984,7 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 	else
 		collide_mrt(f, P, rho, vx, vy, vz);
 }
-template <int KIND, typename R>
+template <int KIND, bool HW_RCP = true, typename R>
 LBMX_D void collide(R (&f)[19], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
 	if constexpr (KIND == K_SRT)
@@ -732,7 +992,7 @@ LBMX_D void collide(R (&f)[19], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 	else
 		collide_mrt(f, P, rho, vx, vy, vz);
 }
-template <int KIND, typename R>
+template <int KIND, bool HW_RCP = true, typename R>
 LBMX_D void collide(R (&f)[9], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
 	if constexpr (kStrict) {

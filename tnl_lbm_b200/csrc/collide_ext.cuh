@@ -569,5 +569,189 @@ LBMX_D void collide_kbc(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 	});
 }
 
+// 1 / x for weights and scale factors of the default-arithmetic operators: fp32 on the device takes the hardware approximation (MUFU.RCP,
+// 1 ulp) instead of the IEEE sequence (~8 instructions with a slow path; the fp32 KBC kernels are bound by instruction issue).
+// Measured on the KBC_N4 fp32 kernels (profiles/kbench_r2_kbc_variants.txt): A-A even 5050 -> 5209 GB/s, odd 4138 -> 4465, but A-B
+// 4841 -> 3741 (the same source, only this function differs) -- so the A-B bulk kernel keeps the IEEE division (HW = false).
+template <bool HW = true, typename R>
+LBMX_D R rcp_fast(R x)
+{
+#if defined(__CUDA_ARCH__) && ! defined(LBMX_NO_RCP_FAST)
+	if constexpr (HW && sizeof(R) == 4)
+		return __fdividef(R(1), x);
+#endif
+	return R(1) / x;
+}
+
+// The same eight models in default arithmetic, organised for the fp64 / fp32 pipes instead of the reference's statement order (the form
+// above needs ~1080 floating-point instructions per cell, which bounds the fp64 kernels on the FP64 pipe before HBM does):
+//   * the 13 raw moments come from column sums (z, then y, then x: 72 additions instead of 190);
+//   * pass 1 leaves delta-h in the place of f, so pass 2 is  f' = (1 - beta gamma) dh + (1 - 2 beta) ds + (1 + (1 - beta) S) feq
+//     (the reference's  f - beta (2 ds + gamma dh) + (1 - beta) S feq  with f = dh + ds + feq substituted);
+//   * feq_q and 1/feq_q are one multiplication each: the (x,y) factor pairs are formed once per three populations;
+//   * (1 - beta) S_q = sx[cx] + sy[cy] + sz[cz] with three values per axis (S is linear in the lattice velocity, col_bgk.h:62-88).
+// Same quantities as collide_kbc<..., EXACT = false>, agreement with the reference to rounding.
+template <bool CENTRAL, bool USE_T, bool USE_Q, bool HW_RCP = true, typename R, typename PHYS>
+LBMX_D void collide_kbc_fast(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R one = R(1), two = R(2), three = R(3), six = R(6), half = R(0.5), third = R(1.0 / 3.0);
+	const R v[3] = {vx, vy, vz};
+	R g[3][3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R z = third - one + v[a] * v[a];
+		const R p = -half * (z + one + v[a]);
+		g[a][1] = z;
+		g[a][2] = p;
+		g[a][0] = p + v[a];
+	}
+	// ---- raw moments (col_kbc_n.h:351-386) from column sums
+	R T, Nxz, Nyz, Pxy, Pxz, Pyz, Qxxy, Qxxz, Qxyy, Qyyz, Qxzz, Qyzz, Qxyz;
+	{
+		R y00[3], y10[3], y20[3], y01[3], y11[3], y21[3], y02[3], y12[3];
+#pragma unroll
+		for (int a = 0; a < 3; a++) {
+			R z0[3], z1[3], z2[3];
+#pragma unroll
+			for (int b = 0; b < 3; b++) {
+				const R fm = f[L::find(a - 1, b - 1, -1)], f0 = f[L::find(a - 1, b - 1, 0)], fp = f[L::find(a - 1, b - 1, 1)];
+				z2[b] = fp + fm;
+				z1[b] = fp - fm;
+				z0[b] = z2[b] + f0;
+			}
+			y20[a] = z0[2] + z0[0];
+			y10[a] = z0[2] - z0[0];
+			y00[a] = y20[a] + z0[1];
+			y21[a] = z1[2] + z1[0];
+			y11[a] = z1[2] - z1[0];
+			y01[a] = y21[a] + z1[1];
+			y02[a] = (z2[2] + z2[0]) + z2[1];
+			y12[a] = z2[2] - z2[0];
+		}
+		const R m200 = y00[2] + y00[0], m020 = (y20[2] + y20[0]) + y20[1], m002 = (y02[2] + y02[0]) + y02[1];
+		T = (m200 + m020) + m002;
+		Nxz = m200 - m002;
+		Nyz = m020 - m002;
+		Pxy = y10[2] - y10[0];
+		Pxz = y01[2] - y01[0];
+		Pyz = (y11[2] + y11[0]) + y11[1];
+		Qxyz = y11[2] - y11[0];
+		Qxxz = y01[2] + y01[0];
+		Qxzz = y02[2] - y02[0];
+		Qxxy = y10[2] + y10[0];
+		Qxyy = y20[2] - y20[0];
+		Qyyz = (y21[2] + y21[0]) + y21[1];
+		Qyzz = (y12[2] + y12[0]) + y12[1];
+	}
+	if constexpr (! CENTRAL) {	// minus the equilibrium moments (col_kbc_n.h:28-54): the shear tensors are linear in them
+		const R xx = vx * vx, yy = vy * vy, zz = vz * vz;
+		const R rx = rho * vx, ry = rho * vy, rz = rho * vz;
+		T -= rho * (((one + xx) + yy) + zz);
+		Nxz -= rho * (xx - zz);
+		Nyz -= rho * (yy - zz);
+		Pxy -= rx * vy;
+		Pxz -= rx * vz;
+		Pyz -= ry * vz;
+		Qxxy -= ry * (third + xx);
+		Qxxz -= rz * (third + xx);
+		Qxyy -= rx * (third + yy);
+		Qyyz -= rz * (third + yy);
+		Qxzz -= rx * (third + zz);
+		Qyzz -= ry * (third + zz);
+		Qxyz -= rx * vy * vz;
+	}
+	else {	// col_kbc_c.h:56-83: central moments; their equilibria are 0 except the trace (rho)
+		T = T - rho * (vx * vx + vy * vy + vz * vz);
+		Nxz = Nxz + rho * (vz * vz - vx * vx);
+		Nyz = Nyz + rho * (vz * vz - vy * vy);
+		Pxy = Pxy - rho * vx * vy;
+		Pxz = Pxz - rho * vx * vz;
+		Pyz = Pyz - rho * vy * vz;
+		const R cxx = (three * vx * vx + two * Nxz - Nyz) + T, cyy = (three * vy * vy + two * Nyz - Nxz) + T, czz = (three * vz * vz - Nyz - Nxz) + T;
+		Qxxy = Qxxy - third * (six * vx * Pxy + vy * cxx);
+		Qxxz = Qxxz - third * (six * vx * Pxz + vz * cxx);
+		Qxyy = Qxyy - third * (six * vy * Pxy + vx * cyy);
+		Qyyz = Qyyz - third * (six * vy * Pyz + vz * cyy);
+		Qxzz = Qxzz - third * (six * vz * Pxz + vx * czz);
+		Qyzz = Qyzz - third * (six * vz * Pyz + vy * czz);
+		Qxyz = Qxyz - vx * Pyz - vy * Pxz - vz * Pxy - vx * vy * vz;
+		T -= rho;
+	}
+	auto ds_of = [&](auto qc) -> R {
+		constexpr int q = qc;
+		constexpr int n = (L::cx(q) != 0) + (L::cy(q) != 0) + (L::cz(q) != 0);
+		R acc = R(0);
+		if constexpr (n == 1 || n == 2)
+			acc = kbc_tensor_d<false, q>(Nxz, Nyz, Pxy, Pxz, Pyz);
+		if constexpr (USE_T && n <= 1)
+			acc = acc + (n == 0 ? -T : T * R(1.0 / 6.0));
+		if constexpr (USE_Q && n >= 1)
+			acc = acc + kbc_tensor_q<false, q>(Qxxy, Qxxz, Qxyy, Qyyz, Qxzz, Qyzz, Qxyz);
+		return acc;
+	};
+	const R beta = (one / (two * P.nu / third + one));
+	const R irho = rcp_fast<HW_RCP>(rho);
+	R ig[3][3], nrg0[3], nig0[3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+#pragma unroll
+		for (int c = 0; c < 3; c++)
+			ig[a][c] = rcp_fast<HW_RCP>(g[a][c]);
+		nrg0[a] = -rho * g[0][a];
+		nig0[a] = -irho * ig[0][a];
+	}
+	// ---- pass 1: <Ds|Dh> and <Dh|Dh> (weights 1/feq); delta-h replaces f
+	R sd = R(0), hh = R(0);
+	static_for<9>([&](auto abc) {
+		constexpr int a = abc / 3, b = abc % 3;
+		const R gxy = nrg0[a] * g[1][b], igxy = nig0[a] * ig[1][b];
+		static_for<3>([&](auto cc) {
+			constexpr int c = cc;
+			constexpr int q = L::find(a - 1, b - 1, c - 1);
+			const R fe = gxy * g[2][c], ds = ds_of(std::integral_constant<int, q>{});
+			const R dh = f[q] - fe - ds;
+			const R t = dh * (igxy * ig[2][c]);
+			sd = sd + ds * t;
+			hh = hh + dh * t;
+			f[q] = dh;
+		});
+	});
+	const R gamma = (one / beta - (two - one / beta) * sd / hh);
+#if defined(__CUDA_ARCH__) && ! defined(LBMX_KBC_NO_PASS_BARRIER)
+	// keep the compiler from carrying the 27 delta-s / feq values of the first pass over to the second (common subexpressions): the point of
+	// recomputing them is that they do NOT occupy registers in between
+	if constexpr (sizeof(R) == 8)
+		asm volatile("" : "+d"(T), "+d"(Nxz), "+d"(Nyz), "+d"(Pxy), "+d"(Pxz), "+d"(Pyz), "+d"(rho));
+	else
+		asm volatile("" : "+f"(T), "+f"(Nxz), "+f"(Nyz), "+f"(Pxy), "+f"(Pxz), "+f"(Pyz), "+f"(rho));
+#endif
+	// ---- pass 2
+	const R c1 = one - beta * gamma, c2 = one - two * beta;
+	const R ks = three * (one - beta) * irho;
+	const R F[3] = {P.fx, P.fy, P.fz};
+	R sv[3][3];	 // (1 - beta) S_q = sv[0][cx+1] + sv[1][cy+1] + sv[2][cz+1]
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R kf = ks * F[a];
+		sv[a][1] = -v[a] * kf;
+		sv[a][0] = sv[a][1] - kf;
+		sv[a][2] = sv[a][1] + kf;
+	}
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+		nrg0[a] = -rho * g[0][a];
+	static_for<9>([&](auto abc) {
+		constexpr int a = abc / 3, b = abc % 3;
+		const R gxy = nrg0[a] * g[1][b], exy = (one + sv[0][a]) + sv[1][b];
+		static_for<3>([&](auto cc) {
+			constexpr int c = cc;
+			constexpr int q = L::find(a - 1, b - 1, c - 1);
+			const R fe = gxy * g[2][c], ds = ds_of(std::integral_constant<int, q>{});
+			f[q] = c1 * f[q] + (c2 * ds + (exy + sv[2][c]) * fe);
+		});
+	});
+}
+
 }  // namespace ext
 }  // namespace lbmx

@@ -331,7 +331,7 @@ KParams<R> make_params(const lbmx_engine* e)
 	const bool vm = e->d.macro == LBMX_MACRO_VOID;
 	// MACRO_Void::copyQuantities is empty (d3q27/macro.h:174-188): the KernelStruct keeps lbmViscosity = 1, zero force
 	p.phys.nu = vm ? R(1) : (R) e->prm.lbmViscosity;
-	p.phys.omega1 = R(1) / (R(3) * p.phys.nu + R(0.5));	 // IEEE division in precision R: the same bits the kernels used to compute per cell
+	set_rates(p.phys);	// omega1 (IEEE division in precision R: the same bits the kernels used to compute per cell) and the 2017 cumulant rates
 	p.phys.fx = vm ? R(0) : (R) e->prm.fx;
 	p.phys.fy = vm ? R(0) : (R) e->prm.fy;
 	p.phys.fz = (vm || e->d.lattice == LBMX_D2Q9) ? R(0) : (R) e->prm.fz;

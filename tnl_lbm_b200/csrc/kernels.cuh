@@ -24,17 +24,21 @@
 #ifndef LBMX_BULK_MINBLOCKS
 	#define LBMX_BULK_MINBLOCKS 4  // __launch_bounds__ second argument (register cap = 65536 / (BLOCK * MINBLOCKS) = 128: 16 warps per SM)
 #endif
-// KBC kernels: 27 populations + 13 moments + 9 equilibrium factors and their reciprocals live.  fp32 fits 128 registers (4 CTAs per SM:
-// +9..21 % over 3); fp64 takes 168 with a few spilled doubles (3 CTAs: +11 % on the even and A-B kernels, -3 % on the odd one, which
-// stays at 2) -- tools/kbench, profiles/kbench_r2_kbc.txt
+// KBC kernels (collide_kbc_fast: delta-h in place of f, 13 moments, 9 equilibrium factors and their reciprocals live).  fp64 takes 168
+// registers = 3 CTAs per SM in all three kernels (the odd one spills 40 bytes there and still gains 17 % over 2 CTAs; 128 registers spill
+// ~450 bytes and lose 16-30 %); fp32: 128 registers / 4 CTAs for the A-A kernels, 96 / 5 CTAs for A-B (+14 %)
+// -- tools/kbench, profiles/kbench_r2_kbc_clbm_reorganised.txt (profiles/kbench_r2_kbc.txt: the reference statement order)
 #ifndef LBMX_KBC_MINBLOCKS_F64
 	#define LBMX_KBC_MINBLOCKS_F64 3
 #endif
 #ifndef LBMX_KBC_MINBLOCKS_F64_ODD
-	#define LBMX_KBC_MINBLOCKS_F64_ODD 2
+	#define LBMX_KBC_MINBLOCKS_F64_ODD 3
 #endif
 #ifndef LBMX_KBC_MINBLOCKS_F32
 	#define LBMX_KBC_MINBLOCKS_F32 4
+#endif
+#ifndef LBMX_KBC_MINBLOCKS_F32_AB
+	#define LBMX_KBC_MINBLOCKS_F32_AB 5
 #endif
 #ifndef LBMX_BULK_MINBLOCKS_AB
 	#define LBMX_BULK_MINBLOCKS_AB 5  // the A-B kernel fits 96 registers without spilling and likes the extra occupancy (kbench: 6.68 vs 6.33 TB/s)
@@ -464,12 +468,13 @@ __device__ __noinline__ void bulk_cold_cell(const KParams<R>& p, int x, int yz, 
 
 // resident CTAs per SM the register allocation is sized for: the cumulant / MRT_LES kernels fit 128 (A-A) and 96 (A-B)
 // registers without spilling; fp64 SRT and BGK keep f[27], feq[27] and the source terms live and get 170
-template <int KIND, typename R, int MODE>
+template <int KIND, typename R, int MODE, int L_Q = 27>
 constexpr int bulk_minblocks()
 {
 	if (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
-		return sizeof(R) == 8 ? (MODE == S_AA_ODD ? LBMX_KBC_MINBLOCKS_F64_ODD : LBMX_KBC_MINBLOCKS_F64) : LBMX_KBC_MINBLOCKS_F32;
-	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_BGK_GAL || KIND == K_SRT_MF || KIND == K_CLBM))
+		return sizeof(R) == 8 ? (MODE == S_AA_ODD ? LBMX_KBC_MINBLOCKS_F64_ODD : LBMX_KBC_MINBLOCKS_F64) : (MODE == S_AB ? LBMX_KBC_MINBLOCKS_F32_AB : LBMX_KBC_MINBLOCKS_F32);
+	// (the default-arithmetic cascaded operator is as light as the cumulant one; its parity-arithmetic form keeps 27 moments of each kind live)
+	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_BGK_GAL || KIND == K_SRT_MF || (KIND == K_CLBM && (kStrict || L_Q != 27))))
 		return LBMX_BULK_MINBLOCKS < 3 ? LBMX_BULK_MINBLOCKS : 3;
 	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;
 }
@@ -494,7 +499,7 @@ constexpr int bulk_cpt()
 
 // ARITH (= LBMX_STRICT of the object file) only makes the kernel symbols of the fast and the parity-arithmetic builds distinct
 template <typename L, int KIND, typename R, int MODE, int ARITH = LBMX_STRICT>
-__global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>()) k_bulk(const LBMX_GRID_CONSTANT KParams<R> p)
+__global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE, L::Q>()) k_bulk(const LBMX_GRID_CONSTANT KParams<R> p)
 {
 	constexpr int CPT = bulk_cpt<L, R, MODE>();
 	const int x = p.x_begin + blockIdx.y;
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 			vx = vy = vz = R(0);
 #else
 			density_velocity(f[k], p.phys, rho, vx, vy, vz);
-			collide<KIND>(f[k], p.phys, p.eq, rho, vx, vy, vz);
+			collide<KIND, MODE != S_AB>(f[k], p.phys, p.eq, rho, vx, vy, vz);
 #endif
 		}
 		else {
@@ -582,6 +587,10 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE>
 				vx = vy = vz = R(0);
 			}
 		}
+#ifdef LBMX_EXP_ODD_RECOMPUTE_OFFSETS  // tools/kbench experiment: the store addresses of the A-A odd step are formed again from the six deltas instead of living through the collision
+		if constexpr (MODE == S_AA_ODD)
+			asm volatile("" : "+r"(d[k].xp), "+r"(d[k].xm), "+r"(d[k].yp), "+r"(d[k].ym), "+r"(d[k].zp), "+r"(d[k].zm), "+r"(c[k]));
+#endif
 		stream_out<L, MODE, true>(p, f[k], c[k], d[k]);
 		output_macro<L>(p, c[k], rho, vx, vy, vz);
 	}

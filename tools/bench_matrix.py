@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from tnl_lbm_b200 import binding as B  # noqa: E402
 
 NAMES = {B.CUM: "CUM", B.SRT: "SRT", B.BGK: "BGK", B.MRT_LES: "MRT_LES", B.CLBM: "CLBM", B.SRT_MODIF_FORCE: "SRT_MODIF_FORCE", B.KBC_N1: "KBC_N1", B.KBC_N4: "KBC_N4", B.KBC_C4: "KBC_C4",
-         B.CUM_2017: "CUM (USE_GEIER_CUM_2017)", B.CUM_2017_ANTIALIAS: "CUM (2017 + ANTIALIAS)"}
+         B.CUM_2017: "CUM (USE_GEIER_CUM_2017)", B.CUM_ANTIALIAS: "CUM (ANTIALIAS)", B.CUM_2017_ANTIALIAS: "CUM (2017 + ANTIALIAS)"}
 
 
 def run(lattice, coll, eq, prec, streaming, shape, steps, map_kind="periodic", macro=B.MACRO_DEFAULT, flags=0):
@@ -48,7 +48,8 @@ def run(lattice, coll, eq, prec, streaming, shape, steps, map_kind="periodic", m
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "bench_matrix_r1.md"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "bench_matrix_r2.md"))
+    ap.add_argument("--round", default="2")
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--only", default="", help="run only the rows whose name contains this string (e.g. 'ext' = the rows added after the first table)")
     a = ap.parse_args()
@@ -80,9 +81,10 @@ def main():
         for prec in (B.F64, B.F32):
             for st in (B.AA, B.AB):
                 cfgs.append(("D3Q27 ext", B.D3Q27, coll, eq, prec, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, 0))
-    for coll, eq in ((B.KBC_N1, B.EQ_STD), (B.KBC_N4, B.EQ_ENTROPIC), (B.KBC_C4, B.EQ_ENTROPIC), (B.CUM_2017, B.EQ_INV_CUM), (B.CUM_2017_ANTIALIAS, B.EQ_INV_CUM)):
+    for coll, eq in ((B.KBC_N1, B.EQ_STD), (B.KBC_N4, B.EQ_ENTROPIC), (B.KBC_C4, B.EQ_ENTROPIC), (B.CUM_2017, B.EQ_INV_CUM), (B.CUM_ANTIALIAS, B.EQ_INV_CUM), (B.CUM_2017_ANTIALIAS, B.EQ_INV_CUM)):
         for prec in (B.F64, B.F32):
-            cfgs.append(("D3Q27 ext2", B.D3Q27, coll, eq, prec, B.AA, (384, 384, 384), "periodic", B.MACRO_DEFAULT, 0))
+            for st in (B.AA, B.AB):
+                cfgs.append(("D3Q27 ext2", B.D3Q27, coll, eq, prec, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, 0))
     for st in (B.AA, B.AB):
         cfgs.append(("D3Q27 ext MACRO_Mean (+13 RMW fields: 640 B per update)", B.D3Q27, B.CUM, B.EQ_INV_CUM, B.F64, st, (320, 320, 320), "periodic", B.MACRO_MEAN, 0))
         cfgs.append(("D3Q27 ext parity arithmetic", B.D3Q27, B.CUM, B.EQ_INV_CUM, B.F64, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, B.FLAG_STRICT_ARITH))
@@ -95,7 +97,7 @@ def main():
         print(row, flush=True)
         rows.append(row)
     with open(a.out, "w") as f:
-        f.write("# Kernel-family throughput on one B200 (round 1)\n\n`python tools/bench_matrix.py` -- periodic boxes, device-resident, "
+        f.write(f"# Kernel-family throughput on one B200 (round {a.round})\n\n`python tools/bench_matrix.py` -- periodic boxes, device-resident, "
                 f"{a.steps} timed steps after 6 warm-up, CUDA events on the engine stream.\nB = algorithmic bytes per update (Q x 2 x sizeof real); "
                 f"GB/s = MLUPS x B; % of the measured copy bandwidth {peak:.0f} GB/s (MEASURED_PEAKS.json).\n\n"
                 "| lattice | operator | real | streaming | lattice size | B | MLUPS | GB/s | of measured peak | regs (A-A even / A-B) |\n|---|---|---|---|---|---|---|---|---|---|\n")

@@ -89,7 +89,7 @@ int main(int argc, char** argv)
 	CK(cudaMemcpy(b, a, sizeof(R) * L::Q * XYZ, cudaMemcpyDeviceToDevice));
 	KParams<R> p{};
 	p.cur = a; p.out = b; p.macro = mac; p.map = map; p.XYZ = XYZ; p.X = p.Y = S; p.Z = SZ; p.ox = 0; p.YZ = S * SZ; p.x_begin = 0;
-	p.wrap = 1; p.eq = L::Q == 27 ? 1 : 0; p.out_mode = macro == 0 ? OUT_NONE : (macro == 1 ? OUT_DEFAULT : OUT_MEAN); p.phys.nu = R(1e-3); p.phys.omega1 = R(1) / (R(3) * p.phys.nu + R(0.5));
+	p.wrap = 1; p.eq = L::Q == 27 ? 1 : 0; p.out_mode = macro == 0 ? OUT_NONE : (macro == 1 ? OUT_DEFAULT : OUT_MEAN); p.phys.nu = R(1e-3); set_rates(p.phys);
 	{ unsigned Lg = 0; while ((1u << Lg) < (unsigned) S) Lg++; p.ydiv_mul = (unsigned) ((((unsigned long long) 1 << (31 + Lg)) + S - 1) / S); p.ydiv_shift = Lg - 1; }
 	auto set_bases = [&](bool aa) { for (int q = 0; q < L::Q; q++) { p.rd[q] = p.cur + (size_t) q * XYZ; p.wr[q] = (aa ? p.cur : p.out) + (size_t) q * XYZ; } };
 	set_bases(true); p.phys.fx = R(1e-6); p.phys.fy = p.phys.fz = 0;
