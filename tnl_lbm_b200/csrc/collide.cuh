@@ -724,16 +724,18 @@ LBMX_D void collide_srt(R (&f)[9], const Phys<R>& P, int, R rho, R vx, R vy, R)
 	const R itau = P.omega1;
 	const R pre = R(1) - R(0.5) * itau;
 	const R fx = P.fx, fy = P.fy;
+	// (d2q9/col_srt.h:21-29 divides by 9 and 36 per population: in default arithmetic the weights are constants)
+	const R w0 = pre * R(4.0 / 9.0), w1 = pre * R(1.0 / 9.0), w2 = pre * R(1.0 / 36.0);
 	R F[9];
-	F[L::find(0, 0)] = pre * R(4) / R(9) * (R(3) * (-vx * fx - vy * fy));
-	F[L::find(1, 0)] = pre / R(9) * (R(3) * ((R(1) - vx) * fx - vy * fy) + R(9) * vx * fx);
-	F[L::find(-1, 0)] = pre / R(9) * (R(3) * ((R(-1) - vx) * fx - vy * fy) + R(9) * vx * fx);
-	F[L::find(0, 1)] = pre / R(9) * (R(3) * (-vx * fx + (R(1) - vy) * fy) + R(9) * vy * fy);
-	F[L::find(0, -1)] = pre / R(9) * (R(3) * (-vx * fx + (R(-1) - vy) * fy) + R(9) * vy * fy);
-	F[L::find(1, 1)] = pre / R(36) * (R(3) * ((R(1) - vx) * fx + (R(1) - vy) * fy) + R(9) * (vx + vy) * (fx + fy));
-	F[L::find(-1, -1)] = pre / R(36) * (R(3) * ((R(-1) - vx) * fx + (R(-1) - vy) * fy) + R(9) * (vx + vy) * (fx + fy));
-	F[L::find(1, -1)] = pre / R(36) * (R(3) * ((R(1) - vx) * fx + (R(-1) - vy) * fy) + R(9) * (vx - vy) * (fx - fy));
-	F[L::find(-1, 1)] = pre / R(36) * (R(3) * ((R(-1) - vx) * fx + (R(1) - vy) * fy) + R(9) * (vx - vy) * (fx - fy));
+	F[L::find(0, 0)] = w0 * (R(3) * (-vx * fx - vy * fy));
+	F[L::find(1, 0)] = w1 * (R(3) * ((R(1) - vx) * fx - vy * fy) + R(9) * vx * fx);
+	F[L::find(-1, 0)] = w1 * (R(3) * ((R(-1) - vx) * fx - vy * fy) + R(9) * vx * fx);
+	F[L::find(0, 1)] = w1 * (R(3) * (-vx * fx + (R(1) - vy) * fy) + R(9) * vy * fy);
+	F[L::find(0, -1)] = w1 * (R(3) * (-vx * fx + (R(-1) - vy) * fy) + R(9) * vy * fy);
+	F[L::find(1, 1)] = w2 * (R(3) * ((R(1) - vx) * fx + (R(1) - vy) * fy) + R(9) * (vx + vy) * (fx + fy));
+	F[L::find(-1, -1)] = w2 * (R(3) * ((R(-1) - vx) * fx + (R(-1) - vy) * fy) + R(9) * (vx + vy) * (fx + fy));
+	F[L::find(1, -1)] = w2 * (R(3) * ((R(1) - vx) * fx + (R(-1) - vy) * fy) + R(9) * (vx - vy) * (fx - fy));
+	F[L::find(-1, 1)] = w2 * (R(3) * ((R(-1) - vx) * fx + (R(1) - vy) * fy) + R(9) * (vx - vy) * (fx - fy));
 	R feq[9];
 	equilibrium(feq, 0, rho, vx, vy, R(0));
 	static_for<9>([&](auto qc) {

@@ -466,6 +466,15 @@ __device__ __noinline__ void bulk_cold_cell(const KParams<R>& p, int x, int yz, 
 	output_macro_impl<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, c, R(1), R(0), R(0), R(0));
 }
 
+// A-B bulk kernel: do obstacle / inert lanes store together with their warp (phase 2)?  Everywhere (LBMX_AB_WHOLE_SECTORS) except the D3Q19
+// SRT fp64 kernel (156 registers, 3 CTAs per SM), whose periodic-box rate the extra path costs 16 % (5 129 -> 6 091 GB/s without it,
+// profiles/kbench_r2_q9_q19srt_features.txt): there those lanes take the cold path of phase 3 like under A-A.
+template <typename L, int KIND, typename R>
+constexpr bool ab_whole_sectors()
+{
+	return LBMX_AB_WHOLE_SECTORS && ! (L::Q == 19 && KIND == K_SRT && sizeof(R) == 8);
+}
+
 // resident CTAs per SM the register allocation is sized for: the cumulant / MRT_LES kernels fit 128 (A-A) and 96 (A-B)
 // registers without spilling; fp64 SRT and BGK keep f[27], feq[27] and the source terms live and get 170
 template <int KIND, typename R, int MODE, int L_Q = 27>
@@ -569,7 +578,7 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE,
 #endif
 		}
 		else {
-			if constexpr (MODE != S_AB || ! LBMX_AB_WHOLE_SECTORS)
+			if constexpr (MODE != S_AB || ! ab_whole_sectors<L, KIND, R>())
 				continue;  // A-A: phase 3
 			else {
 				// A-B writes the OTHER array: a 32-byte sector that a warp's store covers only in part is not in L2 and costs DRAM a
@@ -597,7 +606,7 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE,
 	// ---- phase 3 (cold; A-A, where stores land on sectors the warp has just read): obstacle cells away from the faces, inert cells
 #pragma unroll
 	for (int k = 0; k < CPT; k++) {
-		if (MODE == S_AB && LBMX_AB_WHOLE_SECTORS)
+		if (MODE == S_AB && ab_whole_sectors<L, KIND, R>())
 			break;
 		if (m[k] != L::WALL && m[k] != L::NOTHING)
 			continue;
