@@ -60,7 +60,8 @@ enum lbmx_coll {
 	LBMX_COLL_KBC_C2 = 18,
 	LBMX_COLL_KBC_C3 = 19,
 	LBMX_COLL_KBC_C4 = 20,
-	LBMX_COLL_BGK_GALILEAN = 21		   /* D3Q27_BGK built with -DUSE_GALILEAN_CORRECTION (defs.h:253; col_bgk.h:20-45) */
+	LBMX_COLL_BGK_GALILEAN = 21,	   /* D3Q27_BGK built with -DUSE_GALILEAN_CORRECTION (defs.h:253; col_bgk.h:20-45) */
+	LBMX_COLL_CUM_HP_RHO = 22		   /* D3Q27_CUM built with -DUSE_HIGH_PRECISION_RHO (defs.h:252; d3q27/common.h:19-29: the density is a Kahan sum over the 27 populations) */
 };
 enum lbmx_eq {
 	LBMX_EQ_STD = 0,	  /* D3Q27_EQ eq.h:8-130, D2Q9_EQ */

@@ -76,6 +76,7 @@ struct Cell
 	R fx = 0, fy = 0, fz = 0;
 	R vx = 0, vy = 0, vz = 0;
 	R rho = 1, nu = 1;	// defaults matter: MACRO_Void never overwrites them (d3q27/macro.h:174-188)
+	bool kahan_rho = false;	 // the reference compiled with -DUSE_HIGH_PRECISION_RHO (defs.h:252)
 };
 
 template <typename R>
@@ -212,6 +213,16 @@ void density_velocity(Cell<R, 27>& K)
 	const R edges = ((s(D(0, 1, 1)) + s(D(0, 1, -1))) + (s(D(1, 0, 1)) + s(D(1, 0, -1)))) + (s(D(1, 1, 0)) + s(D(1, -1, 0)));
 	const R axes = (s(D(1, 0, 0)) + s(D(0, 1, 0))) + s(D(0, 0, 1));
 	K.rho = ((corners + edges) + axes) + f[D(0, 0, 0)];
+	if (K.kahan_rho) {	// d3q27/common.h:19-29: Kahan summation over the populations in index order
+		K.rho = 0;
+		R c = 0;
+		for (int i = 0; i < 27; i++) {
+			const R y = f[i] - c;
+			const R t = K.rho + y;
+			c = (t - K.rho) - y;
+			K.rho = t;
+		}
+	}
 
 	const R half = (R) 0.5;
 	const R cz = (d(D(1, 1, 1)) + d(D(-1, 1, 1))) + (d(D(1, -1, 1)) + d(D(-1, -1, 1)));
@@ -785,7 +796,7 @@ template <typename R>
 void collide(Cell<R, 27>& K, const oracle_desc& d)
 {
 	switch (d.coll) {
-		case ORC_COLL_CUM: collide_cum(K); break;
+		case ORC_COLL_CUM: case ORC_COLL_CUM_HP_RHO: collide_cum(K); break;
 		case ORC_COLL_SRT: collide_srt27(K, d.eq); break;
 		case ORC_COLL_BGK: collide_bgk27(K); break;
 		case ORC_COLL_BGK_GALILEAN: collide_bgk27<R, true>(K); break;
@@ -1203,6 +1214,7 @@ void cell_update(const Block<R>& B, const oracle_desc& d, idx x, idx y, idx z)
 	const int m = B.map[B.cell(x, y, z)];
 	const Nbr n = neighbours(B, m == L::PERIODIC, aa, x, y, z);
 	Cell<R, Q> K;
+	K.kahan_rho = d.coll == ORC_COLL_CUM_HP_RHO;
 	if (d.macro != ORC_MACRO_VOID) {  // copyQuantities (macro.h:73-80); MACRO_Void leaves the KernelStruct defaults
 		K.nu = B.nu;
 		K.fx = B.fx;
@@ -1302,6 +1314,7 @@ int initial_macro(const oracle_desc* d, const oracle_params* p, void* df, void* 
 		for (idx z = 0; z < B.Z; z++)
 			for (idx y = 0; y < B.Y; y++) {
 				Cell<R, L::Q> K;
+				K.kahan_rho = d->coll == ORC_COLL_CUM_HP_RHO;
 				for (int q = 0; q < L::Q; q++)
 					K.f[q] = f[B.at(q, x, y, z)];
 				if (d->macro != ORC_MACRO_VOID)
@@ -1322,7 +1335,7 @@ bool supported(const oracle_desc* d)
 	if (d->macro < ORC_MACRO_VOID || d->macro > ORC_MACRO_WITH_MEAN_2D || (d->macro == ORC_MACRO_WITH_MEAN_2D && d->lattice != ORC_D2Q9))
 		return false;
 	if (d->lattice == ORC_D3Q27)
-		return ((d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE) || (d->coll >= ORC_COLL_CUM_2017 && d->coll <= ORC_COLL_BGK_GALILEAN))
+		return ((d->coll >= ORC_COLL_CUM && d->coll <= ORC_COLL_SRT_MODIF_FORCE) || (d->coll >= ORC_COLL_CUM_2017 && d->coll <= ORC_COLL_CUM_HP_RHO))
 			&& (d->eq == ORC_EQ_STD || d->eq == ORC_EQ_INV_CUM || d->eq == ORC_EQ_ENTROPIC);
 	if (d->lattice == ORC_D2Q9)
 		return (d->coll == ORC_COLL_SRT || d->coll == ORC_COLL_CLBM) && d->eq == ORC_EQ_STD && d->Z == 1;

@@ -22,6 +22,7 @@ D3Q27, D2Q9, D3Q19 = 0, 1, 2
 CUM, SRT, BGK, MRT_LES, CLBM, SRT_MODIF_FORCE, SRT_WELL, BGK_WELL, CLBM_WELL, CUM_WELL, CUM_2017, CUM_ANTIALIAS, CUM_2017_ANTIALIAS = range(13)
 KBC_N1, KBC_N2, KBC_N3, KBC_N4, KBC_C1, KBC_C2, KBC_C3, KBC_C4 = range(13, 21)
 BGK_GALILEAN = 21  # D3Q27_BGK built with -DUSE_GALILEAN_CORRECTION (defs.h:253)
+CUM_HP_RHO = 22  # D3Q27_CUM built with -DUSE_HIGH_PRECISION_RHO (defs.h:252)
 EQ_STD, EQ_INV_CUM, EQ_WELL, EQ_ENTROPIC = 0, 1, 2, 3
 AB, AA = 0, 1
 MACRO_VOID, MACRO_DEFAULT, MACRO_MEAN, MACRO_WITH_MEAN_2D = 0, 1, 2, 3

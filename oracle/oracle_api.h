@@ -45,7 +45,8 @@ enum {
 	ORC_COLL_KBC_C2 = 18,
 	ORC_COLL_KBC_C3 = 19,
 	ORC_COLL_KBC_C4 = 20,
-	ORC_COLL_BGK_GALILEAN = 21 /* D3Q27_BGK compiled with -DUSE_GALILEAN_CORRECTION (defs.h:253, col_bgk.h:20-45) */
+	ORC_COLL_BGK_GALILEAN = 21, /* D3Q27_BGK compiled with -DUSE_GALILEAN_CORRECTION (defs.h:253, col_bgk.h:20-45) */
+	ORC_COLL_CUM_HP_RHO = 22 /* D3Q27_CUM compiled with -DUSE_HIGH_PRECISION_RHO (defs.h:252, d3q27/common.h:19-29) */
 };
 enum { ORC_EQ_STD = 0, ORC_EQ_INV_CUM = 1, ORC_EQ_WELL = 2, ORC_EQ_ENTROPIC = 3 };
 enum { ORC_STREAM_AB = 0, ORC_STREAM_AA = 1 };

@@ -288,6 +288,7 @@ int ref_dispatch_d3q27_cum(const RefCall& c);
 int ref_dispatch_d3q27_srt(const RefCall& c);
 int ref_dispatch_d3q27_bgk(const RefCall& c);
 int ref_dispatch_d3q27_bgk_gal(const RefCall& c);
+int ref_dispatch_d3q27_cum_hprho(const RefCall& c);
 int ref_dispatch_d3q27_mrt(const RefCall& c);
 int ref_dispatch_d3q27_clbm(const RefCall& c);
 int ref_dispatch_d3q27_srtmf(const RefCall& c);

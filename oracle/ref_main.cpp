@@ -12,6 +12,8 @@ static int ref_dispatch(const RefCall& c)
 		return r;
 	if ((r = ref_dispatch_d3q27_bgk_gal(c)) != -1)
 		return r;
+	if ((r = ref_dispatch_d3q27_cum_hprho(c)) != -1)
+		return r;
 	if ((r = ref_dispatch_d3q27_mrt(c)) != -1)
 		return r;
 	if ((r = ref_dispatch_d3q27_clbm(c)) != -1)

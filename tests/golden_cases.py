@@ -58,6 +58,10 @@ CASES = [
     Case("bgkgal_f64_ab_zoo", O.Desc(coll=O.BGK_GALILEAN, eq=O.EQ_STD, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("bgkgal_f32_aa_zoo", O.Desc(coll=O.BGK_GALILEAN, eq=O.EQ_STD, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("bgkgal_f64_aa_box", O.Desc(coll=O.BGK_GALILEAN, eq=O.EQ_STD, streaming=O.AA, X=12, Y=12, Z=12), O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 40, "smooth"),
+    # D3Q27_CUM built with USE_HIGH_PRECISION_RHO (defs.h:252, d3q27/common.h:19-29: Kahan-summed density)
+    Case("cumhp_f64_ab_zoo", O.Desc(coll=O.CUM_HP_RHO, eq=O.EQ_INV_CUM, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("cumhp_f32_aa_zoo", O.Desc(coll=O.CUM_HP_RHO, eq=O.EQ_INV_CUM, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
+    Case("cumhp_f32_aa_box", O.Desc(coll=O.CUM_HP_RHO, eq=O.EQ_INV_CUM, streaming=O.AA, precision=O.F32, X=12, Y=12, Z=12), O.Params(lbmViscosity=1e-3, fx=1e-6), lc.map_periodic, 40, "smooth"),
     Case("mrt_f64_ab_zoo", O.Desc(coll=O.MRT_LES, eq=O.EQ_STD, streaming=O.AB, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("mrt_f32_aa_zoo", O.Desc(coll=O.MRT_LES, eq=O.EQ_STD, streaming=O.AA, precision=O.F32, X=9, Y=8, Z=7), _p3(), zoo, 4),
     Case("d2q9_srt_f64_ab_cavity", O.Desc(lattice=O.D2Q9, coll=O.SRT, eq=O.EQ_STD, streaming=O.AB, X=24, Y=24, Z=1), O.Params(lbmViscosity=0.05, inflow_vx=0.1), lc.map_cavity_2d, 40, "uniform"),

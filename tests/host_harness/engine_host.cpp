@@ -137,6 +137,7 @@ KParams<R> params_for(const oracle_desc* d, const oracle_params* op, R* cur, R* 
 	p.stream = aa ? (iteration % 2 == 0 ? S_AA_EVEN : S_AA_ODD) : S_AB;
 	p.out_mode = OUT_NONE;
 	p.stat_counter = op->stat_counter;
+	p.kahan_rho = d->lattice == ORC_D3Q27 && d->coll == ORC_COLL_CUM_HP_RHO;
 	const bool vm = d->macro == ORC_MACRO_VOID;	 // MACRO_Void::copyQuantities is empty: viscosity 1, no force (d3q27/macro.h:174-188)
 	p.phys.nu = vm ? R(1) : (R) op->lbmViscosity;
 	set_rates(p.phys);

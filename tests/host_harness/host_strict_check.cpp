@@ -41,7 +41,7 @@ int run(int coll, int eq, int prec)
 			f[q] = a[q * XYZ + ((size_t) xs * N + zs) * N + ys];
 		}
 		R rho, vx, vy, vz;
-		density_velocity(f, P, rho, vx, vy, vz);
+		density_velocity<KIND == K_CUM_HP_RHO>(f, P, rho, vx, vy, vz);
 		collide<KIND>(f, P, eq, rho, vx, vy, vz);
 		for (int q = 0; q < 27; q++) mine[q * XYZ + ((size_t) x * N + z) * N + y] = f[q];
 	}
@@ -98,6 +98,8 @@ int main()
 	r |= run<float, K_BGK>(ORC_COLL_BGK, ORC_EQ_STD, ORC_F32);
 	r |= run<float, K_BGK_GAL>(ORC_COLL_BGK_GALILEAN, ORC_EQ_STD, ORC_F32);
 	r |= run<double, K_BGK_GAL>(ORC_COLL_BGK_GALILEAN, ORC_EQ_STD, ORC_F64);
+	r |= run<float, K_CUM_HP_RHO>(ORC_COLL_CUM_HP_RHO, ORC_EQ_INV_CUM, ORC_F32);
+	r |= run<double, K_CUM_HP_RHO>(ORC_COLL_CUM_HP_RHO, ORC_EQ_INV_CUM, ORC_F64);
 	r |= run<float, K_MRT>(ORC_COLL_MRT_LES, ORC_EQ_STD, ORC_F32);
 	r |= run<float, K_CLBM>(ORC_COLL_CLBM, ORC_EQ_STD, ORC_F32);
 	r |= run<double, K_CLBM>(ORC_COLL_CLBM, ORC_EQ_STD, ORC_F64);

@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 SRC = os.path.join(ROOT, "tests", "host_harness", "engine_host.cpp")
 BIN = os.path.join(ROOT, "tests", "host_harness", "bin")
-KIND_NUMBER = {"K_CUM": 0, "K_SRT": 1, "K_BGK": 2, "K_MRT": 3, "K_CLBM": 4, "K_SRT_MF": 5, "K_CUM_2017": 10, "K_CUM_AALIAS": 11, "K_CUM_2017_AALIAS": 12, "K_BGK_GAL": 21,
+KIND_NUMBER = {"K_CUM": 0, "K_SRT": 1, "K_BGK": 2, "K_MRT": 3, "K_CLBM": 4, "K_SRT_MF": 5, "K_CUM_2017": 10, "K_CUM_AALIAS": 11, "K_CUM_2017_AALIAS": 12, "K_BGK_GAL": 21, "K_CUM_HP_RHO": 22,
                **{f"K_KBC_{g}{i}": 13 + 4 * k + i - 1 for k, g in enumerate("NC") for i in (1, 2, 3, 4)}}
 TOL = {O.F64: 1e-12, O.F32: 1e-5}
 

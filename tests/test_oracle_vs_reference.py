@@ -17,7 +17,7 @@ pytestmark = pytest.mark.skipif(
     reason="oracle/_ref (reference build) or the port library is not built",
 )
 
-COMBOS_3D = [(O.CUM, O.EQ_INV_CUM), (O.CUM, O.EQ_STD), (O.SRT, O.EQ_STD), (O.SRT, O.EQ_INV_CUM), (O.BGK, O.EQ_STD), (O.BGK_GALILEAN, O.EQ_STD), (O.MRT_LES, O.EQ_STD), (O.MRT_LES, O.EQ_INV_CUM),
+COMBOS_3D = [(O.CUM, O.EQ_INV_CUM), (O.CUM, O.EQ_STD), (O.CUM_HP_RHO, O.EQ_INV_CUM), (O.CUM_HP_RHO, O.EQ_STD), (O.SRT, O.EQ_STD), (O.SRT, O.EQ_INV_CUM), (O.BGK, O.EQ_STD), (O.BGK_GALILEAN, O.EQ_STD), (O.MRT_LES, O.EQ_STD), (O.MRT_LES, O.EQ_INV_CUM),
              (O.CLBM, O.EQ_STD), (O.CLBM, O.EQ_INV_CUM), (O.SRT_MODIF_FORCE, O.EQ_STD), (O.SRT_MODIF_FORCE, O.EQ_INV_CUM),
              (O.CUM_2017, O.EQ_INV_CUM), (O.CUM_ANTIALIAS, O.EQ_INV_CUM), (O.CUM_2017_ANTIALIAS, O.EQ_INV_CUM), (O.CUM_2017_ANTIALIAS, O.EQ_STD),
              (O.KBC_N1, O.EQ_STD), (O.KBC_N2, O.EQ_ENTROPIC), (O.KBC_N3, O.EQ_ENTROPIC), (O.KBC_N4, O.EQ_ENTROPIC), (O.KBC_N4, O.EQ_INV_CUM),
@@ -164,3 +164,22 @@ def test_d2q9_parabolic_inflow(streaming, prec):
     p = O.Params(lbmViscosity=0.02, fx=2e-5, fy=-1e-5, inflow_vx=0.07, inflow_vy=1.0, inflow_vz=1.0 / (d.Y - 3))
     ref, port = run_pair(d, m, p, nsteps=4)
     assert_same(ref, port, f"2d parabolic st={streaming} prec={prec}")
+
+
+def test_the_high_precision_rho_build_is_a_different_build():
+    """USE_HIGH_PRECISION_RHO (defs.h:252) changes the summation of the density (d3q27/common.h:19-29): the reference compiled with the
+    switch must differ from the default build in the last bits (otherwise oracle/ref_d3q27_cum_hprho.cpp did not get the switch into
+    common.h), and only there."""
+    outs = []
+    for coll in (O.CUM, O.CUM_HP_RHO):
+        d = O.Desc(lattice=O.D3Q27, coll=coll, eq=O.EQ_INV_CUM, streaming=O.AB, precision=O.F32, X=9, Y=8, Z=7)
+        m = lc.map_random_ab(d)
+        p = O.Params(lbmViscosity=0.013, fx=3e-5, fy=-2e-5, fz=1e-5, inflow_vx=0.04, inflow_vy=0.01, inflow_vz=-0.02)
+        orc = O.Oracle(d, "reference")
+        a = lc.noisy_df(d, orc, seed=11, noise=0.05)
+        b = a.copy()
+        mac = d.new_macro()
+        orc.step(p, a, b, mac, m, 0, 1, 1)
+        outs.append(b)
+    assert not np.array_equal(outs[0], outs[1])
+    np.testing.assert_allclose(outs[0], outs[1], rtol=0, atol=2e-6)

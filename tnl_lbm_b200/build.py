@@ -30,6 +30,7 @@ FAMILIES = [
     ("d3q27_srt", "D3Q27", "K_SRT"),
     ("d3q27_bgk", "D3Q27", "K_BGK"),
     ("d3q27_bgkgal", "D3Q27", "K_BGK_GAL"),
+    ("d3q27_cumhp", "D3Q27", "K_CUM_HP_RHO"),
     ("d3q27_mrt", "D3Q27", "K_MRT"),
     ("d3q27_clbm", "D3Q27", "K_CLBM"),
     ("d3q27_srtmf", "D3Q27", "K_SRT_MF"),

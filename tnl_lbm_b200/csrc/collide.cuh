@@ -57,12 +57,13 @@ constexpr bool kStrict = LBMX_STRICT != 0;
 // The sums are organised as the z-column sums the cumulant transform needs anyway (the compiler merges them); the
 // association differs from the reference's tree, i.e. agreement to a few ulp.
 // --------------------------------------------------------------------------------------------------------------------
-template <typename R>
+// KAHAN: the build with USE_HIGH_PRECISION_RHO (defs.h:252, d3q27/common.h:19-29; D3Q27 only here) -- strict::kahan_sum for the density
+template <bool KAHAN = false, typename R>
 LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
 {
 	using L = D3Q27;
 	if constexpr (kStrict) {
-		strict::density_velocity(f, P, rho, vx, vy, vz);
+		strict::density_velocity<KAHAN>(f, P, rho, vx, vy, vz);
 		return;
 	}
 	R k0[3][3], d[3][3];
@@ -81,7 +82,7 @@ LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, 
 		By[a] = k0[a][2] - k0[a][0];
 		Dz[a] = (d[a][2] + d[a][0]) + d[a][1];
 	}
-	rho = (A[2] + A[0]) + A[1];
+	rho = KAHAN ? strict::kahan_sum(f) : (A[2] + A[0]) + A[1];
 	const R jx = A[2] - A[0];
 	const R jy = (By[2] + By[0]) + By[1];
 	const R jz = (Dz[2] + Dz[0]) + Dz[1];
@@ -91,7 +92,7 @@ LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, 
 	vz = (jz + R(0.5) * P.fz) * ir;
 }
 
-template <typename R>
+template <bool KAHAN = false, typename R>
 LBMX_D void density_velocity(const R (&f)[9], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
 {
 	using L = D2Q9;
@@ -596,24 +597,84 @@ LBMX_D void collide_clbm_fast(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R
 // --------------------------------------------------------------------------------------------------------------------
 // D3Q27 SRT (col_srt.h:16-108), BGK (col_bgk.h:16-145, no Galilean correction), MRT_LES (col_mrt.h:13-141)
 // --------------------------------------------------------------------------------------------------------------------
+// SRT in default arithmetic, one routine for D3Q27 and D3Q19 (col_srt.h:16-108):
+//   f' = f + (feq - f) / tau + (1 - 1/(2 tau)) S feq  =  (1 - 1/tau) f + feq (1/tau + (1 - 1/(2 tau)) S),   S = 3 (c - u).F / rho.
+// The equilibrium is evaluated population by population and never stored (f[Q] and feq[Q] together pushed the fp64 kernels to 160
+// registers = 3 CTAs per SM), the bracket is a sum of three per-axis values, and the equilibrium family is a compile-time argument
+// (EQ: 0 = second-order polynomial, eq.h:13-130; 1 = product form, eq_inv_cum.h:24-136).
+template <typename L, int EQ, typename R>
+LBMX_D void srt_update(R (&f)[L::Q], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	const R itau = P.omega1, keep = R(1) - itau;
+	const R iRho = R(1) / (rho == R(0) ? R(1) : rho);
+	const R pre = (R(1) - R(0.5) * itau) * (R(3) * iRho);
+	const R v[3] = {vx, vy, vz}, F[3] = {P.fx, P.fy, P.fz};
+	R s[3][3];	// 1/tau + pre (c - u).F = s[0][cx+1] + s[1][cy+1] + s[2][cz+1]
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R kf = pre * F[a];
+		const R mid = (a == 0 ? itau : R(0)) - v[a] * kf;
+		s[a][1] = mid;
+		s[a][0] = mid - kf;
+		s[a][2] = mid + kf;
+	}
+	R g[3][3];	// EQ 1: per-axis factors g(0) = 3v^2 - 2, g(+-1) = 3v^2 +- 3v + 1; EQ 0: +-3v and 0
+	R base = R(0);
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		if constexpr (EQ == 1) {
+			const R t = R(3) * v[a] * v[a];
+			g[a][1] = t - R(2);
+			g[a][2] = (t + R(3) * v[a]) + R(1);
+			g[a][0] = (t - R(3) * v[a]) + R(1);
+		}
+		else {
+			g[a][1] = R(0);
+			g[a][2] = R(3) * v[a];
+			g[a][0] = R(-3) * v[a];
+		}
+	}
+	if constexpr (EQ == 0)
+		base = R(1) - R(1.5) * ((vx * vx + vy * vy) + vz * vz);
+	static_for<L::Q>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int cx = L::cx(q), cy = L::cy(q), cz = L::cz(q), n = (cx != 0) + (cy != 0) + (cz != 0);
+		R feq;
+		if constexpr (EQ == 1) {
+			constexpr R w = n == 0 ? -R(1.0 / 27.0) : n == 1 ? R(1.0 / 54.0) : n == 2 ? -R(1.0 / 108.0) : R(1.0 / 216.0);
+			feq = (w * rho) * ((g[0][cx + 1] * g[1][cy + 1]) * g[2][cz + 1]);
+		}
+		else {
+			constexpr R w = L::Q == 27 ? (n == 0 ? R(8.0 / 27.0) : n == 1 ? R(2.0 / 27.0) : n == 2 ? R(1.0 / 54.0) : R(1.0 / 216.0))
+									   : (n == 0 ? R(1.0 / 3.0) : n == 1 ? R(1.0 / 18.0) : R(1.0 / 36.0));
+			R cu3 = R(0);  // 3 c.u from the components that are not zero
+			if constexpr (n > 0) {
+				if constexpr (cx != 0 && cy != 0 && cz != 0)
+					cu3 = (g[0][cx + 1] + g[1][cy + 1]) + g[2][cz + 1];
+				else if constexpr (cx != 0 && cy != 0)
+					cu3 = g[0][cx + 1] + g[1][cy + 1];
+				else if constexpr (cx != 0 && cz != 0)
+					cu3 = g[0][cx + 1] + g[2][cz + 1];
+				else if constexpr (cy != 0 && cz != 0)
+					cu3 = g[1][cy + 1] + g[2][cz + 1];
+				else
+					cu3 = cx != 0 ? g[0][cx + 1] : (cy != 0 ? g[1][cy + 1] : g[2][cz + 1]);
+				feq = (w * rho) * ((base + cu3) + (R(0.5) * cu3) * cu3);
+			}
+			else
+				feq = (w * rho) * base;
+		}
+		f[q] = keep * f[q] + feq * ((s[0][cx + 1] + s[1][cy + 1]) + s[2][cz + 1]);
+	});
+}
+
 template <typename R>
 LBMX_D void collide_srt(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
-	using L = D3Q27;
-	const R itau = P.omega1;
-	const R iRho = R(1) / (rho == R(0) ? R(1) : rho);
-	const R pre = (R(1) - R(0.5) * itau) * (R(3) * iRho);
-	// (c - u).F per axis and sign
-	const R tx[3] = {(-vx - R(1)) * P.fx, -vx * P.fx, (-vx + R(1)) * P.fx};
-	const R ty[3] = {(-vy - R(1)) * P.fy, -vy * P.fy, (-vy + R(1)) * P.fy};
-	const R tz[3] = {(-vz - R(1)) * P.fz, -vz * P.fz, (-vz + R(1)) * P.fz};
-	R feq[27];
-	equilibrium(feq, eqkind, rho, vx, vy, vz);
-	static_for<27>([&](auto qc) {
-		constexpr int q = qc;
-		const R S = (tx[L::cx(q) + 1] + ty[L::cy(q) + 1]) + tz[L::cz(q) + 1];
-		f[q] = f[q] + ((feq[q] - f[q]) * itau + (pre * S) * feq[q]);
-	});
+	if (eqkind == 1)
+		srt_update<D3Q27, 1>(f, P, rho, vx, vy, vz);
+	else
+		srt_update<D3Q27, 0>(f, P, rho, vx, vy, vz);
 }
 
 // GALILEAN: the build with USE_GALILEAN_CORRECTION (defs.h:253, col_bgk.h:20-45) -- the diagonal second moments (here from the
@@ -622,8 +683,9 @@ template <bool GALILEAN = false, typename R>
 LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
-	const R omega1 = P.omega1;
-	const R pre = (R(1) - R(0.5) * omega1) * (R(3) / rho);
+	const R omega1 = P.omega1, keep = R(1) - omega1;
+	const R irho3 = R(3) / rho;
+	const R pre = (R(1) - R(0.5) * omega1) * irho3;
 	const R v[3] = {vx, vy, vz};
 	R G[3] = {R(0), R(0), R(0)};
 	if constexpr (GALILEAN) {
@@ -638,7 +700,6 @@ LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 				m[2] += f[q];
 		});
 		const R k = (R(1) / omega1 - R(0.5)) * (R(1.5) * omega1);  // -3 v^2 D (1/omega - 1/2) with D = -omega/2 (3 m/rho - 1 - 3 v^2)
-		const R irho3 = R(3) / rho;
 #pragma unroll
 		for (int a = 0; a < 3; a++)
 			G[a] = (v[a] * v[a]) * k * ((m[a] * irho3 - R(1)) - R(3) * (v[a] * v[a]));
@@ -652,14 +713,21 @@ LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 		g[a][2] = p;
 		g[a][0] = p + v[a];
 	}
-	const R tx[3] = {(-vx - R(1)) * P.fx, -vx * P.fx, (-vx + R(1)) * P.fx};
-	const R ty[3] = {(-vy - R(1)) * P.fy, -vy * P.fy, (-vy + R(1)) * P.fy};
-	const R tz[3] = {(-vz - R(1)) * P.fz, -vz * P.fz, (-vz + R(1)) * P.fz};
+	// f' = (1 - omega) f + feq (omega + pre (c - u).F), the bracket as a sum of three per-axis values (as in srt_update)
+	const R F[3] = {P.fx, P.fy, P.fz};
+	R s[3][3];
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R kf = pre * F[a];
+		const R mid = (a == 0 ? omega1 : R(0)) - v[a] * kf;
+		s[a][1] = mid;
+		s[a][0] = mid - kf;
+		s[a][2] = mid + kf;
+	}
 	static_for<27>([&](auto qc) {
 		constexpr int q = qc;
 		const R feq = ((-rho * g[0][L::cx(q) + 1]) * g[1][L::cy(q) + 1]) * g[2][L::cz(q) + 1];
-		const R S = (tx[L::cx(q) + 1] + ty[L::cy(q) + 1]) + tz[L::cz(q) + 1];
-		f[q] = f[q] + ((feq - f[q]) * omega1 + (pre * S) * feq);
+		f[q] = keep * f[q] + feq * ((s[0][L::cx(q) + 1] + s[1][L::cy(q) + 1]) + s[2][L::cz(q) + 1]);
 	});
 }
 
@@ -717,30 +785,36 @@ LBMX_D void collide_mrt(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 // --------------------------------------------------------------------------------------------------------------------
 // D2Q9 SRT (d2q9/col_srt.h:16-44) and cascaded CLBM (d2q9/col_clbm.h:13-89)
 // --------------------------------------------------------------------------------------------------------------------
+// d2q9/col_srt.h:16-44 in default arithmetic: f' = f + (feq - f) / tau + F_q with the source term
+//   F_q = (1 - 1/(2 tau)) w_q [3 (c - u).F + 9 (c.u)(c.F)] = (1 - 1/(2 tau)) w_q [(3 c.F)(1 + 3 c.u) - 3 u.F],
+// so with cu3 = 3 c.u shared between the equilibrium polynomial and the source:
+//   f' = (1 - 1/tau) f + w_q [ (rho / tau) (base + cu3 + cu3^2 / 2) + pre ((3 c.F)(1 + cu3) - 3 u.F) ]
+// (the reference divides by 9 and 36 per population and evaluates all nine brackets in full: ~225 fp64 instructions per cell, which is
+// most of the time of a step on an L2-resident lattice -- BASELINE configs[1]; this form takes ~110)
 template <typename R>
 LBMX_D void collide_srt(R (&f)[9], const Phys<R>& P, int, R rho, R vx, R vy, R)
 {
 	using L = D2Q9;
-	const R itau = P.omega1;
+	const R itau = P.omega1, keep = R(1) - itau;
 	const R pre = R(1) - R(0.5) * itau;
-	const R fx = P.fx, fy = P.fy;
-	// (d2q9/col_srt.h:21-29 divides by 9 and 36 per population: in default arithmetic the weights are constants)
-	const R w0 = pre * R(4.0 / 9.0), w1 = pre * R(1.0 / 9.0), w2 = pre * R(1.0 / 36.0);
-	R F[9];
-	F[L::find(0, 0)] = w0 * (R(3) * (-vx * fx - vy * fy));
-	F[L::find(1, 0)] = w1 * (R(3) * ((R(1) - vx) * fx - vy * fy) + R(9) * vx * fx);
-	F[L::find(-1, 0)] = w1 * (R(3) * ((R(-1) - vx) * fx - vy * fy) + R(9) * vx * fx);
-	F[L::find(0, 1)] = w1 * (R(3) * (-vx * fx + (R(1) - vy) * fy) + R(9) * vy * fy);
-	F[L::find(0, -1)] = w1 * (R(3) * (-vx * fx + (R(-1) - vy) * fy) + R(9) * vy * fy);
-	F[L::find(1, 1)] = w2 * (R(3) * ((R(1) - vx) * fx + (R(1) - vy) * fy) + R(9) * (vx + vy) * (fx + fy));
-	F[L::find(-1, -1)] = w2 * (R(3) * ((R(-1) - vx) * fx + (R(-1) - vy) * fy) + R(9) * (vx + vy) * (fx + fy));
-	F[L::find(1, -1)] = w2 * (R(3) * ((R(1) - vx) * fx + (R(-1) - vy) * fy) + R(9) * (vx - vy) * (fx - fy));
-	F[L::find(-1, 1)] = w2 * (R(3) * ((R(-1) - vx) * fx + (R(1) - vy) * fy) + R(9) * (vx - vy) * (fx - fy));
-	R feq[9];
-	equilibrium(feq, 0, rho, vx, vy, R(0));
+	const R base = R(1) - R(1.5) * (vx * vx + vy * vy);
+	const R u3[2][3] = {{R(-3) * vx, R(0), R(3) * vx}, {R(-3) * vy, R(0), R(3) * vy}};
+	const R gx = (R(3) * pre) * P.fx, gy = (R(3) * pre) * P.fy;	 // pre * 3 F
+	const R g3[2][3] = {{-gx, R(0), gx}, {-gy, R(0), gy}};
+	const R B = vx * gx + vy * gy;	// pre * 3 u.F
+	const R ir = itau * rho;
 	static_for<9>([&](auto qc) {
 		constexpr int q = qc;
-		f[q] = f[q] + ((feq[q] - f[q]) * itau + F[q]);
+		constexpr int cx = L::cx(q), cy = L::cy(q), n = (cx != 0) + (cy != 0);
+		constexpr R w = n == 0 ? R(4.0 / 9.0) : n == 1 ? R(1.0 / 9.0) : R(1.0 / 36.0);
+		if constexpr (n == 0)
+			f[q] = keep * f[q] + w * (ir * base - B);
+		else {
+			const R cu3 = n == 2 ? u3[0][cx + 1] + u3[1][cy + 1] : (cx != 0 ? u3[0][cx + 1] : u3[1][cy + 1]);
+			const R cg = n == 2 ? g3[0][cx + 1] + g3[1][cy + 1] : (cx != 0 ? g3[0][cx + 1] : g3[1][cy + 1]);
+			const R poly = (base + cu3) + (R(0.5) * cu3) * cu3;
+			f[q] = keep * f[q] + w * (ir * poly + (cg * cu3 + (cg - B)));
+		}
 	});
 }
 
@@ -800,7 +874,7 @@ LBMX_HD constexpr R w19(int q)
 	return n == 0 ? R(1.0 / 3.0) : n == 1 ? R(1.0 / 18.0) : R(1.0 / 36.0);
 }
 
-template <typename R>
+template <bool KAHAN = false, typename R>
 LBMX_D void density_velocity(const R (&f)[19], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
 {
 	using L = D3Q19;
@@ -838,20 +912,7 @@ LBMX_D void equilibrium(R (&feq)[19], int, R rho, R vx, R vy, R vz)
 template <typename R>
 LBMX_D void collide_srt(R (&f)[19], const Phys<R>& P, int, R rho, R vx, R vy, R vz)
 {
-	using L = D3Q19;
-	const R itau = P.omega1;
-	const R iRho = R(1) / (rho == R(0) ? R(1) : rho);
-	const R pre = (R(1) - R(0.5) * itau) * (R(3) * iRho);
-	const R tx[3] = {(-vx - R(1)) * P.fx, -vx * P.fx, (-vx + R(1)) * P.fx};
-	const R ty[3] = {(-vy - R(1)) * P.fy, -vy * P.fy, (-vy + R(1)) * P.fy};
-	const R tz[3] = {(-vz - R(1)) * P.fz, -vz * P.fz, (-vz + R(1)) * P.fz};
-	R feq[19];
-	equilibrium(feq, 0, rho, vx, vy, vz);
-	static_for<19>([&](auto qc) {
-		constexpr int q = qc;
-		const R S = (tx[L::cx(q) + 1] + ty[L::cy(q) + 1]) + tz[L::cz(q) + 1];
-		f[q] = f[q] + ((feq[q] - f[q]) * itau + (pre * S) * feq[q]);
-	});
+	srt_update<D3Q19, 0>(f, P, rho, vx, vy, vz);
 }
 
 template <typename R>
@@ -922,7 +983,8 @@ LBMX_D void equilibrium_any(R (&feq)[Q], int eqkind, R rho, R vx, R vy, R vz)
 // --------------------------------------------------------------------------------------------------------------------
 enum CollKind : int { K_CUM = 0, K_SRT = 1, K_BGK = 2, K_MRT = 3, K_CLBM = 4 /* D2Q9_CLBM or D3Q27_CLBM, by lattice */, K_SRT_MF = 5, K_CUM_2017 = 10, K_CUM_AALIAS = 11, K_CUM_2017_AALIAS = 12 /* D3Q27_CUM built with the switches of defs.h:254-255 */,
 						K_KBC_N1 = 13, K_KBC_N2, K_KBC_N3, K_KBC_N4, K_KBC_C1, K_KBC_C2, K_KBC_C3, K_KBC_C4,
-						K_BGK_GAL = 21 /* D3Q27_BGK built with USE_GALILEAN_CORRECTION (defs.h:253) */ };
+						K_BGK_GAL = 21 /* D3Q27_BGK built with USE_GALILEAN_CORRECTION (defs.h:253) */,
+						K_CUM_HP_RHO = 22 /* D3Q27_CUM built with USE_HIGH_PRECISION_RHO (defs.h:252): density_velocity<true>, same collision */ };
 
 template <int KIND, bool HW_RCP = true, typename R>
 LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
@@ -961,7 +1023,7 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 		ext::collide_srt_modif<kStrict>(f, feq, P, vx, vy, vz);
 	}
 	else if constexpr (kStrict) {
-		if constexpr (KIND == K_CUM)
+		if constexpr (KIND == K_CUM || KIND == K_CUM_HP_RHO)
 			strict::collide_cum(f, P, rho, vx, vy, vz);
 		else if constexpr (KIND == K_SRT) {
 			R feq[27];
@@ -975,7 +1037,7 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 		else
 			strict::collide_mrt(f, P, rho, vx, vy, vz);
 	}
-	else if constexpr (KIND == K_CUM)
+	else if constexpr (KIND == K_CUM || KIND == K_CUM_HP_RHO)
 		collide_cum(f, P, rho, vx, vy, vz);
 	else if constexpr (KIND == K_SRT)
 		collide_srt(f, P, eqkind, rho, vx, vy, vz);

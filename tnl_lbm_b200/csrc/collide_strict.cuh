@@ -18,8 +18,23 @@ struct Phys;
 
 namespace strict {
 
+// the density of a build with USE_HIGH_PRECISION_RHO (defs.h:252; d3q27/common.h:19-29): compensated (Kahan) sum over the populations in
+// index order.  No multiplications: FMA contraction cannot touch it, and nvcc does not reassociate without -use_fast_math.
+template <typename R, int Q>
+LBMX_D R kahan_sum(const R (&f)[Q])
+{
+	R s = R(0), c = R(0);
+	static_for<Q>([&](auto qc) {
+		const R y = f[qc] - c;
+		const R t = s + y;
+		c = (t - s) - y;
+		s = t;
+	});
+	return s;
+}
+
 // d3q27/common.h:16-50 -- s(q) = f[q] + f[opp q], d(q) = f[q] - f[opp q]
-template <typename R>
+template <bool KAHAN = false, typename R>
 LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
 {
 	using L = D3Q27;
@@ -28,7 +43,7 @@ LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, 
 	const R corners = (SQ(1, 1, 1) + SQ(1, -1, 1)) + (SQ(1, 1, -1) + SQ(-1, 1, 1));
 	const R edges = ((SQ(0, 1, 1) + SQ(0, 1, -1)) + (SQ(1, 0, 1) + SQ(1, 0, -1))) + (SQ(1, 1, 0) + SQ(1, -1, 0));
 	const R axes = (SQ(1, 0, 0) + SQ(0, 1, 0)) + SQ(0, 0, 1);
-	rho = ((corners + edges) + axes) + f[L::find(0, 0, 0)];
+	rho = KAHAN ? kahan_sum(f) : ((corners + edges) + axes) + f[L::find(0, 0, 0)];
 	const R half = R(0.5);
 	const R cz = (DQ(1, 1, 1) + DQ(-1, 1, 1)) + (DQ(1, -1, 1) + DQ(-1, -1, 1));
 	const R ez = (DQ(0, 1, 1) + DQ(0, -1, 1)) + (DQ(1, 0, 1) + DQ(-1, 0, 1));
@@ -44,7 +59,7 @@ LBMX_D void density_velocity(const R (&f)[27], const Phys<R>& P, R& rho, R& vx, 
 }
 
 // d2q9/common.h:16-36
-template <typename R>
+template <bool KAHAN = false, typename R>
 LBMX_D void density_velocity(const R (&f)[9], const Phys<R>& P, R& rho, R& vx, R& vy, R& vz)
 {
 	using L = D2Q9;

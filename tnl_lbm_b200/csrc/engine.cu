@@ -328,6 +328,7 @@ KParams<R> make_params(const lbmx_engine* e)
 	p.stream = e->aa() ? (e->iter % 2 == 0 ? S_AA_EVEN : S_AA_ODD) : S_AB;
 	p.out_mode = OUT_NONE;
 	p.stat_counter = e->prm.stat_counter;
+	p.kahan_rho = e->d.lattice == LBMX_D3Q27 && e->d.coll == LBMX_COLL_CUM_HP_RHO;
 	const bool vm = e->d.macro == LBMX_MACRO_VOID;
 	// MACRO_Void::copyQuantities is empty (d3q27/macro.h:174-188): the KernelStruct keeps lbmViscosity = 1, zero force
 	p.phys.nu = vm ? R(1) : (R) e->prm.lbmViscosity;
@@ -740,6 +741,7 @@ bool pick_kernels(lbmx_engine* e)
 				case LBMX_COLL_SRT: return e->f64() ? get_kernels_d3q27_srt_strict(e->kd) : get_kernels_d3q27_srt_strict(e->kf);
 				case LBMX_COLL_BGK: return e->f64() ? get_kernels_d3q27_bgk_strict(e->kd) : get_kernels_d3q27_bgk_strict(e->kf);
 				case LBMX_COLL_BGK_GALILEAN: return e->f64() ? get_kernels_d3q27_bgkgal_strict(e->kd) : get_kernels_d3q27_bgkgal_strict(e->kf);
+				case LBMX_COLL_CUM_HP_RHO: return e->f64() ? get_kernels_d3q27_cumhp_strict(e->kd) : get_kernels_d3q27_cumhp_strict(e->kf);
 				case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt_strict(e->kd) : get_kernels_d3q27_mrt_strict(e->kf);
 				case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm_strict(e->kd) : get_kernels_d3q27_clbm_strict(e->kf);
 				case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf_strict(e->kd) : get_kernels_d3q27_srtmf_strict(e->kf);
@@ -770,6 +772,7 @@ bool pick_kernels(lbmx_engine* e)
 			case LBMX_COLL_SRT: return e->f64() ? get_kernels_d3q27_srt(e->kd) : get_kernels_d3q27_srt(e->kf);
 			case LBMX_COLL_BGK: return e->f64() ? get_kernels_d3q27_bgk(e->kd) : get_kernels_d3q27_bgk(e->kf);
 			case LBMX_COLL_BGK_GALILEAN: return e->f64() ? get_kernels_d3q27_bgkgal(e->kd) : get_kernels_d3q27_bgkgal(e->kf);
+			case LBMX_COLL_CUM_HP_RHO: return e->f64() ? get_kernels_d3q27_cumhp(e->kd) : get_kernels_d3q27_cumhp(e->kf);
 			case LBMX_COLL_MRT_LES: return e->f64() ? get_kernels_d3q27_mrt(e->kd) : get_kernels_d3q27_mrt(e->kf);
 			case LBMX_COLL_CLBM: return e->f64() ? get_kernels_d3q27_clbm(e->kd) : get_kernels_d3q27_clbm(e->kf);
 			case LBMX_COLL_SRT_MODIF_FORCE: return e->f64() ? get_kernels_d3q27_srtmf(e->kd) : get_kernels_d3q27_srtmf(e->kf);

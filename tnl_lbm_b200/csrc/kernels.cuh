@@ -90,6 +90,7 @@ struct KParams
 	int profile_sy;
 	int tile_y, tile_y_shift;  // k_bulk_tma: cells of one row per CTA (power of two dividing Y) and its log2
 	int eq, inflow, stream, out_mode, stat_counter;
+	int kahan_rho;	   // 1: the operator is a build with USE_HIGH_PRECISION_RHO (k_initial_macro has no operator template argument)
 	int pdl;		   // k_boundary under programmatic dependent launch: 1 = runs beside the bulk kernel launched just before it (see pdl_wait)
 	Phys<R> phys;
 	R in_vx, in_vy, in_vz;
@@ -466,13 +467,14 @@ __device__ __noinline__ void bulk_cold_cell(const KParams<R>& p, int x, int yz, 
 	output_macro_impl<L, R>(p.macro, p.XYZ, p.out_mode, p.stat_counter, c, R(1), R(0), R(0), R(0));
 }
 
-// A-B bulk kernel: do obstacle / inert lanes store together with their warp (phase 2)?  Everywhere (LBMX_AB_WHOLE_SECTORS) except the D3Q19
-// SRT fp64 kernel (156 registers, 3 CTAs per SM), whose periodic-box rate the extra path costs 16 % (5 129 -> 6 091 GB/s without it,
-// profiles/kbench_r2_q9_q19srt_features.txt): there those lanes take the cold path of phase 3 like under A-A.
+// A-B bulk kernel: do obstacle / inert lanes store together with their warp (phase 2)?  Measured per kernel on a map without obstacles
+// (profiles/kbench_r2_ab_whole_sectors_per_kernel.txt): free or slightly positive on the D3Q27 kernels, D3Q19 MRT_LES and D2Q9 CLBM fp64,
+// but the SRT kernels of D3Q19 and D2Q9 lose 6-26 % to the extra path (D3Q19 fp64 5.13 -> 6.09 TB/s without it, fp32 4.67 -> 5.90; D2Q9 fp64
+// 5.43 -> 6.16, fp32 5.24 -> 5.55): there those lanes take the cold path of phase 3 like under A-A.
 template <typename L, int KIND, typename R>
 constexpr bool ab_whole_sectors()
 {
-	return LBMX_AB_WHOLE_SECTORS && ! (L::Q == 19 && KIND == K_SRT && sizeof(R) == 8);
+	return LBMX_AB_WHOLE_SECTORS && ! (L::Q != 27 && KIND == K_SRT);
 }
 
 // resident CTAs per SM the register allocation is sized for: the cumulant / MRT_LES kernels fit 128 (A-A) and 96 (A-B)
@@ -483,7 +485,9 @@ constexpr int bulk_minblocks()
 	if (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
 		return sizeof(R) == 8 ? (MODE == S_AA_ODD ? LBMX_KBC_MINBLOCKS_F64_ODD : LBMX_KBC_MINBLOCKS_F64) : (MODE == S_AB ? LBMX_KBC_MINBLOCKS_F32_AB : LBMX_KBC_MINBLOCKS_F32);
 	// (the default-arithmetic cascaded operator is as light as the cumulant one; its parity-arithmetic form keeps 27 moments of each kind live)
-	if (sizeof(R) == 8 && (KIND == K_SRT || KIND == K_BGK || KIND == K_BGK_GAL || KIND == K_SRT_MF || (KIND == K_CLBM && (kStrict || L_Q != 27))))
+	// (D3Q19 SRT in its default-arithmetic form fits 128 / 96 registers: 4 / 5 CTAs run the chained A-A steps at 6.39 instead of 5.69 TB/s,
+	// profiles/kbench_r2_srt_reorganised.txt; D3Q27 SRT is best at 3)
+	if (sizeof(R) == 8 && ((KIND == K_SRT && (kStrict || L_Q != 19)) || KIND == K_BGK || KIND == K_BGK_GAL || KIND == K_SRT_MF || (KIND == K_CLBM && (kStrict || L_Q != 27))))
 		return LBMX_BULK_MINBLOCKS < 3 ? LBMX_BULK_MINBLOCKS : 3;
 	return MODE == S_AB ? LBMX_BULK_MINBLOCKS_AB : LBMX_BULK_MINBLOCKS;
 }
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE,
 			rho = f[k][0];
 			vx = vy = vz = R(0);
 #else
-			density_velocity(f[k], p.phys, rho, vx, vy, vz);
+			density_velocity<KIND == K_CUM_HP_RHO>(f[k], p.phys, rho, vx, vy, vz);
 			collide<KIND, MODE != S_AB>(f[k], p.phys, p.eq, rho, vx, vy, vz);
 #endif
 		}
@@ -833,16 +837,16 @@ __global__ void __launch_bounds__(128, LBMX_BOUNDARY_MINBLOCKS) k_boundary(const
 		inflow_left_moments(f, rho, vx, vy, vz);
 	}
 	else if (m == L::OUTFLOW_EQ) {
-		density_velocity(f, p.phys, rho, vx, vy, vz);
+		density_velocity<KIND == K_CUM_HP_RHO>(f, p.phys, rho, vx, vy, vz);
 		rho = R(1);
 		set_equilibrium();
 	}
 	else if (m == L::OUTFLOW_RIGHT) {
-		density_velocity(f, p.phys, rho, vx, vy, vz);
+		density_velocity<KIND == K_CUM_HP_RHO>(f, p.phys, rho, vx, vy, vz);
 		rho = R(1);
 	}
 	else if (m == L::OUTFLOW_RIGHT_INTERP) {
-		density_velocity(f, p.phys, rho, vx, vy, vz);
+		density_velocity<KIND == K_CUM_HP_RHO>(f, p.phys, rho, vx, vy, vz);
 		R e1[L::Q], e0[L::Q];
 		equilibrium_any(e1, p.eq, R(1), vx, vy, vz);
 		equilibrium_any(e0, p.eq, rho, vx, vy, vz);
@@ -866,7 +870,7 @@ __global__ void __launch_bounds__(128, LBMX_BOUNDARY_MINBLOCKS) k_boundary(const
 			mirror_pops<L, 1, -1>(f);
 		else if (L::NDIM == 2 && m == 12 && p.stream == S_AB)  // D2Q9 GEO_FLUID_NEAR_WALL (d2q9/bc.h:29); plain fluid under A-A
 			bouzidi_near_wall(p, f, c, d);
-		density_velocity(f, p.phys, rho, vx, vy, vz);
+		density_velocity<KIND == K_CUM_HP_RHO>(f, p.phys, rho, vx, vy, vz);
 	}
 
 	if (L::collides(m))
@@ -914,7 +918,10 @@ __global__ void k_initial_macro(const KParams<R> p)
 	Phys<R> ph = p.phys;
 	ph.fx = ph.fy = ph.fz = R(0);
 	R rho, vx, vy, vz;
-	density_velocity(f, ph, rho, vx, vy, vz);
+	if (p.kahan_rho)
+		density_velocity<true>(f, ph, rho, vx, vy, vz);
+	else
+		density_velocity<false>(f, ph, rho, vx, vy, vz);
 	output_macro<L>(p, c, rho, vx, vy, vz);
 }
 
@@ -991,6 +998,8 @@ bool get_kernels_d3q27_bgk(StepKernels<float>&);
 bool get_kernels_d3q27_bgk(StepKernels<double>&);
 bool get_kernels_d3q27_bgkgal(StepKernels<float>&);
 bool get_kernels_d3q27_bgkgal(StepKernels<double>&);
+bool get_kernels_d3q27_cumhp(StepKernels<float>&);
+bool get_kernels_d3q27_cumhp(StepKernels<double>&);
 bool get_kernels_d3q27_mrt(StepKernels<float>&);
 bool get_kernels_d3q27_mrt(StepKernels<double>&);
 bool get_kernels_d3q27_cum2017(StepKernels<float>&);
@@ -1054,6 +1063,8 @@ bool get_kernels_d3q27_bgk_strict(StepKernels<float>&);
 bool get_kernels_d3q27_bgk_strict(StepKernels<double>&);
 bool get_kernels_d3q27_bgkgal_strict(StepKernels<float>&);
 bool get_kernels_d3q27_bgkgal_strict(StepKernels<double>&);
+bool get_kernels_d3q27_cumhp_strict(StepKernels<float>&);
+bool get_kernels_d3q27_cumhp_strict(StepKernels<double>&);
 bool get_kernels_d3q27_mrt_strict(StepKernels<float>&);
 bool get_kernels_d3q27_mrt_strict(StepKernels<double>&);
 bool get_kernels_d2q9_srt_strict(StepKernels<float>&);

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(tma::TILE, tma_minblocks<KIND, R, MODE>()) k_b
 	});
 	R rho = R(1), vx = R(0), vy = R(0), vz = R(0);
 	if (is_bulk) {
-		density_velocity(f, p.phys, rho, vx, vy, vz);
+		density_velocity<KIND == K_CUM_HP_RHO>(f, p.phys, rho, vx, vy, vz);
 		collide<KIND>(f, p.phys, p.eq, rho, vx, vy, vz);
 	}
 	if (! fallback) {

@@ -485,6 +485,8 @@ LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM_2017_ANTIALIAS, "CUM")
 LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM_2017, "CUM")
 #elif defined(USE_GEIER_CUM_ANTIALIAS)
 LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM_ANTIALIAS, "CUM")
+#elif defined(USE_HIGH_PRECISION_RHO)  // defs.h:252: Kahan-summed density (the engine has that build of the default cumulant operator; not of the others)
+LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM_HP_RHO, "CUM")
 #else
 LBMX_COLL_TAG(D3Q27_CUM, D3Q27_EQ, LBMX_COLL_CUM, "CUM")
 #endif
