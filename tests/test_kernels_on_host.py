@@ -210,6 +210,22 @@ def test_1000_steps_of_the_cumulant_kernels_on_the_host(strict_lib, fast_lib, st
         assert lc.rel_err(mac[lo:hi], mac_ref[lo:hi]) <= 1e-12, label
 
 
+@pytest.mark.parametrize("coll,eq,tol", [(O.SRT, O.EQ_STD, 1e-5), (O.BGK, O.EQ_STD, 1e-5), (O.KBC_N4, O.EQ_ENTROPIC, 1e-5), (O.CLBM, O.EQ_STD, 5e-5), (O.CUM_2017_ANTIALIAS, O.EQ_INV_CUM, 5e-5)])
+def test_1000_fp32_steps_of_the_reorganised_operators_on_the_host(fast_lib, coll, eq, tol):
+    """The default-arithmetic operators are reorganised for the GPU's pipes.  In fp32 the *form* of the update matters
+    over a long run: an update that rebuilds f from products rounds several times at the magnitude of f per step, the reference's incremental
+    form once -- after 1000 steps the former sat 4e-5 off the reference on the GPU.  Here: the kernels' host build against the restatement,
+    1000 fp32 steps, within the tolerance of the GPU test (tests/test_gpu_parity.py::test_1000_steps_fp32_srt_and_d2q9).  The operators
+    that rebuild f from moments in the reference as well (CLBM, the cumulant family) carry the error class of the default cumulant kernel
+    (2.2e-5 here; the reference itself loses 2.9e-5 of its mass over these 1000 fp32 steps): bound 5e-5, density within 4e-6."""
+    d = O.Desc(coll=coll, eq=eq, streaming=O.AB, precision=O.F32, X=10, Y=8, Z=8)
+    case = gc.Case("long", d, O.Params(lbmViscosity=0.02, fx=1e-6), lc.map_periodic, 1000, "smooth")
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=4)
+    df, mac = gc.run_case(case, "engine_host", fast=True, init_kind="port")
+    assert lc.rel_err_df(df, df_ref, d) <= tol
+    assert lc.rel_err(mac[0:1], mac_ref[0:1]) <= (2e-6 if tol <= 1e-5 else 4e-6), "density"
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_plane_copy_kernel_on_the_host(strict_lib, dtype):
     """k_copy_planes (the data mover of the halo exchange: self-exchange, and the push into a neighbour's array with its own component

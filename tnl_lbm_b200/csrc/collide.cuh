@@ -598,22 +598,26 @@ LBMX_D void collide_clbm_fast(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R
 // D3Q27 SRT (col_srt.h:16-108), BGK (col_bgk.h:16-145, no Galilean correction), MRT_LES (col_mrt.h:13-141)
 // --------------------------------------------------------------------------------------------------------------------
 // SRT in default arithmetic, one routine for D3Q27 and D3Q19 (col_srt.h:16-108):
-//   f' = f + (feq - f) / tau + (1 - 1/(2 tau)) S feq  =  (1 - 1/tau) f + feq (1/tau + (1 - 1/(2 tau)) S),   S = 3 (c - u).F / rho.
+//   f' = f + ((feq - f) / tau + ((1 - 1/(2 tau)) S) feq),   S = 3 (c - u).F / rho.
 // The equilibrium is evaluated population by population and never stored (f[Q] and feq[Q] together pushed the fp64 kernels to 160
-// registers = 3 CTAs per SM), the bracket is a sum of three per-axis values, and the equilibrium family is a compile-time argument
-// (EQ: 0 = second-order polynomial, eq.h:13-130; 1 = product form, eq_inv_cum.h:24-136).
+// registers = 3 CTAs per SM), (1 - 1/(2 tau)) S is a sum of three per-axis values, and the equilibrium family is a compile-time argument
+// (EQ: 0 = second-order polynomial, eq.h:13-130; 1 = product form, eq_inv_cum.h:24-136).  The update keeps the reference's incremental
+// form: feq - f is exact where it matters (Sterbenz), so a step rounds once at the magnitude of f.  The algebraically equal
+// (1 - 1/tau) f + feq (1/tau + ...) saves one operation per population and rounds three times there -- after 1000 fp32 steps the
+// populations were 4e-5 off the reference instead of < 1e-5 (tests/test_gpu_parity.py::test_1000_steps_fp32_srt_and_d2q9): fp32 keeps
+// the incremental form, fp64 (where three roundings at 1e-16 do not show) takes the shorter one (A-A odd kernel 5.75 -> 6.49 TB/s).
 template <typename L, int EQ, typename R>
 LBMX_D void srt_update(R (&f)[L::Q], const Phys<R>& P, R rho, R vx, R vy, R vz)
 {
-	const R itau = P.omega1, keep = R(1) - itau;
+	const R itau = P.omega1;
 	const R iRho = R(1) / (rho == R(0) ? R(1) : rho);
 	const R pre = (R(1) - R(0.5) * itau) * (R(3) * iRho);
 	const R v[3] = {vx, vy, vz}, F[3] = {P.fx, P.fy, P.fz};
-	R s[3][3];	// 1/tau + pre (c - u).F = s[0][cx+1] + s[1][cy+1] + s[2][cz+1]
+	R s[3][3];	// pre (c - u).F = s[0][cx+1] + s[1][cy+1] + s[2][cz+1]
 #pragma unroll
 	for (int a = 0; a < 3; a++) {
 		const R kf = pre * F[a];
-		const R mid = (a == 0 ? itau : R(0)) - v[a] * kf;
+		const R mid = -v[a] * kf;
 		s[a][1] = mid;
 		s[a][0] = mid - kf;
 		s[a][2] = mid + kf;
@@ -664,7 +668,11 @@ LBMX_D void srt_update(R (&f)[L::Q], const Phys<R>& P, R rho, R vx, R vy, R vz)
 			else
 				feq = (w * rho) * base;
 		}
-		f[q] = keep * f[q] + feq * ((s[0][cx + 1] + s[1][cy + 1]) + s[2][cz + 1]);
+		const R ps = (s[0][cx + 1] + s[1][cy + 1]) + s[2][cz + 1];
+		if constexpr (sizeof(R) == 8)
+			f[q] = (R(1) - itau) * f[q] + feq * (itau + ps);  // fp64: three roundings at 1e-16 instead of one, 1000 steps stay within 1e-12
+		else
+			f[q] = f[q] + ((feq - f[q]) * itau + ps * feq);
 	});
 }
 
@@ -683,7 +691,7 @@ template <bool GALILEAN = false, typename R>
 LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
-	const R omega1 = P.omega1, keep = R(1) - omega1;
+	const R omega1 = P.omega1;
 	const R irho3 = R(3) / rho;
 	const R pre = (R(1) - R(0.5) * omega1) * irho3;
 	const R v[3] = {vx, vy, vz};
@@ -713,13 +721,13 @@ LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 		g[a][2] = p;
 		g[a][0] = p + v[a];
 	}
-	// f' = (1 - omega) f + feq (omega + pre (c - u).F), the bracket as a sum of three per-axis values (as in srt_update)
+	// pre (c - u).F as a sum of three per-axis values; the update in the reference's incremental form (see srt_update)
 	const R F[3] = {P.fx, P.fy, P.fz};
 	R s[3][3];
 #pragma unroll
 	for (int a = 0; a < 3; a++) {
 		const R kf = pre * F[a];
-		const R mid = (a == 0 ? omega1 : R(0)) - v[a] * kf;
+		const R mid = -v[a] * kf;
 		s[a][1] = mid;
 		s[a][0] = mid - kf;
 		s[a][2] = mid + kf;
@@ -727,7 +735,11 @@ LBMX_D void collide_bgk(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 	static_for<27>([&](auto qc) {
 		constexpr int q = qc;
 		const R feq = ((-rho * g[0][L::cx(q) + 1]) * g[1][L::cy(q) + 1]) * g[2][L::cz(q) + 1];
-		f[q] = keep * f[q] + feq * ((s[0][L::cx(q) + 1] + s[1][L::cy(q) + 1]) + s[2][L::cz(q) + 1]);
+		const R ps = (s[0][L::cx(q) + 1] + s[1][L::cy(q) + 1]) + s[2][L::cz(q) + 1];
+		if constexpr (sizeof(R) == 8)
+			f[q] = (R(1) - omega1) * f[q] + feq * (omega1 + ps);
+		else
+			f[q] = f[q] + ((feq - f[q]) * omega1 + ps * feq);
 	});
 }
 
@@ -788,32 +800,40 @@ LBMX_D void collide_mrt(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
 // d2q9/col_srt.h:16-44 in default arithmetic: f' = f + (feq - f) / tau + F_q with the source term
 //   F_q = (1 - 1/(2 tau)) w_q [3 (c - u).F + 9 (c.u)(c.F)] = (1 - 1/(2 tau)) w_q [(3 c.F)(1 + 3 c.u) - 3 u.F],
 // so with cu3 = 3 c.u shared between the equilibrium polynomial and the source:
-//   f' = (1 - 1/tau) f + w_q [ (rho / tau) (base + cu3 + cu3^2 / 2) + pre ((3 c.F)(1 + cu3) - 3 u.F) ]
+//   f' = f + ( (w_q rho (base + cu3 + cu3^2 / 2) - f) / tau + w_q pre ((3 c.F)(1 + cu3) - 3 u.F) )
 // (the reference divides by 9 and 36 per population and evaluates all nine brackets in full: ~225 fp64 instructions per cell, which is
-// most of the time of a step on an L2-resident lattice -- BASELINE configs[1]; this form takes ~110)
+// most of the time of a step on an L2-resident lattice -- BASELINE configs[1]; this form takes ~130.  Incremental like the reference:
+// see srt_update)
 template <typename R>
 LBMX_D void collide_srt(R (&f)[9], const Phys<R>& P, int, R rho, R vx, R vy, R)
 {
 	using L = D2Q9;
-	const R itau = P.omega1, keep = R(1) - itau;
+	const R itau = P.omega1;
 	const R pre = R(1) - R(0.5) * itau;
 	const R base = R(1) - R(1.5) * (vx * vx + vy * vy);
 	const R u3[2][3] = {{R(-3) * vx, R(0), R(3) * vx}, {R(-3) * vy, R(0), R(3) * vy}};
 	const R gx = (R(3) * pre) * P.fx, gy = (R(3) * pre) * P.fy;	 // pre * 3 F
 	const R g3[2][3] = {{-gx, R(0), gx}, {-gy, R(0), gy}};
 	const R B = vx * gx + vy * gy;	// pre * 3 u.F
-	const R ir = itau * rho;
 	static_for<9>([&](auto qc) {
 		constexpr int q = qc;
 		constexpr int cx = L::cx(q), cy = L::cy(q), n = (cx != 0) + (cy != 0);
 		constexpr R w = n == 0 ? R(4.0 / 9.0) : n == 1 ? R(1.0 / 9.0) : R(1.0 / 36.0);
-		if constexpr (n == 0)
-			f[q] = keep * f[q] + w * (ir * base - B);
+		constexpr bool compact = sizeof(R) == 8;  // fp64: (1 - 1/tau) f + w (...), fp32: the incremental form (see srt_update)
+		if constexpr (n == 0) {
+			if constexpr (compact)
+				f[q] = (R(1) - itau) * f[q] + w * ((itau * rho) * base - B);
+			else
+				f[q] = f[q] + (((w * rho) * base - f[q]) * itau - w * B);
+		}
 		else {
 			const R cu3 = n == 2 ? u3[0][cx + 1] + u3[1][cy + 1] : (cx != 0 ? u3[0][cx + 1] : u3[1][cy + 1]);
 			const R cg = n == 2 ? g3[0][cx + 1] + g3[1][cy + 1] : (cx != 0 ? g3[0][cx + 1] : g3[1][cy + 1]);
 			const R poly = (base + cu3) + (R(0.5) * cu3) * cu3;
-			f[q] = keep * f[q] + w * (ir * poly + (cg * cu3 + (cg - B)));
+			if constexpr (compact)
+				f[q] = (R(1) - itau) * f[q] + w * ((itau * rho) * poly + (cg * cu3 + (cg - B)));
+			else
+				f[q] = f[q] + (((w * rho) * poly - f[q]) * itau + w * (cg * cu3 + (cg - B)));
 		}
 	});
 }

@@ -586,8 +586,8 @@ LBMX_D R rcp_fast(R x)
 // The same eight models in default arithmetic, organised for the fp64 / fp32 pipes instead of the reference's statement order (the form
 // above needs ~1080 floating-point instructions per cell, which bounds the fp64 kernels on the FP64 pipe before HBM does):
 //   * the 13 raw moments come from column sums (z, then y, then x: 72 additions instead of 190);
-//   * pass 1 leaves delta-h in the place of f, so pass 2 is  f' = (1 - beta gamma) dh + (1 - 2 beta) ds + (1 + (1 - beta) S) feq
-//     (the reference's  f - beta (2 ds + gamma dh) + (1 - beta) S feq  with f = dh + ds + feq substituted);
+//   * fp64: pass 1 leaves delta-h in the place of f, so pass 2 is  f' = (1 - beta gamma) dh + (1 - 2 beta) ds + (1 + (1 - beta) S) feq
+//     (the reference's  f - beta (2 ds + gamma dh) + (1 - beta) S feq  with f = dh + ds + feq substituted); fp32 keeps the incremental form;
 //   * feq_q and 1/feq_q are one multiplication each: the (x,y) factor pairs are formed once per three populations;
 //   * (1 - beta) S_q = sx[cx] + sy[cy] + sz[cz] with three values per axis (S is linear in the lattice velocity, col_bgk.h:62-88).
 // Same quantities as collide_kbc<..., EXACT = false>, agreement with the reference to rounding.
@@ -595,6 +595,7 @@ template <bool CENTRAL, bool USE_T, bool USE_Q, bool HW_RCP = true, typename R, 
 LBMX_D void collide_kbc_fast(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 {
 	using L = D3Q27;
+	constexpr bool INCREMENTAL = sizeof(R) == 4;
 	const R one = R(1), two = R(2), three = R(3), six = R(6), half = R(0.5), third = R(1.0 / 3.0);
 	const R v[3] = {vx, vy, vz};
 	R g[3][3];
@@ -714,7 +715,8 @@ LBMX_D void collide_kbc_fast(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 			const R t = dh * (igxy * ig[2][c]);
 			sd = sd + ds * t;
 			hh = hh + dh * t;
-			f[q] = dh;
+			if constexpr (! INCREMENTAL)
+				f[q] = dh;
 		});
 	});
 	const R gamma = (one / beta - (two - one / beta) * sd / hh);
@@ -726,7 +728,9 @@ LBMX_D void collide_kbc_fast(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 	else
 		asm volatile("" : "+f"(T), "+f"(Nxz), "+f"(Nyz), "+f"(Pxy), "+f"(Pxz), "+f"(Pyz), "+f"(rho));
 #endif
-	// ---- pass 2
+	// ---- pass 2.  fp64: the compact form on the stored delta-h.  fp32: the reference's incremental form f - (beta (2 ds + gamma dh) - (1 - beta) S feq)
+	// on the untouched f (delta-h recomputed): one rounding at the magnitude of f per step instead of three -- what 1000-step fp32 runs need to stay
+	// within the reference's own noise (cf. srt_update in collide.cuh); it costs the fp32 kernels ~70 of their ~700 floating-point instructions
 	const R c1 = one - beta * gamma, c2 = one - two * beta;
 	const R ks = three * (one - beta) * irho;
 	const R F[3] = {P.fx, P.fy, P.fz};
@@ -743,12 +747,17 @@ LBMX_D void collide_kbc_fast(R (&f)[27], const PHYS& P, R rho, R vx, R vy, R vz)
 		nrg0[a] = -rho * g[0][a];
 	static_for<9>([&](auto abc) {
 		constexpr int a = abc / 3, b = abc % 3;
-		const R gxy = nrg0[a] * g[1][b], exy = (one + sv[0][a]) + sv[1][b];
+		const R gxy = nrg0[a] * g[1][b], exy = (INCREMENTAL ? sv[0][a] : one + sv[0][a]) + sv[1][b];
 		static_for<3>([&](auto cc) {
 			constexpr int c = cc;
 			constexpr int q = L::find(a - 1, b - 1, c - 1);
 			const R fe = gxy * g[2][c], ds = ds_of(std::integral_constant<int, q>{});
-			f[q] = c1 * f[q] + (c2 * ds + (exy + sv[2][c]) * fe);
+			if constexpr (INCREMENTAL) {
+				const R dh = f[q] - fe - ds;
+				f[q] = f[q] - (((beta * gamma) * dh + (two * beta) * ds) - (exy + sv[2][c]) * fe);
+			}
+			else
+				f[q] = c1 * f[q] + (c2 * ds + (exy + sv[2][c]) * fe);
 		});
 	});
 }

@@ -425,13 +425,18 @@ __device__ __noinline__ void output_macro_at_rest(R* M, const long long S, const
 #ifndef LBMX_COLD_INLINE_ODD_Q27
 	#define LBMX_COLD_INLINE_ODD_Q27 1
 #endif
+// ... in fp64 only: by the end of round 2 the fp32 A-A odd kernel of the D3Q27 cumulant ran at 5.02 TB/s with the cold path in line and at
+// 5.71 TB/s with the call (profiles/kbench_r2_f32_odd_cold_path.txt)
+#ifndef LBMX_COLD_INLINE_ODD_F32
+	#define LBMX_COLD_INLINE_ODD_F32 0
+#endif
 template <typename L, typename R, int MODE>
 constexpr bool bulk_cold_inline()
 {
 #ifdef LBMX_COLD_INLINE_ALL
 	return LBMX_COLD_INLINE_ALL;
 #else
-	return LBMX_COLD_INLINE_ODD_Q27 && MODE == S_AA_ODD && L::Q != 19;
+	return LBMX_COLD_INLINE_ODD_Q27 && MODE == S_AA_ODD && L::Q != 19 && (sizeof(R) == 8 || LBMX_COLD_INLINE_ODD_F32);
 #endif
 }
 
