@@ -488,7 +488,13 @@ template <int KIND, typename R, int MODE, int L_Q = 27>
 constexpr int bulk_minblocks()
 {
 	if (KIND >= K_KBC_N1 && KIND <= K_KBC_C4)
-		return sizeof(R) == 8 ? (MODE == S_AA_ODD ? LBMX_KBC_MINBLOCKS_F64_ODD : LBMX_KBC_MINBLOCKS_F64) : (MODE == S_AB ? LBMX_KBC_MINBLOCKS_F32_AB : LBMX_KBC_MINBLOCKS_F32);
+	{
+		// fp32 A-B, measured model by model (profiles/kbench_r2_kbc_f32_ab_per_model.txt): the models whose shear part includes the trace
+		// (N2, N4, C2, C4) run 11-13 % faster at 96 registers / 5 CTAs, the others (N1, N3, C1, C3) 14 % faster at 128 / 4
+		constexpr bool with_trace = (KIND - K_KBC_N1) % 4 == 1 || (KIND - K_KBC_N1) % 4 == 3;
+		return sizeof(R) == 8 ? (MODE == S_AA_ODD ? LBMX_KBC_MINBLOCKS_F64_ODD : LBMX_KBC_MINBLOCKS_F64)
+							  : (MODE == S_AB && with_trace ? LBMX_KBC_MINBLOCKS_F32_AB : LBMX_KBC_MINBLOCKS_F32);
+	}
 	// (the default-arithmetic cascaded operator is as light as the cumulant one; its parity-arithmetic form keeps 27 moments of each kind live)
 	// (D3Q19 SRT in its default-arithmetic form fits 128 / 96 registers: 4 / 5 CTAs run the chained A-A steps at 6.39 instead of 5.69 TB/s,
 	// profiles/kbench_r2_srt_reorganised.txt; D3Q27 SRT is best at 3)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn an ncu report (scratch, gpurun_out/) into the committed text summary + profiles/traffic.json.
-   python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/ncu_rN_name.txt <cells per launch> "<command line>" """
+   python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/ncu_rN_name.txt <cells per launch> "<command line>" [--update-traffic-json] """
 import csv
 import json
 import os
@@ -30,9 +30,10 @@ for r in rows[2:]:
     dur = float(r[hdr.index('gpu__time_duration.sum')]) * {'ms': 1e-3, 'us': 1e-6, 'ns': 1e-9, 's': 1}[units[hdr.index('gpu__time_duration.sum')]]
     traffic.append(rd + wr)
     lines.append(f"=> DRAM traffic per launch = {(rd + wr) / 1e9:.3f} GB = {(rd + wr) / cells:.1f} B per lattice update (algorithmic minimum 432 B); {(rd + wr) / dur / 1e12:.2f} TB/s under ncu")
-head = f"ncu --set full --clock-control none --import-source on -k regex:k_bulk -s 4 -c 2   (one A-A even + one A-A odd launch)\ncommand: {cmdline}\nreport : {rep} (scratch); selected raw metrics below.  Numbers under ncu are cold-cache, serialised replays.\n"
+head = f"command: {cmdline}\nreport : {rep} (scratch); selected raw metrics below.  Numbers under ncu are cold-cache, serialised replays.\n"
 open(out, 'w').write(head + '\n'.join(lines) + '\n')
 print('\n'.join(lines))
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-json.dump({"dram_bytes_per_update": sum(traffic) / len(traffic) / cells, "measured_at": f"{cells} cells per launch, D3Q27 cumulant fp64 A-A, mean of one even and one odd launch",
+if len(sys.argv) > 5 and sys.argv[5] == "--update-traffic-json":  # only for the capture of the headline kernel: bench.py reads profiles/traffic.json
+    json.dump({"dram_bytes_per_update": sum(traffic) / len(traffic) / cells, "measured_at": f"{cells} cells per launch, D3Q27 cumulant fp64 A-A, mean of one even and one odd launch",
            "source": os.path.relpath(out, root), "streaming": "AA"}, open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)
