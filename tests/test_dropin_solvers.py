@@ -52,6 +52,26 @@ int main() { return NSE::lbmx_macro; }
     assert r.returncode != 0 and "lbmx_macro" in r.stderr
 
 
+@pytest.mark.parametrize("switch,expr,const", [
+    ("", "D3Q27_CUM<TraitsDP>", "LBMX_COLL_CUM"),
+    ("-DUSE_GEIER_CUM_2017", "D3Q27_CUM<TraitsDP>", "LBMX_COLL_CUM_2017"),
+    ("-DUSE_GEIER_CUM_ANTIALIAS", "D3Q27_CUM<TraitsDP>", "LBMX_COLL_CUM_ANTIALIAS"),
+    ("-DUSE_GEIER_CUM_2017 -DUSE_GEIER_CUM_ANTIALIAS", "D3Q27_CUM<TraitsSP>", "LBMX_COLL_CUM_2017_ANTIALIAS"),
+    ("-DUSE_HIGH_PRECISION_RHO", "D3Q27_CUM<TraitsDP>", "LBMX_COLL_CUM_HP_RHO"),
+    ("-DUSE_GALILEAN_CORRECTION", "D3Q27_BGK<TraitsDP>", "LBMX_COLL_BGK_GALILEAN"),
+    ("", "D3Q27_BGK<TraitsSP>", "LBMX_COLL_BGK"),
+])
+def test_the_reference_build_switches_select_kernel_families(switch, expr, const):
+    """defs.h:252-255: a solver compiled with one of the reference's arithmetic switches gets the kernel family that is that build of the
+    operator (the engine has no #ifdef of its own: the switch becomes the collision kind of the lbmx_desc)."""
+    src = f'#include "lbm3d/core.h"\nstatic_assert({expr}::lbmx_coll == {const}, "wrong kernel family");\nint main() {{ return 0; }}\n'
+    with tempfile.TemporaryDirectory() as tmp:
+        f = os.path.join(tmp, "tag.cpp")
+        open(f, "w").write(src)
+        r = subprocess.run(["g++", "-std=c++17", *switch.split(), f"-I{ROOT}/tnl_lbm_b200/host", f"-I{ROOT}/include", "-fsyntax-only", f], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_channel3d_matches_oracle(prec):
