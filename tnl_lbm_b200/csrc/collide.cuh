@@ -838,6 +838,14 @@ LBMX_D void collide_srt(R (&f)[9], const Phys<R>& P, int, R rho, R vx, R vy, R)
 	});
 }
 
+// d2q9/col_clbm.h:13-89 in default arithmetic.  Same quantities as the reference's statements, organised around the six raw moments of
+// order >= 2 (the reference spells every sum out population by population: ~315 floating-point instructions per cell, this form ~170):
+//   m20 = sum cx^2 f, m02, m11, m21 = sum cx^2 cy f, m12, m22   (rho and u are the caller's: imposed on inflow / outflow cells, so no
+//   identity that needs rho = sum f is used -- rho - zp - zm - zz stays what it is).
+// The cascade increments leave through four shared partial sums, and the Premnath-Banerjee source -- the population set with raw
+// moments F . grad_u (u^a v^b), a, b <= 2 -- is separable:  S_ij = Fx a'_i b_j + Fy a_i b'_j  with a = ((u^2-u)/2, 1-u^2, (u^2+u)/2) and
+// a' = (u - 1/2, -2u, u + 1/2) per axis (the inverse raw-moment transform applied to (1, u, u^2) and to its derivative), instead of eight
+// source moments times a 9 x 8 table.  The update stays incremental: f + (cascade + source).
 template <typename R>
 LBMX_D void collide_clbm(R (&f)[9], const Phys<R>& P, R rho, R vx, R vy)
 {
@@ -847,39 +855,42 @@ LBMX_D void collide_clbm(R (&f)[9], const Phys<R>& P, R rho, R vx, R vy)
 	const R zz = f[L::find(0, 0)], pz = f[L::find(1, 0)], mz = f[L::find(-1, 0)], zp = f[L::find(0, 1)], zm = f[L::find(0, -1)];
 	const R pp = f[L::find(1, 1)], mm = f[L::find(-1, -1)], pm = f[L::find(1, -1)], mp = f[L::find(-1, 1)];
 	const R q4t = R(0.25) / tau;
-	const R diag = (pm + mm) + (pp + mp);
-	const R vx2 = vx * vx, vy2 = vy * vy;
-	// cascaded relaxation of the second moments (trace P, normal difference NE, shear V) and the higher central moments
-	const R Pm = R(1.0 / 12.0) * (rho * (vx2 + vy2) - pz - zp - zm - mz - R(2) * (diag - R(1.0 / 3.0) * rho) - (fx * vx + fy * vy));
-	const R NE = q4t * (zp + zm - pz - mz + rho * (vx2 - vy2) - (fx * vx - fy * vy));
-	const R V = q4t * ((pp + mm - mp - pm) - vx * vy * rho + R(0.5) * (fx * vy + fy * vx));
-	const R kxxyy = (pz + pp + mp + pm + mm + mz - vx2 * rho + R(2) * NE + R(6) * Pm) * (zp + pp + mp + zm + pm + mm - vy2 * rho - R(2) * NE + R(6) * Pm);
-	const R UP = -(R(0.25) * (pm + mm - pp - mp - R(2) * vx2 * vy * rho + vy * (rho - zp - zm - zz) + R(0.5) * vx2 * fy + fx * vx * vy)
-				   - vy * R(0.5) * (R(-3) * Pm - NE) + vx * ((pp - mp - pm + mm) * R(0.5) - R(2) * V));
-	const R RIGHT = -(R(0.25) * (mm + mp - pm - pp - R(2) * vy2 * vx * rho + vx * (rho - zz - mz - pz) + R(0.5) * vy2 * fx + fy * vy * vx)
-					  - vx * R(0.5) * (R(-3) * Pm + NE) + vy * ((pp + mm - pm - mp) * R(0.5) - R(2) * V));
+	const R dpos = pp + mm, dneg = pm + mp;			 // diagonal pairs
+	const R cup = pp + mp, cdn = pm + mm;			 // cy = +1 / -1 corners
+	const R crt = pp + pm, clf = mp + mm;			 // cx = +1 / -1 corners
+	const R m22 = dpos + dneg;
+	const R sx = pz + mz, sy = zp + zm;
+	const R m20 = sx + m22, m02 = sy + m22;
+	const R m11 = dpos - dneg, m21 = cup - cdn, m12 = crt - clf;
+	const R vx2 = vx * vx, vy2 = vy * vy, vxy = vx * vy;
+	const R Fv = fx * vx + fy * vy, Fd = fx * vx - fy * vy, Fc = fx * vy + fy * vx;
+	// cascaded relaxation of the second moments (trace Pm, normal difference NE, shear V) and the higher central moments
+	const R Pm = R(1.0 / 12.0) * (((rho * (vx2 + vy2) - (m20 + m02)) + R(2.0 / 3.0) * rho) - Fv);
+	const R NE = q4t * (((m02 - m20) + rho * (vx2 - vy2)) - Fd);
+	const R V = q4t * ((m11 - vxy * rho) + R(0.5) * Fc);
+	const R P6 = R(6) * Pm, N2 = R(2) * NE;
+	const R kxxyy = (((m20 - vx2 * rho) + N2) + P6) * (((m02 - vy2 * rho) - N2) + P6);
+	const R UP = -(R(0.25) * ((((vy * (rho - (sy + zz)) - m21) - R(2) * vx2 * vy * rho) + R(0.5) * vx2 * fy) + fx * vxy) + (vy * R(0.5)) * (R(3) * Pm + NE) + vx * (m11 * R(0.5) - R(2) * V));
+	const R RIGHT = -(R(0.25) * ((((vx * (rho - (sx + zz)) - m12) - R(2) * vy2 * vx * rho) + R(0.5) * vy2 * fx) + fy * vxy) + (vx * R(0.5)) * (R(3) * Pm - NE) + vy * (m11 * R(0.5) - R(2) * V));
 	const R NP = R(0.25)
-			   * (kxxyy - pp - mp - pm - mm - R(8) * Pm + R(2) * (vx * (pp - mp + pm - mm - R(4) * RIGHT) + vy * (pp + mp - pm - mm - R(4) * UP))
-				  + R(4) * vx * vy * (-pp + mp + pm - mm + R(4) * V) + vx2 * (-zp - pp - mp - zm - pm - mm + R(2) * NE - R(6) * Pm)
-				  + vy2 * ((-pz - pp - mp - pm - mm - mz - R(2) * NE - R(6) * Pm) + R(3) * vx2 * rho) - (fx * vx * vy2 + fy * vy * vx2));
-	// Premnath-Banerjee central-moment forcing
-	const R m1 = fx, m2 = fy;
-	const R m3 = R(6) * (fx * vx + fy * vy);
-	const R m4 = R(2) * (fx * vx - fy * vy);
-	const R m5 = fx * vy + fy * vx;
-	const R m6 = (R(2) - R(3) * vx2) * fy - R(6) * fx * vx * vy;
-	const R m7 = (R(2) - R(3) * vy2) * fx - R(6) * fy * vx * vy;
-	const R m8 = R(6) * ((R(3) * vy2 - R(2)) * fx * vx + (R(3) * vx2 - R(2)) * fy * vy);
-	const R i36 = R(1.0 / 36.0);
-	f[L::find(-1, 1)] = (mp + (R(2) * Pm + NP + V - UP + RIGHT)) + (R(-6) * m1 + R(6) * m2 + R(2) * m3 - R(9) * m5 - R(3) * m6 + R(3) * m7 + m8) * i36;
-	f[L::find(-1, 0)] = (mz + (-Pm - R(2) * NP + NE - R(2) * RIGHT)) + (R(-6) * m1 - m3 + R(9) * m4 - R(6) * m7 - R(2) * m8) * i36;
-	f[L::find(-1, -1)] = (mm + (R(2) * Pm + NP - V + UP + RIGHT)) + (R(-6) * m1 - R(6) * m2 + R(2) * m3 + R(9) * m5 + R(3) * m6 + R(3) * m7 + m8) * i36;
-	f[L::find(0, -1)] = (zm + (-Pm - R(2) * NP - NE - R(2) * UP)) + (R(-6) * m2 - m3 - R(9) * m4 - R(6) * m6 - R(2) * m8) * i36;
-	f[L::find(1, -1)] = (pm + (R(2) * Pm + NP + V + UP - RIGHT)) + (R(6) * m1 - R(6) * m2 + R(2) * m3 - R(9) * m5 + R(3) * m6 - R(3) * m7 + m8) * i36;
-	f[L::find(1, 0)] = (pz + (-Pm - R(2) * NP + NE + R(2) * RIGHT)) + (R(6) * m1 - m3 + R(9) * m4 + R(6) * m7 - R(2) * m8) * i36;
-	f[L::find(1, 1)] = (pp + (R(2) * Pm + NP - V - UP - RIGHT)) + (R(6) * m1 + R(6) * m2 + R(2) * m3 + R(9) * m5 - R(3) * m6 - R(3) * m7 + m8) * i36;
-	f[L::find(0, 1)] = (zp + (-Pm - R(2) * NP - NE + R(2) * UP)) + (R(6) * m2 - m3 - R(9) * m4 + R(6) * m6 - R(2) * m8) * i36;
-	f[L::find(0, 0)] = (zz + R(4) * (-Pm + NP)) + (-m3 + m8) * R(1.0 / 9.0);
+			   * ((((kxxyy - m22) - R(8) * Pm) + R(2) * (vx * (m12 - R(4) * RIGHT) + vy * (m21 - R(4) * UP))) + R(4) * vxy * (R(4) * V - m11)
+				  + (vx2 * ((N2 - m02) - P6) + vy2 * (((-m20 - N2) - P6) + R(3) * vx2 * rho)) - vxy * Fc);
+	// source populations, separable
+	const R ax[3] = {R(0.5) * (vx2 - vx), R(1) - vx2, R(0.5) * (vx2 + vx)}, ay[3] = {R(0.5) * (vy2 - vy), R(1) - vy2, R(0.5) * (vy2 + vy)};
+	const R dx[3] = {fx * (vx - R(0.5)), fx * (R(-2) * vx), fx * (vx + R(0.5))}, dy[3] = {fy * (vy - R(0.5)), fy * (R(-2) * vy), fy * (vy + R(0.5))};
+	// cascade increments
+	const R a = R(2) * Pm + NP, b = -Pm - R(2) * NP;
+	const R aV = a + V, amV = a - V, ru = RIGHT - UP, rs = RIGHT + UP;
+	const R bN = b + NE, bmN = b - NE;
+	f[L::find(-1, 1)] = mp + ((aV + ru) + (dx[0] * ay[2] + ax[0] * dy[2]));
+	f[L::find(1, -1)] = pm + ((aV - ru) + (dx[2] * ay[0] + ax[2] * dy[0]));
+	f[L::find(-1, -1)] = mm + ((amV + rs) + (dx[0] * ay[0] + ax[0] * dy[0]));
+	f[L::find(1, 1)] = pp + ((amV - rs) + (dx[2] * ay[2] + ax[2] * dy[2]));
+	f[L::find(-1, 0)] = mz + ((bN - R(2) * RIGHT) + (dx[0] * ay[1] + ax[0] * dy[1]));
+	f[L::find(1, 0)] = pz + ((bN + R(2) * RIGHT) + (dx[2] * ay[1] + ax[2] * dy[1]));
+	f[L::find(0, -1)] = zm + ((bmN - R(2) * UP) + (dx[1] * ay[0] + ax[1] * dy[0]));
+	f[L::find(0, 1)] = zp + ((bmN + R(2) * UP) + (dx[1] * ay[2] + ax[1] * dy[2]));
+	f[L::find(0, 0)] = zz + (R(4) * (NP - Pm) + (dx[1] * ay[1] + ax[1] * dy[1]));
 }
 
 // --------------------------------------------------------------------------------------------------------------------
