@@ -226,6 +226,17 @@ def test_1000_fp32_steps_of_the_reorganised_operators_on_the_host(fast_lib, coll
     assert lc.rel_err(mac[0:1], mac_ref[0:1]) <= (2e-6 if tol <= 1e-5 else 4e-6), "density"
 
 
+@pytest.mark.parametrize("coll", [O.SRT, O.CLBM])
+def test_1000_fp32_steps_of_the_d2q9_operators_on_the_host(fast_lib, coll):
+    """The same long fp32 run for the reorganised D2Q9 operators (both keep the reference's incremental update), on the periodic channel with a body force."""
+    d = O.Desc(lattice=O.D2Q9, coll=coll, eq=O.EQ_STD, streaming=O.AA, precision=O.F32, X=24, Y=16, Z=1)
+    case = gc.Case("long2d", d, O.Params(lbmViscosity=0.02, fx=2e-6, fy=-1e-6), lc.map_periodic, 1000, "smooth")
+    df_ref, mac_ref = gc.run_case(case, "port", nthreads=4)
+    df, mac = gc.run_case(case, "engine_host", fast=True, init_kind="port")
+    assert lc.rel_err_df(df, df_ref, d) <= TOL[O.F32]
+    assert lc.rel_err(mac[0:1], mac_ref[0:1]) <= 2e-6, "density"
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_plane_copy_kernel_on_the_host(strict_lib, dtype):
     """k_copy_planes (the data mover of the halo exchange: self-exchange, and the push into a neighbour's array with its own component
