@@ -210,7 +210,7 @@ def test_1000_steps_of_the_cumulant_kernels_on_the_host(strict_lib, fast_lib, st
         assert lc.rel_err(mac[lo:hi], mac_ref[lo:hi]) <= 1e-12, label
 
 
-@pytest.mark.parametrize("coll,eq,tol", [(O.SRT, O.EQ_STD, 1e-5), (O.BGK, O.EQ_STD, 1e-5), (O.KBC_N4, O.EQ_ENTROPIC, 1e-5), (O.CLBM, O.EQ_STD, 5e-5), (O.CUM_2017_ANTIALIAS, O.EQ_INV_CUM, 5e-5)])
+@pytest.mark.parametrize("coll,eq,tol", [(O.SRT, O.EQ_STD, 1e-5), (O.BGK, O.EQ_STD, 1e-5), (O.KBC_N4, O.EQ_ENTROPIC, 1e-5), (O.SRT_MODIF_FORCE, O.EQ_STD, 1e-5), (O.CLBM, O.EQ_STD, 5e-5), (O.CUM_2017_ANTIALIAS, O.EQ_INV_CUM, 5e-5)])
 def test_1000_fp32_steps_of_the_reorganised_operators_on_the_host(fast_lib, coll, eq, tol):
     """The default-arithmetic operators are reorganised for the GPU's pipes.  In fp32 the *form* of the update matters
     over a long run: an update that rebuilds f from products rounds several times at the magnitude of f per step, the reference's incremental

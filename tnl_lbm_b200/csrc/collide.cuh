@@ -676,6 +676,78 @@ LBMX_D void srt_update(R (&f)[L::Q], const Phys<R>& P, R rho, R vx, R vy, R vz)
 	});
 }
 
+// D3Q27_SRT_MODIF_FORCE in default arithmetic (col_srt_modif_force.h:9-120): SRT with the source term
+//   (1 - 1/(2 tau)) w_q [3 (c - u).F + 9 (c.u)(c.F)]  =  w_q [(cg)(1 + cu3) - B],   cg = (1 - 1/(2 tau)) 3 c.F,  cu3 = 3 c.u,  B = (1 - 1/(2 tau)) 3 u.F
+// (the reference writes the 27 brackets out with three double-precision divisions each).  Same organisation as srt_update: nothing stored
+// per population, cu3 shared with the polynomial equilibrium, fp32 incremental / fp64 compact update.
+template <int EQ, typename R>
+LBMX_D void srt_modif_update(R (&f)[27], const Phys<R>& P, R rho, R vx, R vy, R vz)
+{
+	using L = D3Q27;
+	const R itau = P.omega1;
+	const R pre = R(1) - R(0.5) * itau;
+	const R v[3] = {vx, vy, vz}, F[3] = {P.fx, P.fy, P.fz};
+	R u3[3][3], g3[3][3], g[3][3];
+	R B = R(0);
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		const R gf = (R(3) * pre) * F[a];
+		u3[a][0] = R(-3) * v[a];
+		u3[a][1] = R(0);
+		u3[a][2] = R(3) * v[a];
+		g3[a][0] = -gf;
+		g3[a][1] = R(0);
+		g3[a][2] = gf;
+		B = a == 0 ? v[a] * gf : B + v[a] * gf;
+		if constexpr (EQ == 1) {
+			const R t = R(3) * v[a] * v[a];
+			g[a][1] = t - R(2);
+			g[a][2] = (t + R(3) * v[a]) + R(1);
+			g[a][0] = (t - R(3) * v[a]) + R(1);
+		}
+	}
+	const R base = R(1) - R(1.5) * ((vx * vx + vy * vy) + vz * vz);
+	static_for<27>([&](auto qc) {
+		constexpr int q = qc;
+		constexpr int cx = L::cx(q), cy = L::cy(q), cz = L::cz(q), n = (cx != 0) + (cy != 0) + (cz != 0);
+		constexpr R w = n == 0 ? R(8.0 / 27.0) : n == 1 ? R(2.0 / 27.0) : n == 2 ? R(1.0 / 54.0) : R(1.0 / 216.0);
+		// sums over the components that are not zero, associated (x + y) + z so that pairs are shared between populations
+		R cu3 = R(0), cg = R(0);
+		if constexpr (cx != 0 && cy != 0 && cz != 0) {
+			cu3 = (u3[0][cx + 1] + u3[1][cy + 1]) + u3[2][cz + 1];
+			cg = (g3[0][cx + 1] + g3[1][cy + 1]) + g3[2][cz + 1];
+		}
+		else if constexpr (cx != 0 && cy != 0) {
+			cu3 = u3[0][cx + 1] + u3[1][cy + 1];
+			cg = g3[0][cx + 1] + g3[1][cy + 1];
+		}
+		else if constexpr (cx != 0 && cz != 0) {
+			cu3 = u3[0][cx + 1] + u3[2][cz + 1];
+			cg = g3[0][cx + 1] + g3[2][cz + 1];
+		}
+		else if constexpr (cy != 0 && cz != 0) {
+			cu3 = u3[1][cy + 1] + u3[2][cz + 1];
+			cg = g3[1][cy + 1] + g3[2][cz + 1];
+		}
+		else if constexpr (n == 1) {
+			cu3 = cx != 0 ? u3[0][cx + 1] : (cy != 0 ? u3[1][cy + 1] : u3[2][cz + 1]);
+			cg = cx != 0 ? g3[0][cx + 1] : (cy != 0 ? g3[1][cy + 1] : g3[2][cz + 1]);
+		}
+		const R src = n == 0 ? -(w * B) : w * (cg * cu3 + (cg - B));
+		R feq;
+		if constexpr (EQ == 1) {
+			constexpr R wp = n == 0 ? -R(1.0 / 27.0) : n == 1 ? R(1.0 / 54.0) : n == 2 ? -R(1.0 / 108.0) : R(1.0 / 216.0);
+			feq = (wp * rho) * ((g[0][cx + 1] * g[1][cy + 1]) * g[2][cz + 1]);
+		}
+		else
+			feq = n == 0 ? (w * rho) * base : (w * rho) * ((base + cu3) + (R(0.5) * cu3) * cu3);
+		if constexpr (sizeof(R) == 8)
+			f[q] = (R(1) - itau) * f[q] + (itau * feq + src);
+		else
+			f[q] = f[q] + ((feq - f[q]) * itau + src);
+	});
+}
+
 template <typename R>
 LBMX_D void collide_srt(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy, R vz)
 {
@@ -1049,9 +1121,15 @@ LBMX_D void collide(R (&f)[27], const Phys<R>& P, int eqkind, R rho, R vx, R vy,
 #endif
 	}
 	else if constexpr (KIND == K_SRT_MF) {
-		R feq[27];
-		equilibrium(feq, eqkind, rho, vx, vy, vz);
-		ext::collide_srt_modif<kStrict>(f, feq, P, vx, vy, vz);
+		if constexpr (kStrict) {
+			R feq[27];
+			equilibrium(feq, eqkind, rho, vx, vy, vz);
+			ext::collide_srt_modif<true>(f, feq, P, vx, vy, vz);
+		}
+		else if (eqkind == 1)
+			srt_modif_update<1>(f, P, rho, vx, vy, vz);
+		else
+			srt_modif_update<0>(f, P, rho, vx, vy, vz);
 	}
 	else if constexpr (kStrict) {
 		if constexpr (KIND == K_CUM || KIND == K_CUM_HP_RHO)

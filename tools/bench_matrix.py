@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--round", default="2")
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--only", default="", help="run only the rows whose name contains this string (e.g. 'ext' = the rows added after the first table)")
+    ap.add_argument("--operator", default="", help="run only the rows whose operator name contains this string (e.g. SRT_MODIF)")
     a = ap.parse_args()
     peak = 6446.9
     pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -91,6 +92,8 @@ def main():
         cfgs.append(("D3Q27 ext parity arithmetic", B.D3Q27, B.CUM, B.EQ_INV_CUM, B.F32, st, (384, 384, 384), "periodic", B.MACRO_DEFAULT, B.FLAG_STRICT_ARITH))
     if a.only:
         cfgs = [c for c in cfgs if a.only in c[0]]
+    if a.operator:
+        cfgs = [c for c in cfgs if a.operator in NAMES[c[2]]]
     for name, lat, coll, eq, prec, st, shape, mk, macro, flags in cfgs:
         mlups, gbs, regs, bpu = run(lat, coll, eq, prec, st, shape, a.steps, mk, macro, flags)
         row = f"| {name} | {NAMES[coll]} | {'fp64' if prec == B.F64 else 'fp32'} | {'A-A' if st == B.AA else 'A-B'} | {shape[0]}x{shape[1]}x{shape[2]} | {bpu} | {mlups:,.0f} | {gbs:,.0f} | {gbs / peak * 100:.0f} % | {regs} |"
