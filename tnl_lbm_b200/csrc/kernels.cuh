@@ -611,7 +611,8 @@ __global__ void __launch_bounds__(LBMX_BULK_BLOCK, bulk_minblocks<KIND, R, MODE,
 				vx = vy = vz = R(0);
 			}
 		}
-#ifdef LBMX_EXP_ODD_RECOMPUTE_OFFSETS  // tools/kbench experiment: the store addresses of the A-A odd step are formed again from the six deltas instead of living through the collision
+#ifdef LBMX_EXP_ODD_RECOMPUTE_OFFSETS  // tools/kbench experiment (no gain: ptxas already re-forms them; the barrier only cost registers -- cumulant fp64 odd 118 -> 128, fp32 72 -> 96):
+		// the store addresses of the A-A odd step formed again from the six deltas instead of living through the collision
 		if constexpr (MODE == S_AA_ODD)
 			asm volatile("" : "+r"(d[k].xp), "+r"(d[k].xm), "+r"(d[k].yp), "+r"(d[k].ym), "+r"(d[k].zp), "+r"(d[k].zm), "+r"(c[k]));
 #endif
